@@ -1,0 +1,893 @@
+// tsdf.cu -- hashed-voxel TSDF: reset / alloc / compactify / integrate / de-integrate / GC
+// for sm_100a.  Implements include/bf_tsdf.h (rows a1-a9 of SURVEY.md section 8).
+//
+// Behavioural source (what, not how): FL/DepthSensing/CUDASceneRepHashSDF.cu:27-684,
+// FL/DepthSensing/VoxelUtilHashSDF.h:226-826, FL/DepthSensing/DepthCameraUtil.h:71-144.
+//
+// B200-first design (see DESIGN.md section "TSDF"):
+//  * no __constant__ uploads, no texture binds: parameters travel as __grid_constant__
+//    kernel arguments, images are read through the read-only path;
+//  * allocation is ONE kernel (in-kernel bucket spin locks), not a host retry loop with a
+//    device->host copy per round (reference: CUDASceneRepHashSDF.h:335-348);
+//  * compactify walks a dense slot-indexed side table (16 B per EVER-allocated block) instead
+//    of the whole 4*numBuckets entry table (reference: .cu:324-384), and leaves its count on
+//    the device; the integrate kernel is a persistent grid that reads that count itself;
+//  * the integrate stencil owns 4 consecutive voxels (48 B = three 16-byte vector accesses)
+//    per thread, touches voxel memory only for threads that pass the truncation test, and
+//    is preceded by a conservative per-block depth-range cull;
+//  * garbage collection is a single fused kernel (identify + unlink + heap push + clear).
+//
+// Compiled with -fmad=false so that float results are bit-identical to oracle/tsdf_oracle.c.
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "../../include/bf_tsdf.h"
+#include "bf_common.cuh"
+
+namespace bf {
+
+// ------------------------------------------------------------------------------------------
+// global (per-process) latched state -- the reference keeps the same things in __constant__
+// memory and texture references, which makes its entry points non-re-entrant per device too.
+// ------------------------------------------------------------------------------------------
+static thread_local std::string t_lastError;
+static cudaStream_t g_stream = 0;
+void set_last_error(const char* where, cudaError_t e) {
+    t_lastError = std::string(where) + ": " + cudaGetErrorString(e);
+}
+cudaStream_t stream() { return g_stream; }
+
+static BFHashParams g_hashParams;           // updateConstantHashParams
+static BFDepthCameraParams g_camParams;     // updateConstantDepthCameraParams
+static BFDepthCameraData g_bound = {nullptr, nullptr};   // bindInputDepthColorTextures
+static unsigned g_boundW = 0, g_boundH = 0;
+
+// library-private per-hash scratch ("aux"), keyed by the d_hash pointer
+struct TsdfAux {
+    int4* slotInfo = nullptr;        // [numSDFBlocks] {bx,by,bz, entryIdx} ; entryIdx < 0: slot free
+    unsigned* ctrs = nullptr;        // see CTR_* below
+    unsigned numSlots = 0;
+    unsigned parity = 0;             // which of the two compactify counters is live
+};
+enum { CTR_HIGH_WATER = 0, CTR_COUNT0 = 1, CTR_COUNT1 = 2, CTR_E = 3, CTR_CULLED = 4, CTR_U_LO = 6, CTR_U_HI = 7, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_NUM = 16 };
+
+static std::mutex g_auxMutex;
+static std::map<const void*, TsdfAux> g_aux;
+
+static int get_aux(const BFHashDataStruct* hd, const BFHashParams* hp, TsdfAux** out, bool create, bool adopt = true);
+
+// ------------------------------------------------------------------------------------------
+// device math shared by every kernel (bit-exact mirror of oracle/tsdf_oracle.c)
+// ------------------------------------------------------------------------------------------
+struct F3 { float x, y, z; };
+struct I3 { int x, y, z; };
+
+__device__ __forceinline__ int isign(float v) { return (0.0f < v) - (v < 0.0f); }
+
+// cuda_SimpleMatrixUtil.h:937-944 (affine, implicit w = 1)
+__device__ __forceinline__ F3 xform(const BFFloat4x4& M, F3 v) {
+    F3 r;
+    r.x = M.m[0] * v.x + M.m[1] * v.y + M.m[2] * v.z + M.m[3] * 1.0f;
+    r.y = M.m[4] * v.x + M.m[5] * v.y + M.m[6] * v.z + M.m[7] * 1.0f;
+    r.z = M.m[8] * v.x + M.m[9] * v.y + M.m[10] * v.z + M.m[11] * 1.0f;
+    return r;
+}
+// VoxelUtilHashSDF.h:226-234 (unsigned modulo, see oracle note)
+__device__ __forceinline__ unsigned hash_pos(unsigned numBuckets, I3 p) {
+    unsigned v = ((unsigned)p.x * 73856093u) ^ ((unsigned)p.y * 19349669u) ^ ((unsigned)p.z * 83492791u);
+    return v % numBuckets;
+}
+__device__ __forceinline__ float truncation(const BFHashParams& hp, float z) { return hp.m_truncation + hp.m_truncScale * z; }
+__device__ __forceinline__ I3 world_to_voxel(const BFHashParams& hp, F3 pos) {
+    F3 p = { pos.x / hp.m_virtualVoxelSize, pos.y / hp.m_virtualVoxelSize, pos.z / hp.m_virtualVoxelSize };
+    I3 r = { (int)(p.x + (float)isign(p.x) * 0.5f), (int)(p.y + (float)isign(p.y) * 0.5f), (int)(p.z + (float)isign(p.z) * 0.5f) };
+    return r;
+}
+__device__ __forceinline__ I3 voxel_to_block(I3 v) {
+    if (v.x < 0) v.x -= BF_SDF_BLOCK_SIZE - 1;
+    if (v.y < 0) v.y -= BF_SDF_BLOCK_SIZE - 1;
+    if (v.z < 0) v.z -= BF_SDF_BLOCK_SIZE - 1;
+    I3 r = { v.x / BF_SDF_BLOCK_SIZE, v.y / BF_SDF_BLOCK_SIZE, v.z / BF_SDF_BLOCK_SIZE };
+    return r;
+}
+__device__ __forceinline__ F3 voxel_to_world(const BFHashParams& hp, I3 v) {
+    F3 r = { (float)v.x * hp.m_virtualVoxelSize, (float)v.y * hp.m_virtualVoxelSize, (float)v.z * hp.m_virtualVoxelSize };
+    return r;
+}
+__device__ __forceinline__ F3 block_to_world(const BFHashParams& hp, I3 b) {
+    I3 v = { b.x * BF_SDF_BLOCK_SIZE, b.y * BF_SDF_BLOCK_SIZE, b.z * BF_SDF_BLOCK_SIZE };
+    return voxel_to_world(hp, v);
+}
+__device__ __forceinline__ I3 world_to_block(const BFHashParams& hp, F3 w) { return voxel_to_block(world_to_voxel(hp, w)); }
+
+__device__ __forceinline__ float proj_z(const BFDepthCameraParams& cp, float z) {
+    return (z - cp.m_sensorDepthWorldMin) / (cp.m_sensorDepthWorldMax - cp.m_sensorDepthWorldMin);
+}
+__device__ __forceinline__ F3 depth_to_skeleton(const BFDepthCameraParams& cp, unsigned ux, unsigned uy, float depth) {
+    const float x = ((float)ux - cp.mx) / cp.fx;
+    const float y = ((float)uy - cp.my) / cp.fy;
+    F3 r = { depth * x, depth * y, depth };
+    return r;
+}
+// DepthCameraUtil.h:95-107,137-144 + VoxelUtilHashSDF.h:322-326
+__device__ __forceinline__ bool block_in_frustum(const BFHashParams& hp, const BFDepthCameraParams& cp, I3 b) {
+    F3 w = block_to_world(hp, b);
+    const float off = hp.m_virtualVoxelSize * 0.5f * ((float)BF_SDF_BLOCK_SIZE - 1.0f);
+    w.x += off; w.y += off; w.z += off;
+    F3 pc = xform(hp.m_rigidTransformInverse, w);
+    const float px = pc.x * cp.fx / pc.z + cp.mx;
+    const float py = pc.y * cp.fy / pc.z + cp.my;
+    const float w1 = (float)cp.m_imageWidth - 1.0f, h1 = (float)cp.m_imageHeight - 1.0f;
+    float ix = (2.0f * px - w1) / w1;
+    float iy = (h1 - 2.0f * py) / h1;
+    float iz = proj_z(cp, pc.z);
+    ix *= 0.95f; iy *= 0.95f; iz *= 0.95f;
+    return !(ix < -1.0f || ix > 1.0f || iy < -1.0f || iy > 1.0f || iz < 0.0f || iz > 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------
+// hash table primitives.  Entry = 5 ints (20 B).  Loads on the lock-free fast path may come
+// from L1 (possibly stale => at worst a spurious miss that is re-checked under the lock);
+// loads under a bucket lock use ld.global.cg (L2), stores are followed by __threadfence().
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool entry_matches(const BFHashEntry* e, I3 p) {
+    return e->pos[0] == p.x && e->pos[1] == p.y && e->pos[2] == p.z && e->ptr != BF_FREE_ENTRY;
+}
+__device__ __forceinline__ BFHashEntry load_entry_cg(const BFHashEntry* e) {
+    BFHashEntry r;
+    const int* s = reinterpret_cast<const int*>(e);
+    r.pos[0] = __ldcg(s + 0); r.pos[1] = __ldcg(s + 1); r.pos[2] = __ldcg(s + 2); r.ptr = __ldcg(s + 3);
+    r.offset = (unsigned)__ldcg(s + 4);
+    return r;
+}
+__device__ __forceinline__ bool entry_matches_v(const BFHashEntry& e, I3 p) {
+    return e.pos[0] == p.x && e.pos[1] == p.y && e.pos[2] == p.z && e.ptr != BF_FREE_ENTRY;
+}
+
+// VoxelUtilHashSDF.h:440-485 ; returns entry index or -1.  kCoherent: read through L2.
+template <bool kCoherent>
+__device__ int find_entry(const BFHashEntry* __restrict__ hash, const BFHashParams& hp, I3 p, unsigned h) {
+    const unsigned hpz = h * BF_HASH_BUCKET_SIZE;
+    const unsigned total = BF_HASH_BUCKET_SIZE * hp.m_hashNumBuckets;
+#pragma unroll
+    for (unsigned j = 0; j < BF_HASH_BUCKET_SIZE; ++j) {
+        if (kCoherent) { if (entry_matches_v(load_entry_cg(&hash[hpz + j]), p)) return (int)(hpz + j); }
+        else           { if (entry_matches(&hash[hpz + j], p)) return (int)(hpz + j); }
+    }
+    const unsigned last = hpz + BF_HASH_BUCKET_SIZE - 1;
+    unsigned i = last;
+    for (unsigned it = 0; it < hp.m_hashMaxCollisionLinkedListSize; ++it) {
+        BFHashEntry c = kCoherent ? load_entry_cg(&hash[i]) : hash[i];
+        if (entry_matches_v(c, p)) return (int)i;
+        if (c.offset == 0) break;
+        i = (last + c.offset) % total;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ bool try_lock(int* mutex) { return atomicCAS(mutex, BF_FREE_ENTRY, BF_LOCK_ENTRY) == BF_FREE_ENTRY; }
+__device__ __forceinline__ void unlock(int* mutex) { __threadfence(); atomicExch(mutex, BF_FREE_ENTRY); }
+
+// VoxelUtilHashSDF.h:535-540 consumeHeap, plus an exhaustion guard (the reference has none)
+__device__ __forceinline__ bool heap_pop(unsigned* heap, unsigned* heapCounter, unsigned* slot) {
+    unsigned addr = atomicSub(heapCounter, 1u);
+    if (addr == 0xFFFFFFFFu || addr >= 0x80000000u) { atomicAdd(heapCounter, 1u); return false; }
+    *slot = __ldcg(&heap[addr]);
+    return true;
+}
+
+__device__ __forceinline__ void write_entry(BFHashEntry* e, I3 p, unsigned offset, int ptr) {
+    int* d = reinterpret_cast<int*>(e);
+    __stcg(d + 0, p.x); __stcg(d + 1, p.y); __stcg(d + 2, p.z); __stcg(d + 4, (int)offset);
+    __threadfence();
+    __stcg(d + 3, ptr);       // ptr last: a reader that sees a valid ptr sees a valid pos
+}
+
+// Insert `pos` (VoxelUtilHashSDF.h:549-655 semantics: bucket slot first, else splice into the
+// bucket's overflow list).  Unlike the reference (try-lock, give up, host retries) this spins
+// until the block is present, so one launch reaches the reference's fixed point.
+__device__ void alloc_block(const BFHashDataStruct& hd, const BFHashParams& hp, int4* slotInfo, unsigned* ctrs, I3 pos) {
+    const unsigned h = hash_pos(hp.m_hashNumBuckets, pos);
+    if (find_entry<false>(hd.d_hash, hp, pos, h) >= 0) return;      // fast path, no lock
+
+    const unsigned hpz = h * BF_HASH_BUCKET_SIZE;
+    const unsigned last = hpz + BF_HASH_BUCKET_SIZE - 1;
+    const unsigned total = BF_HASH_BUCKET_SIZE * hp.m_hashNumBuckets;
+    const unsigned maxLoop = hp.m_hashMaxCollisionLinkedListSize;
+    int* mutexH = &hd.d_hashBucketMutex[h];
+
+    bool done = false;
+    unsigned backoff = 32;
+    while (!done) {
+        if (try_lock(mutexH)) {
+            __threadfence();
+            if (find_entry<true>(hd.d_hash, hp, pos, h) >= 0) { unlock(mutexH); return; }
+            // first free slot of the home bucket
+            int firstEmpty = -1;
+#pragma unroll
+            for (unsigned j = 0; j < BF_HASH_BUCKET_SIZE; ++j) {
+                int p = __ldcg(&hd.d_hash[hpz + j].ptr);
+                if (firstEmpty == -1 && p == BF_FREE_ENTRY) firstEmpty = (int)(hpz + j);
+            }
+            if (firstEmpty != -1) {
+                unsigned slot;
+                if (heap_pop(hd.d_heap, hd.d_heapCounter, &slot)) {
+                    slotInfo[slot] = make_int4(pos.x, pos.y, pos.z, firstEmpty);
+                    atomicMax(&ctrs[CTR_HIGH_WATER], slot + 1u);
+                    write_entry(&hd.d_hash[firstEmpty], pos, BF_NO_OFFSET, (int)(slot * BF_SDF_BLOCK_VOXELS));
+                } else {
+                    atomicAdd(&ctrs[CTR_HEAP_FAIL], 1u);
+                }
+                unlock(mutexH);
+                return;
+            }
+            // overflow: probe forward for a free non-bucket-last slot (:614-654)
+            unsigned offset = 0, it = 0;
+            bool retry = false;
+            while (it < maxLoop) {
+                offset++;
+                const unsigned i = (last + offset) % total;
+                if ((offset % BF_HASH_BUCKET_SIZE) == 0) continue;
+                if (__ldcg(&hd.d_hash[i].ptr) == BF_FREE_ENTRY) {
+                    const unsigned h2 = i / BF_HASH_BUCKET_SIZE;
+                    int* mutex2 = &hd.d_hashBucketMutex[h2];
+                    const bool same = (h2 == h);
+                    if (!same && !try_lock(mutex2)) { retry = true; break; }   // avoid lock-order deadlock
+                    __threadfence();
+                    if (__ldcg(&hd.d_hash[i].ptr) == BF_FREE_ENTRY) {
+                        unsigned slot;
+                        if (heap_pop(hd.d_heap, hd.d_heapCounter, &slot)) {
+                            const unsigned lastOffset = (unsigned)__ldcg(reinterpret_cast<const int*>(&hd.d_hash[last]) + 4);
+                            slotInfo[slot] = make_int4(pos.x, pos.y, pos.z, (int)i);
+                            atomicMax(&ctrs[CTR_HIGH_WATER], slot + 1u);
+                            write_entry(&hd.d_hash[i], pos, lastOffset, (int)(slot * BF_SDF_BLOCK_VOXELS));
+                            __threadfence();
+                            __stcg(reinterpret_cast<int*>(&hd.d_hash[last]) + 4, (int)offset);   // publish: head -> new
+                        } else {
+                            atomicAdd(&ctrs[CTR_HEAP_FAIL], 1u);
+                        }
+                        if (!same) unlock(mutex2);
+                        unlock(mutexH);
+                        return;
+                    }
+                    if (!same) unlock(mutex2);
+                    // slot was taken meanwhile: keep probing (does not count as an iteration)
+                    continue;
+                }
+                it++;
+            }
+            unlock(mutexH);
+            if (!retry) return;      // no room within the probe window: block is dropped (as the reference)
+        }
+        __nanosleep(backoff + ((threadIdx.x * 7u) & 63u));     // jitter: break lock-step livelock inside a warp
+        if (backoff < 1024) backoff <<= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+
+// reset (CUDASceneRepHashSDF.cu:27-65): heap = identity stack, voxels = 0, entries = FREE.
+__global__ void reset_kernel(BFHashDataStruct hd, unsigned numSDFBlocks, unsigned numBuckets, int4* slotInfo, unsigned* ctrs) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (tid == 0) hd.d_heapCounter[0] = numSDFBlocks - 1;
+    if (tid < CTR_NUM) ctrs[tid] = 0;
+    for (size_t i = tid; i < numSDFBlocks; i += stride) {
+        hd.d_heap[i] = numSDFBlocks - (unsigned)i - 1;
+        slotInfo[i] = make_int4(0, 0, 0, -1);
+    }
+    // voxels: 12 B each -> clear as 16-byte vectors (the heap is 16-byte aligned, 6144 B per block)
+    uint4* vox = reinterpret_cast<uint4*>(hd.d_SDFBlocks);
+    const size_t nVec = (size_t)numSDFBlocks * (BF_SDF_BLOCK_VOXELS * sizeof(BFVoxel) / 16);
+    for (size_t i = tid; i < nVec; i += stride) vox[i] = make_uint4(0, 0, 0, 0);
+    const size_t nEntries = (size_t)numBuckets * BF_HASH_BUCKET_SIZE;
+    for (size_t i = tid; i < nEntries; i += stride) {
+        BFHashEntry e; e.pos[0] = e.pos[1] = e.pos[2] = 0; e.ptr = BF_FREE_ENTRY; e.offset = 0;
+        hd.d_hash[i] = e;
+        hd.d_hashCompactified[i] = e;
+    }
+    for (size_t i = tid; i < numBuckets; i += stride) hd.d_hashBucketMutex[i] = BF_FREE_ENTRY;
+}
+
+__global__ void reset_mutex_kernel(int* mutex, unsigned numBuckets) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < numBuckets) mutex[i] = BF_FREE_ENTRY;
+}
+
+// allocKernel (CUDASceneRepHashSDF.cu:165-251): one thread per depth pixel, DDA over SDF blocks
+// along the ray segment [d-t, d+t].
+__global__ void __launch_bounds__(256)
+alloc_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
+             const float* __restrict__ depth, int4* slotInfo, unsigned* ctrs) {
+    const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cp.m_imageWidth || y >= cp.m_imageHeight) return;
+
+    const float d = __ldg(&depth[y * cp.m_imageWidth + x]);
+    if (d == -INFINITY || d == 0.0f) return;
+    if (d >= hp.m_maxIntegrationDistance) return;
+    const float t = truncation(hp, d);
+    const float minDepth = fminf(hp.m_maxIntegrationDistance, d - t);
+    const float maxDepth = fminf(hp.m_maxIntegrationDistance, d + t);
+    if (minDepth >= maxDepth) return;
+
+    const F3 rayMin = xform(hp.m_rigidTransform, depth_to_skeleton(cp, x, y, minDepth));
+    const F3 rayMax = xform(hp.m_rigidTransform, depth_to_skeleton(cp, x, y, maxDepth));
+    const F3 dv = { rayMax.x - rayMin.x, rayMax.y - rayMin.y, rayMax.z - rayMin.z };
+    const float inv = 1.0f / sqrtf(dv.x * dv.x + dv.y * dv.y + dv.z * dv.z);
+    const F3 dir = { dv.x * inv, dv.y * inv, dv.z * inv };
+
+    I3 cur = world_to_block(hp, rayMin);
+    const I3 end = world_to_block(hp, rayMax);
+    const F3 step = { (float)isign(dir.x), (float)isign(dir.y), (float)isign(dir.z) };
+    const I3 nb = { cur.x + (int)fminf(fmaxf(step.x, 0.0f), 1.0f), cur.y + (int)fminf(fmaxf(step.y, 0.0f), 1.0f),
+                    cur.z + (int)fminf(fmaxf(step.z, 0.0f), 1.0f) };
+    const F3 bw = block_to_world(hp, nb);
+    const float vs = hp.m_virtualVoxelSize;
+    const float half = 0.5f * vs;
+    const F3 boundary = { bw.x - half, bw.y - half, bw.z - half };
+    F3 tMax = { (boundary.x - rayMin.x) / dir.x, (boundary.y - rayMin.y) / dir.y, (boundary.z - rayMin.z) / dir.z };
+    F3 tDelta = { (step.x * (float)BF_SDF_BLOCK_SIZE * vs) / dir.x, (step.y * (float)BF_SDF_BLOCK_SIZE * vs) / dir.y,
+                  (step.z * (float)BF_SDF_BLOCK_SIZE * vs) / dir.z };
+    const I3 bound = { (int)((float)end.x + step.x), (int)((float)end.y + step.y), (int)((float)end.z + step.z) };
+    if (dir.x == 0.0f) { tMax.x = INFINITY; tDelta.x = INFINITY; }
+    if (boundary.x - rayMin.x == 0.0f) { tMax.x = INFINITY; tDelta.x = INFINITY; }
+    if (dir.y == 0.0f) { tMax.y = INFINITY; tDelta.y = INFINITY; }
+    if (boundary.y - rayMin.y == 0.0f) { tMax.y = INFINITY; tDelta.y = INFINITY; }
+    if (dir.z == 0.0f) { tMax.z = INFINITY; tDelta.z = INFINITY; }
+    if (boundary.z - rayMin.z == 0.0f) { tMax.z = INFINITY; tDelta.z = INFINITY; }
+
+#pragma unroll 1
+    for (unsigned iter = 0; iter < 1024; ++iter) {
+        if (block_in_frustum(hp, cp, cur)) alloc_block(hd, hp, slotInfo, ctrs, cur);
+        if (tMax.x < tMax.y && tMax.x < tMax.z) {
+            cur.x = (int)((float)cur.x + step.x);
+            if (cur.x == bound.x) return;
+            tMax.x += tDelta.x;
+        } else if (tMax.z < tMax.y) {
+            cur.z = (int)((float)cur.z + step.z);
+            if (cur.z == bound.z) return;
+            tMax.z += tDelta.z;
+        } else {
+            cur.y = (int)((float)cur.y + step.y);
+            if (cur.y == bound.y) return;
+            tMax.y += tDelta.y;
+        }
+    }
+}
+
+// compactify: list of allocated AND in-frustum blocks (CUDASceneRepHashSDF.cu:324-366),
+// produced from the dense slot table [0, highWater) instead of the 4*numBuckets entry table.
+// Warp-aggregated append; count accumulates in ctrs[countIdx]; the other parity is zeroed for
+// the next call.
+__global__ void __launch_bounds__(256)
+compactify_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
+                  const int4* __restrict__ slotInfo, unsigned* ctrs, int countIdx, int otherIdx) {
+    const unsigned highWater = ctrs[CTR_HIGH_WATER];
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid == 0) { ctrs[otherIdx] = 0; ctrs[CTR_CULLED] = 0; ctrs[CTR_U_LO] = 0; ctrs[CTR_U_HI] = 0; }
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned lane = threadIdx.x & 31;
+    for (unsigned base = tid - lane; base < highWater; base += stride) {
+        const unsigned slot = base + lane;
+        bool keep = false;
+        int4 info = make_int4(0, 0, 0, -1);
+        if (slot < highWater) {
+            info = __ldcg(&slotInfo[slot]);
+            if (info.w >= 0) { I3 b = { info.x, info.y, info.z }; keep = block_in_frustum(hp, cp, b); }
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        if (ballot) {
+            unsigned warpBase = 0;
+            if (lane == 0) warpBase = atomicAdd(&ctrs[countIdx], __popc(ballot));
+            warpBase = __shfl_sync(0xffffffffu, warpBase, 0);
+            if (keep) {
+                BFHashEntry e;
+                e.pos[0] = info.x; e.pos[1] = info.y; e.pos[2] = info.z;
+                e.ptr = (int)(slot * BF_SDF_BLOCK_VOXELS);
+                e.offset = hd.d_hash[info.w].offset;
+                hd.d_hashCompactified[warpBase + __popc(ballot & ((1u << lane) - 1u))] = e;
+            }
+        }
+    }
+}
+
+// legacy full-table variants (fillDecisionArrayKernel / compactifyHashKernel, .cu:268-320, and a
+// table-scan rebuild of the slot table for hashes populated outside this library)
+__global__ void fill_decision_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= hp.m_hashNumBuckets * BF_HASH_BUCKET_SIZE) return;
+    int dec = 0;
+    const BFHashEntry e = hd.d_hash[idx];
+    if (e.ptr != BF_FREE_ENTRY) { I3 b = { e.pos[0], e.pos[1], e.pos[2] }; if (block_in_frustum(hp, cp, b)) dec = 1; }
+    hd.d_hashDecision[idx] = dec;
+}
+__global__ void compactify_prefix_kernel(BFHashDataStruct hd, unsigned numEntries) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= numEntries) return;
+    if (hd.d_hashDecision[idx] == 1) hd.d_hashCompactified[hd.d_hashDecisionPrefix[idx] - 1] = hd.d_hash[idx];
+}
+__global__ void rebuild_aux_kernel(BFHashDataStruct hd, unsigned numEntries, unsigned numSlots, int4* slotInfo, unsigned* ctrs) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= numEntries) return;
+    const BFHashEntry e = hd.d_hash[idx];
+    if (e.ptr == BF_FREE_ENTRY || e.ptr == BF_LOCK_ENTRY) return;
+    const unsigned slot = (unsigned)e.ptr / BF_SDF_BLOCK_VOXELS;
+    if (e.ptr < 0 || slot >= numSlots) return;
+    slotInfo[slot] = make_int4(e.pos[0], e.pos[1], e.pos[2], (int)idx);
+    atomicMax(&ctrs[CTR_HIGH_WATER], slot + 1u);
+}
+
+// ---- the integrate / de-integrate stencil (CUDASceneRepHashSDF.cu:420-521) --------------
+// 128 threads per SDF block, 4 consecutive voxels (48 B) per thread.  Persistent grid: each CTA
+// walks the compactified list with stride gridDim.x; the list length is read from device memory.
+struct VoxelQuad { uint4 a, b, c; };   // 4 voxels = 12 words: v0{a.x,a.y,a.z} v1{a.w,b.x,b.y} v2{b.z,b.w,c.x} v3{c.y,c.z,c.w}
+
+__device__ __forceinline__ float clamp_color(float v) { return fmaxf(0.0f, fminf(v, 254.5f)); }
+
+template <bool kDeIntegrate>
+__device__ __forceinline__ void update_voxel(const BFHashParams& hp, float sdf, uchar4 cur, unsigned& wSdf, unsigned& wWeight, unsigned& wColor) {
+    const float oldSdf = __uint_as_float(wSdf), oldW = __uint_as_float(wWeight);
+    const float oc[3] = { (float)(wColor & 0xff), (float)((wColor >> 8) & 0xff), (float)((wColor >> 16) & 0xff) };
+    const float cc[3] = { (float)cur.x, (float)cur.y, (float)cur.z };
+    float nSdf, nW;
+    unsigned nColor = 0;
+    if (!kDeIntegrate) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float r = (oldW == 0) ? cc[k] : 0.2f * cc[k] + 0.8f * oc[k];
+            nColor |= ((unsigned)clamp_color(roundf(r)) & 0xffu) << (8 * k);
+        }
+        nColor |= 255u << 24;
+        nSdf = (sdf * 1.0f + oldSdf * oldW) / (1.0f + oldW);
+        nW = fminf((float)hp.m_integrationWeightMax, 1.0f + oldW);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float r = (oc[k] * oldW - cc[k] * 1.0f) / (oldW - 1.0f);
+            nColor |= ((unsigned)clamp_color(roundf(r)) & 0xffu) << (8 * k);
+        }
+        nColor |= 255u << 24;
+        nSdf = (oldSdf * oldW - sdf * 1.0f) / (oldW - 1.0f);
+        nW = fmaxf(0.0f, oldW - 1.0f);
+        if (nW <= 0.001f) { nSdf = 0.0f; nW = 0.0f; nColor = 0; }
+    }
+    wSdf = __float_as_uint(nSdf); wWeight = __float_as_uint(nW); wColor = nColor;
+}
+
+template <bool kDeIntegrate>
+__global__ void __launch_bounds__(128)
+integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
+                 const float* __restrict__ depthImg, const uchar4* __restrict__ colorImg,
+                 const unsigned* __restrict__ countPtr, unsigned countOverride, unsigned* ctrs) {
+    const unsigned count = countPtr ? *countPtr : countOverride;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && countPtr) { hd.d_hashCompactifiedCounter[0] = (int)count; ctrs[CTR_E] = count; }
+    const unsigned t = threadIdx.x;
+    const unsigned W = cp.m_imageWidth, H = cp.m_imageHeight;
+    // local voxel coordinates of this thread's first voxel: i = 4t -> x = (4t)%8, y = (4t%64)/8, z = 4t/64
+    const int lx = (int)((4 * t) & 7), ly = (int)(((4 * t) & 63) >> 3), lz = (int)((4 * t) >> 6);
+    unsigned passed = 0;
+
+    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) {
+        const BFHashEntry* ep = &hd.d_hashCompactified[b];
+        const int bx = __ldg(&ep->pos[0]), by = __ldg(&ep->pos[1]), bz = __ldg(&ep->pos[2]);
+        const unsigned ptr = (unsigned)__ldg(&ep->ptr);
+
+        float sdfv[4];
+        uchar4 colv[4];
+        unsigned mask = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const I3 pi = { bx * BF_SDF_BLOCK_SIZE + lx + k, by * BF_SDF_BLOCK_SIZE + ly, bz * BF_SDF_BLOCK_SIZE + lz };
+            const F3 pf = xform(hp.m_rigidTransformInverse, voxel_to_world(hp, pi));
+            const float sx = pf.x * cp.fx / pf.z + cp.mx;
+            const float sy = pf.y * cp.fy / pf.z + cp.my;
+            const unsigned px = (unsigned)(int)(sx + 0.5f), py = (unsigned)(int)(sy + 0.5f);
+            if (px < W && py < H && colorImg != nullptr) {
+                const float depth = __ldg(&depthImg[py * W + px]);
+                if (depth != -INFINITY && depth < hp.m_maxIntegrationDistance) {
+                    float sdf = depth - pf.z;
+                    const float trunc = truncation(hp, depth);
+                    if (fabsf(sdf) < trunc) {
+                        sdf = (sdf >= 0.0f) ? fminf(trunc, sdf) : fmaxf(-trunc, sdf);
+                        sdfv[k] = sdf;
+                        colv[k] = __ldg(&colorImg[py * W + px]);
+                        mask |= 1u << k;
+                    }
+                }
+            }
+        }
+        if (mask) {
+            uint4* vp = reinterpret_cast<uint4*>(hd.d_SDFBlocks + (size_t)ptr) + 3 * t;   // 48 B per thread, 16-B aligned
+            VoxelQuad q;
+            q.a = vp[0]; q.b = vp[1]; q.c = vp[2];
+            if (mask & 1u) update_voxel<kDeIntegrate>(hp, sdfv[0], colv[0], q.a.x, q.a.y, q.a.z);
+            if (mask & 2u) update_voxel<kDeIntegrate>(hp, sdfv[1], colv[1], q.a.w, q.b.x, q.b.y);
+            if (mask & 4u) update_voxel<kDeIntegrate>(hp, sdfv[2], colv[2], q.b.z, q.b.w, q.c.x);
+            if (mask & 8u) update_voxel<kDeIntegrate>(hp, sdfv[3], colv[3], q.c.y, q.c.z, q.c.w);
+            // write back only the 16-byte pieces that contain an updated voxel
+            // words: v0 = a.xyz | v1 = a.w b.xy | v2 = b.zw c.x | v3 = c.yzw
+            if (mask & 0x3u) vp[0] = q.a;
+            if (mask & 0x6u) vp[1] = q.b;
+            if (mask & 0xCu) vp[2] = q.c;
+            passed += __popc(mask);
+        }
+    }
+    // U statistics: one 64-bit atomic per CTA
+    passed = warp_sum_u(passed);
+    __shared__ unsigned sPassed[4];
+    if ((t & 31) == 0) sPassed[t >> 5] = passed;
+    __syncthreads();
+    if (t == 0) {
+        const unsigned long long tot = (unsigned long long)sPassed[0] + sPassed[1] + sPassed[2] + sPassed[3];
+        if (tot) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot);
+    }
+}
+
+// starveVoxelsKernel (.cu:554-563)
+__global__ void starve_kernel(BFHashDataStruct hd) {
+    const BFHashEntry& e = hd.d_hashCompactified[blockIdx.x];
+    BFVoxel* v = &hd.d_SDFBlocks[(size_t)(unsigned)e.ptr + threadIdx.x];
+    int w = (int)v->weight;
+    w = max(0, w - 1);
+    v->weight = (float)w;
+}
+
+// ---- garbage collection ------------------------------------------------------------------
+// identify (.cu:584-631): d_hashDecision[i] = (uint(max weight of block i) == 0)
+__device__ __forceinline__ unsigned block_max_weight_u(const BFVoxel* base, unsigned t, float* sWarp) {
+    const uint4* vp = reinterpret_cast<const uint4*>(base) + 3 * t;
+    const uint4 a = vp[0], b = vp[1], c = vp[2];
+    float m = fmaxf(fmaxf(__uint_as_float(a.y), __uint_as_float(b.x)), fmaxf(__uint_as_float(b.w), __uint_as_float(c.z)));
+    m = warp_max(m);
+    if ((t & 31) == 0) sWarp[t >> 5] = m;
+    __syncthreads();
+    const float bm = fmaxf(fmaxf(sWarp[0], sWarp[1]), fmaxf(sWarp[2], sWarp[3]));
+    __syncthreads();
+    return (unsigned)bm;        // cvt.rzi.u32.f32: the reference reduces through a uint array (Q13)
+}
+
+__global__ void __launch_bounds__(128)
+gc_identify_kernel(BFHashDataStruct hd, unsigned count) {
+    __shared__ float sWarp[4];
+    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) {
+        const unsigned ptr = (unsigned)hd.d_hashCompactified[b].ptr;
+        const unsigned mw = block_max_weight_u(hd.d_SDFBlocks + (size_t)ptr, threadIdx.x, sWarp);
+        if (threadIdx.x == 0) hd.d_hashDecision[b] = (mw == 0) ? 1 : 0;
+    }
+}
+
+// deleteHashEntryElement (VoxelUtilHashSDF.h:739-826) under the home bucket's spin lock.
+__device__ bool delete_entry(const BFHashDataStruct& hd, const BFHashParams& hp, int4* slotInfo, I3 p) {
+    const unsigned h = hash_pos(hp.m_hashNumBuckets, p);
+    const unsigned hpz = h * BF_HASH_BUCKET_SIZE;
+    const unsigned last = hpz + BF_HASH_BUCKET_SIZE - 1;
+    const unsigned total = BF_HASH_BUCKET_SIZE * hp.m_hashNumBuckets;
+    int* mutexH = &hd.d_hashBucketMutex[h];
+    unsigned backoff = 32;
+    while (!try_lock(mutexH)) { __nanosleep(backoff); if (backoff < 1024) backoff <<= 1; }
+    __threadfence();
+    bool ok = false;
+    BFHashEntry freeE; freeE.pos[0] = freeE.pos[1] = freeE.pos[2] = 0; freeE.ptr = BF_FREE_ENTRY; freeE.offset = 0;
+    for (unsigned j = 0; j < BF_HASH_BUCKET_SIZE && !ok; ++j) {
+        const unsigned i = hpz + j;
+        const BFHashEntry c = load_entry_cg(&hd.d_hash[i]);
+        if (entry_matches_v(c, p)) {
+            const unsigned slot = (unsigned)c.ptr / BF_SDF_BLOCK_VOXELS;
+            const unsigned addr = atomicAdd(hd.d_heapCounter, 1u);            // appendHeap :541-546
+            hd.d_heap[addr + 1] = slot;
+            slotInfo[slot] = make_int4(0, 0, 0, -1);
+            if (c.offset != 0) {
+                const unsigned next = (i + c.offset) % total;
+                const BFHashEntry n = load_entry_cg(&hd.d_hash[next]);
+                hd.d_hash[i] = n;
+                if (n.ptr >= 0) slotInfo[(unsigned)n.ptr / BF_SDF_BLOCK_VOXELS].w = (int)i;   // the moved entry changed index
+                hd.d_hash[next] = freeE;
+            } else {
+                hd.d_hash[i] = freeE;
+            }
+            ok = true;
+        }
+    }
+    if (!ok) {
+        BFHashEntry c = load_entry_cg(&hd.d_hash[last]);
+        unsigned prev = last;
+        unsigned i = (last + c.offset) % total;
+        for (unsigned it = 0; it < hp.m_hashMaxCollisionLinkedListSize; ++it) {
+            c = load_entry_cg(&hd.d_hash[i]);
+            if (entry_matches_v(c, p)) {
+                const unsigned slot = (unsigned)c.ptr / BF_SDF_BLOCK_VOXELS;
+                const unsigned addr = atomicAdd(hd.d_heapCounter, 1u);
+                hd.d_heap[addr + 1] = slot;
+                slotInfo[slot] = make_int4(0, 0, 0, -1);
+                hd.d_hash[i] = freeE;
+                hd.d_hash[prev].offset = c.offset;
+                ok = true;
+                break;
+            }
+            if (c.offset == 0) break;
+            prev = i;
+            i = (last + c.offset) % total;
+        }
+    }
+    unlock(mutexH);
+    return ok;
+}
+
+// free (.cu:648-668) given d_hashDecision
+__global__ void __launch_bounds__(128)
+gc_free_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, unsigned count, int4* slotInfo, unsigned* ctrs) {
+    __shared__ int sOk;
+    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) {
+        if (hd.d_hashDecision[b] == 0) continue;           // uniform per CTA
+        const BFHashEntry e = hd.d_hashCompactified[b];
+        if (threadIdx.x == 0) {
+            I3 p = { e.pos[0], e.pos[1], e.pos[2] };
+            sOk = delete_entry(hd, hp, slotInfo, p) ? 1 : 0;
+            if (sOk) atomicAdd(&ctrs[CTR_FREED], 1u);
+        }
+        __syncthreads();
+        if (sOk) {
+            uint4* vp = reinterpret_cast<uint4*>(hd.d_SDFBlocks + (size_t)(unsigned)e.ptr) + 3 * threadIdx.x;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            vp[0] = z; vp[1] = z; vp[2] = z;
+        }
+        __syncthreads();
+    }
+}
+
+// fused identify + free: what bfTsdfGarbageCollect launches (one pass over the voxels)
+__global__ void __launch_bounds__(128)
+gc_fused_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const unsigned* __restrict__ countPtr, int4* slotInfo, unsigned* ctrs) {
+    __shared__ float sWarp[4];
+    __shared__ int sOk;
+    const unsigned count = *countPtr;
+    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) {
+        const BFHashEntry e = hd.d_hashCompactified[b];
+        const unsigned mw = block_max_weight_u(hd.d_SDFBlocks + (size_t)(unsigned)e.ptr, threadIdx.x, sWarp);
+        if (threadIdx.x == 0) hd.d_hashDecision[b] = (mw == 0) ? 1 : 0;
+        if (mw != 0) continue;                               // uniform per CTA
+        if (threadIdx.x == 0) {
+            I3 p = { e.pos[0], e.pos[1], e.pos[2] };
+            sOk = delete_entry(hd, hp, slotInfo, p) ? 1 : 0;
+            if (sOk) atomicAdd(&ctrs[CTR_FREED], 1u);
+        }
+        __syncthreads();
+        if (sOk) {
+            uint4* vp = reinterpret_cast<uint4*>(hd.d_SDFBlocks + (size_t)(unsigned)e.ptr) + 3 * threadIdx.x;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            vp[0] = z; vp[1] = z; vp[2] = z;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int get_aux(const BFHashDataStruct* hd, const BFHashParams* hp, TsdfAux** out, bool create, bool adopt) {
+    std::lock_guard<std::mutex> lk(g_auxMutex);
+    auto it = g_aux.find(hd->d_hash);
+    if (it != g_aux.end() && (hp == nullptr || it->second.numSlots == hp->m_numSDFBlocks)) { *out = &it->second; return 0; }
+    if (!create || hp == nullptr) { *out = nullptr; return (int)cudaErrorInvalidValue; }
+    if (it != g_aux.end()) { cudaFree(it->second.slotInfo); cudaFree(it->second.ctrs); g_aux.erase(it); }
+    TsdfAux a;
+    a.numSlots = hp->m_numSDFBlocks;
+    BF_CHECK(cudaMalloc(&a.slotInfo, sizeof(int4) * (size_t)a.numSlots));
+    BF_CHECK(cudaMalloc(&a.ctrs, sizeof(unsigned) * CTR_NUM));
+    BF_CHECK(cudaMemsetAsync(a.ctrs, 0, sizeof(unsigned) * CTR_NUM, g_stream));
+    BF_CHECK(cudaMemsetAsync(a.slotInfo, 0xff, sizeof(int4) * (size_t)a.numSlots, g_stream));
+    // adopt whatever the table already holds (a hash populated elsewhere, or a fresh reset)
+    const unsigned numEntries = hp->m_hashNumBuckets * BF_HASH_BUCKET_SIZE;
+    if (adopt) {
+        rebuild_aux_kernel<<<(numEntries + 255) / 256, 256, 0, g_stream>>>(*hd, numEntries, a.numSlots, a.slotInfo, a.ctrs);
+        BF_CHECK(cudaGetLastError());
+    }
+    auto res = g_aux.emplace(hd->d_hash, a);
+    *out = &res.first->second;
+    return 0;
+}
+
+static inline int grid_for(unsigned work, int perSm) {
+    int g = num_sms() * perSm;
+    if (work > 0 && (unsigned)g > work) g = (int)work;
+    return g < 1 ? 1 : g;
+}
+
+static int do_reset(BFHashDataStruct* hd, const BFHashParams* hp) {
+    TsdfAux* aux;
+    { // (re)create aux without the table-adopting scan mattering: reset overwrites everything
+        int rc = get_aux(hd, hp, &aux, true, /*adopt=*/false);
+        if (rc) return rc;
+    }
+    aux->parity = 0;
+    reset_kernel<<<num_sms() * 8, 256, 0, g_stream>>>(*hd, hp->m_numSDFBlocks, hp->m_hashNumBuckets, aux->slotInfo, aux->ctrs);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static int do_alloc(BFHashDataStruct* hd, const BFHashParams* hp, const float* depth, const BFDepthCameraParams* cp, TsdfAux* aux) {
+    dim3 block(32, 8);
+    dim3 grid((cp->m_imageWidth + block.x - 1) / block.x, (cp->m_imageHeight + block.y - 1) / block.y);
+    alloc_kernel<<<grid, block, 0, g_stream>>>(*hd, *hp, *cp, depth, aux->slotInfo, aux->ctrs);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static int do_compactify(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraParams* cp, TsdfAux* aux) {
+    aux->parity ^= 1u;
+    const int countIdx = aux->parity ? CTR_COUNT1 : CTR_COUNT0;
+    const int otherIdx = aux->parity ? CTR_COUNT0 : CTR_COUNT1;
+    compactify_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, *hp, *cp, aux->slotInfo, aux->ctrs, countIdx, otherIdx);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static inline const unsigned* live_count_ptr(const TsdfAux* aux) { return aux->ctrs + (aux->parity ? CTR_COUNT1 : CTR_COUNT0); }
+
+static int do_integrate(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraData* dd, const BFDepthCameraParams* cp,
+                        TsdfAux* aux, bool deIntegrate, const unsigned* countPtr, unsigned countOverride) {
+    const unsigned upper = countPtr ? hp->m_numSDFBlocks : countOverride;
+    if (upper == 0) return 0;
+    const int grid = grid_for(upper, 16);
+    const uchar4* color = reinterpret_cast<const uchar4*>(dd->d_colorData);
+    if (deIntegrate) integrate_kernel<true><<<grid, 128, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs);
+    else             integrate_kernel<false><<<grid, 128, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace bf
+
+using namespace bf;
+
+// ==========================================================================================
+// extension API
+// ==========================================================================================
+BF_API void bfSetStream(void* s) { g_stream = (cudaStream_t)s; }
+BF_API void* bfGetStream(void) { return (void*)g_stream; }
+BF_API const char* bfGetLastErrorString(void) { return t_lastError.c_str(); }
+
+BF_API size_t bfTsdfAuxBytes(const BFHashParams* hp) { return sizeof(int4) * (size_t)hp->m_numSDFBlocks + sizeof(unsigned) * CTR_NUM; }
+
+BF_API int bfTsdfReset(BFHashDataStruct* hd, const BFHashParams* hp) { return do_reset(hd, hp); }
+
+BF_API int bfTsdfIntegrateFrame(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraData* dd,
+                                const BFDepthCameraParams* cp, int deIntegrate) {
+    TsdfAux* aux;
+    int rc = get_aux(hd, hp, &aux, true);
+    if (rc) return rc;
+    if (!deIntegrate) { rc = do_alloc(hd, hp, dd->d_depthData, cp, aux); if (rc) return rc; }
+    rc = do_compactify(hd, hp, cp, aux); if (rc) return rc;
+    return do_integrate(hd, hp, dd, cp, aux, deIntegrate != 0, live_count_ptr(aux), 0);
+}
+
+BF_API int bfTsdfGarbageCollect(BFHashDataStruct* hd, const BFHashParams* hp) {
+    TsdfAux* aux;
+    int rc = get_aux(hd, hp, &aux, true);
+    if (rc) return rc;
+    gc_fused_kernel<<<grid_for(hp->m_numSDFBlocks, 16), 128, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
+
+BF_API int bfTsdfGetHeapFreeCount(const BFHashDataStruct* hd, unsigned int* out) {
+    unsigned c = 0;
+    BF_CHECK(cudaMemcpyAsync(&c, hd->d_heapCounter, sizeof(unsigned), cudaMemcpyDeviceToHost, g_stream));
+    BF_CHECK(cudaStreamSynchronize(g_stream));
+    *out = c + 1;     // CUDASceneRepHashSDF.h:168-172
+    return 0;
+}
+
+BF_API int bfTsdfGetNumOccupiedBlocks(const BFHashDataStruct* hd, unsigned int* out) {
+    int c = 0;
+    BF_CHECK(cudaMemcpyAsync(&c, hd->d_hashCompactifiedCounter, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    BF_CHECK(cudaStreamSynchronize(g_stream));
+    *out = (unsigned)c;
+    return 0;
+}
+
+BF_API int bfTsdfGetLastFrameStats(const BFHashDataStruct* hd, unsigned long long out[4]) {
+    TsdfAux* aux;
+    int rc = get_aux(hd, nullptr, &aux, false);
+    if (rc) return rc;
+    unsigned c[CTR_NUM];
+    BF_CHECK(cudaMemcpyAsync(c, aux->ctrs, sizeof(c), cudaMemcpyDeviceToHost, g_stream));
+    BF_CHECK(cudaStreamSynchronize(g_stream));
+    out[0] = c[CTR_E];
+    out[1] = c[CTR_CULLED];
+    out[2] = ((unsigned long long)c[CTR_U_HI] << 32) | c[CTR_U_LO];
+    out[3] = c[CTR_HIGH_WATER];
+    return 0;
+}
+
+BF_API int bfTsdfReleaseAux(const BFHashDataStruct* hd) {
+    std::lock_guard<std::mutex> lk(g_auxMutex);
+    auto it = g_aux.find(hd->d_hash);
+    if (it == g_aux.end()) return 0;
+    cudaFree(it->second.slotInfo);
+    cudaFree(it->second.ctrs);
+    g_aux.erase(it);
+    return 0;
+}
+
+// ==========================================================================================
+// reference-named stubs
+// ==========================================================================================
+BF_API void updateConstantHashParams(const BFHashParams* hp) { g_hashParams = *hp; }
+BF_API void updateConstantDepthCameraParams(const BFDepthCameraParams* p) { g_camParams = *p; }
+BF_API void bindInputDepthColorTextures(const BFDepthCameraData* dd, unsigned int width, unsigned int height) {
+    g_bound = *dd; g_boundW = width; g_boundH = height;
+}
+
+BF_API void resetCUDA(BFHashDataStruct* hd, const BFHashParams* hp) { BF_SAFE(do_reset(hd, hp)); }
+
+BF_API void resetHashBucketMutexCUDA(BFHashDataStruct* hd, const BFHashParams* hp) {
+    reset_mutex_kernel<<<(hp->m_hashNumBuckets + 255) / 256, 256, 0, g_stream>>>(hd->d_hashBucketMutex, hp->m_hashNumBuckets);
+    BF_SAFE((int)cudaGetLastError());
+}
+
+// The reference's kernels read c_hashParams / c_depthCameraParams and the bound textures, not the
+// stub arguments (which only size the grid): the stubs below do the same with the latched copies.
+BF_API void allocCUDA(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraData* dd, const BFDepthCameraParams* cp, const unsigned int* d_bitMask) {
+    (void)hp; (void)dd;
+    if (d_bitMask != nullptr) { fprintf(stderr, "bundlefusion_b200: allocCUDA: chunk streaming (d_bitMask) is out of scope (disabled in BundleFusion)\n"); exit(-1); }
+    TsdfAux* aux;
+    BF_SAFE(get_aux(hd, &g_hashParams, &aux, true));
+    BFDepthCameraParams cam = g_camParams;
+    cam.m_imageWidth = cp->m_imageWidth; cam.m_imageHeight = cp->m_imageHeight;   // grid follows the argument (.cu:255)
+    BF_SAFE(do_alloc(hd, &g_hashParams, g_bound.d_depthData, &cam, aux));
+}
+
+BF_API void fillDecisionArrayCUDA(BFHashDataStruct* hd, const BFHashParams* hp) {
+    const unsigned n = hp->m_hashNumBuckets * BF_HASH_BUCKET_SIZE;
+    fill_decision_kernel<<<(n + 255) / 256, 256, 0, g_stream>>>(*hd, g_hashParams, g_camParams);
+    BF_SAFE((int)cudaGetLastError());
+}
+BF_API void compactifyHashCUDA(BFHashDataStruct* hd, const BFHashParams* hp) {
+    const unsigned n = hp->m_hashNumBuckets * BF_HASH_BUCKET_SIZE;
+    compactify_prefix_kernel<<<(n + 255) / 256, 256, 0, g_stream>>>(*hd, n);
+    BF_SAFE((int)cudaGetLastError());
+}
+
+BF_API unsigned int compactifyHashAllInOneCUDA(BFHashDataStruct* hd, const BFHashParams* hp) {
+    (void)hp;
+    TsdfAux* aux;
+    BF_SAFE(get_aux(hd, &g_hashParams, &aux, true));
+    BF_SAFE(do_compactify(hd, &g_hashParams, &g_camParams, aux));
+    unsigned res = 0;
+    BF_SAFE((int)cudaMemcpyAsync(&res, live_count_ptr(aux), sizeof(unsigned), cudaMemcpyDeviceToHost, g_stream));
+    BF_SAFE((int)cudaStreamSynchronize(g_stream));
+    BF_SAFE((int)cudaMemcpyAsync(hd->d_hashCompactifiedCounter, &res, sizeof(unsigned), cudaMemcpyHostToDevice, g_stream));
+    return res;
+}
+
+static void integrate_stub(BFHashDataStruct* hd, const BFHashParams* hp, bool de) {
+    TsdfAux* aux;
+    BF_SAFE(get_aux(hd, &g_hashParams, &aux, true));
+    BF_SAFE(do_integrate(hd, &g_hashParams, &g_bound, &g_camParams, aux, de, nullptr, hp->m_numOccupiedBlocks));
+}
+BF_API void integrateDepthMapCUDA(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraData*, const BFDepthCameraParams*) { integrate_stub(hd, hp, false); }
+BF_API void deIntegrateDepthMapCUDA(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraData*, const BFDepthCameraParams*) { integrate_stub(hd, hp, true); }
+
+BF_API void starveVoxelsKernelCUDA(BFHashDataStruct* hd, const BFHashParams* hp) {
+    if (hp->m_numOccupiedBlocks == 0) return;
+    starve_kernel<<<hp->m_numOccupiedBlocks, BF_SDF_BLOCK_VOXELS, 0, g_stream>>>(*hd);
+    BF_SAFE((int)cudaGetLastError());
+}
+
+BF_API void garbageCollectIdentifyCUDA(BFHashDataStruct* hd, const BFHashParams* hp) {
+    if (hp->m_numOccupiedBlocks == 0) return;
+    gc_identify_kernel<<<grid_for(hp->m_numOccupiedBlocks, 16), 128, 0, g_stream>>>(*hd, hp->m_numOccupiedBlocks);
+    BF_SAFE((int)cudaGetLastError());
+}
+BF_API void garbageCollectFreeCUDA(BFHashDataStruct* hd, const BFHashParams* hp) {
+    if (hp->m_numOccupiedBlocks == 0) return;
+    TsdfAux* aux;
+    BF_SAFE(get_aux(hd, &g_hashParams, &aux, true));
+    gc_free_kernel<<<grid_for(hp->m_numOccupiedBlocks, 16), 128, 0, g_stream>>>(*hd, g_hashParams, hp->m_numOccupiedBlocks, aux->slotInfo, aux->ctrs);
+    BF_SAFE((int)cudaGetLastError());
+}

@@ -1,0 +1,210 @@
+/*
+ * bf_tsdf.h -- C-ABI of the hashed-voxel TSDF path.
+ *
+ * Every entry point in the first half of this header carries the NAME and the
+ * machine-level signature of an `extern "C"` launch stub of the reference, so a
+ * FriedLiver build can link this library in place of its own
+ * CUDASceneRepHashSDF.cu / CUDAConstant.cu objects:
+ *
+ *   reference declaration (C++ reference parameter)         here (pointer; same ABI)
+ *   FL/DepthSensing/CUDASceneRepHashSDF.h:15-27             resetCUDA ... garbageCollectFreeCUDA
+ *   FL/DepthSensing/VoxelUtilHashSDF.h:101                  updateConstantHashParams
+ *   FL/DepthSensing/DepthCameraUtil.h:13                    updateConstantDepthCameraParams
+ *
+ * (FL/ = /root/reference/FriedLiver/Source/).  A C++ reference parameter and a
+ * pointer parameter are the same thing at the x86-64 SysV ABI level, which is
+ * why these prototypes can be plain C.
+ *
+ * The POD structs are layout-identical to the reference's (sizes/offsets probed
+ * with nvcc 12.9 + g++ 13 against the reference headers; the `__align__(16)` in
+ * front of `struct HashEntry` / `struct HashParams` is ignored by nvcc/gcc, so
+ * HashEntry is 20 bytes).  Types carry a BF prefix so that
+ * both headers can be visible in one translation unit.
+ *
+ * The second half (bfTsdf*) is the B200-native, sync-free extension the host
+ * mirror class (bundlefusion_b200/host/SceneRepHashSDF.h) drives: one call per
+ * integrate / de-integrate, no device->host copy, no constant upload.
+ *
+ * Ownership: the caller allocates every buffer named in BFHashDataStruct
+ * (FL/DepthSensing/VoxelUtilHashSDF.h:124-149) and passes raw DEVICE pointers.
+ * Depth / colour images are borrowed for the duration of the call.
+ */
+#ifndef BF_TSDF_H
+#define BF_TSDF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_SDF_BLOCK_SIZE 8          /* FL/DepthSensing/VoxelUtilHashSDF.h:40 */
+#define BF_SDF_BLOCK_VOXELS 512
+#define BF_HASH_BUCKET_SIZE 4        /* :41 */
+#define BF_LOCK_ENTRY (-1)           /* :52 */
+#define BF_FREE_ENTRY (-2)           /* :53 */
+#define BF_NO_OFFSET 0               /* :54 */
+
+/* row-major 4x4, m[r*4+c]  (FL/SiftGPU/cuda_SimpleMatrixUtil.h:855; mLib mat4f) */
+typedef struct BFFloat4x4 { float m[16]; } BFFloat4x4;
+
+/* FL/DepthSensing/VoxelUtilHashSDF.h:56-74 : 20 bytes, 4-byte aligned */
+typedef struct BFHashEntry {
+    int32_t  pos[3];   /* SDF-block coordinate (block = 8^3 voxels)            */
+    int32_t  ptr;      /* heapSlot*512 (index of first voxel) or FREE/LOCK     */
+    uint32_t offset;   /* linked-list offset relative to bucket's last slot    */
+} BFHashEntry;
+
+/* FL/DepthSensing/VoxelUtilHashSDF.h:77-98 : 12 bytes */
+typedef struct BFVoxel {
+    float   sdf;
+    float   weight;
+    uint8_t color[4];
+} BFVoxel;
+
+/* FL/DepthSensing/CUDAHashParams.h:10-38 : 224 bytes, 8-byte aligned */
+typedef struct BFHashParams {
+    BFFloat4x4 m_rigidTransform;            /*   0 */
+    BFFloat4x4 m_rigidTransformInverse;     /*  64 */
+    uint32_t m_hashNumBuckets;              /* 128 */
+    uint32_t m_hashBucketSize;
+    uint32_t m_hashMaxCollisionLinkedListSize;
+    uint32_t m_numSDFBlocks;
+    int32_t  m_SDFBlockSize;                /* 144 */
+    float    m_virtualVoxelSize;
+    uint32_t m_numOccupiedBlocks;
+    float    m_maxIntegrationDistance;      /* 156 */
+    float    m_truncScale;
+    float    m_truncation;
+    uint32_t m_integrationWeightSample;
+    uint32_t m_integrationWeightMax;
+    float    m_streamingVoxelExtents[3];    /* 176 */
+    int32_t  m_streamingGridDimensions[3];
+    int32_t  m_streamingMinGridPos[3];
+    uint32_t m_streamingInitialChunkListSize;
+#if defined(__GNUC__) || defined(__CUDACC__)
+    uint32_t m_dummy[2] __attribute__((aligned(8)));   /* 216 (uint2) */
+#else
+    __declspec(align(8)) uint32_t m_dummy[2];
+#endif
+} BFHashParams;
+
+/* FL/DepthSensing/CUDADepthCameraParams.h:7-19 : 32 bytes */
+typedef struct BFDepthCameraParams {
+    float fx, fy, mx, my;
+    uint32_t m_imageWidth, m_imageHeight;
+    float m_sensorDepthWorldMin;   /* "render depth" min, used by the frustum test */
+    float m_sensorDepthWorldMax;
+} BFDepthCameraParams;
+
+/* FL/DepthSensing/DepthCameraUtil.h:17-154 : two device pointers */
+typedef struct BFDepthCameraData {
+    const float*   d_depthData;    /* W*H float, metres, invalid = -inf          */
+    const uint8_t* d_colorData;    /* W*H uchar4 RGBA (may be NULL)              */
+} BFDepthCameraData;
+
+/* FL/DepthSensing/VoxelUtilHashSDF.h:830-840 : 80 bytes */
+typedef struct BFHashDataStruct {
+    uint32_t*    d_heap;                    /* free-slot stack                   */
+    uint32_t*    d_heapCounter;             /* index of the top element          */
+    int32_t*     d_hashDecision;            /* per compactified entry: GC flag   */
+    int32_t*     d_hashDecisionPrefix;      /* scratch (4*buckets ints)          */
+    BFHashEntry* d_hash;                    /* numBuckets*4 entries              */
+    BFHashEntry* d_hashCompactified;        /* in-frustum entries                */
+    int32_t*     d_hashCompactifiedCounter;
+    BFVoxel*     d_SDFBlocks;               /* numSDFBlocks*512 voxels           */
+    int32_t*     d_hashBucketMutex;         /* one int per bucket                */
+    uint8_t      m_bIsOnGPU;                /* bool                              */
+} BFHashDataStruct;
+
+/* ------------------------------------------------------------------------ *
+ *  Part 1: the reference's own launch stubs (drop-in names).               *
+ *  Error behaviour follows cutilSafeCall (cutil_inline_runtime.h:277-285): *
+ *  a CUDA error prints file/line to stderr and terminates with exit(-1).   *
+ * ------------------------------------------------------------------------ */
+
+/* FL/DepthSensing/CUDAConstant.cu:10-20 -- latches the params every later stub uses */
+void updateConstantHashParams(const BFHashParams* hashParams);
+/* FL/DepthSensing/CUDAConstant.cu:23-33 */
+void updateConstantDepthCameraParams(const BFDepthCameraParams* params);
+/* FL/DepthSensing/CUDASceneRepHashSDF.cu:15-25 -- latches depth/colour pointers */
+void bindInputDepthColorTextures(const BFDepthCameraData* depthCameraData,
+                                 unsigned int width, unsigned int height);
+
+/* FL/DepthSensing/CUDASceneRepHashSDF.cu:67-111 */
+void resetCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams);
+/* :113-124 */
+void resetHashBucketMutexCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams);
+/* :253-264 -- one call allocates EVERY block the frame needs (no host retry loop needed;
+ * calling it repeatedly as the reference's host loop does is harmless and idempotent). */
+void allocCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams,
+               const BFDepthCameraData* depthCameraData,
+               const BFDepthCameraParams* depthCameraParams,
+               const unsigned int* d_bitMask);
+/* :284-296, :309-320 -- the (unused by the reference's live path) 3-step compactify */
+void fillDecisionArrayCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams);
+void compactifyHashCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams);
+/* :368-384 -- returns the in-frustum block count (device->host sync, as the reference) */
+unsigned int compactifyHashAllInOneCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams);
+/* :524-536, :538-550 -- grid = hashParams->m_numOccupiedBlocks entries of d_hashCompactified */
+void integrateDepthMapCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams,
+                           const BFDepthCameraData* depthCameraData,
+                           const BFDepthCameraParams* depthCameraParams);
+void deIntegrateDepthMapCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams,
+                             const BFDepthCameraData* depthCameraData,
+                             const BFDepthCameraParams* depthCameraParams);
+/* :565-577 */
+void starveVoxelsKernelCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams);
+/* :633-645, :671-683 */
+void garbageCollectIdentifyCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams);
+void garbageCollectFreeCUDA(BFHashDataStruct* hashData, const BFHashParams* hashParams);
+
+/* ------------------------------------------------------------------------ *
+ *  Part 2: B200-native extension (what the host mirror class calls).       *
+ *  All calls are asynchronous on the stream set by bfSetStream(); they      *
+ *  return 0 or a cudaError_t value and never terminate the process.         *
+ * ------------------------------------------------------------------------ */
+
+/* stream every entry point of this library launches on (default: legacy stream 0) */
+void  bfSetStream(void* cudaStream);
+void* bfGetStream(void);
+/* last error string recorded by a bf* call on this thread ("" if none) */
+const char* bfGetLastErrorString(void);
+
+/* bytes of library-private device scratch bfTsdf* keeps per hash (reported for DESIGN.md) */
+size_t bfTsdfAuxBytes(const BFHashParams* hashParams);
+
+/* FL/DepthSensing/CUDASceneRepHashSDF.h:147-155 (reset) */
+int bfTsdfReset(BFHashDataStruct* hashData, const BFHashParams* hashParams);
+
+/* One whole CUDASceneRepHashSDF::integrate (h:65-83) or ::deIntegrate (h:85-108):
+ * [alloc] -> compactify -> (de)integrate, three launches, zero host syncs.
+ * hashParams carries the pose (m_rigidTransform AND its inverse, as the reference's
+ * setLastRigidTransform computes them on the host, h:128-134).  The in-frustum block
+ * count stays on the device (d_hashCompactifiedCounter); fetch it with
+ * bfTsdfGetNumOccupiedBlocks() only when the host needs it. */
+int bfTsdfIntegrateFrame(BFHashDataStruct* hashData, const BFHashParams* hashParams,
+                         const BFDepthCameraData* depthCameraData,
+                         const BFDepthCameraParams* depthCameraParams,
+                         int deIntegrate);
+
+/* CUDASceneRepHashSDF::garbageCollect (h:110-126) over the last compactified list */
+int bfTsdfGarbageCollect(BFHashDataStruct* hashData, const BFHashParams* hashParams);
+
+/* synchronising getters (h:168-172 getHeapFreeCount; m_numOccupiedBlocks) */
+int bfTsdfGetHeapFreeCount(const BFHashDataStruct* hashData, unsigned int* outCount);
+int bfTsdfGetNumOccupiedBlocks(const BFHashDataStruct* hashData, unsigned int* outCount);
+
+/* counters of the last bfTsdfIntegrateFrame, for the roofline arithmetic
+ * (U = voxels passing the truncation test, E = in-frustum blocks).
+ * out[0]=E, out[1]=blocks surviving the depth-range cull, out[2]=U.  Synchronises. */
+int bfTsdfGetLastFrameStats(const BFHashDataStruct* hashData, unsigned long long out[4]);
+
+/* release the library-private scratch attached to this hash (call before freeing d_hash) */
+int bfTsdfReleaseAux(const BFHashDataStruct* hashData);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BF_TSDF_H */

@@ -1,0 +1,173 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle*.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (bundlefusion_b200/) never imports
+this module.  The struct definitions are shared with the product's ctypes view of include/*.h
+(bundlefusion_b200/_capi.py) because both sides speak the same C-ABI PODs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from bundlefusion_b200._capi import (BF_HASH_BUCKET_SIZE, BF_SDF_BLOCK_VOXELS, BFDepthCameraParams, BFHashDataStruct,
+                                     BFHashParams)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_libs = {}
+
+
+def build() -> None:
+    subprocess.check_call(["make", "-C", _HERE, "--no-print-directory"], stdout=subprocess.DEVNULL)
+
+
+def lib(fast: bool = False) -> C.CDLL:
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    if name in _libs:
+        return _libs[name]
+    path = os.path.join(_HERE, name)
+    if not os.path.exists(path):
+        build()
+    L = C.CDLL(path)
+    P = C.POINTER
+    fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    L.orc_tsdf_reset.argtypes = [P(BFHashDataStruct), P(BFHashParams)]
+    L.orc_tsdf_reset.restype = None
+    L.orc_tsdf_find.argtypes = [P(BFHashDataStruct), P(BFHashParams), C.c_int, C.c_int, C.c_int]
+    L.orc_tsdf_find.restype = C.c_int
+    L.orc_tsdf_alloc.argtypes = [P(BFHashDataStruct), P(BFHashParams), fp, P(BFDepthCameraParams)]
+    L.orc_tsdf_alloc.restype = None
+    L.orc_tsdf_compactify.argtypes = [P(BFHashDataStruct), P(BFHashParams), P(BFDepthCameraParams)]
+    L.orc_tsdf_compactify.restype = C.c_uint
+    L.orc_tsdf_integrate.argtypes = [P(BFHashDataStruct), P(BFHashParams), fp, C.c_void_p, P(BFDepthCameraParams), C.c_uint, C.c_int]
+    L.orc_tsdf_integrate.restype = C.c_ulonglong
+    L.orc_tsdf_garbage_collect.argtypes = [P(BFHashDataStruct), P(BFHashParams), C.c_uint]
+    L.orc_tsdf_garbage_collect.restype = C.c_uint
+    L.orc_tsdf_integrate_dense.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float * 3, P(BFHashParams), fp, C.c_void_p,
+                                           P(BFDepthCameraParams), C.c_int]
+    L.orc_tsdf_integrate_dense.restype = C.c_ulonglong
+    _libs[name] = L
+    return L
+
+
+class OracleSceneRepHashSDF:
+    """The same call surface as bundlefusion_b200.scene_rep.CUDASceneRepHashSDF, on host arrays."""
+
+    def __init__(self, params: BFHashParams, fast: bool = False):
+        self.L = lib(fast)
+        self.hp = BFHashParams()
+        C.memmove(C.byref(self.hp), C.byref(params), C.sizeof(BFHashParams))
+        n_entries = self.hp.m_hashNumBuckets * BF_HASH_BUCKET_SIZE
+        n_blocks = self.hp.m_numSDFBlocks
+        self.heap = np.zeros(n_blocks, np.uint32)
+        self.heap_counter = np.zeros(1, np.uint32)
+        self.hash = np.zeros((n_entries, 5), np.int32)
+        self.decision = np.zeros(n_entries, np.int32)
+        self.prefix = np.zeros(n_entries, np.int32)
+        self.compactified = np.zeros((n_entries, 5), np.int32)
+        self.compactified_counter = np.zeros(1, np.int32)
+        self.voxels = np.zeros((n_blocks, BF_SDF_BLOCK_VOXELS, 3), np.int32)
+        self.mutex = np.zeros(self.hp.m_hashNumBuckets, np.int32)
+        hd = BFHashDataStruct()
+        hd.d_heap = self.heap.ctypes.data
+        hd.d_heapCounter = self.heap_counter.ctypes.data
+        hd.d_hashDecision = self.decision.ctypes.data
+        hd.d_hashDecisionPrefix = self.prefix.ctypes.data
+        hd.d_hash = self.hash.ctypes.data
+        hd.d_hashCompactified = self.compactified.ctypes.data
+        hd.d_hashCompactifiedCounter = self.compactified_counter.ctypes.data
+        hd.d_SDFBlocks = self.voxels.ctypes.data
+        hd.d_hashBucketMutex = self.mutex.ctypes.data
+        hd.m_bIsOnGPU = 0
+        self.hd = hd
+        self.num_occupied = 0
+        self.last_U = 0
+        self.reset()
+
+    def reset(self):
+        self.L.orc_tsdf_reset(C.byref(self.hd), C.byref(self.hp))
+        self.num_occupied = 0
+
+    def _set_pose(self, T):
+        from bundlefusion_b200.scene_rep import set_pose
+        set_pose(self.hp, T)
+
+    def integrate(self, T, depth: np.ndarray, color: np.ndarray | None, cam: BFDepthCameraParams):
+        self._set_pose(T)
+        depth = np.ascontiguousarray(depth, np.float32)
+        self.L.orc_tsdf_alloc(C.byref(self.hd), C.byref(self.hp), depth, C.byref(cam))
+        self.num_occupied = self.L.orc_tsdf_compactify(C.byref(self.hd), C.byref(self.hp), C.byref(cam))
+        cptr = color.ctypes.data if color is not None else None
+        self.last_U = self.L.orc_tsdf_integrate(C.byref(self.hd), C.byref(self.hp), depth, cptr, C.byref(cam), self.num_occupied, 0)
+
+    def deIntegrate(self, T, depth: np.ndarray, color: np.ndarray | None, cam: BFDepthCameraParams):
+        self._set_pose(T)
+        depth = np.ascontiguousarray(depth, np.float32)
+        self.num_occupied = self.L.orc_tsdf_compactify(C.byref(self.hd), C.byref(self.hp), C.byref(cam))
+        cptr = color.ctypes.data if color is not None else None
+        self.last_U = self.L.orc_tsdf_integrate(C.byref(self.hd), C.byref(self.hp), depth, cptr, C.byref(cam), self.num_occupied, 1)
+
+    def garbageCollect(self) -> int:
+        return self.L.orc_tsdf_garbage_collect(C.byref(self.hd), C.byref(self.hp), self.num_occupied)
+
+    def getHeapFreeCount(self) -> int:
+        return (int(self.heap_counter[0]) + 1) & 0xFFFFFFFF
+
+    def download(self) -> dict:
+        return {"hash": self.hash, "compactified": self.compactified, "compactified_count": self.num_occupied,
+                "heap": self.heap, "heap_counter": int(self.heap_counter[0]), "voxels": self.voxels,
+                "decision": self.decision, "mutex": self.mutex}
+
+
+def canonical_blocks(snap: dict):
+    """Sorted (N,3) block coordinates and the matching (N,512,3) voxel words, keyed by world block
+    position -- the parity key SURVEY.md section 7 ("hard parts") prescribes: slot/ptr assignment is
+    race-dependent in the reference, the block SET and per-voxel values are not."""
+    h = snap["hash"]
+    used = h[:, 3] != -2
+    ent = h[used]
+    order = np.lexsort((ent[:, 2], ent[:, 1], ent[:, 0]))
+    ent = ent[order]
+    slots = ent[:, 3] // BF_SDF_BLOCK_VOXELS
+    return ent[:, :3].copy(), snap["voxels"][slots]
+
+
+def check_hash_invariants(snap: dict, hp: BFHashParams) -> None:
+    """CUDASceneRepHashSDF::debugHash (h:179-314): no duplicate blocks, heap and table partition the slots,
+    every chain entry reachable from its home bucket within the list limit, all mutexes released."""
+    h = snap["hash"]
+    n_blocks = hp.m_numSDFBlocks
+    used = np.nonzero(h[:, 3] != -2)[0]
+    assert not np.any(h[:, 3] == -1), "LOCK_ENTRY left in the table"
+    pos = h[used, :3]
+    assert len(np.unique(pos, axis=0)) == len(pos), "duplicate block positions"
+    slots = h[used, 3] // BF_SDF_BLOCK_VOXELS
+    assert np.all(h[used, 3] % BF_SDF_BLOCK_VOXELS == 0)
+    n_free = (snap["heap_counter"] + 1) & 0xFFFFFFFF
+    free = snap["heap"][:n_free].astype(np.int64)
+    assert len(np.unique(free)) == n_free, "duplicate free slots"
+    assert len(np.unique(slots)) == len(slots), "two entries share a slot"
+    assert len(np.intersect1d(free, slots)) == 0, "slot both free and allocated"
+    assert n_free + len(slots) == n_blocks, "slot leaked"
+    assert np.all(snap["mutex"] == -2), "bucket mutex left locked"
+    # reachability
+    total = hp.m_hashNumBuckets * BF_HASH_BUCKET_SIZE
+    p = pos.astype(np.uint32)
+    hv = ((p[:, 0] * np.uint32(73856093)) ^ (p[:, 1] * np.uint32(19349669)) ^ (p[:, 2] * np.uint32(83492791))) % np.uint32(hp.m_hashNumBuckets)
+    for idx, hb in zip(used, hv.astype(np.int64)):
+        if idx // BF_HASH_BUCKET_SIZE == hb:
+            continue
+        last = hb * BF_HASH_BUCKET_SIZE + BF_HASH_BUCKET_SIZE - 1
+        i, found = last, False
+        for _ in range(hp.m_hashMaxCollisionLinkedListSize + 1):
+            off = int(np.uint32(h[i, 4]))
+            if off == 0:
+                break
+            i = (last + off) % total
+            if i == idx:
+                found = True
+                break
+        assert found, f"entry {idx} not reachable from bucket {hb}"

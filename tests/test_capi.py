@@ -1,0 +1,49 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports every symbol the
+headers declare, and the POD layouts match the reference's (sizes probed from the reference headers,
+SURVEY.md section 8a / appendix Q1)."""
+import ctypes as C
+import os
+import re
+
+from bundlefusion_b200 import _capi as capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_pod_layouts():
+    assert C.sizeof(capi.BFHashEntry) == 20          # __align__(16) is ignored by nvcc/gcc (Q1)
+    assert C.sizeof(capi.BFVoxel) == 12
+    assert C.sizeof(capi.BFHashParams) == 224
+    assert capi.BFHashParams.m_hashNumBuckets.offset == 128
+    assert capi.BFHashParams.m_SDFBlockSize.offset == 144
+    assert capi.BFHashParams.m_maxIntegrationDistance.offset == 156
+    assert capi.BFHashParams.m_streamingVoxelExtents.offset == 176
+    assert capi.BFHashParams.m_dummy.offset == 216
+    assert C.sizeof(capi.BFDepthCameraParams) == 32
+    assert C.sizeof(capi.BFDepthCameraData) == 16
+    assert C.sizeof(capi.BFHashDataStruct) == 80
+    assert capi.BFHashDataStruct.d_hash.offset == 32
+    assert capi.BFHashDataStruct.d_hashBucketMutex.offset == 64
+    assert capi.BFHashDataStruct.m_bIsOnGPU.offset == 72
+
+
+def _declared_symbols(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^[A-Za-z_][A-Za-z0-9_ \*]*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", src, flags=re.M)
+    return [n for n in names if n not in ("aligned", "__attribute__", "align")]
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if not header.endswith(".h"):
+            continue
+        names = _declared_symbols(header)
+        assert names, header
+        for n in names:
+            assert hasattr(L, n), f"{header}: {n} not exported"
+
+
+def test_symbol_list_matches_header():
+    assert sorted(set(_declared_symbols("bf_tsdf.h"))) == sorted(set(capi.TSDF_SYMBOLS))
