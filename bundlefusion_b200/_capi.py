@@ -103,6 +103,15 @@ TSDF_SYMBOLS = [
     "bfTsdfReleaseAux",
 ]
 
+HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
+
+
+class BFTsdfOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("frame", C.c_int32), ("pose", C.c_float * 16)]
+
+
+BF_TSDF_OP_INTEGRATE, BF_TSDF_OP_DEINTEGRATE, BF_TSDF_OP_GARBAGE_COLLECT = 0, 1, 2
+
 _lib = None
 
 
@@ -147,6 +156,9 @@ def lib() -> C.CDLL:
     L.bfTsdfGetNumOccupiedBlocks.argtypes = [P(BFHashDataStruct), P(C.c_uint)]
     L.bfTsdfGetLastFrameStats.argtypes = [P(BFHashDataStruct), C.c_ulonglong * 4]
     L.bfTsdfReleaseAux.argtypes = [P(BFHashDataStruct)]
+    L.bfMat4Inverse.argtypes = [P(C.c_float), P(C.c_float)]
+    L.bfMat4Inverse.restype = None
+    L.bfTsdfRunOps.argtypes = [P(BFHashDataStruct), P(BFHashParams), P(BFDepthCameraParams), P(BFTsdfOp), C.c_int, P(vp), P(vp)]
     _lib = L
     return L
 

@@ -47,10 +47,12 @@ static unsigned g_boundW = 0, g_boundH = 0;
 struct TsdfAux {
     int4* slotInfo = nullptr;        // [numSDFBlocks] {bx,by,bz, entryIdx} ; entryIdx < 0: slot free
     unsigned* ctrs = nullptr;        // see CTR_* below
+    int* live = nullptr;             // [numSDFBlocks] number of voxels with weight > 0 in the slot's block
+    bool liveValid = false;          // false once something outside integrate/de-integrate changed weights
     unsigned numSlots = 0;
     unsigned parity = 0;             // which of the two compactify counters is live
 };
-enum { CTR_HIGH_WATER = 0, CTR_COUNT0 = 1, CTR_COUNT1 = 2, CTR_E = 3, CTR_CULLED = 4, CTR_U_LO = 6, CTR_U_HI = 7, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_NUM = 16 };
+enum { CTR_HIGH_WATER = 0, CTR_COUNT0 = 1, CTR_COUNT1 = 2, CTR_E = 3, CTR_CULLED = 4, CTR_U_LO = 6, CTR_U_HI = 7, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROPPED = 10, CTR_NUM = 16 };
 
 static std::mutex g_auxMutex;
 static std::map<const void*, TsdfAux> g_aux;
@@ -258,7 +260,7 @@ __device__ void alloc_block(const BFHashDataStruct& hd, const BFHashParams& hp, 
                 it++;
             }
             unlock(mutexH);
-            if (!retry) return;      // no room within the probe window: block is dropped (as the reference)
+            if (!retry) { atomicAdd(&ctrs[CTR_DROPPED], 1u); return; }   // no room within the probe window: dropped (as the reference)
         }
         __nanosleep(backoff + ((threadIdx.x * 7u) & 63u));     // jitter: break lock-step livelock inside a warp
         if (backoff < 1024) backoff <<= 1;
@@ -270,7 +272,7 @@ __device__ void alloc_block(const BFHashDataStruct& hd, const BFHashParams& hp, 
 // ------------------------------------------------------------------------------------------
 
 // reset (CUDASceneRepHashSDF.cu:27-65): heap = identity stack, voxels = 0, entries = FREE.
-__global__ void reset_kernel(BFHashDataStruct hd, unsigned numSDFBlocks, unsigned numBuckets, int4* slotInfo, unsigned* ctrs) {
+__global__ void reset_kernel(BFHashDataStruct hd, unsigned numSDFBlocks, unsigned numBuckets, int4* slotInfo, unsigned* ctrs, int* live) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     if (tid == 0) hd.d_heapCounter[0] = numSDFBlocks - 1;
@@ -278,6 +280,7 @@ __global__ void reset_kernel(BFHashDataStruct hd, unsigned numSDFBlocks, unsigne
     for (size_t i = tid; i < numSDFBlocks; i += stride) {
         hd.d_heap[i] = numSDFBlocks - (unsigned)i - 1;
         slotInfo[i] = make_int4(0, 0, 0, -1);
+        live[i] = 0;
     }
     // voxels: 12 B each -> clear as 16-byte vectors (the heap is 16-byte aligned, 6144 B per block)
     uint4* vox = reinterpret_cast<uint4*>(hd.d_SDFBlocks);
@@ -299,20 +302,36 @@ __global__ void reset_mutex_kernel(int* mutex, unsigned numBuckets) {
 
 // allocKernel (CUDASceneRepHashSDF.cu:165-251): one thread per depth pixel, DDA over SDF blocks
 // along the ray segment [d-t, d+t].
-__global__ void __launch_bounds__(256)
-alloc_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
-             const float* __restrict__ depth, int4* slotInfo, unsigned* ctrs) {
-    const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= cp.m_imageWidth || y >= cp.m_imageHeight) return;
+//
+// Two phases per 16x16-pixel CTA.  Phase 1 walks every pixel's DDA with NO global-memory access and
+// collects the distinct blocks the tile touches in a shared-memory hash set (a tile touches a few dozen
+// blocks, each 8^3 block spans ~20 px at 2 m, while its 256 pixels take ~3 000 DDA steps).  Phase 2
+// resolves the distinct blocks in parallel, one thread per block: frustum test, table lookup, insert.
+// The dependent chain of table lookups a pixel would otherwise pay once per new block (5 L2 round trips
+// each) collapses to a single round.  The union over pixels -- the set the reference allocates -- is
+// unchanged.
+#define BF_ALLOC_SET 1024      // slots of the per-CTA set (power of two); overflow falls back to direct handling
+__device__ __forceinline__ I3 unpack_block_key(unsigned long long key) {
+    const int lim = 1 << 20;
+    I3 b = { (int)((key >> 42) & 0x1FFFFF) - lim, (int)((key >> 21) & 0x1FFFFF) - lim, (int)(key & 0x1FFFFF) - lim };
+    return b;
+}
 
+struct DDA {                    // state of one pixel's block walk (.cu:189-219)
+    I3 cur, bound;
+    F3 step, tMax, tDelta;
+};
+// returns false when the pixel contributes nothing (.cu:176-187)
+__device__ __forceinline__ bool dda_setup(const BFHashParams& hp, const BFDepthCameraParams& cp, const float* __restrict__ depth,
+                                          unsigned x, unsigned y, DDA& s) {
+    if (!(x < cp.m_imageWidth && y < cp.m_imageHeight)) return false;
     const float d = __ldg(&depth[y * cp.m_imageWidth + x]);
-    if (d == -INFINITY || d == 0.0f) return;
-    if (d >= hp.m_maxIntegrationDistance) return;
+    if (d == -INFINITY || d == 0.0f) return false;
+    if (d >= hp.m_maxIntegrationDistance) return false;
     const float t = truncation(hp, d);
     const float minDepth = fminf(hp.m_maxIntegrationDistance, d - t);
     const float maxDepth = fminf(hp.m_maxIntegrationDistance, d + t);
-    if (minDepth >= maxDepth) return;
+    if (minDepth >= maxDepth) return false;
 
     const F3 rayMin = xform(hp.m_rigidTransform, depth_to_skeleton(cp, x, y, minDepth));
     const F3 rayMax = xform(hp.m_rigidTransform, depth_to_skeleton(cp, x, y, maxDepth));
@@ -320,43 +339,115 @@ alloc_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const
     const float inv = 1.0f / sqrtf(dv.x * dv.x + dv.y * dv.y + dv.z * dv.z);
     const F3 dir = { dv.x * inv, dv.y * inv, dv.z * inv };
 
-    I3 cur = world_to_block(hp, rayMin);
+    s.cur = world_to_block(hp, rayMin);
     const I3 end = world_to_block(hp, rayMax);
-    const F3 step = { (float)isign(dir.x), (float)isign(dir.y), (float)isign(dir.z) };
-    const I3 nb = { cur.x + (int)fminf(fmaxf(step.x, 0.0f), 1.0f), cur.y + (int)fminf(fmaxf(step.y, 0.0f), 1.0f),
-                    cur.z + (int)fminf(fmaxf(step.z, 0.0f), 1.0f) };
+    s.step.x = (float)isign(dir.x); s.step.y = (float)isign(dir.y); s.step.z = (float)isign(dir.z);
+    const I3 nb = { s.cur.x + (int)fminf(fmaxf(s.step.x, 0.0f), 1.0f), s.cur.y + (int)fminf(fmaxf(s.step.y, 0.0f), 1.0f),
+                    s.cur.z + (int)fminf(fmaxf(s.step.z, 0.0f), 1.0f) };
     const F3 bw = block_to_world(hp, nb);
     const float vs = hp.m_virtualVoxelSize;
     const float half = 0.5f * vs;
     const F3 boundary = { bw.x - half, bw.y - half, bw.z - half };
-    F3 tMax = { (boundary.x - rayMin.x) / dir.x, (boundary.y - rayMin.y) / dir.y, (boundary.z - rayMin.z) / dir.z };
-    F3 tDelta = { (step.x * (float)BF_SDF_BLOCK_SIZE * vs) / dir.x, (step.y * (float)BF_SDF_BLOCK_SIZE * vs) / dir.y,
-                  (step.z * (float)BF_SDF_BLOCK_SIZE * vs) / dir.z };
-    const I3 bound = { (int)((float)end.x + step.x), (int)((float)end.y + step.y), (int)((float)end.z + step.z) };
-    if (dir.x == 0.0f) { tMax.x = INFINITY; tDelta.x = INFINITY; }
-    if (boundary.x - rayMin.x == 0.0f) { tMax.x = INFINITY; tDelta.x = INFINITY; }
-    if (dir.y == 0.0f) { tMax.y = INFINITY; tDelta.y = INFINITY; }
-    if (boundary.y - rayMin.y == 0.0f) { tMax.y = INFINITY; tDelta.y = INFINITY; }
-    if (dir.z == 0.0f) { tMax.z = INFINITY; tDelta.z = INFINITY; }
-    if (boundary.z - rayMin.z == 0.0f) { tMax.z = INFINITY; tDelta.z = INFINITY; }
-
+    s.tMax.x = (boundary.x - rayMin.x) / dir.x; s.tMax.y = (boundary.y - rayMin.y) / dir.y; s.tMax.z = (boundary.z - rayMin.z) / dir.z;
+    s.tDelta.x = (s.step.x * (float)BF_SDF_BLOCK_SIZE * vs) / dir.x;
+    s.tDelta.y = (s.step.y * (float)BF_SDF_BLOCK_SIZE * vs) / dir.y;
+    s.tDelta.z = (s.step.z * (float)BF_SDF_BLOCK_SIZE * vs) / dir.z;
+    s.bound.x = (int)((float)end.x + s.step.x); s.bound.y = (int)((float)end.y + s.step.y); s.bound.z = (int)((float)end.z + s.step.z);
+    if (dir.x == 0.0f) { s.tMax.x = INFINITY; s.tDelta.x = INFINITY; }
+    if (boundary.x - rayMin.x == 0.0f) { s.tMax.x = INFINITY; s.tDelta.x = INFINITY; }
+    if (dir.y == 0.0f) { s.tMax.y = INFINITY; s.tDelta.y = INFINITY; }
+    if (boundary.y - rayMin.y == 0.0f) { s.tMax.y = INFINITY; s.tDelta.y = INFINITY; }
+    if (dir.z == 0.0f) { s.tMax.z = INFINITY; s.tDelta.z = INFINITY; }
+    if (boundary.z - rayMin.z == 0.0f) { s.tMax.z = INFINITY; s.tDelta.z = INFINITY; }
+    return true;
+}
+// advance along the axis with the smallest tMax (same tie-breaking as .cu:232-246); returns false at the end of the walk
+__device__ __forceinline__ bool dda_step(DDA& s, int& axis) {
+    const bool sx = (s.tMax.x < s.tMax.y) && (s.tMax.x < s.tMax.z);
+    const bool sz = !sx && (s.tMax.z < s.tMax.y);
+    int v = sx ? s.cur.x : (sz ? s.cur.z : s.cur.y);
+    const float st = sx ? s.step.x : (sz ? s.step.z : s.step.y);
+    const int bd = sx ? s.bound.x : (sz ? s.bound.z : s.bound.y);
+    v = (int)((float)v + st);
+    if (v == bd) return false;
+    if (sx)      { s.cur.x = v; s.tMax.x += s.tDelta.x; axis = 0; }
+    else if (sz) { s.cur.z = v; s.tMax.z += s.tDelta.z; axis = 2; }
+    else         { s.cur.y = v; s.tMax.y += s.tDelta.y; axis = 1; }
+    return true;
+}
+// the reference's single-phase walk: every visited in-frustum block goes straight to the table (rare fallback)
+__device__ __noinline__ void alloc_pixel_direct(const BFHashDataStruct& hd, const BFHashParams& hp, const BFDepthCameraParams& cp,
+                                                const float* __restrict__ depth, unsigned x, unsigned y, int4* slotInfo, unsigned* ctrs) {
+    DDA s;
+    if (!dda_setup(hp, cp, depth, x, y, s)) return;
 #pragma unroll 1
     for (unsigned iter = 0; iter < 1024; ++iter) {
-        if (block_in_frustum(hp, cp, cur)) alloc_block(hd, hp, slotInfo, ctrs, cur);
-        if (tMax.x < tMax.y && tMax.x < tMax.z) {
-            cur.x = (int)((float)cur.x + step.x);
-            if (cur.x == bound.x) return;
-            tMax.x += tDelta.x;
-        } else if (tMax.z < tMax.y) {
-            cur.z = (int)((float)cur.z + step.z);
-            if (cur.z == bound.z) return;
-            tMax.z += tDelta.z;
+        if (block_in_frustum(hp, cp, s.cur)) alloc_block(hd, hp, slotInfo, ctrs, s.cur);
+        int axis;
+        if (!dda_step(s, axis)) return;
+    }
+}
+
+__global__ void __launch_bounds__(256, 8)    // 32 regs: the whole 640x480 frame is resident in one wave
+alloc_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
+             const float* __restrict__ depth, int4* slotInfo, unsigned* ctrs) {
+    __shared__ unsigned long long sSet[BF_ALLOC_SET];
+    const unsigned tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (unsigned i = tid; i < BF_ALLOC_SET; i += 256) sSet[i] = 0ull;
+    __syncthreads();
+    const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
+
+    DDA s;
+    bool needDirect = false;
+    if (dda_setup(hp, cp, depth, x, y, s)) {
+        // Set bookkeeping maintained incrementally along the walk: a 64-bit key with three biased 21-bit fields
+        // and an additive hash (both change by a per-axis constant when the walk steps along that axis).
+        const int lim = 1 << 20;
+        const bool packable = s.cur.x > -lim && s.cur.x < lim && s.cur.y > -lim && s.cur.y < lim && s.cur.z > -lim && s.cur.z < lim &&
+                              s.bound.x > -lim && s.bound.x < lim && s.bound.y > -lim && s.bound.y < lim && s.bound.z > -lim && s.bound.z < lim;
+        if (!packable) {
+            needDirect = true;
         } else {
-            cur.y = (int)((float)cur.y + step.y);
-            if (cur.y == bound.y) return;
-            tMax.y += tDelta.y;
+            const unsigned HA = 0x9E3779B1u, HB = 0x85EBCA77u, HC = 0xC2B2AE3Du;
+            unsigned long long key = (1ull << 63) | ((unsigned long long)(unsigned)(s.cur.x + lim) << 42) |
+                                     ((unsigned long long)(unsigned)(s.cur.y + lim) << 21) | (unsigned long long)(unsigned)(s.cur.z + lim);
+            unsigned h = (unsigned)s.cur.x * HA + (unsigned)s.cur.y * HB + (unsigned)s.cur.z * HC;
+            const int isx = (int)s.step.x, isy = (int)s.step.y, isz = (int)s.step.z;
+            const long long dk[3] = { (long long)isx * (1ll << 42), (long long)isy * (1ll << 21), (long long)isz };
+            const unsigned dh[3] = { (unsigned)isx * HA, (unsigned)isy * HB, (unsigned)isz * HC };
+#pragma unroll 1
+            for (unsigned iter = 0; iter < 1024; ++iter) {
+                // record the block in the CTA's set (linear probing, <= 8 probes)
+                bool recorded = false;
+                unsigned slot = h >> 22;                                    // BF_ALLOC_SET == 1024 slots
+#pragma unroll 1
+                for (int probe = 0; probe < 8; ++probe) {
+                    const unsigned long long seen = sSet[slot];
+                    if (seen == key) { recorded = true; break; }
+                    if (seen == 0ull) {
+                        const unsigned long long prev = atomicCAS(&sSet[slot], 0ull, key);
+                        if (prev == 0ull || prev == key) { recorded = true; break; }
+                    }
+                    slot = (slot + 1) & (BF_ALLOC_SET - 1);
+                }
+                if (!recorded) { needDirect = true; break; }
+                int axis;
+                if (!dda_step(s, axis)) break;
+                key += (unsigned long long)(axis == 0 ? dk[0] : (axis == 2 ? dk[2] : dk[1]));
+                h += (axis == 0 ? dh[0] : (axis == 2 ? dh[2] : dh[1]));
+            }
         }
     }
+    __syncthreads();
+    // phase 2: one thread per distinct block
+    for (unsigned i = tid; i < BF_ALLOC_SET; i += 256) {
+        const unsigned long long key = sSet[i];
+        if (key == 0ull) continue;
+        const I3 b = unpack_block_key(key);
+        if (block_in_frustum(hp, cp, b)) alloc_block(hd, hp, slotInfo, ctrs, b);
+    }
+    if (needDirect) alloc_pixel_direct(hd, hp, cp, depth, x, y, slotInfo, ctrs);   // set overflow / coordinates out of key range
 }
 
 // compactify: list of allocated AND in-frustum blocks (CUDASceneRepHashSDF.cu:324-366),
@@ -429,7 +520,7 @@ struct VoxelQuad { uint4 a, b, c; };   // 4 voxels = 12 words: v0{a.x,a.y,a.z} v
 __device__ __forceinline__ float clamp_color(float v) { return fmaxf(0.0f, fminf(v, 254.5f)); }
 
 template <bool kDeIntegrate>
-__device__ __forceinline__ void update_voxel(const BFHashParams& hp, float sdf, uchar4 cur, unsigned& wSdf, unsigned& wWeight, unsigned& wColor) {
+__device__ __forceinline__ void update_voxel(const BFHashParams& hp, float sdf, uchar4 cur, unsigned& wSdf, unsigned& wWeight, unsigned& wColor, int& liveDelta) {
     const float oldSdf = __uint_as_float(wSdf), oldW = __uint_as_float(wWeight);
     const float oc[3] = { (float)(wColor & 0xff), (float)((wColor >> 8) & 0xff), (float)((wColor >> 16) & 0xff) };
     const float cc[3] = { (float)cur.x, (float)cur.y, (float)cur.z };
@@ -455,6 +546,7 @@ __device__ __forceinline__ void update_voxel(const BFHashParams& hp, float sdf, 
         nW = fmaxf(0.0f, oldW - 1.0f);
         if (nW <= 0.001f) { nSdf = 0.0f; nW = 0.0f; nColor = 0; }
     }
+    liveDelta += (int)(nW > 0.0f) - (int)(oldW > 0.0f);
     wSdf = __float_as_uint(nSdf); wWeight = __float_as_uint(nW); wColor = nColor;
 }
 
@@ -462,7 +554,7 @@ template <bool kDeIntegrate>
 __global__ void __launch_bounds__(128)
 integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
                  const float* __restrict__ depthImg, const uchar4* __restrict__ colorImg,
-                 const unsigned* __restrict__ countPtr, unsigned countOverride, unsigned* ctrs) {
+                 const unsigned* __restrict__ countPtr, unsigned countOverride, unsigned* ctrs, int* __restrict__ live) {
     const unsigned count = countPtr ? *countPtr : countOverride;
     if (blockIdx.x == 0 && threadIdx.x == 0 && countPtr) { hd.d_hashCompactifiedCounter[0] = (int)count; ctrs[CTR_E] = count; }
     const unsigned t = threadIdx.x;
@@ -479,6 +571,7 @@ integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, c
         float sdfv[4];
         uchar4 colv[4];
         unsigned mask = 0;
+        int liveDelta = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const I3 pi = { bx * BF_SDF_BLOCK_SIZE + lx + k, by * BF_SDF_BLOCK_SIZE + ly, bz * BF_SDF_BLOCK_SIZE + lz };
@@ -504,10 +597,10 @@ integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, c
             uint4* vp = reinterpret_cast<uint4*>(hd.d_SDFBlocks + (size_t)ptr) + 3 * t;   // 48 B per thread, 16-B aligned
             VoxelQuad q;
             q.a = vp[0]; q.b = vp[1]; q.c = vp[2];
-            if (mask & 1u) update_voxel<kDeIntegrate>(hp, sdfv[0], colv[0], q.a.x, q.a.y, q.a.z);
-            if (mask & 2u) update_voxel<kDeIntegrate>(hp, sdfv[1], colv[1], q.a.w, q.b.x, q.b.y);
-            if (mask & 4u) update_voxel<kDeIntegrate>(hp, sdfv[2], colv[2], q.b.z, q.b.w, q.c.x);
-            if (mask & 8u) update_voxel<kDeIntegrate>(hp, sdfv[3], colv[3], q.c.y, q.c.z, q.c.w);
+            if (mask & 1u) update_voxel<kDeIntegrate>(hp, sdfv[0], colv[0], q.a.x, q.a.y, q.a.z, liveDelta);
+            if (mask & 2u) update_voxel<kDeIntegrate>(hp, sdfv[1], colv[1], q.a.w, q.b.x, q.b.y, liveDelta);
+            if (mask & 4u) update_voxel<kDeIntegrate>(hp, sdfv[2], colv[2], q.b.z, q.b.w, q.c.x, liveDelta);
+            if (mask & 8u) update_voxel<kDeIntegrate>(hp, sdfv[3], colv[3], q.c.y, q.c.z, q.c.w, liveDelta);
             // write back only the 16-byte pieces that contain an updated voxel
             // words: v0 = a.xyz | v1 = a.w b.xy | v2 = b.zw c.x | v3 = c.yzw
             if (mask & 0x3u) vp[0] = q.a;
@@ -515,12 +608,173 @@ integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, c
             if (mask & 0xCu) vp[2] = q.c;
             passed += __popc(mask);
         }
+        // live-voxel bookkeeping for O(E) garbage collection: one RED per warp, only when a weight crossed zero
+        if (__any_sync(0xffffffffu, liveDelta != 0)) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) liveDelta += __shfl_xor_sync(0xffffffffu, liveDelta, o);
+            if ((t & 31) == 0 && liveDelta != 0) atomicAdd(&live[ptr / BF_SDF_BLOCK_VOXELS], liveDelta);
+        }
     }
     // U statistics: one 64-bit atomic per CTA
     passed = warp_sum_u(passed);
     __shared__ unsigned sPassed[4];
     if ((t & 31) == 0) sPassed[t >> 5] = passed;
     __syncthreads();
+    if (t == 0) {
+        const unsigned long long tot = (unsigned long long)sPassed[0] + sPassed[1] + sPassed[2] + sPassed[3];
+        if (tot) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot);
+    }
+}
+
+// ---- TMA-staged variant of the same stencil -------------------------------------------------------
+// One producer warp streams whole 6144-byte voxel tiles into a 4-deep shared-memory ring with the bulk
+// async-copy engine (cp.async.bulk, mbarrier completion); four consumer warps (128 threads, 4 voxels
+// each) project / gather depth for block k+1 while tile k is in flight, read their 48 bytes from shared
+// memory, and write only the dirty 16-byte pieces back to HBM.  Latency of the entry -> tile dependency
+// is carried by the copy engine instead of by resident warps.
+#define BF_TMA_STAGES 4
+#define BF_TILE_BYTES (BF_SDF_BLOCK_VOXELS * 12)
+
+struct GatherSet {           // what consumer thread t needs to update its 4 voxels of one block
+    float pz[4];             // camera-space z of the voxel centres
+    float depth[4];          // depth at the projected pixel (or -inf)
+    uchar4 col[4];
+    unsigned onscreen;       // bit k: voxel k projects inside the image
+};
+
+__device__ __forceinline__ void gather_block(const BFHashParams& hp, const BFDepthCameraParams& cp, const float* __restrict__ depthImg,
+                                             const uchar4* __restrict__ colorImg, int bx, int by, int bz, int lx, int ly, int lz, GatherSet& g) {
+    const unsigned W = cp.m_imageWidth, H = cp.m_imageHeight;
+    g.onscreen = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const I3 pi = { bx * BF_SDF_BLOCK_SIZE + lx + k, by * BF_SDF_BLOCK_SIZE + ly, bz * BF_SDF_BLOCK_SIZE + lz };
+        const F3 pf = xform(hp.m_rigidTransformInverse, voxel_to_world(hp, pi));
+        const float sx = pf.x * cp.fx / pf.z + cp.mx;
+        const float sy = pf.y * cp.fy / pf.z + cp.my;
+        const unsigned px = (unsigned)(int)(sx + 0.5f), py = (unsigned)(int)(sy + 0.5f);
+        g.pz[k] = pf.z;
+        g.depth[k] = -INFINITY;
+        g.col[k] = make_uchar4(0, 0, 0, 0);
+        if (px < W && py < H) {
+            g.onscreen |= 1u << k;
+            g.depth[k] = __ldg(&depthImg[py * W + px]);
+            g.col[k] = __ldg(&colorImg[py * W + px]);
+        }
+    }
+}
+
+template <bool kDeIntegrate>
+__global__ void __launch_bounds__(160)
+integrate_tma_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
+                     const float* __restrict__ depthImg, const uchar4* __restrict__ colorImg,
+                     const unsigned* __restrict__ countPtr, unsigned countOverride, unsigned* ctrs, int* __restrict__ live) {
+    __shared__ __align__(128) uint4 sTile[BF_TMA_STAGES][BF_TILE_BYTES / 16];
+    __shared__ __align__(8) unsigned long long sFull[BF_TMA_STAGES], sEmpty[BF_TMA_STAGES];
+    __shared__ unsigned sPassed[4];
+
+    const unsigned count = countPtr ? *countPtr : countOverride;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && countPtr) { hd.d_hashCompactifiedCounter[0] = (int)count; ctrs[CTR_E] = count; }
+    const unsigned t = threadIdx.x;
+    const unsigned nLocal = (count > blockIdx.x) ? (count - blockIdx.x - 1) / gridDim.x + 1 : 0;   // blocks this CTA owns
+    if (nLocal == 0 || colorImg == nullptr) return;        // without colour nothing passes (.cu:441-448)
+
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < BF_TMA_STAGES; ++s) { mbar_init(&sFull[s], 1); mbar_init(&sEmpty[s], 4); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const BFHashEntry* __restrict__ list = hd.d_hashCompactified;
+    if (t >= 128) {
+        // ---------------- producer warp ----------------
+        const unsigned lane = t - 128;
+        unsigned ptrBatch = 0;
+        for (unsigned k = 0; k < nLocal; ++k) {
+            if ((k & 31) == 0) {                                // prefetch the next 32 block pointers, one per lane
+                const unsigned kk = k + lane;
+                ptrBatch = (kk < nLocal) ? (unsigned)__ldg(&list[blockIdx.x + (size_t)kk * gridDim.x].ptr) : 0u;
+            }
+            const unsigned ptr = __shfl_sync(0xffffffffu, ptrBatch, k & 31);
+            const unsigned s = k % BF_TMA_STAGES, use = k / BF_TMA_STAGES;
+            if (lane == 0) {
+                if (use > 0) mbar_wait(&sEmpty[s], (use - 1) & 1);
+                mbar_arrive_expect_tx(&sFull[s], BF_TILE_BYTES);
+                bulk_g2s(&sTile[s][0], hd.d_SDFBlocks + (size_t)ptr, BF_TILE_BYTES, &sFull[s]);
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    const int lx = (int)((4 * t) & 7), ly = (int)(((4 * t) & 63) >> 3), lz = (int)((4 * t) >> 6);
+    unsigned passed = 0;
+    auto loadPos = [&](unsigned k, int& x, int& y, int& z, unsigned& p) {
+        const BFHashEntry* e = &list[blockIdx.x + (size_t)k * gridDim.x];
+        x = __ldg(&e->pos[0]); y = __ldg(&e->pos[1]); z = __ldg(&e->pos[2]); p = (unsigned)__ldg(&e->ptr);
+    };
+    int nx = 0, ny = 0, nz = 0; unsigned nptr = 0;              // entry of block k+1
+    unsigned curPtr;
+    GatherSet cur, nxt;
+    {
+        int x0, y0, z0;
+        loadPos(0, x0, y0, z0, curPtr);
+        if (nLocal > 1) loadPos(1, nx, ny, nz, nptr);
+        gather_block(hp, cp, depthImg, colorImg, x0, y0, z0, lx, ly, lz, cur);
+    }
+    for (unsigned k = 0; k < nLocal; ++k) {
+        // (1) start the gathers of block k+1 and the entry load of block k+2
+        int fx = 0, fy = 0, fz = 0; unsigned fptr = 0;
+        const bool haveNext = (k + 1 < nLocal);
+        if (haveNext) gather_block(hp, cp, depthImg, colorImg, nx, ny, nz, lx, ly, lz, nxt);
+        if (k + 2 < nLocal) loadPos(k + 2, fx, fy, fz, fptr);
+
+        // (2) truncation test of block k (gathers issued one iteration ago)
+        float sdfv[4];
+        unsigned mask = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float depth = cur.depth[j];
+            sdfv[j] = 0.0f;
+            if (((cur.onscreen >> j) & 1u) && depth != -INFINITY && depth < hp.m_maxIntegrationDistance) {
+                float sdf = depth - cur.pz[j];
+                const float trunc = truncation(hp, depth);
+                if (fabsf(sdf) < trunc) { sdfv[j] = (sdf >= 0.0f) ? fminf(trunc, sdf) : fmaxf(-trunc, sdf); mask |= 1u << j; }
+            }
+        }
+        // (3) tile k: wait for the bulk copy, pull this thread's 48 bytes, release the stage
+        const unsigned s = k % BF_TMA_STAGES;
+        mbar_wait(&sFull[s], (k / BF_TMA_STAGES) & 1);
+        VoxelQuad q;
+        q.a = sTile[s][3 * t]; q.b = sTile[s][3 * t + 1]; q.c = sTile[s][3 * t + 2];
+        __syncwarp();
+        if ((t & 31) == 0) mbar_arrive(&sEmpty[s]);
+        // (4) update + write back dirty 16-byte pieces
+        int liveDelta = 0;
+        if (mask) {
+            uint4* vp = reinterpret_cast<uint4*>(hd.d_SDFBlocks + (size_t)curPtr) + 3 * t;
+            if (mask & 1u) update_voxel<kDeIntegrate>(hp, sdfv[0], cur.col[0], q.a.x, q.a.y, q.a.z, liveDelta);
+            if (mask & 2u) update_voxel<kDeIntegrate>(hp, sdfv[1], cur.col[1], q.a.w, q.b.x, q.b.y, liveDelta);
+            if (mask & 4u) update_voxel<kDeIntegrate>(hp, sdfv[2], cur.col[2], q.b.z, q.b.w, q.c.x, liveDelta);
+            if (mask & 8u) update_voxel<kDeIntegrate>(hp, sdfv[3], cur.col[3], q.c.y, q.c.z, q.c.w, liveDelta);
+            if (mask & 0x3u) vp[0] = q.a;
+            if (mask & 0x6u) vp[1] = q.b;
+            if (mask & 0xCu) vp[2] = q.c;
+            passed += __popc(mask);
+        }
+        if (__any_sync(0xffffffffu, liveDelta != 0)) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) liveDelta += __shfl_xor_sync(0xffffffffu, liveDelta, o);
+            if ((t & 31) == 0 && liveDelta != 0) atomicAdd(&live[curPtr / BF_SDF_BLOCK_VOXELS], liveDelta);
+        }
+        cur = nxt; curPtr = nptr;
+        nx = fx; ny = fy; nz = fz; nptr = fptr;
+    }
+    passed = warp_sum_u(passed);
+    if ((t & 31) == 0) sPassed[t >> 5] = passed;
+    asm volatile("bar.sync 1, 128;" ::: "memory");          // consumers only (the producer warp has left)
     if (t == 0) {
         const unsigned long long tot = (unsigned long long)sPassed[0] + sPassed[1] + sPassed[2] + sPassed[3];
         if (tot) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot);
@@ -665,6 +919,24 @@ gc_fused_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, co
     }
 }
 
+// O(E) garbage collection from the live-voxel counters the integrate kernels maintain: a block is garbage iff
+// no voxel has weight > 0 (weights are whole numbers, so this equals the reference's uint(max weight) == 0).
+// Freed blocks are already all-zero (de-integration clears a voxel when its weight reaches 0, .cu:509-513).
+__global__ void __launch_bounds__(256)
+gc_live_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const unsigned* __restrict__ countPtr,
+               int4* slotInfo, unsigned* ctrs, const int* __restrict__ live) {
+    const unsigned count = *countPtr;
+    for (unsigned b = blockIdx.x * blockDim.x + threadIdx.x; b < count; b += gridDim.x * blockDim.x) {
+        const BFHashEntry e = hd.d_hashCompactified[b];
+        const int dead = (__ldcg(&live[(unsigned)e.ptr / BF_SDF_BLOCK_VOXELS]) <= 0) ? 1 : 0;
+        hd.d_hashDecision[b] = dead;
+        if (dead) {
+            I3 p = { e.pos[0], e.pos[1], e.pos[2] };
+            if (delete_entry(hd, hp, slotInfo, p)) atomicAdd(&ctrs[CTR_FREED], 1u);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -673,11 +945,14 @@ static int get_aux(const BFHashDataStruct* hd, const BFHashParams* hp, TsdfAux**
     auto it = g_aux.find(hd->d_hash);
     if (it != g_aux.end() && (hp == nullptr || it->second.numSlots == hp->m_numSDFBlocks)) { *out = &it->second; return 0; }
     if (!create || hp == nullptr) { *out = nullptr; return (int)cudaErrorInvalidValue; }
-    if (it != g_aux.end()) { cudaFree(it->second.slotInfo); cudaFree(it->second.ctrs); g_aux.erase(it); }
+    if (it != g_aux.end()) { cudaFree(it->second.slotInfo); cudaFree(it->second.ctrs); cudaFree(it->second.live); g_aux.erase(it); }
     TsdfAux a;
     a.numSlots = hp->m_numSDFBlocks;
     BF_CHECK(cudaMalloc(&a.slotInfo, sizeof(int4) * (size_t)a.numSlots));
     BF_CHECK(cudaMalloc(&a.ctrs, sizeof(unsigned) * CTR_NUM));
+    BF_CHECK(cudaMalloc(&a.live, sizeof(int) * (size_t)a.numSlots));
+    BF_CHECK(cudaMemsetAsync(a.live, 0, sizeof(int) * (size_t)a.numSlots, g_stream));
+    a.liveValid = !adopt;           // an adopted table has unknown weights: fall back to the scanning GC
     BF_CHECK(cudaMemsetAsync(a.ctrs, 0, sizeof(unsigned) * CTR_NUM, g_stream));
     BF_CHECK(cudaMemsetAsync(a.slotInfo, 0xff, sizeof(int4) * (size_t)a.numSlots, g_stream));
     // adopt whatever the table already holds (a hash populated elsewhere, or a fresh reset)
@@ -704,13 +979,14 @@ static int do_reset(BFHashDataStruct* hd, const BFHashParams* hp) {
         if (rc) return rc;
     }
     aux->parity = 0;
-    reset_kernel<<<num_sms() * 8, 256, 0, g_stream>>>(*hd, hp->m_numSDFBlocks, hp->m_hashNumBuckets, aux->slotInfo, aux->ctrs);
+    aux->liveValid = true;
+    reset_kernel<<<num_sms() * 8, 256, 0, g_stream>>>(*hd, hp->m_numSDFBlocks, hp->m_hashNumBuckets, aux->slotInfo, aux->ctrs, aux->live);
     BF_CHECK(cudaGetLastError());
     return 0;
 }
 
 static int do_alloc(BFHashDataStruct* hd, const BFHashParams* hp, const float* depth, const BFDepthCameraParams* cp, TsdfAux* aux) {
-    dim3 block(32, 8);
+    dim3 block(16, 16);   // = BF_ALLOC_CACHE threads
     dim3 grid((cp->m_imageWidth + block.x - 1) / block.x, (cp->m_imageHeight + block.y - 1) / block.y);
     alloc_kernel<<<grid, block, 0, g_stream>>>(*hd, *hp, *cp, depth, aux->slotInfo, aux->ctrs);
     BF_CHECK(cudaGetLastError());
@@ -732,10 +1008,18 @@ static int do_integrate(BFHashDataStruct* hd, const BFHashParams* hp, const BFDe
                         TsdfAux* aux, bool deIntegrate, const unsigned* countPtr, unsigned countOverride) {
     const unsigned upper = countPtr ? hp->m_numSDFBlocks : countOverride;
     if (upper == 0) return 0;
-    const int grid = grid_for(upper, 16);
     const uchar4* color = reinterpret_cast<const uchar4*>(dd->d_colorData);
-    if (deIntegrate) integrate_kernel<true><<<grid, 128, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs);
-    else             integrate_kernel<false><<<grid, 128, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs);
+    static int variant = -1;        // BF_TSDF_INTEGRATE=tma selects the TMA-staged variant (measured slower)
+    if (variant < 0) { const char* e = getenv("BF_TSDF_INTEGRATE"); variant = (e && e[0] == 't') ? 1 : 0; }
+    if (variant == 0) {
+        const int grid = grid_for(upper, 16);
+        if (deIntegrate) integrate_kernel<true><<<grid, 128, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live);
+        else             integrate_kernel<false><<<grid, 128, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live);
+    } else {
+        const int grid = grid_for(upper, 6);
+        if (deIntegrate) integrate_tma_kernel<true><<<grid, 160, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live);
+        else             integrate_tma_kernel<false><<<grid, 160, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live);
+    }
     BF_CHECK(cudaGetLastError());
     return 0;
 }
@@ -751,7 +1035,7 @@ BF_API void bfSetStream(void* s) { g_stream = (cudaStream_t)s; }
 BF_API void* bfGetStream(void) { return (void*)g_stream; }
 BF_API const char* bfGetLastErrorString(void) { return t_lastError.c_str(); }
 
-BF_API size_t bfTsdfAuxBytes(const BFHashParams* hp) { return sizeof(int4) * (size_t)hp->m_numSDFBlocks + sizeof(unsigned) * CTR_NUM; }
+BF_API size_t bfTsdfAuxBytes(const BFHashParams* hp) { return (sizeof(int4) + sizeof(int)) * (size_t)hp->m_numSDFBlocks + sizeof(unsigned) * CTR_NUM; }
 
 BF_API int bfTsdfReset(BFHashDataStruct* hd, const BFHashParams* hp) { return do_reset(hd, hp); }
 
@@ -769,7 +1053,8 @@ BF_API int bfTsdfGarbageCollect(BFHashDataStruct* hd, const BFHashParams* hp) {
     TsdfAux* aux;
     int rc = get_aux(hd, hp, &aux, true);
     if (rc) return rc;
-    gc_fused_kernel<<<grid_for(hp->m_numSDFBlocks, 16), 128, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs);
+    if (aux->liveValid) gc_live_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 2), 256, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs, aux->live);
+    else                gc_fused_kernel<<<grid_for(hp->m_numSDFBlocks, 16), 128, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs);
     BF_CHECK(cudaGetLastError());
     return 0;
 }
@@ -800,7 +1085,7 @@ BF_API int bfTsdfGetLastFrameStats(const BFHashDataStruct* hd, unsigned long lon
     out[0] = c[CTR_E];
     out[1] = c[CTR_CULLED];
     out[2] = ((unsigned long long)c[CTR_U_HI] << 32) | c[CTR_U_LO];
-    out[3] = c[CTR_HIGH_WATER];
+    out[3] = (unsigned long long)c[CTR_HEAP_FAIL] + c[CTR_DROPPED];
     return 0;
 }
 
@@ -810,6 +1095,7 @@ BF_API int bfTsdfReleaseAux(const BFHashDataStruct* hd) {
     if (it == g_aux.end()) return 0;
     cudaFree(it->second.slotInfo);
     cudaFree(it->second.ctrs);
+    cudaFree(it->second.live);
     g_aux.erase(it);
     return 0;
 }
@@ -875,6 +1161,7 @@ BF_API void deIntegrateDepthMapCUDA(BFHashDataStruct* hd, const BFHashParams* hp
 
 BF_API void starveVoxelsKernelCUDA(BFHashDataStruct* hd, const BFHashParams* hp) {
     if (hp->m_numOccupiedBlocks == 0) return;
+    { TsdfAux* aux; if (get_aux(hd, nullptr, &aux, false) == 0) aux->liveValid = false; }
     starve_kernel<<<hp->m_numOccupiedBlocks, BF_SDF_BLOCK_VOXELS, 0, g_stream>>>(*hd);
     BF_SAFE((int)cudaGetLastError());
 }

@@ -25,8 +25,11 @@ def mat4_to_c(m) -> capi.BFFloat4x4:
 
 def mat4_inverse_f32(m) -> np.ndarray:
     """fp32 inverse (the reference inverts on the host: cuda_SimpleMatrixUtil.h:980-1100)."""
-    m = np.asarray(m, dtype=np.float32).reshape(4, 4)
-    return np.linalg.inv(m.astype(np.float64)).astype(np.float32)
+    m = np.ascontiguousarray(np.asarray(m, dtype=np.float32).reshape(16))
+    out = np.empty(16, dtype=np.float32)
+    fp = C.POINTER(C.c_float)
+    capi.lib().bfMat4Inverse(m.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    return out.reshape(4, 4)
 
 
 def default_hash_params(num_buckets=800000, num_sdf_blocks=200000, voxel_size=0.010, truncation=0.06,
@@ -186,7 +189,24 @@ class CUDASceneRepHashSDF:
         self._bind_stream()
         out = (C.c_ulonglong * 4)()
         capi.check(self.lib.bfTsdfGetLastFrameStats(C.byref(self.m_hashData), out), "bfTsdfGetLastFrameStats")
-        return {"E": out[0], "active": out[1], "U": out[2], "high_water": out[3]}
+        return {"E": out[0], "active": out[1], "U": out[2], "dropped": out[3]}
+
+    def runOps(self, ops, depth_frames, color_frames, cam: BFDepthCameraParams):
+        """Replay a list of (kind, frame, pose) TSDF operations in ONE library call (bfTsdfRunOps): the re-integration
+        batch of DepthSensing.cpp:854-902 without a Python round trip per operation.  Asynchronous."""
+        self._bind_stream()
+        arr = (capi.BFTsdfOp * len(ops))()
+        for i, (kind, frame, pose) in enumerate(ops):
+            arr[i].kind, arr[i].frame = kind, frame
+            if pose is not None:
+                flat = np.asarray(pose, dtype=np.float32).reshape(16)
+                for k in range(16):
+                    arr[i].pose[k] = float(flat[k])
+        dptr = (C.c_void_p * len(depth_frames))(*[t.data_ptr() for t in depth_frames])
+        cptr = (C.c_void_p * len(color_frames))(*[t.data_ptr() for t in color_frames])
+        self._op_keepalive = (arr, dptr, cptr)
+        capi.check(self.lib.bfTsdfRunOps(C.byref(self.m_hashData), C.byref(self.m_hashParams), C.byref(cam), arr, len(ops), dptr, cptr),
+                   "bfTsdfRunOps")
 
     def getHashData(self) -> BFHashDataStruct:
         return self.m_hashData

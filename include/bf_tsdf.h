@@ -198,7 +198,8 @@ int bfTsdfGetNumOccupiedBlocks(const BFHashDataStruct* hashData, unsigned int* o
 
 /* counters of the last bfTsdfIntegrateFrame, for the roofline arithmetic
  * (U = voxels passing the truncation test, E = in-frustum blocks).
- * out[0]=E, out[1]=blocks surviving the depth-range cull, out[2]=U.  Synchronises. */
+ * out[0]=E, out[1]=blocks surviving the depth-range cull, out[2]=U, out[3]=block inserts dropped since reset
+ * (heap exhausted or no free entry inside the probe window; 0 in a sanely sized table).  Synchronises. */
 int bfTsdfGetLastFrameStats(const BFHashDataStruct* hashData, unsigned long long out[4]);
 
 /* release the library-private scratch attached to this hash (call before freeing d_hash) */

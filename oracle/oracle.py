@@ -39,7 +39,7 @@ def lib(fast: bool = False) -> C.CDLL:
     L.orc_tsdf_find.argtypes = [P(BFHashDataStruct), P(BFHashParams), C.c_int, C.c_int, C.c_int]
     L.orc_tsdf_find.restype = C.c_int
     L.orc_tsdf_alloc.argtypes = [P(BFHashDataStruct), P(BFHashParams), fp, P(BFDepthCameraParams)]
-    L.orc_tsdf_alloc.restype = None
+    L.orc_tsdf_alloc.restype = C.c_uint
     L.orc_tsdf_compactify.argtypes = [P(BFHashDataStruct), P(BFHashParams), P(BFDepthCameraParams)]
     L.orc_tsdf_compactify.restype = C.c_uint
     L.orc_tsdf_integrate.argtypes = [P(BFHashDataStruct), P(BFHashParams), fp, C.c_void_p, P(BFDepthCameraParams), C.c_uint, C.c_int]
@@ -85,6 +85,7 @@ class OracleSceneRepHashSDF:
         self.hd = hd
         self.num_occupied = 0
         self.last_U = 0
+        self.dropped = 0      # block inserts that found no room (table over-full)
         self.reset()
 
     def reset(self):
@@ -98,7 +99,7 @@ class OracleSceneRepHashSDF:
     def integrate(self, T, depth: np.ndarray, color: np.ndarray | None, cam: BFDepthCameraParams):
         self._set_pose(T)
         depth = np.ascontiguousarray(depth, np.float32)
-        self.L.orc_tsdf_alloc(C.byref(self.hd), C.byref(self.hp), depth, C.byref(cam))
+        self.dropped += self.L.orc_tsdf_alloc(C.byref(self.hd), C.byref(self.hp), depth, C.byref(cam))
         self.num_occupied = self.L.orc_tsdf_compactify(C.byref(self.hd), C.byref(self.hp), C.byref(cam))
         cptr = color.ctypes.data if color is not None else None
         self.last_U = self.L.orc_tsdf_integrate(C.byref(self.hd), C.byref(self.hp), depth, cptr, C.byref(cam), self.num_occupied, 0)

@@ -195,14 +195,15 @@ static void heap_push(BFHashDataStruct* hd, uint32_t slot) {
     hd->d_heapCounter[0] = c + 1;
 }
 
-/* VoxelUtilHashSDF.h:549-655 allocBlock, with every try-lock succeeding */
-static void alloc_block(BFHashDataStruct* hd, const BFHashParams* hp, i3 pos) {
+/* VoxelUtilHashSDF.h:549-655 allocBlock, with every try-lock succeeding.
+ * Returns 1 if the block had to be DROPPED (no heap slot, or no free entry inside the probe window). */
+static int alloc_block(BFHashDataStruct* hd, const BFHashParams* hp, i3 pos) {
     const uint32_t h = hash_pos(hp, pos), hpz = h * BF_HASH_BUCKET_SIZE;
     const uint32_t total = BF_HASH_BUCKET_SIZE * hp->m_hashNumBuckets;
     int firstEmpty = -1;
     for (uint32_t j = 0; j < BF_HASH_BUCKET_SIZE; ++j) {
         const BFHashEntry* c = &hd->d_hash[hpz + j];
-        if (entry_is(c, pos)) return;
+        if (entry_is(c, pos)) return 0;
         if (firstEmpty == -1 && c->ptr == BF_FREE_ENTRY) firstEmpty = (int)(hpz + j);
     }
     const uint32_t last = (h + 1) * BF_HASH_BUCKET_SIZE - 1;
@@ -210,18 +211,18 @@ static void alloc_block(BFHashDataStruct* hd, const BFHashParams* hp, i3 pos) {
     const uint32_t maxLoop = hp->m_hashMaxCollisionLinkedListSize;
     for (uint32_t it = 0; it < maxLoop; ++it) {
         const BFHashEntry* c = &hd->d_hash[i];
-        if (entry_is(c, pos)) return;
+        if (entry_is(c, pos)) return 0;
         if (c->offset == 0) break;
         i = (last + c->offset) % total;
     }
     uint32_t slot;
     if (firstEmpty != -1) {
-        if (!heap_pop(hd, &slot)) return;
+        if (!heap_pop(hd, &slot)) return 1;
         BFHashEntry* e = &hd->d_hash[firstEmpty];
         e->pos[0] = pos.x; e->pos[1] = pos.y; e->pos[2] = pos.z;
         e->offset = BF_NO_OFFSET;
         e->ptr = (int32_t)(slot * BF_SDF_BLOCK_VOXELS);
-        return;
+        return 0;
     }
     /* linear probe for a free non-bucket-last slot, splice into the list (:614-654) */
     uint32_t offset = 0, it = 0;
@@ -230,26 +231,27 @@ static void alloc_block(BFHashDataStruct* hd, const BFHashParams* hp, i3 pos) {
         i = (last + offset) % total;
         if ((offset % BF_HASH_BUCKET_SIZE) == 0) continue;
         if (hd->d_hash[i].ptr == BF_FREE_ENTRY) {
-            if (!heap_pop(hd, &slot)) return;
+            if (!heap_pop(hd, &slot)) return 1;
             BFHashEntry lastE = hd->d_hash[last];
             BFHashEntry* e = &hd->d_hash[i];
             e->pos[0] = pos.x; e->pos[1] = pos.y; e->pos[2] = pos.z;
             e->offset = lastE.offset;
             e->ptr = (int32_t)(slot * BF_SDF_BLOCK_VOXELS);
             hd->d_hash[last].offset = offset;
-            return;
+            return 0;
         }
         it++;
     }
+    return 1;
 }
 
 /* allocKernel: CUDASceneRepHashSDF.cu:165-251 (d_bitMask == NULL: streaming is disabled
- * for BundleFusion, zParametersDefault.txt:99).  Optional outBlocks/outCap/outCount record
- * every in-frustum block the DDA visits (with duplicates) for set-level tests. */
-ORC_API void orc_tsdf_alloc(BFHashDataStruct* hd, const BFHashParams* hp,
+ * for BundleFusion, zParametersDefault.txt:99). */
+ORC_API unsigned orc_tsdf_alloc(BFHashDataStruct* hd, const BFHashParams* hp,
                             const float* depth, const BFDepthCameraParams* cp) {
     const unsigned W = cp->m_imageWidth, H = cp->m_imageHeight;
     const float vs = hp->m_virtualVoxelSize;
+    unsigned dropped = 0;
     for (unsigned y = 0; y < H; ++y) for (unsigned x = 0; x < W; ++x) {
         float d = depth[y * W + x];
         if (d == ORC_MINF || d == 0.0f) continue;
@@ -287,7 +289,7 @@ ORC_API void orc_tsdf_alloc(BFHashDataStruct* hd, const BFHashParams* hp,
         if (boundary.z - rayMin.z == 0.0f) { tMax.z = INFINITY; tDelta.z = INFINITY; }
 
         for (unsigned iter = 0; iter < 1024; ++iter) {
-            if (block_in_frustum(hp, cp, cur)) alloc_block(hd, hp, cur);
+            if (block_in_frustum(hp, cp, cur)) dropped += (unsigned)alloc_block(hd, hp, cur);
             if (tMax.x < tMax.y && tMax.x < tMax.z) {
                 cur.x = f2i((float)cur.x + step.x);
                 if (cur.x == bound.x) break;
@@ -303,6 +305,7 @@ ORC_API void orc_tsdf_alloc(BFHashDataStruct* hd, const BFHashParams* hp,
             }
         }
     }
+    return dropped;   /* insert attempts that found no room (0 in any sanely sized table) */
 }
 
 /* compactifyHashAllInOneKernel: CUDASceneRepHashSDF.cu:324-384 (table order) */
