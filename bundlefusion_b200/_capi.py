@@ -105,6 +105,66 @@ TSDF_SYMBOLS = [
 
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
 
+SOLVER_SYMBOLS = [
+    "solveBundlingStub", "buildVariablesToCorrespondencesTableCUDA", "evalMaxResidual", "countHighResiduals", "collectHighResiduals",
+    "convertLiePosesToMatricesCU", "convertMatricesToPosesCU", "convertPosesToMatricesCU",
+    "bfSolverSolve", "bfSolverGetStats", "bfSolverMaxResidual", "bfSolverWorkspaceBytes", "bfSolverReleaseWorkspace",
+]
+
+
+class BFEntryJ(C.Structure):
+    _fields_ = [("imgIdx_i", C.c_uint32), ("imgIdx_j", C.c_uint32), ("pos_i", C.c_float * 3), ("pos_j", C.c_float * 3)]
+
+
+class BFCUDACachedFrame(C.Structure):
+    _fields_ = [("d_depthDownsampled", C.c_void_p), ("d_cameraposDownsampled", C.c_void_p), ("d_intensityDownsampled", C.c_void_p),
+                ("d_intensityDerivsDownsampled", C.c_void_p), ("d_normalsDownsampledUCHAR4", C.c_void_p), ("d_normalsDownsampled", C.c_void_p)]
+
+
+class _F4(C.Structure):
+    _pack_ = 16
+    _fields_ = [("v", C.c_float * 4)]
+
+
+class BFSolverInput(C.Structure):
+    _fields_ = [
+        ("d_correspondences", C.c_void_p), ("d_variablesToCorrespondences", C.c_void_p), ("d_numEntriesPerRow", C.c_void_p),
+        ("numberOfCorrespondences", C.c_uint32), ("numberOfImages", C.c_uint32), ("maxNumberOfImages", C.c_uint32), ("maxCorrPerImage", C.c_uint32),
+        ("d_validImages", C.c_void_p), ("d_cacheFrames", C.c_void_p), ("denseDepthWidth", C.c_uint32), ("denseDepthHeight", C.c_uint32),
+        ("intrinsics", C.c_float * 4), ("maxNumDenseImPairs", C.c_uint32), ("_pad0", C.c_uint32), ("colorFocalLength", C.c_float * 2),
+        ("weightsSparse", C.POINTER(C.c_float)), ("weightsDenseDepth", C.POINTER(C.c_float)), ("weightsDenseColor", C.POINTER(C.c_float)),
+        ("_tail", C.c_uint64),
+    ]
+
+
+_STATE_FIELDS = ["d_deltaRot", "d_deltaTrans", "d_xRot", "d_xTrans", "d_rRot", "d_rTrans", "d_zRot", "d_zTrans", "d_pRot", "d_pTrans", "d_Jp",
+                 "d_Ap_XRot", "d_Ap_XTrans", "d_scanAlpha", "d_rDotzOld", "d_precondionerRot", "d_precondionerTrans", "d_sumResidual",
+                 "d_countHighResidual", "d_denseJtJ", "d_denseJtr", "d_denseCorrCounts", "d_xTransforms", "d_xTransformInverses",
+                 "d_denseOverlappingImages", "d_numDenseOverlappingImages", "d_corrCount", "d_corrCountColor", "d_sumResidualColor"]
+
+
+class BFSolverState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _STATE_FIELDS]
+
+
+class BFSolverParameters(C.Structure):
+    _fields_ = [
+        ("nNonLinearIterations", C.c_uint32), ("nLinIterations", C.c_uint32), ("verifyOptDistThresh", C.c_float), ("verifyOptPercentThresh", C.c_float),
+        ("highResidualThresh", C.c_float), ("denseDistThresh", C.c_float), ("denseNormalThresh", C.c_float), ("denseColorThresh", C.c_float),
+        ("denseColorGradientMin", C.c_float), ("denseDepthMin", C.c_float), ("denseDepthMax", C.c_float),
+        ("useDenseDepthAllPairwise", C.c_uint8), ("_pad0", C.c_uint8 * 3), ("denseOverlapCheckSubsampleFactor", C.c_uint32),
+        ("weightSparse", C.c_float), ("weightDenseDepth", C.c_float), ("weightDenseColor", C.c_float), ("useDense", C.c_uint8), ("_pad1", C.c_uint8 * 3),
+    ]
+
+
+class BFSolverStateAnalysis(C.Structure):
+    _fields_ = [("d_maxResidualIndex", C.c_void_p), ("d_maxResidual", C.c_void_p), ("h_maxResidualIndex", C.c_void_p), ("h_maxResidual", C.c_void_p)]
+
+
+assert C.sizeof(BFEntryJ) == 32 and C.sizeof(BFCUDACachedFrame) == 48
+assert BFSolverInput.intrinsics.offset == 64 and BFSolverInput.colorFocalLength.offset == 88 and BFSolverInput.weightsSparse.offset == 96
+assert C.sizeof(BFSolverInput) == 128 and C.sizeof(BFSolverState) == 232 and C.sizeof(BFSolverParameters) == 68
+
 
 class BFTsdfOp(C.Structure):
     _fields_ = [("kind", C.c_int32), ("frame", C.c_int32), ("pose", C.c_float * 16)]
@@ -159,6 +219,29 @@ def lib() -> C.CDLL:
     L.bfMat4Inverse.argtypes = [P(C.c_float), P(C.c_float)]
     L.bfMat4Inverse.restype = None
     L.bfTsdfRunOps.argtypes = [P(BFHashDataStruct), P(BFHashParams), P(BFDepthCameraParams), P(BFTsdfOp), C.c_int, P(vp), P(vp)]
+    # solver
+    L.solveBundlingStub.argtypes = [P(BFSolverInput), P(BFSolverState), P(BFSolverParameters), P(BFSolverStateAnalysis), P(C.c_float), vp]
+    L.solveBundlingStub.restype = None
+    L.buildVariablesToCorrespondencesTableCUDA.argtypes = [vp, C.c_uint, C.c_uint, vp, vp, vp]
+    L.buildVariablesToCorrespondencesTableCUDA.restype = None
+    L.evalMaxResidual.argtypes = [P(BFSolverInput), P(BFSolverState), P(BFSolverStateAnalysis), P(BFSolverParameters), vp]
+    L.evalMaxResidual.restype = None
+    L.countHighResiduals.argtypes = [P(BFSolverInput), P(BFSolverState), P(BFSolverParameters), vp]
+    L.countHighResiduals.restype = C.c_int
+    L.collectHighResiduals.argtypes = [P(BFSolverInput), P(BFSolverState), P(BFSolverStateAnalysis), P(BFSolverParameters), vp]
+    L.collectHighResiduals.restype = None
+    L.convertLiePosesToMatricesCU.argtypes = [vp, vp, C.c_uint, vp, vp]
+    L.convertLiePosesToMatricesCU.restype = None
+    L.convertMatricesToPosesCU.argtypes = [vp, C.c_uint, vp, vp, vp]
+    L.convertMatricesToPosesCU.restype = None
+    L.convertPosesToMatricesCU.argtypes = [vp, vp, C.c_uint, vp, vp]
+    L.convertPosesToMatricesCU.restype = None
+    L.bfSolverSolve.argtypes = [P(BFSolverInput), P(BFSolverState), P(BFSolverParameters)]
+    L.bfSolverGetStats.argtypes = [P(BFSolverState), C.c_ulonglong * 8]
+    L.bfSolverMaxResidual.argtypes = [P(BFSolverInput), P(BFSolverState), P(BFSolverParameters), vp]
+    L.bfSolverWorkspaceBytes.argtypes = [C.c_uint, C.c_uint]
+    L.bfSolverWorkspaceBytes.restype = C.c_size_t
+    L.bfSolverReleaseWorkspace.argtypes = [P(BFSolverState)]
     _lib = L
     return L
 

@@ -95,3 +95,116 @@ def plane_frame(W: int, H: int, z0: float, color=(128, 64, 32)):
     col = np.zeros((H, W, 4), dtype=np.uint8)
     col[..., 0], col[..., 1], col[..., 2], col[..., 3] = color[0], color[1], color[2], 255
     return depth, col
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic bundle-adjustment problems
+# ------------------------------------------------------------------------------------------------
+def se3_exp(rot, trans) -> np.ndarray:
+    """float64 SE(3) exponential T = [exp(w) | V(w) u] (the parametrisation of FL/Solver/LieDerivUtil.h:160-207)."""
+    w = np.asarray(rot, np.float64); u = np.asarray(trans, np.float64)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-9:
+        R = np.eye(3) + K; Vm = np.eye(3) + 0.5 * K
+    else:
+        A, B, Cc = np.sin(th) / th, (1 - np.cos(th)) / th ** 2, (1 - np.sin(th) / th) / th ** 2
+        R = np.eye(3) + A * K + B * K @ K
+        Vm = np.eye(3) + B * K + Cc * K @ K
+    T = np.eye(4); T[:3, :3] = R; T[:3, 3] = Vm @ u
+    return T
+
+
+def se3_log(T):
+    """float64 inverse of se3_exp -> (rot, trans)."""
+    R = T[:3, :3]; t = T[:3, 3]
+    c = np.clip((np.trace(R) - 1) / 2, -1, 1); th = np.arccos(c)
+    if th < 1e-9:
+        w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2
+    else:
+        w = th / (2 * np.sin(th)) * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-9:
+        Vm = np.eye(3) + 0.5 * K
+    else:
+        Vm = np.eye(3) + (1 - np.cos(th)) / th ** 2 * K + (1 - np.sin(th) / th) / th ** 2 * K @ K
+    return w, np.linalg.solve(Vm, t)
+
+
+def make_ba_problem(n_images: int, degree: int = 6, corr_per_pair: int = 25, noise: float = 0.002, outliers: float = 0.0,
+                    perturb_rot: float = 0.02, perturb_trans: float = 0.03, seed: int = 7, stride: int = 10):
+    """Keyframes on the Lissajous path (every `stride`-th frame), a co-visibility graph (each image paired with its
+    `degree` successors), `corr_per_pair` exact 3-D correspondences per pair observed in both camera frames with
+    Gaussian noise (and a fraction of gross outliers).  Returns dict with EntryJ-layout arrays and float32 poses:
+    corr (C,8) uint32 view-compatible, gt (N,4,4), init_rot/init_trans (N,3) float32 (image 0 = ground truth)."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    gt = np.stack([lissajous_pose(stride * k).astype(np.float64) for k in range(n_images)])
+    pairs = [(i, j) for i in range(n_images) for j in range(i + 1, min(n_images, i + 1 + degree))]
+    C = len(pairs) * corr_per_pair
+    corr = np.zeros(C, dtype=[("i", "<u4"), ("j", "<u4"), ("pi", "<f4", 3), ("pj", "<f4", 3)])
+    k = 0
+    for (i, j) in pairs:
+        # points in front of camera i, 0.5 .. 3 m away
+        z = rng.uniform(0.5, 3.0, corr_per_pair)
+        xy = rng.uniform(-0.5, 0.5, (corr_per_pair, 2)) * z[:, None]
+        pi = np.concatenate([xy, z[:, None]], 1)
+        X = pi @ gt[i][:3, :3].T + gt[i][:3, 3]
+        Tj_inv = np.linalg.inv(gt[j])
+        pj = X @ Tj_inv[:3, :3].T + Tj_inv[:3, 3]
+        pi_n = pi + rng.standard_normal(pi.shape) * noise
+        pj_n = pj + rng.standard_normal(pj.shape) * noise
+        if outliers > 0:
+            bad = rng.random(corr_per_pair) < outliers
+            pj_n[bad] += rng.standard_normal((int(bad.sum()), 3)) * 0.3
+        sl = slice(k, k + corr_per_pair)
+        corr["i"][sl], corr["j"][sl], corr["pi"][sl], corr["pj"][sl] = i, j, pi_n, pj_n
+        k += corr_per_pair
+    rot = np.zeros((n_images, 3), np.float32); trans = np.zeros((n_images, 3), np.float32)
+    for n in range(n_images):
+        T = gt[n]
+        if n > 0:
+            T = se3_exp(rng.standard_normal(3) * perturb_rot, rng.standard_normal(3) * perturb_trans) @ T
+        w, u = se3_log(T)
+        rot[n], trans[n] = w, u
+    return {"corr": corr, "gt": gt, "init_rot": rot, "init_trans": trans, "pairs": pairs}
+
+
+def ba_reference_f64(corr, rot0, trans0, n_gn: int = 10, w_sparse: float = 1.0):
+    """Independent float64 Gauss-Newton (dense normal equations, numpy) on the sparse energy of
+    FL/Solver/SolverBundlingEquationsLie.h:42-57 with left-multiplicative updates; image 0 fixed.
+    Returns (rot, trans) float64 [N,3]."""
+    N = len(rot0)
+    T = [se3_exp(rot0[k], trans0[k]) for k in range(N)]
+    valid = corr["i"] != 0xFFFFFFFF
+    ci, cj = corr["i"][valid].astype(int), corr["j"][valid].astype(int)
+    pi, pj = corr["pi"][valid].astype(np.float64), corr["pj"][valid].astype(np.float64)
+    for _ in range(n_gn):
+        Tm = np.stack(T)
+        Pi = np.einsum("cab,cb->ca", Tm[ci][:, :3, :3], pi) + Tm[ci][:, :3, 3]
+        Pj = np.einsum("cab,cb->ca", Tm[cj][:, :3, :3], pj) + Tm[cj][:, :3, 3]
+        r = Pi - Pj
+
+        def J(P):  # d(exp(e) P)/de = [-[P]x | I], columns (rot, trans)
+            Jm = np.zeros((len(P), 3, 6))
+            Jm[:, 0, 1], Jm[:, 0, 2] = P[:, 2], -P[:, 1]
+            Jm[:, 1, 0], Jm[:, 1, 2] = -P[:, 2], P[:, 0]
+            Jm[:, 2, 0], Jm[:, 2, 1] = P[:, 1], -P[:, 0]
+            Jm[:, 0, 3] = Jm[:, 1, 4] = Jm[:, 2, 5] = 1
+            return Jm
+        Ji, Jj = J(Pi), -J(Pj)
+        H = np.zeros((6 * N, 6 * N)); g = np.zeros(6 * N)
+        for c in range(len(ci)):
+            a, b = 6 * ci[c], 6 * cj[c]
+            H[a:a + 6, a:a + 6] += Ji[c].T @ Ji[c]; H[b:b + 6, b:b + 6] += Jj[c].T @ Jj[c]
+            H[a:a + 6, b:b + 6] += Ji[c].T @ Jj[c]; H[b:b + 6, a:a + 6] += Jj[c].T @ Ji[c]
+            g[a:a + 6] += Ji[c].T @ r[c]; g[b:b + 6] += Jj[c].T @ r[c]
+        H *= w_sparse; g *= w_sparse
+        d = np.zeros(6 * N)
+        d[6:] = np.linalg.solve(H[6:, 6:] + 1e-12 * np.eye(6 * N - 6), -g[6:])
+        for k in range(1, N):
+            T[k] = se3_exp(d[6 * k:6 * k + 3], d[6 * k + 3:6 * k + 6]) @ T[k]
+        if np.abs(d).max() < 1e-10:
+            break
+    out = [se3_log(Tk) for Tk in T]
+    return np.array([o[0] for o in out]), np.array([o[1] for o in out])

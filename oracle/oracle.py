@@ -172,3 +172,70 @@ def check_hash_invariants(snap: dict, hp: BFHashParams) -> None:
                 found = True
                 break
         assert found, f"entry {idx} not reachable from bucket {hb}"
+
+
+# ------------------------------------------------------------------------------------------------
+# solver oracle
+# ------------------------------------------------------------------------------------------------
+def _bind_solver(L):
+    if getattr(L, "_solver_bound", False):
+        return L
+    fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    L.orc_pose_to_matrix.argtypes = [fp, fp, fp]
+    L.orc_matrix_to_pose.argtypes = [fp, fp, fp]
+    L.orc_mat4_inverse.argtypes = [fp, fp]
+    L.orc_solver_build_table.argtypes = [C.c_void_p, C.c_uint, C.c_uint, ip, ip, C.c_uint]
+    L.orc_solver_solve_sparse.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, fp, fp, C.c_uint, C.c_uint, fp, C.c_int, ip, ip, C.c_uint * 4]
+    L.orc_solver_solve_sparse.restype = C.c_int
+    L.orc_solver_max_residual.argtypes = [C.c_void_p, C.c_uint, fp, fp, C.c_float, C.POINTER(C.c_int)]
+    L.orc_solver_max_residual.restype = C.c_float
+    L.orc_solver_energy.argtypes = [C.c_void_p, C.c_uint, fp, fp, C.c_float]
+    L.orc_solver_energy.restype = C.c_double
+    L._solver_bound = True
+    return L
+
+
+def pose_to_matrix(rot, trans) -> np.ndarray:
+    L = _bind_solver(lib())
+    M = np.zeros(16, np.float32)
+    L.orc_pose_to_matrix(np.ascontiguousarray(rot, np.float32), np.ascontiguousarray(trans, np.float32), M)
+    return M.reshape(4, 4)
+
+
+def matrix_to_pose(M):
+    L = _bind_solver(lib())
+    r, t = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    L.orc_matrix_to_pose(np.ascontiguousarray(M, np.float32).reshape(16), r, t)
+    return r, t
+
+
+def solve_sparse(corr: np.ndarray, rot0, trans0, n_gn: int, n_pcg: int, weights=None, max_corr_per_image: int = 4000, fast: bool = False):
+    """CUDASolverBundling::solve for the sparse term.  `corr`: structured array in EntryJ layout (copied; entries the
+    table build invalidates are reported back).  Returns dict(rot, trans, stats, corr)."""
+    L = _bind_solver(lib(fast))
+    corr = np.ascontiguousarray(corr).copy()
+    N = len(rot0)
+    rot = np.ascontiguousarray(rot0, np.float32).copy()
+    trans = np.ascontiguousarray(trans0, np.float32).copy()
+    w = np.ascontiguousarray(weights if weights is not None else np.ones(n_gn), np.float32)
+    table = np.zeros(N * max_corr_per_image, np.int32)
+    rows = np.zeros(N, np.int32)
+    stats = (C.c_uint * 4)()
+    rc = L.orc_solver_solve_sparse(corr.ctypes.data, len(corr), N, max_corr_per_image, rot, trans, n_gn, n_pcg, w, 1, table, rows, stats)
+    assert rc == 0
+    return {"rot": rot, "trans": trans, "gn": stats[0], "pcg": stats[1], "corr": corr, "rows": rows}
+
+
+def max_residual(corr, rot, trans, w=1.0):
+    L = _bind_solver(lib())
+    idx = C.c_int(0)
+    corr = np.ascontiguousarray(corr)
+    v = L.orc_solver_max_residual(corr.ctypes.data, len(corr), np.ascontiguousarray(rot, np.float32), np.ascontiguousarray(trans, np.float32), w, C.byref(idx))
+    return float(v), idx.value
+
+
+def energy(corr, rot, trans, w=1.0) -> float:
+    L = _bind_solver(lib())
+    corr = np.ascontiguousarray(corr)
+    return float(L.orc_solver_energy(corr.ctypes.data, len(corr), np.ascontiguousarray(rot, np.float32), np.ascontiguousarray(trans, np.float32), w))

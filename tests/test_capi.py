@@ -47,3 +47,15 @@ def test_library_exports_every_declared_symbol():
 
 def test_symbol_list_matches_header():
     assert sorted(set(_declared_symbols("bf_tsdf.h"))) == sorted(set(capi.TSDF_SYMBOLS))
+    assert sorted(set(_declared_symbols("bf_host.h"))) == sorted(set(capi.HOST_SYMBOLS))
+    assert sorted(set(_declared_symbols("bf_solver.h"))) == sorted(set(capi.SOLVER_SYMBOLS))
+
+
+def test_solver_pod_layouts():
+    assert C.sizeof(capi.BFEntryJ) == 32
+    assert C.sizeof(capi.BFSolverInput) == 128 and capi.BFSolverInput.intrinsics.offset == 64
+    assert capi.BFSolverInput.d_validImages.offset == 40 and capi.BFSolverInput.weightsDenseColor.offset == 112
+    assert C.sizeof(capi.BFSolverState) == 29 * 8
+    assert C.sizeof(capi.BFSolverParameters) == 68 and capi.BFSolverParameters.denseOverlapCheckSubsampleFactor.offset == 48
+    assert capi.BFSolverParameters.useDense.offset == 64
+    assert C.sizeof(capi.BFCUDACachedFrame) == 48
