@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the BundleFusion hot path built so far (hashed-voxel TSDF integrate / re-integrate / GC per
+frame + local and global sparse bundle adjustment per 10-frame chunk) on synthetic 640x480 RGB-D.
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (libbundlefusion_b200.so)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the host cores (rank 0 only)
+
+A "step" is one frame of the reference's frame loop (FL/DepthSensing/DepthSensing.cpp:966-1129):
+    reintegrate(): up to s_maxFrameFixes = 10 x { deIntegrate(old pose); integrate(new pose) }, garbageCollect()
+    integrate(current frame)
+and, on the last frame of every 10-frame chunk (FL/OnlineBundler.cpp:410-416), one local BA (11 frames, 2 GN x 100 PCG) and
+one global BA over the keyframes (3 GN x 150 PCG).  One JSON line is printed by rank 0 (contract: see the task statement).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 640, 480
+WORKLOAD = {
+    "workload": "configs[1]: 640x480 RGB-D stream, hashed TSDF (1 cm voxels, 4M-block heap, 4M buckets), per frame 1 integrate + 10 "
+                "re-integrations (de-integrate + integrate) + GC; per 10-frame chunk 1 local BA (11 frames, 2 GN x 100 PCG) + 1 global BA "
+                "(500 keyframes, 187k correspondences, 3 GN x 150 PCG); SIFT detect/match and the dense BA term are not built yet",
+    "frame": [W, H], "voxel_m": 0.010, "sdf_blocks": 4000000, "hash_buckets": 4000000, "reintegrations_per_frame": 10,
+    "chunk": 10, "global_keyframes": 500, "global_degree": 15, "frame_bank": 128,
+    "l2_policy": "inputs larger than L2: the frame bank (315 MB) and the voxel working set are cycled; no explicit flush",
+}
+METRIC = "frames/sec (TSDF integrate + global BA solve) on synthetic 640x480 RGB-D"
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+def clocks_sampler(stop_evt, out, gpu_index):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    try:
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(gpu_index)],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return
+    def reader():
+        for line in p.stdout:
+            out.append(line.strip())
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    stop_evt.wait()
+    p.terminate()
+
+
+def summarize_clocks(lines):
+    sm, smax, reasons = [], 0, set()
+    for ln in lines:
+        f = [x.strip() for x in ln.split(",")]
+        if len(f) < 6:
+            continue
+        try:
+            sm.append(float(f[0])); smax = max(smax, float(f[1]))
+        except ValueError:
+            continue
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+            if v.lower().startswith("active"):
+                reasons.add(name)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+class Workload:
+    """Frame schedule shared by the GPU arm and the CPU arm: which frame is integrated, which are re-integrated at which poses."""
+
+    def __init__(self, bank_poses, seed=99):
+        self.poses_cur = [p.copy() for p in bank_poses]          # pose each bank frame is currently integrated with
+        self.B = len(bank_poses)
+        self.rng = np.random.Generator(np.random.MT19937(seed))
+
+    def perturb(self, T):
+        from bundlefusion_b200 import synth
+        d = synth.se3_exp(self.rng.standard_normal(3) * 0.002, self.rng.standard_normal(3) * 0.003)
+        return (d @ T.astype(np.float64)).astype(np.float32)
+
+    def step_ops(self, f, n_reint):
+        """ops of frame f: [(kind, bank index, pose)], kinds 0 integrate / 1 de-integrate / 2 GC (DepthSensing.cpp:854-902,1049)."""
+        ops = []
+        cur = f % self.B
+        # re-integration targets: the most recent frames (TrajectoryManager's top-N by pose change, here all changed)
+        for k in range(1, n_reint + 1):
+            r = (cur - k) % self.B
+            old = self.poses_cur[r]
+            new = self.perturb(old)
+            ops.append((1, r, old)); ops.append((0, r, new))
+            self.poses_cur[r] = new
+        ops.append((2, 0, None))
+        # the incoming frame replaces what the slot held in the stream one bank-cycle ago (that observation stays integrated)
+        ops.append((0, cur, self.poses_cur[cur]))
+        return ops
+
+
+def make_ba_problems():
+    from bundlefusion_b200 import synth
+    loc = synth.make_ba_problem(11, degree=10, corr_per_pair=25, noise=0.002, seed=31)
+    glo = synth.make_ba_problem(WORKLOAD["global_keyframes"], degree=WORKLOAD["global_degree"], corr_per_pair=25, noise=0.002, seed=32, stride=10)
+    return loc, glo
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from bundlefusion_b200 import _capi as capi
+    from bundlefusion_b200 import synth_gpu
+    from bundlefusion_b200.scene_rep import CUDASceneRepHashSDF, camera_params, default_hash_params
+    from bundlefusion_b200.solver import CUDASolverBundling
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = capi.lib()
+    cam = camera_params(W, H)
+    hp = default_hash_params(num_buckets=WORKLOAD["hash_buckets"], num_sdf_blocks=WORKLOAD["sdf_blocks"], voxel_size=WORKLOAD["voxel_m"])
+    if world > 1:
+        hp.m_dummy = (world << 32) | rank            # spatial shard of the voxel hash: this rank owns blocks with owner(pos) == rank
+    scene = CUDASceneRepHashSDF(hp, dev)
+
+    B = WORKLOAD["frame_bank"]
+    idx = [8 * i for i in range(B)]
+    depth, color, poses = synth_gpu.make_frames(idx, W, H, device=str(dev))
+    dlist, clist = [depth[i] for i in range(B)], [color[i] for i in range(B)]
+    # host copies for the e2e leg (pinned), plus a device landing slot per bank frame
+    h_depth = depth.cpu().pin_memory(); h_color = color.cpu().pin_memory()
+    wl = Workload(list(poses))
+    n_re = WORKLOAD["reintegrations_per_frame"]
+    # the whole op schedule is prepared up front (poses come from the schedule, not from the timed loop)
+    total_steps = args.warmup + 2 * args.steps
+    packed_ops = [scene.packOps(wl.step_ops(f, n_re)) for f in range(total_steps)]
+    packed_frames = scene.packFrames(dlist, clist)
+
+    loc, glo = make_ba_problems()
+    def upload(prob):
+        return (torch.from_numpy(prob["corr"].view(np.uint8).reshape(-1).copy()).to(dev), torch.from_numpy(prob["init_rot"]).to(dev),
+                torch.from_numpy(prob["init_trans"]).to(dev), torch.ones(len(prob["init_rot"]), dtype=torch.int32, device=dev))
+    lc, lr0, lt0, lv = upload(loc); gc_, gr0, gt0, gv = upload(glo)
+    lrot, ltrans, grot, gtrans = lr0.clone(), lt0.clone(), gr0.clone(), gt0.clone()
+    sol_l = CUDASolverBundling(11, 11 * 1000, dev); sol_g = CUDASolverBundling(len(glo["init_rot"]), max(len(glo["corr"]), 1000 * len(glo["init_rot"])), dev)
+    h_grot = torch.empty_like(grot, device="cpu").pin_memory(); h_gtrans = torch.empty_like(gtrans, device="cpu").pin_memory()
+    h_heap = torch.empty(1, dtype=torch.int32).pin_memory()
+
+    # warm model: every bank frame integrated once
+    scene.runOps([(0, i, poses[i]) for i in range(B)], dlist, clist, cam)
+    torch.cuda.synchronize()
+
+    def ba():
+        lrot.copy_(lr0); ltrans.copy_(lt0); grot.copy_(gr0); gtrans.copy_(gt0)
+        sol_l.solve(lc, len(loc["corr"]), lv, 11, 2, 100, [1.0, 1.0], d_rotationAnglesUnknowns=lrot, d_translationUnknowns=ltrans)
+        sol_g.solve(gc_, len(glo["corr"]), gv, len(glo["init_rot"]), 3, 150, [1.0, 1.0, 1.0], d_rotationAnglesUnknowns=grot, d_translationUnknowns=gtrans)
+
+    def step(f, e2e):
+        cur = f % B
+        if e2e:   # host -> device of the incoming frame (pinned), the call a user makes hands HOST buffers
+            dlist[cur].copy_(h_depth[cur], non_blocking=True); clist[cur].copy_(h_color[cur], non_blocking=True)
+        if world > 1:     # the sensor frame lives on rank 0: broadcast over NVLink, every rank integrates its own shard
+            dist.broadcast(dlist[cur], 0); dist.broadcast(clist[cur], 0)
+        scene.runPackedOps(packed_ops[f], packed_frames, cam)
+        if f % WORKLOAD["chunk"] == WORKLOAD["chunk"] - 1:
+            ba()
+            if e2e:
+                h_grot.copy_(grot, non_blocking=True); h_gtrans.copy_(gtrans, non_blocking=True)
+        if e2e:
+            h_heap.copy_(scene.d_heapCounter, non_blocking=True)
+
+    def timed(n_steps, f0, e2e, profile):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            L.bfTsdfSetProfiling(1)
+        l0 = L.bfGetLaunchCount()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for f in range(f0, f0 + n_steps):
+            step(f, e2e)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item()); dist.barrier()
+        return ms, L.bfGetLaunchCount() - l0
+
+    K, Wm = args.steps, args.warmup
+    timed(Wm, 0, False, False)
+    clk_lines, stop_evt = [], threading.Event()
+    th = threading.Thread(target=clocks_sampler, args=(stop_evt, clk_lines, local), daemon=True); th.start()
+    ms, launches = timed(K, Wm, False, False)
+    stop_evt.set()
+    # separate pass with CUDA events around every stencil launch (the events cost a little, so it is not the headline run)
+    total_needed = Wm + 3 * K
+    while len(packed_ops) < total_needed:
+        packed_ops.append(scene.packOps(wl.step_ops(len(packed_ops), n_re)))
+    timed(K, Wm + 2 * K, False, True)
+    prof = (ctypes.c_ulonglong * 8)()
+    capi.check(L.bfTsdfGetProfile(ctypes.byref(scene.m_hashData), prof), "bfTsdfGetProfile")
+    L.bfTsdfSetProfiling(0)
+    ms_e2e, _ = timed(K, Wm + K, True, False)
+    stats = scene.getLastFrameStats()
+    heap_free = scene.getHeapFreeCount()
+    sg = sol_g.getStats()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, peak_kind = measured_peaks()
+    n_launch, n_timed, ns, U, E = int(prof[0]), int(prof[1]), int(prof[2]), int(prof[3]), int(prof[4])
+    alg_bytes = 24.0 * U + 20.0 * E + n_launch * 2.0 * W * H * 4.0            # 24 B x U + E x 20 B + 2 x W x H x 4 B per launch
+    ach = (alg_bytes * (n_timed / max(1, n_launch))) / max(1e-9, ns * 1e-9) / 1e9 if n_timed else 0.0
+    roof = {"kernel": "integrate_kernel<deIntegrate> (TSDF stencil)", "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"],
+            "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
+            "traffic": None, "launches": n_launch, "avg_launch_us": round(ns / max(1, n_timed) / 1e3, 2),
+            "algorithmic_bytes_per_launch": round(alg_bytes / max(1, n_launch)), "U_per_launch": round(U / max(1, n_launch)), "E_per_launch": round(E / max(1, n_launch))}
+    bytes_in = (W * H * 4 * 2)
+    bytes_out = 4 + (6 * 4 * len(glo["init_rot"])) / WORKLOAD["chunk"]
+    out = {
+        "metric": METRIC, "value": round(K / (ms / 1e3), 2), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(WORKLOAD, parallelism=("single GPU" if world == 1 else f"voxel hash sharded over {world} GPUs by block owner; frame broadcast (NCCL) per step; BA replicated"),
+                       active_blocks=int(WORKLOAD["sdf_blocks"] - heap_free), in_frustum_blocks_last=int(stats["E"]), global_pcg_iters=int(sg["pcg"]), global_gn_iters=int(sg["gn"])),
+        "e2e": {"value": round(K / (ms_e2e / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": int(bytes_out),
+                "note": "incoming frame copied from pinned host memory every step; re-integrated frames come from the device-resident frame store"},
+        "gpu_launches": int(launches), "roofline": roof, "clocks": summarize_clocks(clk_lines),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_arm(1, 0, quiet=True, n_reint=2)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+def cpu_arm(steps, warmup, quiet=False, n_reint=None):
+    """The reference's algorithm on the host cores: oracle port (liboracle_fast.so: -O3 -march=native, OpenMP over blocks for the
+    integrate stencil; alloc / compactify / solver single-threaded as restated).  The heap is sized for the sample (400k blocks)
+    instead of 4M to keep host memory modest; work per step is unchanged."""
+    from bundlefusion_b200 import synth
+    from bundlefusion_b200.scene_rep import camera_params, default_hash_params
+    from oracle import oracle as orc
+    orc.build()
+    cam = camera_params(W, H)
+    hp = default_hash_params(num_buckets=WORKLOAD["hash_buckets"], num_sdf_blocks=400000, voxel_size=WORKLOAD["voxel_m"])
+    n_re = WORKLOAD["reintegrations_per_frame"] if n_reint is None else n_reint
+    B = 12
+    frames = [synth.make_frame(8 * i, W, H) for i in range(B)]
+    scene = orc.OracleSceneRepHashSDF(hp, fast=True)
+    for d, c, T in frames:
+        scene.integrate(T, d, c, cam)
+    wl = Workload([f[2] for f in frames])
+    loc, glo = make_ba_problems()
+    def ba():
+        orc.solve_sparse(loc["corr"], loc["init_rot"], loc["init_trans"], 2, 100, fast=True)
+        orc.solve_sparse(glo["corr"], glo["init_rot"], glo["init_trans"], 3, 150, fast=True)
+    def step(f, with_ba):
+        for kind, r, pose in wl.step_ops(f, n_re):
+            if kind == 2: scene.garbageCollect()
+            elif kind == 1: scene.deIntegrate(pose, frames[r][0], frames[r][1], cam)
+            else: scene.integrate(pose, frames[r][0], frames[r][1], cam)
+        if with_ba:
+            ba()
+    for f in range(warmup):
+        step(f, False)
+    t0 = time.perf_counter()
+    for f in range(warmup, warmup + steps):
+        step(f, False)
+    t_tsdf = (time.perf_counter() - t0) / steps
+    t0 = time.perf_counter(); ba(); t_ba = time.perf_counter() - t0
+    # scale the TSDF part to the full 10 re-integrations per frame if a reduced sample was timed
+    passes_timed, passes_full = 2 * n_re + 1, 2 * WORKLOAD["reintegrations_per_frame"] + 1
+    per_frame = t_tsdf * passes_full / passes_timed + t_ba / WORKLOAD["chunk"]
+    cores = os.cpu_count() or 1
+    return {"value": round(1.0 / per_frame, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} frame(s) x ({n_re} re-integrations + 1 integrate + GC) at 640x480 scaled to {WORKLOAD['reintegrations_per_frame']} re-integrations, "
+                      f"+ 1 local and 1 global BA solve / {WORKLOAD['chunk']} frames; TSDF {t_tsdf:.2f} s per sampled frame, BA {t_ba:.2f} s per chunk; "
+                      f"OpenMP threads = {cores} on the integrate stencil, other stages single-threaded as restated"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, Wm = max(1, min(args.steps, 6)), min(args.warmup, 1)
+    t0 = time.perf_counter()
+    base = cpu_arm(K, Wm, n_reint=WORKLOAD["reintegrations_per_frame"])
+    wall = time.perf_counter() - t0
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": K, "warmup": Wm, "ms_per_step": round(1e3 / base["value"], 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, note="CPU arm: oracle port of the reference algorithm (the reference ships no CPU path and its CUDA does not build here)"),
+           "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": round(wall, 1)}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

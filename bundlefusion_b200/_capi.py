@@ -100,7 +100,7 @@ TSDF_SYMBOLS = [
     "garbageCollectIdentifyCUDA", "garbageCollectFreeCUDA",
     "bfSetStream", "bfGetStream", "bfGetLastErrorString", "bfTsdfAuxBytes", "bfTsdfReset", "bfTsdfIntegrateFrame",
     "bfTsdfGarbageCollect", "bfTsdfGetHeapFreeCount", "bfTsdfGetNumOccupiedBlocks", "bfTsdfGetLastFrameStats",
-    "bfTsdfReleaseAux",
+    "bfTsdfReleaseAux", "bfGetLaunchCount", "bfTsdfSetProfiling", "bfTsdfGetProfile",
 ]
 
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
@@ -216,6 +216,9 @@ def lib() -> C.CDLL:
     L.bfTsdfGetNumOccupiedBlocks.argtypes = [P(BFHashDataStruct), P(C.c_uint)]
     L.bfTsdfGetLastFrameStats.argtypes = [P(BFHashDataStruct), C.c_ulonglong * 4]
     L.bfTsdfReleaseAux.argtypes = [P(BFHashDataStruct)]
+    L.bfGetLaunchCount.restype = C.c_ulonglong
+    L.bfTsdfSetProfiling.argtypes = [C.c_int]
+    L.bfTsdfGetProfile.argtypes = [P(BFHashDataStruct), C.c_ulonglong * 8]
     L.bfMat4Inverse.argtypes = [P(C.c_float), P(C.c_float)]
     L.bfMat4Inverse.restype = None
     L.bfTsdfRunOps.argtypes = [P(BFHashDataStruct), P(BFHashParams), P(BFDepthCameraParams), P(BFTsdfOp), C.c_int, P(vp), P(vp)]

@@ -28,6 +28,8 @@ namespace cg = cooperative_groups;
 
 namespace bf {
 
+extern unsigned long long g_launchCount;      // defined in tsdf.cu (bfGetLaunchCount)
+
 #define BF_FLOAT_EPSILON 0.000001f      // FL/SolverUtil.h:9
 #define BF_MAX_ROW 8192                 // longest variable row the in-smem row sort handles
 #define BF_SOLVER_THREADS 256
@@ -342,9 +344,18 @@ __device__ __forceinline__ float block_sum(float v, float* sRed) {
     __syncthreads();
     return tot;
 }
-__device__ __forceinline__ float grid_sum_after_sync(const float* partials, unsigned grid) {
-    float tot = 0.0f;
-    for (unsigned b = 0; b < grid; ++b) tot += __ldcg(&partials[b]);
+// every CTA evaluates the same fixed-shape sum of the per-CTA partials: lane l adds partials[l], [l+32], ... in order, then a
+// fixed shuffle tree -- one L2 round trip instead of gridDim.x dependent ones, and identical bits in every CTA
+__device__ __forceinline__ float grid_sum_after_sync(const float* partials, unsigned grid, float* sRed) {
+    if (threadIdx.x < 32) {
+        float v = 0.0f;
+        for (unsigned b = threadIdx.x; b < grid; b += 32) v += __ldcg(&partials[b]);
+        v = warp_sum(v);
+        if (threadIdx.x == 0) sRed[0] = v;
+    }
+    __syncthreads();
+    const float tot = sRed[0];
+    __syncthreads();
     return tot;
 }
 
@@ -460,7 +471,7 @@ gn_iteration_kernel(const GnArgs a) {
     part = block_sum(part, sRed);
     if (threadIdx.x == 0) a.partials[a.maxGrid + blockIdx.x] = part;      // second array: the first is rewritten by PCG step A
     grid.sync();
-    float rDotzOld = grid_sum_after_sync(a.partials + a.maxGrid, gridDim.x);
+    float rDotzOld = grid_sum_after_sync(a.partials + a.maxGrid, gridDim.x, sRed);
 
     // (3) PCG iterations (SolverBundling.cu:1024-1108): rows are dealt to warps; lanes split a row's segments
     const unsigned warpsPerBlock = blockDim.x / 32, gwarp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nwarps = gridDim.x * warpsPerBlock;
@@ -491,7 +502,7 @@ gn_iteration_kernel(const GnArgs a) {
         pAp = block_sum(pAp, sRed);
         if (threadIdx.x == 0) a.partials[blockIdx.x] = pAp;
         grid.sync();
-        const float dotProduct = grid_sum_after_sync(a.partials, gridDim.x);
+        const float dotProduct = grid_sum_after_sync(a.partials, gridDim.x, sRed);
         // B: step, residual, preconditioned residual, partial z.r
         float alpha = 0.0f;
         if (dotProduct > BF_FLOAT_EPSILON) alpha = rDotzOld / dotProduct;
@@ -509,7 +520,7 @@ gn_iteration_kernel(const GnArgs a) {
         zr = block_sum(zr, sRed);
         if (threadIdx.x == 0) a.partials[a.maxGrid + blockIdx.x] = zr;
         grid.sync();
-        const float rDotzNew = grid_sum_after_sync(a.partials + a.maxGrid, gridDim.x);
+        const float rDotzNew = grid_sum_after_sync(a.partials + a.maxGrid, gridDim.x, sRed);
         if (fabsf(dotProduct) < 5e-7f) last = true;                     // ENABLE_EARLY_OUT (:1088-1093)
         // C: new direction (+ Lie update on the last iteration, LieDerivUtil.h:301-307)
         float beta = 0.0f;
@@ -667,6 +678,7 @@ static int run_prep(const BFSolverInput* in, const BFSolverState* st, SolverWs* 
     if (C > 0) prep_count_kernel<<<(C + 255) / 256, 256, 0, stream()>>>(in->d_correspondences, C, ws->rowCount);
     prep_scan_kernel<<<1, 1024, 0, stream()>>>(ws->rowCount, ws->rowStart, ws->cursor, in->d_numEntriesPerRow, N, ws->scal);
     if (C > 0) prep_scatter_kernel<<<(C + 255) / 256, 256, 0, stream()>>>(in->d_correspondences, C, ws->rowStart, ws->cursor, ws->entries);
+    g_launchCount += (C > 0 ? 4 : 2);
     static bool attrSet = false;
     if (!attrSet) { BF_CHECK(cudaFuncSetAttribute(prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_MAX_ROW * 8)); attrSet = true; }
     prep_rows_kernel<<<N, 256, BF_MAX_ROW * 8, stream()>>>(in->d_correspondences, ws->rowStart, ws->entries, ws->segCount, ws->segs,
@@ -699,6 +711,7 @@ static int run_gn(const BFSolverInput* in, const BFSolverState* st, const BFSolv
     if (grid > ws->maxGrid) grid = ws->maxGrid;
     if (grid < 1) grid = 1;
     void* args[] = { (void*)&a };
+    ++g_launchCount;
     BF_CHECK(cudaLaunchCooperativeKernel((void*)gn_iteration_kernel, dim3(grid), dim3(BF_SOLVER_THREADS), args, 0, stream()));
     return 0;
 }

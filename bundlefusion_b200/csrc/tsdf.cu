@@ -21,6 +21,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/bf_tsdf.h"
 #include "bf_common.cuh"
@@ -52,7 +53,15 @@ struct TsdfAux {
     unsigned numSlots = 0;
     unsigned parity = 0;             // which of the two compactify counters is live
 };
-enum { CTR_HIGH_WATER = 0, CTR_COUNT0 = 1, CTR_COUNT1 = 2, CTR_E = 3, CTR_CULLED = 4, CTR_U_LO = 6, CTR_U_HI = 7, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROPPED = 10, CTR_NUM = 16 };
+enum { CTR_HIGH_WATER = 0, CTR_COUNT0 = 1, CTR_COUNT1 = 2, CTR_E = 3, CTR_CULLED = 4, CTR_U_LO = 6, CTR_U_HI = 7, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROPPED = 10, CTR_U_TOT_LO = 12, CTR_U_TOT_HI = 13, CTR_E_TOT_LO = 14, CTR_E_TOT_HI = 15, CTR_NUM = 16 };
+
+// launch accounting + optional CUDA-event timing of the integrate / de-integrate stencil (bench.py's roofline line)
+unsigned long long g_launchCount = 0;
+static bool g_profile = false;
+static std::vector<cudaEvent_t> g_evStart, g_evStop;
+static size_t g_evUsed = 0;
+static unsigned long long g_profLaunches = 0;
+static const size_t kMaxProfiledLaunches = 16384;
 
 static std::mutex g_auxMutex;
 static std::map<const void*, TsdfAux> g_aux;
@@ -317,6 +326,15 @@ __device__ __forceinline__ I3 unpack_block_key(unsigned long long key) {
     return b;
 }
 
+// Multi-GPU spatial shard: when hp.m_dummy = {rank, world} with world > 1, this device allocates
+// (and therefore integrates) only the blocks it owns; owner(pos) is a hash independent of the bucket hash.
+__device__ __forceinline__ bool owns_block(const BFHashParams& hp, I3 b) {
+    const unsigned world = hp.m_dummy[1];
+    if (world <= 1) return true;
+    const unsigned mix = ((unsigned)b.x * 73856093u) ^ ((unsigned)b.y * 19349669u) ^ ((unsigned)b.z * 83492791u);
+    return ((mix * 0x9E3779B1u) >> 8) % world == hp.m_dummy[0];
+}
+
 struct DDA {                    // state of one pixel's block walk (.cu:189-219)
     I3 cur, bound;
     F3 step, tMax, tDelta;
@@ -382,7 +400,7 @@ __device__ __noinline__ void alloc_pixel_direct(const BFHashDataStruct& hd, cons
     if (!dda_setup(hp, cp, depth, x, y, s)) return;
 #pragma unroll 1
     for (unsigned iter = 0; iter < 1024; ++iter) {
-        if (block_in_frustum(hp, cp, s.cur)) alloc_block(hd, hp, slotInfo, ctrs, s.cur);
+        if (block_in_frustum(hp, cp, s.cur) && owns_block(hp, s.cur)) alloc_block(hd, hp, slotInfo, ctrs, s.cur);
         int axis;
         if (!dda_step(s, axis)) return;
     }
@@ -445,7 +463,7 @@ alloc_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const
         const unsigned long long key = sSet[i];
         if (key == 0ull) continue;
         const I3 b = unpack_block_key(key);
-        if (block_in_frustum(hp, cp, b)) alloc_block(hd, hp, slotInfo, ctrs, b);
+        if (block_in_frustum(hp, cp, b) && owns_block(hp, b)) alloc_block(hd, hp, slotInfo, ctrs, b);
     }
     if (needDirect) alloc_pixel_direct(hd, hp, cp, depth, x, y, slotInfo, ctrs);   // set overflow / coordinates out of key range
 }
@@ -556,7 +574,10 @@ integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, c
                  const float* __restrict__ depthImg, const uchar4* __restrict__ colorImg,
                  const unsigned* __restrict__ countPtr, unsigned countOverride, unsigned* ctrs, int* __restrict__ live) {
     const unsigned count = countPtr ? *countPtr : countOverride;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && countPtr) { hd.d_hashCompactifiedCounter[0] = (int)count; ctrs[CTR_E] = count; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (countPtr) { hd.d_hashCompactifiedCounter[0] = (int)count; ctrs[CTR_E] = count; }
+        atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_E_TOT_LO]), (unsigned long long)count);
+    }
     const unsigned t = threadIdx.x;
     const unsigned W = cp.m_imageWidth, H = cp.m_imageHeight;
     // local voxel coordinates of this thread's first voxel: i = 4t -> x = (4t)%8, y = (4t%64)/8, z = 4t/64
@@ -622,7 +643,7 @@ integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, c
     __syncthreads();
     if (t == 0) {
         const unsigned long long tot = (unsigned long long)sPassed[0] + sPassed[1] + sPassed[2] + sPassed[3];
-        if (tot) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot);
+        if (tot) { atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot); atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_TOT_LO]), tot); }
     }
 }
 
@@ -777,7 +798,7 @@ integrate_tma_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams h
     asm volatile("bar.sync 1, 128;" ::: "memory");          // consumers only (the producer warp has left)
     if (t == 0) {
         const unsigned long long tot = (unsigned long long)sPassed[0] + sPassed[1] + sPassed[2] + sPassed[3];
-        if (tot) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot);
+        if (tot) { atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot); atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_TOT_LO]), tot); }
     }
 }
 
@@ -988,6 +1009,7 @@ static int do_reset(BFHashDataStruct* hd, const BFHashParams* hp) {
 static int do_alloc(BFHashDataStruct* hd, const BFHashParams* hp, const float* depth, const BFDepthCameraParams* cp, TsdfAux* aux) {
     dim3 block(16, 16);   // = BF_ALLOC_CACHE threads
     dim3 grid((cp->m_imageWidth + block.x - 1) / block.x, (cp->m_imageHeight + block.y - 1) / block.y);
+    ++g_launchCount;
     alloc_kernel<<<grid, block, 0, g_stream>>>(*hd, *hp, *cp, depth, aux->slotInfo, aux->ctrs);
     BF_CHECK(cudaGetLastError());
     return 0;
@@ -997,6 +1019,7 @@ static int do_compactify(BFHashDataStruct* hd, const BFHashParams* hp, const BFD
     aux->parity ^= 1u;
     const int countIdx = aux->parity ? CTR_COUNT1 : CTR_COUNT0;
     const int otherIdx = aux->parity ? CTR_COUNT0 : CTR_COUNT1;
+    ++g_launchCount;
     compactify_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, *hp, *cp, aux->slotInfo, aux->ctrs, countIdx, otherIdx);
     BF_CHECK(cudaGetLastError());
     return 0;
@@ -1011,6 +1034,13 @@ static int do_integrate(BFHashDataStruct* hd, const BFHashParams* hp, const BFDe
     const uchar4* color = reinterpret_cast<const uchar4*>(dd->d_colorData);
     static int variant = -1;        // BF_TSDF_INTEGRATE=tma selects the TMA-staged variant (measured slower)
     if (variant < 0) { const char* e = getenv("BF_TSDF_INTEGRATE"); variant = (e && e[0] == 't') ? 1 : 0; }
+    const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
+    if (g_profile) ++g_profLaunches;
+    if (timeIt) {
+        if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
+        BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], g_stream));
+    }
+    ++g_launchCount;
     if (variant == 0) {
         const int grid = grid_for(upper, 16);
         if (deIntegrate) integrate_kernel<true><<<grid, 128, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live);
@@ -1021,6 +1051,7 @@ static int do_integrate(BFHashDataStruct* hd, const BFHashParams* hp, const BFDe
         else             integrate_tma_kernel<false><<<grid, 160, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live);
     }
     BF_CHECK(cudaGetLastError());
+    if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], g_stream)); ++g_evUsed; }
     return 0;
 }
 
@@ -1053,6 +1084,7 @@ BF_API int bfTsdfGarbageCollect(BFHashDataStruct* hd, const BFHashParams* hp) {
     TsdfAux* aux;
     int rc = get_aux(hd, hp, &aux, true);
     if (rc) return rc;
+    ++g_launchCount;
     if (aux->liveValid) gc_live_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 2), 256, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs, aux->live);
     else                gc_fused_kernel<<<grid_for(hp->m_numSDFBlocks, 16), 128, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs);
     BF_CHECK(cudaGetLastError());
@@ -1086,6 +1118,37 @@ BF_API int bfTsdfGetLastFrameStats(const BFHashDataStruct* hd, unsigned long lon
     out[1] = c[CTR_CULLED];
     out[2] = ((unsigned long long)c[CTR_U_HI] << 32) | c[CTR_U_LO];
     out[3] = (unsigned long long)c[CTR_HEAP_FAIL] + c[CTR_DROPPED];
+    return 0;
+}
+
+BF_API unsigned long long bfGetLaunchCount(void) { return g_launchCount; }
+
+BF_API int bfTsdfSetProfiling(int enable) {
+    g_profile = enable != 0;
+    g_evUsed = 0; g_profLaunches = 0;
+    std::lock_guard<std::mutex> lk(g_auxMutex);
+    for (auto& kv : g_aux) BF_CHECK(cudaMemsetAsync(kv.second.ctrs + CTR_U_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));   // restart the U / E sums
+    return 0;
+}
+
+// out[0] = stencil launches since bfTsdfSetProfiling(1), out[1] = launches that were timed, out[2] = their summed duration in ns,
+// out[3] = sum of U (voxels rewritten) over ALL launches since the last reset, out[4] = sum of E (blocks visited).  Synchronises.
+BF_API int bfTsdfGetProfile(const BFHashDataStruct* hd, unsigned long long out[8]) {
+    TsdfAux* aux;
+    int rc = get_aux(hd, nullptr, &aux, false);
+    if (rc) return rc;
+    BF_CHECK(cudaStreamSynchronize(g_stream));
+    double ms = 0.0;
+    for (size_t i = 0; i < g_evUsed; ++i) { float t = 0.0f; BF_CHECK(cudaEventElapsedTime(&t, g_evStart[i], g_evStop[i])); ms += t; }
+    unsigned c[CTR_NUM];
+    BF_CHECK(cudaMemcpy(c, aux->ctrs, sizeof(c), cudaMemcpyDeviceToHost));
+    out[0] = g_profLaunches; out[1] = g_evUsed; out[2] = (unsigned long long)(ms * 1e6);
+    out[3] = ((unsigned long long)c[CTR_U_TOT_HI] << 32) | c[CTR_U_TOT_LO];
+    out[4] = ((unsigned long long)c[CTR_E_TOT_HI] << 32) | c[CTR_E_TOT_LO];
+    out[5] = out[6] = out[7] = 0;
+    // restart accumulation
+    BF_CHECK(cudaMemsetAsync(aux->ctrs + CTR_U_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
+    g_evUsed = 0; g_profLaunches = 0;
     return 0;
 }
 

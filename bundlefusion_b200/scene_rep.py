@@ -194,18 +194,28 @@ class CUDASceneRepHashSDF:
     def runOps(self, ops, depth_frames, color_frames, cam: BFDepthCameraParams):
         """Replay a list of (kind, frame, pose) TSDF operations in ONE library call (bfTsdfRunOps): the re-integration
         batch of DepthSensing.cpp:854-902 without a Python round trip per operation.  Asynchronous."""
-        self._bind_stream()
+        self.runPackedOps(self.packOps(ops), self.packFrames(depth_frames, color_frames), cam)
+
+    @staticmethod
+    def packOps(ops):
+        """(kind, frame, pose) tuples -> BFTsdfOp array (host-side preparation, reusable)."""
         arr = (capi.BFTsdfOp * len(ops))()
         for i, (kind, frame, pose) in enumerate(ops):
             arr[i].kind, arr[i].frame = kind, frame
             if pose is not None:
-                flat = np.asarray(pose, dtype=np.float32).reshape(16)
-                for k in range(16):
-                    arr[i].pose[k] = float(flat[k])
+                C.memmove(arr[i].pose, np.ascontiguousarray(pose, dtype=np.float32).ctypes.data, 64)
+        return arr
+
+    @staticmethod
+    def packFrames(depth_frames, color_frames):
         dptr = (C.c_void_p * len(depth_frames))(*[t.data_ptr() for t in depth_frames])
         cptr = (C.c_void_p * len(color_frames))(*[t.data_ptr() for t in color_frames])
-        self._op_keepalive = (arr, dptr, cptr)
-        capi.check(self.lib.bfTsdfRunOps(C.byref(self.m_hashData), C.byref(self.m_hashParams), C.byref(cam), arr, len(ops), dptr, cptr),
+        return (dptr, cptr)
+
+    def runPackedOps(self, arr, frames, cam: BFDepthCameraParams):
+        self._bind_stream()
+        self._op_keepalive = (arr, frames)
+        capi.check(self.lib.bfTsdfRunOps(C.byref(self.m_hashData), C.byref(self.m_hashParams), C.byref(cam), arr, len(arr), frames[0], frames[1]),
                    "bfTsdfRunOps")
 
     def getHashData(self) -> BFHashDataStruct:

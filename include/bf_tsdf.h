@@ -202,6 +202,15 @@ int bfTsdfGetNumOccupiedBlocks(const BFHashDataStruct* hashData, unsigned int* o
  * (heap exhausted or no free entry inside the probe window; 0 in a sanely sized table).  Synchronises. */
 int bfTsdfGetLastFrameStats(const BFHashDataStruct* hashData, unsigned long long out[4]);
 
+/* measurement hooks used by bench.py (never needed for correctness):
+ * bfGetLaunchCount   -- kernels this library has launched since load (all paths);
+ * bfTsdfSetProfiling -- when enabled every integrate / de-integrate stencil launch is bracketed by CUDA events on the library stream;
+ * bfTsdfGetProfile   -- out[0] stencil launches, out[1] launches timed, out[2] their summed duration (ns), out[3] sum of U,
+ *                       out[4] sum of E over those launches; synchronises and restarts the accumulation. */
+unsigned long long bfGetLaunchCount(void);
+int bfTsdfSetProfiling(int enable);
+int bfTsdfGetProfile(const BFHashDataStruct* hashData, unsigned long long out[8]);
+
 /* release the library-private scratch attached to this hash (call before freeing d_hash) */
 int bfTsdfReleaseAux(const BFHashDataStruct* hashData);
 
