@@ -100,7 +100,7 @@ TSDF_SYMBOLS = [
     "garbageCollectIdentifyCUDA", "garbageCollectFreeCUDA",
     "bfSetStream", "bfGetStream", "bfGetLastErrorString", "bfTsdfAuxBytes", "bfTsdfReset", "bfTsdfIntegrateFrame",
     "bfTsdfGarbageCollect", "bfTsdfGetHeapFreeCount", "bfTsdfGetNumOccupiedBlocks", "bfTsdfGetLastFrameStats",
-    "bfTsdfReleaseAux", "bfGetLaunchCount", "bfTsdfSetProfiling", "bfTsdfGetProfile",
+    "bfTsdfReleaseAux", "bfTsdfReintegrateFrame", "bfGetLaunchCount", "bfTsdfSetProfiling", "bfTsdfGetProfile",
 ]
 
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
@@ -216,6 +216,7 @@ def lib() -> C.CDLL:
     L.bfTsdfGetNumOccupiedBlocks.argtypes = [P(BFHashDataStruct), P(C.c_uint)]
     L.bfTsdfGetLastFrameStats.argtypes = [P(BFHashDataStruct), C.c_ulonglong * 4]
     L.bfTsdfReleaseAux.argtypes = [P(BFHashDataStruct)]
+    L.bfTsdfReintegrateFrame.argtypes = [P(BFHashDataStruct), P(BFHashParams), P(BFHashParams), P(BFDepthCameraData), P(BFDepthCameraParams)]
     L.bfGetLaunchCount.restype = C.c_ulonglong
     L.bfTsdfSetProfiling.argtypes = [C.c_int]
     L.bfTsdfGetProfile.argtypes = [P(BFHashDataStruct), C.c_ulonglong * 8]

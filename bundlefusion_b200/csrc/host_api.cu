@@ -37,8 +37,26 @@ BF_API void bfMat4Inverse(const float* m, float* out) {
 
 BF_API int bfTsdfRunOps(BFHashDataStruct* hd, BFHashParams* hp, const BFDepthCameraParams* cam, const BFTsdfOp* ops, int numOps,
                         const float* const* d_depthFrames, const uint8_t* const* d_colorFrames) {
+    static int fuse = -1;        // BF_TSDF_FUSE_REINT=0 replays every op separately (A/B measurements)
+    if (fuse < 0) { const char* e = getenv("BF_TSDF_FUSE_REINT"); fuse = (e && e[0] == '0') ? 0 : 1; }
     for (int i = 0; i < numOps; ++i) {
         const BFTsdfOp& op = ops[i];
+        if (fuse && op.kind == BF_TSDF_OP_DEINTEGRATE && i + 1 < numOps && ops[i + 1].kind == BF_TSDF_OP_INTEGRATE && ops[i + 1].frame == op.frame) {
+            // the reference's re-integration pair: one fused pass (bfTsdfReintegrateFrame)
+            BFHashParams hpOld = *hp;
+            for (int k = 0; k < 16; ++k) hpOld.m_rigidTransform.m[k] = op.pose[k];
+            bfMat4Inverse(op.pose, hpOld.m_rigidTransformInverse.m);
+            const BFTsdfOp& nx = ops[i + 1];
+            for (int k = 0; k < 16; ++k) hp->m_rigidTransform.m[k] = nx.pose[k];
+            bfMat4Inverse(nx.pose, hp->m_rigidTransformInverse.m);
+            BFDepthCameraData dd;
+            dd.d_depthData = d_depthFrames[op.frame];
+            dd.d_colorData = d_colorFrames ? d_colorFrames[op.frame] : nullptr;
+            int rc = bfTsdfReintegrateFrame(hd, &hpOld, hp, &dd, cam);
+            if (rc) return rc;
+            ++i;
+            continue;
+        }
         if (op.kind == BF_TSDF_OP_GARBAGE_COLLECT) {
             int rc = bfTsdfGarbageCollect(hd, hp);
             if (rc) return rc;

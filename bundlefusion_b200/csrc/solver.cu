@@ -359,10 +359,20 @@ __device__ __forceinline__ float grid_sum_after_sync(const float* partials, unsi
     return tot;
 }
 
-__global__ void __launch_bounds__(BF_SOLVER_THREADS)
+// kCluster = false: cooperative launch, cg grid barrier (any N).  kCluster = true: ONE thread-block cluster of <= 16 CTAs x 1024
+// threads, hardware cluster barrier (~0.4 us instead of ~3 us) -- the PCG of a <= few-thousand-image problem is barrier-bound.
+template <bool kCluster>
+struct GridBarrier {
+    __device__ __forceinline__ void sync() const {
+        if (kCluster) { __threadfence(); cg::this_cluster().sync(); } else cg::this_grid().sync();
+    }
+};
+
+template <bool kCluster, int kThreads>
+__global__ void __launch_bounds__(kThreads)
 gn_iteration_kernel(const GnArgs a) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ float sRed[BF_SOLVER_THREADS / 32];
+    GridBarrier<kCluster> grid;
+    __shared__ float sRed[32];
     if (__ldcg(&a.scal[SC_DONE]) != 0) return;                 // an earlier GN iteration converged (uniform for the grid)
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const unsigned N = a.N;
@@ -382,9 +392,10 @@ gn_iteration_kernel(const GnArgs a) {
     //     H_vo = -w G_v^T G_o and the row's diagonal / rhs moments, G(P) = [-[P]x | I], P = T * p.
     {
         // segments are addressed through their row: flatten (row, local segment) over the grid
-        for (unsigned v = blockIdx.x; v < N; v += gridDim.x) {
+        const unsigned gw = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x / 32);
+        for (unsigned v = gw; v < N; v += nw) {                      // a warp per row, lanes over the row's segments
             const int ns = a.segCount[v], rs = a.rowStart[v];
-            for (int sI = threadIdx.x; sI < ns; sI += blockDim.x) {
+            for (int sI = threadIdx.x & 31; sI < ns; sI += 32) {
                 const Segment sg = a.segs[rs + sI];
                 float nCnt = 0.0f, sumPP = 0.0f, sPvPo = 0.0f;
                 V3 sPv = mk(0, 0, 0), sPo = mk(0, 0, 0), gRot = mk(0, 0, 0);
@@ -698,11 +709,45 @@ static int run_gn(const BFSolverInput* in, const BFSolverState* st, const BFSolv
     a.rowStart = ws->rowStart; a.entries = ws->entries; a.segCount = ws->segCount; a.segs = ws->segs;
     a.offBlk = ws->offBlk; a.segMom = ws->segMom; a.diagBlk = ws->diagBlk; a.partials = ws->partials; a.scal = ws->scal;
     a.wSparse = in->weightsSparse[nIter]; a.nLin = par->nLinIterations; a.isLastGn = isLast ? 1 : 0; a.maxGrid = ws->maxGrid;
-    // grid: enough CTAs to give every row a warp, never more than are co-resident
+    void* args[] = { (void*)&a };
+    ++g_launchCount;
+    // Path 1: one thread-block cluster (hardware barrier).  Chosen when a cluster's warps cover the rows within ~8 rows per warp.
+    static int clusterCap = -1;             // largest launchable cluster size for the 1024-thread variant (0 = unavailable)
+    static int variant = -1;                // BF_SOLVER_BARRIER=cluster selects the cluster variant (measured slower: 20.6 vs 12.8 us per
+                                            // PCG iteration at N = 500 -- the iteration is L2-latency-bound, not barrier-bound, and 16 SMs
+                                            // give it less memory parallelism than 63); default is the cooperative grid
+    if (variant < 0) { const char* e = getenv("BF_SOLVER_BARRIER"); variant = (e && e[0] == 'c') ? 1 : 0; }
+    if (clusterCap < 0) {
+        clusterCap = 0;
+        auto kern = gn_iteration_kernel<true, 1024>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            for (int cs = 16; cs >= 2; cs >>= 1) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(cs); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0;
+                cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = cs; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+                cfg.attrs = &at; cfg.numAttrs = 1;
+                int nClusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nClusters, kern, &cfg) == cudaSuccess && nClusters >= 1) { clusterCap = cs; break; }
+            }
+        }
+        (void)cudaGetLastError();
+    }
+    if (variant == 1 && clusterCap >= 2 && a.N <= (unsigned)clusterCap * 32u * 8u) {
+        int cs = 2;
+        while (cs < clusterCap && (unsigned)cs * 32u < a.N) cs <<= 1;          // one row per warp when possible
+        if (a.N <= 32) cs = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = stream();
+        cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = cs; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        BF_CHECK(cudaLaunchKernelEx(&cfg, gn_iteration_kernel<true, 1024>, a));
+        return 0;
+    }
+    // Path 2: cooperative grid, enough CTAs to give every row a warp, never more than are co-resident
     static int maxCoResident = 0;
     if (!maxCoResident) {
         int perSm = 0;
-        BF_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, gn_iteration_kernel, BF_SOLVER_THREADS, 0));
+        BF_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, gn_iteration_kernel<false, BF_SOLVER_THREADS>, BF_SOLVER_THREADS, 0));
         maxCoResident = perSm * num_sms();
     }
     int grid = (int)((a.N + (BF_SOLVER_THREADS / 32) - 1) / (BF_SOLVER_THREADS / 32));
@@ -710,9 +755,7 @@ static int run_gn(const BFSolverInput* in, const BFSolverState* st, const BFSolv
     if (grid > maxCoResident) grid = maxCoResident;
     if (grid > ws->maxGrid) grid = ws->maxGrid;
     if (grid < 1) grid = 1;
-    void* args[] = { (void*)&a };
-    ++g_launchCount;
-    BF_CHECK(cudaLaunchCooperativeKernel((void*)gn_iteration_kernel, dim3(grid), dim3(BF_SOLVER_THREADS), args, 0, stream()));
+    BF_CHECK(cudaLaunchCooperativeKernel((void*)gn_iteration_kernel<false, BF_SOLVER_THREADS>, dim3(grid), dim3(BF_SOLVER_THREADS), args, 0, stream()));
     return 0;
 }
 

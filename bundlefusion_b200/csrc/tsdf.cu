@@ -49,9 +49,11 @@ struct TsdfAux {
     int4* slotInfo = nullptr;        // [numSDFBlocks] {bx,by,bz, entryIdx} ; entryIdx < 0: slot free
     unsigned* ctrs = nullptr;        // see CTR_* below
     int* live = nullptr;             // [numSDFBlocks] number of voxels with weight > 0 in the slot's block
+    unsigned char* listFlags = nullptr;   // [numSDFBlocks] per compactified entry: bit0 in old frustum, bit1 in new (fused re-integration)
     bool liveValid = false;          // false once something outside integrate/de-integrate changed weights
     unsigned numSlots = 0;
     unsigned parity = 0;             // which of the two compactify counters is live
+    bool lastListDual = false;       // the live list is a union list of a fused re-integration (GC then visits only its new-pose part)
 };
 enum { CTR_HIGH_WATER = 0, CTR_COUNT0 = 1, CTR_COUNT1 = 2, CTR_E = 3, CTR_CULLED = 4, CTR_U_LO = 6, CTR_U_HI = 7, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROPPED = 10, CTR_U_TOT_LO = 12, CTR_U_TOT_HI = 13, CTR_E_TOT_LO = 14, CTR_E_TOT_HI = 15, CTR_NUM = 16 };
 
@@ -802,6 +804,124 @@ integrate_tma_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams h
     }
 }
 
+// ---- fused re-integration: deIntegrate(old pose) + integrate(new pose) of ONE frame in one pass -------------------
+// The reference re-integrates a frame as two full passes (DepthSensing.cpp:867-895): compactify + stencil for the old pose,
+// alloc + compactify + stencil for the new one.  Each voxel's result depends only on its own state, so running "alloc(new),
+// then per voxel: de-integrate with the old pose, integrate with the new pose" in registers gives bit-identical voxels with one
+// voxel read + one write instead of two of each, and 3 launches instead of 5.
+__global__ void __launch_bounds__(256)
+compactify_dual_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hpOld, const __grid_constant__ BFHashParams hpNew,
+                       const __grid_constant__ BFDepthCameraParams cp, const int4* __restrict__ slotInfo, unsigned* ctrs, int countIdx, int otherIdx,
+                       unsigned char* __restrict__ listFlags) {
+    const unsigned highWater = ctrs[CTR_HIGH_WATER];
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid == 0) { ctrs[otherIdx] = 0; ctrs[CTR_CULLED] = 0; ctrs[CTR_U_LO] = 0; ctrs[CTR_U_HI] = 0; }
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned lane = threadIdx.x & 31;
+    for (unsigned base = tid - lane; base < highWater; base += stride) {
+        const unsigned slot = base + lane;
+        unsigned fl = 0;
+        int4 info = make_int4(0, 0, 0, -1);
+        if (slot < highWater) {
+            info = __ldcg(&slotInfo[slot]);
+            if (info.w >= 0) { I3 b = { info.x, info.y, info.z }; fl = (block_in_frustum(hpOld, cp, b) ? 1u : 0u) | (block_in_frustum(hpNew, cp, b) ? 2u : 0u); }
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, fl != 0);
+        if (ballot) {
+            unsigned warpBase = 0;
+            if (lane == 0) warpBase = atomicAdd(&ctrs[countIdx], __popc(ballot));
+            warpBase = __shfl_sync(0xffffffffu, warpBase, 0);
+            if (fl) {
+                const unsigned k = warpBase + __popc(ballot & ((1u << lane) - 1u));
+                BFHashEntry e;
+                e.pos[0] = info.x; e.pos[1] = info.y; e.pos[2] = info.z;
+                e.ptr = (int)(slot * BF_SDF_BLOCK_VOXELS);
+                e.offset = hd.d_hash[info.w].offset;
+                hd.d_hashCompactified[k] = e;
+                listFlags[k] = (unsigned char)fl;
+            }
+        }
+    }
+}
+
+// truncation test of one voxel against one pose; returns true and the clamped sdf / colour when it passes (.cu:433-463)
+__device__ __forceinline__ bool probe_voxel(const BFHashParams& hp, const BFDepthCameraParams& cp, const float* __restrict__ depthImg,
+                                            const uchar4* __restrict__ colorImg, I3 pi, float& sdfOut, uchar4& colOut) {
+    const F3 pf = xform(hp.m_rigidTransformInverse, voxel_to_world(hp, pi));
+    const float sx = pf.x * cp.fx / pf.z + cp.mx;
+    const float sy = pf.y * cp.fy / pf.z + cp.my;
+    const unsigned px = (unsigned)(int)(sx + 0.5f), py = (unsigned)(int)(sy + 0.5f);
+    if (!(px < cp.m_imageWidth && py < cp.m_imageHeight)) return false;
+    const float depth = __ldg(&depthImg[py * cp.m_imageWidth + px]);
+    if (!(depth != -INFINITY && depth < hp.m_maxIntegrationDistance)) return false;
+    float sdf = depth - pf.z;
+    const float trunc = truncation(hp, depth);
+    if (!(fabsf(sdf) < trunc)) return false;
+    sdfOut = (sdf >= 0.0f) ? fminf(trunc, sdf) : fmaxf(-trunc, sdf);
+    colOut = __ldg(&colorImg[py * cp.m_imageWidth + px]);
+    return true;
+}
+
+__global__ void __launch_bounds__(128)
+reintegrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hpOld, const __grid_constant__ BFHashParams hpNew,
+                   const __grid_constant__ BFDepthCameraParams cp, const float* __restrict__ depthImg, const uchar4* __restrict__ colorImg,
+                   const unsigned* __restrict__ countPtr, const unsigned char* __restrict__ listFlags, unsigned* ctrs, int* __restrict__ live) {
+    const unsigned count = *countPtr;
+    const unsigned t = threadIdx.x;
+    const int lx = (int)((4 * t) & 7), ly = (int)(((4 * t) & 63) >> 3), lz = (int)((4 * t) >> 6);
+    unsigned passed = 0, eBoth = 0;
+    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) {
+        const BFHashEntry* ep = &hd.d_hashCompactified[b];
+        const int bx = __ldg(&ep->pos[0]), by = __ldg(&ep->pos[1]), bz = __ldg(&ep->pos[2]);
+        const unsigned ptr = (unsigned)__ldg(&ep->ptr);
+        const unsigned fl = __ldg(&listFlags[b]);
+        if (t == 0) eBoth += (fl & 1u) + ((fl >> 1) & 1u);
+        float sdfD[4], sdfI[4];
+        uchar4 colD[4], colI[4];
+        unsigned maskD = 0, maskI = 0;
+        int liveDelta = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const I3 pi = { bx * BF_SDF_BLOCK_SIZE + lx + k, by * BF_SDF_BLOCK_SIZE + ly, bz * BF_SDF_BLOCK_SIZE + lz };
+            if ((fl & 1u) && probe_voxel(hpOld, cp, depthImg, colorImg, pi, sdfD[k], colD[k])) maskD |= 1u << k;
+            if ((fl & 2u) && probe_voxel(hpNew, cp, depthImg, colorImg, pi, sdfI[k], colI[k])) maskI |= 1u << k;
+        }
+        const unsigned mask = maskD | maskI;
+        if (mask) {
+            uint4* vp = reinterpret_cast<uint4*>(hd.d_SDFBlocks + (size_t)ptr) + 3 * t;
+            VoxelQuad q;
+            q.a = vp[0]; q.b = vp[1]; q.c = vp[2];
+            if (maskD & 1u) update_voxel<true>(hpOld, sdfD[0], colD[0], q.a.x, q.a.y, q.a.z, liveDelta);
+            if (maskI & 1u) update_voxel<false>(hpNew, sdfI[0], colI[0], q.a.x, q.a.y, q.a.z, liveDelta);
+            if (maskD & 2u) update_voxel<true>(hpOld, sdfD[1], colD[1], q.a.w, q.b.x, q.b.y, liveDelta);
+            if (maskI & 2u) update_voxel<false>(hpNew, sdfI[1], colI[1], q.a.w, q.b.x, q.b.y, liveDelta);
+            if (maskD & 4u) update_voxel<true>(hpOld, sdfD[2], colD[2], q.b.z, q.b.w, q.c.x, liveDelta);
+            if (maskI & 4u) update_voxel<false>(hpNew, sdfI[2], colI[2], q.b.z, q.b.w, q.c.x, liveDelta);
+            if (maskD & 8u) update_voxel<true>(hpOld, sdfD[3], colD[3], q.c.y, q.c.z, q.c.w, liveDelta);
+            if (maskI & 8u) update_voxel<false>(hpNew, sdfI[3], colI[3], q.c.y, q.c.z, q.c.w, liveDelta);
+            if (mask & 0x3u) vp[0] = q.a;
+            if (mask & 0x6u) vp[1] = q.b;
+            if (mask & 0xCu) vp[2] = q.c;
+            passed += __popc(maskD) + __popc(maskI);
+        }
+        if (__any_sync(0xffffffffu, liveDelta != 0)) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) liveDelta += __shfl_xor_sync(0xffffffffu, liveDelta, o);
+            if ((t & 31) == 0 && liveDelta != 0) atomicAdd(&live[ptr / BF_SDF_BLOCK_VOXELS], liveDelta);
+        }
+    }
+    passed = warp_sum_u(passed);
+    __shared__ unsigned sPassed[4];
+    if ((t & 31) == 0) sPassed[t >> 5] = passed;
+    __syncthreads();
+    if (t == 0) {
+        const unsigned long long tot = (unsigned long long)sPassed[0] + sPassed[1] + sPassed[2] + sPassed[3];
+        if (tot) { atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot); atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_TOT_LO]), tot); }
+        if (eBoth) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_E_TOT_LO]), (unsigned long long)eBoth);   // E of both passes
+        if (blockIdx.x == 0) { hd.d_hashCompactifiedCounter[0] = (int)count; ctrs[CTR_E] = count; }
+    }
+}
+
 // starveVoxelsKernel (.cu:554-563)
 __global__ void starve_kernel(BFHashDataStruct hd) {
     const BFHashEntry& e = hd.d_hashCompactified[blockIdx.x];
@@ -945,9 +1065,12 @@ gc_fused_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, co
 // Freed blocks are already all-zero (de-integration clears a voxel when its weight reaches 0, .cu:509-513).
 __global__ void __launch_bounds__(256)
 gc_live_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const unsigned* __restrict__ countPtr,
-               int4* slotInfo, unsigned* ctrs, const int* __restrict__ live) {
+               int4* slotInfo, unsigned* ctrs, const int* __restrict__ live, const unsigned char* __restrict__ listFlags) {
     const unsigned count = *countPtr;
     for (unsigned b = blockIdx.x * blockDim.x + threadIdx.x; b < count; b += gridDim.x * blockDim.x) {
+        // after a fused re-integration the list is the union of two frusta; the reference's GC walks the list of the LAST
+        // integrate only (DepthSensing.cpp:901), i.e. the entries inside the new pose's frustum
+        if (listFlags && !(listFlags[b] & 2u)) { hd.d_hashDecision[b] = 0; continue; }
         const BFHashEntry e = hd.d_hashCompactified[b];
         const int dead = (__ldcg(&live[(unsigned)e.ptr / BF_SDF_BLOCK_VOXELS]) <= 0) ? 1 : 0;
         hd.d_hashDecision[b] = dead;
@@ -966,12 +1089,13 @@ static int get_aux(const BFHashDataStruct* hd, const BFHashParams* hp, TsdfAux**
     auto it = g_aux.find(hd->d_hash);
     if (it != g_aux.end() && (hp == nullptr || it->second.numSlots == hp->m_numSDFBlocks)) { *out = &it->second; return 0; }
     if (!create || hp == nullptr) { *out = nullptr; return (int)cudaErrorInvalidValue; }
-    if (it != g_aux.end()) { cudaFree(it->second.slotInfo); cudaFree(it->second.ctrs); cudaFree(it->second.live); g_aux.erase(it); }
+    if (it != g_aux.end()) { cudaFree(it->second.slotInfo); cudaFree(it->second.ctrs); cudaFree(it->second.live); cudaFree(it->second.listFlags); g_aux.erase(it); }
     TsdfAux a;
     a.numSlots = hp->m_numSDFBlocks;
     BF_CHECK(cudaMalloc(&a.slotInfo, sizeof(int4) * (size_t)a.numSlots));
     BF_CHECK(cudaMalloc(&a.ctrs, sizeof(unsigned) * CTR_NUM));
     BF_CHECK(cudaMalloc(&a.live, sizeof(int) * (size_t)a.numSlots));
+    BF_CHECK(cudaMalloc(&a.listFlags, (size_t)a.numSlots));
     BF_CHECK(cudaMemsetAsync(a.live, 0, sizeof(int) * (size_t)a.numSlots, g_stream));
     a.liveValid = !adopt;           // an adopted table has unknown weights: fall back to the scanning GC
     BF_CHECK(cudaMemsetAsync(a.ctrs, 0, sizeof(unsigned) * CTR_NUM, g_stream));
@@ -1017,6 +1141,7 @@ static int do_alloc(BFHashDataStruct* hd, const BFHashParams* hp, const float* d
 
 static int do_compactify(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraParams* cp, TsdfAux* aux) {
     aux->parity ^= 1u;
+    aux->lastListDual = false;
     const int countIdx = aux->parity ? CTR_COUNT1 : CTR_COUNT0;
     const int otherIdx = aux->parity ? CTR_COUNT0 : CTR_COUNT1;
     ++g_launchCount;
@@ -1066,7 +1191,7 @@ BF_API void bfSetStream(void* s) { g_stream = (cudaStream_t)s; }
 BF_API void* bfGetStream(void) { return (void*)g_stream; }
 BF_API const char* bfGetLastErrorString(void) { return t_lastError.c_str(); }
 
-BF_API size_t bfTsdfAuxBytes(const BFHashParams* hp) { return (sizeof(int4) + sizeof(int)) * (size_t)hp->m_numSDFBlocks + sizeof(unsigned) * CTR_NUM; }
+BF_API size_t bfTsdfAuxBytes(const BFHashParams* hp) { return (sizeof(int4) + sizeof(int) + 1) * (size_t)hp->m_numSDFBlocks + sizeof(unsigned) * CTR_NUM; }
 
 BF_API int bfTsdfReset(BFHashDataStruct* hd, const BFHashParams* hp) { return do_reset(hd, hp); }
 
@@ -1080,12 +1205,41 @@ BF_API int bfTsdfIntegrateFrame(BFHashDataStruct* hd, const BFHashParams* hp, co
     return do_integrate(hd, hp, dd, cp, aux, deIntegrate != 0, live_count_ptr(aux), 0);
 }
 
+// CUDASceneRepHashSDF::deIntegrate(old pose) immediately followed by ::integrate(new pose) of the SAME frame
+// (the body of the reference's re-integration loop, DepthSensing.cpp:867-895) as one fused pass; voxels bit-identical.
+BF_API int bfTsdfReintegrateFrame(BFHashDataStruct* hd, const BFHashParams* hpOld, const BFHashParams* hpNew,
+                                  const BFDepthCameraData* dd, const BFDepthCameraParams* cp) {
+    TsdfAux* aux;
+    int rc = get_aux(hd, hpNew, &aux, true);
+    if (rc) return rc;
+    if (dd->d_colorData == nullptr) return do_alloc(hd, hpNew, dd->d_depthData, cp, aux);     // no colour: neither pass updates a voxel
+    rc = do_alloc(hd, hpNew, dd->d_depthData, cp, aux); if (rc) return rc;
+    aux->parity ^= 1u;
+    aux->lastListDual = true;
+    const int countIdx = aux->parity ? CTR_COUNT1 : CTR_COUNT0, otherIdx = aux->parity ? CTR_COUNT0 : CTR_COUNT1;
+    ++g_launchCount;
+    compactify_dual_kernel<<<grid_for((hpNew->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, *hpOld, *hpNew, *cp, aux->slotInfo, aux->ctrs, countIdx, otherIdx, aux->listFlags);
+    BF_CHECK(cudaGetLastError());
+    const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
+    if (g_profile) ++g_profLaunches;
+    if (timeIt) {
+        if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
+        BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], g_stream));
+    }
+    ++g_launchCount;
+    reintegrate_kernel<<<grid_for(hpNew->m_numSDFBlocks, 16), 128, 0, g_stream>>>(*hd, *hpOld, *hpNew, *cp, dd->d_depthData, reinterpret_cast<const uchar4*>(dd->d_colorData),
+                                                                                  live_count_ptr(aux), aux->listFlags, aux->ctrs, aux->live);
+    BF_CHECK(cudaGetLastError());
+    if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], g_stream)); ++g_evUsed; }
+    return 0;
+}
+
 BF_API int bfTsdfGarbageCollect(BFHashDataStruct* hd, const BFHashParams* hp) {
     TsdfAux* aux;
     int rc = get_aux(hd, hp, &aux, true);
     if (rc) return rc;
     ++g_launchCount;
-    if (aux->liveValid) gc_live_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 2), 256, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs, aux->live);
+    if (aux->liveValid) gc_live_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 2), 256, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs, aux->live, aux->lastListDual ? aux->listFlags : nullptr);
     else                gc_fused_kernel<<<grid_for(hp->m_numSDFBlocks, 16), 128, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs);
     BF_CHECK(cudaGetLastError());
     return 0;
@@ -1159,6 +1313,7 @@ BF_API int bfTsdfReleaseAux(const BFHashDataStruct* hd) {
     cudaFree(it->second.slotInfo);
     cudaFree(it->second.ctrs);
     cudaFree(it->second.live);
+    cudaFree(it->second.listFlags);
     g_aux.erase(it);
     return 0;
 }

@@ -189,6 +189,13 @@ int bfTsdfIntegrateFrame(BFHashDataStruct* hashData, const BFHashParams* hashPar
                          const BFDepthCameraParams* depthCameraParams,
                          int deIntegrate);
 
+/* deIntegrate(old pose) + integrate(new pose) of the SAME frame -- the body of the reference's re-integration loop
+ * (FL/DepthSensing/DepthSensing.cpp:867-895) -- as ONE fused pass: alloc(new) -> compactify over the union of both frusta ->
+ * per voxel de-integrate then integrate in registers.  Voxels, block set and heap are bit-identical to the two-call sequence;
+ * one voxel read + write instead of two.  d_hashCompactified then holds the union list. */
+int bfTsdfReintegrateFrame(BFHashDataStruct* hashData, const BFHashParams* hashParamsOldPose, const BFHashParams* hashParamsNewPose,
+                           const BFDepthCameraData* depthCameraData, const BFDepthCameraParams* depthCameraParams);
+
 /* CUDASceneRepHashSDF::garbageCollect (h:110-126) over the last compactified list */
 int bfTsdfGarbageCollect(BFHashDataStruct* hashData, const BFHashParams* hashParams);
 

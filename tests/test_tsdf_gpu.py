@@ -246,3 +246,36 @@ def test_overfull_table_keeps_invariants(cuda_device):
         orc.check_hash_invariants(gpu.download(), hp)
     assert gpu.getLastFrameStats()["dropped"] > 0
     assert gpu.getHeapFreeCount() >= 0
+
+
+def test_fused_reintegration_matches_two_pass_oracle(cuda_device):
+    """bfTsdfRunOps fuses every (de-integrate f @ old pose, integrate f @ new pose) pair into one pass
+    (bfTsdfReintegrateFrame); voxels, block set and heap must equal the oracle's two separate passes bit for bit."""
+    import torch
+    W, H = 160, 120
+    cam, hp = camera_params(W, H), small_params()
+    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device), orc.OracleSceneRepHashSDF(hp)
+    frames = [synth.make_frame(35 * i, W, H) for i in range(6)]
+    dl = [torch.from_numpy(f[0]).to(cuda_device) for f in frames]
+    cl = [torch.from_numpy(f[1]).to(cuda_device) for f in frames]
+    gpu.runOps([(capi.BF_TSDF_OP_INTEGRATE, i, frames[i][2]) for i in range(6)], dl, cl, cam)
+    for d, c, T in frames:
+        cpu.integrate(T, d, c, cam)
+    assert_same_state(gpu, cpu, hp)
+    rng = np.random.default_rng(4)
+    ops = []
+    for k in (4, 2, 0, 5):
+        T = frames[k][2]
+        T2 = (synth.se3_exp(rng.standard_normal(3) * 0.01, rng.standard_normal(3) * 0.02) @ T.astype(np.float64)).astype(F)
+        ops += [(capi.BF_TSDF_OP_DEINTEGRATE, k, T), (capi.BF_TSDF_OP_INTEGRATE, k, T2)]
+        cpu.deIntegrate(T, frames[k][0], frames[k][1], cam)
+        cpu.integrate(T2, frames[k][0], frames[k][1], cam)
+    ops.append((capi.BF_TSDF_OP_GARBAGE_COLLECT, 0, None))
+    gpu.runOps(ops, dl, cl, cam)
+    cpu.garbageCollect()
+    assert_same_state(gpu, cpu, hp, check_list=False)
+    # a lone de-integration (no partner) still takes the single-pass route
+    gpu.runOps([(capi.BF_TSDF_OP_DEINTEGRATE, 1, frames[1][2]), (capi.BF_TSDF_OP_GARBAGE_COLLECT, 0, None)], dl, cl, cam)
+    cpu.deIntegrate(frames[1][2], frames[1][0], frames[1][1], cam)
+    cpu.garbageCollect()
+    assert_same_state(gpu, cpu, hp, check_list=False)
