@@ -32,7 +32,7 @@ W, H = 640, 480
 WORKLOAD = {
     "workload": "configs[1]: 640x480 RGB-D stream, hashed TSDF (1 cm voxels, 4M-block heap, 4M buckets), per frame 1 integrate + 10 "
                 "re-integrations (de-integrate + integrate) + GC; per 10-frame chunk 1 local BA (11 frames, 2 GN x 100 PCG) + 1 global BA "
-                "(500 keyframes, 187k correspondences, 3 GN x 150 PCG); SIFT detect/match and the dense BA term are not built yet",
+                "(500 keyframes, 187k correspondences, 3 GN x 150 PCG, sparse); local BA = sparse + dense depth term (80x60 caches); SIFT detect/match not built yet",
     "frame": [W, H], "voxel_m": 0.010, "sdf_blocks": 4000000, "hash_buckets": 4000000, "reintegrations_per_frame": 10,
     "chunk": 10, "global_keyframes": 500, "global_degree": 15, "frame_bank": 128,
     "streams": "reconstruction (TSDF) and bundling (BA) on two CUDA streams of one GPU, as the reference's two threads/devices",
@@ -119,7 +119,7 @@ class Workload:
 
 def make_ba_problems():
     from bundlefusion_b200 import synth
-    loc = synth.make_ba_problem(11, degree=10, corr_per_pair=25, noise=0.002, seed=31)
+    loc = synth.make_dense_ba_problem(11, stride=3, start=100, corr_per_pair=25, noise=0.002, seed=31)    # sparse + dense 80x60 caches
     glo = synth.make_ba_problem(WORKLOAD["global_keyframes"], degree=WORKLOAD["global_degree"], corr_per_pair=25, noise=0.002, seed=32, stride=10)
     return loc, glo
 
@@ -167,6 +167,8 @@ def run_ours(args):
                 torch.from_numpy(prob["init_trans"]).to(dev), torch.ones(len(prob["init_rot"]), dtype=torch.int32, device=dev))
     lc, lr0, lt0, lv = upload(loc); gc_, gr0, gt0, gv = upload(glo)
     lrot, ltrans, grot, gtrans = lr0.clone(), lt0.clone(), gr0.clone(), gt0.clone()
+    from bundlefusion_b200.solver import DeviceCache
+    loc_cache = DeviceCache(loc["caches"], loc["intrinsics"], dev)
     sol_l = CUDASolverBundling(11, 11 * 1000, dev); sol_g = CUDASolverBundling(len(glo["init_rot"]), max(len(glo["corr"]), 1000 * len(glo["init_rot"])), dev)
     h_grot = torch.empty_like(grot, device="cpu").pin_memory(); h_gtrans = torch.empty_like(gtrans, device="cpu").pin_memory()
     h_heap = torch.empty(1, dtype=torch.int32).pin_memory()
@@ -183,7 +185,8 @@ def run_ours(args):
         ba_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(ba_stream):
             lrot.copy_(lr0); ltrans.copy_(lt0); grot.copy_(gr0); gtrans.copy_(gt0)
-            sol_l.solve(lc, len(loc["corr"]), lv, 11, 2, 100, [1.0, 1.0], d_rotationAnglesUnknowns=lrot, d_translationUnknowns=ltrans)
+            # local BA as FL/SBA.cpp:28-31, 64-75: sparse weight 1, dense depth weights 1, 2, colour 0
+            sol_l.solve(lc, len(loc["corr"]), lv, 11, 2, 100, [1.0, 1.0], [1.0, 2.0], [0.0, 0.0], d_rotationAnglesUnknowns=lrot, d_translationUnknowns=ltrans, cudaCache=loc_cache)
             sol_g.solve(gc_, len(glo["corr"]), gv, len(glo["init_rot"]), 3, 150, [1.0, 1.0, 1.0], d_rotationAnglesUnknowns=grot, d_translationUnknowns=gtrans)
             if e2e:
                 h_grot.copy_(grot, non_blocking=True); h_gtrans.copy_(gtrans, non_blocking=True)
@@ -288,7 +291,7 @@ def cpu_arm(steps, warmup, quiet=False, n_reint=None):
     wl = Workload([f[2] for f in frames])
     loc, glo = make_ba_problems()
     def ba():
-        orc.solve_sparse(loc["corr"], loc["init_rot"], loc["init_trans"], 2, 100, fast=True)
+        orc.solve(loc["corr"], loc["init_rot"], loc["init_trans"], 2, 100, [1.0, 1.0], [1.0, 2.0], [0.0, 0.0], loc["caches"], loc["intrinsics"], fast=True)
         orc.solve_sparse(glo["corr"], glo["init_rot"], glo["init_trans"], 3, 150, fast=True)
     def step(f, with_ba):
         for kind, r, pose in wl.step_ops(f, n_re):

@@ -33,6 +33,7 @@ extern unsigned long long g_launchCount;      // defined in tsdf.cu (bfGetLaunch
 #define BF_FLOAT_EPSILON 0.000001f      // FL/SolverUtil.h:9
 #define BF_MAX_ROW 8192                 // longest variable row the in-smem row sort handles
 #define BF_SOLVER_THREADS 256
+#define BF_DENSE_MAX_IMAGES 64          // the dense term is built for chunk-sized problems (local BA: 11 images)
 
 struct V3 { float x, y, z; };
 __host__ __device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r = { x, y, z }; return r; }
@@ -148,7 +149,7 @@ __device__ void mat4_inverse(const float* m, float* out) {
 
 // ---- workspace --------------------------------------------------------------------------------------------
 struct Segment { int nbr; int start; int count; int _pad; };      // one (row image, neighbour image) run of a row
-enum { SC_DONE = 0, SC_GN_RUN = 1, SC_PCG_RUN = 2, SC_NUM_SEG = 3, SC_NUM_VALID = 4, SC_MAXDELTA_BITS = 5, SC_ERROR = 6, SC_NUM = 16 };
+enum { SC_DONE = 0, SC_GN_RUN = 1, SC_PCG_RUN = 2, SC_NUM_SEG = 3, SC_NUM_VALID = 4, SC_MAXDELTA_BITS = 5, SC_ERROR = 6, SC_DENSE_ON = 7, SC_DENSE_OVERLAP = 8, SC_DENSE_PAIRS = 9, SC_NUM = 16 };
 
 struct SolverWs {
     unsigned maxImages = 0, maxCorr = 0;
@@ -162,6 +163,11 @@ struct SolverWs {
     float* segMom = nullptr;      // [2*maxCorr][20] per-segment diagonal moments + rhs
     float* diagBlk = nullptr;     // [N][36]
     float* partials = nullptr;    // [2][maxGrid]
+    // dense depth / colour term (N <= BF_DENSE_MAX_IMAGES): pair weights, per-pair 90-sum records, assembled dense system
+    float* pairW = nullptr;       // [Nd*Nd]
+    float* pairOut = nullptr;     // [Nd*Nd][90]
+    float* denseJtJ = nullptr;    // [(6 Nd)^2]  (translation-first ordering per image, as the reference)
+    float* denseJtr = nullptr;    // [6 Nd]
     unsigned* scal = nullptr;     // [SC_NUM]
     int maxGrid = 0;
 };
@@ -176,6 +182,7 @@ static int get_ws(const BFSolverState* st, unsigned maxImages, unsigned maxCorr,
         SolverWs& w = it->second;
         cudaFree(w.rowCount); cudaFree(w.rowStart); cudaFree(w.cursor); cudaFree(w.entries); cudaFree(w.segCount); cudaFree(w.segs);
         cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.scal);
+        cudaFree(w.pairW); cudaFree(w.pairOut); cudaFree(w.denseJtJ); cudaFree(w.denseJtr);
         g_ws.erase(it);
     }
     SolverWs w;
@@ -193,6 +200,13 @@ static int get_ws(const BFSolverState* st, unsigned maxImages, unsigned maxCorr,
     BF_CHECK(cudaMalloc(&w.diagBlk, sizeof(float) * 36 * maxImages));
     BF_CHECK(cudaMalloc(&w.partials, sizeof(float) * 2 * w.maxGrid));
     BF_CHECK(cudaMalloc(&w.scal, sizeof(unsigned) * SC_NUM));
+    {
+        const size_t Nd = BF_DENSE_MAX_IMAGES;
+        BF_CHECK(cudaMalloc(&w.pairW, sizeof(float) * Nd * Nd));
+        BF_CHECK(cudaMalloc(&w.pairOut, sizeof(float) * Nd * Nd * 90));
+        BF_CHECK(cudaMalloc(&w.denseJtJ, sizeof(float) * 36 * Nd * Nd));
+        BF_CHECK(cudaMalloc(&w.denseJtr, sizeof(float) * 6 * Nd));
+    }
     BF_CHECK(cudaMemsetAsync(w.scal, 0, sizeof(unsigned) * SC_NUM, stream()));
     auto res = g_ws.emplace(st->d_deltaRot, w);
     *out = &res.first->second;
@@ -322,6 +336,7 @@ struct GnArgs {
     const int* rowStart; const int* entries; const int* segCount; const Segment* segs;
     float* offBlk; float* segMom; float* diagBlk; float* partials; unsigned* scal;
     float wSparse; unsigned nLin; int isLastGn; int maxGrid;
+    const float* denseJtJ; const float* denseJtr; int useDense;       // dense term: assembled system (NULL / 0 when off)
 };
 
 // 6x6 block times 6-vector (rot,trans order)
@@ -441,6 +456,7 @@ gn_iteration_kernel(const GnArgs a) {
     }
     grid.sync();
 
+    const bool denseOn = a.useDense && (__ldcg(&a.scal[SC_DENSE_ON]) != 0);      // BuildDenseSystem found overlapping pairs (:1167)
     // (2) one thread per row: sum the row's segment moments in segment order -> diagonal block, -J^T f, Jacobi
     //     preconditioner from the UNWEIGHTED diagonal (SolverBundlingEquationsLie.h:105-147), PCG init (:756-794)
     float part = 0.0f;
@@ -467,7 +483,11 @@ gn_iteration_kernel(const GnArgs a) {
         D[24] = w * (-m[3]); D[25] = 0.0f;        D[26] = w * (m[1]);
         D[30] = w * (m[2]);  D[31] = w * (-m[1]); D[32] = 0.0f;
         D[21] = w * m[0]; D[22] = 0.0f; D[23] = 0.0f; D[27] = 0.0f; D[28] = w * m[0]; D[29] = 0.0f; D[33] = 0.0f; D[34] = 0.0f; D[35] = w * m[0];
-        const V3 resRot = mk(-w * m[11], -w * m[12], -w * m[13]), resTrans = mk(-w * m[14], -w * m[15], -w * m[16]);
+        V3 resRot = mk(-w * m[11], -w * m[12], -w * m[13]), resTrans = mk(-w * m[14], -w * m[15], -w * m[16]);
+        if (denseOn) {      // minus since -J^T f, weight already built in (SolverBundlingEquationsLie.h:114-118)
+            resRot = resRot - mk(a.denseJtr[v * 6 + 3], a.denseJtr[v * 6 + 4], a.denseJtr[v * 6 + 5]);
+            resTrans = resTrans - mk(a.denseJtr[v * 6 + 0], a.denseJtr[v * 6 + 1], a.denseJtr[v * 6 + 2]);
+        }
         const V3 pr = mk(m[4] - m[5], m[4] - m[8], m[4] - m[10]);            // sum (da.da, db.db, dc.dc)
         const V3 precR = mk(pr.x > BF_FLOAT_EPSILON ? 1.0f / pr.x : 1.0f, pr.y > BF_FLOAT_EPSILON ? 1.0f / pr.y : 1.0f, pr.z > BF_FLOAT_EPSILON ? 1.0f / pr.z : 1.0f);
         const float pt = (m[0] > BF_FLOAT_EPSILON) ? 1.0f / m[0] : 1.0f;
@@ -500,6 +520,18 @@ gn_iteration_kernel(const GnArgs a) {
                 const unsigned o = (unsigned)a.segs[rs + sI].nbr;
                 if (o == 0) continue;                                   // variable 0 is fixed: its p is zero by construction
                 blk_mv(&a.offBlk[36 * (size_t)(rs + sI)], ld3(a.pRot, o), ld3(a.pTrans, o), y);
+            }
+            if (denseOn) {      // dense J^T J p (applyJTJDenseDevice, SolverBundlingDenseUtil.h:371-411): lanes over column blocks
+                const unsigned dim = 6 * N;
+                for (unsigned o = 1 + lane; o < N; o += 32) {
+                    const float* B = &a.denseJtJ[(size_t)(v * 6) * dim + o * 6];
+                    const V3 pt = ld3(a.pTrans, o), pr = ld3(a.pRot, o);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        y[3 + r] += B[r * dim + 0] * pt.x + B[r * dim + 1] * pt.y + B[r * dim + 2] * pt.z + B[r * dim + 3] * pr.x + B[r * dim + 4] * pr.y + B[r * dim + 5] * pr.z;
+                        y[r] += B[(3 + r) * dim + 0] * pt.x + B[(3 + r) * dim + 1] * pt.y + B[(3 + r) * dim + 2] * pt.z + B[(3 + r) * dim + 3] * pr.x + B[(3 + r) * dim + 4] * pr.y + B[(3 + r) * dim + 5] * pr.z;
+                    }
+                }
             }
 #pragma unroll
             for (int k = 0; k < 6; ++k) y[k] = warp_sum(y[k]);
@@ -582,6 +614,292 @@ gn_iteration_kernel(const GnArgs a) {
     }
 }
 
+// ---- dense depth / colour term -------------------------------------------------------------------
+// FindImageImageCorr / FindDenseCorrespondences / Weight / BuildDenseSystem (SolverBundling.cu:30-471) restructured: one CTA
+// per candidate pair decides overlap, counts and weights without a host round trip; one CTA per weighted pair reduces its 90
+// sums (6x6 blocks ii, jj, ij + two 6-vectors) in registers with a fixed tree; an assemble kernel lays the dense system out
+// in pair order.  No atomics: deterministic.
+struct DenseArgs {
+    const BFCUDACachedFrame* frames; const int* valid; const float* T; const float* Tinv;
+    unsigned N, W, H; float fx, fy, mx, my;
+    float distThresh, normalThresh, colorThresh, colorGradientMin, depthMin, depthMax;
+    unsigned subsample; int usePairwise; float wDepth, wColor;
+    float* pairW; float* pairOut; float* JtJ; float* Jtr; unsigned* scal;
+};
+__device__ __forceinline__ V3 rot3(const float* m, V3 v) { return mk(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); }
+__device__ __forceinline__ V3 depth_to_cam(const DenseArgs& d, int x, int y, float depth) {
+    const float fx = ((float)x - d.mx) / d.fx, fy = ((float)y - d.my) / d.fy;
+    return mk(depth * fx, depth * fy, depth);
+}
+// ICPUtil.h:56-110 (nc channels, validity on channel 0)
+template <int NC>
+__device__ bool bilinear(const float* __restrict__ img, float x, float y, unsigned W, unsigned H, float* out) {
+    const int x0 = (int)floorf(x), y0 = (int)floorf(y);
+    const float alpha = x - (float)x0, beta = y - (float)y0;
+    float s0[NC], s1[NC], w0 = 0.0f, w1 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { s0[c] = 0.0f; s1[c] = 0.0f; }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int xs = x0 + k;
+        const float wgt = k ? alpha : (1.0f - alpha);
+        if ((unsigned)xs < W && (unsigned)y0 < H) { const float* v = &img[((size_t)y0 * W + xs) * NC]; if (v[0] != -INFINITY) { for (int c = 0; c < NC; ++c) s0[c] += wgt * v[c]; w0 += wgt; } }
+        if ((unsigned)xs < W && (unsigned)(y0 + 1) < H) { const float* v = &img[((size_t)(y0 + 1) * W + xs) * NC]; if (v[0] != -INFINITY) { for (int c = 0; c < NC; ++c) s1[c] += wgt * v[c]; w1 += wgt; } }
+    }
+    float ww = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) out[c] = 0.0f;
+    if (w0 > 0.0f) { for (int c = 0; c < NC; ++c) out[c] += (1.0f - beta) * (s0[c] / w0); ww += (1.0f - beta); }
+    if (w1 > 0.0f) { for (int c = 0; c < NC; ++c) out[c] += beta * (s1[c] / w1); ww += beta; }
+    if (ww > 0.0f) { for (int c = 0; c < NC; ++c) out[c] = out[c] / ww; return true; }
+    for (int c = 0; c < NC; ++c) out[c] = -INFINITY;
+    return false;
+}
+__device__ __forceinline__ int block_sum_int(int v, int* sRed) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int tot = 0;
+    for (unsigned w = 0; w < blockDim.x / 32; ++w) tot += sRed[w];
+    __syncthreads();
+    return tot;
+}
+__global__ void __launch_bounds__(512)
+dense_pair_weight_kernel(const DenseArgs d) {
+    __shared__ int sRed[16];
+    const unsigned i = blockIdx.x, j = blockIdx.y, N = d.N;
+    if (d.scal[SC_DONE] != 0) return;
+    if (i >= j) { if (threadIdx.x == 0 && i < N && j < N) d.pairW[i * N + j] = 0.0f; return; }
+    float weight = 0.0f; int overlap = 0;
+    bool cand = d.usePairwise || (j == i + 1);
+    if (cand && d.valid && (d.valid[i] == 0 || d.valid[j] == 0)) cand = false;
+    float tr[16];
+    if (cand) {
+        mat4_mul(&d.Tinv[16 * i], &d.T[16 * j], tr);
+        const float inv = 1.0f / sqrtf(3.0f);
+        const V3 x = mk(inv, inv, inv), vv = rot3(tr, x);
+        const float angle = acosf(fminf(fmaxf(dot(x, vv), -1.0f), 1.0f));
+        if (!(fabsf(angle) < 0.52f)) cand = false;                       // computeAngleDiff, ~30 degrees (:60)
+    }
+    if (cand) {
+        const BFCUDACachedFrame fi = d.frames[i], fj = d.frames[j];
+        // overlap pre-filter on the sub-sampled grid (SolverBundlingDenseUtil.h:22-42)
+        int hit = 0;
+        {
+            const unsigned subW = d.W / d.subsample, t = threadIdx.x;
+            const unsigned x = (t % subW) * d.subsample, y = (t / subW) * d.subsample, idx = y * d.W + x;
+            if (idx < d.W * d.H) {
+                const V3 cj = depth_to_cam(d, (int)x, (int)y, fj.d_depthDownsampled[idx]);
+                if (cj.z > d.depthMin && cj.z < d.depthMax) {
+                    const V3 s2t = xf(tr, cj);
+                    const int tx = (int)roundf(s2t.x * d.fx / s2t.z + d.mx), ty = (int)roundf(s2t.y * d.fy / s2t.z + d.my);
+                    if (tx >= 0 && ty >= 0 && tx < (int)d.W && ty < (int)d.H) {
+                        const V3 ct = depth_to_cam(d, tx, ty, fi.d_depthDownsampled[ty * d.W + tx]);
+                        if (ct.z > d.depthMin && ct.z < d.depthMax && length(s2t - ct) <= d.distThresh) hit = 1;
+                    }
+                }
+            }
+        }
+        const int found = block_sum_int(hit, sRed);
+        if (found > 10) {
+            overlap = 1;
+            // full-resolution count with the uchar4 normals (SolverBundlingDenseUtil.h:152-184)
+            int cnt = 0;
+            for (unsigned idx = threadIdx.x; idx < d.W * d.H; idx += blockDim.x) {
+                const unsigned x = idx % d.W, y = idx / d.W;
+                const V3 cj = depth_to_cam(d, (int)x, (int)y, fj.d_depthDownsampled[idx]);
+                if (!(cj.z > d.depthMin && cj.z < d.depthMax)) continue;
+                const uchar4 nu = reinterpret_cast<const uchar4*>(fj.d_normalsDownsampledUCHAR4)[idx];
+                if ((nu.x | nu.y | nu.z | nu.w) == 0) continue;
+                const V3 nj = rot3(tr, mk((float)nu.x / 255.0f * 2.0f - 1.0f, (float)nu.y / 255.0f * 2.0f - 1.0f, (float)nu.z / 255.0f * 2.0f - 1.0f));
+                const V3 s2t = xf(tr, cj);
+                const int tx = (int)roundf(s2t.x * d.fx / s2t.z + d.mx), ty = (int)roundf(s2t.y * d.fy / s2t.z + d.my);
+                if (!(tx >= 0 && ty >= 0 && tx < (int)d.W && ty < (int)d.H)) continue;
+                const V3 ct = depth_to_cam(d, tx, ty, fi.d_depthDownsampled[ty * d.W + tx]);
+                if (!(ct.z > d.depthMin && ct.z < d.depthMax)) continue;
+                const uchar4 tu = reinterpret_cast<const uchar4*>(fi.d_normalsDownsampledUCHAR4)[ty * d.W + tx];
+                if ((tu.x | tu.y | tu.z | tu.w) == 0) continue;
+                const V3 nt = mk((float)tu.x / 255.0f * 2.0f - 1.0f, (float)tu.y / 255.0f * 2.0f - 1.0f, (float)tu.z / 255.0f * 2.0f - 1.0f);
+                if (dot(nj, nt) >= d.normalThresh && length(s2t - ct) <= d.distThresh) ++cnt;
+            }
+            const float count = (float)block_sum_int(cnt, sRed);
+            if (count > 0) weight = (count < 800) ? 0.0f : 1.0f / fminf(logf(count), 9.0f);      // (:162-180)
+        }
+    }
+    if (threadIdx.x == 0) {
+        d.pairW[i * N + j] = weight;
+        if (overlap) atomicAdd(&d.scal[SC_DENSE_OVERLAP], 1u);
+        if (weight != 0.0f) atomicAdd(&d.scal[SC_DENSE_PAIRS], 1u);
+    }
+}
+
+// rows of one dense correspondence: depth row = -n^T d(s2t)/de, colour row = dI^T dProj d(s2t)/de, with d(s2t)/de for image i
+// (evalLie_derivI, A = Tj^-1, D = Ti) and image j (evalLie_derivJ, A = Ti^-1, D = Tj) in closed form (LieDerivUtil.h:247-295):
+//   J_i = [ -M | rows_k = d_k x q + (M skew(t_D))_k ],  M = R_T^T R_A, T = A D, q = R_A^T (p - t_T), d_k = k-th column of R_D
+//   J_j = [ R_A | -R_A skew(D p) ]
+__device__ void lie_jac_i(const float* A, const float* D, V3 p, float J[18]) {
+    float T[16]; mat4_mul(A, D, T);
+    const V3 pt = p - mk(T[3], T[7], T[11]);
+    const V3 q = mk(A[0] * pt.x + A[4] * pt.y + A[8] * pt.z, A[1] * pt.x + A[5] * pt.y + A[9] * pt.z, A[2] * pt.x + A[6] * pt.y + A[10] * pt.z);
+    float M[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) M[r * 3 + c] = T[0 * 4 + r] * A[0 * 4 + c] + T[1 * 4 + r] * A[1 * 4 + c] + T[2 * 4 + r] * A[2 * 4 + c];
+    const V3 tD = mk(D[3], D[7], D[11]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        J[k * 6 + 0] = -M[k * 3 + 0]; J[k * 6 + 1] = -M[k * 3 + 1]; J[k * 6 + 2] = -M[k * 3 + 2];
+        const V3 dk = mk(D[0 * 4 + k], D[1 * 4 + k], D[2 * 4 + k]);
+        const V3 c1 = cross(dk, q);
+        // (M skew(t))_k = row_k(M) * [[0,-tz,ty],[tz,0,-tx],[-ty,tx,0]]
+        const float m0 = M[k * 3 + 0], m1 = M[k * 3 + 1], m2 = M[k * 3 + 2];
+        J[k * 6 + 3] = c1.x + (m1 * tD.z - m2 * tD.y);
+        J[k * 6 + 4] = c1.y + (-m0 * tD.z + m2 * tD.x);
+        J[k * 6 + 5] = c1.z + (m0 * tD.y - m1 * tD.x);
+    }
+}
+__device__ void lie_jac_j(const float* A, const float* D, V3 p, float J[18]) {
+    const V3 a = xf(D, p);
+    const float G[3][3] = { { 0.0f, a.z, -a.y }, { -a.z, 0.0f, a.x }, { a.y, -a.x, 0.0f } };
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        J[r * 6 + 0] = A[r * 4 + 0]; J[r * 6 + 1] = A[r * 4 + 1]; J[r * 6 + 2] = A[r * 4 + 2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) J[r * 6 + 3 + c] = A[r * 4 + 0] * G[0][c] + A[r * 4 + 1] * G[1][c] + A[r * 4 + 2] * G[2][c];
+    }
+}
+// one 128-thread CTA per weighted pair; 90 sums per thread: ii (21, a<=b), jj (21), ij (36, a over i, b over j), gi (6), gj (6)
+__device__ __forceinline__ void accum_rows(float* acc, const float* ri, const float* rj, float res, float w, bool hasI, bool hasJ) {
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) { if (hasI) acc[k] += ri[a] * ri[b] * w; if (hasJ) acc[21 + k] += rj[a] * rj[b] * w; ++k; }
+    if (hasI && hasJ) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b < 6; ++b) acc[42 + a * 6 + b] += ri[a] * rj[b] * w;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { if (hasI) acc[78 + a] += ri[a] * res * w; if (hasJ) acc[84 + a] += rj[a] * res * w; }
+}
+__global__ void __launch_bounds__(128)
+dense_build_kernel(const DenseArgs d) {
+    __shared__ float sAcc[4][90];
+    const unsigned i = blockIdx.x, j = blockIdx.y, N = d.N;
+    if (d.scal[SC_DONE] != 0 || i >= j) return;
+    const float pairW = d.pairW[i * N + j];
+    if (pairW == 0.0f) return;
+    const BFCUDACachedFrame fi = d.frames[i], fj = d.frames[j];
+    const float* Ti = &d.T[16 * i]; const float* Tj = &d.T[16 * j]; const float* Tii = &d.Tinv[16 * i]; const float* Tji = &d.Tinv[16 * j];
+    float tr[16]; mat4_mul(Tii, Tj, tr);
+    float acc[90];
+#pragma unroll
+    for (int k = 0; k < 90; ++k) acc[k] = 0.0f;
+    const bool hasI = i > 0, hasJ = j > 0;
+    for (unsigned idx = threadIdx.x; idx < d.W * d.H; idx += blockDim.x) {
+        // findDenseCorr, camera-position version with float4 normals (SolverBundlingDenseUtil.h:79-113)
+        const float4 cp = reinterpret_cast<const float4*>(fj.d_cameraposDownsampled)[idx];
+        if (!(cp.z > d.depthMin && cp.z < d.depthMax)) continue;
+        const V3 cps = mk(cp.x, cp.y, cp.z);
+        const float4 nj4 = reinterpret_cast<const float4*>(fj.d_normalsDownsampled)[idx];
+        if (nj4.x == -INFINITY) continue;
+        const float n4[4] = { tr[0] * nj4.x + tr[1] * nj4.y + tr[2] * nj4.z + tr[3] * nj4.w, tr[4] * nj4.x + tr[5] * nj4.y + tr[6] * nj4.z + tr[7] * nj4.w,
+                              tr[8] * nj4.x + tr[9] * nj4.y + tr[10] * nj4.z + tr[11] * nj4.w, tr[12] * nj4.x + tr[13] * nj4.y + tr[14] * nj4.z + tr[15] * nj4.w };
+        const V3 s2t = xf(tr, cps);
+        const float sx = s2t.x * d.fx / s2t.z + d.mx, sy = s2t.y * d.fy / s2t.z + d.my;
+        const int tx = (int)roundf(sx), ty = (int)roundf(sy);
+        if (!(tx >= 0 && ty >= 0 && tx < (int)d.W && ty < (int)d.H)) continue;
+        float ci[4], ni[4];
+        bilinear<4>(fi.d_cameraposDownsampled, sx, sy, d.W, d.H, ci);
+        if (!(ci[2] > d.depthMin && ci[2] < d.depthMax)) continue;
+        bilinear<4>(fi.d_normalsDownsampled, sx, sy, d.W, d.H, ni);
+        if (ni[0] == -INFINITY) continue;
+        const V3 cpt = mk(ci[0], ci[1], ci[2]), nt = mk(ni[0], ni[1], ni[2]);
+        const float dist = length(s2t - cpt);
+        const float dNormal = n4[0] * ni[0] + n4[1] * ni[1] + n4[2] * ni[2] + n4[3] * ni[3];
+        if (!(dNormal >= d.normalThresh && dist <= d.distThresh)) continue;
+        float Ji[18], Jj[18];
+        if (hasI) lie_jac_i(Tji, Ti, cps, Ji);
+        if (hasJ) lie_jac_j(Tii, Tj, cps, Jj);
+        if (d.wDepth > 0.0f) {
+            const float res = dot(cpt - s2t, nt);
+            const float w = d.wDepth * pairW * powf(fmaxf(0.0f, 1.0f - cpt.z / 2.0f), 2.5f);       // (:256)
+            float ri[6], rj[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                ri[c] = hasI ? -(Ji[c] * nt.x + Ji[6 + c] * nt.y + Ji[12 + c] * nt.z) : 0.0f;
+                rj[c] = hasJ ? -(Jj[c] * nt.x + Jj[6 + c] * nt.y + Jj[12 + c] * nt.z) : 0.0f;
+            }
+            accum_rows(acc, ri, rj, res, w, hasI, hasJ);
+        }
+        if (d.wColor > 0.0f) {
+            float dI[2], It;
+            bilinear<2>(fi.d_intensityDerivsDownsampled, sx, sy, d.W, d.H, dI);
+            bilinear<1>(fi.d_intensityDownsampled, sx, sy, d.W, d.H, &It);
+            const float cres = It - fj.d_intensityDownsampled[idx];
+            if (dI[0] != -INFINITY && fabsf(cres) < d.colorThresh && sqrtf(dI[0] * dI[0] + dI[1] * dI[1]) > d.colorGradientMin) {
+                const float z2 = s2t.z * s2t.z;
+                const float P00 = d.fx / s2t.z, P02 = -d.fx * s2t.x / z2, P11 = d.fy / s2t.z, P12 = -d.fy * s2t.y / z2;
+                float ri[6], rj[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    ri[c] = hasI ? dI[0] * (P00 * Ji[c] + P02 * Ji[12 + c]) + dI[1] * (P11 * Ji[6 + c] + P12 * Ji[12 + c]) : 0.0f;
+                    rj[c] = hasJ ? dI[0] * (P00 * Jj[c] + P02 * Jj[12 + c]) + dI[1] * (P11 * Jj[6 + c] + P12 * Jj[12 + c]) : 0.0f;
+                }
+                const float w = d.wColor * pairW * fmaxf(0.0f, 1.0f - fabsf(cres) / (1.15f * d.colorThresh));   // (:294)
+                accum_rows(acc, ri, rj, cres, w, hasI, hasJ);
+            }
+        }
+    }
+    // fixed-shape reduction: warp tree, then the 4 warps in order
+#pragma unroll
+    for (int k = 0; k < 90; ++k) { const float v = warp_sum(acc[k]); if ((threadIdx.x & 31) == 0) sAcc[threadIdx.x >> 5][k] = v; }
+    __syncthreads();
+    if (threadIdx.x < 90) d.pairOut[(size_t)(i * N + j) * 90 + threadIdx.x] = sAcc[0][threadIdx.x] + sAcc[1][threadIdx.x] + sAcc[2][threadIdx.x] + sAcc[3][threadIdx.x];
+}
+// dense system in the reference's layout: entry (row, col) of the (6N)^2 matrix, translation-first per image, symmetric
+__device__ __forceinline__ int tri_index(int a, int b) { if (a > b) { const int t = a; a = b; b = t; } return a * 6 - (a * (a - 1)) / 2 + (b - a); }   // (a<=b) -> 0..20
+__global__ void dense_assemble_kernel(const DenseArgs d) {
+    const unsigned N = d.N, dim = 6 * N;
+    if (d.scal[SC_DONE] != 0) return;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < dim * dim + dim; e += gridDim.x * blockDim.x) {
+        if (e >= dim * dim) {            // J^T r
+            const unsigned r = e - dim * dim, v = r / 6, a = r % 6;
+            float sum = 0.0f;
+            for (unsigned o = 0; o < N; ++o) {
+                if (o == v) continue;
+                const unsigned lo = o < v ? o : v, hi = o < v ? v : o;
+                if (d.pairW[lo * N + hi] == 0.0f) continue;
+                sum += d.pairOut[(size_t)(lo * N + hi) * 90 + (v == lo ? 78 : 84) + a];
+            }
+            d.Jtr[r] = sum;
+            continue;
+        }
+        const unsigned row = e / dim, col = e % dim, rv = row / 6, cv = col / 6, ra = row % 6, cb = col % 6;
+        float val = 0.0f;
+        if (rv == cv) {
+            for (unsigned o = 0; o < N; ++o) {
+                if (o == rv) continue;
+                const unsigned lo = o < rv ? o : rv, hi = o < rv ? rv : o;
+                if (d.pairW[lo * N + hi] == 0.0f) continue;
+                val += d.pairOut[(size_t)(lo * N + hi) * 90 + (rv == lo ? 0 : 21) + tri_index((int)ra, (int)cb)];
+            }
+        } else {
+            const unsigned lo = rv < cv ? rv : cv, hi = rv < cv ? cv : rv;
+            if (d.pairW[lo * N + hi] != 0.0f) {
+                // ij record: [a over image lo (=i)][b over image hi (=j)]
+                const unsigned a = (rv == lo) ? ra : cb, b = (rv == lo) ? cb : ra;
+                val = d.pairOut[(size_t)(lo * N + hi) * 90 + 42 + a * 6 + b];
+            }
+        }
+        d.JtJ[e] = val;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.scal[SC_DENSE_ON] = (d.scal[SC_DENSE_OVERLAP] > 0) ? 1u : 0u;
+}
+
 // ---- small kernels behind the reference-named stubs -------------------------------------------------------------
 __global__ void poses_to_matrices_kernel(const float* rot, const float* trans, unsigned n, float* T, float* Tinv, const int* valid) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -590,6 +908,18 @@ __global__ void poses_to_matrices_kernel(const float* rot, const float* trans, u
     pose_to_matrix(ld3(rot, k), ld3(trans, k), M);
     for (int e = 0; e < 16; ++e) T[16 * k + e] = M[e];
     if (Tinv) { float Mi[16]; mat4_inverse(M, Mi); for (int e = 0; e < 16; ++e) Tinv[16 * k + e] = Mi[e]; }
+}
+// first kernel of a dense GN iteration: matrices for this iteration's poses + reset of the pair counters -- skipped once an
+// earlier iteration has converged, so the statistics of the last iteration that ran stay readable
+__global__ void dense_begin_kernel(const float* rot, const float* trans, unsigned n, float* T, float* Tinv, unsigned* scal) {
+    if (scal[SC_DONE] != 0) return;
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) { scal[SC_DENSE_ON] = 0; scal[SC_DENSE_OVERLAP] = 0; scal[SC_DENSE_PAIRS] = 0; }
+    if (k >= n) return;
+    float M[16], Mi[16];
+    pose_to_matrix(ld3(rot, k), ld3(trans, k), M);
+    mat4_inverse(M, Mi);
+    for (int e = 0; e < 16; ++e) { T[16 * k + e] = M[e]; Tinv[16 * k + e] = Mi[e]; }
 }
 __global__ void matrices_to_poses_kernel(const float* T, unsigned n, float* rot, float* trans, const int* valid) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -709,6 +1039,28 @@ static int run_gn(const BFSolverInput* in, const BFSolverState* st, const BFSolv
     a.rowStart = ws->rowStart; a.entries = ws->entries; a.segCount = ws->segCount; a.segs = ws->segs;
     a.offBlk = ws->offBlk; a.segMom = ws->segMom; a.diagBlk = ws->diagBlk; a.partials = ws->partials; a.scal = ws->scal;
     a.wSparse = in->weightsSparse[nIter]; a.nLin = par->nLinIterations; a.isLastGn = isLast ? 1 : 0; a.maxGrid = ws->maxGrid;
+    const float wDepth = in->weightsDenseDepth ? in->weightsDenseDepth[nIter] : 0.0f, wColor = in->weightsDenseColor ? in->weightsDenseColor[nIter] : 0.0f;
+    const bool dense = (wDepth > 0.0f || wColor > 0.0f) && in->d_cacheFrames != nullptr;
+    a.denseJtJ = ws->denseJtJ; a.denseJtr = ws->denseJtr; a.useDense = dense ? 1 : 0;
+    if (dense) {
+        // BuildDenseSystem (SolverBundling.cu:308-471) for this iteration's poses: 1 pose kernel + 3 dense kernels, no host sync
+        DenseArgs d;
+        d.frames = in->d_cacheFrames; d.valid = in->d_validImages; d.T = st->d_xTransforms; d.Tinv = st->d_xTransformInverses;
+        d.N = a.N; d.W = in->denseDepthWidth; d.H = in->denseDepthHeight;
+        d.fx = in->intrinsics[0]; d.fy = in->intrinsics[1]; d.mx = in->intrinsics[2]; d.my = in->intrinsics[3];
+        d.distThresh = par->denseDistThresh; d.normalThresh = par->denseNormalThresh; d.colorThresh = par->denseColorThresh;
+        d.colorGradientMin = par->denseColorGradientMin; d.depthMin = par->denseDepthMin; d.depthMax = par->denseDepthMax;
+        d.subsample = par->denseOverlapCheckSubsampleFactor ? par->denseOverlapCheckSubsampleFactor : 1; d.usePairwise = par->useDenseDepthAllPairwise ? 1 : 0;
+        d.wDepth = wDepth; d.wColor = wColor;
+        d.pairW = ws->pairW; d.pairOut = ws->pairOut; d.JtJ = ws->denseJtJ; d.Jtr = ws->denseJtr; d.scal = ws->scal;
+        dense_begin_kernel<<<(a.N + 127) / 128, 128, 0, stream()>>>(st->d_xRot, st->d_xTrans, a.N, st->d_xTransforms, st->d_xTransformInverses, ws->scal);
+        dense_pair_weight_kernel<<<dim3(a.N, a.N), 512, 0, stream()>>>(d);
+        dense_build_kernel<<<dim3(a.N, a.N), 128, 0, stream()>>>(d);
+        const unsigned entries = 36 * a.N * a.N + 6 * a.N;
+        dense_assemble_kernel<<<(entries + 255) / 256, 256, 0, stream()>>>(d);
+        BF_CHECK(cudaGetLastError());
+        g_launchCount += 4;
+    }
     void* args[] = { (void*)&a };
     ++g_launchCount;
     // Path 1: one thread-block cluster (hardware barrier).  Chosen when a cluster's warps cover the rows within ~8 rows per warp.
@@ -762,8 +1114,9 @@ static int run_gn(const BFSolverInput* in, const BFSolverState* st, const BFSolv
 static int solve_impl(const BFSolverInput* in, const BFSolverState* st, const BFSolverParameters* par, bool rebuild) {
     if (in->numberOfImages < 2 || par->nNonLinearIterations == 0) return 0;
     for (unsigned k = 0; k < par->nNonLinearIterations; ++k)
-        if ((in->weightsDenseDepth && in->weightsDenseDepth[k] > 0.0f) || (in->weightsDenseColor && in->weightsDenseColor[k] > 0.0f)) {
-            set_last_error("bfSolverSolve: dense depth/colour term not built yet (SURVEY.md row a13)", cudaErrorNotSupported);
+        if (((in->weightsDenseDepth && in->weightsDenseDepth[k] > 0.0f) || (in->weightsDenseColor && in->weightsDenseColor[k] > 0.0f)) &&
+            in->d_cacheFrames != nullptr && in->numberOfImages > BF_DENSE_MAX_IMAGES) {
+            set_last_error("bfSolverSolve: the dense depth/colour term is built for <= 64 images (chunk-sized problems) in this round", cudaErrorNotSupported);
             return (int)cudaErrorNotSupported;
         }
     SolverWs* ws;
@@ -795,8 +1148,8 @@ BF_API int bfSolverGetStats(const BFSolverState* st, unsigned long long out[8]) 
     BF_CHECK(cudaMemcpyAsync(s, ws->scal, sizeof(s), cudaMemcpyDeviceToHost, stream()));
     BF_CHECK(cudaStreamSynchronize(stream()));
     float md; memcpy(&md, &s[SC_MAXDELTA_BITS], 4);
-    out[0] = s[SC_GN_RUN]; out[1] = s[SC_PCG_RUN]; out[2] = s[SC_NUM_SEG] / 2; out[3] = s[SC_NUM_VALID];
-    out[4] = (unsigned long long)(md * 1e6f); out[5] = s[SC_ERROR]; out[6] = s[SC_DONE]; out[7] = 0;
+    out[0] = s[SC_GN_RUN]; out[1] = s[SC_PCG_RUN]; out[2] = s[SC_NUM_SEG] / 2; out[3] = s[SC_DENSE_OVERLAP];
+    out[4] = (unsigned long long)(md * 1e6f); out[5] = s[SC_ERROR]; out[6] = s[SC_DONE]; out[7] = s[SC_DENSE_PAIRS];
     return 0;
 }
 
@@ -826,6 +1179,7 @@ BF_API int bfSolverReleaseWorkspace(const BFSolverState* st) {
     SolverWs& w = it->second;
     cudaFree(w.rowCount); cudaFree(w.rowStart); cudaFree(w.cursor); cudaFree(w.entries); cudaFree(w.segCount); cudaFree(w.segs);
     cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.scal);
+        cudaFree(w.pairW); cudaFree(w.pairOut); cudaFree(w.denseJtJ); cudaFree(w.denseJtr);
     g_ws.erase(it);
     return 0;
 }

@@ -862,7 +862,7 @@ __device__ __forceinline__ bool probe_voxel(const BFHashParams& hp, const BFDept
     return true;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 reintegrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hpOld, const __grid_constant__ BFHashParams hpNew,
                    const __grid_constant__ BFDepthCameraParams cp, const float* __restrict__ depthImg, const uchar4* __restrict__ colorImg,
                    const unsigned* __restrict__ countPtr, const unsigned char* __restrict__ listFlags, unsigned* ctrs, int* __restrict__ live) {

@@ -12,6 +12,30 @@ from . import _capi as capi
 from ._capi import BFSolverInput, BFSolverParameters, BFSolverState, BFSolverStateAnalysis
 
 
+class DeviceCache:
+    """Device-side array of ``CUDACachedFrame`` structs (FL/CUDACacheUtil.h:41-53) -- what ``CUDACache::getCacheFramesGPU()``
+    hands the solver.  Built here from host arrays (dict per frame: depth, campos, intensity, intensityDerivs, normalsU, normals)."""
+
+    def __init__(self, caches, intrinsics, device):
+        import torch
+        self.width, self.height = caches[0]["depth"].shape[1], caches[0]["depth"].shape[0]
+        self.intrinsics = tuple(float(x) for x in intrinsics)
+        self._keep = []
+        arr = (capi.BFCUDACachedFrame * len(caches))()
+        names = {"depth": "d_depthDownsampled", "campos": "d_cameraposDownsampled", "intensity": "d_intensityDownsampled",
+                 "intensityDerivs": "d_intensityDerivsDownsampled", "normalsU": "d_normalsDownsampledUCHAR4", "normals": "d_normalsDownsampled"}
+        for k, c in enumerate(caches):
+            for src, dst in names.items():
+                t = torch.from_numpy(np.ascontiguousarray(c[src])).to(device)
+                self._keep.append(t)
+                setattr(arr[k], dst, t.data_ptr())
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.d_frames = torch.from_numpy(raw).to(device)
+
+    def getCacheFramesGPU(self):
+        return self.d_frames
+
+
 class CUDASolverBundling:
     def __init__(self, maxNumberOfImages: int, maxNumResiduals: int, device="cuda:0", max_res_thresh: float = 0.08):
         import torch
@@ -63,7 +87,7 @@ class CUDASolverBundling:
         t.cuda.set_device(self.device)
         self.lib.bfSetStream(C.c_void_p(t.cuda.current_stream(self.device).cuda_stream))
 
-    def _make_input(self, d_corr, nCorr, d_valid, nImages, wS, wD, wC):
+    def _make_input(self, d_corr, nCorr, d_valid, nImages, wS, wD, wC, cudaCache=None):
         si = BFSolverInput()
         si.d_correspondences = d_corr.data_ptr()
         si.d_variablesToCorrespondences = self.d_variablesToCorrespondences.data_ptr()
@@ -71,7 +95,14 @@ class CUDASolverBundling:
         si.numberOfCorrespondences, si.numberOfImages = nCorr, nImages
         si.maxNumberOfImages, si.maxCorrPerImage = self.m_maxNumberOfImages, self.m_maxCorrPerImage
         si.d_validImages = d_valid.data_ptr() if d_valid is not None else None
-        si.d_cacheFrames = None
+        if cudaCache is not None:       # cpp:237-244
+            si.d_cacheFrames = cudaCache.getCacheFramesGPU().data_ptr()
+            si.denseDepthWidth, si.denseDepthHeight = cudaCache.width, cudaCache.height
+            for k in range(4):
+                si.intrinsics[k] = cudaCache.intrinsics[k]
+            self._cache_keep = cudaCache
+        else:
+            si.d_cacheFrames = None
         si.maxNumDenseImPairs = self.m_maxNumberOfImages * (self.m_maxNumberOfImages - 1) // 2
         arrs = [np.ascontiguousarray(w, np.float32) for w in (wS, wD, wC)]
         fp = C.POINTER(C.c_float)
@@ -93,7 +124,7 @@ class CUDASolverBundling:
 
     def solve(self, d_correspondences, numberOfCorrespondences, d_validImages, numberOfImages, nNonLinearIterations, nLinearIterations,
               weightsSparse, weightsDenseDepth=None, weightsDenseColor=None, d_rotationAnglesUnknowns=None, d_translationUnknowns=None,
-              rebuildJT=True, findMaxResidual=False):
+              rebuildJT=True, findMaxResidual=False, cudaCache=None, usePairwiseDense=True):
         """CUDASolverBundling::solve (cpp:187-284).  d_correspondences: uint8/int32 cuda tensor holding EntryJ[]; unknowns: float32
         cuda tensors [N,3] updated in place.  Asynchronous unless findMaxResidual."""
         self._bind_stream()
@@ -102,8 +133,9 @@ class CUDASolverBundling:
         wC = weightsDenseColor if weightsDenseColor is not None else [0.0] * len(weightsSparse)
         self.m_solverState.d_xRot = d_rotationAnglesUnknowns.data_ptr()
         self.m_solverState.d_xTrans = d_translationUnknowns.data_ptr()
-        si = self._make_input(d_correspondences, numberOfCorrespondences, d_validImages, numberOfImages, weightsSparse, wD, wC)
+        si = self._make_input(d_correspondences, numberOfCorrespondences, d_validImages, numberOfImages, weightsSparse, wD, wC, cudaCache)
         par = self._params(nNonLin, nLinearIterations, weightsSparse, wD, wC)
+        par.useDenseDepthAllPairwise = 1 if usePairwiseDense else 0
         capi.check(self.lib.bfSolverSolve(C.byref(si), C.byref(self.m_solverState), C.byref(par)), "bfSolverSolve")
         if findMaxResidual:
             capi.check(self.lib.bfSolverMaxResidual(C.byref(si), C.byref(self.m_solverState), C.byref(par), self.d_maxOut.data_ptr()), "bfSolverMaxResidual")
@@ -132,7 +164,8 @@ class CUDASolverBundling:
         self._bind_stream()
         out = (C.c_ulonglong * 8)()
         capi.check(self.lib.bfSolverGetStats(C.byref(self.m_solverState), out), "bfSolverGetStats")
-        return {"gn": out[0], "pcg": out[1], "pairs": out[2], "max_delta": out[4] * 1e-6, "error": out[5], "converged": out[6]}
+        return {"gn": out[0], "pcg": out[1], "pairs": out[2], "max_delta": out[4] * 1e-6, "error": out[5], "converged": out[6],
+                "dense_overlap_pairs": out[3], "dense_weighted_pairs": out[7]}
 
     def getVarToCorrNumEntriesPerRow(self):
         return self.d_numEntriesPerRow

@@ -208,3 +208,95 @@ def ba_reference_f64(corr, rot0, trans0, n_gn: int = 10, w_sparse: float = 1.0):
             break
     out = [se3_log(Tk) for Tk in T]
     return np.array([o[0] for o in out]), np.array([o[1] for o in out])
+
+
+# ------------------------------------------------------------------------------------------------
+# dense cache frames (FL/CUDACache.cpp:45-86 without the optional bilateral / Gaussian pre-filters)
+# ------------------------------------------------------------------------------------------------
+def cache_intrinsics(W_in=640, H_in=480, cw=80, ch=60):
+    """FL/CUDACache.cpp:20-24: intrinsics of the down-sampled cache from the input intrinsics."""
+    fx = 525.0 * W_in / 640.0; fy = fx
+    mx, my = (W_in - 1) / 2.0, (H_in - 1) / 2.0
+    return (np.float32(fx * cw / W_in), np.float32(fy * ch / H_in), np.float32(mx * (cw - 1) / (W_in - 1)), np.float32(my * (ch - 1) / (H_in - 1)))
+
+
+def make_cache_frame(depth: np.ndarray, color: np.ndarray, cw: int = 80, ch: int = 60) -> dict:
+    """One CUDACachedFrame (FL/CUDACacheUtil.h:41-53) as host arrays: depth [ch,cw] f32, campos [ch,cw,4] f32, normals [ch,cw,4] f32,
+    normalsU [ch,cw,4] u8, intensity [ch,cw] f32, intensityDerivs [ch,cw,2] f32.  Invalid = -inf (0 for the uchar4 normals)."""
+    F = np.float32
+    H_in, W_in = depth.shape
+    fx = fy = F(525.0 * W_in / 640.0); mx, my = F((W_in - 1) / 2.0), F((H_in - 1) / 2.0)
+    u, v = np.meshgrid(np.arange(W_in, dtype=F), np.arange(H_in, dtype=F))
+    valid = depth != -np.inf
+    cam = np.full((H_in, W_in, 4), -np.inf, F)
+    with np.errstate(invalid="ignore"):
+        cam[..., 0] = np.where(valid, (u - mx) / fx * depth, -np.inf)
+        cam[..., 1] = np.where(valid, (v - my) / fy * depth, -np.inf)
+        cam[..., 2] = np.where(valid, depth, -np.inf)
+        cam[..., 3] = np.where(valid, F(1.0), -np.inf)
+    # computeNormals (FL/CUDAImageUtil.cu:404-431): -normalize((P(x,y+1)-P(x,y-1)) x (P(x+1,y)-P(x-1,y))), all five valid
+    nrm = np.full((H_in, W_in, 4), -np.inf, F)
+    P = cam[..., :3]
+    ok = valid.copy(); ok[1:-1, 1:-1] &= valid[2:, 1:-1] & valid[:-2, 1:-1] & valid[1:-1, 2:] & valid[1:-1, :-2]
+    ok[0, :] = ok[-1, :] = False; ok[:, 0] = ok[:, -1] = False
+    with np.errstate(invalid="ignore", divide="ignore"):
+        a = P[2:, 1:-1] - P[:-2, 1:-1]; b = P[1:-1, 2:] - P[1:-1, :-2]
+        n = np.cross(a, b).astype(F)
+        l = np.sqrt((n * n).sum(-1)).astype(F)
+        inner = ok[1:-1, 1:-1] & (l > 0)
+        nn = np.where(inner[..., None], n / -l[..., None], -np.inf)
+    nrm[1:-1, 1:-1, :3] = nn
+    nrm[1:-1, 1:-1, 3] = np.where(inner, F(0.0), -np.inf)
+    # nearest-neighbour resample with scale (in-1)/(out-1)  (FL/CUDAImageUtil.cu:93-110)
+    xs = (np.arange(cw, dtype=F) * F((W_in - 1) / (cw - 1)) + F(0.5)).astype(np.int64)
+    ys = (np.arange(ch, dtype=F) * F((H_in - 1) / (ch - 1)) + F(0.5)).astype(np.int64)
+    yy, xx = np.meshgrid(ys, xs, indexing="ij")
+    out = {"depth": np.ascontiguousarray(depth[yy, xx]), "campos": np.ascontiguousarray(cam[yy, xx]), "normals": np.ascontiguousarray(nrm[yy, xx])}
+    nd = out["normals"]
+    nu = np.zeros((ch, cw, 4), np.uint8)
+    vn = nd[..., 0] != -np.inf
+    with np.errstate(invalid="ignore"):
+        q = (np.where(vn[..., None], nd[..., :3], 0) + F(1.0)) / F(2.0)
+        r = q * F(255)
+        nu[..., :3] = np.where(vn[..., None], np.where(r >= 0, np.floor(r + F(0.5)), np.ceil(r - F(0.5))), 0).astype(np.uint8)   # (uchar)round(p*255)
+    out["normalsU"] = nu
+    c = color[yy, xx].astype(F)
+    inten = ((F(0.299) * c[..., 0] + F(0.587) * c[..., 1] + F(0.114) * c[..., 2]) / F(255.0)).astype(F)
+    out["intensity"] = np.ascontiguousarray(inten)
+    # computeIntensityDerivatives (FL/CUDAImageUtil.cu:260-300): Sobel / 8 on the interior
+    dv = np.full((ch, cw, 2), -np.inf, F)
+    I = inten
+    ru = (-I[:-2, :-2] + I[:-2, 2:] - F(2) * I[1:-1, :-2] + F(2) * I[1:-1, 2:] - I[2:, :-2] + I[2:, 2:]) / F(8.0)
+    rv = (-I[:-2, :-2] - F(2) * I[:-2, 1:-1] - I[:-2, 2:] + I[2:, :-2] + F(2) * I[2:, 1:-1] + I[2:, 2:]) / F(8.0)
+    dv[1:-1, 1:-1, 0] = ru; dv[1:-1, 1:-1, 1] = rv
+    out["intensityDerivs"] = dv
+    return out
+
+
+def make_dense_ba_problem(n_images: int = 11, stride: int = 3, start: int = 100, corr_per_pair: int = 25, noise: float = 0.002,
+                          perturb_rot: float = 0.01, perturb_trans: float = 0.015, seed: int = 17, W: int = 640, H: int = 480):
+    """A local-chunk problem (FL/OnlineBundler.cpp:41: 11 frames) with BOTH terms: sparse correspondences between all pairs and
+    dense 80x60 cache frames rendered from the synthetic room at the ground-truth poses."""
+    # noise-free depth: the reference smooths depth (bilateral, sigma_d 1.0 sigma_r 0.05) before it takes normals; that filter
+    # belongs to row a20 (CUDACache::storeFrame) and is not part of this generator yet
+    frames = [make_frame(start + stride * k, W, H, noise=False, dropout=0.0) for k in range(n_images)]
+    gt = np.stack([f[2].astype(np.float64) for f in frames])
+    caches = [make_cache_frame(f[0], f[1]) for f in frames]
+    rng = np.random.Generator(np.random.MT19937(seed))
+    pairs = [(i, j) for i in range(n_images) for j in range(i + 1, n_images)]
+    corr = np.zeros(len(pairs) * corr_per_pair, dtype=[("i", "<u4"), ("j", "<u4"), ("pi", "<f4", 3), ("pj", "<f4", 3)])
+    k = 0
+    for (i, j) in pairs:
+        z = rng.uniform(0.6, 2.5, corr_per_pair); xy = rng.uniform(-0.4, 0.4, (corr_per_pair, 2)) * z[:, None]
+        pi = np.concatenate([xy, z[:, None]], 1)
+        X = pi @ gt[i][:3, :3].T + gt[i][:3, 3]
+        Tj = np.linalg.inv(gt[j]); pj = X @ Tj[:3, :3].T + Tj[:3, 3]
+        sl = slice(k, k + corr_per_pair)
+        corr["i"][sl], corr["j"][sl] = i, j
+        corr["pi"][sl] = pi + rng.standard_normal(pi.shape) * noise; corr["pj"][sl] = pj + rng.standard_normal(pj.shape) * noise
+        k += corr_per_pair
+    rot = np.zeros((n_images, 3), np.float32); trans = np.zeros((n_images, 3), np.float32)
+    for n in range(n_images):
+        T = gt[n] if n == 0 else se3_exp(rng.standard_normal(3) * perturb_rot, rng.standard_normal(3) * perturb_trans) @ gt[n]
+        rot[n], trans[n] = se3_log(T)
+    return {"corr": corr, "gt": gt, "init_rot": rot, "init_trans": trans, "caches": caches, "pairs": pairs, "intrinsics": cache_intrinsics(W, H)}

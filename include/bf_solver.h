@@ -165,7 +165,8 @@ int bfSolverSolve(const BFSolverInput* input, const BFSolverState* state, const 
 
 /* statistics of the last bfSolverSolve on this state (synchronises):
  * out[0] = GN iterations run, out[1] = PCG iterations run (all GN iterations), out[2] = image pairs (6x6 blocks),
- * out[3] = valid correspondences, out[4] = last max|delta| * 1e6 (fixed point) */
+ * out[3] = overlapping dense image pairs (last GN iteration), out[4] = last max|delta| * 1e6 (fixed point), out[5] = error flag,
+ * out[6] = converged early, out[7] = dense pairs with non-zero weight */
 int bfSolverGetStats(const BFSolverState* state, unsigned long long out[8]);
 
 /* CUDASolverBundling::getMaxResidual's device part (FL/Solver/CUDASolverBundling.cpp:313-329) without the host

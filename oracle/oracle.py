@@ -239,3 +239,80 @@ def energy(corr, rot, trans, w=1.0) -> float:
     L = _bind_solver(lib())
     corr = np.ascontiguousarray(corr)
     return float(L.orc_solver_energy(corr.ctypes.data, len(corr), np.ascontiguousarray(rot, np.float32), np.ascontiguousarray(trans, np.float32), w))
+
+
+class OrcCacheFrame(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("campos", C.c_void_p), ("intensity", C.c_void_p), ("intensityDerivs", C.c_void_p),
+                ("normalsU", C.c_void_p), ("normals", C.c_void_p)]
+
+
+class OrcDenseParams(C.Structure):
+    _fields_ = [("W", C.c_uint), ("H", C.c_uint), ("fx", C.c_float), ("fy", C.c_float), ("mx", C.c_float), ("my", C.c_float),
+                ("distThresh", C.c_float), ("normalThresh", C.c_float), ("colorThresh", C.c_float), ("colorGradientMin", C.c_float),
+                ("depthMin", C.c_float), ("depthMax", C.c_float), ("subsample", C.c_uint), ("usePairwise", C.c_int)]
+
+
+def dense_params(intrinsics, W=80, H=60, pairwise=True) -> OrcDenseParams:
+    """defaults of FriedLiver/zParametersBundlingDefault.txt:22-28"""
+    d = OrcDenseParams()
+    d.W, d.H = W, H
+    d.fx, d.fy, d.mx, d.my = [float(x) for x in intrinsics]
+    d.distThresh, d.normalThresh, d.colorThresh, d.colorGradientMin, d.depthMin, d.depthMax = 0.15, 0.97, 0.1, 0.005, 0.5, 4.0
+    d.subsample, d.usePairwise = 4, 1 if pairwise else 0
+    return d
+
+
+def _pack_frames(caches):
+    arr = (OrcCacheFrame * len(caches))()
+    keep = []
+    for k, c in enumerate(caches):
+        for name in ("depth", "campos", "intensity", "intensityDerivs", "normalsU", "normals"):
+            a = np.ascontiguousarray(c[name]); keep.append(a)
+            setattr(arr[k], name, a.ctypes.data)
+    return arr, keep
+
+
+def solve(corr, rot0, trans0, n_gn, n_pcg, w_sparse, w_depth=None, w_color=None, caches=None, intrinsics=None, valid=None,
+          max_corr_per_image=4000, pairwise=True, fast=False):
+    """The complete solveBundlingStub (sparse + dense depth/colour)."""
+    L = _bind_solver(lib(fast))
+    fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    L.orc_solver_solve.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, fp, fp, C.c_uint, C.c_uint, fp, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, ip, ip, C.c_uint * 4]
+    L.orc_solver_solve.restype = C.c_int
+    corr = np.ascontiguousarray(corr).copy()
+    N = len(rot0)
+    rot, trans = np.ascontiguousarray(rot0, np.float32).copy(), np.ascontiguousarray(trans0, np.float32).copy()
+    wS = np.ascontiguousarray(w_sparse, np.float32)
+    wD = np.ascontiguousarray(w_depth if w_depth is not None else np.zeros(n_gn), np.float32)
+    wC = np.ascontiguousarray(w_color if w_color is not None else np.zeros(n_gn), np.float32)
+    table, rows = np.zeros(N * max_corr_per_image, np.int32), np.zeros(N, np.int32)
+    stats = (C.c_uint * 4)()
+    frames, keep, dp = None, None, None
+    if caches is not None:
+        frames, keep = _pack_frames(caches)
+        dp = dense_params(intrinsics, caches[0]["depth"].shape[1], caches[0]["depth"].shape[0], pairwise)
+    v = np.ascontiguousarray(valid, np.int32) if valid is not None else None
+    rc = L.orc_solver_solve(corr.ctypes.data, len(corr), N, max_corr_per_image, rot, trans, n_gn, n_pcg, wS, wD.ctypes.data, wC.ctypes.data,
+                            C.cast(frames, C.c_void_p) if frames is not None else None, C.cast(C.pointer(dp), C.c_void_p) if dp is not None else None,
+                            v.ctypes.data if v is not None else None, table, rows, stats)
+    assert rc == 0
+    return {"rot": rot, "trans": trans, "gn": stats[0], "pcg": stats[1], "overlap_pairs": stats[2], "weighted_pairs": stats[3], "corr": corr, "rows": rows}
+
+
+def build_dense(rot, trans, caches, intrinsics, w_depth, w_color, valid=None, pairwise=True):
+    """dense J^T J [(6N)^2] and J^T r [6N] at the given poses (translation-first ordering per image)."""
+    L = _bind_solver(lib())
+    fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    L.orc_solver_build_dense.argtypes = [fp, fp, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, fp, fp, C.c_uint * 2]
+    L.orc_solver_build_dense.restype = C.c_uint
+    N = len(rot)
+    frames, keep = _pack_frames(caches)
+    dp = dense_params(intrinsics, caches[0]["depth"].shape[1], caches[0]["depth"].shape[0], pairwise)
+    JtJ, Jtr = np.zeros((6 * N) ** 2, np.float32), np.zeros(6 * N, np.float32)
+    pairs = (C.c_uint * 2)()
+    v = np.ascontiguousarray(valid, np.int32) if valid is not None else None
+    L.orc_solver_build_dense(np.ascontiguousarray(rot, np.float32), np.ascontiguousarray(trans, np.float32), N, C.cast(frames, C.c_void_p),
+                             C.cast(C.pointer(dp), C.c_void_p), v.ctypes.data if v is not None else None, w_depth, w_color, JtJ, Jtr, pairs)
+    return JtJ.reshape(6 * N, 6 * N), Jtr, (pairs[0], pairs[1])

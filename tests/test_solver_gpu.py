@@ -145,3 +145,40 @@ def test_global_scale_problem_properties(cuda_device):
     g3b = gpu_solve(cuda_device, prob, 3, 150, max_images=2000)
     np.testing.assert_array_equal(g3["rot"], g3b["rot"])
     assert g3["stats"]["pairs"] == len(prob["pairs"])
+
+
+# ---- dense depth / colour term (row a13) ----------------------------------------------------------------------------
+def gpu_solve_dense(dev, prob, n_gn, n_pcg, wS, wD, wC, corr=None):
+    import torch
+    from bundlefusion_b200.solver import DeviceCache
+    N = len(prob["init_rot"])
+    c = prob["corr"] if corr is None else corr
+    corr_t = torch.from_numpy(np.ascontiguousarray(c).view(np.uint8).reshape(-1).copy()).to(dev) if len(c) else torch.zeros(32, dtype=torch.uint8, device=dev)
+    rot = torch.from_numpy(prob["init_rot"].copy()).to(dev); trans = torch.from_numpy(prob["init_trans"].copy()).to(dev)
+    valid = torch.ones(N, dtype=torch.int32, device=dev)
+    cache = DeviceCache(prob["caches"], prob["intrinsics"], dev)
+    solver = CUDASolverBundling(N, max(len(c), 1000 * N), dev)
+    solver.solve(corr_t, len(c), valid, N, n_gn, n_pcg, wS, wD, wC, d_rotationAnglesUnknowns=rot, d_translationUnknowns=trans, cudaCache=cache)
+    torch.cuda.synchronize()
+    return {"rot": rot.cpu().numpy(), "trans": trans.cpu().numpy(), "stats": solver.getStats()}
+
+
+def test_dense_only_solve_matches_oracle(cuda_device):
+    prob = synth.make_dense_ba_problem(5, stride=3, perturb_rot=0.004, perturb_trans=0.008, W=320, H=240)
+    wS, wD, wC = [0.0] * 3, [1.0, 2.0, 3.0], [0.0] * 3
+    g = gpu_solve_dense(cuda_device, prob, 3, 60, wS, wD, wC, corr=prob["corr"][:0])
+    o = orc.solve(prob["corr"][:0], prob["init_rot"], prob["init_trans"], 3, 60, wS, wD, wC, prob["caches"], prob["intrinsics"])
+    assert g["stats"]["dense_overlap_pairs"] == o["overlap_pairs"] and g["stats"]["dense_weighted_pairs"] == o["weighted_pairs"] > 0
+    assert g["stats"]["gn"] == o["gn"]
+    assert rel_l2(np.c_[g["rot"], g["trans"]], np.c_[o["rot"], o["trans"]]) < 1e-4
+
+
+def test_local_chunk_sparse_plus_dense_matches_oracle(cuda_device):
+    """The reference's local BA: 11 frames, sparse weight 1, dense depth weights 1, 2 (FL/SBA.cpp:28-31), 2 GN x 100 PCG; plus the
+    colour term switched on (global end-of-scan weights use 0.1, :34-38) to cover computeJacobianBlockIntensityRow."""
+    prob = synth.make_dense_ba_problem(11, stride=3, W=320, H=240)
+    for wC in ([0.0, 0.0], [0.1, 0.1]):
+        g = gpu_solve_dense(cuda_device, prob, 2, 100, [1.0, 1.0], [1.0, 2.0], wC)
+        o = orc.solve(prob["corr"], prob["init_rot"], prob["init_trans"], 2, 100, [1.0, 1.0], [1.0, 2.0], wC, prob["caches"], prob["intrinsics"])
+        assert g["stats"]["dense_weighted_pairs"] == o["weighted_pairs"] > 10
+        assert rel_l2(np.c_[g["rot"], g["trans"]], np.c_[o["rot"], o["trans"]]) < 1e-4
