@@ -24,7 +24,10 @@ class BFFloat4x4(C.Structure):
 
 
 class BFHashEntry(C.Structure):
-    _fields_ = [("pos", C.c_int32 * 3), ("ptr", C.c_int32), ("offset", C.c_uint32)]
+    _fields_ = [("pos", C.c_int32 * 3), ("ptr", C.c_int32), ("offset", C.c_uint32), ("_pad", C.c_uint32 * 3)]
+
+
+HASH_ENTRY_INTS = 8        # sizeof(BFHashEntry) / 4: the MSVC layout of `__align__(16) struct HashEntry` (32 bytes)
 
 
 class BFVoxel(C.Structure):
@@ -89,7 +92,7 @@ class BFHashDataStruct(C.Structure):
 
 assert C.sizeof(BFHashParams) == 224, C.sizeof(BFHashParams)
 assert BFHashParams.m_dummy.offset == 216
-assert C.sizeof(BFHashEntry) == 20 and C.sizeof(BFVoxel) == 12
+assert C.sizeof(BFHashEntry) == 32 and C.sizeof(BFVoxel) == 12
 assert C.sizeof(BFDepthCameraParams) == 32 and C.sizeof(BFHashDataStruct) == 80
 
 # every symbol include/bf_tsdf.h declares (the "library exports what the header says" test walks this)

@@ -104,10 +104,10 @@ class CUDASceneRepHashSDF:
         with torch.cuda.device(self.device):
             self.d_heap = torch.empty(n_blocks, dtype=torch.int32, **kw)
             self.d_heapCounter = torch.zeros(1, dtype=torch.int32, **kw)
-            self.d_hash = torch.empty(n_entries * 5, dtype=torch.int32, **kw)
+            self.d_hash = torch.empty(n_entries * 8, dtype=torch.int32, **kw)
             self.d_hashDecision = torch.zeros(n_entries, dtype=torch.int32, **kw)
             self.d_hashDecisionPrefix = torch.zeros(n_entries, dtype=torch.int32, **kw)
-            self.d_hashCompactified = torch.empty(n_entries * 5, dtype=torch.int32, **kw)
+            self.d_hashCompactified = torch.empty(n_entries * 8, dtype=torch.int32, **kw)
             self.d_hashCompactifiedCounter = torch.zeros(1, dtype=torch.int32, **kw)
             self.d_SDFBlocks = torch.empty(n_blocks * BF_SDF_BLOCK_VOXELS * 3, dtype=torch.int32, **kw)
             self.d_hashBucketMutex = torch.empty(hp.m_hashNumBuckets, dtype=torch.int32, **kw)
@@ -234,8 +234,8 @@ class CUDASceneRepHashSDF:
         t.cuda.synchronize(self.device)
         n_entries = self.m_hashParams.m_hashNumBuckets * BF_HASH_BUCKET_SIZE
         return {
-            "hash": self.d_hash.cpu().numpy().reshape(n_entries, 5),
-            "compactified": self.d_hashCompactified.cpu().numpy().reshape(n_entries, 5),
+            "hash": self.d_hash.cpu().numpy().reshape(n_entries, 8),
+            "compactified": self.d_hashCompactified.cpu().numpy().reshape(n_entries, 8),
             "compactified_count": int(self.d_hashCompactifiedCounter.cpu().numpy()[0]),
             "heap": self.d_heap.cpu().numpy().view(np.uint32),
             "heap_counter": int(self.d_heapCounter.cpu().numpy().view(np.uint32)[0]),

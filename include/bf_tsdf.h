@@ -16,10 +16,10 @@
  * why these prototypes can be plain C.
  *
  * The POD structs are layout-identical to the reference's (sizes/offsets probed
- * with nvcc 12.9 + g++ 13 against the reference headers; the `__align__(16)` in
- * front of `struct HashEntry` / `struct HashParams` is ignored by nvcc/gcc, so
- * HashEntry is 20 bytes).  Types carry a BF prefix so that
- * both headers can be visible in one translation unit.
+ * with nvcc 12.9 + g++ 13 against the reference headers, with the `__align__(16)` of
+ * HashEntry / HashParams / DepthCameraParams honoured as MSVC does: HashEntry is 32 bytes,
+ * see below and SURVEY.md quirk Q1).  Types carry a BF prefix so that both headers can be
+ * visible in one translation unit.
  *
  * The second half (bfTsdf*) is the B200-native, sync-free extension the host
  * mirror class (bundlefusion_b200/host/SceneRepHashSDF.h) drives: one call per
@@ -49,12 +49,31 @@ extern "C" {
 /* row-major 4x4, m[r*4+c]  (FL/SiftGPU/cuda_SimpleMatrixUtil.h:855; mLib mat4f) */
 typedef struct BFFloat4x4 { float m[16]; } BFFloat4x4;
 
-/* FL/DepthSensing/VoxelUtilHashSDF.h:56-74 : 20 bytes, 4-byte aligned */
+/* FL/DepthSensing/VoxelUtilHashSDF.h:56-74 : 5 x int32 declared `__align__(16) struct HashEntry`.
+ * In the build the reference actually ships (MSVC host + nvcc, FriedLiver.vcxproj) that is __declspec(align(16)):
+ * sizeof == 32, 16-byte aligned -- the layout used here.  (gcc / nvcc-on-Linux ignore an attribute placed BEFORE `struct`,
+ * giving 20 bytes; the reference then faults on its own 8-byte entry copies, VoxelUtilHashSDF.h:70-72 -- observed when
+ * building oracle/_ref, which therefore moves the attribute.)  Define BF_HASH_ENTRY_PACKED20 to get the 20-byte variant. */
+#ifdef BF_HASH_ENTRY_PACKED20
 typedef struct BFHashEntry {
     int32_t  pos[3];   /* SDF-block coordinate (block = 8^3 voxels)            */
     int32_t  ptr;      /* heapSlot*512 (index of first voxel) or FREE/LOCK     */
     uint32_t offset;   /* linked-list offset relative to bucket's last slot    */
 } BFHashEntry;
+#else
+typedef struct
+#if defined(__GNUC__) || defined(__CUDACC__)
+    __attribute__((aligned(16)))
+#else
+    __declspec(align(16))
+#endif
+BFHashEntry {
+    int32_t  pos[3];   /* SDF-block coordinate (block = 8^3 voxels)            */
+    int32_t  ptr;      /* heapSlot*512 (index of first voxel) or FREE/LOCK     */
+    uint32_t offset;   /* linked-list offset relative to bucket's last slot    */
+    uint32_t _pad[3];  /* tail padding of the 16-byte aligned struct           */
+} BFHashEntry;
+#endif
 
 /* FL/DepthSensing/VoxelUtilHashSDF.h:77-98 : 12 bytes */
 typedef struct BFVoxel {

@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Builds oracle/_ref/: the REFERENCE's own TSDF kernels, compiled for sm_100a from the sources where they lie under
+/root/reference, with a mechanical, behaviour-preserving compatibility patch applied to a scratch copy (the reference does
+not compile under CUDA 12.9 as it is).  Nothing from the reference is copied into the repository; the
+outputs are shared libraries under oracle/_ref/ (git-ignored, shipped to the GPU box by gpurun).
+
+TEST INFRASTRUCTURE ONLY: loaded by tests/ (parity of our CUDA path against the reference's CUDA path on the same inputs) and
+by scripts that time the reference kernels beside ours.
+
+Patch list (each is a textual substitution on the scratch copy):
+  1. FL/SiftGPU/cuda_SimpleMatrixUtil.h  : `matNxM<4,1>::operator float4()` explicit specialisation needs `template<>`.
+  2. FL/SiftGPU/cudaUtil.h               : `__shfl_down/__shfl_xor(...)` -> `_sync(0xffffffff, ...)` (removed in CUDA 9+).
+  3. FL/DepthSensing/CUDASceneRepHashSDF.cu : texture REFERENCES (removed in CUDA 12) -> plain global pointers;
+     `tex2D(depthTextureRef, x, y)` -> `g_refDepth[y * g_refW + x]` (point sampling at integer in-range coordinates, which is
+     all the kernels ever do); `bindInputDepthColorTextures` stores the pointers with cudaMemcpyToSymbol.
+  4. CUDAConstant.cu and CUDASceneRepHashSDF.cu are compiled as ONE translation unit (the `extern __constant__` parameter blocks
+     would otherwise need relocatable device code); the three parameter headers get the `#pragma once` they lack.
+Two builds: libref_tsdf_fast.so (--use_fast_math, as the reference ships: FriedLiver.vcxproj:124) and libref_tsdf.so (IEEE).
+"""
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+REF = "/root/reference/FriedLiver"
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+TMP = "/tmp/bf_ref_build"
+
+
+def patch(path, subs):
+    s = open(path, encoding="latin-1").read()
+    for pat, rep, count in subs:
+        s, n = re.subn(pat, rep, s, flags=re.S)
+        if count is not None and n != count:
+            raise RuntimeError(f"{path}: pattern {pat!r} matched {n} times, expected {count}")
+    open(path, "w", encoding="latin-1").write(s)
+
+
+def main():
+    if not os.path.isdir(REF):
+        print("oracle/build_ref.py: /root/reference not present, nothing to do")
+        return 0
+    shutil.rmtree(TMP, ignore_errors=True)
+    os.makedirs(TMP)
+    os.makedirs(OUT, exist_ok=True)
+    ds, sg = os.path.join(REF, "Source", "DepthSensing"), os.path.join(REF, "Source", "SiftGPU")
+    for f in ("CUDAConstant.cu", "CUDASceneRepHashSDF.cu", "VoxelUtilHashSDF.h", "DepthCameraUtil.h", "CUDAHashParams.h",
+              "CUDADepthCameraParams.h", "CUDARayCastParams.h"):
+        shutil.copy(os.path.join(ds, f), TMP)
+    for f in ("cuda_SimpleMatrixUtil.h", "cudaUtil.h"):
+        shutil.copy(os.path.join(sg, f), TMP)
+    patch(os.path.join(TMP, "cuda_SimpleMatrixUtil.h"),
+          [(r"\ninline __device__ __host__ matNxM<4, 1>::operator float4\(\)", "\ntemplate<> inline __device__ __host__ matNxM<4, 1>::operator float4()", 1)])
+    patch(os.path.join(TMP, "cudaUtil.h"),
+          [(r"__shfl_down\(", "__shfl_down_sync(0xffffffffu, ", None), (r"__shfl_xor\(", "__shfl_xor_sync(0xffffffffu, ", None)])
+    patch(os.path.join(TMP, "CUDASceneRepHashSDF.cu"), [
+        (r"texture<float, cudaTextureType2D, cudaReadModeElementType> depthTextureRef;", "__device__ const float* g_refDepth; __device__ unsigned int g_refW;", 1),
+        (r"texture<uchar4, cudaTextureType2D, cudaReadModeElementType> colorTextureRef;", "__device__ const uchar4* g_refColor;", 1),
+        (r"cutilSafeCall\(cudaBindTexture2D\(0, depthTextureRef[^;]*;", "cutilSafeCall(cudaMemcpyToSymbol(g_refDepth, &depthCameraData.d_depthData, sizeof(float*))); cutilSafeCall(cudaMemcpyToSymbol(g_refW, &width, sizeof(unsigned int)));", 1),
+        (r"cutilSafeCall\(cudaBindTexture2D\(0, colorTextureRef[^;]*;", "cutilSafeCall(cudaMemcpyToSymbol(g_refColor, &depthCameraData.d_colorData, sizeof(uchar4*)));", 1),
+        (r"depthTextureRef\.filterMode = cudaFilterModePoint;", "", 1),
+        (r"colorTextureRef\.filterMode = cudaFilterModePoint;", "", 1),
+        (r"tex2D\(depthTextureRef,\s*([^,()]+),\s*([^,()]+)\)", r"g_refDepth[(\2) * g_refW + (\1)]", None),
+        (r"tex2D\(colorTextureRef,\s*([^,()]+),\s*([^,()]+)\)", r"g_refColor[(\2) * g_refW + (\1)]", None),
+    ])
+    for f in ("CUDAHashParams.h", "CUDADepthCameraParams.h", "CUDARayCastParams.h"):      # no include guards in the reference
+        q = os.path.join(TMP, f)
+        open(q, "w", encoding="latin-1").write("#pragma once\n" + open(os.path.join(ds, f), encoding="latin-1").read())
+    unit = os.path.join(TMP, "ref_tsdf_unit.cu")
+    # definitions first; the headers' `extern __constant__` re-declarations are dropped (nvcc's host pass turns a __constant__
+    # definition into a static shadow variable, which may not follow an extern declaration of the same name)
+    patch(os.path.join(TMP, "VoxelUtilHashSDF.h"), [
+        (r"extern\s+__constant__ HashParams c_hashParams;", "", 1),
+        # `__align__(16)` placed BEFORE `struct` is honoured by MSVC (the reference's host compiler: sizeof(HashEntry) == 32) and
+        # silently ignored by gcc / nvcc-on-Linux (20 bytes) -- and then the reference's own 8-byte entry copies (operator=,
+        # VoxelUtilHashSDF.h:70-72) fault with "misaligned address".  Put the attribute where every compiler honours it.
+        (r"__align__\(16\)\s*struct HashEntry", "struct __align__(16) HashEntry", 1)])
+    patch(os.path.join(TMP, "DepthCameraUtil.h"), [(r"extern __constant__ DepthCameraParams c_depthCameraParams;", "", 1)])
+    open(unit, "w").write('#include "CUDAConstant.cu"\n#include "CUDASceneRepHashSDF.cu"\n')
+    inc = ["-I", TMP, "-I", os.path.join(REF, "Include", "cutil", "inc")]
+    base = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-w", "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic",
+            "-Xcompiler", "-fpermissive"] + inc
+    for name, extra in (("libref_tsdf_fast.so", ["--use_fast_math"]), ("libref_tsdf.so", [])):
+        cmd = base + extra + [unit, "-o", os.path.join(OUT, name), "-lcudart"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout[-4000:])
+            raise RuntimeError(f"building {name} failed")
+    print("oracle/_ref built:", sorted(os.listdir(OUT)))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -64,10 +64,10 @@ class OracleSceneRepHashSDF:
         n_blocks = self.hp.m_numSDFBlocks
         self.heap = np.zeros(n_blocks, np.uint32)
         self.heap_counter = np.zeros(1, np.uint32)
-        self.hash = np.zeros((n_entries, 5), np.int32)
+        self.hash = np.zeros((n_entries, 8), np.int32)
         self.decision = np.zeros(n_entries, np.int32)
         self.prefix = np.zeros(n_entries, np.int32)
-        self.compactified = np.zeros((n_entries, 5), np.int32)
+        self.compactified = np.zeros((n_entries, 8), np.int32)
         self.compactified_counter = np.zeros(1, np.int32)
         self.voxels = np.zeros((n_blocks, BF_SDF_BLOCK_VOXELS, 3), np.int32)
         self.mutex = np.zeros(self.hp.m_hashNumBuckets, np.int32)

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_pod_layouts():
-    assert C.sizeof(capi.BFHashEntry) == 20          # __align__(16) is ignored by nvcc/gcc (Q1)
+    assert C.sizeof(capi.BFHashEntry) == 32          # `__align__(16) struct HashEntry` as MSVC lays it out (Q1); 5 ints + tail padding
     assert C.sizeof(capi.BFVoxel) == 12
     assert C.sizeof(capi.BFHashParams) == 224
     assert capi.BFHashParams.m_hashNumBuckets.offset == 128

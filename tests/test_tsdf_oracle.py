@@ -94,9 +94,9 @@ def test_hash_function_known_values(oracle_lib):
         expect_bucket = v % 800000
         # insert by faking a depth pixel is heavy; instead place the entry by hand and let find() hash to it
         idx = expect_bucket * 4
-        o.hash[idx] = (x, y, z, 512 * 7, 0)
+        o.hash[idx, :5] = (x, y, z, 512 * 7, 0)
         assert oracle_lib.orc_tsdf_find(C.byref(o.hd), C.byref(o.hp), x, y, z) == idx
-        o.hash[idx] = (0, 0, 0, -2, 0)
+        o.hash[idx, :5] = (0, 0, 0, -2, 0)
         assert oracle_lib.orc_tsdf_find(C.byref(o.hd), C.byref(o.hp), x, y, z) == -1
 
 
