@@ -88,8 +88,54 @@ def main():
         if r.returncode != 0:
             sys.stderr.write(r.stdout[-4000:])
             raise RuntimeError(f"building {name} failed")
+    build_solver()
     print("oracle/_ref built:", sorted(os.listdir(OUT)))
     return 0
+
+
+def build_solver():
+    """The reference's bundle-adjustment solver (FL/Solver/SolverBundling.cu + FL/SBA.cu) for sm_100a -> libref_solver[_fast].so.
+    Scratch tree mirrors the reference's relative include layout; patches: the two listed at the top (template<>, shfl_sync) plus
+      5. FL/Solver/SolverBundlingUtil.h : `__shfl_down` -> `_sync`;
+      6. FL/SBA.cu : the Windows back-slash in the LieDerivUtil.h include -> slash;
+      7. stub headers standing in for <windows.h>, <conio.h> and mLib's core-base/common.h (MLIB_EXCEPTION / MLIB_ASSERT /
+         SAFE_DELETE_ARRAY only -- CUDATimer.h and cudaUtil.h include them, the solver kernels use nothing from them)."""
+    root = os.path.join(TMP, "solver")
+    src = os.path.join(root, "Source")
+    S = os.path.join(REF, "Source")
+    for d in (os.path.join(src, "Solver"), os.path.join(src, "SiftGPU"), os.path.join(root, "SiftGPU"), os.path.join(root, "stubs", "core-base")):
+        os.makedirs(d)
+    for f in os.listdir(os.path.join(S, "Solver")):
+        if f.endswith(".h") or f == "SolverBundling.cu":
+            shutil.copy(os.path.join(S, "Solver", f), os.path.join(src, "Solver"))
+    for f in ("SolverUtil.h", "GlobalDefines.h", "CUDACacheUtil.h", "CUDACameraUtil.h", "mLibCuda.h", "SBA.cu"):
+        shutil.copy(os.path.join(S, f), src)
+    for f in ("SIFTImageManager.h", "cuda_SimpleMatrixUtil.h", "cudaUtil.h", "CUDATimer.h"):
+        for d in (os.path.join(src, "SiftGPU"), os.path.join(root, "SiftGPU")):       # "../SiftGPU/" and "../../SiftGPU/" includes
+            shutil.copy(os.path.join(S, "SiftGPU", f), d)
+    for d in (os.path.join(src, "SiftGPU"), os.path.join(root, "SiftGPU")):
+        patch(os.path.join(d, "cuda_SimpleMatrixUtil.h"),
+              [(r"\ninline __device__ __host__ matNxM<4, 1>::operator float4\(\)", "\ntemplate<> inline __device__ __host__ matNxM<4, 1>::operator float4()", 1)])
+        patch(os.path.join(d, "cudaUtil.h"),
+              [(r"__shfl_down\(", "__shfl_down_sync(0xffffffffu, ", None), (r"__shfl_xor\(", "__shfl_xor_sync(0xffffffffu, ", None)])
+    patch(os.path.join(src, "Solver", "SolverBundlingUtil.h"),
+          [(r"__shfl_down\(", "__shfl_down_sync(0xffffffffu, ", None), (r"__shfl_xor\(", "__shfl_xor_sync(0xffffffffu, ", None)])
+    patch(os.path.join(src, "SBA.cu"), [(r'#include "Solver\\LieDerivUtil.h"', '#include "Solver/LieDerivUtil.h"', 1)])
+    st = os.path.join(root, "stubs")
+    open(os.path.join(st, "windows.h"), "w").write("#pragma once\n#include <mutex>\n#include <list>\n#include <string>\n#include <fstream>\n#include <algorithm>\n")
+    open(os.path.join(st, "conio.h"), "w").write("#pragma once\n")
+    open(os.path.join(st, "core-base", "common.h"), "w").write(
+        "#pragma once\n#include <stdexcept>\n#include <string>\n#define MLIB_EXCEPTION(s) std::runtime_error(std::string(s))\n"
+        "#define MLIB_ASSERT(x)\n#define SAFE_DELETE_ARRAY(p) { if (p) { delete[] (p); (p) = NULL; } }\n")
+    base = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-w", "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic",
+            "-Xcompiler", "-fpermissive", "-I", st, "-I", src, "-I", os.path.join(src, "SiftGPU"), "-I", os.path.join(src, "Solver"),
+            "-I", os.path.join(REF, "Include", "cutil", "inc")]
+    for name, extra in (("libref_solver_fast.so", ["--use_fast_math"]), ("libref_solver.so", [])):
+        cmd = base + extra + [os.path.join(src, "Solver", "SolverBundling.cu"), os.path.join(src, "SBA.cu"), "-o", os.path.join(OUT, name), "-lcudart"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout[-4000:])
+            raise RuntimeError(f"building {name} failed")
 
 
 if __name__ == "__main__":
