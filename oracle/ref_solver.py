@@ -80,8 +80,8 @@ class ReferenceSolverBundling:
         self.h_maxResidual, self.h_maxResidualIndex = np.zeros(nblk, np.float32), np.zeros(nblk, np.int32)
         an = BFSolverStateAnalysis()
         an.d_maxResidual, an.d_maxResidualIndex = self.d_maxResidual.data_ptr(), self.d_maxResidualIndex.data_ptr()
-        an.h_maxResidual = self.h_maxResidual.ctypes.data_as(C.POINTER(C.c_float))
-        an.h_maxResidualIndex = self.h_maxResidualIndex.ctypes.data_as(C.POINTER(C.c_int32))
+        an.h_maxResidual = self.h_maxResidual.ctypes.data
+        an.h_maxResidualIndex = self.h_maxResidualIndex.ctypes.data
         self.an = an
 
     def solve(self, d_corr, nCorr, d_valid, nImages, nNonLin, nLin, wS, wD=None, wC=None, d_rot=None, d_trans=None, cudaCache=None,
