@@ -103,7 +103,7 @@ TSDF_SYMBOLS = [
     "garbageCollectIdentifyCUDA", "garbageCollectFreeCUDA",
     "bfSetStream", "bfGetStream", "bfGetLastErrorString", "bfTsdfAuxBytes", "bfTsdfReset", "bfTsdfIntegrateFrame",
     "bfTsdfGarbageCollect", "bfTsdfGetHeapFreeCount", "bfTsdfGetNumOccupiedBlocks", "bfTsdfGetLastFrameStats",
-    "bfTsdfReleaseAux", "bfTsdfReintegrateFrame", "bfGetLaunchCount", "bfTsdfSetProfiling", "bfTsdfGetProfile",
+    "bfTsdfReleaseAux", "bfTsdfReintegrateFrame", "bfGetLaunchCount", "bfTsdfSetProfiling", "bfTsdfGetProfile", "bfTsdfSetBlockCull",
 ]
 
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
@@ -213,6 +213,8 @@ def lib() -> C.CDLL:
     L.bfTsdfAuxBytes.argtypes = [P(BFHashParams)]
     L.bfTsdfAuxBytes.restype = C.c_size_t
     L.bfTsdfReset.argtypes = [P(BFHashDataStruct), P(BFHashParams)]
+    L.bfTsdfSetBlockCull.argtypes = [C.c_int]
+    L.bfTsdfSetBlockCull.restype = C.c_int
     L.bfTsdfIntegrateFrame.argtypes = [P(BFHashDataStruct), P(BFHashParams), P(BFDepthCameraData), P(BFDepthCameraParams), C.c_int]
     L.bfTsdfGarbageCollect.argtypes = [P(BFHashDataStruct), P(BFHashParams)]
     L.bfTsdfGetHeapFreeCount.argtypes = [P(BFHashDataStruct), P(C.c_uint)]

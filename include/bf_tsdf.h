@@ -197,6 +197,10 @@ size_t bfTsdfAuxBytes(const BFHashParams* hashParams);
 /* FL/DepthSensing/CUDASceneRepHashSDF.h:147-155 (reset) */
 int bfTsdfReset(BFHashDataStruct* hashData, const BFHashParams* hashParams);
 
+/* Per-block depth-range cull of the stencil (default on; results are identical either way -- the cull only skips blocks none
+ * of whose voxels can pass the reference's truncation test, .cu:433-449).  Returns the previous setting. */
+int bfTsdfSetBlockCull(int enable);
+
 /* One whole CUDASceneRepHashSDF::integrate (h:65-83) or ::deIntegrate (h:85-108):
  * [alloc] -> compactify -> (de)integrate, three launches, zero host syncs.
  * hashParams carries the pose (m_rigidTransform AND its inverse, as the reference's
@@ -224,7 +228,7 @@ int bfTsdfGetNumOccupiedBlocks(const BFHashDataStruct* hashData, unsigned int* o
 
 /* counters of the last bfTsdfIntegrateFrame, for the roofline arithmetic
  * (U = voxels passing the truncation test, E = in-frustum blocks).
- * out[0]=E, out[1]=blocks surviving the depth-range cull, out[2]=U, out[3]=block inserts dropped since reset
+ * out[0]=E, out[1]=block passes the depth-range cull skipped in the last stencil, out[2]=U, out[3]=block inserts dropped since reset
  * (heap exhausted or no free entry inside the probe window; 0 in a sanely sized table).  Synchronises. */
 int bfTsdfGetLastFrameStats(const BFHashDataStruct* hashData, unsigned long long out[4]);
 

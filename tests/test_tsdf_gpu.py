@@ -279,3 +279,65 @@ def test_fused_reintegration_matches_two_pass_oracle(cuda_device):
     cpu.deIntegrate(frames[1][2], frames[1][0], frames[1][1], cam)
     cpu.garbageCollect()
     assert_same_state(gpu, cpu, hp, check_list=False)
+
+
+def test_block_cull_is_conservative(cuda_device):
+    """The per-block depth-range cull (depth tiles -> work list) must not change a single voxel word: the same stream run with the
+    cull on and off gives bit-identical state, equal to the oracle's, while a sizeable share of block passes is actually skipped.
+    The stream mixes what the cull keys on: a model seen from other viewpoints (blocks in front of / behind this frame's surface),
+    depths beyond the integration distance, invalid (-inf) pixels and depth discontinuities."""
+    import torch
+    W, H = 320, 240
+    cam = camera_params(W, H)
+    hp = small_params(num_buckets=100003, num_sdf_blocks=60000, max_integration_distance=2.5)
+    frames = [list(synth.make_frame(40 * i, W, H)) for i in range(7)]
+    rng = np.random.default_rng(7)
+    for d, c, T in frames:                     # a hole, a band beyond the integration distance, salt noise of invalid pixels
+        d[60:90, 100:180] = -np.inf
+        d[150:170, 20:300] = 3.4
+        d[rng.integers(0, H, 300), rng.integers(0, W, 300)] = -np.inf
+    lib = capi.lib()
+    states = {}
+    for cull in (1, 0):
+        prev = lib.bfTsdfSetBlockCull(cull)
+        try:
+            gpu = CUDASceneRepHashSDF(hp, cuda_device)
+            culled = 0
+            for k, (d, c, T) in enumerate(frames):
+                dd, dc = to_dev(torch, cuda_device, d, c)
+                gpu.integrate(T, dd, dc, cam)
+                culled += gpu.getLastFrameStats()["culled"]
+            # re-integrate two frames (fused path) and de-integrate one (tile kernel path)
+            dl = [torch.from_numpy(f[0]).to(cuda_device) for f in frames]
+            cl = [torch.from_numpy(f[1]).to(cuda_device) for f in frames]
+            ops = []
+            for k in (1, 5):
+                T = frames[k][2]
+                T2 = T.copy(); T2[:3, 3] += np.array([0.02, -0.01, 0.015], F)
+                ops += [(capi.BF_TSDF_OP_DEINTEGRATE, k, T), (capi.BF_TSDF_OP_INTEGRATE, k, T2)]
+            gpu.runOps(ops, dl, cl, cam)
+            culled += gpu.getLastFrameStats()["culled"]
+            gpu.deIntegrate(frames[3][2], dl[3], cl[3], cam)
+            culled += gpu.getLastFrameStats()["culled"]
+            states[cull] = (gpu.download(), culled, gpu.getHeapFreeCount())
+        finally:
+            lib.bfTsdfSetBlockCull(prev)
+    (s1, c1, h1), (s0, c0, h0) = states[1], states[0]
+    assert c0 == 0 and c1 > 0.1 * 7 * 1000, (c0, c1)
+    b1, v1 = orc.canonical_blocks(s1)
+    b0, v0 = orc.canonical_blocks(s0)
+    np.testing.assert_array_equal(b1, b0)
+    np.testing.assert_array_equal(v1, v0)
+    assert h1 == h0
+    # and against the oracle
+    cpu = orc.OracleSceneRepHashSDF(hp)
+    for d, c, T in frames:
+        cpu.integrate(T, d, c, cam)
+    for k in (1, 5):
+        T = frames[k][2]
+        T2 = T.copy(); T2[:3, 3] += np.array([0.02, -0.01, 0.015], F)
+        cpu.deIntegrate(T, frames[k][0], frames[k][1], cam); cpu.integrate(T2, frames[k][0], frames[k][1], cam)
+    cpu.deIntegrate(frames[3][2], frames[3][0], frames[3][1], cam)
+    cb, cv = orc.canonical_blocks(cpu.download())
+    np.testing.assert_array_equal(b1, cb)
+    np.testing.assert_array_equal(v1, cv)
