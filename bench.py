@@ -191,6 +191,8 @@ def run_ours(args):
             if e2e:
                 h_grot.copy_(grot, non_blocking=True); h_gtrans.copy_(gtrans, non_blocking=True)
 
+    skip_ba = [args.no_ba]
+
     def step(f, e2e):
         cur = f % B
         if e2e:   # host -> device of the incoming frame (pinned), the call a user makes hands HOST buffers
@@ -198,7 +200,7 @@ def run_ours(args):
         if world > 1:     # the sensor frame lives on rank 0: broadcast over NVLink, every rank integrates its own shard
             dist.broadcast(dlist[cur], 0); dist.broadcast(clist[cur], 0)
         scene.runPackedOps(packed_ops[f], packed_frames, cam)
-        if f % WORKLOAD["chunk"] == WORKLOAD["chunk"] - 1:
+        if f % WORKLOAD["chunk"] == WORKLOAD["chunk"] - 1 and not skip_ba[0]:
             ba(e2e)
         if e2e:
             h_heap.copy_(scene.d_heapCounter, non_blocking=True)
@@ -232,14 +234,16 @@ def run_ours(args):
     total_needed = Wm + 3 * K
     while len(packed_ops) < total_needed:
         packed_ops.append(scene.packOps(wl.step_ops(len(packed_ops), n_re)))
+    skip_ba[0] = True        # the stencil is timed alone (no bundling kernel sharing the SMs): the burst HBM peak is its roof
     timed(K, Wm + 2 * K, False, True)
+    skip_ba[0] = args.no_ba
     prof = (ctypes.c_ulonglong * 8)()
     capi.check(L.bfTsdfGetProfile(ctypes.byref(scene.m_hashData), prof), "bfTsdfGetProfile")
     L.bfTsdfSetProfiling(0)
     ms_e2e, _ = timed(K, Wm + K, True, False)
     stats = scene.getLastFrameStats()
     heap_free = scene.getHeapFreeCount()
-    sg = sol_g.getStats()
+    sg = sol_g.getStats() if not args.no_ba else {"pcg": 0, "gn": 0}
 
     if rank != 0:
         if world > 1:
@@ -264,6 +268,8 @@ def run_ours(args):
                 "note": "incoming frame copied from pinned host memory every step; re-integrated frames come from the device-resident frame store"},
         "gpu_launches": int(launches), "roofline": roof, "clocks": summarize_clocks(clk_lines),
     }
+    if args.no_ba:
+        out["diagnostic"] = "--no-ba: bundle adjustment left out, not a bench value"
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_arm(1, 0, quiet=True, n_reint=2)
     print(json.dumps(out))
@@ -339,6 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ba", action="store_true", help="diagnostic: leave the bundle-adjustment solves out (the JSON line is then NOT a bench value)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -81,12 +81,13 @@ struct I3 { int x, y, z; };
 
 __device__ __forceinline__ int isign(float v) { return (0.0f < v) - (v < 0.0f); }
 
-// cuda_SimpleMatrixUtil.h:937-944 (affine, implicit w = 1)
+// cuda_SimpleMatrixUtil.h:937-944 (affine, implicit w = 1), fused exactly as nvcc fuses the reference's expression
+// (oracle/tsdf_oracle.c header: the arithmetic contract); the TU is built -fmad=false so only these explicit FMAs fuse
 __device__ __forceinline__ F3 xform(const BFFloat4x4& M, F3 v) {
     F3 r;
-    r.x = M.m[0] * v.x + M.m[1] * v.y + M.m[2] * v.z + M.m[3] * 1.0f;
-    r.y = M.m[4] * v.x + M.m[5] * v.y + M.m[6] * v.z + M.m[7] * 1.0f;
-    r.z = M.m[8] * v.x + M.m[9] * v.y + M.m[10] * v.z + M.m[11] * 1.0f;
+    r.x = __fmaf_rn(v.z, M.m[2], __fmaf_rn(v.x, M.m[0], v.y * M.m[1])) + M.m[3];
+    r.y = __fmaf_rn(v.z, M.m[6], __fmaf_rn(v.x, M.m[4], v.y * M.m[5])) + M.m[7];
+    r.z = __fmaf_rn(v.z, M.m[10], __fmaf_rn(v.x, M.m[8], v.y * M.m[9])) + M.m[11];
     return r;
 }
 // VoxelUtilHashSDF.h:226-234 (unsigned modulo, see oracle note)
@@ -94,7 +95,7 @@ __device__ __forceinline__ unsigned hash_pos(unsigned numBuckets, I3 p) {
     unsigned v = ((unsigned)p.x * 73856093u) ^ ((unsigned)p.y * 19349669u) ^ ((unsigned)p.z * 83492791u);
     return v % numBuckets;
 }
-__device__ __forceinline__ float truncation(const BFHashParams& hp, float z) { return hp.m_truncation + hp.m_truncScale * z; }
+__device__ __forceinline__ float truncation(const BFHashParams& hp, float z) { return __fmaf_rn(hp.m_truncScale, z, hp.m_truncation); }
 __device__ __forceinline__ I3 world_to_voxel(const BFHashParams& hp, F3 pos) {
     F3 p = { pos.x / hp.m_virtualVoxelSize, pos.y / hp.m_virtualVoxelSize, pos.z / hp.m_virtualVoxelSize };
     I3 r = { (int)(p.x + (float)isign(p.x) * 0.5f), (int)(p.y + (float)isign(p.y) * 0.5f), (int)(p.z + (float)isign(p.z) * 0.5f) };
@@ -128,9 +129,10 @@ __device__ __forceinline__ F3 depth_to_skeleton(const BFDepthCameraParams& cp, u
 }
 // DepthCameraUtil.h:95-107,137-144 + VoxelUtilHashSDF.h:322-326
 __device__ __forceinline__ bool block_in_frustum(const BFHashParams& hp, const BFDepthCameraParams& cp, I3 b) {
-    F3 w = block_to_world(hp, b);
-    const float off = hp.m_virtualVoxelSize * 0.5f * ((float)BF_SDF_BLOCK_SIZE - 1.0f);
-    w.x += off; w.y += off; w.z += off;
+    const float vs = hp.m_virtualVoxelSize;
+    const float off = vs * 0.5f * ((float)BF_SDF_BLOCK_SIZE - 1.0f);
+    const F3 w = { __fmaf_rn((float)(b.x * BF_SDF_BLOCK_SIZE), vs, off), __fmaf_rn((float)(b.y * BF_SDF_BLOCK_SIZE), vs, off),
+                   __fmaf_rn((float)(b.z * BF_SDF_BLOCK_SIZE), vs, off) };
     F3 pc = xform(hp.m_rigidTransformInverse, w);
     const float px = pc.x * cp.fx / pc.z + cp.mx;
     const float py = pc.y * cp.fy / pc.z + cp.my;
@@ -624,34 +626,58 @@ __global__ void rebuild_aux_kernel(BFHashDataStruct hd, unsigned numEntries, uns
 // ---- the integrate / de-integrate stencil (CUDASceneRepHashSDF.cu:420-521) --------------
 // 128 threads per SDF block, 4 consecutive voxels (48 B) per thread.  Persistent grid: each CTA
 // walks the compactified list with stride gridDim.x; the list length is read from device memory.
-struct VoxelQuad { uint4 a, b, c; };   // 4 voxels = 12 words: v0{a.x,a.y,a.z} v1{a.w,b.x,b.y} v2{b.z,b.w,c.x} v3{c.y,c.z,c.w}
+struct VoxelQuad { uint4 a, b, c; };
+#define BF_SPEC_BLOCKS 24576u   // 4 voxels = 12 words: v0{a.x,a.y,a.z} v1{a.w,b.x,b.y} v2{b.z,b.w,c.x} v3{c.y,c.z,c.w}
 
 __device__ __forceinline__ float clamp_color(float v) { return fmaxf(0.0f, fminf(v, 254.5f)); }
+
+// The stencil is bound by the XU pipe (conversions, roundf and MUFU run at 1/8 rate), not by FMA/ALU issue, so the
+// byte <-> float traffic of the colour update and the float -> pixel conversions are done with exact integer/FMA-pipe
+// identities instead of cvt / frnd.  Each is value-identical to the plain expression in its comment for EVERY input.
+// (float)b for b in [0, 255]
+__device__ __forceinline__ float u8_to_float(unsigned b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
+// (unsigned)clamp_color(roundf(r))   [roundf: half away from zero; cvt.rzi of a value in [0, 254.5]]
+__device__ __forceinline__ unsigned round_clamp_u8(float r) {
+    const float rc = fmaxf(-1.0f, fminf(r, 256.0f));           // roundf is monotone, so pre-clamping cannot change the clamped result; NaN -> 256 -> 254
+    float t = (rc + 12582912.0f) - 12582912.0f;                // nearest integer, ties to even (|rc| <= 2^22)
+    if (rc - t == 0.5f) t += 1.0f;                             // the ties roundf sends away from zero (the negative one, -0.5, clamps to 0 either way)
+    const float v = clamp_color(t);                            // an integer in [0, 254] or 254.5
+    return __float_as_uint(v + 8388608.0f) & 0xffu;            // 254.5 + 2^23 rounds to the even 254 = trunc
+}
+// idx = (unsigned)(int)t and the test idx < limit, t = screen coordinate + 0.5   [cvt.rzi.s32.f32: NaN -> 0, (-1, 0) -> 0]
+__device__ __forceinline__ bool pixel_index(float t, unsigned limit, float limitF, unsigned& idx) {
+    if (limit > (1u << 22)) { idx = (unsigned)(int)t; return idx < limit; }
+    if (t <= -1.0f || t >= limitF) return false;               // NaN passes both tests, as the conversion gives 0
+    const float c = fmaxf(t, 0.0f);                            // fmaxf(NaN, 0) = 0
+    const float n = c + 8388608.0f;                            // 2^23 + rne(c)
+    idx = (__float_as_uint(n) & 0x7FFFFFu) - ((n - 8388608.0f) > c ? 1u : 0u);   // floor(c)
+    return true;
+}
 
 template <bool kDeIntegrate>
 __device__ __forceinline__ void update_voxel(const BFHashParams& hp, float sdf, uchar4 cur, unsigned& wSdf, unsigned& wWeight, unsigned& wColor, int& liveDelta) {
     const float oldSdf = __uint_as_float(wSdf), oldW = __uint_as_float(wWeight);
-    const float oc[3] = { (float)(wColor & 0xff), (float)((wColor >> 8) & 0xff), (float)((wColor >> 16) & 0xff) };
-    const float cc[3] = { (float)cur.x, (float)cur.y, (float)cur.z };
+    const float oc[3] = { u8_to_float(wColor & 0xff), u8_to_float((wColor >> 8) & 0xff), u8_to_float((wColor >> 16) & 0xff) };
+    const float cc[3] = { u8_to_float(cur.x), u8_to_float(cur.y), u8_to_float(cur.z) };
     float nSdf, nW;
     unsigned nColor = 0;
     if (!kDeIntegrate) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float r = (oldW == 0) ? cc[k] : 0.2f * cc[k] + 0.8f * oc[k];
-            nColor |= ((unsigned)clamp_color(roundf(r)) & 0xffu) << (8 * k);
+            const float r = (oldW == 0) ? cc[k] : __fmaf_rn(cc[k], 0.2f, 0.8f * oc[k]);
+            nColor |= round_clamp_u8(r) << (8 * k);
         }
         nColor |= 255u << 24;
-        nSdf = (sdf * 1.0f + oldSdf * oldW) / (1.0f + oldW);
+        nSdf = __fmaf_rn(oldSdf, oldW, sdf) / (1.0f + oldW);
         nW = fminf((float)hp.m_integrationWeightMax, 1.0f + oldW);
     } else {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float r = (oc[k] * oldW - cc[k] * 1.0f) / (oldW - 1.0f);
-            nColor |= ((unsigned)clamp_color(roundf(r)) & 0xffu) << (8 * k);
+            const float r = __fmaf_rn(oc[k], oldW, -cc[k]) / (oldW - 1.0f);
+            nColor |= round_clamp_u8(r) << (8 * k);
         }
         nColor |= 255u << 24;
-        nSdf = (oldSdf * oldW - sdf * 1.0f) / (oldW - 1.0f);
+        nSdf = __fmaf_rn(oldSdf, oldW, -sdf) / (oldW - 1.0f);
         nW = fmaxf(0.0f, oldW - 1.0f);
         if (nW <= 0.001f) { nSdf = 0.0f; nW = 0.0f; nColor = 0; }
     }
@@ -675,15 +701,25 @@ integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, c
     }
     const unsigned t = threadIdx.x;
     const unsigned W = cp.m_imageWidth, H = cp.m_imageHeight;
+    const float Wf = (float)W, Hf = (float)H;
     // local voxel coordinates of this thread's first voxel: i = 4t -> x = (4t)%8, y = (4t%64)/8, z = 4t/64
     const int lx = (int)((4 * t) & 7), ly = (int)(((4 * t) & 63) >> 3), lz = (int)((4 * t) >> 6);
     unsigned passed = 0;
+    // Latency, not bandwidth, bounds this kernel while the list is short (a few thousand blocks: each warp walks a dependent
+    // chain work item -> projection -> depth gather -> voxel load -> store).  Below BF_SPEC_BLOCKS list entries the voxel quad is
+    // loaded up front, in the shadow of the projection arithmetic, whether or not one of its voxels will pass (<= 2x the voxel
+    // read bytes, still far from the HBM roof at that size); above it only passing threads touch voxel memory, which is what
+    // keeps the long-list regime at ~80 % of the roof.  The next work item is prefetched either way.
+    const bool spec = count < BF_SPEC_BLOCKS;
+    int4 wNext = make_int4(0, 0, 0, 0);
+    if (work && blockIdx.x < count) wNext = __ldg(&work[blockIdx.x]);
 
     for (unsigned b = blockIdx.x; b < count; b += gridDim.x) {
         int bx, by, bz;
         unsigned ptr;
         if (work) {
-            const int4 w = __ldg(&work[b]);
+            const int4 w = wNext;
+            if (b + gridDim.x < count) wNext = __ldg(&work[b + gridDim.x]);
             bx = w.x; by = w.y; bz = w.z; ptr = ((unsigned)w.w & 0x0FFFFFFFu) * BF_SDF_BLOCK_VOXELS;
         } else {
             const BFHashEntry* ep = &hd.d_hashCompactified[b];
@@ -691,6 +727,9 @@ integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, c
             ptr = (unsigned)__ldg(&ep->ptr);
         }
 
+        uint4* const vp = reinterpret_cast<uint4*>(hd.d_SDFBlocks + (size_t)ptr) + 3 * t;   // 48 B per thread, 16-B aligned
+        VoxelQuad q;
+        if (spec) { q.a = vp[0]; q.b = vp[1]; q.c = vp[2]; }
         float sdfv[4];
         uchar4 colv[4];
         unsigned mask = 0;
@@ -701,8 +740,8 @@ integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, c
             const F3 pf = xform(hp.m_rigidTransformInverse, voxel_to_world(hp, pi));
             const float sx = pf.x * cp.fx / pf.z + cp.mx;
             const float sy = pf.y * cp.fy / pf.z + cp.my;
-            const unsigned px = (unsigned)(int)(sx + 0.5f), py = (unsigned)(int)(sy + 0.5f);
-            if (px < W && py < H && colorImg != nullptr) {
+            unsigned px, py;
+            if (pixel_index(sx + 0.5f, W, Wf, px) && pixel_index(sy + 0.5f, H, Hf, py) && colorImg != nullptr) {
                 const float depth = __ldg(&depthImg[py * W + px]);
                 if (depth != -INFINITY && depth < hp.m_maxIntegrationDistance) {
                     float sdf = depth - pf.z;
@@ -717,9 +756,7 @@ integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, c
             }
         }
         if (mask) {
-            uint4* vp = reinterpret_cast<uint4*>(hd.d_SDFBlocks + (size_t)ptr) + 3 * t;   // 48 B per thread, 16-B aligned
-            VoxelQuad q;
-            q.a = vp[0]; q.b = vp[1]; q.c = vp[2];
+            if (!spec) { q.a = vp[0]; q.b = vp[1]; q.c = vp[2]; }
             if (mask & 1u) update_voxel<kDeIntegrate>(hp, sdfv[0], colv[0], q.a.x, q.a.y, q.a.z, liveDelta);
             if (mask & 2u) update_voxel<kDeIntegrate>(hp, sdfv[1], colv[1], q.a.w, q.b.x, q.b.y, liveDelta);
             if (mask & 4u) update_voxel<kDeIntegrate>(hp, sdfv[2], colv[2], q.b.z, q.b.w, q.c.x, liveDelta);
@@ -965,12 +1002,12 @@ compactify_dual_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams
 
 // truncation test of one voxel against one pose; returns true and the clamped sdf / colour when it passes (.cu:433-463)
 __device__ __forceinline__ bool probe_voxel(const BFHashParams& hp, const BFDepthCameraParams& cp, const float* __restrict__ depthImg,
-                                            const uchar4* __restrict__ colorImg, I3 pi, float& sdfOut, uchar4& colOut) {
+                                            const uchar4* __restrict__ colorImg, I3 pi, float Wf, float Hf, float& sdfOut, uchar4& colOut) {
     const F3 pf = xform(hp.m_rigidTransformInverse, voxel_to_world(hp, pi));
     const float sx = pf.x * cp.fx / pf.z + cp.mx;
     const float sy = pf.y * cp.fy / pf.z + cp.my;
-    const unsigned px = (unsigned)(int)(sx + 0.5f), py = (unsigned)(int)(sy + 0.5f);
-    if (!(px < cp.m_imageWidth && py < cp.m_imageHeight)) return false;
+    unsigned px, py;
+    if (!(pixel_index(sx + 0.5f, cp.m_imageWidth, Wf, px) && pixel_index(sy + 0.5f, cp.m_imageHeight, Hf, py))) return false;
     const float depth = __ldg(&depthImg[py * cp.m_imageWidth + px]);
     if (!(depth != -INFINITY && depth < hp.m_maxIntegrationDistance)) return false;
     float sdf = depth - pf.z;
@@ -990,11 +1027,19 @@ reintegrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hpO
     const unsigned t = threadIdx.x;
     const int lx = (int)((4 * t) & 7), ly = (int)(((4 * t) & 63) >> 3), lz = (int)((4 * t) >> 6);
     unsigned passed = 0;
+    const bool spec = count < BF_SPEC_BLOCKS;           // see integrate_kernel
+    const float Wf = (float)cp.m_imageWidth, Hf = (float)cp.m_imageHeight;
+    int4 wNext = make_int4(0, 0, 0, 0);
+    if (blockIdx.x < count) wNext = __ldg(&work[blockIdx.x]);
     for (unsigned b = blockIdx.x; b < count; b += gridDim.x) {
-        const int4 w = __ldg(&work[b]);
+        const int4 w = wNext;
+        if (b + gridDim.x < count) wNext = __ldg(&work[b + gridDim.x]);
         const int bx = w.x, by = w.y, bz = w.z;
         const unsigned ptr = ((unsigned)w.w & 0x0FFFFFFFu) * BF_SDF_BLOCK_VOXELS;
         const unsigned fl = (unsigned)w.w >> 28;        // bit0: the old pose can touch this block, bit1: the new pose can
+        uint4* const vp = reinterpret_cast<uint4*>(hd.d_SDFBlocks + (size_t)ptr) + 3 * t;
+        VoxelQuad q;
+        if (spec) { q.a = vp[0]; q.b = vp[1]; q.c = vp[2]; }
         float sdfD[4], sdfI[4];
         uchar4 colD[4], colI[4];
         unsigned maskD = 0, maskI = 0;
@@ -1002,14 +1047,12 @@ reintegrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hpO
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const I3 pi = { bx * BF_SDF_BLOCK_SIZE + lx + k, by * BF_SDF_BLOCK_SIZE + ly, bz * BF_SDF_BLOCK_SIZE + lz };
-            if ((fl & 1u) && probe_voxel(hpOld, cp, depthImg, colorImg, pi, sdfD[k], colD[k])) maskD |= 1u << k;
-            if ((fl & 2u) && probe_voxel(hpNew, cp, depthImg, colorImg, pi, sdfI[k], colI[k])) maskI |= 1u << k;
+            if ((fl & 1u) && probe_voxel(hpOld, cp, depthImg, colorImg, pi, Wf, Hf, sdfD[k], colD[k])) maskD |= 1u << k;
+            if ((fl & 2u) && probe_voxel(hpNew, cp, depthImg, colorImg, pi, Wf, Hf, sdfI[k], colI[k])) maskI |= 1u << k;
         }
         const unsigned mask = maskD | maskI;
         if (mask) {
-            uint4* vp = reinterpret_cast<uint4*>(hd.d_SDFBlocks + (size_t)ptr) + 3 * t;
-            VoxelQuad q;
-            q.a = vp[0]; q.b = vp[1]; q.c = vp[2];
+            if (!spec) { q.a = vp[0]; q.b = vp[1]; q.c = vp[2]; }
             if (maskD & 1u) update_voxel<true>(hpOld, sdfD[0], colD[0], q.a.x, q.a.y, q.a.z, liveDelta);
             if (maskI & 1u) update_voxel<false>(hpNew, sdfI[0], colI[0], q.a.x, q.a.y, q.a.z, liveDelta);
             if (maskD & 2u) update_voxel<true>(hpOld, sdfD[1], colD[1], q.a.w, q.b.x, q.b.y, liveDelta);

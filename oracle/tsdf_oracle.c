@@ -16,12 +16,21 @@
  * Every function cites the reference lines it restates.  FL/ = FriedLiver/Source/.
  *
  * Arithmetic contract (shared with bundlefusion_b200/csrc/tsdf.cu so the two can
- * be compared BIT-exactly): IEEE-754 binary32, round-to-nearest-even, every
- * + - * / individually rounded (no FMA contraction: build with
- * -ffp-contract=off here, -fmad=false there), 1/sqrt(x) computed as a correctly
- * rounded sqrt followed by a correctly rounded divide (the reference uses the
- * approximate rsqrtf, FL/../Include/cutil/inc/cutil_math.h:1207-1211), float->int
- * conversion as CUDA's cvt.rzi.s32.f32 (truncate, saturate, NaN -> 0).
+ * be compared BIT-exactly): IEEE-754 binary32, round-to-nearest-even; + - * / are
+ * individually rounded EXCEPT where fmaf() is written out, and fmaf() is written
+ * exactly where nvcc 12.9 -O3 (without --use_fast_math) fuses the reference's
+ * expressions -- read off the SASS of oracle/_ref/libref_tsdf.so: the 4x4 * float3
+ * product (t = y*m1; t = fma(x, m0, t); t = fma(z, m2, t); t + m3), the truncation
+ * fma(scale, z, trunc), the block centre fma(float(8b), voxelSize, off), and the voxel
+ * update (fma(oldSdf, oldW, +-sdf), fma(cur, 0.2, old*0.8), fma(old, oldW, -cur)).
+ * With that, the integrate / de-integrate stencil is bit-identical not only to tsdf.cu
+ * but to the reference's own kernels in the IEEE build (tests/test_tsdf_vs_reference_gpu.py).
+ * Built with -ffp-contract=off here and -fmad=false there so that nothing ELSE fuses.
+ * 1/sqrt(x) is a correctly rounded sqrt followed by a correctly rounded divide (the
+ * reference uses the approximate rsqrtf, FL/../Include/cutil/inc/cutil_math.h:1207-1211,
+ * which no CPU can reproduce: the alloc walk is therefore equal as a SET of blocks, not
+ * operation by operation), float->int conversion is CUDA's cvt.rzi.s32.f32 (truncate,
+ * saturate, NaN -> 0).
  * Sequential semantics: where the reference resolves races with try-locks and a
  * host retry loop (FL/DepthSensing/CUDASceneRepHashSDF.h:335-348) the oracle simply
  * performs every insertion, which is the fixed point of that loop.
@@ -57,13 +66,13 @@ static inline uint8_t f2u8(float v) {
 /* cutil_math.h:31-33 */
 static inline int isign(float v) { return (0.0f < v) - (v < 0.0f); }
 
-/* cuda_SimpleMatrixUtil.h:937-944 : affine transform, implicit w = 1 */
+/* cuda_SimpleMatrixUtil.h:937-944 : affine transform, implicit w = 1; `m0*x + m1*y + m2*z + m3*1` as nvcc fuses it */
 static inline f3 xform(const BFFloat4x4* M, f3 v) {
     const float* m = M->m;
     f3 r;
-    r.x = m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3] * 1.0f;
-    r.y = m[4] * v.x + m[5] * v.y + m[6] * v.z + m[7] * 1.0f;
-    r.z = m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11] * 1.0f;
+    r.x = fmaf(v.z, m[2], fmaf(v.x, m[0], v.y * m[1])) + m[3];
+    r.y = fmaf(v.z, m[6], fmaf(v.x, m[4], v.y * m[5])) + m[7];
+    r.z = fmaf(v.z, m[10], fmaf(v.x, m[8], v.y * m[9])) + m[11];
     return r;
 }
 
@@ -77,7 +86,7 @@ static inline uint32_t hash_pos(const BFHashParams* hp, i3 p) {
 
 /* VoxelUtilHashSDF.h:272-274 */
 static inline float truncation(const BFHashParams* hp, float z) {
-    return hp->m_truncation + hp->m_truncScale * z;
+    return fmaf(hp->m_truncScale, z, hp->m_truncation);
 }
 /* VoxelUtilHashSDF.h:283-287 */
 static inline i3 world_to_voxel(const BFHashParams* hp, f3 pos) {
@@ -134,9 +143,9 @@ static inline int in_frustum_approx(const BFDepthCameraParams* cp, const BFFloat
 }
 /* VoxelUtilHashSDF.h:322-326 */
 static inline int block_in_frustum(const BFHashParams* hp, const BFDepthCameraParams* cp, i3 b) {
-    f3 w = block_to_world(hp, b);
-    float off = hp->m_virtualVoxelSize * 0.5f * ((float)BF_SDF_BLOCK_SIZE - 1.0f);
-    w.x += off; w.y += off; w.z += off;
+    const float vs = hp->m_virtualVoxelSize;
+    const float off = vs * 0.5f * ((float)BF_SDF_BLOCK_SIZE - 1.0f);
+    f3 w = { fmaf((float)(b.x * BF_SDF_BLOCK_SIZE), vs, off), fmaf((float)(b.y * BF_SDF_BLOCK_SIZE), vs, off), fmaf((float)(b.z * BF_SDF_BLOCK_SIZE), vs, off) };
     return in_frustum_approx(cp, &hp->m_rigidTransformInverse, w);
 }
 
@@ -363,19 +372,19 @@ ORC_API unsigned long long orc_tsdf_integrate(BFHashDataStruct* hd, const BFHash
             float cc[3] = { cur[0], cur[1], cur[2] };
             if (!deIntegrate) {
                 for (int k = 0; k < 3; ++k) {
-                    float r = (old.weight == 0) ? cc[k] : 0.2f * cc[k] + 0.8f * oc[k];
+                    float r = (old.weight == 0) ? cc[k] : fmaf(cc[k], 0.2f, 0.8f * oc[k]);
                     nv.color[k] = f2u8(clamp_color(roundf(r)));
                 }
                 nv.color[3] = 255;
-                nv.sdf = (sdf * cw + old.sdf * old.weight) / (cw + old.weight);
+                nv.sdf = fmaf(old.sdf, old.weight, sdf * cw) / (cw + old.weight);
                 nv.weight = fminf((float)hp->m_integrationWeightMax, cw + old.weight);
             } else {
                 for (int k = 0; k < 3; ++k) {
-                    float r = (oc[k] * old.weight - cc[k] * cw) / (old.weight - cw);
+                    float r = fmaf(oc[k], old.weight, -(cc[k] * cw)) / (old.weight - cw);
                     nv.color[k] = f2u8(clamp_color(roundf(r)));
                 }
                 nv.color[3] = 255;
-                nv.sdf = (old.sdf * old.weight - sdf * cw) / (old.weight - cw);
+                nv.sdf = fmaf(old.sdf, old.weight, -(sdf * cw)) / (old.weight - cw);
                 nv.weight = fmaxf(0.0f, old.weight - cw);
                 if (nv.weight <= 0.001f) { nv.sdf = 0.0f; nv.weight = 0.0f; nv.color[0] = nv.color[1] = nv.color[2] = nv.color[3] = 0; }
             }
@@ -481,16 +490,16 @@ ORC_API unsigned long long orc_tsdf_integrate_dense(BFVoxel* grid, int D, float 
         const uint8_t* c = colorImg ? &colorImg[4 * (py * W + px)] : NULL;
         for (int k = 0; k < 3; ++k) {
             float cc = c ? (float)c[k] : (k == 1 ? 255.0f : 0.0f), oc = old.color[k], r;
-            if (!deIntegrate) r = (old.weight == 0) ? cc : 0.2f * cc + 0.8f * oc;
-            else r = (oc * old.weight - cc) / (old.weight - 1.0f);
+            if (!deIntegrate) r = (old.weight == 0) ? cc : fmaf(cc, 0.2f, 0.8f * oc);
+            else r = fmaf(oc, old.weight, -cc) / (old.weight - 1.0f);
             nv.color[k] = f2u8(clamp_color(roundf(r)));
         }
         nv.color[3] = 255;
         if (!deIntegrate) {
-            nv.sdf = (sdf + old.sdf * old.weight) / (1.0f + old.weight);
+            nv.sdf = fmaf(old.sdf, old.weight, sdf) / (1.0f + old.weight);
             nv.weight = fminf((float)hp->m_integrationWeightMax, 1.0f + old.weight);
         } else {
-            nv.sdf = (old.sdf * old.weight - sdf) / (old.weight - 1.0f);
+            nv.sdf = fmaf(old.sdf, old.weight, -sdf) / (old.weight - 1.0f);
             nv.weight = fmaxf(0.0f, old.weight - 1.0f);
             if (nv.weight <= 0.001f) { memset(&nv, 0, sizeof nv); }
         }

@@ -24,6 +24,14 @@ def small_params(**kw):
     return default_hash_params(**kw)
 
 
+def fma32(a, b, c):
+    """fmaf(a, b, c) on float32 arrays: the product of two binary32 values is exact in binary64; the one binary64 addition is
+    then rounded to binary32 (double rounding can differ from a true FMA only when the binary64 sum lands within 2^-29 relative
+    of a binary32 rounding boundary -- not on these seeds)."""
+    D = np.float64
+    return (np.asarray(a, F).astype(D) * np.asarray(b, F).astype(D) + np.asarray(c, F).astype(D)).astype(F)
+
+
 def numpy_expected_voxels(blocks, T, depth, color, cam, hp, old=None, deintegrate=False):
     """Vectorised float32 restatement of integrateDepthMapKernel for a list of block coords.
     Returns (sdf, weight, rgba, passed-mask) arrays of shape (N,512[,4])."""
@@ -35,8 +43,8 @@ def numpy_expected_voxels(blocks, T, depth, color, cam, hp, old=None, deintegrat
     vz = (blocks[:, 2:3] * 8 + lz[None, :]).astype(F) * F(hp.m_virtualVoxelSize)
     M = mat4_inverse_f32(T)
 
-    def row(r):
-        return ((M[r, 0] * vx + M[r, 1] * vy) + M[r, 2] * vz) + M[r, 3] * F(1.0)
+    def row(r):       # the contract's fused form of m0*x + m1*y + m2*z + m3 (oracle/tsdf_oracle.c header)
+        return fma32(vz, M[r, 2], fma32(vx, M[r, 0], vy * M[r, 1])) + M[r, 3]
     px, py, pz = row(0), row(1), row(2)
     with np.errstate(all="ignore"):
         sx = px * F(cam.fx) / pz + F(cam.mx)
@@ -51,7 +59,7 @@ def numpy_expected_voxels(blocks, T, depth, color, cam, hp, old=None, deintegrat
     with np.errstate(all="ignore"):
         ok = on & (d != -np.inf) & (d < F(hp.m_maxIntegrationDistance))
         sdf = d - pz
-        trunc = F(hp.m_truncation) + F(hp.m_truncScale) * d
+        trunc = fma32(F(hp.m_truncScale), d, F(hp.m_truncation))
         ok &= np.abs(sdf) < trunc
         sdf = np.where(sdf >= 0, np.minimum(trunc, sdf), np.maximum(-trunc, sdf)).astype(F)
     if old is None:
@@ -60,14 +68,14 @@ def numpy_expected_voxels(blocks, T, depth, color, cam, hp, old=None, deintegrat
         old_sdf, old_w, old_c = old
     with np.errstate(all="ignore"):
         if not deintegrate:
-            n_sdf = (sdf * F(1) + old_sdf * old_w) / (F(1) + old_w)
+            n_sdf = fma32(old_sdf, old_w, sdf) / (F(1) + old_w)
             n_w = np.minimum(F(hp.m_integrationWeightMax), F(1) + old_w)
-            blend = F(0.2) * c[..., :3] + F(0.8) * old_c[..., :3]
+            blend = fma32(c[..., :3], F(0.2), F(0.8) * old_c[..., :3])
             res = np.where((old_w == 0)[..., None], c[..., :3], blend)
         else:
-            n_sdf = (old_sdf * old_w - sdf * F(1)) / (old_w - F(1))
+            n_sdf = fma32(old_sdf, old_w, -sdf) / (old_w - F(1))
             n_w = np.maximum(F(0), old_w - F(1))
-            res = (old_c[..., :3] * old_w[..., None] - c[..., :3]) / (old_w - F(1))[..., None]
+            res = fma32(old_c[..., :3], old_w[..., None], -c[..., :3]) / (old_w - F(1))[..., None]
         r = np.where(res >= 0, np.floor(res + F(0.5)), np.ceil(res - F(0.5)))        # roundf: half away from zero
         r = np.maximum(F(0), np.fmin(r, F(254.5)))
         rgba = np.concatenate([np.trunc(np.nan_to_num(r)).astype(np.uint8), np.full((N, 512, 1), 255, np.uint8)], -1)
