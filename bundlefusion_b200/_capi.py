@@ -183,11 +183,12 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("BF_B200_LIB", LIB_PATH)        # development: A/B a differently compiled build of the same sources
+    if not os.path.exists(path):
         raise RuntimeError(
             f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make -C bundlefusion_b200/csrc`). There is no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     P = C.POINTER
     vp = C.c_void_p
     # reference-named stubs

@@ -14,7 +14,7 @@
 //    the device; the integrate kernel is a persistent grid that reads that count itself;
 //  * the integrate stencil owns 4 consecutive voxels (48 B = three 16-byte vector accesses)
 //    per thread, touches voxel memory only for threads that pass the truncation test, and
-//    is preceded by a conservative per-block depth-range cull;
+//    can be preceded by a conservative per-block depth-range cull (off by default, measured);
 //  * garbage collection is a single fused kernel (identify + unlink + heap push + clear).
 //
 // Compiled with -fmad=false so that float results are bit-identical to oracle/tsdf_oracle.c.
@@ -627,7 +627,9 @@ __global__ void rebuild_aux_kernel(BFHashDataStruct hd, unsigned numEntries, uns
 // 128 threads per SDF block, 4 consecutive voxels (48 B) per thread.  Persistent grid: each CTA
 // walks the compactified list with stride gridDim.x; the list length is read from device memory.
 struct VoxelQuad { uint4 a, b, c; };
-#define BF_SPEC_BLOCKS 24576u   // 4 voxels = 12 words: v0{a.x,a.y,a.z} v1{a.w,b.x,b.y} v2{b.z,b.w,c.x} v3{c.y,c.z,c.w}
+#ifndef BF_SPEC_BLOCKS
+#define BF_SPEC_BLOCKS 24576u
+#endif   // 4 voxels = 12 words: v0{a.x,a.y,a.z} v1{a.w,b.x,b.y} v2{b.z,b.w,c.x} v3{c.y,c.z,c.w}
 
 __device__ __forceinline__ float clamp_color(float v) { return fmaxf(0.0f, fminf(v, 254.5f)); }
 
@@ -645,8 +647,11 @@ __device__ __forceinline__ unsigned round_clamp_u8(float r) {
     return __float_as_uint(v + 8388608.0f) & 0xffu;            // 254.5 + 2^23 rounds to the even 254 = trunc
 }
 // idx = (unsigned)(int)t and the test idx < limit, t = screen coordinate + 0.5   [cvt.rzi.s32.f32: NaN -> 0, (-1, 0) -> 0]
+#ifndef BF_PIXEL_F2I
+#define BF_PIXEL_F2I 1      // 1: one cvt.rzi per coordinate (XU pipe); 0: the ~10-instruction FMA/ALU-pipe identity below
+#endif
 __device__ __forceinline__ bool pixel_index(float t, unsigned limit, float limitF, unsigned& idx) {
-    if (limit > (1u << 22)) { idx = (unsigned)(int)t; return idx < limit; }
+    if (BF_PIXEL_F2I || limit > (1u << 22)) { idx = (unsigned)(int)t; return idx < limit; }
     if (t <= -1.0f || t >= limitF) return false;               // NaN passes both tests, as the conversion gives 0
     const float c = fmaxf(t, 0.0f);                            // fmaxf(NaN, 0) = 0
     const float n = c + 8388608.0f;                            // 2^23 + rne(c)
@@ -1002,8 +1007,8 @@ compactify_dual_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams
 
 // truncation test of one voxel against one pose; returns true and the clamped sdf / colour when it passes (.cu:433-463)
 __device__ __forceinline__ bool probe_voxel(const BFHashParams& hp, const BFDepthCameraParams& cp, const float* __restrict__ depthImg,
-                                            const uchar4* __restrict__ colorImg, I3 pi, float Wf, float Hf, float& sdfOut, uchar4& colOut) {
-    const F3 pf = xform(hp.m_rigidTransformInverse, voxel_to_world(hp, pi));
+                                            const uchar4* __restrict__ colorImg, F3 world, float Wf, float Hf, float& sdfOut, uchar4& colOut) {
+    const F3 pf = xform(hp.m_rigidTransformInverse, world);
     const float sx = pf.x * cp.fx / pf.z + cp.mx;
     const float sy = pf.y * cp.fy / pf.z + cp.my;
     unsigned px, py;
@@ -1018,7 +1023,10 @@ __device__ __forceinline__ bool probe_voxel(const BFHashParams& hp, const BFDept
     return true;
 }
 
-__global__ void __launch_bounds__(128, 8)
+#ifndef BF_REINT_MINBLOCKS
+#define BF_REINT_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, BF_REINT_MINBLOCKS)
 reintegrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hpOld, const __grid_constant__ BFHashParams hpNew,
                    const __grid_constant__ BFDepthCameraParams cp, const float* __restrict__ depthImg, const uchar4* __restrict__ colorImg,
                    const unsigned* __restrict__ countPtr, const int4* __restrict__ work, const unsigned* __restrict__ workCountPtr,
@@ -1047,8 +1055,9 @@ reintegrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hpO
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const I3 pi = { bx * BF_SDF_BLOCK_SIZE + lx + k, by * BF_SDF_BLOCK_SIZE + ly, bz * BF_SDF_BLOCK_SIZE + lz };
-            if ((fl & 1u) && probe_voxel(hpOld, cp, depthImg, colorImg, pi, Wf, Hf, sdfD[k], colD[k])) maskD |= 1u << k;
-            if ((fl & 2u) && probe_voxel(hpNew, cp, depthImg, colorImg, pi, Wf, Hf, sdfI[k], colI[k])) maskI |= 1u << k;
+            const F3 world = voxel_to_world(hpNew, pi);       // both poses of one scene share the voxel size (checked by the host)
+            if ((fl & 1u) && probe_voxel(hpOld, cp, depthImg, colorImg, world, Wf, Hf, sdfD[k], colD[k])) maskD |= 1u << k;
+            if ((fl & 2u) && probe_voxel(hpNew, cp, depthImg, colorImg, world, Wf, Hf, sdfI[k], colI[k])) maskI |= 1u << k;
         }
         const unsigned mask = maskD | maskI;
         if (mask) {
@@ -1303,9 +1312,13 @@ static int ensure_tiles(TsdfAux* aux, const BFDepthCameraParams* cp) {
     aux->tilesCap = need;
     return 0;
 }
-static int g_cull = -1;               // per-block depth-range cull: bfTsdfSetBlockCull(), or BF_TSDF_CULL=0 in the environment
+// Per-block depth-range cull: OFF by default.  Measured on the bench stream (profiles/r1_tsdf_experiments.md): the cull test
+// lengthens the compactify kernels' critical path by ~4.5 us per call while the blocks it can prove dead (mostly: looking at
+// depths beyond the integration distance) were cheap for the stencil anyway (their probes exit at the depth test).
+// bfTsdfSetBlockCull(1) or BF_TSDF_CULL=1 switches it on; results are identical either way (tests/test_tsdf_gpu.py).
+static int g_cull = -1;
 static bool cull_enabled() {
-    if (g_cull < 0) { const char* e = getenv("BF_TSDF_CULL"); g_cull = (e && e[0] == '0') ? 0 : 1; }
+    if (g_cull < 0) { const char* e = getenv("BF_TSDF_CULL"); g_cull = (e && e[0] == '1') ? 1 : 0; }
     return g_cull == 1;
 }
 
@@ -1413,7 +1426,7 @@ BF_API int bfTsdfReintegrateFrame(BFHashDataStruct* hd, const BFHashParams* hpOl
     int rc = get_aux(hd, hpNew, &aux, true);
     if (rc) return rc;
     if (dd->d_colorData == nullptr) return do_alloc(hd, hpNew, dd->d_depthData, cp, aux, false);     // no colour: neither pass updates a voxel
-    if (aux->work == nullptr) return (int)cudaErrorNotSupported;
+    if (aux->work == nullptr || hpOld->m_virtualVoxelSize != hpNew->m_virtualVoxelSize) return (int)cudaErrorNotSupported;
     // the tiles are built with the new pose's parameters; both passes may use them only if they accept the same depths
     const bool cull = cull_enabled() && hpOld->m_maxIntegrationDistance == hpNew->m_maxIntegrationDistance;
     rc = do_alloc(hd, hpNew, dd->d_depthData, cp, aux, cull); if (rc) return rc;

@@ -197,7 +197,7 @@ size_t bfTsdfAuxBytes(const BFHashParams* hashParams);
 /* FL/DepthSensing/CUDASceneRepHashSDF.h:147-155 (reset) */
 int bfTsdfReset(BFHashDataStruct* hashData, const BFHashParams* hashParams);
 
-/* Per-block depth-range cull of the stencil (default on; results are identical either way -- the cull only skips blocks none
+/* Per-block depth-range cull of the stencil (default off, see tsdf.cu; results are identical either way -- the cull only skips blocks none
  * of whose voxels can pass the reference's truncation test, .cu:433-449).  Returns the previous setting. */
 int bfTsdfSetBlockCull(int enable);
 
