@@ -254,6 +254,15 @@ static int alloc_block(BFHashDataStruct* hd, const BFHashParams* hp, i3 pos) {
     return 1;
 }
 
+/* Multi-GPU spatial shard of the voxel hash (not in the reference; SURVEY.md section 8e, tsdf.cu owns_block): with
+ * hp->m_dummy = {rank, world}, world > 1, a device allocates -- and therefore integrates -- only the blocks it owns. */
+static inline int owns_block(const BFHashParams* hp, i3 b) {
+    const uint32_t world = hp->m_dummy[1];
+    if (world <= 1) return 1;
+    const uint32_t mix = ((uint32_t)b.x * 73856093u) ^ ((uint32_t)b.y * 19349669u) ^ ((uint32_t)b.z * 83492791u);
+    return ((mix * 0x9E3779B1u) >> 8) % world == hp->m_dummy[0];
+}
+
 /* allocKernel: CUDASceneRepHashSDF.cu:165-251 (d_bitMask == NULL: streaming is disabled
  * for BundleFusion, zParametersDefault.txt:99). */
 ORC_API unsigned orc_tsdf_alloc(BFHashDataStruct* hd, const BFHashParams* hp,
@@ -298,7 +307,7 @@ ORC_API unsigned orc_tsdf_alloc(BFHashDataStruct* hd, const BFHashParams* hp,
         if (boundary.z - rayMin.z == 0.0f) { tMax.z = INFINITY; tDelta.z = INFINITY; }
 
         for (unsigned iter = 0; iter < 1024; ++iter) {
-            if (block_in_frustum(hp, cp, cur)) dropped += (unsigned)alloc_block(hd, hp, cur);
+            if (block_in_frustum(hp, cp, cur) && owns_block(hp, cur)) dropped += (unsigned)alloc_block(hd, hp, cur);
             if (tMax.x < tMax.y && tMax.x < tMax.z) {
                 cur.x = f2i((float)cur.x + step.x);
                 if (cur.x == bound.x) break;

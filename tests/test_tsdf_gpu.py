@@ -341,3 +341,32 @@ def test_block_cull_is_conservative(cuda_device):
     cb, cv = orc.canonical_blocks(cpu.download())
     np.testing.assert_array_equal(b1, cb)
     np.testing.assert_array_equal(v1, cv)
+
+
+def test_spatial_shard_matches_oracle_and_unsharded(cuda_device):
+    """Multi-GPU shard (hp.m_dummy = {rank, world}), both ranks run one after the other on this GPU: each shard is bit-identical to
+    the oracle's shard, the shards are disjoint and their union is the unsharded state (the world-size-2
+    process-level version with the frame broadcast runs on CPU/gloo in tests/test_shard_gloo_cpu.py)."""
+    import torch
+    W, H = 160, 120
+    cam = camera_params(W, H)
+    frames = [synth.make_frame(35 * i, W, H) for i in range(4)]
+    whole = orc.OracleSceneRepHashSDF(small_params())
+    for d, c, T in frames:
+        whole.integrate(T, d, c, cam)
+    wb, wv = orc.canonical_blocks(whole.download())
+    got_b, got_v = [], []
+    for rank in range(2):
+        hp = small_params(); hp.m_dummy = (2 << 32) | rank
+        gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device), orc.OracleSceneRepHashSDF(hp)
+        for d, c, T in frames:
+            dd, dc = to_dev(torch, cuda_device, d, c)
+            gpu.integrate(T, dd, dc, cam); cpu.integrate(T, d, c, cam)
+        assert_same_state(gpu, cpu, hp)
+        b, v = orc.canonical_blocks(gpu.download())
+        got_b.append(b); got_v.append(v)
+    assert not (set(map(tuple, got_b[0])) & set(map(tuple, got_b[1])))
+    mb, mv = np.concatenate(got_b), np.concatenate(got_v)
+    order = np.lexsort((mb[:, 2], mb[:, 1], mb[:, 0]))
+    np.testing.assert_array_equal(mb[order], wb)
+    np.testing.assert_array_equal(mv[order], wv)
