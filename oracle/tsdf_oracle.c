@@ -6,12 +6,16 @@
  * cpu_baseline / --impl reference legs use it (as the checker / the timed CPU
  * baseline, never as the product).
  *
- * PARITY STATUS: "parity unpinned" -- the reference ships no golden vectors or
- * tests for this path and its .cu files do not compile
- * with CUDA 12.9 as they are.  This restatement is pinned (a) by analytic
- * known-answer tests we author (tests/test_tsdf_oracle.py) and (b) on the GPU
- * box against oracle/_ref, the reference's own kernels built from
- * /root/reference with the mechanical compat patch in oracle/build_ref.py.
+ * PARITY STATUS: the reference ships no golden vectors or tests for this path
+ * (SURVEY.md section 4 / 8c), its .cu files do not compile with CUDA 12.9 as they
+ * are, and they need a GPU.  This restatement is pinned (a) in the authoring
+ * container by analytic known-answer tests we author (tests/test_tsdf_oracle.py)
+ * -- by itself that would be "parity unpinned" -- and (b) on the GPU box against
+ * the reference itself: oracle/_ref holds the reference's own kernels built from
+ * /root/reference with the mechanical compat patch in oracle/build_ref.py, and
+ * tests/test_tsdf_vs_reference_gpu.py compares them, this oracle's contract and
+ * the CUDA library on identical frames (block set bit-exact, voxel words equal but
+ * for a ~2e-5 fraction on a pixel / truncation decision boundary).
  *
  * Every function cites the reference lines it restates.  FL/ = FriedLiver/Source/.
  *
