@@ -35,8 +35,27 @@ BF_API void bfMat4Inverse(const float* m, float* out) {
     out[15] = (a20 * s3 - a21 * s1 + a22 * s0) * r;
 }
 
+namespace bf {
+int tsdf_lanes_begin(const BFHashDataStruct* hd, const BFHashParams* hp);     // tsdf.cu: two-lane replay bracket
+int tsdf_lanes_end(const BFHashDataStruct* hd);
+}
+
+static int run_ops(BFHashDataStruct* hd, BFHashParams* hp, const BFDepthCameraParams* cam, const BFTsdfOp* ops, int numOps,
+                   const float* const* d_depthFrames, const uint8_t* const* d_colorFrames);
+
+// One call replays a whole batch of TSDF operations.  Inside, the stencil of op k runs on the library's back lane while alloc +
+// compactify of op k+1 run on the caller's stream (tsdf.cu, "two lanes"); on return the caller's stream is ordered after all of it.
 BF_API int bfTsdfRunOps(BFHashDataStruct* hd, BFHashParams* hp, const BFDepthCameraParams* cam, const BFTsdfOp* ops, int numOps,
                         const float* const* d_depthFrames, const uint8_t* const* d_colorFrames) {
+    int rc = bf::tsdf_lanes_begin(hd, hp);
+    if (rc) return rc;
+    rc = run_ops(hd, hp, cam, ops, numOps, d_depthFrames, d_colorFrames);
+    const int rc2 = bf::tsdf_lanes_end(hd);
+    return rc ? rc : rc2;
+}
+
+static int run_ops(BFHashDataStruct* hd, BFHashParams* hp, const BFDepthCameraParams* cam, const BFTsdfOp* ops, int numOps,
+                   const float* const* d_depthFrames, const uint8_t* const* d_colorFrames) {
     static int fuse = -1;        // BF_TSDF_FUSE_REINT=0 replays every op separately (A/B measurements)
     if (fuse < 0) { const char* e = getenv("BF_TSDF_FUSE_REINT"); fuse = (e && e[0] == '0') ? 0 : 1; }
     for (int i = 0; i < numOps; ++i) {

@@ -57,8 +57,18 @@ struct TsdfAux {
     unsigned numSlots = 0;
     unsigned parity = 0;             // which of the two compactify counters is live
     bool lastListDual = false;       // the live list is a union list of a fused re-integration (GC then visits only its new-pose part)
+    // two-lane replay (bfTsdfRunOps): alloc + compactify of op k+1 on the caller's stream while the stencil of op k runs on `lane`
+    int4* work2[2] = { nullptr, nullptr };   // work list per counter set (work2[0] aliases `work`)
+    cudaStream_t lane = nullptr;
+    cudaEvent_t evFork = nullptr, evList[2] = { nullptr, nullptr }, evStencil[2] = { nullptr, nullptr };
+    bool stencilPending[2] = { false, false };
+    bool pipeOpen = false;
 };
-enum { CTR_HIGH_WATER = 0, CTR_COUNT0 = 1, CTR_COUNT1 = 2, CTR_E = 3, CTR_CULLED = 4, CTR_WORK0 = 5, CTR_U_LO = 6, CTR_U_HI = 7, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROPPED = 10, CTR_WORK1 = 11, CTR_U_TOT_LO = 12, CTR_U_TOT_HI = 13, CTR_E_TOT_LO = 14, CTR_E_TOT_HI = 15, CTR_NUM = 16 };
+enum { CTR_HIGH_WATER = 0, CTR_E = 3, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROPPED = 10, CTR_U_TOT_LO = 12, CTR_U_TOT_HI = 13, CTR_E_TOT_LO = 14, CTR_E_TOT_HI = 15,
+       // two per-list counter sets (the list / work list of op k and of op k+1 are alive at the same time when alloc + compactify of
+       // op k+1 run on the front lane while the stencil of op k runs on the back lane); a set is zeroed by the op that is about to fill it
+       CTR_SET0 = 16, CTR_SET1 = 24, CTR_NUM = 32,
+       SET_COUNT = 0, SET_WORK = 1, SET_CULLED = 2, SET_U_LO = 4, SET_U_HI = 5, SET_WORDS = 8 };
 
 // launch accounting + optional CUDA-event timing of the integrate / de-integrate stencil (bench.py's roofline line)
 unsigned long long g_launchCount = 0;
@@ -479,10 +489,11 @@ __device__ __noinline__ void alloc_pixel_direct(const BFHashDataStruct& hd, cons
 
 __global__ void __launch_bounds__(256, 8)    // 32 regs: the whole 640x480 frame is resident in one wave
 alloc_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
-             const float* __restrict__ depth, int4* slotInfo, unsigned* ctrs, float2* tiles) {
+             const float* __restrict__ depth, int4* slotInfo, unsigned* ctrs, float2* tiles, int zeroSet) {
     __shared__ unsigned long long sSet[BF_ALLOC_SET];
     __shared__ float2 sRed[8];
     const unsigned tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (zeroSet >= 0 && blockIdx.x == 0 && blockIdx.y == 0 && tid < SET_WORDS) ctrs[zeroSet + tid] = 0;   // nothing in this kernel reads the set
     for (unsigned i = tid; i < BF_ALLOC_SET; i += 256) sSet[i] = 0ull;
     const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -547,16 +558,14 @@ alloc_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const
 
 // compactify: list of allocated AND in-frustum blocks (CUDASceneRepHashSDF.cu:324-366),
 // produced from the dense slot table [0, highWater) instead of the 4*numBuckets entry table.
-// Warp-aggregated append; count accumulates in ctrs[countIdx]; the other parity is zeroed for
-// the next call.
+// Warp-aggregated append; counts accumulate in the counter set `set` (zeroed by the preceding launch).
 __global__ void __launch_bounds__(256)
 compactify_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
-                  const int4* __restrict__ slotInfo, unsigned* ctrs, int countIdx, int otherIdx,
+                  const int4* __restrict__ slotInfo, unsigned* ctrs, int set,
                   int4* __restrict__ work, const float2* __restrict__ tiles, int tilesX) {
     const unsigned highWater = ctrs[CTR_HIGH_WATER];
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int workIdx = countIdx == CTR_COUNT0 ? CTR_WORK0 : CTR_WORK1, otherWork = countIdx == CTR_COUNT0 ? CTR_WORK1 : CTR_WORK0;
-    if (tid == 0) { ctrs[otherIdx] = 0; ctrs[otherWork] = 0; ctrs[CTR_CULLED] = 0; ctrs[CTR_U_LO] = 0; ctrs[CTR_U_HI] = 0; }
+    const int countIdx = set + SET_COUNT, workIdx = set + SET_WORK;       // zeroed by the launch before this one
     const unsigned stride = gridDim.x * blockDim.x;
     const unsigned lane = threadIdx.x & 31;
     for (unsigned base = tid - lane; base < highWater; base += stride) {
@@ -579,7 +588,7 @@ compactify_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, 
                 warpBase = atomicAdd(&ctrs[countIdx], __popc(ballot));
                 if (work) {
                     if (ballotW) workBase = atomicAdd(&ctrs[workIdx], __popc(ballotW));
-                    if (ballot != ballotW) atomicAdd(&ctrs[CTR_CULLED], __popc(ballot) - __popc(ballotW));
+                    if (ballot != ballotW) atomicAdd(&ctrs[set + SET_CULLED], __popc(ballot) - __popc(ballotW));
                     atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_E_TOT_LO]), (unsigned long long)__popc(ballot));
                 }
             }
@@ -694,8 +703,10 @@ template <bool kDeIntegrate>
 __global__ void __launch_bounds__(128)
 integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
                  const float* __restrict__ depthImg, const uchar4* __restrict__ colorImg,
-                 const unsigned* __restrict__ countPtr, unsigned countOverride, unsigned* ctrs, int* __restrict__ live,
-                 const int4* __restrict__ work, const unsigned* __restrict__ workCountPtr) {
+                 int useListCount, unsigned countOverride, unsigned* ctrs, int* __restrict__ live,
+                 const int4* __restrict__ work, int set) {
+    const unsigned* countPtr = useListCount ? ctrs + set + SET_COUNT : nullptr;
+    const unsigned* workCountPtr = ctrs + set + SET_WORK;
     // `work` (from the library's own compactify): the list entries that survive the depth-range cull, 16 B each; without it
     // (reference-named stubs, whose list may come from anywhere) the kernel walks d_hashCompactified itself.
     const unsigned listCount = countPtr ? *countPtr : countOverride;
@@ -787,7 +798,7 @@ integrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, c
     __syncthreads();
     if (t == 0) {
         const unsigned long long tot = (unsigned long long)sPassed[0] + sPassed[1] + sPassed[2] + sPassed[3];
-        if (tot) { atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot); atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_TOT_LO]), tot); }
+        if (tot) { atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[set + SET_U_LO]), tot); atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_TOT_LO]), tot); }
     }
 }
 
@@ -833,7 +844,7 @@ template <bool kDeIntegrate>
 __global__ void __launch_bounds__(160)
 integrate_tma_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
                      const float* __restrict__ depthImg, const uchar4* __restrict__ colorImg,
-                     const unsigned* __restrict__ countPtr, unsigned countOverride, unsigned* ctrs, int* __restrict__ live) {
+                     const unsigned* __restrict__ countPtr, unsigned countOverride, unsigned* ctrs, int* __restrict__ live, int set) {
     __shared__ __align__(128) uint4 sTile[BF_TMA_STAGES][BF_TILE_BYTES / 16];
     __shared__ __align__(8) unsigned long long sFull[BF_TMA_STAGES], sEmpty[BF_TMA_STAGES];
     __shared__ unsigned sPassed[4];
@@ -942,7 +953,7 @@ integrate_tma_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams h
     asm volatile("bar.sync 1, 128;" ::: "memory");          // consumers only (the producer warp has left)
     if (t == 0) {
         const unsigned long long tot = (unsigned long long)sPassed[0] + sPassed[1] + sPassed[2] + sPassed[3];
-        if (tot) { atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot); atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_TOT_LO]), tot); }
+        if (tot) { atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[set + SET_U_LO]), tot); atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_TOT_LO]), tot); }
     }
 }
 
@@ -953,12 +964,11 @@ integrate_tma_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams h
 // voxel read + one write instead of two of each, and 3 launches instead of 5.
 __global__ void __launch_bounds__(256)
 compactify_dual_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hpOld, const __grid_constant__ BFHashParams hpNew,
-                       const __grid_constant__ BFDepthCameraParams cp, const int4* __restrict__ slotInfo, unsigned* ctrs, int countIdx, int otherIdx,
+                       const __grid_constant__ BFDepthCameraParams cp, const int4* __restrict__ slotInfo, unsigned* ctrs, int set,
                        unsigned char* __restrict__ listFlags, int4* __restrict__ work, const float2* __restrict__ tiles, int tilesX) {
     const unsigned highWater = ctrs[CTR_HIGH_WATER];
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int workIdx = countIdx == CTR_COUNT0 ? CTR_WORK0 : CTR_WORK1, otherWork = countIdx == CTR_COUNT0 ? CTR_WORK1 : CTR_WORK0;
-    if (tid == 0) { ctrs[otherIdx] = 0; ctrs[otherWork] = 0; ctrs[CTR_CULLED] = 0; ctrs[CTR_U_LO] = 0; ctrs[CTR_U_HI] = 0; }
+    const int countIdx = set + SET_COUNT, workIdx = set + SET_WORK;
     const unsigned stride = gridDim.x * blockDim.x;
     const unsigned lane = threadIdx.x & 31;
     for (unsigned base = tid - lane; base < highWater; base += stride) {
@@ -986,7 +996,7 @@ compactify_dual_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams
             if (lane == 0) {
                 warpBase = atomicAdd(&ctrs[countIdx], __popc(ballot));
                 if (ballotW) workBase = atomicAdd(&ctrs[workIdx], __popc(ballotW));
-                if (nE != nP) atomicAdd(&ctrs[CTR_CULLED], nE - nP);
+                if (nE != nP) atomicAdd(&ctrs[set + SET_CULLED], nE - nP);
                 atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_E_TOT_LO]), (unsigned long long)nE);
             }
             warpBase = __shfl_sync(0xffffffffu, warpBase, 0);
@@ -1029,9 +1039,9 @@ __device__ __forceinline__ bool probe_voxel(const BFHashParams& hp, const BFDept
 __global__ void __launch_bounds__(128, BF_REINT_MINBLOCKS)
 reintegrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hpOld, const __grid_constant__ BFHashParams hpNew,
                    const __grid_constant__ BFDepthCameraParams cp, const float* __restrict__ depthImg, const uchar4* __restrict__ colorImg,
-                   const unsigned* __restrict__ countPtr, const int4* __restrict__ work, const unsigned* __restrict__ workCountPtr,
-                   unsigned* ctrs, int* __restrict__ live) {
-    const unsigned count = *workCountPtr;
+                   const int4* __restrict__ work, int set, unsigned* ctrs, int* __restrict__ live) {
+    const unsigned* countPtr = ctrs + set + SET_COUNT;
+    const unsigned count = ctrs[set + SET_WORK];
     const unsigned t = threadIdx.x;
     const int lx = (int)((4 * t) & 7), ly = (int)(((4 * t) & 63) >> 3), lz = (int)((4 * t) >> 6);
     unsigned passed = 0;
@@ -1087,7 +1097,7 @@ reintegrate_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hpO
     __syncthreads();
     if (t == 0) {
         const unsigned long long tot = (unsigned long long)sPassed[0] + sPassed[1] + sPassed[2] + sPassed[3];
-        if (tot) { atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_LO]), tot); atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_TOT_LO]), tot); }
+        if (tot) { atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[set + SET_U_LO]), tot); atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_U_TOT_LO]), tot); }
         if (blockIdx.x == 0) { const unsigned listCount = *countPtr; hd.d_hashCompactifiedCounter[0] = (int)listCount; ctrs[CTR_E] = listCount; }
     }
 }
@@ -1254,20 +1264,30 @@ gc_live_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, con
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+static void free_aux(TsdfAux& a) {
+    cudaFree(a.slotInfo); cudaFree(a.ctrs); cudaFree(a.live); cudaFree(a.listFlags); cudaFree(a.work2[0]); cudaFree(a.work2[1]); cudaFree(a.tiles);
+    if (a.lane) cudaStreamDestroy(a.lane);
+    if (a.evFork) cudaEventDestroy(a.evFork);
+    for (int k = 0; k < 2; ++k) { if (a.evList[k]) cudaEventDestroy(a.evList[k]); if (a.evStencil[k]) cudaEventDestroy(a.evStencil[k]); }
+}
+
 static int get_aux(const BFHashDataStruct* hd, const BFHashParams* hp, TsdfAux** out, bool create, bool adopt) {
     std::lock_guard<std::mutex> lk(g_auxMutex);
     auto it = g_aux.find(hd->d_hash);
     if (it != g_aux.end() && (hp == nullptr || it->second.numSlots == hp->m_numSDFBlocks)) { *out = &it->second; return 0; }
     if (!create || hp == nullptr) { *out = nullptr; return (int)cudaErrorInvalidValue; }
-    if (it != g_aux.end()) { cudaFree(it->second.slotInfo); cudaFree(it->second.ctrs); cudaFree(it->second.live); cudaFree(it->second.listFlags);
-                             cudaFree(it->second.work); cudaFree(it->second.tiles); g_aux.erase(it); }
+    if (it != g_aux.end()) { free_aux(it->second); g_aux.erase(it); }
     TsdfAux a;
     a.numSlots = hp->m_numSDFBlocks;
     BF_CHECK(cudaMalloc(&a.slotInfo, sizeof(int4) * (size_t)a.numSlots));
     BF_CHECK(cudaMalloc(&a.ctrs, sizeof(unsigned) * CTR_NUM));
     BF_CHECK(cudaMalloc(&a.live, sizeof(int) * (size_t)a.numSlots));
     BF_CHECK(cudaMalloc(&a.listFlags, (size_t)a.numSlots));
-    if (a.numSlots < (1u << 28)) BF_CHECK(cudaMalloc(&a.work, sizeof(int4) * (size_t)a.numSlots));     // slot index shares a word with 4 flag bits
+    if (a.numSlots < (1u << 28)) {                                   // slot index shares a word with 4 flag bits
+        BF_CHECK(cudaMalloc(&a.work2[0], sizeof(int4) * (size_t)a.numSlots));
+        BF_CHECK(cudaMalloc(&a.work2[1], sizeof(int4) * (size_t)a.numSlots));
+        a.work = a.work2[0];
+    }
     BF_CHECK(cudaMemsetAsync(a.live, 0, sizeof(int) * (size_t)a.numSlots, g_stream));
     a.liveValid = !adopt;           // an adopted table has unknown weights: fall back to the scanning GC
     BF_CHECK(cudaMemsetAsync(a.ctrs, 0, sizeof(unsigned) * CTR_NUM, g_stream));
@@ -1322,14 +1342,40 @@ static bool cull_enabled() {
     return g_cull == 1;
 }
 
+// ---- two lanes ---------------------------------------------------------------------------------------------------
+// Front lane = the caller's stream (g_stream): alloc, depth tiles, compactify, GC.  Back lane = aux->lane: the stencils.
+// Inside a bfTsdfRunOps bracket the stencil of op k runs on the back lane while alloc + compactify of op k+1 run on the
+// front lane: they touch disjoint state (hash / heap / slot table / list k+1  vs  work list k / voxels), both are
+// issue-bound at roughly half an SM's capacity, and the stencil is launched with a grid that leaves room for the other.
+// Ordering: stencil k waits for list k (evList); the first front-lane launch of op k+2 waits for stencil k (evStencil),
+// because it recycles stencil k's counter set and work list; stencils are serial on the back lane (consecutive stencils
+// may touch the same voxels); GC and the end of the bracket join both lanes.  Outside a bracket everything is launched on
+// the caller's stream, as before.
+static inline int set_of(unsigned parity) { return parity ? CTR_SET1 : CTR_SET0; }
+static inline cudaStream_t back_lane(const TsdfAux* aux) { return aux->pipeOpen ? aux->lane : g_stream; }
+// called before the first front-lane launch of an op whose list will use `parity`
+static int front_acquire_set(TsdfAux* aux, unsigned parity) {
+    if (aux->pipeOpen && aux->stencilPending[parity]) { BF_CHECK(cudaStreamWaitEvent(g_stream, aux->evStencil[parity], 0)); aux->stencilPending[parity] = false; }
+    return 0;
+}
+static int join_lanes(TsdfAux* aux) {
+    if (!aux->pipeOpen) return 0;
+    for (unsigned p = 0; p < 2; ++p)
+        if (aux->stencilPending[p]) { BF_CHECK(cudaStreamWaitEvent(g_stream, aux->evStencil[p], 0)); aux->stencilPending[p] = false; }
+    return 0;
+}
+
 // withTiles: also leave the depth-tile min/max for the stencil's block cull (library sequences only; the reference-named
-// allocCUDA stub has no say over what is integrated afterwards)
-static int do_alloc(BFHashDataStruct* hd, const BFHashParams* hp, const float* depth, const BFDepthCameraParams* cp, TsdfAux* aux, bool withTiles) {
+// allocCUDA stub has no say over what is integrated afterwards).  zeroParity >= 0: the launch also zeroes that counter set
+// (the one the following compactify fills).
+static int do_alloc(BFHashDataStruct* hd, const BFHashParams* hp, const float* depth, const BFDepthCameraParams* cp, TsdfAux* aux, bool withTiles, int zeroParity) {
     dim3 block(BF_TILE, BF_TILE);
     dim3 grid((cp->m_imageWidth + block.x - 1) / block.x, (cp->m_imageHeight + block.y - 1) / block.y);
     if (withTiles) { int rc = ensure_tiles(aux, cp); if (rc) return rc; }
+    if (zeroParity >= 0) { int rc = front_acquire_set(aux, (unsigned)zeroParity); if (rc) return rc; }
     ++g_launchCount;
-    alloc_kernel<<<grid, block, 0, g_stream>>>(*hd, *hp, *cp, depth, aux->slotInfo, aux->ctrs, withTiles ? aux->tiles : nullptr);
+    alloc_kernel<<<grid, block, 0, g_stream>>>(*hd, *hp, *cp, depth, aux->slotInfo, aux->ctrs, withTiles ? aux->tiles : nullptr,
+                                               zeroParity >= 0 ? set_of((unsigned)zeroParity) : -1);
     BF_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1344,49 +1390,111 @@ static int do_depth_tiles(const BFHashParams* hp, const float* depth, const BFDe
 }
 
 // useWork: also emit the stencil work list (library sequences); useTiles: aux->tiles describe the depth image the following
-// stencil will read -> entries no voxel of which can pass are left out of the work list
-static int do_compactify(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraParams* cp, TsdfAux* aux, bool useWork, bool useTiles) {
+// stencil will read -> entries no voxel of which can pass are left out of the work list.  setZeroed: the preceding launch
+// (alloc_kernel) already zeroed the counter set of the new parity.
+static int do_compactify(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraParams* cp, TsdfAux* aux, bool useWork, bool useTiles, bool setZeroed) {
     aux->parity ^= 1u;
     aux->lastListDual = false;
-    const int countIdx = aux->parity ? CTR_COUNT1 : CTR_COUNT0;
-    const int otherIdx = aux->parity ? CTR_COUNT0 : CTR_COUNT1;
+    const int set = set_of(aux->parity);
+    if (!setZeroed) {
+        int rc = front_acquire_set(aux, aux->parity); if (rc) return rc;
+        BF_CHECK(cudaMemsetAsync(aux->ctrs + set, 0, SET_WORDS * sizeof(unsigned), g_stream));
+    }
     ++g_launchCount;
-    compactify_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, *hp, *cp, aux->slotInfo, aux->ctrs, countIdx, otherIdx,
-                                                                                            useWork ? aux->work : nullptr, (useWork && useTiles) ? aux->tiles : nullptr, tiles_x(cp));
+    compactify_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, *hp, *cp, aux->slotInfo, aux->ctrs, set,
+                                                                                            useWork ? aux->work2[aux->parity] : nullptr, (useWork && useTiles) ? aux->tiles : nullptr, tiles_x(cp));
     BF_CHECK(cudaGetLastError());
+    if (aux->pipeOpen) BF_CHECK(cudaEventRecord(aux->evList[aux->parity], g_stream));
     return 0;
 }
 
-static inline const unsigned* live_count_ptr(const TsdfAux* aux) { return aux->ctrs + (aux->parity ? CTR_COUNT1 : CTR_COUNT0); }
-static inline const unsigned* work_count_ptr(const TsdfAux* aux) { return aux->ctrs + (aux->parity ? CTR_WORK1 : CTR_WORK0); }
+static inline const unsigned* live_count_ptr(const TsdfAux* aux) { return aux->ctrs + set_of(aux->parity) + SET_COUNT; }
+
+// before / after a stencil launch on the back lane
+static int stencil_begin(TsdfAux* aux) {
+    if (aux->pipeOpen) BF_CHECK(cudaStreamWaitEvent(aux->lane, aux->evList[aux->parity], 0));
+    return 0;
+}
+static int stencil_end(TsdfAux* aux) {
+    if (aux->pipeOpen) { BF_CHECK(cudaEventRecord(aux->evStencil[aux->parity], aux->lane)); aux->stencilPending[aux->parity] = true; }
+    return 0;
+}
+// Stencil CTAs per SM inside a two-lane bracket.  Measured (profiles/r1_tsdf_experiments.md section 5): capping the stencil at 4-6
+// CTAs per SM so that alloc CTAs can co-reside costs the stencil more (38 -> 49-60 us) than the overlap returns; uncapped, the
+// front lane fills the SMs the stencil's last wave frees, worth ~7 % of the TSDF time.
+static int stencil_per_sm() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BF_TSDF_LANE_STENCIL_PER_SM"); v = e ? atoi(e) : 16; if (v < 1) v = 1; if (v > 16) v = 16; }
+    return v;
+}
 
 static int do_integrate(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraData* dd, const BFDepthCameraParams* cp,
-                        TsdfAux* aux, bool deIntegrate, const unsigned* countPtr, unsigned countOverride) {
-    const unsigned upper = countPtr ? hp->m_numSDFBlocks : countOverride;
+                        TsdfAux* aux, bool deIntegrate, bool useListCount, unsigned countOverride) {
+    const unsigned upper = useListCount ? hp->m_numSDFBlocks : countOverride;
     if (upper == 0) return 0;
     const uchar4* color = reinterpret_cast<const uchar4*>(dd->d_colorData);
     static int variant = -1;        // BF_TSDF_INTEGRATE=tma selects the TMA-staged variant (measured slower)
     if (variant < 0) { const char* e = getenv("BF_TSDF_INTEGRATE"); variant = (e && e[0] == 't') ? 1 : 0; }
+    const cudaStream_t sb = back_lane(aux);
+    int rc = stencil_begin(aux); if (rc) return rc;
     const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
     if (g_profile) ++g_profLaunches;
     if (timeIt) {
         if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
-        BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], g_stream));
+        BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], sb));
     }
     ++g_launchCount;
+    const int set = set_of(aux->parity);
     if (variant == 0) {
-        const int grid = grid_for(upper, 16);
-        const int4* work = countPtr ? aux->work : nullptr;        // the stubs' list (countOverride) has no work list
-        if (deIntegrate) integrate_kernel<true><<<grid, 128, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live, work, work_count_ptr(aux));
-        else             integrate_kernel<false><<<grid, 128, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live, work, work_count_ptr(aux));
+        const int grid = grid_for(upper, aux->pipeOpen ? stencil_per_sm() : 16);
+        const int4* work = useListCount ? aux->work2[aux->parity] : nullptr;        // the stubs' list (countOverride) has no work list
+        if (deIntegrate) integrate_kernel<true><<<grid, 128, 0, sb>>>(*hd, *hp, *cp, dd->d_depthData, color, useListCount ? 1 : 0, countOverride, aux->ctrs, aux->live, work, set);
+        else             integrate_kernel<false><<<grid, 128, 0, sb>>>(*hd, *hp, *cp, dd->d_depthData, color, useListCount ? 1 : 0, countOverride, aux->ctrs, aux->live, work, set);
     } else {
         const int grid = grid_for(upper, 6);
-        if (deIntegrate) integrate_tma_kernel<true><<<grid, 160, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live);
-        else             integrate_tma_kernel<false><<<grid, 160, 0, g_stream>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live);
+        const unsigned* countPtr = useListCount ? live_count_ptr(aux) : nullptr;
+        if (deIntegrate) integrate_tma_kernel<true><<<grid, 160, 0, sb>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live, set);
+        else             integrate_tma_kernel<false><<<grid, 160, 0, sb>>>(*hd, *hp, *cp, dd->d_depthData, color, countPtr, countOverride, aux->ctrs, aux->live, set);
     }
     BF_CHECK(cudaGetLastError());
-    if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], g_stream)); ++g_evUsed; }
+    if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], sb)); ++g_evUsed; }
+    return stencil_end(aux);
+}
+
+// bracket of a two-lane replay (used by bfTsdfRunOps, host_api.cu)
+int tsdf_lanes_begin(const BFHashDataStruct* hd, const BFHashParams* hp) {
+    static int enabled = -1;         // BF_TSDF_LANES=0: everything on the caller's stream (A/B measurements)
+    if (enabled < 0) {
+        const char* e = getenv("BF_TSDF_LANES"); enabled = (e && e[0] == '0') ? 0 : 1;
+        const char* v = getenv("BF_TSDF_INTEGRATE"); if (v && v[0] == 't') enabled = 0;      // the TMA variant walks d_hashCompactified, which the front lane rewrites
+    }
+    if (!enabled) return 0;
+    TsdfAux* aux;
+    int rc = get_aux(hd, hp, &aux, true);
+    if (rc) return rc;
+    if (aux->pipeOpen) return 0;
+    if (!aux->lane) {
+        int lo = 0, hi = 0;
+        BF_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        BF_CHECK(cudaStreamCreateWithPriority(&aux->lane, cudaStreamNonBlocking, hi));     // the stencil is the critical path
+        BF_CHECK(cudaEventCreateWithFlags(&aux->evFork, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            BF_CHECK(cudaEventCreateWithFlags(&aux->evList[k], cudaEventDisableTiming));
+            BF_CHECK(cudaEventCreateWithFlags(&aux->evStencil[k], cudaEventDisableTiming));
+        }
+    }
+    BF_CHECK(cudaEventRecord(aux->evFork, g_stream));          // the back lane starts after everything already queued by the caller
+    BF_CHECK(cudaStreamWaitEvent(aux->lane, aux->evFork, 0));
+    aux->stencilPending[0] = aux->stencilPending[1] = false;
+    aux->pipeOpen = true;
     return 0;
+}
+int tsdf_lanes_end(const BFHashDataStruct* hd) {
+    TsdfAux* aux;
+    if (get_aux(hd, nullptr, &aux, false) != 0 || !aux->pipeOpen) return 0;
+    int rc = join_lanes(aux);          // the caller's stream continues after the last stencil
+    aux->pipeOpen = false;
+    return rc;
 }
 
 }  // namespace bf
@@ -1400,7 +1508,7 @@ BF_API void bfSetStream(void* s) { g_stream = (cudaStream_t)s; }
 BF_API void* bfGetStream(void) { return (void*)g_stream; }
 BF_API const char* bfGetLastErrorString(void) { return t_lastError.c_str(); }
 
-BF_API size_t bfTsdfAuxBytes(const BFHashParams* hp) { return (2 * sizeof(int4) + sizeof(int) + 1) * (size_t)hp->m_numSDFBlocks + sizeof(unsigned) * CTR_NUM; }
+BF_API size_t bfTsdfAuxBytes(const BFHashParams* hp) { return (3 * sizeof(int4) + sizeof(int) + 1) * (size_t)hp->m_numSDFBlocks + sizeof(unsigned) * CTR_NUM; }
 
 BF_API int bfTsdfReset(BFHashDataStruct* hd, const BFHashParams* hp) { return do_reset(hd, hp); }
 
@@ -1412,10 +1520,10 @@ BF_API int bfTsdfIntegrateFrame(BFHashDataStruct* hd, const BFHashParams* hp, co
     int rc = get_aux(hd, hp, &aux, true);
     if (rc) return rc;
     const bool cull = cull_enabled() && dd->d_colorData != nullptr;
-    if (!deIntegrate) { rc = do_alloc(hd, hp, dd->d_depthData, cp, aux, cull); if (rc) return rc; }
-    else if (cull)    { rc = do_depth_tiles(hp, dd->d_depthData, cp, aux); if (rc) return rc; }
-    rc = do_compactify(hd, hp, cp, aux, true, cull); if (rc) return rc;
-    return do_integrate(hd, hp, dd, cp, aux, deIntegrate != 0, live_count_ptr(aux), 0);
+    if (!deIntegrate) { rc = do_alloc(hd, hp, dd->d_depthData, cp, aux, cull, (int)(aux->parity ^ 1u)); if (rc) return rc; }
+    else if (cull)    { rc = front_acquire_set(aux, aux->parity ^ 1u); if (rc) return rc; rc = do_depth_tiles(hp, dd->d_depthData, cp, aux); if (rc) return rc; }
+    rc = do_compactify(hd, hp, cp, aux, true, cull, /*setZeroed=*/!deIntegrate); if (rc) return rc;
+    return do_integrate(hd, hp, dd, cp, aux, deIntegrate != 0, true, 0);
 }
 
 // CUDASceneRepHashSDF::deIntegrate(old pose) immediately followed by ::integrate(new pose) of the SAME frame
@@ -1425,36 +1533,40 @@ BF_API int bfTsdfReintegrateFrame(BFHashDataStruct* hd, const BFHashParams* hpOl
     TsdfAux* aux;
     int rc = get_aux(hd, hpNew, &aux, true);
     if (rc) return rc;
-    if (dd->d_colorData == nullptr) return do_alloc(hd, hpNew, dd->d_depthData, cp, aux, false);     // no colour: neither pass updates a voxel
+    if (dd->d_colorData == nullptr) return do_alloc(hd, hpNew, dd->d_depthData, cp, aux, false, -1);     // no colour: neither pass updates a voxel
     if (aux->work == nullptr || hpOld->m_virtualVoxelSize != hpNew->m_virtualVoxelSize) return (int)cudaErrorNotSupported;
     // the tiles are built with the new pose's parameters; both passes may use them only if they accept the same depths
     const bool cull = cull_enabled() && hpOld->m_maxIntegrationDistance == hpNew->m_maxIntegrationDistance;
-    rc = do_alloc(hd, hpNew, dd->d_depthData, cp, aux, cull); if (rc) return rc;
+    rc = do_alloc(hd, hpNew, dd->d_depthData, cp, aux, cull, (int)(aux->parity ^ 1u)); if (rc) return rc;
     aux->parity ^= 1u;
     aux->lastListDual = true;
-    const int countIdx = aux->parity ? CTR_COUNT1 : CTR_COUNT0, otherIdx = aux->parity ? CTR_COUNT0 : CTR_COUNT1;
+    const int set = set_of(aux->parity);
     ++g_launchCount;
-    compactify_dual_kernel<<<grid_for((hpNew->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, *hpOld, *hpNew, *cp, aux->slotInfo, aux->ctrs, countIdx, otherIdx, aux->listFlags,
-                                                                                                    aux->work, cull ? aux->tiles : nullptr, tiles_x(cp));
+    compactify_dual_kernel<<<grid_for((hpNew->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, *hpOld, *hpNew, *cp, aux->slotInfo, aux->ctrs, set, aux->listFlags,
+                                                                                                    aux->work2[aux->parity], cull ? aux->tiles : nullptr, tiles_x(cp));
     BF_CHECK(cudaGetLastError());
+    if (aux->pipeOpen) BF_CHECK(cudaEventRecord(aux->evList[aux->parity], g_stream));
+    const cudaStream_t sb = back_lane(aux);
+    rc = stencil_begin(aux); if (rc) return rc;
     const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
     if (g_profile) ++g_profLaunches;
     if (timeIt) {
         if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
-        BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], g_stream));
+        BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], sb));
     }
     ++g_launchCount;
-    reintegrate_kernel<<<grid_for(hpNew->m_numSDFBlocks, 16), 128, 0, g_stream>>>(*hd, *hpOld, *hpNew, *cp, dd->d_depthData, reinterpret_cast<const uchar4*>(dd->d_colorData),
-                                                                                  live_count_ptr(aux), aux->work, work_count_ptr(aux), aux->ctrs, aux->live);
+    reintegrate_kernel<<<grid_for(hpNew->m_numSDFBlocks, aux->pipeOpen ? stencil_per_sm() : 16), 128, 0, sb>>>(
+        *hd, *hpOld, *hpNew, *cp, dd->d_depthData, reinterpret_cast<const uchar4*>(dd->d_colorData), aux->work2[aux->parity], set, aux->ctrs, aux->live);
     BF_CHECK(cudaGetLastError());
-    if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], g_stream)); ++g_evUsed; }
-    return 0;
+    if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], sb)); ++g_evUsed; }
+    return stencil_end(aux);
 }
 
 BF_API int bfTsdfGarbageCollect(BFHashDataStruct* hd, const BFHashParams* hp) {
     TsdfAux* aux;
     int rc = get_aux(hd, hp, &aux, true);
     if (rc) return rc;
+    rc = join_lanes(aux); if (rc) return rc;          // GC edits the hash, the heap and the slot table: no stencil may be in flight
     ++g_launchCount;
     if (aux->liveValid) gc_live_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 2), 256, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs, aux->live, aux->lastListDual ? aux->listFlags : nullptr);
     else                gc_fused_kernel<<<grid_for(hp->m_numSDFBlocks, 16), 128, 0, g_stream>>>(*hd, *hp, live_count_ptr(aux), aux->slotInfo, aux->ctrs);
@@ -1486,8 +1598,9 @@ BF_API int bfTsdfGetLastFrameStats(const BFHashDataStruct* hd, unsigned long lon
     BF_CHECK(cudaMemcpyAsync(c, aux->ctrs, sizeof(c), cudaMemcpyDeviceToHost, g_stream));
     BF_CHECK(cudaStreamSynchronize(g_stream));
     out[0] = c[CTR_E];
-    out[1] = c[CTR_CULLED];
-    out[2] = ((unsigned long long)c[CTR_U_HI] << 32) | c[CTR_U_LO];
+    const int set = set_of(aux->parity);
+    out[1] = c[set + SET_CULLED];
+    out[2] = ((unsigned long long)c[set + SET_U_HI] << 32) | c[set + SET_U_LO];
     out[3] = (unsigned long long)c[CTR_HEAP_FAIL] + c[CTR_DROPPED];
     return 0;
 }
@@ -1527,12 +1640,7 @@ BF_API int bfTsdfReleaseAux(const BFHashDataStruct* hd) {
     std::lock_guard<std::mutex> lk(g_auxMutex);
     auto it = g_aux.find(hd->d_hash);
     if (it == g_aux.end()) return 0;
-    cudaFree(it->second.slotInfo);
-    cudaFree(it->second.ctrs);
-    cudaFree(it->second.live);
-    cudaFree(it->second.listFlags);
-    cudaFree(it->second.work);
-    cudaFree(it->second.tiles);
+    free_aux(it->second);
     g_aux.erase(it);
     return 0;
 }
@@ -1562,7 +1670,7 @@ BF_API void allocCUDA(BFHashDataStruct* hd, const BFHashParams* hp, const BFDept
     BF_SAFE(get_aux(hd, &g_hashParams, &aux, true));
     BFDepthCameraParams cam = g_camParams;
     cam.m_imageWidth = cp->m_imageWidth; cam.m_imageHeight = cp->m_imageHeight;   // grid follows the argument (.cu:255)
-    BF_SAFE(do_alloc(hd, &g_hashParams, g_bound.d_depthData, &cam, aux, false));
+    BF_SAFE(do_alloc(hd, &g_hashParams, g_bound.d_depthData, &cam, aux, false, -1));
 }
 
 BF_API void fillDecisionArrayCUDA(BFHashDataStruct* hd, const BFHashParams* hp) {
@@ -1580,7 +1688,7 @@ BF_API unsigned int compactifyHashAllInOneCUDA(BFHashDataStruct* hd, const BFHas
     (void)hp;
     TsdfAux* aux;
     BF_SAFE(get_aux(hd, &g_hashParams, &aux, true));
-    BF_SAFE(do_compactify(hd, &g_hashParams, &g_camParams, aux, false, false));
+    BF_SAFE(do_compactify(hd, &g_hashParams, &g_camParams, aux, false, false, false));
     unsigned res = 0;
     BF_SAFE((int)cudaMemcpyAsync(&res, live_count_ptr(aux), sizeof(unsigned), cudaMemcpyDeviceToHost, g_stream));
     BF_SAFE((int)cudaStreamSynchronize(g_stream));
@@ -1591,7 +1699,7 @@ BF_API unsigned int compactifyHashAllInOneCUDA(BFHashDataStruct* hd, const BFHas
 static void integrate_stub(BFHashDataStruct* hd, const BFHashParams* hp, bool de) {
     TsdfAux* aux;
     BF_SAFE(get_aux(hd, &g_hashParams, &aux, true));
-    BF_SAFE(do_integrate(hd, &g_hashParams, &g_bound, &g_camParams, aux, de, nullptr, hp->m_numOccupiedBlocks));
+    BF_SAFE(do_integrate(hd, &g_hashParams, &g_bound, &g_camParams, aux, de, false, hp->m_numOccupiedBlocks));
 }
 BF_API void integrateDepthMapCUDA(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraData*, const BFDepthCameraParams*) { integrate_stub(hd, hp, false); }
 BF_API void deIntegrateDepthMapCUDA(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraData*, const BFDepthCameraParams*) { integrate_stub(hd, hp, true); }
