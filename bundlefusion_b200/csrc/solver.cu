@@ -163,6 +163,8 @@ struct SolverWs {
     float* segMom = nullptr;      // [2*maxCorr][20] per-segment diagonal moments + rhs
     float* diagBlk = nullptr;     // [N][36]
     float* partials = nullptr;    // [2][maxGrid]
+    float* p2 = nullptr;          // [2][N][3] second search-direction buffer (rot, trans): p ping-pongs so that the update of p
+                                  // can be fused into the next mat-vec (2 grid barriers per PCG iteration instead of 3)
     // dense depth / colour term (N <= BF_DENSE_MAX_IMAGES): pair weights, per-pair 90-sum records, assembled dense system
     float* pairW = nullptr;       // [Nd*Nd]
     float* pairOut = nullptr;     // [Nd*Nd][90]
@@ -181,7 +183,7 @@ static int get_ws(const BFSolverState* st, unsigned maxImages, unsigned maxCorr,
     if (it != g_ws.end()) {
         SolverWs& w = it->second;
         cudaFree(w.rowCount); cudaFree(w.rowStart); cudaFree(w.cursor); cudaFree(w.entries); cudaFree(w.segCount); cudaFree(w.segs);
-        cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.scal);
+        cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.p2); cudaFree(w.scal);
         cudaFree(w.pairW); cudaFree(w.pairOut); cudaFree(w.denseJtJ); cudaFree(w.denseJtr);
         g_ws.erase(it);
     }
@@ -199,6 +201,7 @@ static int get_ws(const BFSolverState* st, unsigned maxImages, unsigned maxCorr,
     BF_CHECK(cudaMalloc(&w.segMom, sizeof(float) * 20 * E));
     BF_CHECK(cudaMalloc(&w.diagBlk, sizeof(float) * 36 * maxImages));
     BF_CHECK(cudaMalloc(&w.partials, sizeof(float) * 2 * w.maxGrid));
+    BF_CHECK(cudaMalloc(&w.p2, sizeof(float) * 6 * maxImages));
     BF_CHECK(cudaMalloc(&w.scal, sizeof(unsigned) * SC_NUM));
     {
         const size_t Nd = BF_DENSE_MAX_IMAGES;
@@ -335,6 +338,7 @@ struct GnArgs {
     float* T; float* Tinv;
     const int* rowStart; const int* entries; const int* segCount; const Segment* segs;
     float* offBlk; float* segMom; float* diagBlk; float* partials; unsigned* scal;
+    float* p2Rot; float* p2Trans;
     float wSparse; unsigned nLin; int isLastGn; int maxGrid;
     const float* denseJtJ; const float* denseJtr; int useDense;       // dense term: assembled system (NULL / 0 when off)
 };
@@ -508,9 +512,17 @@ gn_iteration_kernel(const GnArgs a) {
     const unsigned warpsPerBlock = blockDim.x / 32, gwarp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nwarps = gridDim.x * warpsPerBlock;
     const unsigned lane = threadIdx.x & 31;
     unsigned pcgRun = 0;
+    // Two grid barriers per iteration.  The textbook third one (p <- z + beta p must be complete before the next mat-vec) is
+    // removed by never materialising p before it is needed: a reader forms p_k(o) = z(o) + beta p_{k-1}(o) on the fly from two
+    // vectors that ARE complete, and each row's owner stores its own p_k(v) into the other of two ping-pong buffers (nobody
+    // reads that buffer during this mat-vec).  The expression, and therefore every bit, is the one the stored update had.
+    float beta = 0.0f;
     for (unsigned lin = 0; lin < a.nLin; ++lin) {
         bool last = (lin == a.nLin - 1);
         ++pcgRun;
+        const bool fly = lin > 0;
+        float* const curR = (lin & 1) ? a.p2Rot : a.pRot;   float* const curT = (lin & 1) ? a.p2Trans : a.pTrans;    // p_k of the rows this thread owns
+        const float* const prvR = (lin & 1) ? a.pRot : a.p2Rot; const float* const prvT = (lin & 1) ? a.pTrans : a.p2Trans;    // p_{k-1}, complete
         // A: Ap = H p, partial p.Ap
         float pAp = 0.0f;
         for (unsigned v = 1 + gwarp; v < N; v += nwarps) {
@@ -519,13 +531,16 @@ gn_iteration_kernel(const GnArgs a) {
             for (int sI = lane; sI < ns; sI += 32) {
                 const unsigned o = (unsigned)a.segs[rs + sI].nbr;
                 if (o == 0) continue;                                   // variable 0 is fixed: its p is zero by construction
-                blk_mv(&a.offBlk[36 * (size_t)(rs + sI)], ld3(a.pRot, o), ld3(a.pTrans, o), y);
+                const V3 pr = fly ? ld3(a.zRot, o) + ld3(prvR, o) * beta : ld3(a.pRot, o);
+                const V3 pt = fly ? ld3(a.zTrans, o) + ld3(prvT, o) * beta : ld3(a.pTrans, o);
+                blk_mv(&a.offBlk[36 * (size_t)(rs + sI)], pr, pt, y);
             }
             if (denseOn) {      // dense J^T J p (applyJTJDenseDevice, SolverBundlingDenseUtil.h:371-411): lanes over column blocks
                 const unsigned dim = 6 * N;
                 for (unsigned o = 1 + lane; o < N; o += 32) {
                     const float* B = &a.denseJtJ[(size_t)(v * 6) * dim + o * 6];
-                    const V3 pt = ld3(a.pTrans, o), pr = ld3(a.pRot, o);
+                    const V3 pr = fly ? ld3(a.zRot, o) + ld3(prvR, o) * beta : ld3(a.pRot, o);
+                    const V3 pt = fly ? ld3(a.zTrans, o) + ld3(prvT, o) * beta : ld3(a.pTrans, o);
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
                         y[3 + r] += B[r * dim + 0] * pt.x + B[r * dim + 1] * pt.y + B[r * dim + 2] * pt.z + B[r * dim + 3] * pr.x + B[r * dim + 4] * pr.y + B[r * dim + 5] * pr.z;
@@ -536,7 +551,9 @@ gn_iteration_kernel(const GnArgs a) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) y[k] = warp_sum(y[k]);
             if (lane == 0) {
-                const V3 pr = ld3(a.pRot, v), pt = ld3(a.pTrans, v);
+                const V3 pr = fly ? ld3(a.zRot, v) + ld3(prvR, v) * beta : ld3(a.pRot, v);
+                const V3 pt = fly ? ld3(a.zTrans, v) + ld3(prvT, v) * beta : ld3(a.pTrans, v);
+                if (fly) { st3(curR, v, pr); st3(curT, v, pt); }
                 blk_mv(&a.diagBlk[36 * (size_t)v], pr, pt, y);
                 st3(a.ApRot, v, mk(y[0], y[1], y[2])); st3(a.ApTrans, v, mk(y[3], y[4], y[5]));
                 pAp += pr.x * y[0] + pr.y * y[1] + pr.z * y[2] + pt.x * y[3] + pt.y * y[4] + pt.z * y[5];
@@ -552,8 +569,8 @@ gn_iteration_kernel(const GnArgs a) {
         float zr = 0.0f;
         for (unsigned v = tid; v < N; v += nth) {
             if (v == 0) continue;
-            st3(a.deltaRot, v, ld3(a.deltaRot, v) + ld3(a.pRot, v) * alpha);
-            st3(a.deltaTrans, v, ld3(a.deltaTrans, v) + ld3(a.pTrans, v) * alpha);
+            st3(a.deltaRot, v, ld3(a.deltaRot, v) + ld3(curR, v) * alpha);
+            st3(a.deltaTrans, v, ld3(a.deltaTrans, v) + ld3(curT, v) * alpha);
             const V3 rR = ld3(a.rRot, v) - ld3(a.ApRot, v) * alpha, rT = ld3(a.rTrans, v) - ld3(a.ApTrans, v) * alpha;
             st3(a.rRot, v, rR); st3(a.rTrans, v, rT);
             const V3 zR = mulv(ld3(a.precRot, v), rR), zT = mulv(ld3(a.precTrans, v), rT);
@@ -565,14 +582,13 @@ gn_iteration_kernel(const GnArgs a) {
         grid.sync();
         const float rDotzNew = grid_sum_after_sync(a.partials + a.maxGrid, gridDim.x, sRed);
         if (fabsf(dotProduct) < 5e-7f) last = true;                     // ENABLE_EARLY_OUT (:1088-1093)
-        // C: new direction (+ Lie update on the last iteration, LieDerivUtil.h:301-307)
-        float beta = 0.0f;
+        // C: the new direction's coefficient; the direction itself is formed by the next mat-vec (+ Lie update on the last
+        //    iteration, LieDerivUtil.h:301-307)
+        beta = 0.0f;
         if (rDotzOld > BF_FLOAT_EPSILON) beta = rDotzNew / rDotzOld;
-        for (unsigned v = tid; v < N; v += nth) {
-            if (v == 0) continue;
-            st3(a.pRot, v, ld3(a.zRot, v) + ld3(a.pRot, v) * beta);
-            st3(a.pTrans, v, ld3(a.zTrans, v) + ld3(a.pTrans, v) * beta);
-            if (last) {
+        if (last) {
+            for (unsigned v = tid; v < N; v += nth) {
+                if (v == 0) continue;
                 float U[16], Cm[16], P[16];
                 pose_to_matrix(ld3(a.deltaRot, v), ld3(a.deltaTrans, v), U);
                 pose_to_matrix(ld3(a.xRot, v), ld3(a.xTrans, v), Cm);
@@ -584,7 +600,6 @@ gn_iteration_kernel(const GnArgs a) {
         }
         rDotzOld = rDotzNew;
         if (last) break;
-        grid.sync();                                                    // p is complete before the next mat-vec
     }
 
     // (4) GN convergence: max |delta| over valid variables (SolverBundling.cu:694-749, 1206)
@@ -1038,6 +1053,7 @@ static int run_gn(const BFSolverInput* in, const BFSolverState* st, const BFSolv
     a.T = st->d_xTransforms; a.Tinv = st->d_xTransformInverses;
     a.rowStart = ws->rowStart; a.entries = ws->entries; a.segCount = ws->segCount; a.segs = ws->segs;
     a.offBlk = ws->offBlk; a.segMom = ws->segMom; a.diagBlk = ws->diagBlk; a.partials = ws->partials; a.scal = ws->scal;
+    a.p2Rot = ws->p2; a.p2Trans = ws->p2 + 3 * (size_t)ws->maxImages;
     a.wSparse = in->weightsSparse[nIter]; a.nLin = par->nLinIterations; a.isLastGn = isLast ? 1 : 0; a.maxGrid = ws->maxGrid;
     const float wDepth = in->weightsDenseDepth ? in->weightsDenseDepth[nIter] : 0.0f, wColor = in->weightsDenseColor ? in->weightsDenseColor[nIter] : 0.0f;
     const bool dense = (wDepth > 0.0f || wColor > 0.0f) && in->d_cacheFrames != nullptr;
@@ -1178,7 +1194,7 @@ BF_API int bfSolverReleaseWorkspace(const BFSolverState* st) {
     if (it == g_ws.end()) return 0;
     SolverWs& w = it->second;
     cudaFree(w.rowCount); cudaFree(w.rowStart); cudaFree(w.cursor); cudaFree(w.entries); cudaFree(w.segCount); cudaFree(w.segs);
-    cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.scal);
+    cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.p2); cudaFree(w.scal);
         cudaFree(w.pairW); cudaFree(w.pairOut); cudaFree(w.denseJtJ); cudaFree(w.denseJtr);
     g_ws.erase(it);
     return 0;
