@@ -193,13 +193,30 @@ def run_ours(args):
 
     skip_ba = [args.no_ba]
 
+    # e2e leg: the incoming frame is handed over as HOST (pinned) buffers and copied to its device slot every step, on an upload
+    # stream, one frame ahead -- frame f+1 crosses PCIe while frame f is being fused (the slot it lands in was last read > 100
+    # steps ago), as a sensor thread's upload would (FL/CUDAImageManager.cpp:22-158 uploads on arrival).
+    up_stream = torch.cuda.Stream(device=dev)
+    up_done = {}
+
+    def upload_frame(f):
+        cur = f % B
+        with torch.cuda.stream(up_stream):
+            dlist[cur].copy_(h_depth[cur], non_blocking=True); clist[cur].copy_(h_color[cur], non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(up_stream)
+        up_done[f] = ev
+
     def step(f, e2e):
         cur = f % B
-        if e2e:   # host -> device of the incoming frame (pinned), the call a user makes hands HOST buffers
-            dlist[cur].copy_(h_depth[cur], non_blocking=True); clist[cur].copy_(h_color[cur], non_blocking=True)
+        if e2e:
+            if f not in up_done:
+                upload_frame(f)
+            torch.cuda.current_stream(dev).wait_event(up_done.pop(f))
         if world > 1:     # the sensor frame lives on rank 0: broadcast over NVLink, every rank integrates its own shard
             dist.broadcast(dlist[cur], 0); dist.broadcast(clist[cur], 0)
         scene.runPackedOps(packed_ops[f], packed_frames, cam)
+        if e2e and f + 1 < len(packed_ops):
+            upload_frame(f + 1)
         if f % WORKLOAD["chunk"] == WORKLOAD["chunk"] - 1 and not skip_ba[0]:
             ba(e2e)
         if e2e:
@@ -268,7 +285,7 @@ def run_ours(args):
         "config": dict(WORKLOAD, parallelism=("single GPU" if world == 1 else f"voxel hash sharded over {world} GPUs by block owner; frame broadcast (NCCL) per step; BA replicated"),
                        active_blocks=int(WORKLOAD["sdf_blocks"] - heap_free), in_frustum_blocks_last=int(stats["E"]), global_pcg_iters=int(sg["pcg"]), global_gn_iters=int(sg["gn"])),
         "e2e": {"value": round(K / (ms_e2e / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": int(bytes_out),
-                "note": "incoming frame copied from pinned host memory every step; re-integrated frames come from the device-resident frame store"},
+                "note": "incoming frame copied from pinned host memory every step on an upload stream, one frame ahead of the fusion; re-integrated frames come from the device-resident frame store"},
         "gpu_launches": int(launches), "roofline": roof, "clocks": summarize_clocks(clk_lines),
     }
     if args.no_ba:
