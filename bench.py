@@ -254,8 +254,10 @@ def run_ours(args):
     total_needed = Wm + 3 * K
     while len(packed_ops) < total_needed:
         packed_ops.append(scene.packOps(wl.step_ops(len(packed_ops), n_re)))
-    skip_ba[0] = True        # the stencil is timed alone (no bundling kernel sharing the SMs): the burst HBM peak is its roof
+    skip_ba[0] = True        # the stencil is timed alone (no bundling kernel, no front-lane kernel sharing the SMs): the burst HBM peak is its roof
+    prev_lanes = L.bfTsdfSetLanes(0)
     timed(K, Wm + 2 * K, False, True)
+    L.bfTsdfSetLanes(prev_lanes)
     skip_ba[0] = args.no_ba
     prof = (ctypes.c_ulonglong * 8)()
     capi.check(L.bfTsdfGetProfile(ctypes.byref(scene.m_hashData), prof), "bfTsdfGetProfile")
@@ -277,6 +279,12 @@ def run_ours(args):
             "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
             "traffic": None, "launches": n_launch, "avg_launch_us": round(ns / max(1, n_timed) / 1e3, 2),
             "algorithmic_bytes_per_launch": round(alg_bytes / max(1, n_launch)), "U_per_launch": round(U / max(1, n_launch)), "E_per_launch": round(E / max(1, n_launch))}
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this command (profiles/), per launch
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_stencil_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        roof["traffic"] = tj.get("dram_bytes_per_launch")
+        roof["traffic_note"] = tj.get("note")
     bytes_in = (W * H * 4 * 2)
     bytes_out = 4 + (6 * 4 * len(glo["init_rot"])) / WORKLOAD["chunk"]
     out = {

@@ -103,7 +103,7 @@ TSDF_SYMBOLS = [
     "garbageCollectIdentifyCUDA", "garbageCollectFreeCUDA",
     "bfSetStream", "bfGetStream", "bfGetLastErrorString", "bfTsdfAuxBytes", "bfTsdfReset", "bfTsdfIntegrateFrame",
     "bfTsdfGarbageCollect", "bfTsdfGetHeapFreeCount", "bfTsdfGetNumOccupiedBlocks", "bfTsdfGetLastFrameStats",
-    "bfTsdfReleaseAux", "bfTsdfReintegrateFrame", "bfGetLaunchCount", "bfTsdfSetProfiling", "bfTsdfGetProfile", "bfTsdfSetBlockCull",
+    "bfTsdfReleaseAux", "bfTsdfReintegrateFrame", "bfGetLaunchCount", "bfTsdfSetProfiling", "bfTsdfGetProfile", "bfTsdfSetBlockCull", "bfTsdfSetLanes",
 ]
 
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
@@ -216,6 +216,8 @@ def lib() -> C.CDLL:
     L.bfTsdfReset.argtypes = [P(BFHashDataStruct), P(BFHashParams)]
     L.bfTsdfSetBlockCull.argtypes = [C.c_int]
     L.bfTsdfSetBlockCull.restype = C.c_int
+    L.bfTsdfSetLanes.argtypes = [C.c_int]
+    L.bfTsdfSetLanes.restype = C.c_int
     L.bfTsdfIntegrateFrame.argtypes = [P(BFHashDataStruct), P(BFHashParams), P(BFDepthCameraData), P(BFDepthCameraParams), C.c_int]
     L.bfTsdfGarbageCollect.argtypes = [P(BFHashDataStruct), P(BFHashParams)]
     L.bfTsdfGetHeapFreeCount.argtypes = [P(BFHashDataStruct), P(C.c_uint)]

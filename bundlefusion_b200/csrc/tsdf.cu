@@ -1336,6 +1336,7 @@ static int ensure_tiles(TsdfAux* aux, const BFDepthCameraParams* cp) {
 // lengthens the compactify kernels' critical path by ~4.5 us per call while the blocks it can prove dead (mostly: looking at
 // depths beyond the integration distance) were cheap for the stencil anyway (their probes exit at the depth test).
 // bfTsdfSetBlockCull(1) or BF_TSDF_CULL=1 switches it on; results are identical either way (tests/test_tsdf_gpu.py).
+static int g_lanes = -1;             // two-lane op replay (bfTsdfRunOps), see "two lanes" below
 static int g_cull = -1;
 static bool cull_enabled() {
     if (g_cull < 0) { const char* e = getenv("BF_TSDF_CULL"); g_cull = (e && e[0] == '1') ? 1 : 0; }
@@ -1463,12 +1464,11 @@ static int do_integrate(BFHashDataStruct* hd, const BFHashParams* hp, const BFDe
 
 // bracket of a two-lane replay (used by bfTsdfRunOps, host_api.cu)
 int tsdf_lanes_begin(const BFHashDataStruct* hd, const BFHashParams* hp) {
-    static int enabled = -1;         // BF_TSDF_LANES=0: everything on the caller's stream (A/B measurements)
-    if (enabled < 0) {
-        const char* e = getenv("BF_TSDF_LANES"); enabled = (e && e[0] == '0') ? 0 : 1;
-        const char* v = getenv("BF_TSDF_INTEGRATE"); if (v && v[0] == 't') enabled = 0;      // the TMA variant walks d_hashCompactified, which the front lane rewrites
+    if (g_lanes < 0) {               // BF_TSDF_LANES=0 / bfTsdfSetLanes(0): everything on the caller's stream
+        const char* e = getenv("BF_TSDF_LANES"); g_lanes = (e && e[0] == '0') ? 0 : 1;
     }
-    if (!enabled) return 0;
+    const char* v = getenv("BF_TSDF_INTEGRATE");
+    if (!g_lanes || (v && v[0] == 't')) return 0;      // the TMA variant walks d_hashCompactified, which the front lane rewrites
     TsdfAux* aux;
     int rc = get_aux(hd, hp, &aux, true);
     if (rc) return rc;
@@ -1512,6 +1512,7 @@ BF_API size_t bfTsdfAuxBytes(const BFHashParams* hp) { return (3 * sizeof(int4) 
 
 BF_API int bfTsdfReset(BFHashDataStruct* hd, const BFHashParams* hp) { return do_reset(hd, hp); }
 
+BF_API int bfTsdfSetLanes(int enable) { const int prev = g_lanes; g_lanes = enable ? 1 : 0; return prev < 0 ? 1 : prev; }
 BF_API int bfTsdfSetBlockCull(int enable) { const int prev = cull_enabled() ? 1 : 0; g_cull = enable ? 1 : 0; return prev; }
 
 BF_API int bfTsdfIntegrateFrame(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraData* dd,

@@ -200,6 +200,10 @@ int bfTsdfReset(BFHashDataStruct* hashData, const BFHashParams* hashParams);
 /* Per-block depth-range cull of the stencil (default off, see tsdf.cu; results are identical either way -- the cull only skips blocks none
  * of whose voxels can pass the reference's truncation test, .cu:433-449).  Returns the previous setting. */
 int bfTsdfSetBlockCull(int enable);
+/* Two-lane replay inside bfTsdfRunOps (default on): the stencil of operation k runs on a library-owned stream while alloc +
+ * compactify of operation k+1 run on the caller's stream; the caller's stream is ordered after all of it on return.  Results are
+ * identical either way.  Returns the previous setting. */
+int bfTsdfSetLanes(int enable);
 
 /* One whole CUDASceneRepHashSDF::integrate (h:65-83) or ::deIntegrate (h:85-108):
  * [alloc] -> compactify -> (de)integrate, three launches, zero host syncs.
