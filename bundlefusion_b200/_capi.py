@@ -108,11 +108,22 @@ TSDF_SYMBOLS = [
 
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
 
+SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
+
 SOLVER_SYMBOLS = [
     "solveBundlingStub", "buildVariablesToCorrespondencesTableCUDA", "evalMaxResidual", "countHighResiduals", "collectHighResiduals",
     "convertLiePosesToMatricesCU", "convertMatricesToPosesCU", "convertPosesToMatricesCU",
     "bfSolverSolve", "bfSolverGetStats", "bfSolverMaxResidual", "bfSolverWorkspaceBytes", "bfSolverReleaseWorkspace",
 ]
+
+
+class BFImagePairMatch(C.Structure):      # FL/SiftGPU/SIFTImageManager.h:38-42
+    _fields_ = [("d_numMatches", C.c_void_p), ("d_distances", C.c_void_p), ("d_keyPointIndices", C.c_void_p)]
+
+
+class BFSiftMatchJob(C.Structure):
+    _fields_ = [("d_des1", C.c_void_p), ("num1", C.c_int32), ("d_des2", C.c_void_p), ("num2", C.c_int32),
+                ("out", BFImagePairMatch), ("keyPointOffset", C.c_uint32 * 2)]
 
 
 class BFEntryJ(C.Structure):
@@ -254,6 +265,9 @@ def lib() -> C.CDLL:
     L.bfSolverWorkspaceBytes.argtypes = [C.c_uint, C.c_uint]
     L.bfSolverWorkspaceBytes.restype = C.c_size_t
     L.bfSolverReleaseWorkspace.argtypes = [P(BFSolverState)]
+    # SIFT descriptor matcher
+    L.bfSiftMatchBatch.argtypes = [P(BFSiftMatchJob), C.c_int, C.c_float, C.c_float]
+    L.bfSiftWorkspaceBytes.restype = C.c_size_t
     _lib = L
     return L
 

@@ -1,0 +1,230 @@
+// sift_match.cu -- SIFT descriptor matching for sm_100a.  Implements include/bf_sift.h (row a18 of SURVEY.md section 8).
+//
+// Behavioural source (what, not how): FL/SiftGPU/ProgramCU.cu:1634-1938 (MultiplyDescriptor / RowMatch / ColMatch kernels),
+// FL/SiftGPU/SiftMatch.cpp:160-196, FL/Bundler.cpp:116-137.
+//
+// B200-first design:
+//  * the n1 x n2 dot-product matrix is NEVER written to memory.  The reference writes it (4 MB per pair at 1024 keys), re-reads it
+//    in RowMatch, and keeps a second (n1/4) x n2 int4 array for the column pass; here each CTA sweeps the u8 x u8 -> s32 tensor-core
+//    products (mma.sync m16n8k32, exact) of 64 features against ALL features of the other image and keeps, per feature, the two
+//    largest (value, index) in registers;
+//  * the column direction is the same kernel with the two images swapped (the contraction is ~2 % of the kernel's instructions, the
+//    best / second bookkeeping is the cost) and the reference's column tie-break, followed in the same CTA by the distance / ratio
+//    tests, the mutual-best check against the row pass, and the append;
+//  * all pairs of a frame are ONE batch: two launches in total instead of (2 copies + 3 launches + 1 memset) per pair.
+// Round 1 uses the warp-level mma.sync path; the tcgen05 / TMEM version of the contraction is round-2 work.
+#include <mutex>
+#include <vector>
+
+#include "../../include/bf_sift.h"
+#include "bf_common.cuh"
+
+namespace bf {
+
+extern unsigned long long g_launchCount;
+
+struct SiftJobDev {
+    const uint8_t* desA; int nA;       // the features this pass owns ("rows" of the pass)
+    const uint8_t* desB; int nB;       // the features they are compared with
+    int* rowResult; float* rowDist;    // row pass: outputs; column pass: inputs (indexed by image-1 feature)
+    int* numMatches; float* outDist; uint2* outIdx;
+    uint2 offset;
+};
+
+// Winner among equal maxima, exactly as the reference's 32 strided lanes + fold-upper-half-into-lower tree pick it (see
+// oracle/sift_oracle.c): smallest (bit-reversed lane, position), lane = col % 32 for rows and (row / 4) % 32 for columns.
+template <bool kColumnPass>
+__device__ __forceinline__ unsigned tie_key(unsigned idx) {
+    const unsigned lane = kColumnPass ? ((idx >> 2) & 31u) : (idx & 31u);
+    return ((__brev(lane) >> 27) << 24) | idx;
+}
+// (value, index) packed so that a plain unsigned 64-bit maximum is "larger value, then smaller key"
+template <bool kColumnPass>
+__device__ __forceinline__ unsigned long long pack(int v, unsigned idx) {
+    return ((unsigned long long)(unsigned)v << 32) | (unsigned long long)(0xFFFFFFFFu - tie_key<kColumnPass>(idx));
+}
+__device__ __forceinline__ void top2_insert(unsigned long long& b1, unsigned long long& b2, unsigned long long p) {
+    if (p > b1) { b2 = b1; b1 = p; } else if (p > b2) b2 = p;
+}
+__device__ __forceinline__ float dist_of(int dot) { return acosf(fminf((float)dot * 0.000003814697265625f, 1.0f)); }
+
+#define SM_BM 64              // features of A per CTA (4 warps x 16)
+#define SM_BN 64              // features of B per sweep step
+#define SM_PITCH 144          // bytes per staged descriptor row: 128 + 16 -> the 8 rows a fragment load touches hit 32 distinct banks
+
+__device__ __forceinline__ void mma_u8(int (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// grid = (ceil(maxNA / 64), numJobs), 128 threads
+template <bool kColumnPass>
+__global__ void __launch_bounds__(128)
+sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratiomax) {
+    const SiftJobDev job = jobs[blockIdx.y];
+    const int nA = job.nA, nB = job.nB;
+    const int row0 = blockIdx.x * SM_BM;
+    if (!kColumnPass && blockIdx.x == 0 && threadIdx.x == 0) *job.numMatches = 0;       // SiftMatch.cpp:163 / ProgramCU.cu:1928
+    if (nA <= 0 || nB <= 0 || row0 >= nA) return;
+
+    __shared__ __align__(16) unsigned char sB[SM_BN * SM_PITCH];
+    const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, q = lane & 3;
+
+    // A fragments of this warp's 16 features, all of K = 128 (4 k-steps), kept in registers for the whole sweep
+    unsigned a[4][4];
+    {
+        const int r0 = row0 + (int)warp * 16 + (int)g, r1 = r0 + 8;
+        const unsigned* p0 = reinterpret_cast<const unsigned*>(job.desA + (size_t)(r0 < nA ? r0 : 0) * 128);
+        const unsigned* p1 = reinterpret_cast<const unsigned*>(job.desA + (size_t)(r1 < nA ? r1 : 0) * 128);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            a[ks][0] = (r0 < nA) ? __ldg(p0 + ks * 8 + q) : 0u;
+            a[ks][1] = (r1 < nA) ? __ldg(p1 + ks * 8 + q) : 0u;
+            a[ks][2] = (r0 < nA) ? __ldg(p0 + ks * 8 + 4 + q) : 0u;
+            a[ks][3] = (r1 < nA) ? __ldg(p1 + ks * 8 + 4 + q) : 0u;
+        }
+    }
+    // two largest packed (value, key) of this thread's two features (rows g and g + 8 of the warp tile); 0 = none: a dot product must
+    // be > 0 to be a candidate (the reference starts from max = 0 with a strict '>')
+    unsigned long long b1[2] = { 0ull, 0ull }, b2[2] = { 0ull, 0ull };
+
+    for (int col0 = 0; col0 < nB; col0 += SM_BN) {
+        __syncthreads();                                   // the previous step's fragment loads are done
+        // stage 64 descriptors of B: 64 x 128 B = 512 uint4, 4 per thread, coalesced
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned v = t + 128u * k;               // 0..511
+            const unsigned r = v >> 3, c16 = v & 7u;
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            if (col0 + (int)r < nB) val = __ldg(reinterpret_cast<const uint4*>(job.desB + (size_t)(col0 + r) * 128) + c16);
+            *reinterpret_cast<uint4*>(&sB[r * SM_PITCH + c16 * 16]) = val;
+        }
+        __syncthreads();
+        int acc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const unsigned char* bp = &sB[(nt * 8 + g) * SM_PITCH + ks * 32 + q * 4];
+                const unsigned bb0 = *reinterpret_cast<const unsigned*>(bp), bb1 = *reinterpret_cast<const unsigned*>(bp + 16);
+                mma_u8(acc[nt], a[ks], bb0, bb1);
+            }
+        }
+        // bookkeeping: acc[nt][0..1] belong to feature g, acc[nt][2..3] to feature g + 8; columns col0 + nt*8 + 2q + {0,1}
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = col0 + nt * 8 + 2 * (int)q;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (c + e < nB) {
+                    if (acc[nt][e] > 0) top2_insert(b1[0], b2[0], pack<kColumnPass>(acc[nt][e], (unsigned)(c + e)));
+                    if (acc[nt][2 + e] > 0) top2_insert(b1[1], b2[1], pack<kColumnPass>(acc[nt][2 + e], (unsigned)(c + e)));
+                }
+            }
+        }
+    }
+    // merge the four lanes (q = 0..3) that share a feature
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, b1[h], o), o2 = __shfl_xor_sync(0xffffffffu, b2[h], o);
+            top2_insert(b1[h], b2[h], o1);
+            top2_insert(b1[h], b2[h], o2);
+        }
+    }
+    if (q == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = row0 + (int)warp * 16 + (int)g + 8 * h;
+            if (r >= nA) continue;
+            const int vmax = (int)(b1[h] >> 32), vnxt = (int)(b2[h] >> 32);
+            const int idx = b1[h] ? (int)((0xFFFFFFFFu - (unsigned)(b1[h] & 0xFFFFFFFFull)) & 0x00FFFFFFu) : -1;
+            const float dist = dist_of(vmax), distn = dist_of(vnxt);
+            const int res = (dist < distmax && dist < distn * ratiomax) ? idx : -1;
+            if (!kColumnPass) {
+                job.rowResult[r] = res;                    // RowMatch_Kernel, ProgramCU.cu:1823-1829
+                job.rowDist[r] = dist;
+            } else if (res >= 0 && job.rowResult[res] == r) {            // ColMatch_Kernel, :1900-1915 (here A = image 2, r = its feature)
+                const int addr = atomicAdd(job.numMatches, 1);           // keeps counting past the cap, as the reference's
+                if (addr < BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW) {
+                    job.outIdx[addr] = make_uint2((unsigned)res + job.offset.x, (unsigned)r + job.offset.y);
+                    job.outDist[addr] = job.rowDist[res];
+                }
+            }
+        }
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+struct SiftWs {
+    SiftJobDev* dJobs = nullptr; size_t jobCap = 0;
+    int* rowResult = nullptr; float* rowDist = nullptr; size_t rowCap = 0;
+};
+static SiftWs g_sift;
+static std::mutex g_siftMutex;
+
+}  // namespace bf
+
+using namespace bf;
+
+BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distmax, float ratiomax) {
+    if (numJobs <= 0) return 0;
+    std::lock_guard<std::mutex> lk(g_siftMutex);
+    size_t rows = 0;
+    int maxN1 = 0, maxN2 = 0;
+    for (int i = 0; i < numJobs; ++i) {
+        if (jobs[i].num1 > 0 && jobs[i].num2 > 0) { rows += (size_t)jobs[i].num1; maxN1 = jobs[i].num1 > maxN1 ? jobs[i].num1 : maxN1; maxN2 = jobs[i].num2 > maxN2 ? jobs[i].num2 : maxN2; }
+        if (jobs[i].num1 >= (1 << 24) || jobs[i].num2 >= (1 << 24)) return (int)cudaErrorInvalidValue;       // index field of the packed key
+    }
+    cudaStream_t s = stream();
+    if ((size_t)numJobs > g_sift.jobCap) {
+        if (g_sift.dJobs) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dJobs)); }
+        g_sift.jobCap = (size_t)numJobs * 2;
+        BF_CHECK(cudaMalloc(&g_sift.dJobs, sizeof(SiftJobDev) * 2 * g_sift.jobCap));      // [row-pass jobs | column-pass jobs]
+    }
+    if (rows > g_sift.rowCap) {
+        if (g_sift.rowResult) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.rowResult)); BF_CHECK(cudaFree(g_sift.rowDist)); }
+        g_sift.rowCap = rows * 2;
+        BF_CHECK(cudaMalloc(&g_sift.rowResult, sizeof(int) * g_sift.rowCap));
+        BF_CHECK(cudaMalloc(&g_sift.rowDist, sizeof(float) * g_sift.rowCap));
+    }
+    std::vector<SiftJobDev> h(2 * (size_t)numJobs);
+    size_t off = 0;
+    for (int i = 0; i < numJobs; ++i) {
+        const BFSiftMatchJob& j = jobs[i];
+        const bool live = j.num1 > 0 && j.num2 > 0;
+        SiftJobDev r;
+        r.desA = j.d_des1; r.nA = live ? j.num1 : 0; r.desB = j.d_des2; r.nB = live ? j.num2 : 0;
+        r.rowResult = g_sift.rowResult + off; r.rowDist = g_sift.rowDist + off;
+        r.numMatches = j.out.d_numMatches; r.outDist = j.out.d_distances; r.outIdx = reinterpret_cast<uint2*>(j.out.d_keyPointIndices);
+        r.offset = make_uint2(j.keyPointOffset[0], j.keyPointOffset[1]);
+        SiftJobDev c = r;                                   // column pass: image 2 owns the sweep, image 1 is swept
+        c.desA = j.d_des2; c.nA = r.nB; c.desB = j.d_des1; c.nB = r.nA;
+        h[i] = r; h[(size_t)numJobs + i] = c;
+        if (live) off += (size_t)j.num1;
+    }
+    BF_CHECK(cudaMemcpyAsync(g_sift.dJobs, h.data(), sizeof(SiftJobDev) * h.size(), cudaMemcpyHostToDevice, s));
+    BF_CHECK(cudaStreamSynchronize(s));                     // h is a stack-lifetime staging buffer (pageable): the copy must have left it
+    const int gx1 = maxN1 > 0 ? (maxN1 + SM_BM - 1) / SM_BM : 1, gx2 = maxN2 > 0 ? (maxN2 + SM_BM - 1) / SM_BM : 1;
+    g_launchCount += 2;
+    sift_best_kernel<false><<<dim3(gx1, numJobs), 128, 0, s>>>(g_sift.dJobs, distmax, ratiomax);
+    BF_CHECK(cudaGetLastError());
+    sift_best_kernel<true><<<dim3(gx2, numJobs), 128, 0, s>>>(g_sift.dJobs + numJobs, distmax, ratiomax);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
+
+BF_API size_t bfSiftWorkspaceBytes(void) {
+    std::lock_guard<std::mutex> lk(g_siftMutex);
+    return sizeof(SiftJobDev) * 2 * g_sift.jobCap + (sizeof(int) + sizeof(float)) * g_sift.rowCap;
+}
+BF_API int bfSiftReleaseWorkspace(void) {
+    std::lock_guard<std::mutex> lk(g_siftMutex);
+    cudaFree(g_sift.dJobs); cudaFree(g_sift.rowResult); cudaFree(g_sift.rowDist);
+    g_sift = SiftWs();
+    return 0;
+}

@@ -300,3 +300,36 @@ def make_dense_ba_problem(n_images: int = 11, stride: int = 3, start: int = 100,
         T = gt[n] if n == 0 else se3_exp(rng.standard_normal(3) * perturb_rot, rng.standard_normal(3) * perturb_trans) @ gt[n]
         rot[n], trans[n] = se3_log(T)
     return {"corr": corr, "gt": gt, "init_rot": rot, "init_trans": trans, "caches": caches, "pairs": pairs, "intrinsics": cache_intrinsics(W, H)}
+
+
+# ---- synthetic SIFT descriptors (row a18) ------------------------------------------------------------------------------
+def quantize_descriptors(v: np.ndarray) -> np.ndarray:
+    """SiftGPU's unsigned-char descriptor convention: non-negative, L2-normalised to 512, rounded, clipped to 255."""
+    v = np.maximum(np.asarray(v, np.float64), 0.0)
+    n = np.linalg.norm(v, axis=1, keepdims=True)
+    n[n == 0] = 1.0
+    return np.clip(np.floor(v / n * 512.0 + 0.5), 0, 255).astype(np.uint8)
+
+
+def make_sift_descriptors(n: int, seed: int = 0) -> np.ndarray:
+    """n gradient-histogram-like descriptors [n,128] uint8 (sparse exponential bins, the usual 0.2 clamp before renormalising)."""
+    rng = np.random.default_rng(seed)
+    v = rng.exponential(1.0, (n, 128)) * (rng.random((n, 128)) < 0.6)
+    v /= np.maximum(np.linalg.norm(v, axis=1, keepdims=True), 1e-12)
+    v = np.minimum(v, 0.2)
+    return quantize_descriptors(v)
+
+
+def make_sift_pair(n1: int, n2: int, n_common: int, noise: float = 0.05, seed: int = 0):
+    """Two descriptor sets sharing n_common features (re-observed with noise, in shuffled order).
+    Returns (des1 [n1,128] u8, des2 [n2,128] u8, truth [n_common,2] = (index in 1, index in 2))."""
+    rng = np.random.default_rng(seed + 7919)
+    n_common = min(n_common, n1, n2)
+    d1 = make_sift_descriptors(n1, seed)
+    base = d1[:n_common].astype(np.float64)
+    obs = quantize_descriptors(base + rng.normal(0.0, noise * 512.0 / np.sqrt(128.0), base.shape))
+    d2 = np.concatenate([obs, make_sift_descriptors(n2 - n_common, seed + 1)]) if n2 > n_common else obs
+    p1, p2 = rng.permutation(n1), rng.permutation(n2)
+    inv1, inv2 = np.argsort(p1), np.argsort(p2)
+    truth = np.stack([inv1[:n_common], inv2[:n_common]], 1)
+    return np.ascontiguousarray(d1[p1]), np.ascontiguousarray(d2[p2]), truth

@@ -1,0 +1,57 @@
+/*
+ * bf_sift.h -- C-ABI of the SIFT descriptor matcher.
+ *
+ * The reference exposes this path as a C++ class, not as extern "C" stubs:
+ *   SiftMatchGPU::SetDescriptors(int index, int num, unsigned char* d_descriptors)     FL/SiftGPU/SiftMatch.cpp:110-131
+ *   SiftMatchGPU::GetSiftMatch(int max_match, ImagePairMatch&, uint2 keyPointOffset,
+ *                              float distmax, float ratiomax, int mutual_best_match)   FL/SiftGPU/SiftMatch.cpp:160-196
+ *   -> ProgramCU::MultiplyDescriptor / GetRowMatch / GetColMatch                        FL/SiftGPU/ProgramCU.cu:1734-1938
+ * and calls it once per image pair from Bundler::matchAndFilter (FL/Bundler.cpp:116-137): 2 descriptor copies + 3 launches + a
+ * memset per pair, serialised.  (FL/ = /root/reference/FriedLiver/Source/.)
+ *
+ * This header is the boundary a maintainer binds instead: plain pointers and sizes, one call for ALL pairs of a frame.
+ * Descriptors are 128 unsigned bytes per feature, normalised to length 512 (SiftGPU convention), feature-major.
+ * Semantics per pair are exactly GetSiftMatch with mutual_best_match = 1 (the only mode the reference's GetBestMatch implements):
+ * mutual best matches with dist = acos(dot / 2^18) < distmax and dist < ratiomax * dist_second, including which feature wins a tie;
+ * the ORDER in which matches are appended is race-dependent in the reference (atomicAdd) and here -- consumers sort by
+ * distance next (SIFTImageManager::SortKeyPointMatchesCU).  Dot products are exact int32.
+ */
+#ifndef BF_SIFT_H
+#define BF_SIFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW 128     /* FL/GlobalDefines.h:8 */
+
+/* FL/SiftGPU/SIFTImageManager.h:38-42 */
+typedef struct BFImagePairMatch {
+    int32_t*  d_numMatches;        /* one counter (keeps counting past the cap, as the reference's) */
+    float*    d_distances;         /* [BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW] */
+    uint32_t* d_keyPointIndices;   /* uint2 [BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW]: (feature of image 1 + offset.x, feature of image 2 + offset.y) */
+} BFImagePairMatch;
+
+/* one image pair: what SetDescriptors(0, ..) + SetDescriptors(1, ..) + GetSiftMatch(..) take */
+typedef struct BFSiftMatchJob {
+    const uint8_t* d_des1; int32_t num1;        /* image 1 ("prev" in Bundler::matchAndFilter) */
+    const uint8_t* d_des2; int32_t num2;        /* image 2 (the current frame) */
+    BFImagePairMatch out;
+    uint32_t keyPointOffset[2];
+} BFSiftMatchJob;
+
+/* Matches numJobs image pairs (jobs: HOST array) in two launches, asynchronously on the library stream (bfSetStream).
+ * A job with num1 <= 0 or num2 <= 0 only zeroes its counter (SiftMatch.cpp:162-165).  Returns 0 or a cudaError_t. */
+int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distmax, float ratiomax);
+
+/* device scratch the matcher holds (rowResult / rowDist per job); released by bfSiftReleaseWorkspace */
+size_t bfSiftWorkspaceBytes(void);
+int bfSiftReleaseWorkspace(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BF_SIFT_H */

@@ -316,3 +316,38 @@ def build_dense(rot, trans, caches, intrinsics, w_depth, w_color, valid=None, pa
     L.orc_solver_build_dense(np.ascontiguousarray(rot, np.float32), np.ascontiguousarray(trans, np.float32), N, C.cast(frames, C.c_void_p),
                              C.cast(C.pointer(dp), C.c_void_p), v.ctypes.data if v is not None else None, w_depth, w_color, JtJ, Jtr, pairs)
     return JtJ.reshape(6 * N, 6 * N), Jtr, (pairs[0], pairs[1])
+
+
+# ---- SIFT descriptor matcher (oracle/sift_oracle.c) ----------------------------------------------------------------------
+def sift_multiply(d1: np.ndarray, d2: np.ndarray) -> np.ndarray:
+    L = lib()
+    d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+    dot = np.zeros((len(d1), len(d2)), np.int32)
+    L.orc_sift_multiply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_sift_multiply.restype = None
+    L.orc_sift_multiply(d1.ctypes.data, len(d1), d2.ctypes.data, len(d2), dot.ctypes.data)
+    return dot
+
+
+def sift_match(d1: np.ndarray, d2: np.ndarray, distmax: float = 0.7, ratiomax: float = 0.8, offset=(0, 0), fast: bool = False):
+    """SiftMatchGPU::GetSiftMatch for one pair.  Returns (indices [n,2] uint32, distances [n] float32, counter)."""
+    L = lib(fast)
+    d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+    idx = np.zeros((128, 2), np.uint32); dist = np.zeros(128, np.float32)
+    L.orc_sift_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.orc_sift_match.restype = C.c_int
+    c = L.orc_sift_match(d1.ctypes.data, len(d1), d2.ctypes.data, len(d2), distmax, ratiomax, offset[0], offset[1], idx.ctypes.data, dist.ctypes.data)
+    n = min(c, 128)
+    return idx[:n].copy(), dist[:n].copy(), c
+
+
+def sift_row_match(dot: np.ndarray, distmax: float = 0.7, ratiomax: float = 0.8):
+    """RowMatch_Kernel on a given dot matrix: (best column or -1 per row, distance per row)."""
+    L = lib()
+    dot = np.ascontiguousarray(dot, np.int32)
+    n1, n2 = dot.shape
+    res = np.zeros(n1, np.int32); dist = np.zeros(n1, np.float32)
+    L.orc_sift_row_match.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.orc_sift_row_match.restype = None
+    L.orc_sift_row_match(dot.ctypes.data, n1, n2, distmax, ratiomax, res.ctypes.data, dist.ctypes.data)
+    return res, dist

@@ -49,6 +49,12 @@ def test_symbol_list_matches_header():
     assert sorted(set(_declared_symbols("bf_tsdf.h"))) == sorted(set(capi.TSDF_SYMBOLS))
     assert sorted(set(_declared_symbols("bf_host.h"))) == sorted(set(capi.HOST_SYMBOLS))
     assert sorted(set(_declared_symbols("bf_solver.h"))) == sorted(set(capi.SOLVER_SYMBOLS))
+    assert sorted(set(_declared_symbols("bf_sift.h"))) == sorted(set(capi.SIFT_SYMBOLS))
+
+
+def test_sift_pod_layouts():
+    assert C.sizeof(capi.BFImagePairMatch) == 24                      # three device pointers, SIFTImageManager.h:38-42
+    assert C.sizeof(capi.BFSiftMatchJob) == 64 and capi.BFSiftMatchJob.out.offset == 32 and capi.BFSiftMatchJob.keyPointOffset.offset == 56
 
 
 def test_solver_pod_layouts():
