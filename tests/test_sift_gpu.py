@@ -73,10 +73,8 @@ def test_batch_of_pairs_is_one_call(cuda_device):
     prevs, jobs, ipms = [], [], []
     for k, n in enumerate([1024, 0, 512, 333, 64]):
         if n:
-            _, dk, _ = synth.make_sift_pair(900, n, min(n, 150), seed=30 + k)
-            # make_sift_pair's first set differs per seed: re-observe `cur` instead
             rng = np.random.default_rng(100 + k)
-            sel = rng.permutation(900)[:min(n, 150)]
+            sel = rng.permutation(900)[:min(n, 100)]          # stay under the 128-match cap: above it the stored subset is race-dependent
             obs = synth.quantize_descriptors(cur[sel].astype(np.float64) + rng.normal(0, 0.05 * 512 / np.sqrt(128), (len(sel), 128)))
             dk = np.concatenate([obs, synth.make_sift_descriptors(n - len(sel), seed=40 + k)]) if n > len(sel) else obs
         else:
