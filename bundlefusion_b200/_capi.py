@@ -108,6 +108,8 @@ TSDF_SYMBOLS = [
 
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
 
+CACHE_SYMBOLS = ["bfCacheStoreFrame"]
+
 SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
 
 SOLVER_SYMBOLS = [
@@ -138,6 +140,12 @@ class BFCUDACachedFrame(C.Structure):
 class _F4(C.Structure):
     _pack_ = 16
     _fields_ = [("v", C.c_float * 4)]
+
+
+class BFCacheParams(C.Structure):          # what CUDACache's constructor latches, FL/CUDACache.cpp:14-40
+    _fields_ = [("inputDepthWidth", C.c_uint32), ("inputDepthHeight", C.c_uint32), ("inputColorWidth", C.c_uint32), ("inputColorHeight", C.c_uint32),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("inputIntrinsicsInv", C.c_float * 16),
+                ("filterIntensitySigma", C.c_float), ("filterDepthSigmaD", C.c_float), ("filterDepthSigmaR", C.c_float)]
 
 
 class BFSolverInput(C.Structure):
@@ -265,6 +273,7 @@ def lib() -> C.CDLL:
     L.bfSolverWorkspaceBytes.argtypes = [C.c_uint, C.c_uint]
     L.bfSolverWorkspaceBytes.restype = C.c_size_t
     L.bfSolverReleaseWorkspace.argtypes = [P(BFSolverState)]
+    L.bfCacheStoreFrame.argtypes = [P(BFCacheParams), vp, vp, P(BFCUDACachedFrame)]
     # SIFT descriptor matcher
     L.bfSiftMatchBatch.argtypes = [P(BFSiftMatchJob), C.c_int, C.c_float, C.c_float]
     L.bfSiftWorkspaceBytes.restype = C.c_size_t

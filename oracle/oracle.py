@@ -351,3 +351,29 @@ def sift_row_match(dot: np.ndarray, distmax: float = 0.7, ratiomax: float = 0.8)
     L.orc_sift_row_match.restype = None
     L.orc_sift_row_match(dot.ctypes.data, n1, n2, distmax, ratiomax, res.ctypes.data, dist.ctypes.data)
     return res, dist
+
+
+# ---- dense cache frame (oracle/cache_oracle.c) ----------------------------------------------------------------------------
+def cache_store_frame(depth: np.ndarray, color: np.ndarray, K, cw: int = 80, ch: int = 60, colorDownSigma: float = 2.5,
+                      depthDownSigmaD: float = 1.0, depthDownSigmaR: float = 0.05) -> dict:
+    """CUDACache::storeFrame for one frame; K = 4x4 input intrinsics.  Returns host arrays keyed like synth.make_cache_frame."""
+    from bundlefusion_b200._capi import BFCacheParams
+    from bundlefusion_b200.cache import intrinsics_inverse
+    L = lib()
+    depth = np.ascontiguousarray(depth, np.float32); color = np.ascontiguousarray(color, np.uint8)
+    p = BFCacheParams()
+    p.inputDepthHeight, p.inputDepthWidth = depth.shape
+    p.inputColorHeight, p.inputColorWidth = color.shape[:2]
+    p.width, p.height = cw, ch
+    Ki = intrinsics_inverse(K)
+    for k in range(16):
+        p.inputIntrinsicsInv[k] = float(Ki.reshape(-1)[k])
+    p.filterIntensitySigma, p.filterDepthSigmaD, p.filterDepthSigmaR = colorDownSigma, depthDownSigmaD, depthDownSigmaR
+    out = {"depth": np.full((ch, cw), -np.inf, np.float32), "campos": np.full((ch, cw, 4), -np.inf, np.float32),
+           "normals": np.full((ch, cw, 4), -np.inf, np.float32), "normalsU": np.zeros((ch, cw, 4), np.uint8),
+           "intensity": np.zeros((ch, cw), np.float32), "intensityDerivs": np.full((ch, cw, 2), -np.inf, np.float32)}
+    L.orc_cache_store_frame.argtypes = [C.c_void_p] * 9
+    L.orc_cache_store_frame.restype = None
+    L.orc_cache_store_frame(C.addressof(p), depth.ctypes.data, color.ctypes.data, out["depth"].ctypes.data, out["campos"].ctypes.data,
+                            out["normals"].ctypes.data, out["normalsU"].ctypes.data, out["intensity"].ctypes.data, out["intensityDerivs"].ctypes.data)
+    return out
