@@ -109,6 +109,7 @@ TSDF_SYMBOLS = [
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
 
 CACHE_SYMBOLS = ["bfCacheStoreFrame"]
+INGEST_SYMBOLS = ["bfIngestFrame"]
 
 SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
 
@@ -140,6 +141,12 @@ class BFCUDACachedFrame(C.Structure):
 class _F4(C.Structure):
     _pack_ = 16
     _fields_ = [("v", C.c_float * 4)]
+
+
+class BFIngestParams(C.Structure):         # FL/CUDAImageManager.cpp:88-137 settings
+    _fields_ = [("depthWidth", C.c_uint32), ("depthHeight", C.c_uint32), ("colorWidth", C.c_uint32), ("colorHeight", C.c_uint32),
+                ("widthIntegration", C.c_uint32), ("heightIntegration", C.c_uint32), ("erodeIterations", C.c_int32), ("erodeStructureSize", C.c_int32),
+                ("erodeDThresh", C.c_float), ("erodeFracReq", C.c_float), ("depthSigmaD", C.c_float), ("depthSigmaR", C.c_float)]
 
 
 class BFCacheParams(C.Structure):          # what CUDACache's constructor latches, FL/CUDACache.cpp:14-40
@@ -274,6 +281,7 @@ def lib() -> C.CDLL:
     L.bfSolverWorkspaceBytes.restype = C.c_size_t
     L.bfSolverReleaseWorkspace.argtypes = [P(BFSolverState)]
     L.bfCacheStoreFrame.argtypes = [P(BFCacheParams), vp, vp, P(BFCUDACachedFrame)]
+    L.bfIngestFrame.argtypes = [P(BFIngestParams), vp, vp, vp, vp]
     # SIFT descriptor matcher
     L.bfSiftMatchBatch.argtypes = [P(BFSiftMatchJob), C.c_int, C.c_float, C.c_float]
     L.bfSiftWorkspaceBytes.restype = C.c_size_t

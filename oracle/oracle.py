@@ -377,3 +377,27 @@ def cache_store_frame(depth: np.ndarray, color: np.ndarray, K, cw: int = 80, ch:
     L.orc_cache_store_frame(C.addressof(p), depth.ctypes.data, color.ctypes.data, out["depth"].ctypes.data, out["campos"].ctypes.data,
                             out["normals"].ctypes.data, out["normalsU"].ctypes.data, out["intensity"].ctypes.data, out["intensityDerivs"].ctypes.data)
     return out
+
+
+# ---- frame ingest (oracle/ingest_oracle.c) ---------------------------------------------------------------------------------
+def ingest_params(depth_shape, color_shape, wi, hi, erode=True, depth_filter=True, sigmaD=2.0, sigmaR=0.05):
+    from bundlefusion_b200._capi import BFIngestParams
+    p = BFIngestParams()
+    p.depthHeight, p.depthWidth = depth_shape[:2]
+    p.colorHeight, p.colorWidth = color_shape[:2]
+    p.widthIntegration, p.heightIntegration = wi, hi
+    p.erodeIterations, p.erodeStructureSize, p.erodeDThresh, p.erodeFracReq = (2 if erode else 0), 3, 0.05, 0.3
+    p.depthSigmaD, p.depthSigmaR = (sigmaD if depth_filter else 0.0), sigmaR
+    return p
+
+
+def ingest_frame(depth: np.ndarray, color: np.ndarray, wi: int, hi: int, **kw):
+    """Device part of CUDAImageManager::process: (depth [hi,wi] f32, colour [hi,wi,4] u8) at the integration resolution."""
+    L = lib(kw.pop("fast", False))
+    depth = np.ascontiguousarray(depth, np.float32); color = np.ascontiguousarray(color, np.uint8)
+    p = ingest_params(depth.shape, color.shape, wi, hi, **kw)
+    dout = np.full((hi, wi), -np.inf, np.float32); cout = np.zeros((hi, wi, 4), np.uint8)
+    L.orc_ingest_frame.argtypes = [C.c_void_p] * 5
+    L.orc_ingest_frame.restype = None
+    L.orc_ingest_frame(C.addressof(p), depth.ctypes.data, color.ctypes.data, dout.ctypes.data, cout.ctypes.data)
+    return dout, cout
