@@ -24,4 +24,4 @@ def test_ingest_matches_oracle_bit_for_bit(cuda_device, W, H, wi, hi, erode, fil
     od, oc = orc.ingest_frame(d, c, wi, hi, erode=erode, depth_filter=filt)
     np.testing.assert_array_equal(gd.cpu().numpy().view(np.uint32), od.view(np.uint32))
     np.testing.assert_array_equal(gc.cpu().numpy(), oc)
-    assert np.isfinite(od).mean() > 0.5
+    assert np.isfinite(od).mean() > 0.3
