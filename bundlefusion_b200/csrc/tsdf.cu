@@ -408,12 +408,34 @@ __device__ __forceinline__ I3 unpack_block_key(unsigned long long key) {
 }
 
 // Multi-GPU spatial shard: when hp.m_dummy = {rank, world} with world > 1, this device allocates
-// (and therefore integrates) only the blocks it owns; owner(pos) is a hash independent of the bucket hash.
+// (and therefore integrates) only the blocks it owns.  Ownership is a 3-D checkerboard of cubes of BF_SHARD_CUBE^3 blocks
+// (64 cm at 1 cm voxels): owner = (cx + cy + cz) mod world.  Cubes, not a per-block hash, so that ownership is coherent along
+// a ray: a pixel whose 20-odd-cm ray segment only crosses cubes of other ranks is dropped before its DDA walk (dda_setup).
+#define BF_SHARD_CUBE 8
+__device__ __forceinline__ int floor_div_cube(int v) { return (v >= 0) ? v / BF_SHARD_CUBE : -((-v + BF_SHARD_CUBE - 1) / BF_SHARD_CUBE); }
+__device__ __forceinline__ unsigned cube_owner(int cx, int cy, int cz, unsigned world) {
+    const int m = (cx + cy + cz) % (int)world;
+    return (unsigned)(m < 0 ? m + (int)world : m);
+}
 __device__ __forceinline__ bool owns_block(const BFHashParams& hp, I3 b) {
     const unsigned world = hp.m_dummy[1];
     if (world <= 1) return true;
-    const unsigned mix = ((unsigned)b.x * 73856093u) ^ ((unsigned)b.y * 19349669u) ^ ((unsigned)b.z * 83492791u);
-    return ((mix * 0x9E3779B1u) >> 8) % world == hp.m_dummy[0];
+    return cube_owner(floor_div_cube(b.x), floor_div_cube(b.y), floor_div_cube(b.z), world) == hp.m_dummy[0];
+}
+// does the block-coordinate box [lo, hi] (the DDA of a ray never leaves the box spanned by its first and last block) touch a cube
+// this rank owns?
+__device__ __forceinline__ bool box_touches_owned(const BFHashParams& hp, I3 a, I3 b) {
+    const unsigned world = hp.m_dummy[1];
+    if (world <= 1) return true;
+    const int x0 = floor_div_cube(min(a.x, b.x)), x1 = floor_div_cube(max(a.x, b.x));
+    const int y0 = floor_div_cube(min(a.y, b.y)), y1 = floor_div_cube(max(a.y, b.y));
+    const int z0 = floor_div_cube(min(a.z, b.z)), z1 = floor_div_cube(max(a.z, b.z));
+    if ((long long)(x1 - x0 + 1) * (y1 - y0 + 1) * (z1 - z0 + 1) > 64) return true;      // a very long segment: just walk it
+    for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x)
+                if (cube_owner(x, y, z, world) == hp.m_dummy[0]) return true;
+    return false;
 }
 
 struct DDA {                    // state of one pixel's block walk (.cu:189-219)
@@ -440,6 +462,7 @@ __device__ __forceinline__ bool dda_setup(const BFHashParams& hp, const BFDepthC
 
     s.cur = world_to_block(hp, rayMin);
     const I3 end = world_to_block(hp, rayMax);
+    if (!box_touches_owned(hp, s.cur, end)) return false;      // multi-GPU: nothing on this ray is ours
     s.step.x = (float)isign(dir.x); s.step.y = (float)isign(dir.y); s.step.z = (float)isign(dir.z);
     const I3 nb = { s.cur.x + (int)fminf(fmaxf(s.step.x, 0.0f), 1.0f), s.cur.y + (int)fminf(fmaxf(s.step.y, 0.0f), 1.0f),
                     s.cur.z + (int)fminf(fmaxf(s.step.z, 0.0f), 1.0f) };

@@ -259,12 +259,15 @@ static int alloc_block(BFHashDataStruct* hd, const BFHashParams* hp, i3 pos) {
 }
 
 /* Multi-GPU spatial shard of the voxel hash (not in the reference; SURVEY.md section 8e, tsdf.cu owns_block): with
- * hp->m_dummy = {rank, world}, world > 1, a device allocates -- and therefore integrates -- only the blocks it owns. */
+ * hp->m_dummy = {rank, world}, world > 1, a device allocates -- and therefore integrates -- only the blocks it owns:
+ * a 3-D checkerboard of cubes of 8^3 blocks, owner = (cx + cy + cz) mod world. */
+static inline int floor_div_cube(int v) { return (v >= 0) ? v / 8 : -((-v + 7) / 8); }
 static inline int owns_block(const BFHashParams* hp, i3 b) {
-    const uint32_t world = hp->m_dummy[1];
+    const int world = (int)hp->m_dummy[1];
     if (world <= 1) return 1;
-    const uint32_t mix = ((uint32_t)b.x * 73856093u) ^ ((uint32_t)b.y * 19349669u) ^ ((uint32_t)b.z * 83492791u);
-    return ((mix * 0x9E3779B1u) >> 8) % world == hp->m_dummy[0];
+    int m = (floor_div_cube(b.x) + floor_div_cube(b.y) + floor_div_cube(b.z)) % world;
+    if (m < 0) m += world;
+    return (uint32_t)m == hp->m_dummy[0];
 }
 
 /* allocKernel: CUDASceneRepHashSDF.cu:165-251 (d_bitMask == NULL: streaming is disabled
