@@ -110,6 +110,7 @@ HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
 
 CACHE_SYMBOLS = ["bfCacheStoreFrame"]
 INGEST_SYMBOLS = ["bfIngestFrame"]
+BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updateTrajectoryCU"]
 
 SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
 
@@ -282,6 +283,12 @@ def lib() -> C.CDLL:
     L.bfSolverReleaseWorkspace.argtypes = [P(BFSolverState)]
     L.bfCacheStoreFrame.argtypes = [P(BFCacheParams), vp, vp, P(BFCUDACachedFrame)]
     L.bfIngestFrame.argtypes = [P(BFIngestParams), vp, vp, vp, vp]
+    L.computeSiftTransformCU.argtypes = [vp, vp, vp, C.c_uint, vp, C.c_uint, C.c_uint, vp]
+    L.computeSiftTransformCU.restype = None
+    L.initNextGlobalTransformCU.argtypes = [vp, C.c_uint, C.c_uint, vp, C.c_uint, C.c_uint]
+    L.initNextGlobalTransformCU.restype = None
+    L.updateTrajectoryCU.argtypes = [vp, C.c_uint, vp, C.c_uint, vp, C.c_uint, C.c_uint, vp]
+    L.updateTrajectoryCU.restype = None
     # SIFT descriptor matcher
     L.bfSiftMatchBatch.argtypes = [P(BFSiftMatchJob), C.c_int, C.c_float, C.c_float]
     L.bfSiftWorkspaceBytes.restype = C.c_size_t

@@ -1,0 +1,85 @@
+// trajectory.cu -- trajectory glue for sm_100a.  Implements include/bf_bundler.h (row a22 of SURVEY.md section 8).
+// Behavioural source (what, not how): FL/OnlineBundler.cu:6-140.  Tiny kernels; what matters is that they exist behind the
+// reference's stub names, run on the library stream without a host synchronisation, and agree bit for bit with
+// oracle/trajectory_oracle.c (this TU is built -fmad=false; products are fused only as mat4.cuh writes them).
+#include "../../include/bf_bundler.h"
+#include "bf_common.cuh"
+#include "mat4.cuh"
+
+namespace bf {
+
+extern unsigned long long g_launchCount;
+
+// getSiftTransformCU_Kernel (OnlineBundler.cu:6-53): one thread, the loop walks back to the most recent matched frame of the chunk
+__global__ void sift_transform_kernel(unsigned curFrameIndex, const float* __restrict__ complete, unsigned lastValidComplete, float* siftTraj,
+                                      unsigned curFrameIndexAll, const int* __restrict__ numFiltered, const float* __restrict__ filteredInv, float* currIntegrate) {
+    for (int i = (int)curFrameIndex - 1; i >= 0; --i) {
+        if (numFiltered[i] <= 0) continue;
+        const unsigned prev = curFrameIndexAll - (curFrameIndex - (unsigned)i);
+        float T[16], R[16];
+        mat4_mul_hd(&siftTraj[16 * prev], &filteredInv[16 * i], T);
+        for (int k = 0; k < 16; ++k) siftTraj[16 * curFrameIndexAll + k] = T[k];
+        if (lastValidComplete == 0) {
+            for (int k = 0; k < 16; ++k) R[k] = T[k];
+        } else if (prev < lastValidComplete) {
+            mat4_mul_hd(&complete[16 * prev], &filteredInv[16 * i], R);
+        } else {
+            float inv[16], off[16], t2[16];
+            mat4_inverse_hd(&siftTraj[16 * lastValidComplete], inv);
+            mat4_mul_hd(inv, &siftTraj[16 * prev], off);
+            mat4_mul_hd(&complete[16 * lastValidComplete], off, t2);
+            mat4_mul_hd(t2, &filteredInv[16 * i], R);
+        }
+        for (int k = 0; k < 16; ++k) currIntegrate[k] = R[k];
+        break;
+    }
+}
+
+// updateTrajectoryCU_Kernel (OnlineBundler.cu:71-90)
+__global__ void update_trajectory_kernel(const float* __restrict__ global, float* complete, unsigned numComplete, const float* __restrict__ local,
+                                         unsigned perTraj, const int* __restrict__ invalidate) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= numComplete) return;
+    const unsigned submap = perTraj - 1, g = idx / submap, l = idx % submap;
+    float R[16];
+    if (invalidate[idx] == 0) { for (int k = 0; k < 16; ++k) R[k] = -INFINITY; }
+    else mat4_mul_hd(&global[16 * g], &local[16 * (g * perTraj + l)], R);
+    for (int k = 0; k < 16; ++k) complete[16 * idx + k] = R[k];
+}
+
+// initNextGlobalTransformCU_Kernel (OnlineBundler.cu:114-126)
+__global__ void init_next_global_kernel(float* global, unsigned numGlobal, unsigned initIdx, const float* __restrict__ local, unsigned lastValidLocal, unsigned perTraj) {
+    const float* L = &local[16 * (size_t)(numGlobal * perTraj - (perTraj - lastValidLocal))];
+    float R[16];
+    mat4_mul_hd(&global[16 * initIdx], L, R);
+    for (int k = 0; k < 16; ++k) global[16 * numGlobal + k] = R[k];
+}
+
+}  // namespace bf
+
+using namespace bf;
+
+BF_API void computeSiftTransformCU(const float* d_currFilteredTransformsInv, const int* d_currNumFilteredMatchesPerImagePair, const float* d_completeTrajectory,
+                                   unsigned int lastValidCompleteTransform, float* d_siftTrajectory, unsigned int curFrameIndexAll, unsigned int curFrameIndex,
+                                   float* d_currIntegrateTrans) {
+    if (curFrameIndex == 0) return;                                              // OnlineBundler.cu:59
+    ++g_launchCount;
+    sift_transform_kernel<<<1, 1, 0, stream()>>>(curFrameIndex, d_completeTrajectory, lastValidCompleteTransform, d_siftTrajectory, curFrameIndexAll,
+                                                 d_currNumFilteredMatchesPerImagePair, d_currFilteredTransformsInv, d_currIntegrateTrans);
+    BF_SAFE((int)cudaGetLastError());
+}
+BF_API void updateTrajectoryCU(const float* d_globalTrajectory, unsigned int numGlobalTransforms, float* d_completeTrajectory, unsigned int numCompleteTransforms,
+                               const float* d_localTrajectories, unsigned int numLocalTransformsPerTrajectory, unsigned int numLocalTrajectories, int* d_imageInvalidateList) {
+    (void)numGlobalTransforms; (void)numLocalTrajectories;
+    if (numCompleteTransforms == 0) return;
+    ++g_launchCount;
+    update_trajectory_kernel<<<(numCompleteTransforms + 127) / 128, 128, 0, stream()>>>(d_globalTrajectory, d_completeTrajectory, numCompleteTransforms, d_localTrajectories,
+                                                                                        numLocalTransformsPerTrajectory, d_imageInvalidateList);
+    BF_SAFE((int)cudaGetLastError());
+}
+BF_API void initNextGlobalTransformCU(float* d_globalTrajectory, unsigned int numGlobalTransforms, unsigned int initGlobalIdx, float* d_localTrajectories,
+                                      unsigned int lastValidLocal, unsigned int numLocalTransformsPerTrajectory) {
+    ++g_launchCount;
+    init_next_global_kernel<<<1, 1, 0, stream()>>>(d_globalTrajectory, numGlobalTransforms, initGlobalIdx, d_localTrajectories, lastValidLocal, numLocalTransformsPerTrajectory);
+    BF_SAFE((int)cudaGetLastError());
+}

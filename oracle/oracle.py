@@ -401,3 +401,37 @@ def ingest_frame(depth: np.ndarray, color: np.ndarray, wi: int, hi: int, **kw):
     L.orc_ingest_frame.restype = None
     L.orc_ingest_frame(C.addressof(p), depth.ctypes.data, color.ctypes.data, dout.ctypes.data, cout.ctypes.data)
     return dout, cout
+
+
+# ---- trajectory glue (oracle/trajectory_oracle.c) ---------------------------------------------------------------------------
+def compute_sift_transform(filteredInv, numFiltered, complete, lastValidComplete, siftTraj, curAll, cur):
+    """getSiftTransformCU_Kernel: returns (updated siftTraj copy, currIntegrateTrans [4,4])."""
+    L = lib()
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    filteredInv, complete, siftTraj = f(filteredInv), f(complete), f(siftTraj).copy()
+    nf = np.ascontiguousarray(numFiltered, np.int32)
+    out = np.zeros((4, 4), np.float32)
+    L.orc_compute_sift_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p]
+    L.orc_compute_sift_transform.restype = None
+    L.orc_compute_sift_transform(filteredInv.ctypes.data, nf.ctypes.data, complete.ctypes.data, lastValidComplete, siftTraj.ctypes.data, curAll, cur, out.ctypes.data)
+    return siftTraj, out
+
+
+def update_trajectory(globalT, local, perTraj, invalidate):
+    L = lib()
+    g, l = np.ascontiguousarray(globalT, np.float32), np.ascontiguousarray(local, np.float32)
+    inv = np.ascontiguousarray(invalidate, np.int32)
+    out = np.zeros((len(inv), 4, 4), np.float32)
+    L.orc_update_trajectory.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p]
+    L.orc_update_trajectory.restype = None
+    L.orc_update_trajectory(g.ctypes.data, out.ctypes.data, len(inv), l.ctypes.data, perTraj, inv.ctypes.data)
+    return out
+
+
+def init_next_global(globalT, numGlobal, initIdx, local, lastValidLocal, perTraj):
+    L = lib()
+    g = np.ascontiguousarray(globalT, np.float32).copy(); l = np.ascontiguousarray(local, np.float32)
+    L.orc_init_next_global.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_uint, C.c_uint]
+    L.orc_init_next_global.restype = None
+    L.orc_init_next_global(g.ctypes.data, numGlobal, initIdx, l.ctypes.data, lastValidLocal, perTraj)
+    return g

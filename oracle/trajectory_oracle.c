@@ -1,0 +1,59 @@
+/*
+ * trajectory_oracle.c -- CPU restatement of the trajectory glue kernels: FL/OnlineBundler.cu:6-140.
+ * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header).  PARITY STATUS: "parity unpinned" against the reference itself (no tests /
+ * golden vectors; OnlineBundler.cu is not rebuilt by oracle/build_ref.py); pinned by tests/test_trajectory_oracle.py (numpy float64
+ * products, identity / inverse cases).  Arithmetic contract shared with bundlefusion_b200/csrc/trajectory.cu: the 4x4 product fused
+ * as fma(a4,b4, fma(a3,b3, fma(a1,b1, a2*b2))) (the way nvcc fuses a1*b1 + a2*b2 + a3*b3 + a4*b4, cf. tsdf_oracle.c header), the
+ * inverse by the cofactor formula of bundlefusion_b200/csrc/mat4.cuh, every other operation individually rounded.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+void orc_mat4_inverse(const float* m, float* out);          /* solver_oracle.c */
+
+static void mul(const float* a, const float* b, float* r) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            r[4 * i + j] = fmaf(a[4 * i + 3], b[12 + j], fmaf(a[4 * i + 2], b[8 + j], fmaf(a[4 * i], b[j], a[4 * i + 1] * b[4 + j])));
+}
+
+/* getSiftTransformCU_Kernel, OnlineBundler.cu:6-53 */
+ORC_API void orc_compute_sift_transform(const float* filteredInv, const int* numFiltered, const float* complete, unsigned lastValidComplete,
+                                        float* siftTraj, unsigned curAll, unsigned cur, float* currIntegrate) {
+    if (cur == 0) return;
+    for (int i = (int)cur - 1; i >= 0; --i) {
+        if (numFiltered[i] <= 0) continue;
+        const unsigned prev = curAll - (cur - (unsigned)i);
+        float T[16], R[16];
+        mul(&siftTraj[16 * prev], &filteredInv[16 * i], T);
+        memcpy(&siftTraj[16 * curAll], T, sizeof T);
+        if (lastValidComplete == 0) memcpy(R, T, sizeof R);
+        else if (prev < lastValidComplete) mul(&complete[16 * prev], &filteredInv[16 * i], R);
+        else {
+            float inv[16], off[16], t2[16];
+            orc_mat4_inverse(&siftTraj[16 * lastValidComplete], inv);
+            mul(inv, &siftTraj[16 * prev], off);
+            mul(&complete[16 * lastValidComplete], off, t2);
+            mul(t2, &filteredInv[16 * i], R);
+        }
+        memcpy(currIntegrate, R, sizeof R);
+        break;
+    }
+}
+/* updateTrajectoryCU_Kernel, OnlineBundler.cu:71-90 */
+ORC_API void orc_update_trajectory(const float* global, float* complete, unsigned numComplete, const float* local, unsigned perTraj, const int* invalidate) {
+    const unsigned submap = perTraj - 1;
+    for (unsigned idx = 0; idx < numComplete; ++idx) {
+        if (invalidate[idx] == 0) { for (int k = 0; k < 16; ++k) complete[16 * idx + k] = -INFINITY; }
+        else mul(&global[16 * (idx / submap)], &local[16 * ((idx / submap) * perTraj + idx % submap)], &complete[16 * idx]);
+    }
+}
+/* initNextGlobalTransformCU_Kernel, OnlineBundler.cu:114-126 */
+ORC_API void orc_init_next_global(float* global, unsigned numGlobal, unsigned initIdx, const float* local, unsigned lastValidLocal, unsigned perTraj) {
+    float R[16];
+    mul(&global[16 * initIdx], &local[16 * (size_t)(numGlobal * perTraj - (perTraj - lastValidLocal))], R);
+    memcpy(&global[16 * numGlobal], R, sizeof R);
+}

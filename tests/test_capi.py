@@ -52,6 +52,7 @@ def test_symbol_list_matches_header():
     assert sorted(set(_declared_symbols("bf_sift.h"))) == sorted(set(capi.SIFT_SYMBOLS))
     assert sorted(set(_declared_symbols("bf_cache.h"))) == sorted(set(capi.CACHE_SYMBOLS))
     assert sorted(set(_declared_symbols("bf_ingest.h"))) == sorted(set(capi.INGEST_SYMBOLS))
+    assert sorted(set(_declared_symbols("bf_bundler.h"))) == sorted(set(capi.BUNDLER_SYMBOLS))
 
 
 def test_sift_pod_layouts():
