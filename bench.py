@@ -202,30 +202,31 @@ def run_ours(args):
 
     skip_ba = [args.no_ba]
 
-    # e2e leg: the incoming frame is handed over as HOST (pinned) buffers and copied to its device slot every step, on an upload
-    # stream, one frame ahead -- frame f+1 crosses PCIe while frame f is being fused (the slot it lands in was last read > 100
-    # steps ago), as a sensor thread's upload would (FL/CUDAImageManager.cpp:22-158 uploads on arrival).
-    up_stream = torch.cuda.Stream(device=dev)
-    up_done = {}
+    # The incoming frame reaches its device slot one frame ahead of the fusion, on a side stream: frame f+1 crosses PCIe (e2e leg: the
+    # sensor hands HOST pinned buffers to rank 0 every step, as FL/CUDAImageManager.cpp:22-158 uploads on arrival) and, with several
+    # GPUs, NVLink (the sensor frame lives on rank 0: one NCCL broadcast of depth + colour per step, every rank fuses its own shard)
+    # while frame f is being fused.  The slot it lands in was last read > 100 steps ago.
+    pre_stream = torch.cuda.Stream(device=dev)
+    pre_done = {}
 
-    def upload_frame(f):
+    def prefetch_frame(f, e2e):
         cur = f % B
-        with torch.cuda.stream(up_stream):
-            dlist[cur].copy_(h_depth[cur], non_blocking=True); clist[cur].copy_(h_color[cur], non_blocking=True)
-            ev = torch.cuda.Event(); ev.record(up_stream)
-        up_done[f] = ev
+        with torch.cuda.stream(pre_stream):
+            if e2e and rank == 0:
+                dlist[cur].copy_(h_depth[cur], non_blocking=True); clist[cur].copy_(h_color[cur], non_blocking=True)
+            if world > 1:
+                dist.broadcast(dlist[cur], 0); dist.broadcast(clist[cur], 0)
+            ev = torch.cuda.Event(); ev.record(pre_stream)
+        pre_done[f] = ev
 
     def step(f, e2e):
-        cur = f % B
-        if e2e:
-            if f not in up_done:
-                upload_frame(f)
-            torch.cuda.current_stream(dev).wait_event(up_done.pop(f))
-        if world > 1:     # the sensor frame lives on rank 0: broadcast over NVLink, every rank integrates its own shard
-            dist.broadcast(dlist[cur], 0); dist.broadcast(clist[cur], 0)
+        if e2e or world > 1:
+            if f not in pre_done:
+                prefetch_frame(f, e2e)
+            torch.cuda.current_stream(dev).wait_event(pre_done.pop(f))
         scene.runPackedOps(packed_ops[f], packed_frames, cam)
-        if e2e and f + 1 < len(packed_ops):
-            upload_frame(f + 1)
+        if (e2e or world > 1) and f + 1 < len(packed_ops):
+            prefetch_frame(f + 1, e2e)
         if f % WORKLOAD["chunk"] == WORKLOAD["chunk"] - 1 and not skip_ba[0]:
             ba(e2e, f // WORKLOAD["chunk"])
         if e2e:
@@ -235,6 +236,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        pre_done.clear()               # a frame prefetched at the end of the previous pass is fetched again by this pass's rules
         if profile:
             L.bfTsdfSetProfiling(1)
         l0 = L.bfGetLaunchCount()
