@@ -38,13 +38,24 @@ __device__ __forceinline__ unsigned tie_key(unsigned idx) {
     const unsigned lane = kColumnPass ? ((idx >> 2) & 31u) : (idx & 31u);
     return ((__brev(lane) >> 27) << 24) | idx;
 }
-// (value, index) packed so that a plain unsigned 64-bit maximum is "larger value, then smaller key"
+// Per-feature running state: the largest value with the tie key of its index, and the second largest VALUE of the multiset (its
+// index never matters).  A product can only change the state if it beats the second value or ties the first, which after the first
+// few tiles almost none does: the common case is two integer compares.
+struct Top2 { int v1; unsigned k1; int v2; };
 template <bool kColumnPass>
-__device__ __forceinline__ unsigned long long pack(int v, unsigned idx) {
-    return ((unsigned long long)(unsigned)v << 32) | (unsigned long long)(0xFFFFFFFFu - tie_key<kColumnPass>(idx));
+__device__ __forceinline__ void top2_update(Top2& s, int v, unsigned idx) {
+    if (v > s.v2 || (v == s.v1 && v > 0)) {
+        const unsigned key = tie_key<kColumnPass>(idx);
+        if (v > s.v1) { s.v2 = s.v1; s.v1 = v; s.k1 = key; }
+        else if (v == s.v1) { s.v2 = v; if (key < s.k1) s.k1 = key; }
+        else s.v2 = v;
+    }
 }
-__device__ __forceinline__ void top2_insert(unsigned long long& b1, unsigned long long& b2, unsigned long long p) {
-    if (p > b1) { b2 = b1; b1 = p; } else if (p > b2) b2 = p;
+// union of two states (order-independent)
+__device__ __forceinline__ void top2_merge(Top2& s, int ov1, unsigned ok1, int ov2) {
+    if (ov1 > s.v1) { s.v2 = max(s.v1, ov2); s.v1 = ov1; s.k1 = ok1; }
+    else if (ov1 == s.v1) { if (ov1 > 0) { s.v2 = ov1; if (ok1 < s.k1) s.k1 = ok1; } }
+    else s.v2 = max(s.v2, ov1);
 }
 __device__ __forceinline__ float dist_of(int dot) { return acosf(fminf((float)dot * 0.000003814697265625f, 1.0f)); }
 
@@ -85,9 +96,9 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
             a[ks][3] = (r1 < nA) ? __ldg(p1 + ks * 8 + 4 + q) : 0u;
         }
     }
-    // two largest packed (value, key) of this thread's two features (rows g and g + 8 of the warp tile); 0 = none: a dot product must
-    // be > 0 to be a candidate (the reference starts from max = 0 with a strict '>')
-    unsigned long long b1[2] = { 0ull, 0ull }, b2[2] = { 0ull, 0ull };
+    // running best / second of this thread's two features (rows g and g + 8 of the warp tile); a dot product must be > 0 to be a
+    // candidate (the reference starts from max = 0 with a strict '>')
+    Top2 st[2] = { { 0, 0xFFFFFFFFu, 0 }, { 0, 0xFFFFFFFFu, 0 } };
 
     for (int col0 = 0; col0 < nB; col0 += SM_BN) {
         __syncthreads();                                   // the previous step's fragment loads are done
@@ -120,8 +131,8 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 if (c + e < nB) {
-                    if (acc[nt][e] > 0) top2_insert(b1[0], b2[0], pack<kColumnPass>(acc[nt][e], (unsigned)(c + e)));
-                    if (acc[nt][2 + e] > 0) top2_insert(b1[1], b2[1], pack<kColumnPass>(acc[nt][2 + e], (unsigned)(c + e)));
+                    top2_update<kColumnPass>(st[0], acc[nt][e], (unsigned)(c + e));
+                    top2_update<kColumnPass>(st[1], acc[nt][2 + e], (unsigned)(c + e));
                 }
             }
         }
@@ -131,9 +142,9 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int o = 1; o <= 2; o <<= 1) {
-            const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, b1[h], o), o2 = __shfl_xor_sync(0xffffffffu, b2[h], o);
-            top2_insert(b1[h], b2[h], o1);
-            top2_insert(b1[h], b2[h], o2);
+            const int ov1 = __shfl_xor_sync(0xffffffffu, st[h].v1, o), ov2 = __shfl_xor_sync(0xffffffffu, st[h].v2, o);
+            const unsigned ok1 = __shfl_xor_sync(0xffffffffu, st[h].k1, o);
+            top2_merge(st[h], ov1, ok1, ov2);
         }
     }
     if (q == 0) {
@@ -141,8 +152,8 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
         for (int h = 0; h < 2; ++h) {
             const int r = row0 + (int)warp * 16 + (int)g + 8 * h;
             if (r >= nA) continue;
-            const int vmax = (int)(b1[h] >> 32), vnxt = (int)(b2[h] >> 32);
-            const int idx = b1[h] ? (int)((0xFFFFFFFFu - (unsigned)(b1[h] & 0xFFFFFFFFull)) & 0x00FFFFFFu) : -1;
+            const int vmax = st[h].v1, vnxt = st[h].v2;
+            const int idx = (vmax > 0) ? (int)(st[h].k1 & 0x00FFFFFFu) : -1;
             const float dist = dist_of(vmax), distn = dist_of(vnxt);
             const int res = (dist < distmax && dist < distn * ratiomax) ? idx : -1;
             if (!kColumnPass) {
