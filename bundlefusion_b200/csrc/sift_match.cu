@@ -79,7 +79,7 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
     if (!kColumnPass && blockIdx.x == 0 && threadIdx.x == 0) *job.numMatches = 0;       // SiftMatch.cpp:163 / ProgramCU.cu:1928
     if (nA <= 0 || nB <= 0 || row0 >= nA) return;
 
-    __shared__ __align__(16) unsigned char sB[SM_BN * SM_PITCH];
+    __shared__ __align__(16) unsigned char sBuf[2][SM_BN * SM_PITCH];          // double-buffered tile of B
     const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, q = lane & 3;
 
     // A fragments of this warp's 16 features, all of K = 128 (4 k-steps), kept in registers for the whole sweep
@@ -100,18 +100,28 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
     // candidate (the reference starts from max = 0 with a strict '>')
     Top2 st[2] = { { 0, 0xFFFFFFFFu, 0 }, { 0, 0xFFFFFFFFu, 0 } };
 
-    for (int col0 = 0; col0 < nB; col0 += SM_BN) {
-        __syncthreads();                                   // the previous step's fragment loads are done
-        // stage 64 descriptors of B: 64 x 128 B = 512 uint4, 4 per thread, coalesced
+    // stage 64 descriptors of B per step: 64 x 128 B = 512 uint4, 4 per thread, coalesced; the NEXT tile's global loads are issued
+    // before the current tile's products so that their latency hides behind the tensor-core work (one barrier per step)
+    uint4 pf[4];
+    auto fetch = [&](int col0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const unsigned v = t + 128u * k;               // 0..511
-            const unsigned r = v >> 3, c16 = v & 7u;
-            uint4 val = make_uint4(0u, 0u, 0u, 0u);
-            if (col0 + (int)r < nB) val = __ldg(reinterpret_cast<const uint4*>(job.desB + (size_t)(col0 + r) * 128) + c16);
-            *reinterpret_cast<uint4*>(&sB[r * SM_PITCH + c16 * 16]) = val;
+            const unsigned v = t + 128u * k, r = v >> 3, c16 = v & 7u;
+            pf[k] = (col0 + (int)r < nB) ? __ldg(reinterpret_cast<const uint4*>(job.desB + (size_t)(col0 + r) * 128) + c16) : make_uint4(0u, 0u, 0u, 0u);
         }
-        __syncthreads();
+    };
+    auto stash = [&](unsigned char* dst) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const unsigned v = t + 128u * k, r = v >> 3, c16 = v & 7u; *reinterpret_cast<uint4*>(&dst[r * SM_PITCH + c16 * 16]) = pf[k]; }
+    };
+    fetch(0);
+    stash(sBuf[0]);
+    __syncthreads();
+    int buf = 0;
+    for (int col0 = 0; col0 < nB; col0 += SM_BN) {
+        const bool more = col0 + SM_BN < nB;
+        if (more) fetch(col0 + SM_BN);
+        const unsigned char* sB = sBuf[buf];
         int acc[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0; }
@@ -136,6 +146,9 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
                 }
             }
         }
+        if (more) stash(sBuf[buf ^ 1]);
+        __syncthreads();
+        buf ^= 1;
     }
     // merge the four lanes (q = 0..3) that share a feature
 #pragma unroll
@@ -173,6 +186,8 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
 // ---- host ----------------------------------------------------------------------------------------------------------
 struct SiftWs {
     SiftJobDev* dJobs = nullptr; size_t jobCap = 0;
+    SiftJobDev* hJobs = nullptr;                 // pinned staging for the job table; evCopied = its last upload has left it
+    cudaEvent_t evCopied = nullptr;
     int* rowResult = nullptr; float* rowDist = nullptr; size_t rowCap = 0;
 };
 static SiftWs g_sift;
@@ -193,9 +208,13 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
     }
     cudaStream_t s = stream();
     if ((size_t)numJobs > g_sift.jobCap) {
-        if (g_sift.dJobs) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dJobs)); }
+        if (g_sift.dJobs) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dJobs)); BF_CHECK(cudaFreeHost(g_sift.hJobs)); }
         g_sift.jobCap = (size_t)numJobs * 2;
         BF_CHECK(cudaMalloc(&g_sift.dJobs, sizeof(SiftJobDev) * 2 * g_sift.jobCap));      // [row-pass jobs | column-pass jobs]
+        BF_CHECK(cudaMallocHost(&g_sift.hJobs, sizeof(SiftJobDev) * 2 * g_sift.jobCap));
+        if (!g_sift.evCopied) BF_CHECK(cudaEventCreateWithFlags(&g_sift.evCopied, cudaEventDisableTiming));
+    } else {
+        BF_CHECK(cudaEventSynchronize(g_sift.evCopied));      // the previous call's upload (normally long done) before the staging is rewritten
     }
     if (rows > g_sift.rowCap) {
         if (g_sift.rowResult) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.rowResult)); BF_CHECK(cudaFree(g_sift.rowDist)); }
@@ -203,7 +222,7 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
         BF_CHECK(cudaMalloc(&g_sift.rowResult, sizeof(int) * g_sift.rowCap));
         BF_CHECK(cudaMalloc(&g_sift.rowDist, sizeof(float) * g_sift.rowCap));
     }
-    std::vector<SiftJobDev> h(2 * (size_t)numJobs);
+    SiftJobDev* h = g_sift.hJobs;
     size_t off = 0;
     for (int i = 0; i < numJobs; ++i) {
         const BFSiftMatchJob& j = jobs[i];
@@ -218,8 +237,8 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
         h[i] = r; h[(size_t)numJobs + i] = c;
         if (live) off += (size_t)j.num1;
     }
-    BF_CHECK(cudaMemcpyAsync(g_sift.dJobs, h.data(), sizeof(SiftJobDev) * h.size(), cudaMemcpyHostToDevice, s));
-    BF_CHECK(cudaStreamSynchronize(s));                     // h is a stack-lifetime staging buffer (pageable): the copy must have left it
+    BF_CHECK(cudaMemcpyAsync(g_sift.dJobs, h, sizeof(SiftJobDev) * 2 * (size_t)numJobs, cudaMemcpyHostToDevice, s));
+    BF_CHECK(cudaEventRecord(g_sift.evCopied, s));
     const int gx1 = maxN1 > 0 ? (maxN1 + SM_BM - 1) / SM_BM : 1, gx2 = maxN2 > 0 ? (maxN2 + SM_BM - 1) / SM_BM : 1;
     g_launchCount += 2;
     sift_best_kernel<false><<<dim3(gx1, numJobs), 128, 0, s>>>(g_sift.dJobs, distmax, ratiomax);
@@ -236,6 +255,8 @@ BF_API size_t bfSiftWorkspaceBytes(void) {
 BF_API int bfSiftReleaseWorkspace(void) {
     std::lock_guard<std::mutex> lk(g_siftMutex);
     cudaFree(g_sift.dJobs); cudaFree(g_sift.rowResult); cudaFree(g_sift.rowDist);
+    if (g_sift.hJobs) cudaFreeHost(g_sift.hJobs);
+    if (g_sift.evCopied) cudaEventDestroy(g_sift.evCopied);
     g_sift = SiftWs();
     return 0;
 }
