@@ -110,7 +110,7 @@ HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
 
 CACHE_SYMBOLS = ["bfCacheStoreFrame"]
 INGEST_SYMBOLS = ["bfIngestFrame"]
-BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updateTrajectoryCU"]
+BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updateTrajectoryCU", "bfTrajectorySelectReintegration"]
 
 SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
 
@@ -289,6 +289,7 @@ def lib() -> C.CDLL:
     L.initNextGlobalTransformCU.restype = None
     L.updateTrajectoryCU.argtypes = [vp, C.c_uint, vp, C.c_uint, vp, C.c_uint, C.c_uint, vp]
     L.updateTrajectoryCU.restype = None
+    L.bfTrajectorySelectReintegration.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_float, C.c_float, vp, vp, vp]
     # SIFT descriptor matcher
     L.bfSiftMatchBatch.argtypes = [P(BFSiftMatchJob), C.c_int, C.c_float, C.c_float]
     L.bfSiftWorkspaceBytes.restype = C.c_size_t

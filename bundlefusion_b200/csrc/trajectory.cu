@@ -5,6 +5,7 @@
 #include "../../include/bf_bundler.h"
 #include "bf_common.cuh"
 #include "mat4.cuh"
+#include "se3.cuh"
 
 namespace bf {
 
@@ -55,9 +56,67 @@ __global__ void init_next_global_kernel(float* global, unsigned numGlobal, unsig
     for (int k = 0; k < 16; ++k) global[16 * numGlobal + k] = R[k];
 }
 
+// dist of TrajectoryManager::generateUpdateLists (TrajectoryManager.cpp:56-75) for every frame, then an iterative arg-max: topN <= a few
+// dozen rounds over <= 20 000 frames in ONE CTA -- no trajectory copy to the host, no host sort.
+__global__ void __launch_bounds__(1024)
+select_reintegration_kernel(const float* __restrict__ opt, const float* __restrict__ integ, const int* __restrict__ state, unsigned n, unsigned topN,
+                            float minDist, float scale, float* dist, int* list, int* count) {
+    __shared__ float sVal[32];
+    __shared__ int sIdx[32];
+    __shared__ int sPick;
+    __shared__ unsigned sTaken[2048];                                 // one bit per frame (numFrames <= 65 536, checked by the host)
+    const unsigned t = threadIdx.x;
+    for (unsigned i = t; i < 2048; i += blockDim.x) sTaken[i] = 0u;
+    for (unsigned i = t; i < n; i += blockDim.x) {
+        float d = -1.0f;                                              // not a candidate
+        if (state[i] != 0 && opt[16 * i] != -INFINITY) {
+            V3 ro, to, ri, ti;
+            matrix_to_pose(&opt[16 * i], ro, to);
+            matrix_to_pose(&integ[16 * i], ri, ti);
+            const V3 dr = ri * scale - ro * scale, dt = ti - to;
+            d = dot(dr, dr) + dot(dt, dt);
+        }
+        dist[i] = d;
+    }
+    __syncthreads();
+    unsigned found = 0;
+    for (; found < topN; ++found) {
+        float best = -1.0f; int bi = 0x7fffffff;
+        for (unsigned i = t; i < n; i += blockDim.x) {
+            const float d = dist[i];
+            if (d > minDist && d >= 0.0f && !((sTaken[i >> 5] >> (i & 31)) & 1u) && (d > best || (d == best && (int)i < bi))) { best = d; bi = (int)i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if ((t & 31) == 0) { sVal[t >> 5] = best; sIdx[t >> 5] = bi; }
+        __syncthreads();
+        if (t == 0) {
+            float b = -1.0f; int k = 0x7fffffff;
+            for (unsigned w = 0; w < blockDim.x / 32; ++w) if (sVal[w] > b || (sVal[w] == b && sIdx[w] < k)) { b = sVal[w]; k = sIdx[w]; }
+            sPick = (b >= 0.0f && k != 0x7fffffff) ? k : -1;
+            if (sPick >= 0) { list[found] = sPick; sTaken[sPick >> 5] |= 1u << (sPick & 31); }
+        }
+        __syncthreads();
+        if (sPick < 0) break;
+    }
+    if (t == 0) *count = (int)found;
+}
+
 }  // namespace bf
 
 using namespace bf;
+
+BF_API int bfTrajectorySelectReintegration(const float* d_opt, const float* d_integ, const int* d_state, unsigned int numFrames, unsigned int topN,
+                                           float minPoseDistSqrt, float rescaleRotToTrans, float* d_dist, int* d_list, int* d_count) {
+    if (!d_opt || !d_integ || !d_state || !d_dist || !d_list || !d_count || numFrames > 65536u) return (int)cudaErrorInvalidValue;
+    ++g_launchCount;
+    select_reintegration_kernel<<<1, 1024, 0, stream()>>>(d_opt, d_integ, d_state, numFrames, topN, minPoseDistSqrt, rescaleRotToTrans, d_dist, d_list, d_count);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
 
 BF_API void computeSiftTransformCU(const float* d_currFilteredTransformsInv, const int* d_currNumFilteredMatchesPerImagePair, const float* d_completeTrajectory,
                                    unsigned int lastValidCompleteTransform, float* d_siftTrajectory, unsigned int curFrameIndexAll, unsigned int curFrameIndex,

@@ -28,6 +28,18 @@ void updateTrajectoryCU(const float* d_globalTrajectory, unsigned int numGlobalT
                         const float* d_localTrajectories, unsigned int numLocalTransformsPerTrajectory, unsigned int numLocalTrajectories,
                         int* d_imageInvalidateList);
 
+/* ---- B200-native extension: the re-integration choice of TrajectoryManager::generateUpdateLists (FL/TrajectoryManager.cpp:45-108) on
+ * the device.  The reference copies the whole optimised trajectory to the host every frame, converts every pose with MatrixToPose, and
+ * std::sorts all frames to take the top N.  Here one launch computes, per frame, dist = |(s w, t)_integrated - (s w, t)_optimised|^2
+ * ((w, t) = the SE(3) logarithm, s = rescaleRotToTrans = 2) and selects the up to topN INTEGRATED frames of largest dist > minPoseDistSqrt, in
+ * descending order (ties: lower frame index first; the reference's std::sort leaves ties unspecified).  A frame whose optimised transform
+ * is invalid (first entry -inf) is never selected (the reference routes it to the de-integration list).
+ * d_frameState[i] != 0 <=> frame i is currently integrated.  Outputs: d_dist[numFrames], d_list[topN] (frame indices), d_count[1].
+ * Asynchronous on the library stream; returns 0 or a cudaError_t. */
+int bfTrajectorySelectReintegration(const float* d_optimizedTransforms, const float* d_integratedTransforms, const int* d_frameState,
+                                    unsigned int numFrames, unsigned int topN, float minPoseDistSqrt, float rescaleRotToTrans,
+                                    float* d_dist, int* d_list, int* d_count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -435,3 +435,16 @@ def init_next_global(globalT, numGlobal, initIdx, local, lastValidLocal, perTraj
     L.orc_init_next_global.restype = None
     L.orc_init_next_global(g.ctypes.data, numGlobal, initIdx, l.ctypes.data, lastValidLocal, perTraj)
     return g
+
+
+def select_reintegration(opt, integ, state, topN, minDist, scale=2.0):
+    """(dist [n], list of frame indices) -- TrajectoryManager::generateUpdateLists, re-integration part."""
+    L = lib()
+    opt, integ = np.ascontiguousarray(opt, np.float32), np.ascontiguousarray(integ, np.float32)
+    st = np.ascontiguousarray(state, np.int32)
+    n = len(st)
+    dist = np.zeros(n, np.float32); lst = np.zeros(max(topN, 1), np.int32)
+    L.orc_select_reintegration.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.orc_select_reintegration.restype = C.c_int
+    c = L.orc_select_reintegration(opt.ctypes.data, integ.ctypes.data, st.ctypes.data, n, topN, minDist, scale, dist.ctypes.data, lst.ctypes.data)
+    return dist, lst[:c].copy()

@@ -8,6 +8,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define ORC_API __attribute__((visibility("default")))
@@ -56,4 +57,34 @@ ORC_API void orc_init_next_global(float* global, unsigned numGlobal, unsigned in
     float R[16];
     mul(&global[16 * initIdx], &local[16 * (size_t)(numGlobal * perTraj - (perTraj - lastValidLocal))], R);
     memcpy(&global[16 * numGlobal], R, sizeof R);
+}
+
+void orc_matrix_to_pose(const float* M, float* rot, float* trans);          /* solver_oracle.c: SE(3) log, LieDerivUtil.h:135-158 */
+
+/* TrajectoryManager::generateUpdateLists, the re-integration part (FL/TrajectoryManager.cpp:45-108): dist per frame, then the up to topN
+ * integrated frames of largest dist > minDist, descending (ties: lower index). */
+ORC_API int orc_select_reintegration(const float* opt, const float* integ, const int* state, unsigned n, unsigned topN, float minDist, float scale,
+                                     float* dist, int* list) {
+    for (unsigned i = 0; i < n; ++i) {
+        dist[i] = -1.0f;
+        if (state[i] != 0 && opt[16 * i] != -INFINITY) {
+            float ro[3], to[3], ri[3], ti[3];
+            orc_matrix_to_pose(&opt[16 * i], ro, to);
+            orc_matrix_to_pose(&integ[16 * i], ri, ti);
+            float d = 0.0f, e = 0.0f;
+            for (int k = 0; k < 3; ++k) { const float a = ri[k] * scale - ro[k] * scale; d += a * a; }
+            for (int k = 0; k < 3; ++k) { const float a = ti[k] - to[k]; e += a * a; }
+            dist[i] = d + e;
+        }
+    }
+    int found = 0;
+    char* taken = (char*)calloc(n ? n : 1, 1);
+    for (; (unsigned)found < topN; ++found) {
+        int bi = -1; float best = -1.0f;
+        for (unsigned i = 0; i < n; ++i) if (!taken[i] && dist[i] > minDist && dist[i] >= 0.0f && dist[i] > best) { best = dist[i]; bi = (int)i; }
+        if (bi < 0) break;
+        taken[bi] = 1; list[found] = bi;
+    }
+    free(taken);
+    return found;
 }

@@ -52,3 +52,37 @@ def test_stubs_match_oracle(cuda_device):
     L.computeSiftTransformCU(d_f.data_ptr(), d_n.data_ptr(), d_cm.data_ptr(), 0, d_s.data_ptr(), 5, 0, d_out.data_ptr())
     torch.cuda.synchronize()
     assert float(d_out.abs().sum()) == 0.0
+
+
+def test_select_reintegration_matches_oracle(cuda_device):
+    """bfTrajectorySelectReintegration against the oracle on 5 000 frames: same list (well separated distances), dist within 1e-5
+    relative + 1e-9 (sin / cos / asin of the two SE(3) logs differ in the last bits between CUDA and libm)."""
+    import torch
+    from bundlefusion_b200 import synth
+    dev = cuda_device
+    L = capi.lib()
+    n, topN = 5000, 30
+    rng = np.random.default_rng(3)
+    integ = np.stack([synth.se3_exp(rng.standard_normal(3) * 0.4, rng.standard_normal(3) * 2) for _ in range(n)]).astype(F)
+    opt = integ.copy()
+    movers = rng.permutation(n)[:200]
+    for r, k in enumerate(movers):
+        opt[k] = (synth.se3_exp(rng.standard_normal(3) * 0.002 * (r + 1) / 20, rng.standard_normal(3) * 0.004 * (r + 1) / 20) @ integ[k].astype(np.float64)).astype(F)
+    state = np.ones(n, np.int32); state[movers[-5:]] = 0
+    opt[movers[-8], 0, 0] = -np.inf
+    d_o, d_i, d_s = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (opt, integ, state))
+    d_dist = torch.zeros(n, device=dev); d_list = torch.full((topN,), -1, dtype=torch.int32, device=dev); d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.bfSetStream(None); torch.cuda.synchronize()
+    capi.check(L.bfTrajectorySelectReintegration(d_o.data_ptr(), d_i.data_ptr(), d_s.data_ptr(), n, topN, 0.0004, 2.0, d_dist.data_ptr(), d_list.data_ptr(), d_cnt.data_ptr()),
+               "bfTrajectorySelectReintegration")
+    torch.cuda.synchronize()
+    od, ol = orc.select_reintegration(opt, integ, state, topN, 0.0004)
+    cnt = int(d_cnt.item())
+    assert cnt == len(ol) == topN
+    gd = d_dist.cpu().numpy()
+    np.testing.assert_allclose(gd, od, rtol=1e-4, atol=1e-9)
+    # the selected frames are the same; the order may differ only between frames whose distances agree to 1e-4 relative
+    gl = d_list.cpu().numpy()[:cnt]
+    assert set(gl.tolist()) == set(ol.tolist())
+    assert np.all(np.diff(gd[gl]) <= 0)
+    assert gd[movers[-8]] == -1 and np.all(gd[movers[-5:]] == -1)

@@ -44,3 +44,24 @@ def test_compute_sift_transform_branches():
     # no matched frame in the chunk: nothing is written
     traj, out = orc.compute_sift_transform(finv, np.zeros(cur, np.int32), comp, 5, sift, cur_all, cur)
     np.testing.assert_array_equal(traj, sift); assert np.all(out == 0)
+
+
+def test_select_reintegration_rule():
+    """dist = |(2 w, t)_integrated - (2 w, t)_optimised|^2 on the SE(3) logs; top-N integrated frames above the threshold, descending."""
+    n = 50
+    integ = poses(n, 7)
+    rng = np.random.default_rng(8)
+    opt = integ.copy()
+    moved = {3: 0.05, 10: 0.2, 11: 0.03, 20: 0.1, 30: 0.4, 41: 0.0005}
+    for k, m in moved.items():
+        opt[k] = (synth.se3_exp(np.zeros(3), np.array([m, 0, 0])) @ integ[k].astype(np.float64)).astype(F)
+    state = np.ones(n, np.int32); state[30] = 0                       # frame 30 moved most but is not integrated
+    opt[20, 0, 0] = -np.inf                                          # frame 20 lost its transform
+    dist, lst = orc.select_reintegration(opt, integ, state, 3, 0.0004)
+    assert lst.tolist() == [10, 3, 11]
+    dist, lst = orc.select_reintegration(opt, integ, state, 10, 0.0004)
+    assert lst.tolist() == [10, 3, 11]                               # 41 moved 0.5 mm: dist 2.5e-7 < threshold; unmoved frames: 0
+    assert dist[30] == -1 and dist[20] == -1
+    # a left-multiplied pure translation changes t by exactly that translation (the rotation part of the log is unchanged)
+    np.testing.assert_allclose(dist[10], 0.2 ** 2, rtol=2e-3)
+    np.testing.assert_allclose(dist[5], 0.0, atol=1e-9)
