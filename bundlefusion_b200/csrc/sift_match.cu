@@ -183,6 +183,37 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
     }
 }
 
+// SortKeyPointMatchesCU_Kernel (SIFTImageManager.cu:59-145): one CTA per image pair, 128 slots, bitonic network in shared memory on
+// the total order (distance, image-2 feature, image-1 feature); padding sorts last.
+__global__ void __launch_bounds__(BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW)
+sift_sort_kernel(unsigned curFrame, unsigned startFrame, const int* __restrict__ numMatches, float* dists, uint2* idxs) {
+    const unsigned pair = blockIdx.x + startFrame;
+    if (pair == curFrame) return;
+    const int n = min(BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW, numMatches[pair]);
+    if (n <= 0) return;
+    __shared__ float sD[BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW];
+    __shared__ uint2 sI[BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW];
+    const unsigned t = threadIdx.x;
+    float* d = dists + (size_t)pair * BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW;
+    uint2* ix = idxs + (size_t)pair * BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW;
+    sD[t] = ((int)t < n) ? d[t] : INFINITY;
+    sI[t] = ((int)t < n) ? ix[t] : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    __syncthreads();
+    for (unsigned k = 2; k <= BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW; k <<= 1)
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            const unsigned o = t ^ j;
+            if (o > t) {
+                const float a = sD[t], b = sD[o];
+                const uint2 ia = sI[t], ib = sI[o];
+                const bool aAfterB = (a > b) || (a == b && (ia.y > ib.y || (ia.y == ib.y && ia.x > ib.x)));      // NaN distances do not occur (acosf of a clamped value)
+                const bool up = ((t & k) == 0);
+                if (aAfterB == up) { sD[t] = b; sD[o] = a; sI[t] = ib; sI[o] = ia; }
+            }
+            __syncthreads();
+        }
+    if ((int)t < n) { d[t] = sD[t]; ix[t] = sI[t]; }
+}
+
 // ---- host ----------------------------------------------------------------------------------------------------------
 struct SiftWs {
     SiftJobDev* dJobs = nullptr; size_t jobCap = 0;
@@ -244,6 +275,16 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
     sift_best_kernel<false><<<dim3(gx1, numJobs), 128, 0, s>>>(g_sift.dJobs, distmax, ratiomax);
     BF_CHECK(cudaGetLastError());
     sift_best_kernel<true><<<dim3(gx2, numJobs), 128, 0, s>>>(g_sift.dJobs + numJobs, distmax, ratiomax);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
+
+BF_API int bfSiftSortKeyPointMatches(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const int32_t* d_numMatchesPerImagePair,
+                                     float* d_matchDistances, uint32_t* d_matchKeyPointIndices) {
+    if (numFrames <= startFrame) return 0;                                  // SIFTImageManager.cu:148
+    ++g_launchCount;
+    sift_sort_kernel<<<numFrames - startFrame, BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW, 0, stream()>>>(curFrame, startFrame, d_numMatchesPerImagePair, d_matchDistances,
+                                                                                                 reinterpret_cast<uint2*>(d_matchKeyPointIndices));
     BF_CHECK(cudaGetLastError());
     return 0;
 }

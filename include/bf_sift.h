@@ -47,6 +47,14 @@ typedef struct BFSiftMatchJob {
  * A job with num1 <= 0 or num2 <= 0 only zeroes its counter (SiftMatch.cpp:162-165).  Returns 0 or a cudaError_t. */
 int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distmax, float ratiomax);
 
+/* SIFTImageManager::SortKeyPointMatchesCU(curFrame, startFrame, numFrames) (FL/SiftGPU/SIFTImageManager.cu:59-177): sorts the raw matches
+ * of every image pair p in [startFrame, numFrames), p != curFrame, by ascending distance, in place.  Arrays are the manager's:
+ * d_numMatchesPerImagePair[p], d_matchDistances[p * 128 + k], d_matchKeyPointIndices (uint2) [p * 128 + k].
+ * The reference's odd-even transposition sort is stable with respect to a race-dependent append order; here equal distances are
+ * ordered by (image-2 feature, image-1 feature), so the result does not depend on the append order.  Asynchronous. */
+int bfSiftSortKeyPointMatches(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const int32_t* d_numMatchesPerImagePair,
+                              float* d_matchDistances, uint32_t* d_matchKeyPointIndices);
+
 /* device scratch the matcher holds (rowResult / rowDist per job); released by bfSiftReleaseWorkspace */
 size_t bfSiftWorkspaceBytes(void);
 int bfSiftReleaseWorkspace(void);

@@ -448,3 +448,13 @@ def select_reintegration(opt, integ, state, topN, minDist, scale=2.0):
     L.orc_select_reintegration.restype = C.c_int
     c = L.orc_select_reintegration(opt.ctypes.data, integ.ctypes.data, st.ctypes.data, n, topN, minDist, scale, dist.ctypes.data, lst.ctypes.data)
     return dist, lst[:c].copy()
+
+
+def sift_sort_matches(curFrame, startFrame, numFrames, numMatches, dists, idxs):
+    """SortKeyPointMatchesCU on the manager-layout arrays ([pairs,128] distances, [pairs,128,2] indices); returns sorted copies."""
+    L = lib()
+    nm = np.ascontiguousarray(numMatches, np.int32); d = np.ascontiguousarray(dists, np.float32).copy(); ix = np.ascontiguousarray(idxs, np.uint32).copy()
+    L.orc_sift_sort_matches.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_sift_sort_matches.restype = None
+    L.orc_sift_sort_matches(curFrame, startFrame, numFrames, nm.ctypes.data, d.ctypes.data, ix.ctypes.data)
+    return d, ix

@@ -127,3 +127,22 @@ ORC_API int orc_sift_match(const uint8_t* d1, int n1, const uint8_t* d2, int n2,
     free(dot); free(rr); free(rd);
     return c;
 }
+
+/* SortKeyPointMatchesCU (FL/SiftGPU/SIFTImageManager.cu:59-177): ascending distance; equal distances by (image-2 feature, image-1 feature)
+ * -- the reference's odd-even transposition sort never swaps equal distances, i.e. it is stable with respect to an append order that is
+ * itself race-dependent; the oracle's append order is ascending image-2 feature, so both readings coincide here. */
+ORC_API void orc_sift_sort_matches(unsigned curFrame, unsigned startFrame, unsigned numFrames, const int32_t* numMatches, float* dists, uint32_t* idxs) {
+    for (unsigned p = startFrame; p < numFrames; ++p) {
+        if (p == curFrame) continue;
+        int n = numMatches[p] < MAX_RAW ? numMatches[p] : MAX_RAW;
+        float* d = dists + (size_t)p * MAX_RAW; uint32_t* ix = idxs + 2 * (size_t)p * MAX_RAW;
+        for (int i = 1; i < n; ++i) {                          /* insertion sort on the total order */
+            const float dv = d[i]; const uint32_t a = ix[2 * i], b = ix[2 * i + 1];
+            int j = i - 1;
+            while (j >= 0 && (d[j] > dv || (d[j] == dv && (ix[2 * j + 1] > b || (ix[2 * j + 1] == b && ix[2 * j] > a))))) {
+                d[j + 1] = d[j]; ix[2 * j + 2] = ix[2 * j]; ix[2 * j + 3] = ix[2 * j + 1]; --j;
+            }
+            d[j + 1] = dv; ix[2 * j + 2] = a; ix[2 * j + 3] = b;
+        }
+    }
+}

@@ -93,3 +93,22 @@ def test_batch_of_pairs_is_one_call(cuda_device):
     for k, dk in enumerate(prevs):
         assert_same(ipms[k].download(), orc.sift_match(dk, cur, offset=(1000 * k, 5)))
     assert ipms[1].download()[2] == 0
+
+
+def test_sort_matches_matches_oracle(cuda_device):
+    import torch
+    from bundlefusion_b200 import _capi as capi
+    dev = cuda_device
+    rng = np.random.default_rng(1)
+    P = 40
+    nm = rng.integers(0, 160, P).astype(np.int32); nm[3] = 0; nm[7] = 128; nm[9] = 1
+    d = rng.random((P, 128)).astype(np.float32); ix = rng.integers(0, 1024, (P, 128, 2)).astype(np.uint32)
+    d[5, :60] = np.round(d[5, :60], 1)                                # many equal distances
+    L = capi.lib(); L.bfSetStream(None)
+    t_nm, t_d, t_ix = torch.from_numpy(nm).to(dev), torch.from_numpy(d).to(dev), torch.from_numpy(ix.view(np.int32)).to(dev)
+    torch.cuda.synchronize()
+    capi.check(L.bfSiftSortKeyPointMatches(11, 2, P, t_nm.data_ptr(), t_d.data_ptr(), t_ix.data_ptr()), "bfSiftSortKeyPointMatches")
+    torch.cuda.synchronize()
+    od, oi = orc.sift_sort_matches(11, 2, P, nm, d, ix)
+    np.testing.assert_array_equal(t_d.cpu().numpy(), od)
+    np.testing.assert_array_equal(t_ix.cpu().numpy().view(np.uint32), oi)

@@ -85,3 +85,20 @@ def test_cap_offsets_and_empty():
     assert orc.sift_match(d[:0], d)[2] == 0 and orc.sift_match(d, d[:0])[2] == 0
     z = np.zeros((10, 128), np.uint8)
     assert orc.sift_match(z, d[:10])[2] == 0                                 # all-zero dots never become candidates
+
+
+def test_sort_matches_total_order():
+    rng = np.random.default_rng(0)
+    P = 6
+    nm = np.array([0, 5, 128, 200, 1, 77], np.int32)                  # 200: the counter may exceed the 128 stored
+    d = rng.random((P, 128)).astype(F); ix = rng.integers(0, 1000, (P, 128, 2)).astype(np.uint32)
+    d[2, 10:20] = d[2, 10]                                           # equal distances: ordered by (image-2 feature, image-1 feature)
+    sd, si = orc.sift_sort_matches(4, 1, P, nm, d, ix)               # pair 4 = curFrame is skipped, pair 0 is before startFrame
+    for p in range(P):
+        n = min(int(nm[p]), 128)
+        if p in (0, 4):
+            np.testing.assert_array_equal(sd[p], d[p]); continue
+        order = np.lexsort((ix[p, :n, 0], ix[p, :n, 1], d[p, :n]))
+        np.testing.assert_array_equal(sd[p, :n], d[p, :n][order])
+        np.testing.assert_array_equal(si[p, :n], ix[p, :n][order])
+        np.testing.assert_array_equal(sd[p, n:], d[p, n:])            # entries beyond the count are untouched
