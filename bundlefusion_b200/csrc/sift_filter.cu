@@ -1,0 +1,268 @@
+// sift_filter.cu -- Kabsch match filter for sm_100a.  Implements bfSiftFilterKeyPointMatches of include/bf_sift.h (row a19, first filter).
+//
+// Behavioural source (what, not how): FL/SiftGPU/SIFTImageManager.cu:186-316 (FilterKeyPointMatchesCU), FL/SiftGPU/cuda_kabsch.h:110-502,
+// FL/SiftGPU/cuda_EigenValue.h:9-39.  The per-pair algorithm is inherently sequential (greedy insertion with re-fits), so, as in the
+// reference, one thread walks a pair's raw matches; pairs run in parallel, one warp-sized CTA each, arrays in shared memory.  The
+// device functions below follow oracle/filter_oracle.c operation for operation (this TU is built -fmad=false), including the one
+// documented difference from the reference: a cyclic-Jacobi 3x3 SVD in place of its Numerical-Recipes svdcmp.
+#include "../../include/bf_sift.h"
+#include "bf_common.cuh"
+#include "mat4.cuh"
+
+namespace bf {
+
+extern unsigned long long g_launchCount;
+
+#define MAX_RAW BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW
+#define MAX_FILTERED BF_MAX_MATCHES_PER_IMAGE_PAIR_FILTERED
+#define KABSCH_CONDITION_THRESH 100.0f  /* cuda_kabsch.h:231 */
+
+struct KeyPoint { float px, py, scale, depth; };       // SIFTKeyPoint, FL/SiftGPU/SIFTImageManager.h:22-26
+struct f3 { float x, y, z; };
+
+/* cuda_EigenValue.h:9-39: eigenvalues of a symmetric 3x3, e0 >= e1 >= e2 */
+__device__ void sym_eigenvalues(const float a[9], float e[3]) {
+    const float PI = 3.14159265f;
+    float p = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+    if (p == 0.0f) { e[0] = a[0]; e[1] = a[4]; e[2] = a[8]; return; }
+    const float q = (a[0] + a[4] + a[8]) / 3.0f;
+    p = (a[0] - q) * (a[0] - q) + (a[4] - q) * (a[4] - q) + (a[8] - q) * (a[8] - q) + 2.0f * p;
+    p = sqrtf(p / 6.0f);
+    float B[9];
+    for (int k = 0; k < 9; ++k) B[k] = (a[k] - ((k % 4 == 0) ? q : 0.0f)) * (1.0f / p);
+    const float det = B[0] * (B[4] * B[8] - B[5] * B[7]) - B[1] * (B[3] * B[8] - B[5] * B[6]) + B[2] * (B[3] * B[7] - B[4] * B[6]);
+    const float r = det / 2.0f;
+    float phi;
+    if (r <= -1.0f) phi = PI / 3.0f; else if (r >= 1.0f) phi = 0.0f; else phi = acosf(r) / 3.0f;
+    e[0] = q + 2.0f * p * cosf(phi);
+    e[2] = q + 2.0f * p * cosf(phi + PI * (2.0f / 3.0f));
+    e[1] = 3.0f * q - e[0] - e[2];
+}
+
+/* cyclic-Jacobi SVD of a 3x3 (row-major): H = U diag(s) V^T, s descending, U and V orthonormal (see header) */
+__device__ void svd3(const float H[9], float U[9], float s[3], float V[9]) {
+    float A[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[3 * i + j] = H[i] * H[j] + H[3 + i] * H[3 + j] + H[6 + i] * H[6 + j];      /* H^T H */
+    for (int k = 0; k < 9; ++k) V[k] = (k % 4 == 0) ? 1.0f : 0.0f;
+    const int P[3] = { 0, 0, 1 }, Q[3] = { 1, 2, 2 };
+    for (int sweep = 0; sweep < 10; ++sweep)
+        for (int r = 0; r < 3; ++r) {
+            const int p = P[r], q = Q[r];
+            const float apq = A[3 * p + q];
+            if (fabsf(apq) <= 1e-30f) continue;
+            const float theta = (A[3 * q + q] - A[3 * p + p]) / (2.0f * apq);
+            const float t = ((theta >= 0.0f) ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+            const float c = 1.0f / sqrtf(t * t + 1.0f), sn = t * c;
+            for (int k = 0; k < 3; ++k) { const float akp = A[3 * k + p], akq = A[3 * k + q]; A[3 * k + p] = c * akp - sn * akq; A[3 * k + q] = sn * akp + c * akq; }
+            for (int k = 0; k < 3; ++k) { const float apk = A[3 * p + k], aqk = A[3 * q + k]; A[3 * p + k] = c * apk - sn * aqk; A[3 * q + k] = sn * apk + c * aqk; }
+            for (int k = 0; k < 3; ++k) { const float vkp = V[3 * k + p], vkq = V[3 * k + q]; V[3 * k + p] = c * vkp - sn * vkq; V[3 * k + q] = sn * vkp + c * vkq; }
+        }
+    float ev[3] = { A[0], A[4], A[8] };
+    int ord[3] = { 0, 1, 2 };
+    for (int i = 0; i < 2; ++i) for (int j = i + 1; j < 3; ++j) if (ev[ord[j]] > ev[ord[i]]) { const int tmp = ord[i]; ord[i] = ord[j]; ord[j] = tmp; }
+    float Vs[9];
+    for (int c = 0; c < 3; ++c) { s[c] = sqrtf(fmaxf(ev[ord[c]], 0.0f)); for (int k = 0; k < 3; ++k) Vs[3 * k + c] = V[3 * k + ord[c]]; }
+    for (int k = 0; k < 9; ++k) V[k] = Vs[k];
+    /* U columns: H v / s where s is significant, completed to a right-handed orthonormal basis otherwise */
+    float u[3][3];
+    const float tiny = 1e-7f * s[0];
+    for (int c = 0; c < 3; ++c) {
+        if (s[c] > tiny && s[c] > 0.0f) {
+            for (int k = 0; k < 3; ++k) u[c][k] = (H[3 * k] * V[c] + H[3 * k + 1] * V[3 + c] + H[3 * k + 2] * V[6 + c]) / s[c];
+        } else if (c == 2) {
+            u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1]; u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2]; u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
+        } else if (c == 1) {       /* any unit vector orthogonal to u0 */
+            const float ax = fabsf(u[0][0]), ay = fabsf(u[0][1]), az = fabsf(u[0][2]);
+            float e[3] = { 0, 0, 0 }; e[(ax <= ay && ax <= az) ? 0 : ((ay <= az) ? 1 : 2)] = 1.0f;
+            float w[3] = { u[0][1] * e[2] - u[0][2] * e[1], u[0][2] * e[0] - u[0][0] * e[2], u[0][0] * e[1] - u[0][1] * e[0] };
+            const float l = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+            for (int k = 0; k < 3; ++k) u[1][k] = w[k] / l;
+        } else { u[0][0] = 1.0f; u[0][1] = 0.0f; u[0][2] = 0.0f; }
+    }
+    for (int c = 0; c < 3; ++c) for (int k = 0; k < 3; ++k) U[3 * k + c] = u[c][k];
+}
+
+__device__ float det3(const float m[9]) { return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]); }
+
+/* kabsch(), cuda_kabsch.h:110-176: T (4x4 row-major) with T src ~ tgt; evs = singular values of the covariance, descending */
+__device__ void kabsch(const f3* src, const f3* tgt, unsigned n, float T[16], float evs[3]) {
+    float p0[3] = { 0, 0, 0 }, q0[3] = { 0, 0, 0 };
+    for (unsigned i = 0; i < n; ++i) { p0[0] += src[i].x; p0[1] += src[i].y; p0[2] += src[i].z; q0[0] += tgt[i].x; q0[1] += tgt[i].y; q0[2] += tgt[i].z; }
+    for (int k = 0; k < 3; ++k) { p0[k] /= (float)n; q0[k] /= (float)n; }
+    float H[9] = { 0 };
+    for (unsigned i = 0; i < n; ++i) {
+        const float p[3] = { src[i].x - p0[0], src[i].y - p0[1], src[i].z - p0[2] }, q[3] = { tgt[i].x - q0[0], tgt[i].y - q0[1], tgt[i].z - q0[2] };
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) H[3 * r + c] += p[r] * q[c];
+    }
+    for (int k = 0; k < 9; ++k) H[k] /= (float)n;
+    float U[9], V[9];
+    svd3(H, U, evs, V);
+    /* R = V D U^T, D = diag(1, 1, det(V U^T)) */
+    float VUt[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) VUt[3 * r + c] = V[3 * r] * U[3 * c] + V[3 * r + 1] * U[3 * c + 1] + V[3 * r + 2] * U[3 * c + 2];
+    const float d = (det3(VUt) < 0.0f) ? -1.0f : 1.0f;
+    float R[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[3 * r + c] = V[3 * r] * U[3 * c] + V[3 * r + 1] * U[3 * c + 1] + (V[3 * r + 2] * d) * U[3 * c + 2];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) T[4 * r + c] = R[3 * r + c];
+        T[4 * r + 3] = q0[r] - (R[3 * r] * p0[0] + R[3 * r + 1] * p0[1] + R[3 * r + 2] * p0[2]);
+    }
+    T[12] = T[13] = T[14] = 0.0f; T[15] = 1.0f;
+}
+/* covarianceSVD(), cuda_kabsch.h:178-198 */
+__device__ void covariance_eigs(const f3* pts, unsigned n, float e[3]) {
+    float p0[3] = { 0, 0, 0 };
+    for (unsigned i = 0; i < n; ++i) { p0[0] += pts[i].x; p0[1] += pts[i].y; p0[2] += pts[i].z; }
+    for (int k = 0; k < 3; ++k) p0[k] /= (float)n;
+    float C[9] = { 0 };
+    for (unsigned i = 0; i < n; ++i) {
+        const float p[3] = { pts[i].x - p0[0], pts[i].y - p0[1], pts[i].z - p0[2] };
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C[3 * r + c] += p[r] * p[c];
+    }
+    for (int k = 0; k < 9; ++k) C[k] /= (float)n;
+    sym_eigenvalues(C, e);
+}
+/* ComputeReprojection(), cuda_kabsch.h:381-414 */
+__device__ int compute_reprojection(f3* src, f3* tgt, unsigned n, float* res, float T[16], uint32_t* idx /*[.][2]*/, float* dist) {
+    float evs[3];
+    kabsch(src, tgt, n, T, evs);
+    for (unsigned i = 0; i < n; ++i) {
+        const float dx = (T[0] * src[i].x + T[1] * src[i].y + T[2] * src[i].z + T[3]) - tgt[i].x;
+        const float dy = (T[4] * src[i].x + T[5] * src[i].y + T[6] * src[i].z + T[7]) - tgt[i].y;
+        const float dz = (T[8] * src[i].x + T[9] * src[i].y + T[10] * src[i].z + T[11]) - tgt[i].z;
+        res[i] = dx * dx + dy * dy + dz * dz;
+    }
+    for (unsigned i = 0; i < n; ++i)                /* sortKabschResiduals, :368-377 */
+        for (unsigned j = i; j < n; ++j)
+            if (res[i] > res[j]) {
+                float t = res[i]; res[i] = res[j]; res[j] = t;
+                f3 s = src[i]; src[i] = src[j]; src[j] = s;
+                s = tgt[i]; tgt[i] = tgt[j]; tgt[j] = s;
+                uint32_t a = idx[2 * i], b = idx[2 * i + 1]; idx[2 * i] = idx[2 * j]; idx[2 * i + 1] = idx[2 * j + 1]; idx[2 * j] = a; idx[2 * j + 1] = b;
+                t = dist[i]; dist[i] = dist[j]; dist[j] = t;
+            }
+    const float c1 = evs[0] / evs[1];
+    float e[3];
+    covariance_eigs(src, n, e); const float cp = e[0] / e[1];
+    covariance_eigs(tgt, n, e); const float cq = e[0] / e[1];
+    if (c1 != c1 || cp != cp || cq != cq || fabsf(c1) > KABSCH_CONDITION_THRESH || fabsf(cp) > KABSCH_CONDITION_THRESH || fabsf(cq) > KABSCH_CONDITION_THRESH) return 0;
+    return 1;
+}
+__device__ int add_match(uint32_t ax, uint32_t ay, const KeyPoint* kp, const uint32_t* idx, unsigned cur) {         /* addMatch, :233-247 */
+    for (unsigned i = 0; i < cur; ++i) {
+        const float dix = kp[ax].px - kp[idx[2 * i]].px, diy = kp[ax].py - kp[idx[2 * i]].py;
+        const float djx = kp[ay].px - kp[idx[2 * i + 1]].px, djy = kp[ay].py - kp[idx[2 * i + 1]].py;
+        if (sqrtf(dix * dix + diy * diy) <= 5.0f || sqrtf(djx * djx + djy * djy) <= 5.0f) return 0;
+    }
+    return 1;
+}
+__device__ void key_points_3d(const KeyPoint* kp, const uint32_t* idx, unsigned n, f3* src, f3* tgt, const float* Ki) {   /* getKeySourceAndTargetPoints, :249-321 */
+    for (unsigned i = 0; i < n; ++i)
+        for (int s = 0; s < 2; ++s) {
+            const KeyPoint* k = &kp[idx[2 * i + s]];
+            const float v[3] = { k->depth * k->px, k->depth * k->py, k->depth * 1.0f };
+            f3 o = { Ki[0] * v[0] + Ki[1] * v[1] + Ki[2] * v[2] + Ki[3], Ki[4] * v[0] + Ki[5] * v[1] + Ki[6] * v[2] + Ki[7], Ki[8] * v[0] + Ki[9] * v[1] + Ki[10] * v[2] + Ki[11] };
+            if (s == 0) src[i] = o; else tgt[i] = o;
+        }
+}
+
+/* filterKeyPointMatches, cuda_kabsch.h:417-502.  idx / dist: the pair's raw matches (sorted by distance), modified in place; returns the
+ * number of filtered matches (their indices / distances in the first slots), T = the transform estimate. */
+__device__ unsigned filter_pair(const KeyPoint* kp, uint32_t* idx, float* dist, unsigned numRaw, float T[16], const float* Ki, unsigned minNum, float maxRes2,
+                                f3* src, f3* tgt, float* res) {
+    unsigned i0 = 0, cur = 0;
+    float curMax = 100.0f;
+    int valid = 0;
+    for (int k = 0; k < 16; ++k) T[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+    for (;;) {
+        if (i0 == numRaw || cur >= MAX_FILTERED) {
+            if (cur < minNum || curMax >= maxRes2 || !valid) cur = 0;
+            break;
+        } else if (add_match(idx[2 * i0], idx[2 * i0 + 1], kp, idx, cur)) {
+            idx[2 * cur] = idx[2 * i0]; idx[2 * cur + 1] = idx[2 * i0 + 1]; dist[cur] = dist[i0];
+            ++cur;
+            if (cur >= 3) {
+                key_points_3d(kp, idx, cur, src, tgt, Ki);
+                valid = compute_reprojection(src, tgt, cur, res, T, idx, dist);
+                const int b = valid;
+                float prevT[16]; for (int k = 0; k < 16; ++k) prevT[k] = T[k];
+                curMax = res[cur - 1];
+                if (curMax > maxRes2) {
+                    float lastRes = -1.0f;
+                    for (int i = (int)cur - 1; i >= 3; --i) {
+                        lastRes = res[i];
+                        --cur;
+                        valid = compute_reprojection(src, tgt, cur, res, T, idx, dist);
+                        curMax = res[cur - 1];
+                        if (cur == 3 && (curMax > maxRes2 || (b && !valid))) { ++cur; curMax = lastRes; valid = b; for (int k = 0; k < 16; ++k) T[k] = prevT[k]; break; }
+                        if (curMax < maxRes2) break;
+                    }
+                }
+            }
+        }
+        ++i0;
+    }
+    return cur;
+}
+
+
+struct FilterArgs {
+    unsigned curFrame, startFrame;
+    const KeyPoint* kp; const int* numMatches; const float* dists; const uint2* idxs;
+    int* numFiltered; float* fDists; uint2* fIdxs; float* fT; float* fTinv;
+    float Ki[16]; unsigned minNum; float maxRes2;
+};
+
+__global__ void __launch_bounds__(32)
+sift_filter_kernel(const __grid_constant__ FilterArgs a) {
+    const unsigned p = blockIdx.x + a.startFrame, t = threadIdx.x;
+    if (p == a.curFrame) return;
+    const int raw = a.numMatches[p];
+    if (raw <= 0) { if (t == 0) a.numFiltered[p] = 0; return; }                    // SIFTImageManager.cu:211-216
+    const unsigned n = (unsigned)min(MAX_RAW, raw);
+    __shared__ uint32_t sIdx[2 * MAX_RAW];
+    __shared__ float sDist[MAX_RAW];
+    __shared__ f3 sSrc[MAX_FILTERED], sTgt[MAX_FILTERED];
+    __shared__ float sRes[MAX_FILTERED];
+    __shared__ unsigned sCount;
+    for (unsigned k = t; k < n; k += 32) { const uint2 v = a.idxs[(size_t)p * MAX_RAW + k]; sIdx[2 * k] = v.x; sIdx[2 * k + 1] = v.y; sDist[k] = a.dists[(size_t)p * MAX_RAW + k]; }
+    __syncwarp();
+    if (t == 0) {
+        float T[16], Ti[16];
+        sCount = filter_pair(a.kp, sIdx, sDist, n, T, a.Ki, a.minNum, a.maxRes2, sSrc, sTgt, sRes);
+        mat4_inverse_hd(T, Ti);
+        for (int k = 0; k < 16; ++k) { a.fT[16 * (size_t)p + k] = T[k]; a.fTinv[16 * (size_t)p + k] = Ti[k]; }
+        a.numFiltered[p] = (int)sCount;
+    }
+    __syncwarp();
+    const unsigned c = sCount;
+    if (t < MAX_FILTERED) {                                                        // :243-250
+        const size_t o = (size_t)p * MAX_FILTERED + t;
+        a.fDists[o] = (t < c) ? sDist[t] : 999.0f;
+        a.fIdxs[o] = (t < c) ? make_uint2(sIdx[2 * t], sIdx[2 * t + 1]) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    }
+}
+
+}  // namespace bf
+
+using namespace bf;
+
+BF_API int bfSiftFilterKeyPointMatches(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const BFSIFTKeyPoint* d_keyPoints,
+                                       const int32_t* d_numMatchesPerImagePair, const float* d_matchDistances, const uint32_t* d_matchKeyPointIndices,
+                                       int32_t* d_numFilteredMatchesPerImagePair, float* d_filteredMatchDistances, uint32_t* d_filteredMatchKeyPointIndices,
+                                       float* d_filteredTransforms, float* d_filteredTransformsInv, const float* siftIntrinsicsInv,
+                                       unsigned int minNumMatches, float maxKabschRes2) {
+    if (numFrames <= startFrame) return 0;                                         // SIFTImageManager.cu:267
+    FilterArgs a;
+    a.curFrame = curFrame; a.startFrame = startFrame;
+    a.kp = reinterpret_cast<const KeyPoint*>(d_keyPoints); a.numMatches = d_numMatchesPerImagePair; a.dists = d_matchDistances;
+    a.idxs = reinterpret_cast<const uint2*>(d_matchKeyPointIndices);
+    a.numFiltered = d_numFilteredMatchesPerImagePair; a.fDists = d_filteredMatchDistances; a.fIdxs = reinterpret_cast<uint2*>(d_filteredMatchKeyPointIndices);
+    a.fT = d_filteredTransforms; a.fTinv = d_filteredTransformsInv;
+    for (int k = 0; k < 16; ++k) a.Ki[k] = siftIntrinsicsInv[k];
+    a.minNum = minNumMatches; a.maxRes2 = maxKabschRes2;
+    ++g_launchCount;
+    sift_filter_kernel<<<numFrames - startFrame, 32, 0, stream()>>>(a);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}

@@ -333,3 +333,39 @@ def make_sift_pair(n1: int, n2: int, n_common: int, noise: float = 0.05, seed: i
     inv1, inv2 = np.argsort(p1), np.argsort(p2)
     truth = np.stack([inv1[:n_common], inv2[:n_common]], 1)
     return np.ascontiguousarray(d1[p1]), np.ascontiguousarray(d2[p2]), truth
+
+
+# ---- synthetic key points + raw matches for the Kabsch filter (row a19) --------------------------------------------------
+def make_filter_problem(n_pairs: int = 6, n_inliers: int = 40, n_outliers: int = 12, noise: float = 0.002, seed: int = 0, W: int = 640, H: int = 480):
+    """The current frame plus n_pairs earlier frames observing the same 3-D points.  Returns key points [K,4] (x, y, scale, depth), the
+    manager-layout raw matches of every pair (earlier frame p -> current frame), already sorted by distance, the inverse intrinsics
+    and the ground-truth transforms T_p with T_p * X_p = X_cur."""
+    rng = np.random.default_rng(seed)
+    fx = 525.0 * W / 640.0; mx, my = (W - 1) / 2.0, (H - 1) / 2.0
+    K = np.array([[fx, 0, mx, 0], [0, fx, my, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float64)
+    Kinv = np.linalg.inv(K)
+    n = n_inliers + n_outliers
+    P = n_pairs + 1
+    cur = n_pairs                                               # the current frame is the last image
+    keys = np.zeros((P * n, 4), np.float32)
+    num = np.zeros(P, np.int32); dists = np.full((P, 128), 999.0, np.float32); idxs = np.full((P, 128, 2), 0xFFFFFFFF, np.uint32)
+    # points in the current frame: spread over the image, well separated (> 5 px), depths 0.8 .. 3 m
+    gx, gy = np.meshgrid(np.linspace(30, W - 30, 10), np.linspace(30, H - 30, 8))
+    pix = np.stack([gx.ravel(), gy.ravel()], 1)[rng.permutation(80)[:n]] + rng.uniform(-6, 6, (n, 2))
+    z = rng.uniform(0.8, 3.0, n)
+    Xc = np.stack([(pix[:, 0] - mx) / fx * z, (pix[:, 1] - my) / fx * z, z], 1)
+    keys[cur * n:(cur + 1) * n] = np.c_[pix, np.ones(n), z]
+    T_gt = np.zeros((P, 4, 4)); T_gt[cur] = np.eye(4)
+    for p in range(n_pairs):
+        T = se3_exp(rng.standard_normal(3) * 0.08, rng.standard_normal(3) * 0.15)          # X_cur = T X_p
+        T_gt[p] = T
+        Ti = np.linalg.inv(T)
+        Xp = Xc @ Ti[:3, :3].T + Ti[:3, 3] + rng.standard_normal((n, 3)) * noise
+        Xp[n_inliers:] += rng.uniform(0.15, 0.5, (n_outliers, 3)) * rng.choice([-1, 1], (n_outliers, 3))    # gross outliers
+        keys[p * n:(p + 1) * n] = np.c_[Xp[:, 0] / Xp[:, 2] * fx + mx, Xp[:, 1] / Xp[:, 2] * fx + my, np.ones(n), Xp[:, 2]]
+        order = rng.permutation(n)
+        num[p] = n
+        dists[p, :n] = np.sort(rng.uniform(0.05, 0.6, n)).astype(np.float32)
+        idxs[p, :n, 0] = p * n + order; idxs[p, :n, 1] = cur * n + order
+    return {"keys": keys, "num": num, "dists": dists, "idxs": idxs, "Kinv": Kinv.astype(np.float32), "T_gt": T_gt, "cur": cur, "n": n,
+            "n_inliers": n_inliers, "P": P}

@@ -27,6 +27,10 @@ extern "C" {
 #endif
 
 #define BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW 128     /* FL/GlobalDefines.h:8 */
+#define BF_MAX_MATCHES_PER_IMAGE_PAIR_FILTERED 25 /* FL/GlobalDefines.h:9 */
+
+/* FL/SiftGPU/SIFTImageManager.h:22-26 */
+typedef struct BFSIFTKeyPoint { float pos[2]; float scale; float depth; } BFSIFTKeyPoint;
 
 /* FL/SiftGPU/SIFTImageManager.h:38-42 */
 typedef struct BFImagePairMatch {
@@ -54,6 +58,21 @@ int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distmax, flo
  * ordered by (image-2 feature, image-1 feature), so the result does not depend on the append order.  Asynchronous. */
 int bfSiftSortKeyPointMatches(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const int32_t* d_numMatchesPerImagePair,
                               float* d_matchDistances, uint32_t* d_matchKeyPointIndices);
+
+/* SIFTImageManager::FilterKeyPointMatchesCU(curFrame, startFrame, numFrames, siftIntrinsicsInv, minNumMatches, maxKabschRes2)
+ * (FL/SiftGPU/SIFTImageManager.cu:186-316; filterKeyPointMatches FL/SiftGPU/cuda_kabsch.h:417-502): for every image pair p in
+ * [startFrame, numFrames), p != curFrame, walks the distance-sorted raw matches, greedily grows a geometrically consistent subset
+ * (<= 25 matches: Kabsch re-fit after every insertion, 5-pixel proximity rule, worst residuals dropped until max residual^2 <
+ * maxKabschRes2, three condition numbers <= 100) and writes the filtered matches (ascending residual), their count, the rigid transform
+ * image p -> current image and its inverse.  Arrays are the manager's (raw: [p * 128 + k], filtered: [p * 25 + k], transforms [p][16]);
+ * key-point indices are global indices into d_keyPoints; siftIntrinsicsInv is a HOST 4x4.  The 3x3 SVD inside the Kabsch fit is a
+ * cyclic-Jacobi one (the reference: Numerical-Recipes svdcmp) -- same rotation except that a reflection is resolved on the smallest
+ * singular value.  Asynchronous. */
+int bfSiftFilterKeyPointMatches(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const BFSIFTKeyPoint* d_keyPoints,
+                                const int32_t* d_numMatchesPerImagePair, const float* d_matchDistances, const uint32_t* d_matchKeyPointIndices,
+                                int32_t* d_numFilteredMatchesPerImagePair, float* d_filteredMatchDistances, uint32_t* d_filteredMatchKeyPointIndices,
+                                float* d_filteredTransforms, float* d_filteredTransformsInv, const float* siftIntrinsicsInv,
+                                unsigned int minNumMatches, float maxKabschRes2);
 
 /* device scratch the matcher holds (rowResult / rowDist per job); released by bfSiftReleaseWorkspace */
 size_t bfSiftWorkspaceBytes(void);

@@ -458,3 +458,21 @@ def sift_sort_matches(curFrame, startFrame, numFrames, numMatches, dists, idxs):
     L.orc_sift_sort_matches.restype = None
     L.orc_sift_sort_matches(curFrame, startFrame, numFrames, nm.ctypes.data, d.ctypes.data, ix.ctypes.data)
     return d, ix
+
+
+# ---- Kabsch match filter (oracle/filter_oracle.c) ---------------------------------------------------------------------------
+def sift_filter_matches(curFrame, startFrame, numFrames, keyPoints, numMatches, dists, idxs, siftIntrinsicsInv, minNumMatches=5, maxKabschRes2=0.0004):
+    """FilterKeyPointMatchesCU.  keyPoints [K,4] float32 (x, y, scale, depth); dists [P,128]; idxs [P,128,2] uint32 (global key indices).
+    Returns (numFiltered [P], fDists [P,25], fIdxs [P,25,2], T [P,4,4], Tinv [P,4,4])."""
+    L = lib()
+    kp = np.ascontiguousarray(keyPoints, np.float32); nm = np.ascontiguousarray(numMatches, np.int32)
+    d = np.ascontiguousarray(dists, np.float32); ix = np.ascontiguousarray(idxs, np.uint32)
+    Ki = np.ascontiguousarray(siftIntrinsicsInv, np.float32)
+    P = len(nm)
+    nf = np.zeros(P, np.int32); fd = np.zeros((P, 25), np.float32); fi = np.zeros((P, 25, 2), np.uint32)
+    T = np.zeros((P, 4, 4), np.float32); Ti = np.zeros((P, 4, 4), np.float32)
+    L.orc_sift_filter_matches.argtypes = [C.c_uint, C.c_uint, C.c_uint] + [C.c_void_p] * 10 + [C.c_uint, C.c_float]
+    L.orc_sift_filter_matches.restype = None
+    L.orc_sift_filter_matches(curFrame, startFrame, numFrames, kp.ctypes.data, nm.ctypes.data, d.ctypes.data, ix.ctypes.data, nf.ctypes.data, fd.ctypes.data,
+                              fi.ctypes.data, T.ctypes.data, Ti.ctypes.data, Ki.ctypes.data, minNumMatches, maxKabschRes2)
+    return nf, fd, fi, T, Ti
