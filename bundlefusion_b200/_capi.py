@@ -112,7 +112,7 @@ CACHE_SYMBOLS = ["bfCacheStoreFrame"]
 INGEST_SYMBOLS = ["bfIngestFrame"]
 BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updateTrajectoryCU", "bfTrajectorySelectReintegration"]
 
-SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftSortKeyPointMatches", "bfSiftFilterKeyPointMatches", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
+SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftSortKeyPointMatches", "bfSiftFilterKeyPointMatches", "bfSiftAddCurrToResiduals", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
 
 SOLVER_SYMBOLS = [
     "solveBundlingStub", "buildVariablesToCorrespondencesTableCUDA", "evalMaxResidual", "countHighResiduals", "collectHighResiduals",
@@ -294,6 +294,7 @@ def lib() -> C.CDLL:
     L.bfSiftMatchBatch.argtypes = [P(BFSiftMatchJob), C.c_int, C.c_float, C.c_float]
     L.bfSiftSortKeyPointMatches.argtypes = [C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
     L.bfSiftFilterKeyPointMatches.argtypes = [C.c_uint, C.c_uint, C.c_uint] + [vp] * 9 + [P(C.c_float), C.c_uint, C.c_float]
+    L.bfSiftAddCurrToResiduals.argtypes = [C.c_uint, C.c_uint, C.c_uint] + [vp] * 6 + [P(C.c_float)]
     L.bfSiftWorkspaceBytes.restype = C.c_size_t
     _lib = L
     return L

@@ -243,9 +243,73 @@ sift_filter_kernel(const __grid_constant__ FilterArgs a) {
     }
 }
 
+struct AddArgs {
+    unsigned curFrame, startFrame, numFrames;
+    BFEntryJ* glob; uint2* globIdx; int* globNum; const int* numFiltered; const uint2* fIdxs; const KeyPoint* kp;
+    float Ki[16];
+};
+// AddCurrToResidualsCU_Kernel (SIFTImageManager.cu:610-655), one CTA: slots are handed out in ascending pair order
+__global__ void __launch_bounds__(1024)
+sift_add_residuals_kernel(const __grid_constant__ AddArgs a) {
+    __shared__ int sBase;             // running base while pairs are walked in chunks of blockDim.x
+    __shared__ int sScan[1024];
+    const unsigned t = threadIdx.x;
+    if (t == 0) sBase = *a.globNum;
+    __syncthreads();
+    for (unsigned p0 = a.startFrame; p0 < a.numFrames; p0 += blockDim.x) {
+        const unsigned p = p0 + t;
+        int cnt = 0;
+        if (p < a.numFrames && p != a.curFrame) cnt = a.numFiltered[p];
+        sScan[t] = cnt;
+        __syncthreads();
+        for (unsigned o = 1; o < blockDim.x; o <<= 1) {                 // inclusive Hillis-Steele scan
+            const int v = (t >= o) ? sScan[t - o] : 0;
+            __syncthreads();
+            sScan[t] += v;
+            __syncthreads();
+        }
+        const int base = sBase + sScan[t] - cnt;
+        for (int k = 0; k < cnt; ++k) {
+            const uint2 ij = a.fIdxs[(size_t)p * MAX_FILTERED + k];
+            BFEntryJ e;
+            e.imgIdx_i = p; e.imgIdx_j = a.curFrame;
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const KeyPoint kq = a.kp[s2 == 0 ? ij.x : ij.y];
+                const float v0 = kq.depth * kq.px, v1 = kq.depth * kq.py, v2 = kq.depth * 1.0f;
+                float* o = (s2 == 0) ? e.pos_i : e.pos_j;
+                o[0] = a.Ki[0] * v0 + a.Ki[1] * v1 + a.Ki[2] * v2 + a.Ki[3];
+                o[1] = a.Ki[4] * v0 + a.Ki[5] * v1 + a.Ki[6] * v2 + a.Ki[7];
+                o[2] = a.Ki[8] * v0 + a.Ki[9] * v1 + a.Ki[10] * v2 + a.Ki[11];
+            }
+            a.glob[base + k] = e;
+            a.globIdx[base + k] = ij;
+        }
+        __syncthreads();
+        if (t == blockDim.x - 1) sBase += sScan[t];
+        __syncthreads();
+    }
+    if (t == 0) *a.globNum = sBase;
+}
+
 }  // namespace bf
 
 using namespace bf;
+
+BF_API int bfSiftAddCurrToResiduals(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, BFEntryJ* d_globMatches,
+                                    uint32_t* d_globMatchesKeyPointIndices, int32_t* d_globNumResiduals, const int32_t* d_currNumFilteredMatchesPerImagePair,
+                                    const uint32_t* d_currFilteredMatchKeyPointIndices, const BFSIFTKeyPoint* d_keyPoints, const float* colorIntrinsicsInv) {
+    if (numFrames <= startFrame) return 0;
+    AddArgs a;
+    a.curFrame = curFrame; a.startFrame = startFrame; a.numFrames = numFrames;
+    a.glob = d_globMatches; a.globIdx = reinterpret_cast<uint2*>(d_globMatchesKeyPointIndices); a.globNum = d_globNumResiduals;
+    a.numFiltered = d_currNumFilteredMatchesPerImagePair; a.fIdxs = reinterpret_cast<const uint2*>(d_currFilteredMatchKeyPointIndices);
+    a.kp = reinterpret_cast<const KeyPoint*>(d_keyPoints);
+    for (int k = 0; k < 16; ++k) a.Ki[k] = colorIntrinsicsInv[k];
+    ++g_launchCount;
+    sift_add_residuals_kernel<<<1, 1024, 0, stream()>>>(a);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
 
 BF_API int bfSiftFilterKeyPointMatches(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const BFSIFTKeyPoint* d_keyPoints,
                                        const int32_t* d_numMatchesPerImagePair, const float* d_matchDistances, const uint32_t* d_matchKeyPointIndices,

@@ -22,6 +22,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "bf_solver.h"      /* BFEntryJ */
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -73,6 +75,16 @@ int bfSiftFilterKeyPointMatches(unsigned int curFrame, unsigned int startFrame, 
                                 int32_t* d_numFilteredMatchesPerImagePair, float* d_filteredMatchDistances, uint32_t* d_filteredMatchKeyPointIndices,
                                 float* d_filteredTransforms, float* d_filteredTransformsInv, const float* siftIntrinsicsInv,
                                 unsigned int minNumMatches, float maxKabschRes2);
+
+/* SIFTImageManager::AddCurrToResidualsCU(curFrame, startFrame, numFrames, colorIntrinsicsInv) (FL/SiftGPU/SIFTImageManager.cu:610-685):
+ * appends the filtered matches of every pair p in [startFrame, numFrames), p != curFrame, to the global correspondence list as
+ * EntryJ { p, curFrame, Kinv (d_i (x_i, y_i, 1)), Kinv (d_j (x_j, y_j, 1)) } (+ their key-point index pairs) and advances
+ * *d_globNumResiduals -- the solver's input.  The reference reserves each pair's slots with an atomicAdd (pair order race-dependent)
+ * and copies the counter to the host; here pairs are appended in ascending pair order and the counter stays on the device.
+ * colorIntrinsicsInv: HOST 4x4.  Asynchronous. */
+int bfSiftAddCurrToResiduals(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, BFEntryJ* d_globMatches,
+                             uint32_t* d_globMatchesKeyPointIndices, int32_t* d_globNumResiduals, const int32_t* d_currNumFilteredMatchesPerImagePair,
+                             const uint32_t* d_currFilteredMatchKeyPointIndices, const BFSIFTKeyPoint* d_keyPoints, const float* colorIntrinsicsInv);
 
 /* device scratch the matcher holds (rowResult / rowDist per job); released by bfSiftReleaseWorkspace */
 size_t bfSiftWorkspaceBytes(void);

@@ -240,3 +240,23 @@ ORC_API void orc_sift_filter_matches(unsigned curFrame, unsigned startFrame, uns
         }
     }
 }
+
+/* AddCurrToResidualsCU_Kernel (FL/SiftGPU/SIFTImageManager.cu:610-655) with the pairs appended in ascending order (the reference's
+ * atomicAdd makes the pair order race-dependent).  entries: EntryJ = { uint32 i, uint32 j, float pos_i[3], float pos_j[3] } (32 bytes). */
+ORC_API int orc_sift_add_residuals(unsigned curFrame, unsigned startFrame, unsigned numFrames, uint8_t* entries, uint32_t* entryIdx, int numResiduals,
+                                   const int32_t* numFiltered, const uint32_t* fIdxs, const KeyPoint* kp, const float* Ki) {
+    for (unsigned p = startFrame; p < numFrames; ++p) {
+        if (p == curFrame) continue;
+        for (int k = 0; k < numFiltered[p]; ++k) {
+            const uint32_t* ij = &fIdxs[2 * ((size_t)p * MAX_FILTERED + k)];
+            f3 s, t;
+            key_points_3d(kp, ij, 1, &s, &t, Ki);
+            uint8_t* e = entries + 32 * (size_t)numResiduals;
+            const uint32_t ii = p, jj = curFrame;
+            memcpy(e, &ii, 4); memcpy(e + 4, &jj, 4); memcpy(e + 8, &s, 12); memcpy(e + 20, &t, 12);
+            entryIdx[2 * numResiduals] = ij[0]; entryIdx[2 * numResiduals + 1] = ij[1];
+            ++numResiduals;
+        }
+    }
+    return numResiduals;
+}

@@ -476,3 +476,16 @@ def sift_filter_matches(curFrame, startFrame, numFrames, keyPoints, numMatches, 
     L.orc_sift_filter_matches(curFrame, startFrame, numFrames, kp.ctypes.data, nm.ctypes.data, d.ctypes.data, ix.ctypes.data, nf.ctypes.data, fd.ctypes.data,
                               fi.ctypes.data, T.ctypes.data, Ti.ctypes.data, Ki.ctypes.data, minNumMatches, maxKabschRes2)
     return nf, fd, fi, T, Ti
+
+
+def sift_add_residuals(curFrame, startFrame, numFrames, numFiltered, fIdxs, keyPoints, colorIntrinsicsInv, capacity=None):
+    """AddCurrToResidualsCU: returns (EntryJ structured array, key index pairs [n,2])."""
+    L = lib()
+    nf = np.ascontiguousarray(numFiltered, np.int32); fi = np.ascontiguousarray(fIdxs, np.uint32); kp = np.ascontiguousarray(keyPoints, np.float32)
+    Ki = np.ascontiguousarray(colorIntrinsicsInv, np.float32)
+    cap = capacity or int(nf.clip(0).sum()) + 1
+    ent = np.zeros(cap, dtype=[("i", "<u4"), ("j", "<u4"), ("pi", "<f4", 3), ("pj", "<f4", 3)]); eidx = np.zeros((cap, 2), np.uint32)
+    L.orc_sift_add_residuals.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_sift_add_residuals.restype = C.c_int
+    n = L.orc_sift_add_residuals(curFrame, startFrame, numFrames, ent.ctypes.data, eidx.ctypes.data, 0, nf.ctypes.data, fi.ctypes.data, kp.ctypes.data, Ki.ctypes.data)
+    return ent[:n].copy(), eidx[:n].copy()

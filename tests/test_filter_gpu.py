@@ -76,3 +76,44 @@ def test_sort_then_filter_chain(cuda_device):
     sd, si = orc.sift_sort_matches(pb["cur"], 0, pb["P"], pb["num"], d, ix)
     o = orc.sift_filter_matches(pb["cur"], 0, pb["P"], pb["keys"], pb["num"], sd, si, pb["Kinv"])
     assert_same(g, o, range(pb["P"] - 1))
+
+
+def test_filter_to_residuals_to_bundle_adjustment(cuda_device):
+    """The chain the path exists for: raw matches -> sort -> Kabsch filter -> AddCurrToResiduals -> sparse BA.  The EntryJ list equals the
+    oracle's bit for bit, and the solver recovers the poses the correspondences were generated from."""
+    import torch
+    from bundlefusion_b200.solver import CUDASolverBundling
+    dev = cuda_device
+    pb = synth.make_filter_problem(n_pairs=6, n_inliers=45, n_outliers=10, noise=0.001, seed=11)
+    P, cur = pb["P"], pb["cur"]
+    g = gpu_filter(dev, pb, pb["num"], pb["dists"], pb["idxs"], pb["keys"], sort_first=True)
+    L = capi.lib(); L.bfSetStream(None)
+    nf, fi = torch.from_numpy(g[0].copy()).to(dev), torch.from_numpy(g[2].view(np.int32).copy()).to(dev)
+    nf[cur] = 0
+    keys = torch.from_numpy(pb["keys"]).to(dev)
+    cap = 25 * P
+    ent = torch.zeros(cap * 32, dtype=torch.uint8, device=dev); eidx = torch.zeros(cap, 2, dtype=torch.int32, device=dev); cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    Ki = (C.c_float * 16)(*pb["Kinv"].reshape(-1).tolist())
+    torch.cuda.synchronize()
+    capi.check(L.bfSiftAddCurrToResiduals(cur, 0, P, ent.data_ptr(), eidx.data_ptr(), cnt.data_ptr(), nf.data_ptr(), fi.data_ptr(), keys.data_ptr(), Ki), "add")
+    torch.cuda.synchronize()
+    n = int(cnt.item())
+    nf_h = g[0].copy(); nf_h[cur] = 0
+    o_ent, o_idx = orc.sift_add_residuals(cur, 0, P, nf_h, g[2], pb["keys"], pb["Kinv"])
+    assert n == len(o_ent) > 60
+    np.testing.assert_array_equal(ent.cpu().numpy()[:32 * n], o_ent.view(np.uint8).reshape(-1))
+    np.testing.assert_array_equal(eidx.cpu().numpy()[:n].view(np.uint32), o_idx)
+    # bundle adjustment on those correspondences: image k's pose = T_k (maps frame k into the current frame's coordinates), image 0 fixed
+    gt = pb["T_gt"]
+    rot0 = np.zeros((P, 3), np.float32); tr0 = np.zeros((P, 3), np.float32)
+    rng = np.random.default_rng(1)
+    for k in range(P):
+        Tk = gt[k] if k == 0 else synth.se3_exp(rng.standard_normal(3) * 0.01, rng.standard_normal(3) * 0.02) @ gt[k]
+        r, t = synth.se3_log(Tk); rot0[k], tr0[k] = r, t
+    rot, trans = torch.from_numpy(rot0.copy()).to(dev), torch.from_numpy(tr0.copy()).to(dev)
+    s = CUDASolverBundling(P, 1000 * P, dev)
+    s.solve(ent, n, torch.ones(P, dtype=torch.int32, device=dev), P, 4, 100, [1.0] * 4, d_rotationAnglesUnknowns=rot, d_translationUnknowns=trans)
+    torch.cuda.synchronize()
+    for k in range(P):
+        Tk = synth.se3_exp(rot.cpu().numpy()[k], trans.cpu().numpy()[k])
+        np.testing.assert_allclose(Tk, gt[k], atol=1e-2)

@@ -62,3 +62,21 @@ def test_filter_rejects_bad_sets():
     nf, fd, fi, T, Ti = orc.sift_filter_matches(pb["cur"], 0, pb["P"], keys, num, pb["dists"], idxs, pb["Kinv"])
     assert nf[0] == 0 and nf[1] == 0 and nf[2] == 0
     assert np.all(fd[:3] == 999.0)
+
+
+def test_add_residuals_builds_the_solver_input():
+    pb = synth.make_filter_problem(n_pairs=4, n_inliers=30, n_outliers=5, seed=5)
+    nf, fd, fi, T, Ti = orc.sift_filter_matches(pb["cur"], 0, pb["P"], pb["keys"], pb["num"], pb["dists"], pb["idxs"], pb["Kinv"])
+    ent, eidx = orc.sift_add_residuals(pb["cur"], 0, pb["P"], nf, fi, pb["keys"], pb["Kinv"])
+    assert len(ent) == int(nf[:pb["cur"]].sum())
+    k = 0
+    for p in range(pb["P"] - 1):                                       # ascending pair order, filtered order within a pair
+        for m in range(int(nf[p])):
+            assert ent["i"][k] == p and ent["j"][k] == pb["cur"]
+            np.testing.assert_array_equal(eidx[k], fi[p, m])
+            np.testing.assert_allclose(ent["pi"][k], points3d(pb, fi[p, m:m + 1, 0])[0], atol=1e-5)
+            np.testing.assert_allclose(ent["pj"][k], points3d(pb, fi[p, m:m + 1, 1])[0], atol=1e-5)
+            # the filter's transform maps the source point onto the target point within the residual bound
+            r = T[p][:3, :3].astype(np.float64) @ ent["pi"][k] + T[p][:3, 3] - ent["pj"][k]
+            assert r @ r < 0.0004
+            k += 1
