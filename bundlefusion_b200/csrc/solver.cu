@@ -11,7 +11,7 @@
 //    6x6 block (block-sparse J^T J, both (i,j) and (j,i) stored so a row never needs a transpose), and a PCG
 //    iteration is a block-sparse mat-vec over ~144 B per image pair -- ~25x less traffic, L2-resident;
 //  * one persistent cooperative kernel runs a whole Gauss-Newton iteration: pose -> matrix, block build, row
-//    reduction, PCG init, all PCG iterations (3 grid barriers each), Lie update, convergence test.  The early-outs
+//    reduction, PCG init, all PCG iterations (2 grid barriers each), Lie update, convergence test.  The early-outs
 //    (|p.Ap| < 5e-7, max|delta| < 0.005) are evaluated on the device; later GN launches see a "done" flag;
 //  * every floating-point reduction has a fixed shape (per-segment serial sums, fixed warp trees, partials summed
 //    in CTA order), so results are run-to-run deterministic -- the reference's atomics are not.
