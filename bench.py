@@ -373,7 +373,7 @@ def run_reference(args):
     wall = time.perf_counter() - t0
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
            "steps": K, "warmup": Wm, "ms_per_step": round(1e3 / base["value"], 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, note="CPU arm: oracle port of the reference algorithm (the reference ships no CPU path and its CUDA does not build here)"),
+           "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, note="CPU arm: oracle port of the reference algorithm on the host cores (the reference ships no CPU path of its own; its CUDA path, rebuilt for sm_100a, is timed on the same box in profiles/r1_reference_cuda_same_box.md)"),
            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": round(wall, 1)}
     print(json.dumps(out))
 

@@ -219,6 +219,7 @@ struct SiftWs {
     SiftJobDev* dJobs = nullptr; size_t jobCap = 0;
     SiftJobDev* hJobs = nullptr;                 // pinned staging for the job table; evCopied = its last upload has left it
     cudaEvent_t evCopied = nullptr;
+    cudaEvent_t evDone = nullptr;                // the last batch's column pass has finished (the workspace is shared by every caller)
     int* rowResult = nullptr; float* rowDist = nullptr; size_t rowCap = 0;
 };
 static SiftWs g_sift;
@@ -238,6 +239,8 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
         if (jobs[i].num1 >= (1 << 24) || jobs[i].num2 >= (1 << 24)) return (int)cudaErrorInvalidValue;       // index field of the packed key
     }
     cudaStream_t s = stream();
+    if (!g_sift.evDone) BF_CHECK(cudaEventCreateWithFlags(&g_sift.evDone, cudaEventDisableTiming));
+    BF_CHECK(cudaStreamWaitEvent(s, g_sift.evDone, 0));       // a previous batch (possibly on another stream) still owns rowResult / the job table
     if ((size_t)numJobs > g_sift.jobCap) {
         if (g_sift.dJobs) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dJobs)); BF_CHECK(cudaFreeHost(g_sift.hJobs)); }
         g_sift.jobCap = (size_t)numJobs * 2;
@@ -276,6 +279,7 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
     BF_CHECK(cudaGetLastError());
     sift_best_kernel<true><<<dim3(gx2, numJobs), 128, 0, s>>>(g_sift.dJobs + numJobs, distmax, ratiomax);
     BF_CHECK(cudaGetLastError());
+    BF_CHECK(cudaEventRecord(g_sift.evDone, s));
     return 0;
 }
 
@@ -298,6 +302,7 @@ BF_API int bfSiftReleaseWorkspace(void) {
     cudaFree(g_sift.dJobs); cudaFree(g_sift.rowResult); cudaFree(g_sift.rowDist);
     if (g_sift.hJobs) cudaFreeHost(g_sift.hJobs);
     if (g_sift.evCopied) cudaEventDestroy(g_sift.evCopied);
+    if (g_sift.evDone) cudaEventDestroy(g_sift.evDone);
     g_sift = SiftWs();
     return 0;
 }
