@@ -360,7 +360,7 @@ def cpu_arm(steps, warmup, quiet=False, n_reint=None):
     return {"value": round(1.0 / per_frame, 4), "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": f"{steps} frame(s) x ({n_re} re-integrations + 1 integrate + GC) at 640x480 scaled to {WORKLOAD['reintegrations_per_frame']} re-integrations, "
                       f"+ 1 local and 1 global BA solve / {WORKLOAD['chunk']} frames; TSDF {t_tsdf:.2f} s per sampled frame, BA {t_ba:.2f} s per chunk; "
-                      f"OpenMP threads = {cores} on the integrate stencil, other stages single-threaded as restated"}
+                      f"OpenMP threads = {cores} on the integrate stencil and the alloc ray walk; hash insertions, compactify, GC and the bundle adjustment single-threaded as restated"}
 
 
 def run_reference(args):

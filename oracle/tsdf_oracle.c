@@ -41,6 +41,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../include/bf_tsdf.h"
 
@@ -270,19 +273,19 @@ static inline int owns_block(const BFHashParams* hp, i3 b) {
 
 /* allocKernel: CUDASceneRepHashSDF.cu:165-251 (d_bitMask == NULL: streaming is disabled
  * for BundleFusion, zParametersDefault.txt:99). */
-ORC_API unsigned orc_tsdf_alloc(BFHashDataStruct* hd, const BFHashParams* hp,
-                            const float* depth, const BFDepthCameraParams* cp) {
-    const unsigned W = cp->m_imageWidth, H = cp->m_imageHeight;
+/* the in-frustum (owned) blocks one pixel's DDA visits, in walk order (allocKernel, CUDASceneRepHashSDF.cu:165-251) */
+static unsigned pixel_blocks(const BFHashParams* hp, const float* depth, const BFDepthCameraParams* cp, unsigned x, unsigned y, i3* out /*[1024]*/) {
+    const unsigned W = cp->m_imageWidth;
     const float vs = hp->m_virtualVoxelSize;
-    unsigned dropped = 0;
-    for (unsigned y = 0; y < H; ++y) for (unsigned x = 0; x < W; ++x) {
+    unsigned n = 0;
+    {
         float d = depth[y * W + x];
-        if (d == ORC_MINF || d == 0.0f) continue;
-        if (d >= hp->m_maxIntegrationDistance) continue;
+        if (d == ORC_MINF || d == 0.0f) return n;
+        if (d >= hp->m_maxIntegrationDistance) return n;
         float t = truncation(hp, d);
         float minDepth = fminf(hp->m_maxIntegrationDistance, d - t);
         float maxDepth = fminf(hp->m_maxIntegrationDistance, d + t);
-        if (minDepth >= maxDepth) continue;
+        if (minDepth >= maxDepth) return n;
 
         f3 rayMin = xform(&hp->m_rigidTransform, depth_to_skeleton(cp, x, y, minDepth));
         f3 rayMax = xform(&hp->m_rigidTransform, depth_to_skeleton(cp, x, y, maxDepth));
@@ -312,7 +315,7 @@ ORC_API unsigned orc_tsdf_alloc(BFHashDataStruct* hd, const BFHashParams* hp,
         if (boundary.z - rayMin.z == 0.0f) { tMax.z = INFINITY; tDelta.z = INFINITY; }
 
         for (unsigned iter = 0; iter < 1024; ++iter) {
-            if (block_in_frustum(hp, cp, cur) && owns_block(hp, cur)) dropped += (unsigned)alloc_block(hd, hp, cur);
+            if (block_in_frustum(hp, cp, cur) && owns_block(hp, cur) && n < 1024) out[n++] = cur;
             if (tMax.x < tMax.y && tMax.x < tMax.z) {
                 cur.x = f2i((float)cur.x + step.x);
                 if (cur.x == bound.x) break;
@@ -328,6 +331,43 @@ ORC_API unsigned orc_tsdf_alloc(BFHashDataStruct* hd, const BFHashParams* hp,
             }
         }
     }
+    return n;
+}
+
+ORC_API unsigned orc_tsdf_alloc(BFHashDataStruct* hd, const BFHashParams* hp,
+                            const float* depth, const BFDepthCameraParams* cp) {
+    const unsigned W = cp->m_imageWidth, H = cp->m_imageHeight;
+    unsigned dropped = 0;
+#ifdef _OPENMP
+    /* timing build (liboracle_fast.so, bench.py's CPU arm): every host thread walks rows and collects the blocks its pixels visit;
+     * the insertions -- the only part that touches the table -- then run in one thread.  Same SET of blocks as the serial walk (the
+     * slot a block receives may differ, which no comparison keys on; the drop count differs only in an over-full table). */
+    const int nt = omp_get_max_threads();
+    i3** lists = (i3**)calloc((size_t)nt, sizeof(i3*));
+    size_t* cnt = (size_t*)calloc((size_t)nt, sizeof(size_t)); size_t* cap = (size_t*)calloc((size_t)nt, sizeof(size_t));
+#pragma omp parallel
+    {
+        const int t = omp_get_thread_num();
+        i3 buf[1024];
+#pragma omp for schedule(dynamic, 4)
+        for (unsigned y = 0; y < H; ++y) for (unsigned x = 0; x < W; ++x) {
+            const unsigned n = pixel_blocks(hp, depth, cp, x, y, buf);
+            for (unsigned k = 0; k < n; ++k) {
+                if (cnt[t] && lists[t][cnt[t] - 1].x == buf[k].x && lists[t][cnt[t] - 1].y == buf[k].y && lists[t][cnt[t] - 1].z == buf[k].z) continue;
+                if (cnt[t] == cap[t]) { cap[t] = cap[t] ? 2 * cap[t] : 4096; lists[t] = (i3*)realloc(lists[t], cap[t] * sizeof(i3)); }
+                lists[t][cnt[t]++] = buf[k];
+            }
+        }
+    }
+    for (int t = 0; t < nt; ++t) { for (size_t k = 0; k < cnt[t]; ++k) dropped += (unsigned)alloc_block(hd, hp, lists[t][k]); free(lists[t]); }
+    free(lists); free(cnt); free(cap);
+#else
+    i3 buf[1024];
+    for (unsigned y = 0; y < H; ++y) for (unsigned x = 0; x < W; ++x) {
+        const unsigned n = pixel_blocks(hp, depth, cp, x, y, buf);
+        for (unsigned k = 0; k < n; ++k) dropped += (unsigned)alloc_block(hd, hp, buf[k]);
+    }
+#endif
     return dropped;   /* insert attempts that found no room (0 in any sanely sized table) */
 }
 
