@@ -110,7 +110,12 @@ HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
 
 CACHE_SYMBOLS = ["bfCacheStoreFrame"]
 INGEST_SYMBOLS = ["bfIngestFrame"]
-BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updateTrajectoryCU", "bfTrajectorySelectReintegration"]
+BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updateTrajectoryCU", "bfTrajectorySelectReintegration",
+                   "bfTrajectoryCreate", "bfTrajectoryDestroy", "bfTrajectoryAddFrame", "bfTrajectoryUpdateOptimizedTransform",
+                   "bfTrajectoryGenerateUpdateLists", "bfTrajectoryConfirmIntegration", "bfTrajectoryGetTopFromReIntegrateList",
+                   "bfTrajectoryGetTopFromIntegrateList", "bfTrajectoryGetTopFromDeIntegrateList", "bfTrajectoryGetNumOptimizedFrames",
+                   "bfTrajectoryGetNumAddedFrames", "bfTrajectoryGetNumActiveOperations", "bfTrajectoryGetFrameType", "bfTrajectoryGetFrameDist",
+                   "bfTrajectoryGetOptimizedTransforms"]
 
 SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftSortKeyPointMatches", "bfSiftFilterKeyPointMatches", "bfSiftAddCurrToResiduals", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
 

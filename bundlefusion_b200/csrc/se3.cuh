@@ -7,28 +7,28 @@ namespace bf {
 
 struct V3 { float x, y, z; };
 __host__ __device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r = { x, y, z }; return r; }
-__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ V3 mulv(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
-__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-__device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
-__device__ __forceinline__ V3 ld3(const float* p, unsigned i) { return mk(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
-__device__ __forceinline__ void st3(float* p, unsigned i, V3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
-__device__ __forceinline__ V3 xf(const float* m, V3 v) {
+__host__ __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ V3 mulv(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__host__ __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__host__ __device__ __forceinline__ V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__host__ __device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
+__host__ __device__ __forceinline__ V3 ld3(const float* p, unsigned i) { return mk(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+__host__ __device__ __forceinline__ void st3(float* p, unsigned i, V3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
+__host__ __device__ __forceinline__ V3 xf(const float* m, V3 v) {
     return mk(m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3], m[4] * v.x + m[5] * v.y + m[6] * v.z + m[7], m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11]);
 }
 
 // ---- SE(3) exp / log (LieDerivUtil.h:19-207) ------------------------------------------------------------
-__device__ __forceinline__ void rodrigues(V3 w, float A, float B, float* R /*9*/) {
+__host__ __device__ __forceinline__ void rodrigues(V3 w, float A, float B, float* R /*9*/) {
     const float wx2 = w.x * w.x, wy2 = w.y * w.y, wz2 = w.z * w.z;
     R[0] = 1.0f - B * (wy2 + wz2); R[4] = 1.0f - B * (wx2 + wz2); R[8] = 1.0f - B * (wx2 + wy2);
     float a = A * w.z, b = B * (w.x * w.y); R[1] = b - a; R[3] = b + a;
     a = A * w.y; b = B * (w.x * w.z); R[2] = b + a; R[6] = b - a;
     a = A * w.x; b = B * (w.y * w.z); R[5] = b - a; R[7] = b + a;
 }
-static __device__ void exp_rotation(V3 w, float* R) {
+static __host__ __device__ void exp_rotation(V3 w, float* R) {
     const float theta_sq = dot(w, w), theta = sqrtf(theta_sq);
     float A, B;
     if (theta_sq < 1e-8) { A = 1.0f - 0.16666667f * theta_sq; B = 0.5f; }
@@ -36,7 +36,7 @@ static __device__ void exp_rotation(V3 w, float* R) {
     else { const float inv = 1.0f / theta; A = sinf(theta) * inv; B = (1 - cosf(theta)) * (inv * inv); }
     rodrigues(w, A, B, R);
 }
-static __device__ V3 ln_rotation(const float* M) {
+static __host__ __device__ V3 ln_rotation(const float* M) {
 #define Rm(r, c) M[(r) * 4 + (c)]
     const float cos_angle = (Rm(0, 0) + Rm(1, 1) + Rm(2, 2) - 1.0f) * 0.5f;
     V3 result = mk((Rm(2, 1) - Rm(1, 2)) * 0.5f, (Rm(0, 2) - Rm(2, 0)) * 0.5f, (Rm(1, 0) - Rm(0, 1)) * 0.5f);
@@ -59,7 +59,7 @@ static __device__ V3 ln_rotation(const float* M) {
 #undef Rm
     return result;
 }
-static __device__ void pose_to_matrix(V3 rot, V3 trans, float* M /*16*/) {
+static __host__ __device__ void pose_to_matrix(V3 rot, V3 trans, float* M /*16*/) {
     const float theta_sq = dot(rot, rot), theta = sqrtf(theta_sq);
     float A, B;
     V3 translation;
@@ -81,7 +81,7 @@ static __device__ void pose_to_matrix(V3 rot, V3 trans, float* M /*16*/) {
     M[8] = R[6]; M[9] = R[7]; M[10] = R[8]; M[11] = translation.z;
     M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
 }
-static __device__ void matrix_to_pose(const float* M, V3& rot, V3& trans) {
+static __host__ __device__ void matrix_to_pose(const float* M, V3& rot, V3& trans) {
     const V3 t = mk(M[3], M[7], M[11]);
     rot = ln_rotation(M);
     const float theta = length(rot);

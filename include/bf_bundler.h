@@ -40,6 +40,36 @@ int bfTrajectorySelectReintegration(const float* d_optimizedTransforms, const fl
                                     unsigned int numFrames, unsigned int topN, float minPoseDistSqrt, float rescaleRotToTrans,
                                     float* d_dist, int* d_list, int* d_count);
 
+/* ---- TrajectoryManager (FL/TrajectoryManager.{h,cpp}): the host-side state machine that decides which frames are integrated,
+ * de-integrated and re-integrated.  Host C++ in the reference and host C++ here (no device work), behind an opaque handle; method for method:
+ *   TrajectoryManager(numMaxImage)                      -> bfTrajectoryCreate   (s_topNActive, s_minPoseDistSqrt passed explicitly)
+ *   addFrame / updateOptimizedTransform / generateUpdateLists / confirmIntegration / getTopFrom{ReIntegrate,Integrate,DeIntegrate}List /
+ *   getNumOptimizedFrames / getNumAddedFrames / getNumActiveOperations / getOptimizedTransforms
+ * Differences: updateOptimizedTransform takes a HOST array (the reference cudaMemcpy's from the device itself -- the caller does that, or
+ * keeps the trajectory on the device and uses bfTrajectorySelectReintegration); the sort is std::stable_sort (the reference's std::sort
+ * leaves the order of equal distances unspecified) and orders NaN distances (a frame integrated with an invalid pose) last, which keeps
+ * the comparator a strict weak order.  Kept as in the reference: the refill loop of generateUpdateLists starts at
+ * sorted[len(re-integration list)] (cpp:97), so while k frames are still queued the k largest movers are skipped.
+ * Frame types: FL/TrajectoryManager.h:8-14. */
+enum { BF_TRAJ_INTEGRATED = 0, BF_TRAJ_NOT_INTEGRATED_NO_TRANSFORM = 1, BF_TRAJ_NOT_INTEGRATED_WITH_TRANSFORM = 2, BF_TRAJ_INVALID = 3, BF_TRAJ_REINTEGRATION = 4 };
+typedef struct BFTrajectoryManager BFTrajectoryManager;
+BFTrajectoryManager* bfTrajectoryCreate(unsigned int numMaxImage, unsigned int topNActive, float minPoseDistSqrt);
+void bfTrajectoryDestroy(BFTrajectoryManager* tm);
+void bfTrajectoryAddFrame(BFTrajectoryManager* tm, int type, const float* transform, unsigned int idx);
+void bfTrajectoryUpdateOptimizedTransform(BFTrajectoryManager* tm, const float* h_trajectory, unsigned int numFrames);
+void bfTrajectoryGenerateUpdateLists(BFTrajectoryManager* tm);
+void bfTrajectoryConfirmIntegration(BFTrajectoryManager* tm, unsigned int frameIdx);
+int  bfTrajectoryGetTopFromReIntegrateList(BFTrajectoryManager* tm, float* oldTransform, float* newTransform, unsigned int* frameIdx);
+int  bfTrajectoryGetTopFromIntegrateList(BFTrajectoryManager* tm, float* transform, unsigned int* frameIdx);
+int  bfTrajectoryGetTopFromDeIntegrateList(BFTrajectoryManager* tm, float* transform, unsigned int* frameIdx);
+unsigned int bfTrajectoryGetNumOptimizedFrames(const BFTrajectoryManager* tm);
+unsigned int bfTrajectoryGetNumAddedFrames(const BFTrajectoryManager* tm);
+unsigned int bfTrajectoryGetNumActiveOperations(const BFTrajectoryManager* tm);
+int  bfTrajectoryGetFrameType(const BFTrajectoryManager* tm, unsigned int frameIdx);
+float bfTrajectoryGetFrameDist(const BFTrajectoryManager* tm, unsigned int frameIdx);
+/* getOptimizedTransforms: writes min(added, optimized) 4x4s (invalid frames: all -inf); returns that count */
+unsigned int bfTrajectoryGetOptimizedTransforms(BFTrajectoryManager* tm, float* h_out);
+
 #ifdef __cplusplus
 }
 #endif
