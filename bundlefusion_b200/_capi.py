@@ -117,7 +117,8 @@ BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updat
                    "bfTrajectoryGetNumAddedFrames", "bfTrajectoryGetNumActiveOperations", "bfTrajectoryGetFrameType", "bfTrajectoryGetFrameDist",
                    "bfTrajectoryGetOptimizedTransforms"]
 
-SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftSortKeyPointMatches", "bfSiftFilterKeyPointMatches", "bfSiftAddCurrToResiduals", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
+SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftSortKeyPointMatches", "bfSiftFilterKeyPointMatches", "bfSiftFilterMatchesBySurfaceArea", "bfSiftFilterMatchesByDenseVerify",
+                "bfSiftAddCurrToResiduals", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
 
 SOLVER_SYMBOLS = [
     "solveBundlingStub", "buildVariablesToCorrespondencesTableCUDA", "evalMaxResidual", "countHighResiduals", "collectHighResiduals",
@@ -300,6 +301,8 @@ def lib() -> C.CDLL:
     L.bfSiftSortKeyPointMatches.argtypes = [C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
     L.bfSiftFilterKeyPointMatches.argtypes = [C.c_uint, C.c_uint, C.c_uint] + [vp] * 9 + [P(C.c_float), C.c_uint, C.c_float]
     L.bfSiftAddCurrToResiduals.argtypes = [C.c_uint, C.c_uint, C.c_uint] + [vp] * 6 + [P(C.c_float)]
+    L.bfSiftFilterMatchesBySurfaceArea.argtypes = [C.c_uint, C.c_uint, C.c_uint, vp, vp, vp, P(C.c_float), C.c_float, vp]
+    L.bfSiftFilterMatchesByDenseVerify.argtypes = [C.c_uint] * 5 + [P(C.c_float), vp, vp, vp] + [C.c_float] * 7 + [vp]
     L.bfSiftWorkspaceBytes.restype = C.c_size_t
     _lib = L
     return L

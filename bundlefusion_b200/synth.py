@@ -369,3 +369,58 @@ def make_filter_problem(n_pairs: int = 6, n_inliers: int = 40, n_outliers: int =
         idxs[p, :n, 0] = p * n + order; idxs[p, :n, 1] = cur * n + order
     return {"keys": keys, "num": num, "dists": dists, "idxs": idxs, "Kinv": Kinv.astype(np.float32), "T_gt": T_gt, "cur": cur, "n": n,
             "n_inliers": n_inliers, "P": P}
+
+
+# ---- problems for the surface-area and dense-verify match filters (row a19) ----------------------------------------------------
+def make_area_problem(seed: int = 0, W: int = 640, H: int = 480):
+    """Filtered matches of 8 earlier frames against the current one (index 8), manager layout, with patches of controlled size:
+    pair 0: 20 matches spread over the image in both images (large area)      pair 1: 6 matches inside a 4 x 4 pixel patch in both (tiny)
+    pair 2: tiny in image p, spread in the current image (kept: BOTH must be small)   pair 3: no matches
+    pair 4: 25 matches spread        pair 5: 3 matches spread       pair 6: 2 matches (degenerate: extent 0 in one axis)
+    pair 7: 12 matches on a thin line (area ~ 0)."""
+    rng = np.random.default_rng(seed)
+    fx = 525.0 * W / 640.0; mx, my = (W - 1) / 2.0, (H - 1) / 2.0
+    K = np.array([[fx, 0, mx, 0], [0, fx, my, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float64)
+    P, cur = 9, 8
+    counts = [20, 6, 8, 0, 25, 3, 2, 12]
+    keys, num, fidx = [], np.zeros(P, np.int32), np.full((P, 25, 2), 0xFFFFFFFF, np.uint32)
+
+    def spread(n):
+        return np.c_[rng.uniform(40, W - 40, n), rng.uniform(40, H - 40, n), np.ones(n), rng.uniform(0.8, 3.0, n)]
+
+    def tiny(n):
+        c = rng.uniform(100, 300, 2)
+        return np.c_[c[0] + rng.uniform(-2, 2, n), c[1] + rng.uniform(-2, 2, n), np.ones(n), 1.5 + rng.uniform(-0.002, 0.002, n)]
+
+    def line(n):
+        t = np.linspace(0, 1, n)
+        return np.c_[100 + 300 * t, 120 + 200 * t, np.ones(n), np.full(n, 2.0)]
+
+    kinds = [(spread, spread), (tiny, tiny), (tiny, spread), None, (spread, spread), (spread, spread), (spread, spread), (line, line)]
+    for p, (n, kind) in enumerate(zip(counts, kinds)):
+        num[p] = n
+        if n == 0:
+            continue
+        a, b = kind[0](n), kind[1](n)
+        base = sum(len(k) for k in keys)
+        keys += [a, b]
+        fidx[p, :n, 0] = base + np.arange(n); fidx[p, :n, 1] = base + n + np.arange(n)
+    return {"keys": np.concatenate(keys).astype(np.float32), "num": num, "fidx": fidx, "Kinv": np.linalg.inv(K).astype(np.float32), "cur": cur, "P": P}
+
+
+def make_dense_verify_problem(n_prev: int = 5, stride: int = 4, start: int = 200, W: int = 640, H: int = 480):
+    """Cached 80x60 frames of the synthetic room at n_prev earlier poses plus the current one (last), and per pair a transform frame p ->
+    current frame: exact for even p, grossly wrong (0.35 m / 12 degrees off) for odd p."""
+    frames = [make_frame(start + stride * k, W, H, noise=False, dropout=0.0) for k in range(n_prev + 1)]
+    gt = np.stack([f[2].astype(np.float64) for f in frames])
+    caches = [make_cache_frame(f[0], f[1]) for f in frames]
+    cur = n_prev
+    T = np.zeros((n_prev + 1, 4, 4), np.float32)
+    for p in range(n_prev + 1):
+        rel = np.linalg.inv(gt[cur]) @ gt[p]
+        if p % 2 == 1:
+            rel = se3_exp(np.array([0.0, 0.21, 0.0]), np.array([0.35, 0.0, 0.1])) @ rel
+        T[p] = rel
+    fx, fy, mx, my = cache_intrinsics(W, H)
+    K = np.array([[fx, 0, mx, 0], [0, fy, my, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
+    return {"caches": caches, "T": T, "K": K, "cur": cur, "P": n_prev + 1, "W": 80, "H": 60}

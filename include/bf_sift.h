@@ -76,6 +76,32 @@ int bfSiftFilterKeyPointMatches(unsigned int curFrame, unsigned int startFrame, 
                                 float* d_filteredTransforms, float* d_filteredTransformsInv, const float* siftIntrinsicsInv,
                                 unsigned int minNumMatches, float maxKabschRes2);
 
+/* SIFTImageManager::FilterMatchesBySurfaceAreaCU(curFrame, startFrame, numFrames, colorIntrinsicsInv, areaThresh)
+ * (FL/SiftGPU/SIFTImageManager.cu:318-407; FL/SiftGPU/cuda_surfaceArea.h): for every pair p in [startFrame, numFrames), p != curFrame, with
+ * filtered matches, projects the matched key points of each image into the plane spanned by the first two vectors of the frame
+ * MYEIGEN::eigenSystem returns for their covariance (FL/SiftGPU/cuda_SVD.h:70-110 -- rows of the Jacobi rotation matrix, kept as is),
+ * measures the area of the 2-D oriented bounding box there, and sets d_currNumFilteredMatchesPerImagePair[p] = 0 when BOTH areas are
+ * below areaThresh (an exactly axis-aligned 2-D covariance yields a 0/0 axis and, through the min / max reductions, area 0 -- as in
+ * the reference).
+ * colorIntrinsicsInv: HOST 4x4.  d_areasOut: optional [numFrames][2] (area in image p, area in the current image), else NULL.
+ * Difference: normalize() multiplies by 1 / sqrtf where the reference multiplies by rsqrtf.  Asynchronous. */
+int bfSiftFilterMatchesBySurfaceArea(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const BFSIFTKeyPoint* d_keyPoints,
+                                     int32_t* d_currNumFilteredMatchesPerImagePair, const uint32_t* d_currFilteredMatchKeyPointIndices,
+                                     const float* colorIntrinsicsInv, float areaThresh, float* d_areasOut);
+
+/* SIFTImageManager::FilterMatchesByDenseVerifyCU(curFrame, startFrame, numFrames, imageWidth, imageHeight, intrinsics, d_cachedFrames,
+ * distThresh, normalThresh, colorThresh, errThresh, corrThresh, sensorDepthMin, sensorDepthMax) (FL/SiftGPU/SIFTImageManager.cu:413-608):
+ * for every pair p with filtered matches, warps cached frame p into the current one with d_currFilteredTransforms[p] and back with its
+ * inverse (projective association at the cache resolution, float normals), accumulates residual / weight / count over the pixels
+ * whose position and normal agree or that are known to be in front of the target surface, and zeroes the pair's filtered-match count
+ * when corr = count / (2 W H) < corrThresh, err = residual / weight > errThresh, or err is NaN.  intrinsics: HOST 4x4 (cache
+ * resolution).  colorThresh is accepted and unused, as in the reference.  d_statsOut: optional [numFrames][2] (err, corr), else NULL.
+ * Difference: the three sums are taken in a fixed order (the reference: shared-memory float atomics, race-dependent).  Asynchronous. */
+int bfSiftFilterMatchesByDenseVerify(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, unsigned int imageWidth, unsigned int imageHeight,
+                                     const float* intrinsics, int32_t* d_currNumFilteredMatchesPerImagePair, const float* d_currFilteredTransforms,
+                                     const BFCUDACachedFrame* d_cachedFrames, float distThresh, float normalThresh, float colorThresh, float errThresh,
+                                     float corrThresh, float sensorDepthMin, float sensorDepthMax, float* d_statsOut);
+
 /* SIFTImageManager::AddCurrToResidualsCU(curFrame, startFrame, numFrames, colorIntrinsicsInv) (FL/SiftGPU/SIFTImageManager.cu:610-685):
  * appends the filtered matches of every pair p in [startFrame, numFrames), p != curFrame, to the global correspondence list as
  * EntryJ { p, curFrame, Kinv (d_i (x_i, y_i, 1)), Kinv (d_j (x_j, y_j, 1)) } (+ their key-point index pairs) and advances

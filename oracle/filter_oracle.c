@@ -260,3 +260,268 @@ ORC_API int orc_sift_add_residuals(unsigned curFrame, unsigned startFrame, unsig
     }
     return numResiduals;
 }
+
+/* =====================================================================================================================================
+ * Row a19, second and third filter.  Restated from FilterMatchesBySurfaceAreaCU_Kernel (FL/SiftGPU/SIFTImageManager.cu:318-389) with its
+ * helpers computeKeyPointMatchesCovariance / computeCovariance2d / computeAreaOrientedBoundingBox2 / projectKeysToPlane
+ * (FL/SiftGPU/cuda_surfaceArea.h:13-163), MYEIGEN::eigenSystem / jacobi (FL/SiftGPU/cuda_SVD.h:17-214, the cyclic Jacobi eigenvalue
+ * routine of Numerical Recipes), the 2x2 closed forms of FL/SiftGPU/cuda_EigenValue.h:71-105, warpReduce{Sum,Min,Max}
+ * (FL/SiftGPU/cudaUtil.h:25-43); and from FilterMatchesByDenseVerifyCU_Kernel / computeProjError (FL/SiftGPU/SIFTImageManager.cu:413-585,
+ * the CUDACACHE_FLOAT_NORMALS branch -- FL/CUDACacheUtil.h:7-8 defines both macros and the float one is tested first).
+ *
+ * PARITY STATUS: "parity unpinned" against a run of the reference.  Restated literally: the 32-lane shuffle-down summation trees (lane 0's
+ * association order), the quirk that eigenSystem hands back ROWS of the Jacobi rotation matrix as "eigenvectors" (cuda_SVD.h:94-99 --
+ * an orthonormal frame, but not the eigenframe; which frame depends on the literal sweep order, hence the literal Jacobi), the magnitude
+ * sort by row exchange, NaN handling (a diagonal 2-D covariance gives a 0/0 axis; the NaN coordinates lose every fminf / fmaxf against
+ * the idle lanes' +-FLT_MAX, the extent is -inf and the area 0), and in the dense check the float->int conversion of the GPU
+ * (NaN -> 0, saturating).
+ * Not the reference's: normalize() is v * (1 / sqrtf(v.v)) here and in the CUDA path (the reference: v * rsqrtf(v.v), an approximate
+ * hardware instruction); the dense check's three sums are taken in a fixed order (256 strided partial sums, shuffle-down tree per 32,
+ * then the 8 tree results left to right) where the reference uses shared-memory float atomics in a race-dependent order, and the
+ * inverse transform comes from the sub-determinant form of the adjugate (mat4_inverse_subdet below).
+ * ===================================================================================================================================== */
+
+static float tree_sum32(const float* v) {                    /* warpReduceSum as lane 0 sees it */
+    float a[32]; memcpy(a, v, sizeof a);
+    for (int off = 16; off > 0; off /= 2) for (int l = 0; l < off; ++l) a[l] = a[l] + a[l + off];
+    return a[0];
+}
+static float tree_min32(const float* v) { float a[32]; memcpy(a, v, sizeof a); for (int off = 16; off > 0; off /= 2) for (int l = 0; l < off; ++l) a[l] = fminf(a[l], a[l + off]); return a[0]; }
+static float tree_max32(const float* v) { float a[32]; memcpy(a, v, sizeof a); for (int off = 16; off > 0; off /= 2) for (int l = 0; l < off; ++l) a[l] = fmaxf(a[l], a[l + off]); return a[0]; }
+
+/* cuda_SVD.h:112-214 (Numerical Recipes jacobi, n = 3), zero-based.  a is destroyed; d = eigenvalues, v = rotation matrix. */
+static int jacobi3(float a[3][3], float d[3], float v[3][3]) {
+    float b[3], z[3];
+    for (int p = 0; p < 3; ++p) { for (int q = 0; q < 3; ++q) v[p][q] = 0.0f; v[p][p] = 1.0f; }
+    for (int p = 0; p < 3; ++p) { b[p] = d[p] = a[p][p]; z[p] = 0.0f; }
+    for (int sweep = 1; sweep <= 50; ++sweep) {
+        float sm = 0.0f;
+        for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) sm += fabsf(a[p][q]);
+        if (sm == 0.0f) return 1;
+        const float tresh = sweep < 4 ? 0.2f * sm / 9.0f : 0.0f;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                const float g = 100.0f * fabsf(a[p][q]);
+                if (sweep > 4 && fabsf(d[p]) + g == fabsf(d[p]) && fabsf(d[q]) + g == fabsf(d[q])) a[p][q] = 0.0f;
+                else if (fabsf(a[p][q]) > tresh) {
+                    float h = d[q] - d[p], t;
+                    if (fabsf(h) + g == fabsf(h)) t = a[p][q] / h;
+                    else {
+                        const float theta = 0.5f * h / a[p][q];
+                        t = 1.0f / (fabsf(theta) + sqrtf(1.0f + theta * theta));
+                        if (theta < 0.0f) t = -t;
+                    }
+                    const float c = 1.0f / sqrtf(1.0f + t * t), s = t * c, tau = s / (1.0f + c);
+                    h = t * a[p][q];
+                    z[p] -= h; z[q] += h; d[p] -= h; d[q] += h;
+                    a[p][q] = 0.0f;
+#define ORC_ROT(m, i, j, k, l) { const float g_ = m[i][j], h_ = m[k][l]; m[i][j] = g_ - s * (h_ + g_ * tau); m[k][l] = h_ + s * (g_ - h_ * tau); }
+                    for (int j = 0; j < p; ++j) ORC_ROT(a, j, p, j, q)
+                    for (int j = p + 1; j < q; ++j) ORC_ROT(a, p, j, j, q)
+                    for (int j = q + 1; j < 3; ++j) ORC_ROT(a, p, j, q, j)
+                    for (int j = 0; j < 3; ++j) ORC_ROT(v, j, p, j, q)
+#undef ORC_ROT
+                }
+            }
+        for (int p = 0; p < 3; ++p) { b[p] += z[p]; d[p] = b[p]; z[p] = 0.0f; }
+    }
+    return 0;
+}
+
+/* MYEIGEN::eigenSystem (cuda_SVD.h:17-20, 70-110): "eigenvectors" ev[i] = ROW i of the rotation matrix, rows exchanged by |eigenvalue| */
+static int eigen_system3(const float m[9], float evs[3], f3 ev[3]) {
+    float a[3][3], d[3], v[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) a[i][j] = m[i + 3 * j];
+    if (!jacobi3(a, d, v)) return 0;
+    float e[3][3];
+    for (int i = 0; i < 3; ++i) { evs[i] = d[i]; for (int j = 0; j < 3; ++j) e[i][j] = v[i][j]; }
+    for (int i = 0; i < 3; ++i) {
+        float curMax = 0.0f; int arg = -1;
+        for (int j = i; j < 3; ++j) if (fabsf(evs[j]) > curMax) { curMax = fabsf(evs[j]); arg = j; }
+        if (arg != i && arg != -1) {
+            float t = evs[i]; evs[i] = evs[arg]; evs[arg] = t;
+            for (int j = 0; j < 3; ++j) { t = e[i][j]; e[i][j] = e[arg][j]; e[arg][j] = t; }
+        }
+    }
+    for (int i = 0; i < 3; ++i) { ev[i].x = e[i][0]; ev[i].y = e[i][1]; ev[i].z = e[i][2]; }
+    return 1;
+}
+
+static f3 key_point_3d(const KeyPoint* k, const float* Ki) {
+    const float v[3] = { k->depth * k->px, k->depth * k->py, k->depth * 1.0f };
+    f3 o = { Ki[0] * v[0] + Ki[1] * v[1] + Ki[2] * v[2] + Ki[3], Ki[4] * v[0] + Ki[5] * v[1] + Ki[6] * v[2] + Ki[7], Ki[8] * v[0] + Ki[9] * v[1] + Ki[10] * v[2] + Ki[11] };
+    return o;
+}
+static float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+/* one image of one pair: area of the 2-D oriented bounding box of the key points projected into the plane the "eigenframe" defines */
+static float surface_area_one(const KeyPoint* kp, const uint32_t* idx, unsigned n, const float* Ki, unsigned which) {
+    f3 pt[32]; float lane[32];
+    for (unsigned i = 0; i < 32; ++i) { f3 zero = { 0.0f, 0.0f, 0.0f }; pt[i] = i < n ? key_point_3d(&kp[idx[2 * i + which]], Ki) : zero; }
+    /* computeKeyPointMatchesCovariance, cuda_surfaceArea.h:13-53 */
+    float mean[3], V[9];
+    for (int c = 0; c < 3; ++c) { for (int i = 0; i < 32; ++i) lane[i] = ((const float*)&pt[i])[c]; mean[c] = tree_sum32(lane) / (float)n; }
+    for (int j = 0; j < 9; ++j) {
+        for (unsigned i = 0; i < 32; ++i) {
+            const float* p = (const float*)&pt[i];
+            lane[i] = i < n ? (p[j / 3] - mean[j / 3]) * (p[j % 3] - mean[j % 3]) : 0.0f;
+        }
+        V[j] = tree_sum32(lane) / (float)n;
+    }
+    float evs[3]; f3 ev[3];
+    if (!eigen_system3(V, evs, ev)) return 0.0f;
+    /* projectKeysToPlane, cuda_surfaceArea.h:138-161 */
+    const f3 mu = { mean[0], mean[1], mean[2] };
+    float px[32], py[32];
+    for (unsigned i = 0; i < 32; ++i) {
+        px[i] = py[i] = 0.0f;
+        if (i < n) {
+            const f3 dm = { pt[i].x - mu.x, pt[i].y - mu.y, pt[i].z - mu.z };
+            const float k = dot3(ev[2], dm);
+            const f3 s = { (pt[i].x - k * ev[2].x) - mu.x, (pt[i].y - k * ev[2].y) - mu.y, (pt[i].z - k * ev[2].z) - mu.z };
+            px[i] = dot3(s, ev[0]); py[i] = dot3(s, ev[1]);
+        }
+    }
+    /* computeCovariance2d, cuda_surfaceArea.h:59-90 */
+    float m2[2], c2[4];
+    for (unsigned i = 0; i < 32; ++i) lane[i] = i < n ? px[i] : 0.0f;
+    m2[0] = tree_sum32(lane) / (float)n;
+    for (unsigned i = 0; i < 32; ++i) lane[i] = i < n ? py[i] : 0.0f;
+    m2[1] = tree_sum32(lane) / (float)n;
+    for (int j = 0; j < 4; ++j) {
+        for (unsigned i = 0; i < 32; ++i) { const float q[2] = { px[i] - m2[0], py[i] - m2[1] }; lane[i] = i < n ? q[j / 2] * q[j % 2] : 0.0f; }
+        c2[j] = tree_sum32(lane) / (float)n;
+    }
+    /* computeAreaOrientedBoundingBox2, cuda_surfaceArea.h:93-136; cuda_EigenValue.h:71-105 */
+    const float dd = c2[0] - c2[3];
+    const float disc = 0.5f * sqrtf(dd * dd + (4.0f * c2[1]) * c2[1]);
+    const float l1 = (c2[0] + c2[3]) / 2.0f + disc, l2 = (c2[0] + c2[3]) / 2.0f - disc;
+    float ax[2][2];
+    const float ls[2] = { l1, l2 };
+    for (int k = 0; k < 2; ++k) {
+        float vx = -c2[1], vy = c2[0] - ls[k];
+        const float mag = sqrtf(vx * vx + vy * vy);
+        vx /= mag; vy /= mag;
+        const float inv = 1.0f / sqrtf(vx * vx + vy * vy);            /* normalize(): see the deviation note above */
+        ax[k][0] = vx * inv; ax[k][1] = vy * inv;
+    }
+    float mnx[32], mny[32], mxx[32], mxy[32];
+    for (unsigned i = 0; i < 32; ++i) {
+        mnx[i] = mny[i] = 3.402823466e+38f; mxx[i] = mxy[i] = -3.402823466e+38f;
+        if (i < n) { const float cx = ax[0][0] * px[i] + ax[0][1] * py[i], cy = ax[1][0] * px[i] + ax[1][1] * py[i]; mnx[i] = mxx[i] = cx; mny[i] = mxy[i] = cy; }
+    }
+    const float ex = tree_max32(mxx) - tree_min32(mnx), ey = tree_max32(mxy) - tree_min32(mny);
+    if (ex < 0.00001f || ey < 0.00001f) return 0.0f;
+    return ex * ey;
+}
+
+/* FilterMatchesBySurfaceAreaCU over pairs [startFrame, numFrames) \\ {curFrame}: zeroes the filtered-match count of a pair whose key points
+ * cover less than areaThresh in BOTH images.  areas (optional): [numFrames][2], written for the pairs visited. */
+ORC_API void orc_sift_filter_surface_area(unsigned curFrame, unsigned startFrame, unsigned numFrames, const KeyPoint* kp, int32_t* numFiltered,
+                                          const uint32_t* fIdxs, const float* colorIntrinsicsInv, float areaThresh, float* areas) {
+    for (unsigned p = startFrame; p < numFrames; ++p) {
+        if (p == curFrame) continue;
+        const int32_t c = numFiltered[p];
+        if (c <= 0) continue;
+        const unsigned n = (unsigned)(c < MAX_FILTERED ? c : MAX_FILTERED);
+        const uint32_t* idx = fIdxs + 2 * (size_t)p * MAX_FILTERED;
+        const float a0 = surface_area_one(kp, idx, n, colorIntrinsicsInv, 0), a1 = surface_area_one(kp, idx, n, colorIntrinsicsInv, 1);
+        if (areas) { areas[2 * p] = a0; areas[2 * p + 1] = a1; }
+        if (a0 < areaThresh && a1 < areaThresh) numFiltered[p] = 0;
+    }
+}
+
+/* ---- dense verification ---- */
+typedef struct { const float* depth; const float* campos; const float* intensity; const float* intensityDerivs; const uint8_t* normalsU4; const float* normals; } CachedFrame;   /* CUDACachedFrame, FL/CUDACacheUtil.h */
+
+static int f2i_gpu(float x) {              /* (int) of the GPU: NaN -> 0, saturating */
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return 2147483647;
+    if (x <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)x;
+}
+
+/* computeProjError, SIFTImageManager.cu:413-486.  out = (residual, weight, 1) or zeros */
+static void proj_error(unsigned idx, unsigned W, unsigned H, float distThresh, float normalThresh, const float* T, const float* K,
+                       const CachedFrame* in, const CachedFrame* model, float dMin, float dMax, float out[3]) {
+    out[0] = out[1] = out[2] = 0.0f;
+    const float* p = in->campos + 4 * (size_t)idx; const float* nI = in->normals + 4 * (size_t)idx;
+    const float d = in->depth[idx];
+    if (!(p[0] != -INFINITY && nI[0] != -INFINITY && d >= dMin && d <= dMax)) return;
+    float pt[4], nt[4];
+    for (int r = 0; r < 4; ++r) {
+        pt[r] = T[4 * r] * p[0] + T[4 * r + 1] * p[1] + T[4 * r + 2] * p[2] + T[4 * r + 3] * p[3];
+        nt[r] = T[4 * r] * nI[0] + T[4 * r + 1] * nI[1] + T[4 * r + 2] * nI[2] + T[4 * r + 3] * 0.0f;
+    }
+    const float tx = K[0] * pt[0] + K[1] * pt[1] + K[2] * pt[2] + K[3], ty = K[4] * pt[0] + K[5] * pt[1] + K[6] * pt[2] + K[7], tz = K[8] * pt[0] + K[9] * pt[1] + K[10] * pt[2] + K[11];
+    const int sx = f2i_gpu(roundf(tx / tz)), sy = f2i_gpu(roundf(ty / tz));
+    if (!(sx >= 0 && sy >= 0 && sx < (int)W && sy < (int)H)) return;
+    const size_t m = (size_t)sy * W + sx;
+    const float* q = model->campos + 4 * m; const float* nT = model->normals + 4 * m;
+    if (!(q[0] != -INFINITY && nT[0] != -INFINITY)) return;
+    const float e0 = pt[0] - q[0], e1 = pt[1] - q[1], e2 = pt[2] - q[2], e3 = pt[3] - q[3];
+    const float dist = sqrtf(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3);
+    const float dN = nt[0] * nT[0] + nt[1] * nT[1] + nt[2] * nT[2];
+    const float projDepth = pt[2], tgtDepth = model->depth[m];
+    if (!(tgtDepth >= dMin && tgtDepth <= dMax)) return;
+    const int bad = (tgtDepth != -INFINITY && projDepth < tgtDepth) && dist > distThresh;
+    if ((dN >= normalThresh && dist <= distThresh) || bad) {
+        const float zN = (pt[2] - dMin) / (dMax - dMin);
+        const float w = fmaxf(0.0f, 0.5f * ((1.0f - dist / distThresh) + (1.0f - zN)));
+        out[0] = dist; out[1] = w; out[2] = 1.0f;
+    }
+}
+
+/* The inverse the CUDA path takes (bundlefusion_b200/csrc/mat4.cuh mat4_inverse_hd): adjugate through 2x2 sub-determinants.  The reference's
+ * float4x4::getInverse (cuda_SimpleMatrixUtil.h:975-1100, restated as orc_mat4_inverse) expands every cofactor into six triple products;
+ * the two agree to a few ulp, which moves the sums below by ~1e-7 relative -- decisions differ only for a pair sitting on a threshold. */
+static void mat4_inverse_subdet(const float* m, float* out) {
+    const float a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3], a10 = m[4], a11 = m[5], a12 = m[6], a13 = m[7];
+    const float a20 = m[8], a21 = m[9], a22 = m[10], a23 = m[11], a30 = m[12], a31 = m[13], a32 = m[14], a33 = m[15];
+    const float s0 = a00 * a11 - a10 * a01, s1 = a00 * a12 - a10 * a02, s2 = a00 * a13 - a10 * a03;
+    const float s3 = a01 * a12 - a11 * a02, s4 = a01 * a13 - a11 * a03, s5 = a02 * a13 - a12 * a03;
+    const float c5 = a22 * a33 - a32 * a23, c4 = a21 * a33 - a31 * a23, c3 = a21 * a32 - a31 * a22;
+    const float c2 = a20 * a33 - a30 * a23, c1 = a20 * a32 - a30 * a22, c0 = a20 * a31 - a30 * a21;
+    const float det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    const float r = 1.0f / det;
+    out[0] = (a11 * c5 - a12 * c4 + a13 * c3) * r;   out[1] = (-a01 * c5 + a02 * c4 - a03 * c3) * r;
+    out[2] = (a31 * s5 - a32 * s4 + a33 * s3) * r;   out[3] = (-a21 * s5 + a22 * s4 - a23 * s3) * r;
+    out[4] = (-a10 * c5 + a12 * c2 - a13 * c1) * r;  out[5] = (a00 * c5 - a02 * c2 + a03 * c1) * r;
+    out[6] = (-a30 * s5 + a32 * s2 - a33 * s1) * r;  out[7] = (a20 * s5 - a22 * s2 + a23 * s1) * r;
+    out[8] = (a10 * c4 - a11 * c2 + a13 * c0) * r;   out[9] = (-a00 * c4 + a01 * c2 - a03 * c0) * r;
+    out[10] = (a30 * s4 - a31 * s2 + a33 * s0) * r;  out[11] = (-a20 * s4 + a21 * s2 - a23 * s0) * r;
+    out[12] = (-a10 * c3 + a11 * c1 - a12 * c0) * r; out[13] = (a00 * c3 - a01 * c1 + a02 * c0) * r;
+    out[14] = (-a30 * s3 + a31 * s1 - a32 * s0) * r; out[15] = (a20 * s3 - a21 * s1 + a22 * s0) * r;
+}
+
+#define DV_THREADS 256
+/* FilterMatchesByDenseVerifyCU over pairs [startFrame, numFrames) \\ {curFrame}; frames: HOST array of cached-frame pointer records.
+ * stats (optional): [numFrames][2] = (err, corr) for the pairs visited. */
+ORC_API void orc_sift_filter_dense_verify(unsigned curFrame, unsigned startFrame, unsigned numFrames, unsigned W, unsigned H, const float* intrinsics,
+                                          int32_t* numFiltered, const float* fT, const CachedFrame* frames, float distThresh, float normalThresh,
+                                          float colorThresh, float errThresh, float corrThresh, float dMin, float dMax, float* stats) {
+    (void)colorThresh;
+    for (unsigned p = startFrame; p < numFrames; ++p) {
+        if (p == curFrame) continue;
+        if (numFiltered[p] == 0) continue;
+        const float* T = fT + 16 * (size_t)p;
+        float Tinv[16];
+        mat4_inverse_subdet(T, Tinv);
+        float part[3][DV_THREADS];
+        for (unsigned t = 0; t < DV_THREADS; ++t) {
+            float s[3] = { 0.0f, 0.0f, 0.0f };
+            for (unsigned idx = t; idx < W * H; idx += DV_THREADS) {
+                float a[3], b[3];
+                proj_error(idx, W, H, distThresh, normalThresh, T, intrinsics, &frames[p], &frames[curFrame], dMin, dMax, a);
+                proj_error(idx, W, H, distThresh, normalThresh, Tinv, intrinsics, &frames[curFrame], &frames[p], dMin, dMax, b);
+                for (int k = 0; k < 3; ++k) s[k] += a[k] + b[k];
+            }
+            for (int k = 0; k < 3; ++k) part[k][t] = s[k];
+        }
+        float tot[3];
+        for (int k = 0; k < 3; ++k) { tot[k] = 0.0f; for (unsigned w = 0; w < DV_THREADS / 32; ++w) tot[k] += tree_sum32(&part[k][32 * w]); }
+        const float err = tot[0] / tot[1], corr = 0.5f * tot[2] / (float)(W * H);
+        if (stats) { stats[2 * p] = err; stats[2 * p + 1] = corr; }
+        if (corr < corrThresh || err > errThresh || err != err) numFiltered[p] = 0;
+    }
+}

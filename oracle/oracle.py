@@ -489,3 +489,37 @@ def sift_add_residuals(curFrame, startFrame, numFrames, numFiltered, fIdxs, keyP
     L.orc_sift_add_residuals.restype = C.c_int
     n = L.orc_sift_add_residuals(curFrame, startFrame, numFrames, ent.ctypes.data, eidx.ctypes.data, 0, nf.ctypes.data, fi.ctypes.data, kp.ctypes.data, Ki.ctypes.data)
     return ent[:n].copy(), eidx[:n].copy()
+
+
+def sift_filter_surface_area(curFrame, startFrame, numFrames, keyPoints, numFiltered, fIdxs, colorIntrinsicsInv, areaThresh):
+    """FilterMatchesBySurfaceAreaCU.  Returns (numFiltered' [P], areas [P,2])."""
+    L = lib()
+    kp = np.ascontiguousarray(keyPoints, np.float32); nf = np.ascontiguousarray(numFiltered, np.int32).copy()
+    fi = np.ascontiguousarray(fIdxs, np.uint32); Ki = np.ascontiguousarray(colorIntrinsicsInv, np.float32)
+    areas = np.full((len(nf), 2), -1.0, np.float32)
+    L.orc_sift_filter_surface_area.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    L.orc_sift_filter_surface_area.restype = None
+    L.orc_sift_filter_surface_area(curFrame, startFrame, numFrames, kp.ctypes.data, nf.ctypes.data, fi.ctypes.data, Ki.ctypes.data, areaThresh, areas.ctypes.data)
+    return nf, areas
+
+
+class _CachedFrame(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("campos", C.c_void_p), ("intensity", C.c_void_p), ("intensityDerivs", C.c_void_p), ("normalsU4", C.c_void_p), ("normals", C.c_void_p)]
+
+
+def sift_filter_dense_verify(curFrame, startFrame, numFrames, W, H, intrinsics, numFiltered, fT, frames, distThresh, normalThresh, colorThresh,
+                             errThresh, corrThresh, dMin, dMax):
+    """FilterMatchesByDenseVerifyCU.  frames: list of dicts with float32 arrays 'depth' [H,W], 'campos' [H,W,4], 'normals' [H,W,4].
+    Returns (numFiltered' [P], stats [P,2] = (err, corr))."""
+    L = lib()
+    nf = np.ascontiguousarray(numFiltered, np.int32).copy(); T = np.ascontiguousarray(fT, np.float32); K = np.ascontiguousarray(intrinsics, np.float32)
+    keep = [{k: np.ascontiguousarray(f[k], np.float32) for k in ("depth", "campos", "normals")} for f in frames]
+    recs = (_CachedFrame * len(keep))()
+    for r, f in zip(recs, keep):
+        r.depth, r.campos, r.normals = f["depth"].ctypes.data, f["campos"].ctypes.data, f["normals"].ctypes.data
+    stats = np.full((len(nf), 2), -1.0, np.float32)
+    L.orc_sift_filter_dense_verify.argtypes = [C.c_uint] * 5 + [C.c_void_p] * 4 + [C.c_float] * 7 + [C.c_void_p]
+    L.orc_sift_filter_dense_verify.restype = None
+    L.orc_sift_filter_dense_verify(curFrame, startFrame, numFrames, W, H, K.ctypes.data, nf.ctypes.data, T.ctypes.data, C.addressof(recs),
+                                   distThresh, normalThresh, colorThresh, errThresh, corrThresh, dMin, dMax, stats.ctypes.data)
+    return nf, stats
