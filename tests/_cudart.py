@@ -19,6 +19,7 @@ def runtime():
         rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         rt.cudaMemset.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
         rt.cudaGetDeviceCount.argtypes = [C.POINTER(C.c_int)]
+        rt.cudaDeviceSynchronize.argtypes = []
         _rt = rt
     return _rt
 

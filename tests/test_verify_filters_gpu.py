@@ -34,8 +34,10 @@ def run_area(L, cur, start, P, keys, num, fidx, Kinv, thresh):
 
 
 def same(a, b):
-    """float32 arrays equal bit for bit (NaNs included)"""
-    return np.array_equal(np.ascontiguousarray(a, np.float32).view(np.uint32), np.ascontiguousarray(b, np.float32).view(np.uint32))
+    """float32 arrays equal bit for bit; NaNs must sit at the same places (0/0 is 0xFFC00000 on x86 and 0x7FFFFFFF on the GPU)"""
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
