@@ -193,10 +193,9 @@ __global__ void __launch_bounds__(256)
 prep_rows_kernel(BFEntryJ* corr, const int* __restrict__ rowStart, int* entries, int* segCount, Segment* segs,
                  int* varToCorr, unsigned maxCorrPerImage, unsigned* scal) {
     extern __shared__ unsigned long long sKeys[];
-    __shared__ int sSegN;
     const unsigned v = blockIdx.x;
     const int start = rowStart[v], n = rowStart[v + 1] - start;
-    if (threadIdx.x == 0) { sSegN = 0; segCount[v] = 0; }
+    if (threadIdx.x == 0) segCount[v] = 0;
     if (n <= 0) return;
     if (n > BF_MAX_ROW) { if (threadIdx.x == 0) atomicExch(&scal[SC_ERROR], 1u); return; }
     unsigned nPow2 = 1; while (nPow2 < (unsigned)n) nPow2 <<= 1;

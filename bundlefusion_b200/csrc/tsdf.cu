@@ -42,7 +42,6 @@ cudaStream_t stream() { return g_stream; }
 static BFHashParams g_hashParams;           // updateConstantHashParams
 static BFDepthCameraParams g_camParams;     // updateConstantDepthCameraParams
 static BFDepthCameraData g_bound = {nullptr, nullptr};   // bindInputDepthColorTextures
-static unsigned g_boundW = 0, g_boundH = 0;
 
 // library-private per-hash scratch ("aux"), keyed by the d_hash pointer
 struct TsdfAux {
@@ -1675,7 +1674,7 @@ BF_API int bfTsdfReleaseAux(const BFHashDataStruct* hd) {
 BF_API void updateConstantHashParams(const BFHashParams* hp) { g_hashParams = *hp; }
 BF_API void updateConstantDepthCameraParams(const BFDepthCameraParams* p) { g_camParams = *p; }
 BF_API void bindInputDepthColorTextures(const BFDepthCameraData* dd, unsigned int width, unsigned int height) {
-    g_bound = *dd; g_boundW = width; g_boundH = height;
+    g_bound = *dd; (void)width; (void)height;      // the image size travels in DepthCameraParams (the reference only needs it for its texture binding)
 }
 
 BF_API void resetCUDA(BFHashDataStruct* hd, const BFHashParams* hp) { BF_SAFE(do_reset(hd, hp)); }
