@@ -523,3 +523,32 @@ def sift_filter_dense_verify(curFrame, startFrame, numFrames, W, H, intrinsics, 
     L.orc_sift_filter_dense_verify(curFrame, startFrame, numFrames, W, H, K.ctypes.data, nf.ctypes.data, T.ctypes.data, C.addressof(recs),
                                    distThresh, normalThresh, colorThresh, errThresh, corrThresh, dMin, dMax, stats.ctypes.data)
     return nf, stats
+
+
+# ---- SIFT detection (oracle/sift_detect_oracle.c) -----------------------------------------------------------------------------------
+class SiftDetectParams(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depthWidth", C.c_uint32), ("depthHeight", C.c_uint32), ("depthMin", C.c_float),
+                ("depthMax", C.c_float), ("minKeyScale", C.c_float), ("featureCountThreshold", C.c_int32), ("maxKeyPoints", C.c_uint32)]
+
+
+def sift_detect(intensity, depth, depthMin=0.1, depthMax=3.0, minKeyScale=3.0, featureCountThreshold=150, maxKeyPoints=1024):
+    """SiftGPU::RunSIFT + GetKeyPointsAndDescriptorsCUDA.  intensity [H,W] float32 in 0..1, depth [Hd,Wd] float32 (-inf invalid).
+    Returns (keyPoints [n,4] = (x, y, scale, depth), descriptors [n,128] uint8, levelCounts [12])."""
+    L = lib()
+    I = np.ascontiguousarray(intensity, np.float32); D = np.ascontiguousarray(depth, np.float32)
+    P = SiftDetectParams(I.shape[1], I.shape[0], D.shape[1], D.shape[0], depthMin, depthMax, minKeyScale, featureCountThreshold, maxKeyPoints)
+    kp = np.zeros((maxKeyPoints, 4), np.float32); des = np.zeros((maxKeyPoints, 128), np.uint8); lc = np.zeros(12, np.int32)
+    L.orc_sift_detect.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SiftDetectParams), C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_sift_detect.restype = C.c_int
+    n = L.orc_sift_detect(I.ctypes.data, D.ctypes.data, C.byref(P), kp.ctypes.data, des.ctypes.data, lc.ctypes.data)
+    if n < 0:
+        raise ValueError("unsupported image size")
+    return kp[:n].copy(), des[:n].copy(), lc
+
+
+def sift_filter_bank():
+    L = lib()
+    s = np.zeros(6, np.float32); w = np.zeros(6, np.int32); t = np.zeros((6, 33), np.float32)
+    L.orc_sift_filter_bank.argtypes = [C.c_void_p] * 3
+    L.orc_sift_filter_bank(s.ctypes.data, w.ctypes.data, t.ctypes.data)
+    return s, w, t
