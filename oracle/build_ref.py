@@ -89,6 +89,7 @@ def main():
             sys.stderr.write(r.stdout[-4000:])
             raise RuntimeError(f"building {name} failed")
     build_solver()
+    build_siftmgr()
     print("oracle/_ref built:", sorted(os.listdir(OUT)))
     return 0
 
@@ -135,6 +136,42 @@ def build_solver():
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout[-4000:])
+            raise RuntimeError(f"building {name} failed")
+
+
+def build_siftmgr():
+    """The reference's match-manager kernels (FL/SiftGPU/SIFTImageManager.cu: SortKeyPointMatchesCU, FilterKeyPointMatchesCU,
+    FilterMatchesBySurfaceAreaCU, FilterMatchesByDenseVerifyCU, AddCurrToResidualsCU) for sm_100a -> libref_siftmgr[_fast].so, through
+    oracle/ref_siftmgr_wrap.cu (our own C entry points, which includes the scratch copy as one translation unit).  Patches: template<>
+    and shfl_sync as above, in every header that uses them; stub headers as for the solver."""
+    root = os.path.join(TMP, "siftmgr")
+    src = os.path.join(root, "Source")
+    S = os.path.join(REF, "Source")
+    for d in (os.path.join(src, "SiftGPU"), os.path.join(root, "stubs", "core-base")):
+        os.makedirs(d)
+    for f in os.listdir(os.path.join(S, "SiftGPU")):
+        if f.endswith(".h") or f == "SIFTImageManager.cu":
+            shutil.copy(os.path.join(S, "SiftGPU", f), os.path.join(src, "SiftGPU"))
+    for f in ("GlobalDefines.h", "CUDACacheUtil.h", "mLibCuda.h"):
+        shutil.copy(os.path.join(S, f), src)
+    sg = os.path.join(src, "SiftGPU")
+    patch(os.path.join(sg, "cuda_SimpleMatrixUtil.h"),
+          [(r"\ninline __device__ __host__ matNxM<4, 1>::operator float4\(\)", "\ntemplate<> inline __device__ __host__ matNxM<4, 1>::operator float4()", 1)])
+    for f in os.listdir(sg):
+        patch(os.path.join(sg, f), [(r"__shfl_down\(", "__shfl_down_sync(0xffffffffu, ", None), (r"__shfl_xor\(", "__shfl_xor_sync(0xffffffffu, ", None)])
+    st = os.path.join(root, "stubs")
+    open(os.path.join(st, "windows.h"), "w").write("#pragma once\n#include <cfloat>\n#include <mutex>\n#include <list>\n#include <string>\n#include <fstream>\n#include <algorithm>\n")
+    open(os.path.join(st, "conio.h"), "w").write("#pragma once\n")
+    open(os.path.join(st, "core-base", "common.h"), "w").write(
+        "#pragma once\n#include <stdexcept>\n#include <string>\n#define MLIB_EXCEPTION(s) std::runtime_error(std::string(s))\n"
+        "#define MLIB_ASSERT(x)\n#define SAFE_DELETE_ARRAY(p) { if (p) { delete[] (p); (p) = NULL; } }\n")
+    base = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-w", "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic",
+            "-Xcompiler", "-fpermissive", "-I", st, "-I", src, "-I", sg, "-I", os.path.join(REF, "Include", "cutil", "inc")]
+    for name, extra in (("libref_siftmgr_fast.so", ["--use_fast_math"]), ("libref_siftmgr.so", [])):
+        cmd = base + extra + [os.path.join(HERE, "ref_siftmgr_wrap.cu"), "-o", os.path.join(OUT, name), "-lcudart"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout[-6000:])
             raise RuntimeError(f"building {name} failed")
 
 
