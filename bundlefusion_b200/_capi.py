@@ -118,13 +118,19 @@ BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updat
                    "bfTrajectoryGetOptimizedTransforms"]
 
 SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftSortKeyPointMatches", "bfSiftFilterKeyPointMatches", "bfSiftFilterMatchesBySurfaceArea", "bfSiftFilterMatchesByDenseVerify",
-                "bfSiftAddCurrToResiduals", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace"]
+                "bfSiftAddCurrToResiduals", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace", "bfSiftDetect", "bfSiftDetectWorkspaceBytes",
+                "bfSiftDetectReleaseWorkspace"]
 
 SOLVER_SYMBOLS = [
     "solveBundlingStub", "buildVariablesToCorrespondencesTableCUDA", "evalMaxResidual", "countHighResiduals", "collectHighResiduals",
     "convertLiePosesToMatricesCU", "convertMatricesToPosesCU", "convertPosesToMatricesCU",
     "bfSolverSolve", "bfSolverGetStats", "bfSolverMaxResidual", "bfSolverWorkspaceBytes", "bfSolverReleaseWorkspace",
 ]
+
+
+class BFSiftDetectParams(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depthWidth", C.c_uint32), ("depthHeight", C.c_uint32), ("depthMin", C.c_float),
+                ("depthMax", C.c_float), ("minKeyScale", C.c_float), ("featureCountThreshold", C.c_int32), ("maxKeyPoints", C.c_uint32)]
 
 
 class BFImagePairMatch(C.Structure):      # FL/SiftGPU/SIFTImageManager.h:38-42
@@ -304,6 +310,8 @@ def lib() -> C.CDLL:
     L.bfSiftFilterMatchesBySurfaceArea.argtypes = [C.c_uint, C.c_uint, C.c_uint, vp, vp, vp, P(C.c_float), C.c_float, vp]
     L.bfSiftFilterMatchesByDenseVerify.argtypes = [C.c_uint] * 5 + [P(C.c_float), vp, vp, vp] + [C.c_float] * 7 + [vp]
     L.bfSiftWorkspaceBytes.restype = C.c_size_t
+    L.bfSiftDetect.argtypes = [P(BFSiftDetectParams), vp, vp, vp, vp, vp, vp]
+    L.bfSiftDetectWorkspaceBytes.restype = C.c_size_t
     _lib = L
     return L
 

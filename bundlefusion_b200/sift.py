@@ -70,3 +70,43 @@ class SiftMatchGPU:
         pairs = list(pairs)
         arr = (BFSiftMatchJob * len(pairs))(*[self._job(*p) for p in pairs])
         capi.check(self.lib.bfSiftMatchBatch(arr, len(pairs), distmax, ratiomax), "bfSiftMatchBatch")
+
+
+class SiftGPU:
+    """Mirror of ``SiftGPU`` as ``Bundler`` drives it (FL/Bundler.cpp:55-100; FL/SiftGPU/SiftGPU.cpp): ``SetParams`` latches the image size,
+    the feature-count threshold and the depth range, ``RunSIFT`` + ``GetKeyPointsAndDescriptorsCUDA`` become one asynchronous
+    ``bfSiftDetect``.  The count stays on the device; ``GetFeatureNum`` synchronises to read it.
+    STATUS: the CUDA path behind it has been verified under CPU emulation only (tests/test_sift_detect_emulated.py)."""
+
+    def __init__(self, device="cuda:0"):
+        import torch
+        self._torch = torch
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("SiftGPU needs a CUDA device (no CPU fallback)")
+        self.lib = capi.lib()
+        self._p = None
+        self._num = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._levels = torch.zeros(12, dtype=torch.int32, device=self.device)
+
+    def SetParams(self, siftWidth: int, siftHeight: int, enableTiming: bool, featureCountThreshold: int, siftDepthMin: float, siftDepthMax: float,
+                  depthWidth: int | None = None, depthHeight: int | None = None, minKeyScale: float = 3.0):
+        """SiftGPU.cpp:224-254; depth size and minKeyScale are what the reference reads from c_siftCameraParams (FL/OnlineBundler.cpp:45-56)."""
+        self._p = capi.BFSiftDetectParams(siftWidth, siftHeight, depthWidth or siftWidth, depthHeight or siftHeight, siftDepthMin, siftDepthMax, minKeyScale,
+                                          int(featureCountThreshold), 0)
+
+    def RunSIFT(self, d_intensity, d_depth, d_keyPoints, d_keyPointDescs, maxNumKeyPoints: int) -> int:
+        """RunSIFT + GetKeyPointsAndDescriptorsCUDA: d_intensity float32 [H, W] in 0..1, d_depth float32 [Hd, Wd]; outputs float32
+        [maxNumKeyPoints, 4] and uint8 [maxNumKeyPoints, 128] cuda tensors.  Returns 1 (launched) like the reference's success flag."""
+        if self._p is None:
+            raise RuntimeError("SetParams first")
+        t = self._torch
+        t.cuda.set_device(self.device)
+        self.lib.bfSetStream(C.c_void_p(t.cuda.current_stream(self.device).cuda_stream))
+        self._p.maxKeyPoints = int(maxNumKeyPoints)
+        capi.check(self.lib.bfSiftDetect(C.byref(self._p), d_intensity.data_ptr(), d_depth.data_ptr(), d_keyPoints.data_ptr(), d_keyPointDescs.data_ptr(),
+                                         self._num.data_ptr(), self._levels.data_ptr()), "bfSiftDetect")
+        return 1
+
+    def GetFeatureNum(self) -> int:
+        return int(self._num.item())

@@ -112,6 +112,32 @@ int bfSiftAddCurrToResiduals(unsigned int curFrame, unsigned int startFrame, uns
                              uint32_t* d_globMatchesKeyPointIndices, int32_t* d_globNumResiduals, const int32_t* d_currNumFilteredMatchesPerImagePair,
                              const uint32_t* d_currFilteredMatchKeyPointIndices, const BFSIFTKeyPoint* d_keyPoints, const float* colorIntrinsicsInv);
 
+/* ---- row a17: SIFT detection and description ----
+ * SiftGPU::SetParams(width, height, timing, featureCountThreshold, depthMin, depthMax) (FL/SiftGPU/SiftGPU.cpp:224-254) +
+ * SiftGPU::RunSIFT(d_intensity, d_depth) (:86-103) + SiftGPU::GetKeyPointsAndDescriptorsCUDA(siftImage, d_depth, maxNumKeyPoints) (:267-272), as
+ * Bundler::detectFeatures calls them (FL/Bundler.cpp:55-100): four octaves from octave 0, three DoG levels each, no sub-pixel step, key
+ * points only where the depth map holds a value in [depthMin, depthMax], up to two orientations per key point, 128-byte descriptors
+ * (unit vector x 512), whole levels dropped from the fine end while more than featureCountThreshold features would remain without them,
+ * scale >= minKeyScale (c_siftCameraParams.m_minKeyScale).  d_intensity: [height][width] floats in 0..1; d_depth: [depthHeight][depthWidth]
+ * floats, -inf = invalid.  Outputs: d_keyPoints[maxKeyPoints] (x, y, scale, depth -- SIFTKeyPoint), d_descriptors[maxKeyPoints][128],
+ * *d_numKeyPoints (DEVICE counter: the reference copies its level counts to the host mid-way, this path never leaves the device),
+ * d_levelCounts: optional device int[12], features per (octave, level).  width must be a multiple of 32, height of 8, both >= 64.
+ * Differences from the reference (its lists are appended with atomicAdd): key points of a level come in raster order, an orientation
+ * pair as (first, second); histogram sums are taken in scheduling order here as there.  Asynchronous on the library stream.
+ * STATUS: compiled for sm_100a, not yet run on hardware (see csrc/sift_detect.cu). */
+typedef struct BFSiftDetectParams {
+    uint32_t width, height;              /* SIFT (intensity) image */
+    uint32_t depthWidth, depthHeight;
+    float depthMin, depthMax;
+    float minKeyScale;
+    int32_t featureCountThreshold;       /* 150 in FL/Bundler.cpp:61; <= 0: no limit */
+    uint32_t maxKeyPoints;               /* capacity of the two output arrays (s_maxNumKeysPerImage) */
+} BFSiftDetectParams;
+int bfSiftDetect(const BFSiftDetectParams* params, const float* d_intensity, const float* d_depth, BFSIFTKeyPoint* d_keyPoints, uint8_t* d_descriptors,
+                 int32_t* d_numKeyPoints, int32_t* d_levelCounts);
+size_t bfSiftDetectWorkspaceBytes(void);
+int bfSiftDetectReleaseWorkspace(void);
+
 /* device scratch the matcher holds (rowResult / rowDist per job); released by bfSiftReleaseWorkspace */
 size_t bfSiftWorkspaceBytes(void);
 int bfSiftReleaseWorkspace(void);

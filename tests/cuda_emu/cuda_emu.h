@@ -1,0 +1,102 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE ONLY.  A minimal host emulation of the CUDA constructs csrc/sift_detect.cu uses, so that the very same
+// kernel source can be executed on the CPU (tests/test_sift_detect_emulated.py): one OS thread per CUDA thread of a block, blocks run one
+// after the other, __syncthreads / warp collectives on a block-wide barrier, __shared__ as function-static storage.  It checks the
+// kernels' LOGIC (tiling, halos, scans, ranks, list layout) against the oracle when no GPU is at hand; it says nothing about performance
+// and is never part of the product (the library has no CPU path).
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __grid_constant__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define BF_API extern "C"
+
+struct float2 { float x, y; }; struct float4 { float x, y, z, w; }; struct int2 { int x, y; }; struct uint2 { unsigned x, y; };
+static inline float2 make_float2(float x, float y) { return { x, y }; }
+static inline float4 make_float4(float x, float y, float z, float w) { return { x, y, z, w }; }
+static inline int2 make_int2(int x, int y) { return { x, y }; }
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+struct uint3 { unsigned x, y, z; };
+
+typedef int cudaError_t; typedef void* cudaStream_t;
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(1, n); return *p ? 0 : 2; }
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n); }
+static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+
+namespace emu {
+struct Barrier {                     // reusable counting barrier
+    std::mutex m; std::condition_variable cv; unsigned n = 1, waiting = 0, gen = 0;
+    void wait() { std::unique_lock<std::mutex> lk(m); const unsigned g = gen; if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); } else cv.wait(lk, [&] { return gen != g; }); }
+};
+inline Barrier g_bar;
+inline std::mutex g_atomic;
+inline float g_xchg[1024]; inline unsigned g_vote[32];
+inline std::vector<float> g_dynSmem;
+}  // namespace emu
+
+inline thread_local uint3 threadIdx, blockIdx; inline thread_local dim3 blockDim, gridDim;
+alignas(16) inline float sm[64 * 1024];                                       // `extern __shared__ float sm[]`
+#define extern_shared_decl
+
+static inline void __syncthreads() { emu::g_bar.wait(); }
+static inline float atomicAdd(float* p, float v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const float o = *p; *p = o + v; return o; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned __ballot_sync(unsigned, bool pred) {                   // called by every thread of the block at the same point
+    const unsigned t = threadIdx.x, w = t >> 5;
+    if ((t & 31) == 0) emu::g_vote[w] = 0;
+    emu::g_bar.wait();
+    if (pred) { std::lock_guard<std::mutex> lk(emu::g_atomic); emu::g_vote[w] |= 1u << (t & 31); }
+    emu::g_bar.wait();
+    const unsigned r = emu::g_vote[w];
+    emu::g_bar.wait();
+    return r;
+}
+static inline float __shfl_xor_sync(unsigned, float v, int mask) {
+    const unsigned t = threadIdx.x;
+    emu::g_xchg[t] = v;
+    emu::g_bar.wait();
+    const float r = emu::g_xchg[(t & ~31u) | ((t ^ (unsigned)mask) & 31u)];
+    emu::g_bar.wait();
+    return r;
+}
+
+// kernel<<<grid, block, smem, stream>>>(args...) is rewritten by the test into EMU_LAUNCH(kernel, grid, block, args...)
+template <class K, class... A>
+static inline void emu_launch(K kernel, dim3 grid, dim3 block, A... args) {
+    const unsigned nt = block.x * block.y * block.z;
+    emu::g_bar.n = nt;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([=]() {
+            blockDim = block; gridDim = grid;
+            threadIdx = { t % block.x, (t / block.x) % block.y, t / (block.x * block.y) };
+            for (unsigned by = 0; by < grid.y; ++by)
+                for (unsigned bx = 0; bx < grid.x; ++bx) {
+                    blockIdx = { bx, by, 0 };
+                    kernel(args...);
+                    emu::g_bar.wait();                                        // block boundary: function-static "shared" storage is reused
+                }
+        });
+    for (auto& x : th) x.join();
+}
+#define EMU_LAUNCH(kernel, grid, block, ...) emu_launch(kernel, dim3(grid), dim3(block), ##__VA_ARGS__)
