@@ -119,7 +119,7 @@ BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updat
 
 SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftSortKeyPointMatches", "bfSiftFilterKeyPointMatches", "bfSiftFilterMatchesBySurfaceArea", "bfSiftFilterMatchesByDenseVerify",
                 "bfSiftAddCurrToResiduals", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace", "bfSiftDetect", "bfSiftDetectWorkspaceBytes",
-                "bfSiftDetectReleaseWorkspace"]
+                "bfSiftDetectReleaseWorkspace", "bfSiftInvalidateImageToImage", "bfSiftCheckForInvalidFrames"]
 
 SOLVER_SYMBOLS = [
     "solveBundlingStub", "buildVariablesToCorrespondencesTableCUDA", "evalMaxResidual", "countHighResiduals", "collectHighResiduals",
@@ -311,6 +311,8 @@ def lib() -> C.CDLL:
     L.bfSiftFilterMatchesByDenseVerify.argtypes = [C.c_uint] * 5 + [P(C.c_float), vp, vp, vp] + [C.c_float] * 7 + [vp]
     L.bfSiftWorkspaceBytes.restype = C.c_size_t
     L.bfSiftDetect.argtypes = [P(BFSiftDetectParams), vp, vp, vp, vp, vp, vp]
+    L.bfSiftInvalidateImageToImage.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint]
+    L.bfSiftCheckForInvalidFrames.argtypes = [vp, vp, C.c_uint, vp, C.c_uint, C.c_int]
     L.bfSiftDetectWorkspaceBytes.restype = C.c_size_t
     _lib = L
     return L

@@ -112,6 +112,19 @@ int bfSiftAddCurrToResiduals(unsigned int curFrame, unsigned int startFrame, uns
                              uint32_t* d_globMatchesKeyPointIndices, int32_t* d_globNumResiduals, const int32_t* d_currNumFilteredMatchesPerImagePair,
                              const uint32_t* d_currFilteredMatchKeyPointIndices, const BFSIFTKeyPoint* d_keyPoints, const float* colorIntrinsicsInv);
 
+/* SIFTImageManager::InvalidateImageToImageCU(imageToImageIdx) (FL/SiftGPU/SIFTImageManager.cu:692-720): every correspondence of the global list
+ * between images (imgIdx_i, imgIdx_j) -- in that order -- is marked invalid (both indices 0xFFFFFFFF).  This is what SBA::removeMaxResidualCUDA
+ * (FL/SBA.cpp:165-203) does with the pair the solver's max-residual search returns.  Asynchronous. */
+int bfSiftInvalidateImageToImage(BFEntryJ* d_globMatches, unsigned int globNumResiduals, unsigned int imgIdx_i, unsigned int imgIdx_j);
+
+/* SIFTImageManager::CheckForInvalidFramesSimpleCU / CheckForInvalidFramesCU(d_varToCorrNumEntriesPerRow, numVars) (:724-790): images whose row of
+ * the solver's variable-to-correspondence table is empty lose their flag in d_validImages (the reference round-trips that array through the host
+ * around the kernel; here it stays on the device).  comprehensive != 0 (s_useComprehensiveFrameInvalidation) additionally invalidates every
+ * still-valid correspondence touching such an image -- for EVERY (image, correspondence) combination, which is what the reference's kernel is
+ * written to do; its grid arithmetic (resIdx = blockDim.x * blockIdx.x + blockIdx.y) reaches only part of them.  Asynchronous. */
+int bfSiftCheckForInvalidFrames(const int32_t* d_varToCorrNumEntriesPerRow, int32_t* d_validImages, unsigned int numVars, BFEntryJ* d_globMatches,
+                                unsigned int globNumResiduals, int comprehensive);
+
 /* ---- row a17: SIFT detection and description ----
  * SiftGPU::SetParams(width, height, timing, featureCountThreshold, depthMin, depthMax) (FL/SiftGPU/SiftGPU.cpp:224-254) +
  * SiftGPU::RunSIFT(d_intensity, d_depth) (:86-103) + SiftGPU::GetKeyPointsAndDescriptorsCUDA(siftImage, d_depth, maxNumKeyPoints) (:267-272), as

@@ -525,3 +525,23 @@ ORC_API void orc_sift_filter_dense_verify(unsigned curFrame, unsigned startFrame
         if (corr < corrThresh || err > errThresh || err != err) numFiltered[p] = 0;
     }
 }
+
+/* ---- invalidation after a solve: InvalidateImageToImageCU_Kernel, CheckForInvalidFramesSimpleCU_Kernel / CheckForInvalidFramesCU_Kernel
+ * (FL/SiftGPU/SIFTImageManager.cu:692-790).  entries: EntryJ records of 32 bytes.  The comprehensive variant is restated by its intent
+ * (every still-valid correspondence touching an image with an empty table row), not by the reference's partial grid coverage. ---- */
+ORC_API void orc_sift_invalidate_image_to_image(uint8_t* entries, unsigned numResiduals, unsigned imgI, unsigned imgJ) {
+    for (unsigned k = 0; k < numResiduals; ++k) {
+        uint32_t ij[2]; memcpy(ij, entries + 32 * (size_t)k, 8);
+        if (ij[0] == imgI && ij[1] == imgJ) { ij[0] = ij[1] = 0xFFFFFFFFu; memcpy(entries + 32 * (size_t)k, ij, 8); }
+    }
+}
+ORC_API void orc_sift_check_invalid_frames(const int32_t* numEntriesPerRow, int32_t* validImages, unsigned numVars, uint8_t* entries, unsigned numResiduals, int comprehensive) {
+    if (comprehensive)
+        for (unsigned k = 0; k < numResiduals; ++k) {
+            uint32_t ij[2]; memcpy(ij, entries + 32 * (size_t)k, 8);
+            if (ij[0] != 0xFFFFFFFFu && ((ij[0] < numVars && numEntriesPerRow[ij[0]] == 0) || (ij[1] < numVars && numEntriesPerRow[ij[1]] == 0))) {
+                ij[0] = ij[1] = 0xFFFFFFFFu; memcpy(entries + 32 * (size_t)k, ij, 8);
+            }
+        }
+    for (unsigned v = 0; v < numVars; ++v) if (numEntriesPerRow[v] == 0) validImages[v] = 0;
+}

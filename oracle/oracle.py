@@ -552,3 +552,23 @@ def sift_filter_bank():
     L.orc_sift_filter_bank.argtypes = [C.c_void_p] * 3
     L.orc_sift_filter_bank(s.ctypes.data, w.ctypes.data, t.ctypes.data)
     return s, w, t
+
+
+def sift_invalidate_image_to_image(entries, imgI, imgJ):
+    """InvalidateImageToImageCU on a structured EntryJ array (copy returned)."""
+    L = lib()
+    e = np.ascontiguousarray(entries).copy()
+    L.orc_sift_invalidate_image_to_image.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
+    L.orc_sift_invalidate_image_to_image.restype = None
+    L.orc_sift_invalidate_image_to_image(e.ctypes.data, len(e), imgI, imgJ)
+    return e
+
+
+def sift_check_invalid_frames(numEntriesPerRow, validImages, entries, comprehensive):
+    """CheckForInvalidFrames(Simple)CU: returns (validImages', entries')."""
+    L = lib()
+    n = np.ascontiguousarray(numEntriesPerRow, np.int32); v = np.ascontiguousarray(validImages, np.int32).copy(); e = np.ascontiguousarray(entries).copy()
+    L.orc_sift_check_invalid_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_int]
+    L.orc_sift_check_invalid_frames.restype = None
+    L.orc_sift_check_invalid_frames(n.ctypes.data, v.ctypes.data, len(n), e.ctypes.data, len(e), int(comprehensive))
+    return v, e

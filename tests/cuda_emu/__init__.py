@@ -1,0 +1,27 @@
+"""TEST INFRASTRUCTURE ONLY: builds a CPU-executable twin of a csrc/*.cu file on top of cuda_emu.h (see its header)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def build_emulated(cu_name: str, expected_launches: int) -> C.CDLL:
+    src = open(os.path.join(ROOT, "bundlefusion_b200", "csrc", cu_name)).read()
+    src = src.replace('#include "bf_common.cuh"', "")
+    src = src.replace("extern __shared__ float sm[];", "")
+    src, n = re.subn(r"(\w+(?:<\w+>)?)<<<\s*([^,]+),\s*([^,]+),\s*[^,]+,\s*[^>]+>>>\(", r"EMU_LAUNCH(\1, \2, \3, ", src)
+    assert n == expected_launches, (cu_name, n)
+    pre = ('#include "%s"\n' % os.path.join(ROOT, "tests", "cuda_emu", "cuda_emu.h") +
+           "#define BF_CHECK(e) do { int _e = (int)(e); if (_e) return _e; } while (0)\n"
+           "namespace bf { unsigned long long g_launchCount = 0; static inline cudaStream_t stream() { return nullptr; } }\n")
+    d = tempfile.mkdtemp(prefix="bf_emu_")
+    cpp = os.path.join(d, cu_name.replace(".cu", "_emu.cpp"))
+    open(cpp, "w").write(pre + src)
+    so = os.path.join(d, "lib" + cu_name.replace(".cu", "_emu.so"))
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "bundlefusion_b200", "csrc"),
+                        cpp, "-o", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return C.CDLL(so)

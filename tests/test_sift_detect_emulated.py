@@ -6,36 +6,19 @@ oracle, so everything but the order of the histogram additions is bit-comparable
 path and this emulation is never shipped."""
 import ctypes as C
 import os
-import re
-import subprocess
-import tempfile
 
 import numpy as np
 import pytest
 
 from oracle import oracle as orc
+from tests.cuda_emu import build_emulated
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
 def emu():
-    src = open(os.path.join(ROOT, "bundlefusion_b200", "csrc", "sift_detect.cu")).read()
-    src = src.replace('#include "bf_common.cuh"', "")
-    src = src.replace("extern __shared__ float sm[];", "")
-    src, n = re.subn(r"(\w+(?:<\w+>)?)<<<\s*([^,]+),\s*([^,]+),\s*[^,]+,\s*[^>]+>>>\(", r"EMU_LAUNCH(\1, \2, \3, ", src)
-    assert n == 7, n
-    pre = ('#include "%s"\n' % os.path.join(ROOT, "tests", "cuda_emu", "cuda_emu.h") +
-           "#define BF_CHECK(e) do { int _e = (int)(e); if (_e) return _e; } while (0)\n"
-           "namespace bf { unsigned long long g_launchCount = 0; static inline cudaStream_t stream() { return nullptr; } }\n")
-    d = tempfile.mkdtemp(prefix="bf_emu_")
-    cpp = os.path.join(d, "sift_detect_emu.cpp")
-    open(cpp, "w").write(pre + src)
-    so = os.path.join(d, "libsift_detect_emu.so")
-    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "bundlefusion_b200", "csrc"),
-                        cpp, "-o", so], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    L = C.CDLL(so)
+    L = build_emulated("sift_detect.cu", 7)
     L.bfSiftDetect.argtypes = [C.c_void_p] * 7
     return L
 
