@@ -119,7 +119,8 @@ BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updat
 
 SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftSortKeyPointMatches", "bfSiftFilterKeyPointMatches", "bfSiftFilterMatchesBySurfaceArea", "bfSiftFilterMatchesByDenseVerify",
                 "bfSiftAddCurrToResiduals", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace", "bfSiftDetect", "bfSiftDetectWorkspaceBytes",
-                "bfSiftDetectReleaseWorkspace", "bfSiftInvalidateImageToImage", "bfSiftCheckForInvalidFrames"]
+                "bfSiftDetectReleaseWorkspace", "bfSiftInvalidateImageToImage", "bfSiftCheckForInvalidFrames", "bfSiftFilterFrames",
+                "bfSiftAddCurrToResidualsIfMatched"]
 
 SOLVER_SYMBOLS = [
     "solveBundlingStub", "buildVariablesToCorrespondencesTableCUDA", "evalMaxResidual", "countHighResiduals", "collectHighResiduals",
@@ -312,6 +313,8 @@ def lib() -> C.CDLL:
     L.bfSiftWorkspaceBytes.restype = C.c_size_t
     L.bfSiftDetect.argtypes = [P(BFSiftDetectParams), vp, vp, vp, vp, vp, vp]
     L.bfSiftInvalidateImageToImage.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint]
+    L.bfSiftFilterFrames.argtypes = [C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
+    L.bfSiftAddCurrToResidualsIfMatched.argtypes = [C.c_uint, C.c_uint, C.c_uint] + [vp] * 6 + [P(C.c_float), vp]
     L.bfSiftCheckForInvalidFrames.argtypes = [vp, vp, C.c_uint, vp, C.c_uint, C.c_int]
     L.bfSiftDetectWorkspaceBytes.restype = C.c_size_t
     _lib = L

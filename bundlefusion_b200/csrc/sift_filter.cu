@@ -246,14 +246,33 @@ sift_filter_kernel(const __grid_constant__ FilterArgs a) {
 struct AddArgs {
     unsigned curFrame, startFrame, numFrames;
     BFEntryJ* glob; uint2* globIdx; int* globNum; const int* numFiltered; const uint2* fIdxs; const KeyPoint* kp;
+    const int* lastMatched;           // optional device predicate (bfSiftFilterFrames): nothing is appended when *lastMatched < 0
     float Ki[16];
 };
+// SIFTImageManager::filterFrames (FL/SiftGPU/SIFTImageManager.cpp:551-575) without its host round trip: the LAST frame i in
+// [startFrame, numFrames), i != curFrame, that is valid and has filtered matches; the current frame is valid iff there is one
+__global__ void __launch_bounds__(256)
+sift_filter_frames_kernel(unsigned curFrame, unsigned startFrame, unsigned numFrames, const int* __restrict__ numFiltered, int* validImages, int* lastMatched) {
+    __shared__ int sBest[256];
+    int best = -1;
+    for (unsigned i = startFrame + threadIdx.x; i < numFrames; i += blockDim.x)
+        if (i != curFrame && validImages[i] != 0 && numFiltered[i] > 0) best = (int)i;       // strided ascending: the last hit of a thread is its largest
+    sBest[threadIdx.x] = best;
+    __syncthreads();
+    for (unsigned off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off && sBest[threadIdx.x + off] > sBest[threadIdx.x]) sBest[threadIdx.x] = sBest[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { validImages[curFrame] = sBest[0] >= 0 ? 1 : 0; *lastMatched = sBest[0]; }
+}
+
 // AddCurrToResidualsCU_Kernel (SIFTImageManager.cu:610-655), one CTA: slots are handed out in ascending pair order
 __global__ void __launch_bounds__(1024)
 sift_add_residuals_kernel(const __grid_constant__ AddArgs a) {
     __shared__ int sBase;             // running base while pairs are walked in chunks of blockDim.x
     __shared__ int sScan[1024];
     const unsigned t = threadIdx.x;
+    if (a.lastMatched && *a.lastMatched < 0) return;            // Bundler::matchAndFilter: `if (lastMatchedFrame != -1) AddCurrToResidualsCU(...)`
     if (t == 0) sBase = *a.globNum;
     __syncthreads();
     for (unsigned p0 = a.startFrame; p0 < a.numFrames; p0 += blockDim.x) {
@@ -295,11 +314,22 @@ sift_add_residuals_kernel(const __grid_constant__ AddArgs a) {
 
 using namespace bf;
 
-BF_API int bfSiftAddCurrToResiduals(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, BFEntryJ* d_globMatches,
-                                    uint32_t* d_globMatchesKeyPointIndices, int32_t* d_globNumResiduals, const int32_t* d_currNumFilteredMatchesPerImagePair,
-                                    const uint32_t* d_currFilteredMatchKeyPointIndices, const BFSIFTKeyPoint* d_keyPoints, const float* colorIntrinsicsInv) {
+BF_API int bfSiftFilterFrames(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const int32_t* d_currNumFilteredMatchesPerImagePair,
+                              int32_t* d_validImages, int32_t* d_lastMatchedFrame) {
+    if (!d_currNumFilteredMatchesPerImagePair || !d_validImages || !d_lastMatchedFrame || curFrame >= numFrames) return (int)cudaErrorInvalidValue;
+    ++g_launchCount;
+    sift_filter_frames_kernel<<<1, 256, 0, stream()>>>(curFrame, startFrame, numFrames, d_currNumFilteredMatchesPerImagePair, d_validImages, d_lastMatchedFrame);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static int add_curr_to_residuals(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, BFEntryJ* d_globMatches,
+                                 uint32_t* d_globMatchesKeyPointIndices, int32_t* d_globNumResiduals, const int32_t* d_currNumFilteredMatchesPerImagePair,
+                                 const uint32_t* d_currFilteredMatchKeyPointIndices, const BFSIFTKeyPoint* d_keyPoints, const float* colorIntrinsicsInv,
+                                 const int32_t* d_lastMatchedFrame) {
     if (numFrames <= startFrame) return 0;
     AddArgs a;
+    a.lastMatched = d_lastMatchedFrame;
     a.curFrame = curFrame; a.startFrame = startFrame; a.numFrames = numFrames;
     a.glob = d_globMatches; a.globIdx = reinterpret_cast<uint2*>(d_globMatchesKeyPointIndices); a.globNum = d_globNumResiduals;
     a.numFiltered = d_currNumFilteredMatchesPerImagePair; a.fIdxs = reinterpret_cast<const uint2*>(d_currFilteredMatchKeyPointIndices);
@@ -309,6 +339,22 @@ BF_API int bfSiftAddCurrToResiduals(unsigned int curFrame, unsigned int startFra
     sift_add_residuals_kernel<<<1, 1024, 0, stream()>>>(a);
     BF_CHECK(cudaGetLastError());
     return 0;
+}
+
+BF_API int bfSiftAddCurrToResiduals(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, BFEntryJ* d_globMatches,
+                                    uint32_t* d_globMatchesKeyPointIndices, int32_t* d_globNumResiduals, const int32_t* d_currNumFilteredMatchesPerImagePair,
+                                    const uint32_t* d_currFilteredMatchKeyPointIndices, const BFSIFTKeyPoint* d_keyPoints, const float* colorIntrinsicsInv) {
+    return add_curr_to_residuals(curFrame, startFrame, numFrames, d_globMatches, d_globMatchesKeyPointIndices, d_globNumResiduals, d_currNumFilteredMatchesPerImagePair,
+                                 d_currFilteredMatchKeyPointIndices, d_keyPoints, colorIntrinsicsInv, nullptr);
+}
+
+BF_API int bfSiftAddCurrToResidualsIfMatched(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, BFEntryJ* d_globMatches,
+                                             uint32_t* d_globMatchesKeyPointIndices, int32_t* d_globNumResiduals, const int32_t* d_currNumFilteredMatchesPerImagePair,
+                                             const uint32_t* d_currFilteredMatchKeyPointIndices, const BFSIFTKeyPoint* d_keyPoints, const float* colorIntrinsicsInv,
+                                             const int32_t* d_lastMatchedFrame) {
+    if (!d_lastMatchedFrame) return (int)cudaErrorInvalidValue;
+    return add_curr_to_residuals(curFrame, startFrame, numFrames, d_globMatches, d_globMatchesKeyPointIndices, d_globNumResiduals, d_currNumFilteredMatchesPerImagePair,
+                                 d_currFilteredMatchKeyPointIndices, d_keyPoints, colorIntrinsicsInv, d_lastMatchedFrame);
 }
 
 BF_API int bfSiftFilterKeyPointMatches(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const BFSIFTKeyPoint* d_keyPoints,

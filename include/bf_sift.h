@@ -151,6 +151,21 @@ int bfSiftDetect(const BFSiftDetectParams* params, const float* d_intensity, con
 size_t bfSiftDetectWorkspaceBytes(void);
 int bfSiftDetectReleaseWorkspace(void);
 
+/* SIFTImageManager::filterFrames(curFrame, startFrame, numFrames) (FL/SiftGPU/SIFTImageManager.cpp:551-575) without its host round trip (the
+ * reference copies the filtered-match counts to the host, searches there and copies one flag back): *d_lastMatchedFrame = the LAST frame i in
+ * [startFrame, numFrames), i != curFrame, with d_validImages[i] != 0 and filtered matches, or -1; d_validImages[curFrame] = 1 if there is one,
+ * else 0.  One CTA.  Asynchronous. */
+int bfSiftFilterFrames(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const int32_t* d_currNumFilteredMatchesPerImagePair,
+                       int32_t* d_validImages, int32_t* d_lastMatchedFrame);
+
+/* bfSiftAddCurrToResiduals under the condition Bundler::matchAndFilter puts on it (FL/Bundler.cpp:218-219: only when filterFrames found a
+ * matched frame), evaluated on the device: nothing is appended when *d_lastMatchedFrame < 0.  With bfSiftFilterFrames this makes the whole
+ * match -> sort -> filter -> verify -> residuals chain of a frame free of host synchronisation. */
+int bfSiftAddCurrToResidualsIfMatched(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, BFEntryJ* d_globMatches,
+                                      uint32_t* d_globMatchesKeyPointIndices, int32_t* d_globNumResiduals, const int32_t* d_currNumFilteredMatchesPerImagePair,
+                                      const uint32_t* d_currFilteredMatchKeyPointIndices, const BFSIFTKeyPoint* d_keyPoints, const float* colorIntrinsicsInv,
+                                      const int32_t* d_lastMatchedFrame);
+
 /* device scratch the matcher holds (rowResult / rowDist per job); released by bfSiftReleaseWorkspace */
 size_t bfSiftWorkspaceBytes(void);
 int bfSiftReleaseWorkspace(void);

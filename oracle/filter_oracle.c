@@ -545,3 +545,13 @@ ORC_API void orc_sift_check_invalid_frames(const int32_t* numEntriesPerRow, int3
         }
     for (unsigned v = 0; v < numVars; ++v) if (numEntriesPerRow[v] == 0) validImages[v] = 0;
 }
+
+/* SIFTImageManager::filterFrames, FL/SiftGPU/SIFTImageManager.cpp:551-575: returns the last matched frame or -1, sets validImages[curFrame] */
+ORC_API int orc_sift_filter_frames(unsigned curFrame, unsigned startFrame, unsigned numFrames, const int32_t* numFiltered, int32_t* validImages) {
+    if (numFrames == 0) return -1;
+    int connected = 0, last = -1;
+    for (int i = (int)numFrames - 1; i >= (int)startFrame; --i)
+        if (validImages[i] != 0 && numFiltered[i] > 0 && i != (int)curFrame) { connected = 1; last = i; break; }
+    validImages[curFrame] = connected;
+    return last;
+}

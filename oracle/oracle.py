@@ -572,3 +572,12 @@ def sift_check_invalid_frames(numEntriesPerRow, validImages, entries, comprehens
     L.orc_sift_check_invalid_frames.restype = None
     L.orc_sift_check_invalid_frames(n.ctypes.data, v.ctypes.data, len(n), e.ctypes.data, len(e), int(comprehensive))
     return v, e
+
+
+def sift_filter_frames(curFrame, startFrame, numFrames, numFiltered, validImages):
+    """SIFTImageManager::filterFrames: returns (lastMatchedFrame or -1, validImages')."""
+    L = lib()
+    nf = np.ascontiguousarray(numFiltered, np.int32); v = np.ascontiguousarray(validImages, np.int32).copy()
+    L.orc_sift_filter_frames.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
+    L.orc_sift_filter_frames.restype = C.c_int
+    return L.orc_sift_filter_frames(curFrame, startFrame, numFrames, nf.ctypes.data, v.ctypes.data), v

@@ -21,7 +21,7 @@ def build_emulated(cu_name: str, expected_launches: int) -> C.CDLL:
     cpp = os.path.join(d, cu_name.replace(".cu", "_emu.cpp"))
     open(cpp, "w").write(pre + src)
     so = os.path.join(d, "lib" + cu_name.replace(".cu", "_emu.so"))
-    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "bundlefusion_b200", "csrc"),
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "tests", "cuda_emu"), "-I", os.path.join(ROOT, "bundlefusion_b200", "csrc"),
                         cpp, "-o", so], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return C.CDLL(so)

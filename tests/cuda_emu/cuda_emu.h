@@ -31,6 +31,7 @@ struct float2 { float x, y; }; struct float4 { float x, y, z, w; }; struct int2 
 static inline float2 make_float2(float x, float y) { return { x, y }; }
 static inline float4 make_float4(float x, float y, float z, float w) { return { x, y, z, w }; }
 static inline int2 make_int2(int x, int y) { return { x, y }; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return { x, y }; }
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint3 { unsigned x, y, z; };
 
@@ -79,6 +80,25 @@ static inline float __shfl_xor_sync(unsigned, float v, int mask) {
     emu::g_bar.wait();
     return r;
 }
+
+static inline float __shfl_down_sync(unsigned, float v, int delta) {         // lanes past the end keep their own value
+    const unsigned t = threadIdx.x, l = t & 31;
+    emu::g_xchg[t] = v;
+    emu::g_bar.wait();
+    const float r = (l + (unsigned)delta < 32) ? emu::g_xchg[t + delta] : v;
+    emu::g_bar.wait();
+    return r;
+}
+static inline float __shfl_sync(unsigned, float v, int src) {
+    const unsigned t = threadIdx.x;
+    emu::g_xchg[t] = v;
+    emu::g_bar.wait();
+    const float r = emu::g_xchg[(t & ~31u) | ((unsigned)src & 31u)];
+    emu::g_bar.wait();
+    return r;
+}
+static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { emu::g_bar.wait(); }      // the emulated kernels use it only in one-warp blocks, where it is the block barrier
+using std::min; using std::max;
 
 // kernel<<<grid, block, smem, stream>>>(args...) is rewritten by the test into EMU_LAUNCH(kernel, grid, block, args...)
 template <class K, class... A>

@@ -40,3 +40,22 @@ def test_check_for_invalid_frames(comprehensive):
     d_rows, d_valid, d_e = DevBuf(rows), DevBuf(valid), DevBuf(e.view(np.uint8))
     capi.check(L.bfSiftCheckForInvalidFrames(d_rows.ptr, d_valid.ptr, numVars, d_e.ptr, n, comprehensive), "check invalid frames")
     assert np.array_equal(d_valid.get(), wv) and d_e.get().tobytes() == we.tobytes()
+
+
+@pytest.mark.parametrize("seed,numFrames", [(1, 7), (2, 300), (3, 2000)])
+def test_filter_frames(seed, numFrames):
+    """bfSiftFilterFrames (csrc/sift_filter.cu) -- same pending-hardware status as the kernels above."""
+    if device_count() == 0:
+        pytest.skip("no CUDA device")
+    L = capi.lib()
+    rng = np.random.default_rng(seed)
+    for trial in range(4):
+        cur = int(rng.integers(0, numFrames)); start = int(rng.integers(0, cur + 1)) if trial % 2 else 0
+        nf = (rng.integers(0, 12, numFrames) * (rng.random(numFrames) < 0.3)).astype(np.int32)
+        if trial == 2:
+            nf[:] = 0
+        valid = (rng.random(numFrames) < 0.8).astype(np.int32)
+        want_last, want_valid = orc.sift_filter_frames(cur, start, numFrames, nf, valid)
+        d_nf, d_valid, d_last = DevBuf(nf), DevBuf(valid), DevBuf(np.full(1, 12345, np.int32))
+        capi.check(L.bfSiftFilterFrames(cur, start, numFrames, d_nf.ptr, d_valid.ptr, d_last.ptr), "filter frames")
+        assert int(d_last.get()[0]) == want_last and np.array_equal(d_valid.get(), want_valid)
