@@ -3,8 +3,8 @@
 // Behavioural source (what, not how): FL/SiftGPU/SIFTImageManager.cu:186-316 (FilterKeyPointMatchesCU), FL/SiftGPU/cuda_kabsch.h:110-502,
 // FL/SiftGPU/cuda_EigenValue.h:9-39.  The per-pair algorithm is inherently sequential (greedy insertion with re-fits), so, as in the
 // reference, one thread walks a pair's raw matches; pairs run in parallel, one warp-sized CTA each, arrays in shared memory.  The
-// device functions below follow oracle/filter_oracle.c operation for operation (this TU is built -fmad=false), including the one
-// documented difference from the reference: a cyclic-Jacobi 3x3 SVD in place of its Numerical-Recipes svdcmp.
+// device functions below follow oracle/filter_oracle.c operation for operation (this TU is built -fmad=false), including the reference's
+// own 3x3 SVD (the fast approximate one of cuda_svd3.h, with rsqrt taken as 1 / sqrtf).
 #include "../../include/bf_sift.h"
 #include "bf_common.cuh"
 #include "mat4.cuh"
@@ -39,50 +39,117 @@ __device__ void sym_eigenvalues(const float a[9], float e[3]) {
     e[1] = 3.0f * q - e[0] - e[2];
 }
 
-/* cyclic-Jacobi SVD of a 3x3 (row-major): H = U diag(s) V^T, s descending, U and V orthonormal (see header) */
-__device__ void svd3(const float H[9], float U[9], float s[3], float V[9]) {
-    float A[9];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[3 * i + j] = H[i] * H[j] + H[3 + i] * H[3 + j] + H[6 + i] * H[6 + j];      /* H^T H */
-    for (int k = 0; k < 9; ++k) V[k] = (k % 4 == 0) ? 1.0f : 0.0f;
-    const int P[3] = { 0, 0, 1 }, Q[3] = { 1, 2, 2 };
-    for (int sweep = 0; sweep < 10; ++sweep)
-        for (int r = 0; r < 3; ++r) {
-            const int p = P[r], q = Q[r];
-            const float apq = A[3 * p + q];
-            if (fabsf(apq) <= 1e-30f) continue;
-            const float theta = (A[3 * q + q] - A[3 * p + p]) / (2.0f * apq);
-            const float t = ((theta >= 0.0f) ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
-            const float c = 1.0f / sqrtf(t * t + 1.0f), sn = t * c;
-            for (int k = 0; k < 3; ++k) { const float akp = A[3 * k + p], akq = A[3 * k + q]; A[3 * k + p] = c * akp - sn * akq; A[3 * k + q] = sn * akp + c * akq; }
-            for (int k = 0; k < 3; ++k) { const float apk = A[3 * p + k], aqk = A[3 * q + k]; A[3 * p + k] = c * apk - sn * aqk; A[3 * q + k] = sn * apk + c * aqk; }
-            for (int k = 0; k < 3; ++k) { const float vkp = V[3 * k + p], vkq = V[3 * k + q]; V[3 * k + p] = c * vkp - sn * vkq; V[3 * k + q] = sn * vkp + c * vkq; }
-        }
-    float ev[3] = { A[0], A[4], A[8] };
-    int ord[3] = { 0, 1, 2 };
-    for (int i = 0; i < 2; ++i) for (int j = i + 1; j < 3; ++j) if (ev[ord[j]] > ev[ord[i]]) { const int tmp = ord[i]; ord[i] = ord[j]; ord[j] = tmp; }
-    float Vs[9];
-    for (int c = 0; c < 3; ++c) { s[c] = sqrtf(fmaxf(ev[ord[c]], 0.0f)); for (int k = 0; k < 3; ++k) Vs[3 * k + c] = V[3 * k + ord[c]]; }
-    for (int k = 0; k < 9; ++k) V[k] = Vs[k];
-    /* U columns: H v / s where s is significant, completed to a right-handed orthonormal basis otherwise */
-    float u[3][3];
-    const float tiny = 1e-7f * s[0];
-    for (int c = 0; c < 3; ++c) {
-        if (s[c] > tiny && s[c] > 0.0f) {
-            for (int k = 0; k < 3; ++k) u[c][k] = (H[3 * k] * V[c] + H[3 * k + 1] * V[3 + c] + H[3 * k + 2] * V[6 + c]) / s[c];
-        } else if (c == 2) {
-            u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1]; u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2]; u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
-        } else if (c == 1) {       /* any unit vector orthogonal to u0 */
-            const float ax = fabsf(u[0][0]), ay = fabsf(u[0][1]), az = fabsf(u[0][2]);
-            float e[3] = { 0, 0, 0 }; e[(ax <= ay && ax <= az) ? 0 : ((ay <= az) ? 1 : 2)] = 1.0f;
-            float w[3] = { u[0][1] * e[2] - u[0][2] * e[1], u[0][2] * e[0] - u[0][0] * e[2], u[0][0] * e[1] - u[0][1] * e[0] };
-            const float l = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-            for (int k = 0; k < 3; ++k) u[1][k] = w[k] / l;
-        } else { u[0][0] = 1.0f; u[0][1] = 0.0f; u[0][2] = 0.0f; }
+/* The reference's 3x3 SVD (FL/SiftGPU/cuda_svd3.h: E. Jang's version of McAdams et al., TR1690): four fixed sweeps with the approximate
+ * Givens angle, quaternion accumulation, column sort (with the reference's rho2 over b12, b22, b23), Givens QR.  Operation for operation the
+ * same as oracle/filter_oracle.c svd3_fast(), which is pinned bit for bit against the reference's own host build of that header
+ * (tests/test_kabsch_reference_host.py).  rsqrt: the reference's device build calls CUDA's rsqrtf (2 ulp); here, as in the oracle,
+ * 1 / sqrtf, individually rounded. */
+__device__ __forceinline__ float rsqrt_exact(float x) { return 1.0f / sqrtf(x); }
+__device__ void cond_swap(int c, float* X, float* Y) { const float Z = *X; *X = c ? *Y : *X; *Y = c ? Z : *Y; }
+__device__ void cond_neg_swap(int c, float* X, float* Y) { const float Z = -*X; *X = c ? *Y : *X; *Y = c ? Z : *Y; }
+
+__device__ void jacobi_conjugation(int x, int y, int z, float* s11, float* s21, float* s22, float* s31, float* s32, float* s33, float* qV) {    /* cuda_svd3.h:149-204 */
+    float ch = 2.0f * (*s11 - *s22), sh = *s21;                                  /* approximateGivensQuaternion, :134-147 */
+    const int big = 5.828427124f * sh * sh < ch * ch;
+    const float w = rsqrt_exact(ch * ch + sh * sh);
+    ch = big ? w * ch : 0.923879532f;
+    sh = big ? w * sh : 0.3826834323f;
+    const float scale = ch * ch + sh * sh;
+    const float a = (ch * ch - sh * sh) / scale, b = (2.0f * sh * ch) / scale;
+    float t11 = *s11, t21 = *s21, t22 = *s22, t31 = *s31, t32 = *s32, t33 = *s33;
+    *s11 = a * (a * t11 + b * t21) + b * (a * t21 + b * t22);
+    *s21 = a * (-b * t11 + a * t21) + b * (-b * t21 + a * t22);
+    *s22 = -b * (-b * t11 + a * t21) + a * (-b * t21 + a * t22);
+    *s31 = a * t31 + b * t32; *s32 = -b * t31 + a * t32; *s33 = t33;
+    float tmp[3] = { qV[0] * sh, qV[1] * sh, qV[2] * sh };
+    sh *= qV[3];
+    qV[0] *= ch; qV[1] *= ch; qV[2] *= ch; qV[3] *= ch;
+    qV[z] += sh; qV[3] -= tmp[z]; qV[x] += tmp[y]; qV[y] -= tmp[x];
+    t11 = *s22; t21 = *s32; t22 = *s33; t31 = *s21; t32 = *s31; t33 = *s11;      /* re-arrange for the next rotation */
+    *s11 = t11; *s21 = t21; *s22 = t22; *s31 = t31; *s32 = t32; *s33 = t33;
+}
+__device__ void qr_givens(float a1, float a2, float* ch, float* sh) {               /* QRGivensQuaternion, :265-281 */
+    const float eps = 1e-6f, q = a1 * a1 + a2 * a2;
+    const float rho = q * rsqrt_exact(q);                                              /* accurateSqrt */
+    *sh = rho > eps ? a2 : 0.0f;
+    *ch = fabsf(a1) + fmaxf(rho, eps);
+    cond_swap(a1 < 0.0f, sh, ch);
+    const float w = rsqrt_exact(*ch * *ch + *sh * *sh);
+    *ch *= w; *sh *= w;
+}
+/* svd(A) -> U, S (upper triangular R of the QR, its diagonal = singular values up to sign), V; all row-major 3x3.  cuda_svd3.h:347-393 */
+__device__ void svd3_fast(const float A[9], float U[9], float S[9], float V[9]) {
+    const float a11 = A[0], a12 = A[1], a13 = A[2], a21 = A[3], a22 = A[4], a23 = A[5], a31 = A[6], a32 = A[7], a33 = A[8];
+    /* A^T A (multAtB) */
+    float s11 = a11 * a11 + a21 * a21 + a31 * a31;
+    float s21 = a12 * a11 + a22 * a21 + a32 * a31, s22 = a12 * a12 + a22 * a22 + a32 * a32;
+    float s31 = a13 * a11 + a23 * a21 + a33 * a31, s32 = a13 * a12 + a23 * a22 + a33 * a32, s33 = a13 * a13 + a23 * a23 + a33 * a33;
+    float qV[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
+    for (int i = 0; i < 4; ++i) {                                                 /* jacobiEigenanlysis, :214-229 */
+        jacobi_conjugation(0, 1, 2, &s11, &s21, &s22, &s31, &s32, &s33, qV);
+        jacobi_conjugation(1, 2, 0, &s11, &s21, &s22, &s31, &s32, &s33, qV);
+        jacobi_conjugation(2, 0, 1, &s11, &s21, &s22, &s31, &s32, &s33, qV);
     }
-    for (int c = 0; c < 3; ++c) for (int k = 0; k < 3; ++k) U[3 * k + c] = u[c][k];
+    /* quatToMat3, :102-131 */
+    const float w = qV[3], x = qV[0], y = qV[1], z = qV[2];
+    const float qxx = x * x, qyy = y * y, qzz = z * z, qxz = x * z, qxy = x * y, qyz = y * z, qwx = w * x, qwy = w * y, qwz = w * z;
+    float v11 = 1 - 2 * (qyy + qzz), v12 = 2 * (qxy - qwz), v13 = 2 * (qxz + qwy);
+    float v21 = 2 * (qxy + qwz), v22 = 1 - 2 * (qxx + qzz), v23 = 2 * (qyz - qwx);
+    float v31 = 2 * (qxz - qwy), v32 = 2 * (qyz + qwx), v33 = 1 - 2 * (qxx + qyy);
+    /* B = A V (multAB) */
+    float b11 = a11 * v11 + a12 * v21 + a13 * v31, b12 = a11 * v12 + a12 * v22 + a13 * v32, b13 = a11 * v13 + a12 * v23 + a13 * v33;
+    float b21 = a21 * v11 + a22 * v21 + a23 * v31, b22 = a21 * v12 + a22 * v22 + a23 * v32, b23 = a21 * v13 + a22 * v23 + a23 * v33;
+    float b31 = a31 * v11 + a32 * v21 + a33 * v31, b32 = a31 * v12 + a32 * v22 + a33 * v32, b33 = a31 * v13 + a32 * v23 + a33 * v33;
+    /* sortSingularValues, :231-262 (rho2 over b12, b22, b23 as written there) */
+    float rho1 = b11 * b11 + b21 * b21 + b31 * b31, rho2 = b12 * b12 + b22 * b22 + b23 * b23, rho3 = b13 * b13 + b23 * b23 + b33 * b33;
+    int c = rho1 < rho2;
+    cond_neg_swap(c, &b11, &b12); cond_neg_swap(c, &v11, &v12); cond_neg_swap(c, &b21, &b22); cond_neg_swap(c, &v21, &v22); cond_neg_swap(c, &b31, &b32); cond_neg_swap(c, &v31, &v32);
+    cond_swap(c, &rho1, &rho2);
+    c = rho1 < rho3;
+    cond_neg_swap(c, &b11, &b13); cond_neg_swap(c, &v11, &v13); cond_neg_swap(c, &b21, &b23); cond_neg_swap(c, &v21, &v23); cond_neg_swap(c, &b31, &b33); cond_neg_swap(c, &v31, &v33);
+    cond_swap(c, &rho1, &rho3);
+    c = rho2 < rho3;
+    cond_neg_swap(c, &b12, &b13); cond_neg_swap(c, &v12, &v13); cond_neg_swap(c, &b22, &b23); cond_neg_swap(c, &v22, &v23); cond_neg_swap(c, &b32, &b33); cond_neg_swap(c, &v32, &v33);
+    /* QRDecomposition, :283-345 */
+    float ch1, sh1, ch2, sh2, ch3, sh3, r11, r12, r13, r21, r22, r23, r31, r32, r33;
+    qr_givens(b11, b21, &ch1, &sh1);
+    float a = 1 - 2 * sh1 * sh1, b = 2 * ch1 * sh1;
+    r11 = a * b11 + b * b21; r12 = a * b12 + b * b22; r13 = a * b13 + b * b23;
+    r21 = -b * b11 + a * b21; r22 = -b * b12 + a * b22; r23 = -b * b13 + a * b23;
+    r31 = b31; r32 = b32; r33 = b33;
+    qr_givens(r11, r31, &ch2, &sh2);
+    a = 1 - 2 * sh2 * sh2; b = 2 * ch2 * sh2;
+    b11 = a * r11 + b * r31; b12 = a * r12 + b * r32; b13 = a * r13 + b * r33;
+    b21 = r21; b22 = r22; b23 = r23;
+    b31 = -b * r11 + a * r31; b32 = -b * r12 + a * r32; b33 = -b * r13 + a * r33;
+    qr_givens(b22, b32, &ch3, &sh3);
+    a = 1 - 2 * sh3 * sh3; b = 2 * ch3 * sh3;
+    r11 = b11; r12 = b12; r13 = b13;
+    r21 = a * b21 + b * b31; r22 = a * b22 + b * b32; r23 = a * b23 + b * b33;
+    r31 = -b * b21 + a * b31; r32 = -b * b22 + a * b32; r33 = -b * b23 + a * b33;
+    const float sh12 = sh1 * sh1, sh22 = sh2 * sh2, sh32 = sh3 * sh3;
+    U[0] = (-1 + 2 * sh12) * (-1 + 2 * sh22);
+    U[1] = 4 * ch2 * ch3 * (-1 + 2 * sh12) * sh2 * sh3 + 2 * ch1 * sh1 * (-1 + 2 * sh32);
+    U[2] = 4 * ch1 * ch3 * sh1 * sh3 - 2 * ch2 * (-1 + 2 * sh12) * sh2 * (-1 + 2 * sh32);
+    U[3] = 2 * ch1 * sh1 * (1 - 2 * sh22);
+    U[4] = -8 * ch1 * ch2 * ch3 * sh1 * sh2 * sh3 + (-1 + 2 * sh12) * (-1 + 2 * sh32);
+    U[5] = -2 * ch3 * sh3 + 4 * sh1 * (ch3 * sh1 * sh3 + ch1 * ch2 * sh2 * (-1 + 2 * sh32));
+    U[6] = 2 * ch2 * sh2;
+    U[7] = 2 * ch3 * (1 - 2 * sh22) * sh3;
+    U[8] = (-1 + 2 * sh22) * (-1 + 2 * sh32);
+    S[0] = r11; S[1] = r12; S[2] = r13; S[3] = r21; S[4] = r22; S[5] = r23; S[6] = r31; S[7] = r32; S[8] = r33;
+    V[0] = v11; V[1] = v12; V[2] = v13; V[3] = v21; V[4] = v22; V[5] = v23; V[6] = v31; V[7] = v32; V[8] = v33;
+}
+/* svd(m, v, s) + svdAbsEV, cuda_svd3.h:436-482: U, V and the ABSOLUTE diagonal of S (the columns of U follow the sign), unsorted */
+__device__ void svd3(const float H[9], float U[9], float s[3], float V[9]) {
+    float S[9];
+    svd3_fast(H, U, S, V);
+    s[0] = S[0]; s[1] = S[4]; s[2] = S[8];
+    for (int i = 0; i < 3; ++i) if (s[i] < 0.0f) { s[i] *= -1.0f; for (int j = 0; j < 3; ++j) U[3 * j + i] *= -1.0f; }
 }
 
-__device__ float det3(const float m[9]) { return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]); }
+/* matNxM<3,3>::det, cuda_SimpleMatrixUtil.h:1544-1559 */
+__device__ float det3(const float m[9]) { return m[0] * m[4] * m[8] + m[1] * m[5] * m[6] + m[2] * m[3] * m[7] - m[6] * m[4] * m[2] - m[7] * m[5] * m[0] - m[8] * m[3] * m[1]; }
 
 /* kabsch(), cuda_kabsch.h:110-176: T (4x4 row-major) with T src ~ tgt; evs = singular values of the covariance, descending */
 __device__ void kabsch(const f3* src, const f3* tgt, unsigned n, float T[16], float evs[3]) {
@@ -97,10 +164,12 @@ __device__ void kabsch(const f3* src, const f3* tgt, unsigned n, float T[16], fl
     for (int k = 0; k < 9; ++k) H[k] /= (float)n;
     float U[9], V[9];
     svd3(H, U, evs, V);
-    /* R = V D U^T, D = diag(1, 1, det(V U^T)) */
-    float VUt[9];
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) VUt[3 * r + c] = V[3 * r] * U[3 * c] + V[3 * r + 1] * U[3 * c + 1] + V[3 * r + 2] * U[3 * c + 2];
-    const float d = (det3(VUt) < 0.0f) ? -1.0f : 1.0f;
+    { float t; if (evs[0] < evs[1]) { t = evs[0]; evs[0] = evs[1]; evs[1] = t; } if (evs[1] < evs[2]) { t = evs[1]; evs[1] = evs[2]; evs[2] = t; }
+      if (evs[0] < evs[1]) { t = evs[0]; evs[0] = evs[1]; evs[1] = t; } }          /* cuda_kabsch.h:139-141 */
+    /* R = V D U^T, D = diag(1, 1, -1) when det(U V^T) < 0 (cuda_kabsch.h:185-190): always the THIRD column, whatever the order of the values */
+    float UVt[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) UVt[3 * r + c] = U[3 * r] * V[3 * c] + U[3 * r + 1] * V[3 * c + 1] + U[3 * r + 2] * V[3 * c + 2];
+    const float d = (det3(UVt) < 0.0f) ? -1.0f : 1.0f;
     float R[9];
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[3 * r + c] = V[3 * r] * U[3 * c] + V[3 * r + 1] * U[3 * c + 1] + (V[3 * r + 2] * d) * U[3 * c + 2];
     for (int r = 0; r < 3; ++r) {

@@ -67,9 +67,9 @@ int bfSiftSortKeyPointMatches(unsigned int curFrame, unsigned int startFrame, un
  * (<= 25 matches: Kabsch re-fit after every insertion, 5-pixel proximity rule, worst residuals dropped until max residual^2 <
  * maxKabschRes2, three condition numbers <= 100) and writes the filtered matches (ascending residual), their count, the rigid transform
  * image p -> current image and its inverse.  Arrays are the manager's (raw: [p * 128 + k], filtered: [p * 25 + k], transforms [p][16]);
- * key-point indices are global indices into d_keyPoints; siftIntrinsicsInv is a HOST 4x4.  The 3x3 SVD inside the Kabsch fit is a
- * cyclic-Jacobi one (the reference: Numerical-Recipes svdcmp) -- same rotation except that a reflection is resolved on the smallest
- * singular value.  Asynchronous. */
+ * key-point indices are global indices into d_keyPoints; siftIntrinsicsInv is a HOST 4x4.  The 3x3 SVD inside the Kabsch fit is the
+ * reference's own (the fast approximate SVD of FL/SiftGPU/cuda_svd3.h, reflection fixed on the third column), operation for operation,
+ * with rsqrt taken as 1 / sqrtf (the reference's device build: CUDA's rsqrtf).  Asynchronous. */
 int bfSiftFilterKeyPointMatches(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, const BFSIFTKeyPoint* d_keyPoints,
                                 const int32_t* d_numMatchesPerImagePair, const float* d_matchDistances, const uint32_t* d_matchKeyPointIndices,
                                 int32_t* d_numFilteredMatchesPerImagePair, float* d_filteredMatchDistances, uint32_t* d_filteredMatchKeyPointIndices,

@@ -173,6 +173,14 @@ def build_siftmgr():
         if r.returncode != 0:
             sys.stderr.write(r.stdout[-6000:])
             raise RuntimeError(f"building {name} failed")
+    # the reference's host-callable Kabsch filter / eigen code, compiled by g++ (its `#ifdef __CUDACC__` picks `__host__` then): runs on the CPU
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = ["g++", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-shared", "-fPIC", "-I", st, "-I", src, "-I", sg, "-I", os.path.join(REF, "Include", "cutil", "inc"),
+           "-I", cuda_inc, os.path.join(HERE, "ref_kabsch_host.cpp"), "-o", os.path.join(OUT, "libref_kabsch_host.so"), "-lm"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-6000:])
+        raise RuntimeError("building libref_kabsch_host.so failed")
 
 
 if __name__ == "__main__":
