@@ -16,6 +16,9 @@ Patch list (each is a textual substitution on the scratch copy):
   4. CUDAConstant.cu and CUDASceneRepHashSDF.cu are compiled as ONE translation unit (the `extern __constant__` parameter blocks
      would otherwise need relocatable device code); the three parameter headers get the `#pragma once` they lack.
 Two builds: libref_tsdf_fast.so (--use_fast_math, as the reference ships: FriedLiver.vcxproj:124) and libref_tsdf.so (IEEE).
+Further outputs (see build_solver / build_siftmgr): libref_solver[_fast].so (bundle adjustment), libref_siftmgr[_fast].so (match-manager kernels),
+libref_imageutil.so (image and trajectory kernels), and libref_kabsch_host.so -- the reference's host-callable Kabsch / eigen code compiled by
+g++, which runs on the CPU.
 """
 import os
 import re
@@ -163,7 +166,7 @@ def build_siftmgr():
     open(os.path.join(st, "windows.h"), "w").write("#pragma once\n#include <cfloat>\n#include <mutex>\n#include <list>\n#include <string>\n#include <fstream>\n#include <algorithm>\n")
     open(os.path.join(st, "conio.h"), "w").write("#pragma once\n")
     open(os.path.join(st, "core-base", "common.h"), "w").write(
-        "#pragma once\n#include <stdexcept>\n#include <string>\n#define MLIB_EXCEPTION(s) std::runtime_error(std::string(s))\n"
+        "#pragma once\n#include <stdexcept>\n#include <string>\ntypedef unsigned char uchar;\n#define MLIB_EXCEPTION(s) std::runtime_error(std::string(s))\n"
         "#define MLIB_ASSERT(x)\n#define SAFE_DELETE_ARRAY(p) { if (p) { delete[] (p); (p) = NULL; } }\n")
     base = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-w", "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic",
             "-Xcompiler", "-fpermissive", "-I", st, "-I", src, "-I", sg, "-I", os.path.join(REF, "Include", "cutil", "inc")]
@@ -173,6 +176,15 @@ def build_siftmgr():
         if r.returncode != 0:
             sys.stderr.write(r.stdout[-6000:])
             raise RuntimeError(f"building {name} failed")
+    # the reference's image kernels (rows a20 / a21) and trajectory kernels (row a22): FL/CUDAImageUtil.cu, FL/OnlineBundler.cu
+    for f in ("CUDAImageUtil.cu", "CUDAImageUtil.h", "OnlineBundler.cu", "CUDACameraUtil.h"):
+        shutil.copy(os.path.join(S, f), src)
+    shutil.copy(os.path.join(S, "mLibCuda.h"), os.path.join(src, "mlibCuda.h"))          # `#include "mlibCuda.h"`: a case-insensitive file system is assumed
+    cmd = base + [os.path.join(HERE, "ref_imageutil_wrap.cu"), "-o", os.path.join(OUT, "libref_imageutil.so"), "-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-6000:])
+        raise RuntimeError("building libref_imageutil.so failed")
     # the reference's host-callable Kabsch filter / eigen code, compiled by g++ (its `#ifdef __CUDACC__` picks `__host__` then): runs on the CPU
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     cmd = ["g++", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-shared", "-fPIC", "-I", st, "-I", src, "-I", sg, "-I", os.path.join(REF, "Include", "cutil", "inc"),
