@@ -32,7 +32,7 @@ W, H = 640, 480
 WORKLOAD = {
     "workload": "configs[1]: 640x480 RGB-D stream, hashed TSDF (1 cm voxels, 4M-block heap, 4M buckets), per frame 1 integrate + 10 "
                 "re-integrations (de-integrate + integrate) + GC; per 10-frame chunk 1 local BA (11 frames, 2 GN x 100 PCG) + 1 global BA "
-                "(500 keyframes, 187k correspondences, 3 GN x 150 PCG, sparse); local BA = sparse + dense depth term (80x60 caches); frame ingest, dense-cache build and SIFT descriptor matching exist in the library (rows a18, a20, a21) but are not part of this metric's step; SIFT detection is not built",
+                "(500 keyframes, 187k correspondences, 3 GN x 150 PCG, sparse); local BA = sparse + dense depth term (80x60 caches); frame ingest, dense-cache build, SIFT detection / matching / match filters exist in the library (rows a17-a21) but are not part of this metric's step",
     "frame": [W, H], "voxel_m": 0.010, "sdf_blocks": 4000000, "hash_buckets": 4000000, "reintegrations_per_frame": 10,
     "chunk": 10, "global_keyframes": 500, "global_degree": 15, "frame_bank": 128,
     "streams": "reconstruction (TSDF) and bundling (BA) on two CUDA streams of one GPU, as the reference's two threads/devices",
