@@ -18,7 +18,8 @@ Patch list (each is a textual substitution on the scratch copy):
 Two builds: libref_tsdf_fast.so (--use_fast_math, as the reference ships: FriedLiver.vcxproj:124) and libref_tsdf.so (IEEE).
 Further outputs (see build_solver / build_siftmgr): libref_solver[_fast].so (bundle adjustment), libref_siftmgr[_fast].so (match-manager kernels),
 libref_imageutil.so (image and trajectory kernels), and libref_kabsch_host.so -- the reference's host-callable Kabsch / eigen code compiled by
-g++, which runs on the CPU.
+g++, which runs on the CPU; libref_sift_emulated.so -- the reference's SiftGPU (detection, matching) compiled by g++ against a CPU emulation
+of CUDA (build_sift_emulated), which also runs on the CPU.
 """
 import os
 import re
@@ -93,6 +94,7 @@ def main():
             raise RuntimeError(f"building {name} failed")
     build_solver()
     build_siftmgr()
+    build_sift_emulated()
     print("oracle/_ref built:", sorted(os.listdir(OUT)))
     return 0
 
@@ -193,6 +195,51 @@ def build_siftmgr():
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-6000:])
         raise RuntimeError("building libref_kabsch_host.so failed")
+
+
+def build_sift_emulated():
+    """The reference's SiftGPU -- detection and descriptor matching, FL/SiftGPU/{ProgramCU.cu, SiftPyramid.cpp, SiftGPU.cpp, SiftMatch.cpp,
+    CuTexImage.cpp, GlobalUtil.cpp, CUDASiftConstant.cu} -- compiled by g++ against a CPU emulation of CUDA (oracle/ref_emu/ref_emu_cuda.h on top of
+    tests/cuda_emu/cuda_emu.h) -> libref_sift_emulated.so.  ProgramCU.cu is written against texture REFERENCES, which CUDA 12 removed, so nvcc
+    cannot rebuild it here; emulated, the reference's own kernels run on the CPU and pin the SIFT oracles without a GPU.  Patches on the scratch copy:
+      a. `kernel << <grid, block>> >(args)` -> `EMU_KERNEL(kernel, grid, block)(args)`;
+      b. ComputeOrientation_Kernel: the barrier inside `if (tidx < 36)` becomes a barrier among those 36 threads, the barrier only thread 0 reaches
+         is dropped, `weights[maxIndex]` is guarded for maxIndex == -1 (an out-of-bounds shared-memory store on the GPU, memory corruption on a host);
+      c. ComputeDescriptor_Kernel: `des[8]` -> `des[9]` (the kernel indexes des[8] when an angle difference rounds to 8.0 bins);
+      d. `(unsigned int)round(x)` of the four window extents -> the GPU's saturating conversion (a window outside the image has a negative extent:
+         0 on the GPU, undefined behaviour in C++).
+    None of them changes what the kernels compute."""
+    root = os.path.join(TMP, "siftemu")
+    src = os.path.join(root, "Source")
+    S = os.path.join(REF, "Source")
+    sg = os.path.join(src, "SiftGPU")
+    os.makedirs(sg)
+    for f in os.listdir(os.path.join(S, "SiftGPU")):
+        if f.endswith((".h", ".cpp", ".cu")):
+            shutil.copy(os.path.join(S, "SiftGPU", f), sg)
+    for f in ("GlobalDefines.h", "CUDACacheUtil.h", "mLibCuda.h"):
+        shutil.copy(os.path.join(S, f), src)
+    patch(os.path.join(sg, "cuda_SimpleMatrixUtil.h"),
+          [(r"\ninline __device__ __host__ matNxM<4, 1>::operator float4\(\)", "\ntemplate<> inline __device__ __host__ matNxM<4, 1>::operator float4()", 1)])
+    launch = (r"([A-Za-z_]\w*(?:<[^<>()]*>)?)\s*<<\s*<\s*([^;]*?)\s*>>\s*>\s*\(", r"EMU_KERNEL(\1, \2)(", None)
+    patch(os.path.join(sg, "ProgramCU.cu"), [
+        launch,
+        (r"(target\[tidx\] = \(source\[m\] \+ source\[c\] \+ source\[p\]\)\*one_third;\s*)__syncthreads\(\);", r"\1emu_sync_first(36);", 1),
+        (r"weights\[maxIndex\] = -1\.0f;\s*__syncthreads\(\);", "if (maxIndex >= 0) weights[maxIndex] = -1.0f;", 1),
+        (r"__shared__ float des\[8\];", "__shared__ float des[9];", 1),
+        (r"\(unsigned int\)round\(([^;]*?)\);", r"emu_f2u(round(\1));", 4),
+        (r"#if !\(COLMATCH_BLOCK_WIDTH == 32\)", "#if 1", 3),
+    ])
+    emu_dir = os.path.join(HERE, "ref_emu")
+    cmd = ["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-D__CUDACC__", "-x", "c++",
+           "-I", emu_dir, "-I", os.path.join(os.path.dirname(HERE), "tests", "cuda_emu"), "-I", src, "-I", sg, "-I", os.path.join(REF, "Include", "cutil", "inc"),
+           os.path.join(HERE, "ref_sift_emulated.cpp")]
+    cmd += [os.path.join(sg, f) for f in ("ProgramCU.cu", "CUDASiftConstant.cu", "SiftPyramid.cpp", "SiftGPU.cpp", "SiftMatch.cpp", "CuTexImage.cpp", "GlobalUtil.cpp")]
+    cmd += ["-o", os.path.join(OUT, "libref_sift_emulated.so"), "-lm"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-8000:])
+        raise RuntimeError("building libref_sift_emulated.so failed")
 
 
 if __name__ == "__main__":

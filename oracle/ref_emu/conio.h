@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY: empty stand-in for the reference's Windows / precompiled header <conio.h>.
+#pragma once

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY: stands in for <cutil_inline_runtime.h> in the CPU emulation of the reference (see ref_emu_cuda.h).
+#pragma once
+#include "ref_emu_cuda.h"

@@ -14,9 +14,15 @@
  *   outputs           CreateGlobalKeyPointList(_Kernel), ConvertDescriptorToUChar_Kernel       SiftPyramid.cpp:730-781, ProgramCU.cu:2049-2121
  * (FL/ = FriedLiver/Source/.)
  *
- * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header).  PARITY STATUS: "parity unpinned" -- the reference has no tests or golden
- * vectors for this path and ProgramCU.cu is not rebuilt by oracle/build_ref.py yet; pinned only by known-answer and invariance tests
- * (tests/test_sift_detect_oracle.py).
+ * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header).  PARITY STATUS: PINNED against the reference's own kernels and host classes
+ * executed on the CPU.  ProgramCU.cu is written against texture references (removed from CUDA 12: nvcc cannot rebuild it), so
+ * oracle/build_ref.py compiles it -- with SiftPyramid.cpp, SiftGPU.cpp, CuTexImage.cpp, GlobalUtil.cpp -- by g++ against a CPU emulation of
+ * CUDA (oracle/ref_emu, tests/cuda_emu) into oracle/_ref/libref_sift_emulated.so; its outputs on seeded images are committed as
+ * tests/golden/sift_reference_emulated.npz and this file reproduces them (tests/test_sift_reference_emulated.py): the same key points
+ * bit for bit (position, scale, depth; three images incl. a half-resolution depth map with holes, the minimum-scale rule and the
+ * feature-count limit), descriptors identical for > 90 % of the features and within 2 counts for the rest (the reference's histogram sums
+ * run in thread order), one second orientation in 228 features decided differently (a peak sitting at the 0.8 threshold).  Also checked by
+ * known answers and invariances (tests/test_sift_detect_oracle.py).  Not yet compared with a run of the reference on a GPU.
  *
  * Contract where the reference is race-dependent or uses approximate hardware instructions (what a CUDA implementation is compared with):
  *   - key points of a level are listed in raster order (row-major), an orientation pair in (first, second) order; the reference appends

@@ -3,11 +3,14 @@
  * all-pairs u8 x u8 dot products, per-row and per-column best / second-best, distance and ratio tests,
  * mutual-best check.
  *
- * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header for the rules).  PARITY STATUS: "parity unpinned" -- the
- * reference has no tests or golden vectors for this path and its SiftGPU translation unit (ProgramCU.cu, texture
- * references throughout) is not among the files oracle/build_ref.py rebuilds; this file is pinned by the
- * known-answer tests in tests/test_sift_oracle.py (a brute-force numpy restatement of the published SiftGPU
- * matching rule, planted matches, tie cases).
+ * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header for the rules).  PARITY STATUS: PINNED against the reference's own
+ * kernels (MultiplyDescriptor / RowMatch / ColMatch through SiftMatchGPU::GetSiftMatch) executed on the CPU: ProgramCU.cu uses
+ * texture references, which nvcc 12 no longer compiles, so oracle/build_ref.py builds it with g++ against a CPU emulation of
+ * CUDA (oracle/_ref/libref_sift_emulated.so); its outputs on seeded descriptor sets, exact ties and key-point offsets included,
+ * are committed as tests/golden/sift_reference_emulated.npz and this file reproduces them bit for bit -- counters, index pairs,
+ * distances (tests/test_sift_reference_emulated.py).  Also pinned by the known-answer tests in tests/test_sift_oracle.py (a
+ * brute-force numpy restatement of the published SiftGPU matching rule, planted matches, tie cases).  Not yet compared with a run
+ * of the reference on a GPU.
  *
  * Restates (FL/ = FriedLiver/Source/):
  *   MultiplyDescriptor_Kernel   FL/SiftGPU/ProgramCU.cu:1634-1731  dot[i][j] = sum_k d1[i][k] * d2[j][k] (int32, exact),

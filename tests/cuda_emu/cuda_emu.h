@@ -105,17 +105,21 @@ template <class K, class... A>
 static inline void emu_launch(K kernel, dim3 grid, dim3 block, A... args) {
     const unsigned nt = block.x * block.y * block.z;
     emu::g_bar.n = nt;
+    static const bool trace = getenv("EMU_TRACE") != nullptr;
+    static int launchNo = 0;
+    if (trace) fprintf(stderr, "[emu] launch %d: grid (%u,%u,%u) block (%u,%u,%u)\n", ++launchNo, grid.x, grid.y, grid.z, block.x, block.y, block.z);
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nt; ++t)
         th.emplace_back([=]() {
             blockDim = block; gridDim = grid;
             threadIdx = { t % block.x, (t / block.x) % block.y, t / (block.x * block.y) };
-            for (unsigned by = 0; by < grid.y; ++by)
-                for (unsigned bx = 0; bx < grid.x; ++bx) {
-                    blockIdx = { bx, by, 0 };
-                    kernel(args...);
-                    emu::g_bar.wait();                                        // block boundary: function-static "shared" storage is reused
-                }
+            for (unsigned bz = 0; bz < grid.z; ++bz)
+                for (unsigned by = 0; by < grid.y; ++by)
+                    for (unsigned bx = 0; bx < grid.x; ++bx) {
+                        blockIdx = { bx, by, bz };
+                        kernel(args...);
+                        emu::g_bar.wait();                                    // block boundary: function-static "shared" storage is reused
+                    }
         });
     for (auto& x : th) x.join();
 }
