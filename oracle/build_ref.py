@@ -95,6 +95,7 @@ def main():
     build_solver()
     build_siftmgr()
     build_sift_emulated()
+    build_mgr_emulated()
     print("oracle/_ref built:", sorted(os.listdir(OUT)))
     return 0
 
@@ -240,6 +241,43 @@ def build_sift_emulated():
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-8000:])
         raise RuntimeError("building libref_sift_emulated.so failed")
+
+
+def build_mgr_emulated():
+    """The reference's match-manager, image and trajectory kernels (FL/SiftGPU/SIFTImageManager.cu, FL/CUDAImageUtil.cu, FL/OnlineBundler.cu) compiled
+    by g++ against the CUDA emulation -> libref_mgr_emulated.so, through the same two wrapper files the GPU builds use (oracle/ref_siftmgr_wrap.cu,
+    oracle/ref_imageutil_wrap.cu; their own launches are rewritten like the reference's).  Runs on the CPU: pins rows a19 - a22 without a GPU.
+    __NVCC__ is defined so that cuda_svd3.h takes its device flavour of rsqrt (the emulation maps it to 1 / sqrtf, the oracle's default)."""
+    root = os.path.join(TMP, "mgremu")
+    src = os.path.join(root, "Source")
+    S = os.path.join(REF, "Source")
+    sg = os.path.join(src, "SiftGPU")
+    os.makedirs(sg)
+    for f in os.listdir(os.path.join(S, "SiftGPU")):
+        if f.endswith(".h") or f == "SIFTImageManager.cu":
+            shutil.copy(os.path.join(S, "SiftGPU", f), sg)
+    for f in ("GlobalDefines.h", "CUDACacheUtil.h", "mLibCuda.h", "CUDAImageUtil.cu", "CUDAImageUtil.h", "OnlineBundler.cu", "CUDACameraUtil.h"):
+        shutil.copy(os.path.join(S, f), src)
+    shutil.copy(os.path.join(S, "mLibCuda.h"), os.path.join(src, "mlibCuda.h"))
+    patch(os.path.join(sg, "cuda_SimpleMatrixUtil.h"),
+          [(r"\ninline __device__ __host__ matNxM<4, 1>::operator float4\(\)", "\ntemplate<> inline __device__ __host__ matNxM<4, 1>::operator float4()", 1)])
+    launch = (r"([A-Za-z_]\w*(?:<[^<>()]*>)?)\s*<<\s*<\s*([^;]*?)\s*>>\s*>\s*\(", r"EMU_KERNEL(\1, \2)(", None)
+    for f in (os.path.join(sg, "SIFTImageManager.cu"), os.path.join(src, "CUDAImageUtil.cu"), os.path.join(src, "OnlineBundler.cu")):
+        patch(f, [launch])
+    units = []
+    for w in ("ref_siftmgr_wrap.cu", "ref_imageutil_wrap.cu"):
+        dst = os.path.join(root, w.replace(".cu", "_emu.cpp"))
+        shutil.copy(os.path.join(HERE, w), dst)
+        patch(dst, [launch])
+        units.append(dst)
+    emu_dir = os.path.join(HERE, "ref_emu")
+    cmd = ["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-D__CUDACC__", "-D__NVCC__",
+           "-I", emu_dir, "-I", os.path.join(os.path.dirname(HERE), "tests", "cuda_emu"), "-I", src, "-I", sg, "-I", os.path.join(REF, "Include", "cutil", "inc")]
+    cmd += units + ["-o", os.path.join(OUT, "libref_mgr_emulated.so"), "-lm"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-8000:])
+        raise RuntimeError("building libref_mgr_emulated.so failed")
 
 
 if __name__ == "__main__":

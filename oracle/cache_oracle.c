@@ -2,8 +2,8 @@
  * cache_oracle.c -- CPU restatement of CUDACache::storeFrame, kernel by kernel, with the
  * reference's full-resolution intermediates (the CUDA library evaluates the same values at cache resolution only).
  *
- * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header).  PARITY STATUS: "parity unpinned" -- no tests / golden vectors in the
- * reference for this path and FL/CUDAImageUtil.cu is not rebuilt by oracle/build_ref.py; pinned by the known-answer tests in
+ * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header).  PARITY STATUS: PINNED against the reference's own kernels executed on the CPU -- FL/CUDAImageUtil.cu, called in the order of CUDACache::storeFrame, compiled by g++ against the CUDA emulation (oracle/build_ref.py build_mgr_emulated -> oracle/_ref/libref_mgr_emulated.so), outputs committed as tests/golden/manager_reference_emulated.npz, tests/test_manager_reference_emulated.py: depth, camera positions, float and uchar4 normals bit for bit; intensity and its derivatives within 3e-7 (this file places the fused multiply-adds nvcc emits for the reference's expressions, the emulation is built without contraction).
+ * Also pinned by the known-answer tests in
  * tests/test_cache_oracle.py (analytic plane, hand-computed filter cases, agreement with the independent numpy generator
  * bundlefusion_b200/synth.py: make_cache_frame).
  *

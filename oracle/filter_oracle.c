@@ -351,7 +351,16 @@ ORC_API int orc_sift_add_residuals(unsigned curFrame, unsigned startFrame, unsig
  * (FL/SiftGPU/cudaUtil.h:25-43); and from FilterMatchesByDenseVerifyCU_Kernel / computeProjError (FL/SiftGPU/SIFTImageManager.cu:413-585,
  * the CUDACACHE_FLOAT_NORMALS branch -- FL/CUDACacheUtil.h:7-8 defines both macros and the float one is tested first).
  *
- * PARITY STATUS: "parity unpinned" against a run of the reference.  Restated literally: the 32-lane shuffle-down summation trees (lane 0's
+ * PARITY STATUS: PINNED against the reference's own kernels executed on the CPU (SIFTImageManager.cu compiled by g++ against the CUDA
+ * emulation, oracle/_ref/libref_mgr_emulated.so; golden file tests/golden/manager_reference_emulated.npz,
+ * tests/test_manager_reference_emulated.py): the surface-area filter's decisions under thresholds that bracket every area of this file
+ * within 1e-4 relative; the dense check's decisions follow from this file's PER-PIXEL residual / weight / count once they are added up the
+ * way the reference's kernel adds them.  That is not a plain sum: FilterMatchesByDenseVerifyCU_Kernel launches (width, ceil(height / 32))
+ * threads, reduces each warp with `val += __shfl_down(val, offset)` (a lane whose source is past the warp's end adds ITSELF) and lets the
+ * threads with threadIdx.x % 32 == 0 add their value to the block total -- for the 80 x 60 cache that is lane 0 of warps 0 - 2 and lane 16
+ * of warps 2 - 4: part of the image is counted more than once, part not at all.  orc_sift_filter_dense_verify (and the CUDA path) take the
+ * plain sum the kernel was written to take; on the test inputs that flips one decision in twenty, a pair sitting at the overlap threshold.
+ * Restated literally: the 32-lane shuffle-down summation trees (lane 0's
  * association order), the quirk that eigenSystem hands back ROWS of the Jacobi rotation matrix as "eigenvectors" (cuda_SVD.h:94-99 --
  * an orthonormal frame, but not the eigenframe; which frame depends on the literal sweep order, hence the literal Jacobi), the magnitude
  * sort by row exchange, NaN handling (a diagonal 2-D covariance gives a 0/0 axis; the NaN coordinates lose every fminf / fmaxf against
@@ -651,3 +660,18 @@ ORC_API unsigned orc_filter_pair(const float* keyPoints, uint32_t* idx, float* d
     return filter_pair((const KeyPoint*)keyPoints, idx, dist, numRaw, T, Ki, minNum, maxRes2);
 }
 ORC_API float orc_rsqrt_host_estimate(float x) { float out; _mm_store_ss(&out, _mm_rsqrt_ss(_mm_load_ss(&x))); return out; }
+
+/* per-pixel contributions of the dense verification, for pinning against the reference's kernel, whose own reduction is NOT a plain sum (see
+ * tests/test_manager_reference_emulated.py): out [W*H][3] = (residual, weight, count) of pixel idx, input->model plus model->input */
+ORC_API void orc_sift_dense_verify_pixels(unsigned p, unsigned curFrame, unsigned W, unsigned H, const float* intrinsics, const float* fT, const CachedFrame* frames,
+                                          float distThresh, float normalThresh, float dMin, float dMax, float* out) {
+    const float* T = fT + 16 * (size_t)p;
+    float Tinv[16];
+    mat4_inverse_subdet(T, Tinv);
+    for (unsigned idx = 0; idx < W * H; ++idx) {
+        float a[3], b[3];
+        proj_error(idx, W, H, distThresh, normalThresh, T, intrinsics, &frames[p], &frames[curFrame], dMin, dMax, a);
+        proj_error(idx, W, H, distThresh, normalThresh, Tinv, intrinsics, &frames[curFrame], &frames[p], dMin, dMax, b);
+        for (int k = 0; k < 3; ++k) out[3 * (size_t)idx + k] = a[k] + b[k];
+    }
+}

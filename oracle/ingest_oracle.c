@@ -2,8 +2,8 @@
  * ingest_oracle.c -- CPU restatement of the device part of CUDAImageManager::process, pass by pass
  * with the reference's full-image intermediates.
  *
- * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header).  PARITY STATUS: "parity unpinned" (no reference tests / golden vectors;
- * FL/CUDAImageUtil.cu is not rebuilt by oracle/build_ref.py); pinned by the known-answer tests in tests/test_ingest_oracle.py.
+ * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header).  PARITY STATUS: PINNED against the reference's own kernels executed on the CPU -- FL/CUDAImageUtil.cu, called in the order of CUDAImageManager::process, compiled by g++ against the CUDA emulation (oracle/build_ref.py build_mgr_emulated -> oracle/_ref/libref_mgr_emulated.so), outputs committed as tests/golden/manager_reference_emulated.npz, tests/test_manager_reference_emulated.py: depth and colour at the integration resolution bit for bit (two image sizes x four configurations: eroded / filtered / copied / resampled).
+ * Also pinned by the known-answer tests in tests/test_ingest_oracle.py.
  *
  * Restates: erodeDepthMapDevice FL/CUDAImageUtil.cu:701-741, gaussFilterDepthMapDevice :759-794, resampleFloat_Kernel :93-110,
  * resampleUCHAR4_Kernel :160-177, sequencing FL/CUDAImageManager.cpp:44-61, 88-137.

@@ -9,6 +9,7 @@
 
 #include <cassert>
 #include <cmath>
+#include <math.h>        // libstdc++'s wrapper: float overloads of exp / sqrt / atan2 / ... in the global namespace, as in CUDA device code
 #include <string>
 
 #define __constant__

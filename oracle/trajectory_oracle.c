@@ -1,7 +1,7 @@
 /*
  * trajectory_oracle.c -- CPU restatement of the trajectory glue kernels: FL/OnlineBundler.cu:6-140.
- * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header).  PARITY STATUS: "parity unpinned" against the reference itself (no tests /
- * golden vectors; OnlineBundler.cu is not rebuilt by oracle/build_ref.py); pinned by tests/test_trajectory_oracle.py (numpy float64
+ * TEST INFRASTRUCTURE ONLY (see tsdf_oracle.c header).  PARITY STATUS: PINNED against the reference's own kernels executed on the CPU -- FL/OnlineBundler.cu compiled by g++ against the CUDA emulation (oracle/build_ref.py build_mgr_emulated -> oracle/_ref/libref_mgr_emulated.so), outputs committed as tests/golden/manager_reference_emulated.npz, tests/test_manager_reference_emulated.py: same -inf patterns and slots written, values within 2 units in the last place (the fused products below against the emulation's unfused ones).
+ * Also pinned by tests/test_trajectory_oracle.py (numpy float64
  * products, identity / inverse cases).  Arithmetic contract shared with bundlefusion_b200/csrc/trajectory.cu: the 4x4 product fused
  * as fma(a4,b4, fma(a3,b3, fma(a1,b1, a2*b2))) (the way nvcc fuses a1*b1 + a2*b2 + a3*b3 + a4*b4, cf. tsdf_oracle.c header), the
  * inverse by the cofactor formula of bundlefusion_b200/csrc/mat4.cuh, every other operation individually rounded.

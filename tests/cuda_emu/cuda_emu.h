@@ -59,11 +59,12 @@ alignas(16) inline float sm[64 * 1024];                                       //
 #define extern_shared_decl
 
 static inline void __syncthreads() { emu::g_bar.wait(); }
+static inline unsigned emu_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }      // linear id: warps are cut from it
 static inline float atomicAdd(float* p, float v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const float o = *p; *p = o + v; return o; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __ballot_sync(unsigned, bool pred) {                   // called by every thread of the block at the same point
-    const unsigned t = threadIdx.x, w = t >> 5;
+    const unsigned t = emu_tid(), w = t >> 5;
     if ((t & 31) == 0) emu::g_vote[w] = 0;
     emu::g_bar.wait();
     if (pred) { std::lock_guard<std::mutex> lk(emu::g_atomic); emu::g_vote[w] |= 1u << (t & 31); }
@@ -73,7 +74,7 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {                   //
     return r;
 }
 static inline float __shfl_xor_sync(unsigned, float v, int mask) {
-    const unsigned t = threadIdx.x;
+    const unsigned t = emu_tid();
     emu::g_xchg[t] = v;
     emu::g_bar.wait();
     const float r = emu::g_xchg[(t & ~31u) | ((t ^ (unsigned)mask) & 31u)];
@@ -82,7 +83,7 @@ static inline float __shfl_xor_sync(unsigned, float v, int mask) {
 }
 
 static inline float __shfl_down_sync(unsigned, float v, int delta) {         // lanes past the end keep their own value
-    const unsigned t = threadIdx.x, l = t & 31;
+    const unsigned t = emu_tid(), l = t & 31;
     emu::g_xchg[t] = v;
     emu::g_bar.wait();
     const float r = (l + (unsigned)delta < 32) ? emu::g_xchg[t + delta] : v;
@@ -90,7 +91,7 @@ static inline float __shfl_down_sync(unsigned, float v, int delta) {         // 
     return r;
 }
 static inline float __shfl_sync(unsigned, float v, int src) {
-    const unsigned t = threadIdx.x;
+    const unsigned t = emu_tid();
     emu::g_xchg[t] = v;
     emu::g_bar.wait();
     const float r = emu::g_xchg[(t & ~31u) | ((unsigned)src & 31u)];
