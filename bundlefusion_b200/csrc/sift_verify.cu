@@ -6,11 +6,11 @@
 // FL/SiftGPU/SIFTImageManager.cu:413-608 (FilterMatchesByDenseVerifyCU / computeProjError, float-normal branch).
 // Device functions follow oracle/filter_oracle.c operation for operation (TU built -fmad=false): the shuffle-down trees, the
 // rows-of-the-rotation-matrix "eigenvectors", the NaN behaviour (fminf / fmaxf drop NaNs) and the GPU float->int rule are the reference's; normalize() by
-// 1 / sqrtf and the fixed summation order of the dense check are this implementation's contract (see the oracle's note).
+// 1 / sqrtf is this implementation's contract; the dense check's block total is the reference's, quirks included (see below).
 //
 // Surface area: one warp per image pair, every lane carries the pair's small matrices redundantly (no divergence, no shared memory).
-// Dense verify: one 256-thread CTA per image pair walks both cached frames (80x60 by default: 4800 pixels x 2 directions, ~150 KB of
-// gathers out of L2) -- the work is tiny; what matters is that ALL pairs of a frame go in one launch each.
+// Dense verify: one CTA per image pair in the reference's block shape (width x ceil(height / 32) threads: 160 for the 80x60 cache) walks both
+// cached frames (4800 pixels x 2 directions, ~350 KB of gathers out of L2) -- the work is tiny; ALL pairs of a frame go in one launch.
 #include <cfloat>
 
 #include "../../include/bf_sift.h"
@@ -214,31 +214,43 @@ __device__ void proj_error(unsigned idx, const VerifyArgs& a, const float* T, co
     }
 }
 
-#define DV_THREADS 256
-__global__ void __launch_bounds__(DV_THREADS)
+// The block total is formed exactly as FilterMatchesByDenseVerifyCU_Kernel forms it (SIFTImageManager.cu:520-565) -- which is not the plain sum of the
+// per-pixel terms: (W, ceil(H / 32)) threads, thread (x, ty) adds its rows ty * 32 .. in order, warps cut from the linear thread id,
+// `val += __shfl_down(val, offset)` (a lane whose source is past the warp's end adds itself), contributions from the lanes with
+// threadIdx.x % 32 == 0.  The reference adds those with shared-memory atomics (scheduling order); here they are added in ascending (row, x) order.
+// See oracle/filter_oracle.c dense_block_total and tests/test_manager_reference_emulated.py.
+__global__ void __launch_bounds__(1024)
 sift_dense_verify_kernel(const __grid_constant__ VerifyArgs a) {
-    const unsigned p = blockIdx.x + a.startFrame, t = threadIdx.x;
+    const unsigned p = blockIdx.x + a.startFrame, x = threadIdx.x, ty = threadIdx.y;
     if (p == a.curFrame) return;
     if (a.numFiltered[p] == 0) return;
     __shared__ float sT[16], sTinv[16];
-    __shared__ float sPart[3][DV_THREADS / 32];
+    __shared__ float sAdd[64][3];
+    const unsigned t = ty * blockDim.x + x;
     if (t < 16) sT[t] = a.fT[16 * (size_t)p + t];
     __syncthreads();
     if (t == 0) mat4_inverse_hd(sT, sTinv);
     __syncthreads();
     const BFCUDACachedFrame in = a.frames[p], model = a.frames[a.curFrame];
     float s[3] = { 0.0f, 0.0f, 0.0f };
-    for (unsigned idx = t; idx < a.W * a.H; idx += DV_THREADS) {
-        float x[3], y[3];
-        proj_error(idx, a, sT, in, model, x);
-        proj_error(idx, a, sTinv, model, in, y);
-        for (int k = 0; k < 3; ++k) s[k] += x[k] + y[k];
+    for (unsigned i = 0; i < 32; ++i) {
+        const unsigned y = ty * 32 + i;
+        if (y < a.H) {
+            const unsigned idx = y * a.W + x;
+            float u[3], v[3];
+            proj_error(idx, a, sT, in, model, u);
+            proj_error(idx, a, sTinv, model, in, v);
+            for (int k = 0; k < 3; ++k) s[k] += u[k] + v[k];
+        }
     }
-    for (int k = 0; k < 3; ++k) { const float w = tree_sum(s[k]); if ((t & 31) == 0) sPart[k][t >> 5] = w; }
+    for (int k = 0; k < 3; ++k)
+        for (int off = 16; off > 0; off >>= 1) s[k] = s[k] + __shfl_down_sync(0xFFFFFFFFu, s[k], off);     // past the warp's end the source is the lane itself
+    const unsigned perRow = (blockDim.x + 31) / 32;
+    if ((x & 31) == 0) for (int k = 0; k < 3; ++k) sAdd[ty * perRow + (x >> 5)][k] = s[k];
     __syncthreads();
     if (t == 0) {
-        float tot[3];
-        for (int k = 0; k < 3; ++k) { tot[k] = 0.0f; for (int w = 0; w < DV_THREADS / 32; ++w) tot[k] += sPart[k][w]; }
+        float tot[3] = { 0.0f, 0.0f, 0.0f };
+        for (unsigned r = 0; r < blockDim.y; ++r) for (unsigned c = 0; c < perRow; ++c) for (int k = 0; k < 3; ++k) tot[k] += sAdd[r * perRow + c][k];
         const float err = tot[0] / tot[1], corr = 0.5f * tot[2] / (float)(a.W * a.H);
         if (a.stats) { a.stats[2 * p] = err; a.stats[2 * p + 1] = corr; }
         if (corr < a.corrThresh || err > a.errThresh || err != err) a.numFiltered[p] = 0;
@@ -280,8 +292,11 @@ BF_API int bfSiftFilterMatchesByDenseVerify(unsigned int curFrame, unsigned int 
     for (int k = 0; k < 16; ++k) a.K[k] = intrinsics[k];
     a.distThresh = distThresh; a.normalThresh = normalThresh; a.errThresh = errThresh; a.corrThresh = corrThresh;
     a.dMin = sensorDepthMin; a.dMax = sensorDepthMax;
+    const unsigned by = (imageHeight + 31) / 32, nt = imageWidth * by;
+    if (nt % 32 != 0 || nt > 1024) return (int)cudaErrorInvalidValue;             // the reference's block shape; a partial warp in its shuffles is undefined
     ++g_launchCount;
-    sift_dense_verify_kernel<<<numFrames - startFrame, DV_THREADS, 0, stream()>>>(a);
+    const dim3 block(imageWidth, by);
+    sift_dense_verify_kernel<<<numFrames - startFrame, block, 0, stream()>>>(a);
     BF_CHECK(cudaGetLastError());
     return 0;
 }

@@ -96,10 +96,12 @@ int bfSiftFilterMatchesBySurfaceArea(unsigned int curFrame, unsigned int startFr
  * whose position and normal agree or that are known to be in front of the target surface, and zeroes the pair's filtered-match count
  * when corr = count / (2 W H) < corrThresh, err = residual / weight > errThresh, or err is NaN.  intrinsics: HOST 4x4 (cache
  * resolution).  colorThresh is accepted and unused, as in the reference.  d_statsOut: optional [numFrames][2] (err, corr), else NULL.
- * Differences: the three sums are PLAIN sums over the pixels, taken in a fixed order.  The reference's kernel (SIFTImageManager.cu:520-565)
- * reduces with `val += __shfl_down(val, offset)` over warps cut from a (width, height / 32) block and adds the lanes with threadIdx.x % 32 == 0
- * through shared-memory atomics: for the 80 x 60 cache some pixels count twice or more and some not at all, so its err / corr differ from
- * the plain ones by a few percent (per-pixel terms are identical: tests/test_manager_reference_emulated.py).  Asynchronous. */
+ * The block total is formed as the reference's kernel forms it (SIFTImageManager.cu:520-565), which is NOT the plain sum over the pixels:
+ * (width, ceil(height / 32)) threads, `val += __shfl_down(val, offset)` over warps cut from the linear thread id (a lane whose source is past
+ * the warp's end adds itself), contributions from the lanes with threadIdx.x % 32 == 0 -- for the 80 x 60 cache some pixels count twice or more
+ * and some not at all, and err / corr come out a few percent off the plain ones.  Kept for identical decisions
+ * (tests/test_manager_reference_emulated.py); the only difference left is that those contributions are added in a fixed order instead of
+ * through shared-memory atomics.  width * ceil(height / 32) must be a multiple of 32 and at most 1024 (else cudaErrorInvalidValue).  Asynchronous. */
 int bfSiftFilterMatchesByDenseVerify(unsigned int curFrame, unsigned int startFrame, unsigned int numFrames, unsigned int imageWidth, unsigned int imageHeight,
                                      const float* intrinsics, int32_t* d_currNumFilteredMatchesPerImagePair, const float* d_currFilteredTransforms,
                                      const BFCUDACachedFrame* d_cachedFrames, float distThresh, float normalThresh, float colorThresh, float errThresh,

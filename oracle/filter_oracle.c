@@ -24,6 +24,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define ORC_API __attribute__((visibility("default")))
@@ -358,8 +359,8 @@ ORC_API int orc_sift_add_residuals(unsigned curFrame, unsigned startFrame, unsig
  * way the reference's kernel adds them.  That is not a plain sum: FilterMatchesByDenseVerifyCU_Kernel launches (width, ceil(height / 32))
  * threads, reduces each warp with `val += __shfl_down(val, offset)` (a lane whose source is past the warp's end adds ITSELF) and lets the
  * threads with threadIdx.x % 32 == 0 add their value to the block total -- for the 80 x 60 cache that is lane 0 of warps 0 - 2 and lane 16
- * of warps 2 - 4: part of the image is counted more than once, part not at all.  orc_sift_filter_dense_verify (and the CUDA path) take the
- * plain sum the kernel was written to take; on the test inputs that flips one decision in twenty, a pair sitting at the overlap threshold.
+ * of warps 2 - 4: part of the image is counted more than once, part not at all.  orc_sift_filter_dense_verify (dense_block_total) and the
+ * CUDA path form the total the same way, so their decisions are the reference's (a plain sum flips one in twenty on the test inputs).
  * Restated literally: the 32-lane shuffle-down summation trees (lane 0's
  * association order), the quirk that eigenSystem hands back ROWS of the Jacobi rotation matrix as "eigenvectors" (cuda_SVD.h:94-99 --
  * an orthonormal frame, but not the eigenframe; which frame depends on the literal sweep order, hence the literal Jacobi), the magnitude
@@ -585,36 +586,59 @@ static void mat4_inverse_subdet(const float* m, float* out) {
     out[14] = (-a30 * s3 + a31 * s1 - a32 * s0) * r; out[15] = (a20 * s3 - a21 * s1 + a22 * s0) * r;
 }
 
-#define DV_THREADS 256
+/* The block total as FilterMatchesByDenseVerifyCU_Kernel forms it (SIFTImageManager.cu:520-565), restated literally because it is NOT the plain sum
+ * of the per-pixel terms: the block has (W, ceil(H / 32)) threads, thread (x, ty) adds its rows ty * 32 .. ty * 32 + 31 in order; warps are cut
+ * from the linear thread id; `val += __shfl_down(val, offset)` -- a lane whose source lies past the warp's end adds ITSELF --; and the lanes that
+ * contribute to the total are those with threadIdx.x % 32 == 0 (lane 0 of its warp only in the first thread row).  The reference adds those
+ * contributions with shared-memory atomics (order = scheduling); here, and in the CUDA path, in ascending (row, x) order.
+ * Needs W * ceil(H / 32) to be a multiple of 32 and at most 1024 (a partial warp in a full-mask shuffle is undefined on the GPU); returns 0 otherwise. */
+static int dense_block_total(const float* pix /*[W*H][3]*/, unsigned W, unsigned H, float tot[3]) {
+    const unsigned by = (H + 31) / 32, nt = W * by;
+    if (nt % 32 != 0 || nt > 1024) return 0;
+    static float local[1024][3];
+    for (unsigned ty = 0; ty < by; ++ty)
+        for (unsigned x = 0; x < W; ++x) {
+            float acc[3] = { 0.0f, 0.0f, 0.0f };
+            for (unsigned i = 0; i < 32; ++i) { const unsigned y = ty * 32 + i; if (y < H) for (int k = 0; k < 3; ++k) acc[k] += pix[3 * ((size_t)y * W + x) + k]; }
+            for (int k = 0; k < 3; ++k) local[ty * W + x][k] = acc[k];
+        }
+    for (unsigned w0 = 0; w0 < nt; w0 += 32)
+        for (int off = 16; off > 0; off /= 2) {
+            float nxt[32][3];
+            for (int l = 0; l < 32; ++l) { const int src = l + off < 32 ? l + off : l; for (int k = 0; k < 3; ++k) nxt[l][k] = local[w0 + l][k] + local[w0 + src][k]; }
+            for (int l = 0; l < 32; ++l) for (int k = 0; k < 3; ++k) local[w0 + l][k] = nxt[l][k];
+        }
+    tot[0] = tot[1] = tot[2] = 0.0f;
+    for (unsigned ty = 0; ty < by; ++ty) for (unsigned x = 0; x < W; x += 32) for (int k = 0; k < 3; ++k) tot[k] += local[ty * W + x][k];
+    return 1;
+}
+
 /* FilterMatchesByDenseVerifyCU over pairs [startFrame, numFrames) \\ {curFrame}; frames: HOST array of cached-frame pointer records.
  * stats (optional): [numFrames][2] = (err, corr) for the pairs visited. */
 ORC_API void orc_sift_filter_dense_verify(unsigned curFrame, unsigned startFrame, unsigned numFrames, unsigned W, unsigned H, const float* intrinsics,
                                           int32_t* numFiltered, const float* fT, const CachedFrame* frames, float distThresh, float normalThresh,
                                           float colorThresh, float errThresh, float corrThresh, float dMin, float dMax, float* stats) {
     (void)colorThresh;
+    float* pix = (float*)malloc(sizeof(float) * 3 * (size_t)W * H);
     for (unsigned p = startFrame; p < numFrames; ++p) {
         if (p == curFrame) continue;
         if (numFiltered[p] == 0) continue;
         const float* T = fT + 16 * (size_t)p;
         float Tinv[16];
         mat4_inverse_subdet(T, Tinv);
-        float part[3][DV_THREADS];
-        for (unsigned t = 0; t < DV_THREADS; ++t) {
-            float s[3] = { 0.0f, 0.0f, 0.0f };
-            for (unsigned idx = t; idx < W * H; idx += DV_THREADS) {
-                float a[3], b[3];
-                proj_error(idx, W, H, distThresh, normalThresh, T, intrinsics, &frames[p], &frames[curFrame], dMin, dMax, a);
-                proj_error(idx, W, H, distThresh, normalThresh, Tinv, intrinsics, &frames[curFrame], &frames[p], dMin, dMax, b);
-                for (int k = 0; k < 3; ++k) s[k] += a[k] + b[k];
-            }
-            for (int k = 0; k < 3; ++k) part[k][t] = s[k];
+        for (unsigned idx = 0; idx < W * H; ++idx) {
+            float a[3], b[3];
+            proj_error(idx, W, H, distThresh, normalThresh, T, intrinsics, &frames[p], &frames[curFrame], dMin, dMax, a);
+            proj_error(idx, W, H, distThresh, normalThresh, Tinv, intrinsics, &frames[curFrame], &frames[p], dMin, dMax, b);
+            for (int k = 0; k < 3; ++k) pix[3 * (size_t)idx + k] = a[k] + b[k];
         }
         float tot[3];
-        for (int k = 0; k < 3; ++k) { tot[k] = 0.0f; for (unsigned w = 0; w < DV_THREADS / 32; ++w) tot[k] += tree_sum32(&part[k][32 * w]); }
+        if (!dense_block_total(pix, W, H, tot)) continue;
         const float err = tot[0] / tot[1], corr = 0.5f * tot[2] / (float)(W * H);
         if (stats) { stats[2 * p] = err; stats[2 * p + 1] = corr; }
         if (corr < corrThresh || err > errThresh || err != err) numFiltered[p] = 0;
     }
+    free(pix);
 }
 
 /* ---- invalidation after a solve: InvalidateImageToImageCU_Kernel, CheckForInvalidFramesSimpleCU_Kernel / CheckForInvalidFramesCU_Kernel

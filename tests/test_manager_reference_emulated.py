@@ -133,8 +133,8 @@ def reference_reduction(pix, W, H):
 
 def test_dense_verify_pixels_and_the_reference_reduction():
     """The reference's decisions follow from THIS oracle's per-pixel residual / weight / count when they are added up the way the reference's
-    kernel adds them -- which is not a plain sum (see reference_reduction).  The library and orc_sift_filter_dense_verify take the plain
-    sum the kernel was written to take; on these inputs that changes one decision in sixteen (a pair whose overlap sits at the threshold)."""
+    kernel adds them -- which is not a plain sum (see reference_reduction).  orc_sift_filter_dense_verify and the CUDA path form the total the
+    same way (a plain sum would change one decision in twenty on these inputs: a pair whose overlap sits at the threshold)."""
     import ctypes as C
     from oracle.oracle import _CachedFrame
     g = np.load(GOLDEN)
@@ -160,7 +160,7 @@ def test_dense_verify_pixels_and_the_reference_reduction():
             keepit = not (corr < o["corrThresh"] or err > o["errThresh"] or np.isnan(err))
             assert (7 if keepit else 0) == g["dense_nf"][t][p], (t, p, err, corr)
             plain_differs += int(nf_plain[p] != g["dense_nf"][t][p])
-    assert plain_differs <= 1
+    assert plain_differs == 0
 
 
 def test_cache_frame_and_ingest():
