@@ -18,13 +18,12 @@
 
 // ---- vector types beyond cuda_emu.h ----
 struct float3 { float x, y, z; }; struct int3 { int x, y, z; }; struct int4 { int x, y, z, w; }; struct uint4 { unsigned x, y, z, w; };
-struct uchar4 { unsigned char x, y, z, w; }; struct uchar3 { unsigned char x, y, z; }; struct ushort2 { unsigned short x, y; };
+struct uchar3 { unsigned char x, y, z; }; struct ushort2 { unsigned short x, y; };
 static inline float3 make_float3(float x, float y, float z) { return { x, y, z }; }
 static inline int3 make_int3(int x, int y, int z) { return { x, y, z }; }
 static inline int4 make_int4(int x, int y, int z, int w) { return { x, y, z, w }; }
 static inline uint3 make_uint3(unsigned x, unsigned y, unsigned z) { return { x, y, z }; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return { x, y, z, w }; }
-static inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return { x, y, z, w }; }
 
 #define CUDA_VERSION 12090
 #define CUDART_VERSION 12090

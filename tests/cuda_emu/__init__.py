@@ -11,11 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 def build_emulated(cu_name: str, expected_launches: int) -> C.CDLL:
     src = open(os.path.join(ROOT, "bundlefusion_b200", "csrc", cu_name)).read()
     src = src.replace('#include "bf_common.cuh"', "")
-    src = src.replace("extern __shared__ float sm[];", "")
+    src = re.sub(r"extern __shared__ float (\w+)\[\];", lambda m: "" if m.group(1) == "sm" else f"float* {m.group(1)} = sm;", src)      # dynamic shared memory: the shim's sm[]
     src, n = re.subn(r"(\w+(?:<\w+>)?)<<<\s*([^,]+),\s*([^,]+),\s*[^,]+,\s*[^>]+>>>\(", r"EMU_LAUNCH(\1, \2, \3, ", src)
     assert n == expected_launches, (cu_name, n)
     pre = ('#include "%s"\n' % os.path.join(ROOT, "tests", "cuda_emu", "cuda_emu.h") +
-           "#define BF_CHECK(e) do { int _e = (int)(e); if (_e) return _e; } while (0)\n"
+           "#define BF_CHECK(e) do { int _e = (int)(e); if (_e) return _e; } while (0)\n#define BF_SAFE(e) do { (void)(e); } while (0)\n"
            "namespace bf { unsigned long long g_launchCount = 0; static inline cudaStream_t stream() { return nullptr; } }\n")
     d = tempfile.mkdtemp(prefix="bf_emu_")
     cpp = os.path.join(d, cu_name.replace(".cu", "_emu.cpp"))

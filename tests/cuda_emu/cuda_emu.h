@@ -28,6 +28,8 @@
 #define BF_API extern "C"
 
 struct float2 { float x, y; }; struct float4 { float x, y, z, w; }; struct int2 { int x, y; }; struct uint2 { unsigned x, y; };
+struct uchar4 { unsigned char x, y, z, w; };
+static inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return { x, y, z, w }; }
 static inline float2 make_float2(float x, float y) { return { x, y }; }
 static inline float4 make_float4(float x, float y, float z, float w) { return { x, y, z, w }; }
 static inline int2 make_int2(int x, int y) { return { x, y }; }
@@ -62,6 +64,7 @@ static inline void __syncthreads() { emu::g_bar.wait(); }
 static inline unsigned emu_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }      // linear id: warps are cut from it
 static inline float atomicAdd(float* p, float v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const float o = *p; *p = o + v; return o; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __ballot_sync(unsigned, bool pred) {                   // called by every thread of the block at the same point
     const unsigned t = emu_tid(), w = t >> 5;
