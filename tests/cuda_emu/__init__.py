@@ -2,6 +2,7 @@
 import ctypes as C
 import os
 import re
+import shutil
 import subprocess
 import tempfile
 
@@ -24,4 +25,6 @@ def build_emulated(cu_name: str, expected_launches: int) -> C.CDLL:
     r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "tests", "cuda_emu"), "-I", os.path.join(ROOT, "bundlefusion_b200", "csrc"),
                         cpp, "-o", so], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
-    return C.CDLL(so)
+    lib = C.CDLL(so)
+    shutil.rmtree(d, ignore_errors=True)               # the mapping outlives the file
+    return lib
