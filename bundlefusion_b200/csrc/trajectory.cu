@@ -73,8 +73,10 @@ select_reintegration_kernel(const float* __restrict__ opt, const float* __restri
             V3 ro, to, ri, ti;
             matrix_to_pose(&opt[16 * i], ro, to);
             matrix_to_pose(&integ[16 * i], ri, ti);
-            const V3 dr = ri * scale - ro * scale, dt = ti - to;
-            d = dot(dr, dr) + dot(dt, dt);
+            // PoseHelper::MatrixToPose packs (translation, rotation) and TrajectoryManager scales components 0..2 (FL/PoseHelper.h:355-358,
+            // FL/TrajectoryManager.cpp:66-75): the factor its name gives to the rotation lands on the Lie TRANSLATION
+            const V3 dt = ti * scale - to * scale, dr = ri - ro;
+            d = dot(dt, dt) + dot(dr, dr);
         }
         dist[i] = d;
     }

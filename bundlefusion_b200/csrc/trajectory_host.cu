@@ -79,9 +79,11 @@ BF_API void bfTrajectoryGenerateUpdateLists(BFTrajectoryManager* tm) {          
         bf::V3 ro, to, ri, ti;
         bf::matrix_to_pose(tm->opt(i), ro, to);
         bf::matrix_to_pose(f.integrated, ri, ti);
-        const bf::V3 dr = ri * tm->rescale - ro * tm->rescale, dt = ti - to;
+        // PoseHelper::MatrixToPose packs (translation, rotation) (FL/PoseHelper.h:355-358) and components 0..2 are the ones scaled
+        // (FL/TrajectoryManager.cpp:67-74): m_featureRescaleRotToTrans ends up on the Lie TRANSLATION
+        const bf::V3 dt = ti * tm->rescale - to * tm->rescale, dr = ri - ro;
         // point6d operator| (mLib core-math/point6d.h, un-vendored submodule; published form: the six products summed left to right)
-        f.dist = dr.x * dr.x + dr.y * dr.y + dr.z * dr.z + dt.x * dt.x + dt.y * dt.y + dt.z * dt.z;
+        f.dist = dt.x * dt.x + dt.y * dt.y + dt.z * dt.z + dr.x * dr.x + dr.y * dr.y + dr.z * dr.z;
     }
     std::stable_sort(tm->sorted.begin(), tm->sorted.begin() + numFrames, [](const TM::Frame* l, const TM::Frame* r) {
         if (l->type == BF_TRAJ_INTEGRATED && r->type != BF_TRAJ_INTEGRATED) return true;

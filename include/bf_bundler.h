@@ -30,8 +30,9 @@ void updateTrajectoryCU(const float* d_globalTrajectory, unsigned int numGlobalT
 
 /* ---- B200-native extension: the re-integration choice of TrajectoryManager::generateUpdateLists (FL/TrajectoryManager.cpp:45-108) on
  * the device.  The reference copies the whole optimised trajectory to the host every frame, converts every pose with MatrixToPose, and
- * std::sorts all frames to take the top N.  Here one launch computes, per frame, dist = |(s w, t)_integrated - (s w, t)_optimised|^2
- * ((w, t) = the SE(3) logarithm, s = rescaleRotToTrans = 2) and selects the up to topN INTEGRATED frames of largest dist > minPoseDistSqrt, in
+ * std::sorts all frames to take the top N.  Here one launch computes, per frame, dist = |(s t, w)_integrated - (s t, w)_optimised|^2
+ * ((w, t) = the SE(3) logarithm, s = rescaleRotToTrans = 2: despite its name the factor multiplies the TRANSLATION part -- the host's
+ * PoseHelper::MatrixToPose packs (translation, rotation) and TrajectoryManager.cpp:67-74 scales components 0..2) and selects the up to topN INTEGRATED frames of largest dist > minPoseDistSqrt, in
  * descending order (ties: lower frame index first; the reference's std::sort leaves ties unspecified).  A frame whose optimised transform
  * is invalid (first entry -inf) is never selected (the reference routes it to the de-integration list).
  * d_frameState[i] != 0 <=> frame i is currently integrated.  Outputs: d_dist[numFrames], d_list[topN] (frame indices), d_count[1].

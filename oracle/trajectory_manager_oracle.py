@@ -69,10 +69,10 @@ class TrajectoryManagerOracle:
             with np.errstate(all="ignore"):
                 ro, to = orc.matrix_to_pose(self.optimized[i])
                 ri, ti = orc.matrix_to_pose(f.integrated)
-                dr = ri * self.rescale - ro * self.rescale
-                dt = ti - to
+                dt = ti * self.rescale - to * self.rescale      # components 0..2 of the host Pose are the translation (PoseHelper.h:355-358)
+                dr = ri - ro
                 d = np.float32(0)              # point6d operator| (mLib, un-vendored): six products summed left to right
-                for v in (dr[0], dr[1], dr[2], dt[0], dt[1], dt[2]):
+                for v in (dt[0], dt[1], dt[2], dr[0], dr[1], dr[2]):
                     d = np.float32(d + np.float32(v * v))
                 f.dist = d
         head = self.sorted[:n]

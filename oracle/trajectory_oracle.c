@@ -71,9 +71,11 @@ ORC_API int orc_select_reintegration(const float* opt, const float* integ, const
             float ro[3], to[3], ri[3], ti[3];
             orc_matrix_to_pose(&opt[16 * i], ro, to);
             orc_matrix_to_pose(&integ[16 * i], ri, ti);
+            /* the host's PoseHelper::MatrixToPose packs (translation, rotation) -- FL/PoseHelper.h:355-358 -- and the scale factor is applied to
+             * components 0..2 (FL/TrajectoryManager.cpp:67-74): m_featureRescaleRotToTrans multiplies the Lie TRANSLATION, not the rotation */
             float d = 0.0f, e = 0.0f;
-            for (int k = 0; k < 3; ++k) { const float a = ri[k] * scale - ro[k] * scale; d += a * a; }
-            for (int k = 0; k < 3; ++k) { const float a = ti[k] - to[k]; e += a * a; }
+            for (int k = 0; k < 3; ++k) { const float a = ti[k] * scale - to[k] * scale; d += a * a; }
+            for (int k = 0; k < 3; ++k) { const float a = ri[k] - ro[k]; e += a * a; }
             dist[i] = d + e;
         }
     }

@@ -101,6 +101,9 @@ static inline float __shfl_sync(unsigned, float v, int src) {
     emu::g_bar.wait();
     return r;
 }
+static inline int __shfl_xor_sync(unsigned m, int v, int mask) { float f; std::memcpy(&f, &v, 4); f = __shfl_xor_sync(m, f, mask); std::memcpy(&v, &f, 4); return v; }   // bit pattern through the float path
+static inline int __shfl_down_sync(unsigned m, int v, int d) { float f; std::memcpy(&f, &v, 4); f = __shfl_down_sync(m, f, d); std::memcpy(&v, &f, 4); return v; }
+static inline int __shfl_sync(unsigned m, int v, int src) { float f; std::memcpy(&f, &v, 4); f = __shfl_sync(m, f, src); std::memcpy(&v, &f, 4); return v; }
 static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { emu::g_bar.wait(); }      // the emulated kernels use it only in one-warp blocks, where it is the block barrier
 using std::min; using std::max;
 

@@ -78,3 +78,25 @@ def test_trajectory_kernels_emulated(libs):
         t2, c2 = orc.compute_sift_transform(tc["finv"], tc["nf"], tc["comp"], lv, tc["sift"], tc["cur_all"], tc["cur"])
         # the integration transform goes through a 4x4 inverse: sub-determinant adjugate in the kernel (mat4.cuh), triple products in the oracle
         assert np.array_equal(bits(sift), bits(t2)) and np.abs(cur - c2).max() <= 2e-6 * max(1.0, float(np.abs(c2).max()))
+
+
+def test_select_reintegration_emulated(libs):
+    """bfTrajectorySelectReintegration (verified on the B200 before the scaled component of the pose distance was corrected to the translation
+    part, FL/TrajectoryManager.cpp:67-74): the kernel against the oracle under the emulation."""
+    Lt = libs[2]
+    from tests.test_manager_reference_emulated import poses
+    n = 300
+    integ = poses(n, 7)
+    rng = np.random.default_rng(8)
+    opt = integ.copy()
+    for k in rng.choice(n, 60, replace=False):
+        opt[k] = (synth.se3_exp(rng.standard_normal(3) * 0.02, rng.standard_normal(3) * 0.05) @ integ[k].astype(np.float64)).astype(F)
+    state = (rng.random(n) < 0.85).astype(np.int32)
+    opt[[5, 50, 200], 0, 0] = -np.inf
+    Lt.bfTrajectorySelectReintegration.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    for topN, minDist in ((10, 0.0004), (30, 0.0), (5, 0.01)):
+        od, ol = orc.select_reintegration(opt, integ, state, topN, minDist)
+        dist = np.zeros(n, F); lst = np.full(topN, -1, np.int32); cnt = np.zeros(1, np.int32)
+        assert Lt.bfTrajectorySelectReintegration(opt.ctypes.data, integ.ctypes.data, state.ctypes.data, n, topN, minDist, 2.0, dist.ctypes.data, lst.ctypes.data, cnt.ctypes.data) == 0
+        assert cnt[0] == len(ol) and np.array_equal(lst[:cnt[0]], ol)
+        assert np.array_equal(bits(dist), bits(od))

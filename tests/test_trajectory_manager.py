@@ -54,13 +54,13 @@ def test_reintegration_selection_by_pose_distance():
     opt = np.stack(poses).copy()
     opt[1, :3, 3] += np.float32(0.5)
     opt[3, :3, 3] += np.float32(0.1)
-    opt[4, 0, 3] += np.float32(0.01)                          # dist 1e-4 < 1e-3
-    opt[2, 1, 3] += np.float32(0.05)                          # dist 2.5e-3: third largest, cut by topN = 2
+    opt[4, 0, 3] += np.float32(0.01)                          # dist 4e-4 < 1e-3
+    opt[2, 1, 3] += np.float32(0.05)                          # dist 1e-2: third largest, cut by topN = 2
     tm.updateOptimizedTransform(opt, 5)
     tm.generateUpdateLists()
     assert [tm.frameType(i) for i in range(5)] == [tmod.INTEGRATED, tmod.REINTEGRATION, tmod.INTEGRATED, tmod.REINTEGRATION, tmod.INTEGRATED]
     # the distance is taken between Lie-algebra poses (t_lie = V^-1 t), so it is |dt|^2 only up to the rotation's V^-1: a few percent here
-    for i, want in ((1, 0.75), (3, 0.03), (4, 1e-4), (2, 2.5e-3)):
+    for i, want in ((1, 4 * 0.75), (3, 4 * 0.03), (4, 4 * 1e-4), (2, 4 * 2.5e-3)):          # the factor 2 multiplies the translation part of the pose
         assert abs(tm.frameDist(i) - want) < 0.15 * want, (i, tm.frameDist(i))
     assert tm.frameDist(0) == 0.0
     assert tm.getNumActiveOperations() == 2

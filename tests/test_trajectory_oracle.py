@@ -47,7 +47,8 @@ def test_compute_sift_transform_branches():
 
 
 def test_select_reintegration_rule():
-    """dist = |(2 w, t)_integrated - (2 w, t)_optimised|^2 on the SE(3) logs; top-N integrated frames above the threshold, descending."""
+    """dist = |(2 t, w)_integrated - (2 t, w)_optimised|^2 on the SE(3) logs (the host's Pose is (translation, rotation) and the factor 2 lands on
+    components 0..2: FL/PoseHelper.h:355-358, FL/TrajectoryManager.cpp:67-74); top-N integrated frames above the threshold, descending."""
     n = 50
     integ = poses(n, 7)
     rng = np.random.default_rng(8)
@@ -60,8 +61,8 @@ def test_select_reintegration_rule():
     dist, lst = orc.select_reintegration(opt, integ, state, 3, 0.0004)
     assert lst.tolist() == [10, 3, 11]
     dist, lst = orc.select_reintegration(opt, integ, state, 10, 0.0004)
-    assert lst.tolist() == [10, 3, 11]                               # 41 moved 0.5 mm: dist 2.5e-7 < threshold; unmoved frames: 0
+    assert lst.tolist() == [10, 3, 11]                               # 41 moved 0.5 mm: dist 1e-6 < threshold; unmoved frames: 0
     assert dist[30] == -1 and dist[20] == -1
     # a left-multiplied pure translation changes t by exactly that translation (the rotation part of the log is unchanged)
-    np.testing.assert_allclose(dist[10], 0.2 ** 2, rtol=2e-3)
+    np.testing.assert_allclose(dist[10], 4 * 0.2 ** 2, rtol=2e-3)
     np.testing.assert_allclose(dist[5], 0.0, atol=1e-9)
