@@ -12,12 +12,12 @@
  * This header is the boundary a maintainer binds instead: plain pointers and sizes, one call for ALL pairs of a frame.
  * Descriptors are 128 unsigned bytes per feature, normalised to length 512 (SiftGPU convention), feature-major.
  * Semantics per pair are exactly GetSiftMatch with mutual_best_match = 1 (the only mode the reference's GetBestMatch implements):
- * Threading: like the reference's SiftGPU / SIFTImageManager (module-level __constant__ blocks and texture references, FL/Bundler.cpp's
- * mutex_siftMatcher), the entry points of this header share per-process workspaces and one stream (bfSetStream) and are not re-entrant;
- * call them from one thread per process (one process per GPU).
  * mutual best matches with dist = acos(dot / 2^18) < distmax and dist < ratiomax * dist_second, including which feature wins a tie;
  * the ORDER in which matches are appended is race-dependent in the reference (atomicAdd) and here -- consumers sort by
  * distance next (SIFTImageManager::SortKeyPointMatchesCU).  Dot products are exact int32.
+ * Threading: like the reference's SiftGPU / SIFTImageManager (module-level __constant__ blocks and texture references, FL/Bundler.cpp's
+ * mutex_siftMatcher), the entry points of this header share per-process workspaces and one stream (bfSetStream) and are not re-entrant;
+ * call them from one thread per process (one process per GPU).
  */
 #ifndef BF_SIFT_H
 #define BF_SIFT_H
