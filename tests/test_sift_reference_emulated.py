@@ -36,6 +36,11 @@ def detect_cases():
     rng = np.random.default_rng(5)
     D = np.full((96, 128), 1.5, np.float32); D[rng.random(D.shape) < 0.1] = -np.inf; D[:12] = 3.5; D[80:, 100:] = 0.05
     yield I, D, dict(base, minKeyScale=2.0, featureCountThreshold=40)
+    # 4: the application's frame size and parameters (FL/Bundler.cpp:61, s_minKeyScale 3): full list capacities, the 150-feature limit
+    I = texture(11, 480, 640)
+    rng = np.random.default_rng(11)
+    D = np.full((480, 640), 1.5, np.float32); D[rng.random(D.shape) < 0.05] = -np.inf; D[:60] = 3.5
+    yield I, D, dict(base)
 
 
 def match_cases():
