@@ -19,9 +19,9 @@
  * oracle/build_ref.py compiles it -- with SiftPyramid.cpp, SiftGPU.cpp, CuTexImage.cpp, GlobalUtil.cpp -- by g++ against a CPU emulation of
  * CUDA (oracle/ref_emu, tests/cuda_emu) into oracle/_ref/libref_sift_emulated.so; its outputs on seeded images are committed as
  * tests/golden/sift_reference_emulated.npz and this file reproduces them (tests/test_sift_reference_emulated.py): the same key points
- * bit for bit (position, scale, depth; three images incl. a half-resolution depth map with holes, the minimum-scale rule and the
- * feature-count limit), descriptors identical for > 90 % of the features and within 2 counts for the rest (the reference's histogram sums
- * run in thread order), one second orientation in 228 features decided differently (a peak sitting at the 0.8 threshold).  Also checked by
+ * bit for bit (position, scale, depth; four images incl. a half-resolution depth map with holes, the minimum-scale rule, the
+ * feature-count limit, and the application's 640x480 frame with its parameters), descriptors identical for > 90 % of the features and within 2 counts for the rest (the reference's histogram sums
+ * run in thread order), a second orientation decided differently for about one feature in 300 (a peak sitting at the 0.8 threshold).  Also checked by
  * known answers and invariances (tests/test_sift_detect_oracle.py).  Not yet compared with a run of the reference on a GPU.
  *
  * Contract where the reference is race-dependent or uses approximate hardware instructions (what a CUDA implementation is compared with):
