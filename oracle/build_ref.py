@@ -96,6 +96,7 @@ def main():
     build_siftmgr()
     build_sift_emulated()
     build_mgr_emulated()
+    build_trajectory_host()
     print("oracle/_ref built:", sorted(os.listdir(OUT)))
     return 0
 
@@ -278,6 +279,29 @@ def build_mgr_emulated():
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-8000:])
         raise RuntimeError("building libref_mgr_emulated.so failed")
+
+
+def build_trajectory_host():
+    """The reference's TrajectoryManager (FL/TrajectoryManager.{h,cpp}) and the Lie part of FL/PoseHelper.h compiled by g++ -> libref_trajectory_host.so
+    (runs on the CPU), against the minimal mLib types of oracle/ref_traj_stubs/mlib_min.h (mLib is an un-vendored submodule and does not compile
+    under g++).  Patch on the scratch copy of PoseHelper.h: the evaluation / file helpers in front of the pose maps (they need mLib's eigen
+    solver and quaternions) are cut; the Lie pose maps are untouched.  Built -DNDEBUG like the reference's Release configuration (its asserts on list
+    invariants fire on operation orders the application does not produce)."""
+    root = os.path.join(TMP, "trajhost")
+    os.makedirs(root)
+    S = os.path.join(REF, "Source")
+    for f in ("TrajectoryManager.h", "TrajectoryManager.cpp", "PoseHelper.h", "GlobalDefines.h"):
+        shutil.copy(os.path.join(S, f), root)
+    patch(os.path.join(root, "PoseHelper.h"), [
+        (r"\tstatic unsigned int countNumValidTransforms.*?(#ifndef USE_LIE_SPACE)", r"\1", 1),
+    ])
+    stubs = os.path.join(HERE, "ref_traj_stubs")
+    cmd = ["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-DNDEBUG", "-shared", "-fPIC", "-I", stubs, "-I", root,
+           os.path.join(HERE, "ref_trajectory_host.cpp"), os.path.join(root, "TrajectoryManager.cpp"), "-o", os.path.join(OUT, "libref_trajectory_host.so"), "-lm"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-6000:])
+        raise RuntimeError("building libref_trajectory_host.so failed")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY: empty stand-in (TrajectoryManager.h includes it, uses nothing from it)
+#pragma once
+#include "mlib_min.h"

@@ -6,8 +6,10 @@ Follows FL/TrajectoryManager.cpp line by line (FL = /root/reference/FriedLiver/S
   getTopFromReIntegrateList :116-136, getTopFromIntegrateList :138-153, getTopFromDeIntegrateList :155-166,
   getNumActiveOperations :193-199, invalidateFrame :201-210, getOptimizedTransforms FL/TrajectoryManager.h:49-67.
 The pose distance uses the C oracle's SE(3) logarithm (oracle/solver_oracle.c orc_matrix_to_pose, itself pinned against the
-reference's convertMatricesToPosesCU).  Parity unpinned against a RUN of the reference class (it is Windows host code inside the
-application); pinned only through that logarithm.
+reference's convertMatricesToPosesCU).  PINNED against the reference's own class: FL/TrajectoryManager.{h,cpp} + the Lie pose maps of
+FL/PoseHelper.h compiled by g++ against minimal mLib types (oracle/build_ref.py build_trajectory_host), driven through application-like
+sessions; its answers are committed as tests/golden/trajectory_manager_reference.npz and this restatement and the library's C++ replay them
+exactly (tests/test_trajectory_manager_reference.py).
 """
 import numpy as np
 
