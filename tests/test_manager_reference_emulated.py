@@ -43,6 +43,13 @@ def area_problems():
 def dense_problem():
     dv = synth.make_dense_verify_problem()
     opts = [VERIFY, dict(VERIFY, errThresh=0.0215, corrThresh=0.86), dict(VERIFY, errThresh=0.024, corrThresh=0.80), dict(VERIFY, corrThresh=0.45, errThresh=0.5)]
+    # thresholds that bracket every pair's (err, corr) of the oracle within 1e-3 relative: the reference's yes / no answers pin its two numbers
+    _, st = orc.sift_filter_dense_verify(dv["cur"], 0, dv["P"], dv["W"], dv["H"], dv["K"], np.full(dv["P"], 7, np.int32), dv["T"], dv["caches"], **VERIFY)
+    for p in range(dv["P"] - 1):
+        e, c = float(st[p, 0]), float(st[p, 1])
+        if np.isfinite(e) and c > 0:
+            opts += [dict(VERIFY, errThresh=e * (1 + 1e-3), corrThresh=c * (1 - 1e-3)), dict(VERIFY, errThresh=e * (1 - 1e-3), corrThresh=c * (1 - 1e-3)),
+                     dict(VERIFY, errThresh=e * (1 + 1e-3), corrThresh=c * (1 + 1e-3))]
     return dv, opts
 
 
