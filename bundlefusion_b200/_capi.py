@@ -126,6 +126,7 @@ SOLVER_SYMBOLS = [
     "solveBundlingStub", "buildVariablesToCorrespondencesTableCUDA", "evalMaxResidual", "countHighResiduals", "collectHighResiduals",
     "convertLiePosesToMatricesCU", "convertMatricesToPosesCU", "convertPosesToMatricesCU",
     "bfSolverSolve", "bfSolverGetStats", "bfSolverMaxResidual", "bfSolverWorkspaceBytes", "bfSolverReleaseWorkspace",
+    "bfSolverDebugDenseSystem",
 ]
 
 
@@ -294,6 +295,7 @@ def lib() -> C.CDLL:
     L.bfSolverWorkspaceBytes.argtypes = [C.c_uint, C.c_uint]
     L.bfSolverWorkspaceBytes.restype = C.c_size_t
     L.bfSolverReleaseWorkspace.argtypes = [P(BFSolverState)]
+    L.bfSolverDebugDenseSystem.argtypes = [P(BFSolverState), C.c_uint, vp, vp]
     L.bfCacheStoreFrame.argtypes = [P(BFCacheParams), vp, vp, P(BFCUDACachedFrame)]
     L.bfIngestFrame.argtypes = [P(BFIngestParams), vp, vp, vp, vp]
     L.computeSiftTransformCU.argtypes = [vp, vp, vp, C.c_uint, vp, C.c_uint, C.c_uint, vp]

@@ -69,6 +69,7 @@ struct SolverWs {
     int* rowStart = nullptr;      // [N+1] CSR offsets
     int* cursor = nullptr;        // [N]
     int* entries = nullptr;       // [2*maxCorr] correspondence indices, per row sorted by (neighbour, index)
+    int* nbrs = nullptr;          // [2*maxCorr] the other image of each row entry, written with it (never re-read from the correspondence)
     int* segCount = nullptr;      // [N]   segments of each row
     Segment* segs = nullptr;      // [2*maxCorr] segments of row v live at rowStart[v] ...
     float* offBlk = nullptr;      // [2*maxCorr][36] off-diagonal 6x6 blocks, aligned with segs
@@ -84,45 +85,53 @@ struct SolverWs {
     float* denseJtr = nullptr;    // [6 Nd]
     unsigned* scal = nullptr;     // [SC_NUM]
     int maxGrid = 0;
+    const void* owner[4] = { nullptr, nullptr, nullptr, nullptr };   // the caller's d_deltaTrans / d_rRot / d_pRot / d_Ap_XRot: a recycled
+                                                                     // d_deltaRot address with other neighbours is another solver object
 };
+static void free_ws(SolverWs& w) {
+    cudaFree(w.rowCount); cudaFree(w.rowStart); cudaFree(w.cursor); cudaFree(w.entries); cudaFree(w.nbrs); cudaFree(w.segCount); cudaFree(w.segs);
+    cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.p2); cudaFree(w.scal);
+    cudaFree(w.pairW); cudaFree(w.pairOut); cudaFree(w.denseJtJ); cudaFree(w.denseJtr);
+}
 static std::mutex g_wsMutex;
 static std::map<const void*, SolverWs> g_ws;
 
 static int get_ws(const BFSolverState* st, unsigned maxImages, unsigned maxCorr, SolverWs** out) {
     std::lock_guard<std::mutex> lk(g_wsMutex);
     auto it = g_ws.find(st->d_deltaRot);
-    if (it != g_ws.end() && it->second.maxImages >= maxImages && it->second.maxCorr >= maxCorr) { *out = &it->second; return 0; }
-    if (it != g_ws.end()) {
-        SolverWs& w = it->second;
-        cudaFree(w.rowCount); cudaFree(w.rowStart); cudaFree(w.cursor); cudaFree(w.entries); cudaFree(w.segCount); cudaFree(w.segs);
-        cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.p2); cudaFree(w.scal);
-        cudaFree(w.pairW); cudaFree(w.pairOut); cudaFree(w.denseJtJ); cudaFree(w.denseJtr);
-        g_ws.erase(it);
+    const void* owner[4] = { st->d_deltaTrans, st->d_rRot, st->d_pRot, st->d_Ap_XRot };
+    if (it != g_ws.end() && it->second.maxImages >= maxImages && it->second.maxCorr >= maxCorr && memcmp(it->second.owner, owner, sizeof(owner)) == 0) {
+        *out = &it->second; return 0;
     }
+    if (it != g_ws.end()) { free_ws(it->second); g_ws.erase(it); }
     SolverWs w;
     w.maxImages = maxImages; w.maxCorr = maxCorr ? maxCorr : 1;
     w.maxGrid = num_sms() * 4;
+    memcpy(w.owner, owner, sizeof(owner));
     const size_t E = 2 * (size_t)w.maxCorr;
-    BF_CHECK(cudaMalloc(&w.rowCount, sizeof(int) * maxImages));
-    BF_CHECK(cudaMalloc(&w.rowStart, sizeof(int) * (maxImages + 1)));
-    BF_CHECK(cudaMalloc(&w.cursor, sizeof(int) * maxImages));
-    BF_CHECK(cudaMalloc(&w.entries, sizeof(int) * E));
-    BF_CHECK(cudaMalloc(&w.segCount, sizeof(int) * maxImages));
-    BF_CHECK(cudaMalloc(&w.segs, sizeof(Segment) * E));
-    BF_CHECK(cudaMalloc(&w.offBlk, sizeof(float) * 36 * E));
-    BF_CHECK(cudaMalloc(&w.segMom, sizeof(float) * 20 * E));
-    BF_CHECK(cudaMalloc(&w.diagBlk, sizeof(float) * 36 * maxImages));
-    BF_CHECK(cudaMalloc(&w.partials, sizeof(float) * 2 * w.maxGrid));
-    BF_CHECK(cudaMalloc(&w.p2, sizeof(float) * 6 * maxImages));
-    BF_CHECK(cudaMalloc(&w.scal, sizeof(unsigned) * SC_NUM));
+    // every buffer is zeroed once at creation: nothing a kernel reads before writing can depend on what the allocator hands back
+#define BF_WS_ALLOC(ptr, bytes) do { BF_CHECK(cudaMalloc(&(ptr), (bytes))); BF_CHECK(cudaMemsetAsync((ptr), 0, (bytes), stream())); } while (0)
+    BF_WS_ALLOC(w.rowCount, sizeof(int) * maxImages);
+    BF_WS_ALLOC(w.rowStart, sizeof(int) * (maxImages + 1));
+    BF_WS_ALLOC(w.cursor, sizeof(int) * maxImages);
+    BF_WS_ALLOC(w.entries, sizeof(int) * E);
+    BF_WS_ALLOC(w.nbrs, sizeof(int) * E);
+    BF_WS_ALLOC(w.segCount, sizeof(int) * maxImages);
+    BF_WS_ALLOC(w.segs, sizeof(Segment) * E);
+    BF_WS_ALLOC(w.offBlk, sizeof(float) * 36 * E);
+    BF_WS_ALLOC(w.segMom, sizeof(float) * 20 * E);
+    BF_WS_ALLOC(w.diagBlk, sizeof(float) * 36 * maxImages);
+    BF_WS_ALLOC(w.partials, sizeof(float) * 2 * w.maxGrid);
+    BF_WS_ALLOC(w.p2, sizeof(float) * 6 * maxImages);
+    BF_WS_ALLOC(w.scal, sizeof(unsigned) * SC_NUM);
     {
         const size_t Nd = BF_DENSE_MAX_IMAGES;
-        BF_CHECK(cudaMalloc(&w.pairW, sizeof(float) * Nd * Nd));
-        BF_CHECK(cudaMalloc(&w.pairOut, sizeof(float) * Nd * Nd * 90));
-        BF_CHECK(cudaMalloc(&w.denseJtJ, sizeof(float) * 36 * Nd * Nd));
-        BF_CHECK(cudaMalloc(&w.denseJtr, sizeof(float) * 6 * Nd));
+        BF_WS_ALLOC(w.pairW, sizeof(float) * Nd * Nd);
+        BF_WS_ALLOC(w.pairOut, sizeof(float) * Nd * Nd * 90);
+        BF_WS_ALLOC(w.denseJtJ, sizeof(float) * 36 * Nd * Nd);
+        BF_WS_ALLOC(w.denseJtr, sizeof(float) * 6 * Nd);
     }
-    BF_CHECK(cudaMemsetAsync(w.scal, 0, sizeof(unsigned) * SC_NUM, stream()));
+#undef BF_WS_ALLOC
     auto res = g_ws.emplace(st->d_deltaRot, w);
     *out = &res.first->second;
     return 0;
@@ -162,13 +171,14 @@ __global__ void prep_scan_kernel(const int* __restrict__ rowCount, int* rowStart
     if (t == blockDim.x - 1) rowStart[N] = sSum[t];
     if (t == 0) { scal[SC_DONE] = 0; scal[SC_GN_RUN] = 0; scal[SC_PCG_RUN] = 0; scal[SC_ERROR] = 0; }
 }
-__global__ void prep_scatter_kernel(const BFEntryJ* __restrict__ corr, unsigned C, const int* __restrict__ rowStart, int* cursor, int* entries) {
+__global__ void prep_scatter_kernel(const BFEntryJ* __restrict__ corr, unsigned C, const int* __restrict__ rowStart, int* cursor, int* entries, int* nbrs) {
     const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= C) return;
     const unsigned i = corr[x].imgIdx_i, j = corr[x].imgIdx_j;
     if (i == 0xFFFFFFFFu) return;
-    entries[rowStart[i] + atomicAdd(&cursor[i], 1)] = (int)x;
-    entries[rowStart[j] + atomicAdd(&cursor[j], 1)] = (int)x;
+    const int pi = rowStart[i] + atomicAdd(&cursor[i], 1), pj = rowStart[j] + atomicAdd(&cursor[j], 1);
+    entries[pi] = (int)x; nbrs[pi] = (int)j;
+    entries[pj] = (int)x; nbrs[pj] = (int)i;
 }
 // bitonic sort of n 64-bit keys held in shared memory (n padded to a power of two with ~0 keys)
 __device__ void bitonic_sort_smem(unsigned long long* keys, unsigned nPow2) {
@@ -188,39 +198,63 @@ __device__ void bitonic_sort_smem(unsigned long long* keys, unsigned nPow2) {
 }
 // one CTA per image row: (1) sort the row by correspondence index -> reference-format table row + overflow
 // invalidation (SolverBundling.cu:1237-1245 with arrival rank = ascending index); (2) sort by (neighbour, index) and
-// cut the row into neighbour segments.
+// cut the row into neighbour segments.  The neighbour of a row entry comes from the array the scatter kernel wrote, never from
+// the correspondence itself: another row's CTA may be invalidating that correspondence at this moment (two separate stores).
+// Rows longer than BF_MAX_ROW (> maxCorrPerImage, checked by the host) keep their maxCorrPerImage smallest indices, found by
+// a bisection on the index value over the row in global memory; the rest is invalidated as the reference does.
 __global__ void __launch_bounds__(256)
-prep_rows_kernel(BFEntryJ* corr, const int* __restrict__ rowStart, int* entries, int* segCount, Segment* segs,
+prep_rows_kernel(BFEntryJ* corr, const int* __restrict__ rowStart, int* entries, int* nbrs, int* segCount, Segment* segs,
                  int* varToCorr, unsigned maxCorrPerImage, unsigned* scal) {
     extern __shared__ unsigned long long sKeys[];
+    __shared__ unsigned sCnt;
     const unsigned v = blockIdx.x;
-    const int start = rowStart[v], n = rowStart[v + 1] - start;
+    const int start = rowStart[v];
+    int n = rowStart[v + 1] - start;
     if (threadIdx.x == 0) segCount[v] = 0;
     if (n <= 0) return;
-    if (n > BF_MAX_ROW) { if (threadIdx.x == 0) atomicExch(&scal[SC_ERROR], 1u); return; }
+    if (n > BF_MAX_ROW) {
+        // smallest T with #{entries <= T} >= maxCorrPerImage (indices within a row are distinct)
+        unsigned lo = 0u, hi = 0x7FFFFFFFu;
+        while (lo < hi) {
+            const unsigned mid = lo + (hi - lo) / 2;
+            if (threadIdx.x == 0) sCnt = 0;
+            __syncthreads();
+            unsigned c = 0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) c += ((unsigned)entries[start + i] <= mid) ? 1u : 0u;
+            c = warp_sum_u(c);
+            if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sCnt, c);
+            __syncthreads();
+            const unsigned tot = sCnt;
+            __syncthreads();
+            if (tot >= maxCorrPerImage) hi = mid; else lo = mid + 1;
+        }
+        if (threadIdx.x == 0) sCnt = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned c = (unsigned)entries[start + i];
+            if (c <= lo) sKeys[atomicAdd(&sCnt, 1u)] = ((unsigned long long)c << 32) | (unsigned)nbrs[start + i];
+            else { corr[c].imgIdx_i = 0xFFFFFFFFu; corr[c].imgIdx_j = 0xFFFFFFFFu; }
+        }
+        __syncthreads();
+        n = (int)sCnt;                                       // == maxCorrPerImage <= BF_MAX_ROW
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sKeys[i] = ((unsigned long long)(unsigned)entries[start + i] << 32) | (unsigned)nbrs[start + i];
+    }
     unsigned nPow2 = 1; while (nPow2 < (unsigned)n) nPow2 <<= 1;
-    for (unsigned i = threadIdx.x; i < nPow2; i += blockDim.x) sKeys[i] = (i < (unsigned)n) ? (unsigned long long)(unsigned)entries[start + i] : ~0ull;
+    for (unsigned i = n + threadIdx.x; i < nPow2; i += blockDim.x) sKeys[i] = ~0ull;
     __syncthreads();
     bitonic_sort_smem(sKeys, nPow2);
-    // (1) table row + invalidation of the overflow tail
+    // (1) table row + invalidation of the overflow tail; the kept part is re-keyed (neighbour, index), the tail parked at the end
     for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
-        const unsigned c = (unsigned)sKeys[i];
-        if (i < maxCorrPerImage) { if (varToCorr) varToCorr[(size_t)v * maxCorrPerImage + i] = (int)c; }
-        else { corr[c].imgIdx_i = 0xFFFFFFFFu; corr[c].imgIdx_j = 0xFFFFFFFFu; }      // setInvalid (both rows may do it; same value)
+        const unsigned c = (unsigned)(sKeys[i] >> 32), nb = (unsigned)sKeys[i];
+        if (i < maxCorrPerImage) { if (varToCorr) varToCorr[(size_t)v * maxCorrPerImage + i] = (int)c; sKeys[i] = ((unsigned long long)nb << 32) | c; }
+        else { corr[c].imgIdx_i = 0xFFFFFFFFu; corr[c].imgIdx_j = 0xFFFFFFFFu; sKeys[i] = ((unsigned long long)0x7FFFFFFFu << 32) | c; }      // setInvalid (both rows may do it; same value)
     }
     __syncthreads();
-    // (2) key = neighbour << 32 | index.  Entries invalidated by another row just now keep their (stale) neighbour:
-    // read the indices through a private copy taken before step (1) is visible?  Not needed: an invalid entry is
-    // skipped by the block build whatever segment it sits in, so park them under neighbour 0x7FFFFFFF.
-    for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) {
-        const unsigned c = (unsigned)sKeys[i];
-        const unsigned ci = corr[c].imgIdx_i, cj = corr[c].imgIdx_j;
-        const unsigned nbr = (ci == 0xFFFFFFFFu) ? 0x7FFFFFFFu : ((ci == v) ? cj : ci);
-        sKeys[i] = ((unsigned long long)nbr << 32) | c;
-    }
-    __syncthreads();
+    // (2) An entry the OTHER row of its correspondence invalidates keeps its place: the block build skips invalid entries whatever
+    // segment they sit in.
     bitonic_sort_smem(sKeys, nPow2);
-    for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) entries[start + i] = (int)(unsigned)sKeys[i];
+    for (unsigned i = threadIdx.x; i < (unsigned)n; i += blockDim.x) { entries[start + i] = (int)(unsigned)sKeys[i]; nbrs[start + i] = (int)(unsigned)(sKeys[i] >> 32); }
     // segment heads, in order: serial over the row by one warp-sized stride would reorder, so thread 0 walks it
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -441,7 +475,7 @@ gn_iteration_kernel(const GnArgs a) {
             float y[6] = { 0, 0, 0, 0, 0, 0 };
             for (int sI = lane; sI < ns; sI += 32) {
                 const unsigned o = (unsigned)a.segs[rs + sI].nbr;
-                if (o == 0) continue;                                   // variable 0 is fixed: its p is zero by construction
+                if (o == 0 || o >= N) continue;                         // variable 0 is fixed: its p is zero by construction
                 const V3 pr = fly ? ld3(a.zRot, o) + ld3(prvR, o) * beta : ld3(a.pRot, o);
                 const V3 pt = fly ? ld3(a.zTrans, o) + ld3(prvT, o) * beta : ld3(a.pTrans, o);
                 blk_mv(&a.offBlk[36 * (size_t)(rs + sI)], pr, pt, y);
@@ -944,11 +978,11 @@ static int run_prep(const BFSolverInput* in, const BFSolverState* st, SolverWs* 
     BF_CHECK(cudaMemsetAsync(ws->scal + SC_NUM_SEG, 0, sizeof(unsigned), stream()));
     if (C > 0) prep_count_kernel<<<(C + 255) / 256, 256, 0, stream()>>>(in->d_correspondences, C, ws->rowCount);
     prep_scan_kernel<<<1, 1024, 0, stream()>>>(ws->rowCount, ws->rowStart, ws->cursor, in->d_numEntriesPerRow, N, ws->scal);
-    if (C > 0) prep_scatter_kernel<<<(C + 255) / 256, 256, 0, stream()>>>(in->d_correspondences, C, ws->rowStart, ws->cursor, ws->entries);
+    if (C > 0) prep_scatter_kernel<<<(C + 255) / 256, 256, 0, stream()>>>(in->d_correspondences, C, ws->rowStart, ws->cursor, ws->entries, ws->nbrs);
     g_launchCount += (C > 0 ? 4 : 2);
     static bool attrSet = false;
     if (!attrSet) { BF_CHECK(cudaFuncSetAttribute(prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_MAX_ROW * 8)); attrSet = true; }
-    prep_rows_kernel<<<N, 256, BF_MAX_ROW * 8, stream()>>>(in->d_correspondences, ws->rowStart, ws->entries, ws->segCount, ws->segs,
+    prep_rows_kernel<<<N, 256, BF_MAX_ROW * 8, stream()>>>(in->d_correspondences, ws->rowStart, ws->entries, ws->nbrs, ws->segCount, ws->segs,
                                                           in->d_variablesToCorrespondences, in->maxCorrPerImage, ws->scal);
     BF_CHECK(cudaGetLastError());
     (void)st;
@@ -1046,6 +1080,10 @@ static int solve_impl(const BFSolverInput* in, const BFSolverState* st, const BF
             set_last_error("bfSolverSolve: the dense depth/colour term is built for <= 64 images (chunk-sized problems) in this round", cudaErrorNotSupported);
             return (int)cudaErrorNotSupported;
         }
+    if (in->maxCorrPerImage == 0 || in->maxCorrPerImage > BF_MAX_ROW) {      // CUDASolverBundling.cpp:39 clamps it to [1000, 4000]
+        set_last_error("bfSolverSolve: maxCorrPerImage must be in [1, 8192]", cudaErrorInvalidValue);
+        return (int)cudaErrorInvalidValue;
+    }
     SolverWs* ws;
     unsigned cap = 1024;                                  // grow geometrically so a growing problem rarely reallocates
     while (cap < in->numberOfCorrespondences) cap <<= 1;
@@ -1097,17 +1135,27 @@ BF_API int bfSolverMaxResidual(const BFSolverInput* in, const BFSolverState* st,
 
 BF_API size_t bfSolverWorkspaceBytes(unsigned int maxImages, unsigned int maxRes) {
     const size_t E = 2 * (size_t)maxRes;
-    return sizeof(int) * (3 * (size_t)maxImages + 1 + E + maxImages) + sizeof(Segment) * E + sizeof(float) * (36 + 20) * E + sizeof(float) * 36 * maxImages;
+    return sizeof(int) * (3 * (size_t)maxImages + 1 + 2 * E + maxImages) + sizeof(Segment) * E + sizeof(float) * (36 + 20) * E + sizeof(float) * 36 * maxImages;
 }
 BF_API int bfSolverReleaseWorkspace(const BFSolverState* st) {
     std::lock_guard<std::mutex> lk(g_wsMutex);
     auto it = g_ws.find(st->d_deltaRot);
     if (it == g_ws.end()) return 0;
-    SolverWs& w = it->second;
-    cudaFree(w.rowCount); cudaFree(w.rowStart); cudaFree(w.cursor); cudaFree(w.entries); cudaFree(w.segCount); cudaFree(w.segs);
-    cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.p2); cudaFree(w.scal);
-        cudaFree(w.pairW); cudaFree(w.pairOut); cudaFree(w.denseJtJ); cudaFree(w.denseJtr);
+    free_ws(it->second);
     g_ws.erase(it);
+    return 0;
+}
+
+// Test / diagnosis accessor: the dense normal equations of the LAST Gauss-Newton iteration that built them, in the reference's
+// layout (FL/Solver/SolverBundling.cu:308-471: (6N)^2 row-major, translation first per image; J^T r [6N]) -- what the
+// reference keeps in SolverState::d_denseJtJ / d_denseJtr.  Device-to-device copies on the library stream.
+BF_API int bfSolverDebugDenseSystem(const BFSolverState* st, unsigned int numImages, float* d_JtJ, float* d_Jtr) {
+    SolverWs* ws = nullptr;
+    { std::lock_guard<std::mutex> lk(g_wsMutex); auto it = g_ws.find(st->d_deltaRot); if (it != g_ws.end()) ws = &it->second; }
+    if (!ws || numImages > BF_DENSE_MAX_IMAGES) return (int)cudaErrorInvalidValue;
+    const size_t dim = 6 * (size_t)numImages;
+    if (d_JtJ) BF_CHECK(cudaMemcpyAsync(d_JtJ, ws->denseJtJ, sizeof(float) * dim * dim, cudaMemcpyDeviceToDevice, stream()));
+    if (d_Jtr) BF_CHECK(cudaMemcpyAsync(d_Jtr, ws->denseJtr, sizeof(float) * dim, cudaMemcpyDeviceToDevice, stream()));
     return 0;
 }
 

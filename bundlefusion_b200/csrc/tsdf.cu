@@ -18,6 +18,7 @@
 //  * garbage collection is a single fused kernel (identify + unlink + heap push + clear).
 //
 // Compiled with -fmad=false so that float results are bit-identical to oracle/tsdf_oracle.c.
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
@@ -62,6 +63,8 @@ struct TsdfAux {
     cudaEvent_t evFork = nullptr, evList[2] = { nullptr, nullptr }, evStencil[2] = { nullptr, nullptr };
     bool stencilPending[2] = { false, false };
     bool pipeOpen = false;
+    const void* owner[3] = { nullptr, nullptr, nullptr };   // the caller's d_SDFBlocks / d_heap / d_hashCompactified: the key (d_hash) can be
+                                                            // recycled by an allocator for another table; all four together identify one
 };
 enum { CTR_HIGH_WATER = 0, CTR_E = 3, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROPPED = 10, CTR_U_TOT_LO = 12, CTR_U_TOT_HI = 13, CTR_E_TOT_LO = 14, CTR_E_TOT_HI = 15,
        // two per-list counter sets (the list / work list of op k and of op k+1 are alive at the same time when alloc + compactify of
@@ -1296,11 +1299,14 @@ static void free_aux(TsdfAux& a) {
 static int get_aux(const BFHashDataStruct* hd, const BFHashParams* hp, TsdfAux** out, bool create, bool adopt) {
     std::lock_guard<std::mutex> lk(g_auxMutex);
     auto it = g_aux.find(hd->d_hash);
-    if (it != g_aux.end() && (hp == nullptr || it->second.numSlots == hp->m_numSDFBlocks)) { *out = &it->second; return 0; }
+    const void* owner[3] = { hd->d_SDFBlocks, hd->d_heap, hd->d_hashCompactified };
+    const bool same = it != g_aux.end() && memcmp(it->second.owner, owner, sizeof(owner)) == 0;
+    if (same && (hp == nullptr || it->second.numSlots == hp->m_numSDFBlocks)) { *out = &it->second; return 0; }
     if (!create || hp == nullptr) { *out = nullptr; return (int)cudaErrorInvalidValue; }
     if (it != g_aux.end()) { free_aux(it->second); g_aux.erase(it); }
     TsdfAux a;
     a.numSlots = hp->m_numSDFBlocks;
+    memcpy(a.owner, owner, sizeof(owner));
     BF_CHECK(cudaMalloc(&a.slotInfo, sizeof(int4) * (size_t)a.numSlots));
     BF_CHECK(cudaMalloc(&a.ctrs, sizeof(unsigned) * CTR_NUM));
     BF_CHECK(cudaMalloc(&a.live, sizeof(int) * (size_t)a.numSlots));

@@ -178,6 +178,11 @@ int bfSolverMaxResidual(const BFSolverInput* input, const BFSolverState* state, 
 size_t bfSolverWorkspaceBytes(unsigned int maxNumberOfImages, unsigned int maxNumResiduals);
 int bfSolverReleaseWorkspace(const BFSolverState* state);
 
+/* Test / diagnosis accessor: the dense depth/colour normal equations of the last Gauss-Newton iteration that built them, in the
+ * reference's layout -- what it keeps in SolverState::d_denseJtJ [(6N)^2, row-major, translation first per image] and d_denseJtr [6N]
+ * (FL/Solver/SolverBundling.cu:308-471).  Either output may be NULL.  Asynchronous device-to-device copies. */
+int bfSolverDebugDenseSystem(const BFSolverState* state, unsigned int numberOfImages, float* d_JtJ, float* d_Jtr);
+
 #ifdef __cplusplus
 }
 #endif

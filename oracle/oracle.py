@@ -192,8 +192,36 @@ def _bind_solver(L):
     L.orc_solver_max_residual.restype = C.c_float
     L.orc_solver_energy.argtypes = [C.c_void_p, C.c_uint, fp, fp, C.c_float]
     L.orc_solver_energy.restype = C.c_double
+    L.orc_solver_set_trace.argtypes = [C.c_void_p, C.c_uint]
+    L.orc_solver_set_trace.restype = None
+    L.orc_solver_trace_count.argtypes = []
+    L.orc_solver_trace_count.restype = C.c_uint
     L._solver_bound = True
     return L
+
+
+class _Trace:
+    """Records the early-out decisions of one oracle solve (orc_solver_set_trace): list of (gn, p.Ap) and (-(gn+1), max|delta|)."""
+
+    def __init__(self, L, cap=8192):
+        self.L, self.buf = L, np.zeros(2 * cap, np.float32)
+        L.orc_solver_set_trace(self.buf.ctypes.data, cap)
+
+    def finish(self):
+        n = min(self.L.orc_solver_trace_count(), len(self.buf) // 2)
+        self.L.orc_solver_set_trace(None, 0)
+        return self.buf[:2 * n].reshape(-1, 2).copy()
+
+
+def decision_margin(trace) -> float:
+    """Smallest relative distance of any recorded early-out decision from its threshold: p.Ap against 5e-7 (last iteration,
+    SolverBundling.cu:1092) and 1e-6 (alpha guard, :959), max|delta| against 0.005 (:1206).  0.3 means every decision would survive
+    a 30 % change of the value it tests -- float summation order moves these by ~1e-6 relative."""
+    m = np.inf
+    for k, v in trace:
+        for thr in ((5e-7, 1e-6) if k >= 0 else (0.005,)):
+            m = min(m, abs(abs(float(v)) - thr) / thr)
+    return float(m)
 
 
 def pose_to_matrix(rot, trans) -> np.ndarray:
@@ -222,9 +250,11 @@ def solve_sparse(corr: np.ndarray, rot0, trans0, n_gn: int, n_pcg: int, weights=
     table = np.zeros(N * max_corr_per_image, np.int32)
     rows = np.zeros(N, np.int32)
     stats = (C.c_uint * 4)()
+    tr = _Trace(L)
     rc = L.orc_solver_solve_sparse(corr.ctypes.data, len(corr), N, max_corr_per_image, rot, trans, n_gn, n_pcg, w, 1, table, rows, stats)
+    trace = tr.finish()
     assert rc == 0
-    return {"rot": rot, "trans": trans, "gn": stats[0], "pcg": stats[1], "corr": corr, "rows": rows}
+    return {"rot": rot, "trans": trans, "gn": stats[0], "pcg": stats[1], "corr": corr, "rows": rows, "trace": trace}
 
 
 def max_residual(corr, rot, trans, w=1.0):
@@ -294,11 +324,14 @@ def solve(corr, rot0, trans0, n_gn, n_pcg, w_sparse, w_depth=None, w_color=None,
         frames, keep = _pack_frames(caches)
         dp = dense_params(intrinsics, caches[0]["depth"].shape[1], caches[0]["depth"].shape[0], pairwise)
     v = np.ascontiguousarray(valid, np.int32) if valid is not None else None
+    tr = _Trace(L)
     rc = L.orc_solver_solve(corr.ctypes.data, len(corr), N, max_corr_per_image, rot, trans, n_gn, n_pcg, wS, wD.ctypes.data, wC.ctypes.data,
                             C.cast(frames, C.c_void_p) if frames is not None else None, C.cast(C.pointer(dp), C.c_void_p) if dp is not None else None,
                             v.ctypes.data if v is not None else None, table, rows, stats)
+    trace = tr.finish()
     assert rc == 0
-    return {"rot": rot, "trans": trans, "gn": stats[0], "pcg": stats[1], "overlap_pairs": stats[2], "weighted_pairs": stats[3], "corr": corr, "rows": rows}
+    return {"rot": rot, "trans": trans, "gn": stats[0], "pcg": stats[1], "overlap_pairs": stats[2], "weighted_pairs": stats[3], "corr": corr, "rows": rows,
+            "trace": trace}
 
 
 def build_dense(rot, trans, caches, intrinsics, w_depth, w_color, valid=None, pairwise=True):

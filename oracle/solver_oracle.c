@@ -35,6 +35,13 @@
 
 #define ORC_API __attribute__((visibility("default")))
 #define FLOAT_EPSILON 0.000001f       /* FL/SolverUtil.h:9 */
+/* Decision trace (tests): every early-out decision of the last solve -- per PCG iteration (GN index, p.Ap), per evaluated GN
+ * convergence test (-(GN index + 1), max|delta|).  The parity tests use it to certify that a problem's decisions sit clear of their
+ * thresholds (5e-7, 1e-6, 0.005), i.e. that a last-bit difference in a float sum cannot send two implementations down different paths. */
+static float* g_trace = 0; static unsigned g_traceCap = 0, g_traceN = 0;
+ORC_API void orc_solver_set_trace(float* buf, unsigned capPairs) { g_trace = buf; g_traceCap = capPairs; g_traceN = 0; }
+ORC_API unsigned orc_solver_trace_count(void) { return g_traceN; }
+static void trace_put(float a, float b) { if (g_trace && g_traceN < g_traceCap) { g_trace[2 * g_traceN] = a; g_trace[2 * g_traceN + 1] = b; } if (g_trace) ++g_traceN; }
 
 typedef struct { float x, y, z; } v3;
 static inline v3 V(float x, float y, float z) { v3 r = { x, y, z }; return r; }
@@ -329,6 +336,7 @@ ORC_API int orc_solver_solve_sparse(BFEntryJ* corr, unsigned C, unsigned N, unsi
                 scanAlpha1 += dot(zR, rR) + dot(zT, rT);
             }
             if (getenv("ORC_DEBUG")) fprintf(stderr, "gn %u pcg %u pAp %.6e rz_old %.6e rz_new %.6e\n", nIter, lin, scanAlpha0, s.rDotzOld[1], scanAlpha1);
+            trace_put((float)nIter, scanAlpha0);
             if (fabsf(scanAlpha0) < 5e-7f) last = 1;
             for (unsigned x = 1; x < N; ++x) {
                 const float rDotzNew = scanAlpha1, rDotzOld = s.rDotzOld[x];
@@ -354,6 +362,7 @@ ORC_API int orc_solver_solve_sparse(BFEntryJ* corr, unsigned C, unsigned N, unsi
             for (unsigned x = 1; x < N; ++x) for (int k = 0; k < 3; ++k) {
                 m = fmaxf(m, fabsf(s.deltaRot[3 * x + k])); m = fmaxf(m, fabsf(s.deltaTrans[3 * x + k]));
             }
+            trace_put(-(float)(nIter + 1), m);
             if (m < 0.005f) break;
         }
     }
@@ -706,6 +715,7 @@ ORC_API int orc_solver_solve(BFEntryJ* corr, unsigned C, unsigned N, unsigned ma
                 st3(s.zRot, x, zR); st3(s.zTrans, x, zT);
                 scanAlpha1 += dot(zR, rR) + dot(zT, rT);
             }
+            trace_put((float)nIter, scanAlpha0);
             if (fabsf(scanAlpha0) < 5e-7f) last = 1;
             for (unsigned x = 1; x < N; ++x) {
                 const float rDotzNew = scanAlpha1, rDotzOld = s.rDotzOld[x];
@@ -731,6 +741,7 @@ ORC_API int orc_solver_solve(BFEntryJ* corr, unsigned C, unsigned N, unsigned ma
                 if (valid && valid[x] == 0) continue;
                 for (int k = 0; k < 3; ++k) { m = fmaxf(m, fabsf(s.deltaRot[3 * x + k])); m = fmaxf(m, fabsf(s.deltaTrans[3 * x + k])); }
             }
+            trace_put(-(float)(nIter + 1), m);
             if (m < 0.005f) break;
         }
     }

@@ -81,18 +81,70 @@ def test_sparse_solve_matches_reference_cuda(cuda_device, n_images, degree, n_gn
     np.testing.assert_array_equal(x_ref[0], x_our[0])                       # variable 0 is fixed in both
 
 
+def _ulp_perturbed(prob, seed):
+    """initial poses moved by at most 2 ulp (variable 0 untouched): the size of the perturbation a different float summation order is"""
+    rng = np.random.default_rng(seed)
+    r, t = prob["init_rot"].copy(), prob["init_trans"].copy()
+    r = (r * (1 + rng.integers(-2, 3, r.shape) * 6e-8)).astype(np.float32)
+    t = (t * (1 + rng.integers(-2, 3, t.shape) * 6e-8)).astype(np.float32)
+    r[0], t[0] = prob["init_rot"][0], prob["init_trans"][0]
+    return r, t
+
+
+def oracle_sensitivity(prob, corr, n_gn, n_pcg, wS, wD, wC, n=4):
+    """Largest relative-L2 move of the ORACLE's solution under 2-ulp perturbations of the initial poses.  The reference sums with float
+    atomics in scheduling order, i.e. it perturbs itself by about this much from run to run; a problem whose solution
+    moves more than the parity tolerance under such a perturbation cannot pin anything at that tolerance."""
+    o = orc.solve(corr, prob["init_rot"], prob["init_trans"], n_gn, n_pcg, wS, wD, wC, prob["caches"], prob["intrinsics"])
+    x0 = np.c_[o["rot"], o["trans"]]
+    worst = 0.0
+    for k in range(n):
+        r, t = _ulp_perturbed(prob, k)
+        q = orc.solve(corr, r, t, n_gn, n_pcg, wS, wD, wC, prob["caches"], prob["intrinsics"])
+        worst = max(worst, rel_l2(np.c_[q["rot"], q["trans"]], x0))
+    return worst, o
+
+
 def test_dense_only_matches_reference_cuda(cuda_device):
+    """Dense depth term alone (PCGIteration<false,true>, SolverBundling.cu:1181-1184).  The problem is CERTIFIED well-posed by the oracle
+    before it is used: its solution moves < 1e-5 under 2-ulp input perturbations and every early-out decision (|p.Ap| vs 5e-7 / 1e-6,
+    max|delta| vs 0.005) is at least 30 % clear of its threshold."""
+    prob = synth.make_dense_ba_problem(8, stride=2, perturb_rot=0.004, perturb_trans=0.008, W=320, H=240)
+    cache = DeviceCache(prob["caches"], prob["intrinsics"], cuda_device)
+    wS, wD, wC = [0.0] * 2, [1.0, 2.0], [0.0] * 2
+    empty = prob["corr"][:0]
+    sens, o = oracle_sensitivity(prob, empty, 2, 10, wS, wD, wC)
+    assert sens < 1e-5 and orc.decision_margin(o["trace"]) > 0.3, "test problem is not well-posed"
+    x_ref, _, s = run_ref(cuda_device, prob, empty, 2, 10, wS, wD, wC, cache=cache, fast=False)
+    x_ref2, _, _ = run_ref(cuda_device, prob, empty, 2, 10, wS, wD, wC, cache=cache, fast=False)
+    x_our, st = run_ours(cuda_device, prob, empty, 2, 10, wS, wD, wC, cache=cache)
+    n_overlap_ref = int(s._bufs["d_numDenseOverlappingImages"].cpu().numpy()[0])
+    assert st["dense_overlap_pairs"] == n_overlap_ref == o["overlap_pairs"]
+    assert rel_l2(x_ref2, x_ref) < TOL, "the reference does not reproduce itself on this problem"
+    assert rel_l2(x_our, x_ref) < TOL
+    assert rel_l2(np.c_[o["rot"], o["trans"]], x_ref) < TOL
+
+
+def test_dense_only_chaotic_configuration_is_bounded_by_its_own_sensitivity(cuda_device):
+    """Round 1's dense-only case (5 frames, 3 GN x 60 PCG) FAILED on the driver's box at 2.1e-2 after passing on another.  Cause, found
+    with the oracle: with weightSparse == 0 the preconditioner is the identity, PCG stagnates with |p.Ap| hovering around the 5e-7 / 1e-6
+    guards, and whether iteration 16 of the first Gauss-Newton step takes the early-out decides between two end points 2e-2 apart -- a
+    2-ulp change of the input flips it (the oracle shows the same 2.1e-2 against itself).  The reference's float atomics are such a
+    change.  So here the bound is the problem's own measured sensitivity, and the fixed-order implementations (library, oracle) must
+    still agree with each other."""
     prob = synth.make_dense_ba_problem(5, stride=3, perturb_rot=0.004, perturb_trans=0.008, W=320, H=240)
     cache = DeviceCache(prob["caches"], prob["intrinsics"], cuda_device)
     wS, wD, wC = [0.0] * 3, [1.0, 2.0, 3.0], [0.0] * 3
     empty = prob["corr"][:0]
-    x_ref, _, s = run_ref(cuda_device, prob, empty, 3, 60, wS, wD, wC, cache=cache, fast=False)
-    x_our, st = run_ours(cuda_device, prob, empty, 3, 60, wS, wD, wC, cache=cache)
-    o = orc.solve(empty, prob["init_rot"], prob["init_trans"], 3, 60, wS, wD, wC, prob["caches"], prob["intrinsics"])
-    n_overlap_ref = int(s._bufs["d_numDenseOverlappingImages"].cpu().numpy()[0])
-    assert st["dense_overlap_pairs"] == n_overlap_ref == o["overlap_pairs"]
-    assert rel_l2(x_our, x_ref) < TOL
-    assert rel_l2(np.c_[o["rot"], o["trans"]], x_ref) < TOL
+    sens, o = oracle_sensitivity(prob, empty, 3, 60, wS, wD, wC, n=6)
+    assert sens > 1e-3, "this configuration is expected to be chaotic (documented above)"
+    x_ref, _, _ = run_ref(cuda_device, prob, empty, 3, 60, wS, wD, wC, cache=cache, fast=False)
+    x_our, _ = run_ours(cuda_device, prob, empty, 3, 60, wS, wD, wC, cache=cache)
+    assert rel_l2(x_our, x_ref) < max(TOL, 3 * sens)
+    # the first Gauss-Newton step truncated before the stagnation (10 PCG iterations) is decided identically by everyone
+    x_ref1, _, _ = run_ref(cuda_device, prob, empty, 1, 10, wS[:1], wD[:1], wC[:1], cache=cache, fast=False)
+    x_our1, _ = run_ours(cuda_device, prob, empty, 1, 10, wS[:1], wD[:1], wC[:1], cache=cache)
+    assert rel_l2(x_our1, x_ref1) < 2e-4
 
 
 @pytest.mark.parametrize("fast", [True, False])
@@ -112,7 +164,9 @@ def test_local_chunk_sparse_plus_dense_matches_reference_cuda(cuda_device, wC, f
 
 def test_dense_system_matches_reference_cuda(cuda_device):
     """The assembled dense normal equations themselves: the reference's d_denseJtJ (6N x 6N) / d_denseJtr after BuildDenseSystem
-    against the oracle's, entry for entry (float-atomic summation order differs: relative Frobenius 1e-4)."""
+    against THIS LIBRARY's (bfSolverDebugDenseSystem) and the oracle's, entry for entry (float-atomic summation order differs: relative
+    Frobenius 1e-4).  This is the deterministic parity statement for row a13: no solver dynamics in between."""
+    import torch
     prob = synth.make_dense_ba_problem(6, stride=3, W=320, H=240)
     cache = DeviceCache(prob["caches"], prob["intrinsics"], cuda_device)
     N = 6
@@ -125,6 +179,20 @@ def test_dense_system_matches_reference_cuda(cuda_device):
     assert np.linalg.norm(JtJ_ref) > 0
     assert rel_l2(JtJ, JtJ_ref) < TOL
     assert rel_l2(Jtr, Jtr_ref) < TOL
+    # the library's own system
+    corr_t, rot, trans, valid = _dev_inputs(cuda_device, prob, prob["corr"][:0])
+    sv = CUDASolverBundling(N, 1000 * N, cuda_device)
+    sv.solve(corr_t, 0, valid, N, 1, 0, [0.0], [1.0], [0.1], d_rotationAnglesUnknowns=rot, d_translationUnknowns=trans, cudaCache=cache)
+    d_JtJ = torch.zeros(36 * N * N, device=cuda_device); d_Jtr = torch.zeros(6 * N, device=cuda_device)
+    capi.check(sv.lib.bfSolverDebugDenseSystem(C.byref(sv.m_solverState), N, C.c_void_p(d_JtJ.data_ptr()), C.c_void_p(d_Jtr.data_ptr())), "bfSolverDebugDenseSystem")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(np.c_[rot.cpu().numpy(), trans.cpu().numpy()], np.c_[prob["init_rot"], prob["init_trans"]])
+    JtJ_our, Jtr_our = d_JtJ.cpu().numpy().reshape(6 * N, 6 * N), d_Jtr.cpu().numpy()
+    # rows / columns of the fixed variable 0 are never read by either PCG; compare the part that is (and all of J^T r)
+    assert rel_l2(JtJ_our[6:, 6:], JtJ_ref[6:, 6:]) < TOL, "library's dense J^T J vs the reference's"
+    assert rel_l2(Jtr_our[6:], Jtr_ref[6:]) < TOL, "library's dense J^T r vs the reference's"
+    blk = np.abs(JtJ_our[6:, 6:] - JtJ_ref[6:, 6:]).max() / np.abs(JtJ_ref[6:, 6:]).max()
+    assert blk < 1e-4
 
 
 def test_max_residual_and_pose_stubs_match_reference_cuda(cuda_device):
