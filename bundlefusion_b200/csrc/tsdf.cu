@@ -26,6 +26,7 @@
 
 #include "../../include/bf_tsdf.h"
 #include "bf_common.cuh"
+#include "tsdf_shared.cuh"
 
 namespace bf {
 
@@ -66,12 +67,6 @@ struct TsdfAux {
     const void* owner[3] = { nullptr, nullptr, nullptr };   // the caller's d_SDFBlocks / d_heap / d_hashCompactified: the key (d_hash) can be
                                                             // recycled by an allocator for another table; all four together identify one
 };
-enum { CTR_HIGH_WATER = 0, CTR_E = 3, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROPPED = 10, CTR_U_TOT_LO = 12, CTR_U_TOT_HI = 13, CTR_E_TOT_LO = 14, CTR_E_TOT_HI = 15,
-       // two per-list counter sets (the list / work list of op k and of op k+1 are alive at the same time when alloc + compactify of
-       // op k+1 run on the front lane while the stencil of op k runs on the back lane); a set is zeroed by the op that is about to fill it
-       CTR_SET0 = 16, CTR_SET1 = 24, CTR_NUM = 32,
-       SET_COUNT = 0, SET_WORK = 1, SET_CULLED = 2, SET_U_LO = 4, SET_U_HI = 5, SET_WORDS = 8 };
-
 // launch accounting + optional CUDA-event timing of the integrate / de-integrate stencil (bench.py's roofline line)
 unsigned long long g_launchCount = 0;
 static bool g_profile = false;
@@ -1365,6 +1360,13 @@ static int ensure_tiles(TsdfAux* aux, const BFDepthCameraParams* cp) {
 // depths beyond the integration distance) were cheap for the stencil anyway (their probes exit at the depth test).
 // bfTsdfSetBlockCull(1) or BF_TSDF_CULL=1 switches it on; results are identical either way (tests/test_tsdf_gpu.py).
 static int g_lanes = -1;             // two-lane op replay (bfTsdfRunOps), see "two lanes" below
+// Stencil arithmetic: BF_TSDF_ARITH_FAST (default; tsdf_fast.cu: tolerance contract, what the reference's --use_fast_math build is to
+// its IEEE build) or BF_TSDF_ARITH_EXACT (this file's kernels: bit-identical to the reference's IEEE build and to oracle/tsdf_oracle.c).
+static int g_arith = -1;
+static bool arith_fast() {
+    if (g_arith < 0) { const char* e = getenv("BF_TSDF_ARITH"); g_arith = (e && (e[0] == 'e' || e[0] == '0')) ? BF_TSDF_ARITH_EXACT : BF_TSDF_ARITH_FAST; }
+    return g_arith == BF_TSDF_ARITH_FAST;
+}
 static int g_cull = -1;
 static bool cull_enabled() {
     if (g_cull < 0) { const char* e = getenv("BF_TSDF_CULL"); g_cull = (e && e[0] == '1') ? 1 : 0; }
@@ -1474,7 +1476,12 @@ static int do_integrate(BFHashDataStruct* hd, const BFHashParams* hp, const BFDe
     }
     ++g_launchCount;
     const int set = set_of(aux->parity);
-    if (variant == 0) {
+    if (arith_fast() && variant == 0) {
+        const int4* work = useListCount ? aux->work2[aux->parity] : nullptr;
+        rc = launch_integrate_fast(hd, hp, cp, dd->d_depthData, dd->d_colorData, deIntegrate, useListCount, countOverride, aux->ctrs, aux->live, work, set,
+                                   grid_for(upper, fast_stencil_ctas_per_sm()), sb);
+        if (rc) return rc;
+    } else if (variant == 0) {
         const int grid = grid_for(upper, aux->pipeOpen ? stencil_per_sm() : 16);
         const int4* work = useListCount ? aux->work2[aux->parity] : nullptr;        // the stubs' list (countOverride) has no work list
         if (deIntegrate) integrate_kernel<true><<<grid, 128, 0, sb>>>(*hd, *hp, *cp, dd->d_depthData, color, useListCount ? 1 : 0, countOverride, aux->ctrs, aux->live, work, set);
@@ -1541,6 +1548,7 @@ BF_API size_t bfTsdfAuxBytes(const BFHashParams* hp) { return (3 * sizeof(int4) 
 BF_API int bfTsdfReset(BFHashDataStruct* hd, const BFHashParams* hp) { return do_reset(hd, hp); }
 
 BF_API int bfTsdfSetLanes(int enable) { const int prev = g_lanes; g_lanes = enable ? 1 : 0; return prev < 0 ? 1 : prev; }
+BF_API int bfTsdfSetArithmetic(int mode) { const int prev = arith_fast() ? BF_TSDF_ARITH_FAST : BF_TSDF_ARITH_EXACT; g_arith = (mode == BF_TSDF_ARITH_EXACT) ? BF_TSDF_ARITH_EXACT : BF_TSDF_ARITH_FAST; return prev; }
 BF_API int bfTsdfSetBlockCull(int enable) { const int prev = cull_enabled() ? 1 : 0; g_cull = enable ? 1 : 0; return prev; }
 
 BF_API int bfTsdfIntegrateFrame(BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraData* dd,
@@ -1584,8 +1592,14 @@ BF_API int bfTsdfReintegrateFrame(BFHashDataStruct* hd, const BFHashParams* hpOl
         BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], sb));
     }
     ++g_launchCount;
-    reintegrate_kernel<<<grid_for(hpNew->m_numSDFBlocks, aux->pipeOpen ? stencil_per_sm() : 16), 128, 0, sb>>>(
-        *hd, *hpOld, *hpNew, *cp, dd->d_depthData, reinterpret_cast<const uchar4*>(dd->d_colorData), aux->work2[aux->parity], set, aux->ctrs, aux->live);
+    if (arith_fast()) {
+        rc = launch_reintegrate_fast(hd, hpOld, hpNew, cp, dd->d_depthData, dd->d_colorData, aux->work2[aux->parity], set, aux->ctrs, aux->live,
+                                     grid_for(hpNew->m_numSDFBlocks, fast_stencil_ctas_per_sm()), sb);
+        if (rc) return rc;
+    } else {
+        reintegrate_kernel<<<grid_for(hpNew->m_numSDFBlocks, aux->pipeOpen ? stencil_per_sm() : 16), 128, 0, sb>>>(
+            *hd, *hpOld, *hpNew, *cp, dd->d_depthData, reinterpret_cast<const uchar4*>(dd->d_colorData), aux->work2[aux->parity], set, aux->ctrs, aux->live);
+    }
     BF_CHECK(cudaGetLastError());
     if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], sb)); ++g_evUsed; }
     return stencil_end(aux);

@@ -40,7 +40,11 @@ struct FastArgs {
 #define BF_FAST_MINBLOCKS 10
 #endif
 
+#ifdef BF_EMU_SEQUENTIAL      // tests/test_tsdf_fast_emulated.py: this source executed on the CPU, one CUDA thread after the other
+__device__ __forceinline__ float rcp_approx(float x) { return 1.0f / x; }
+#else
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
 // byte k of w as a float, exactly: bits 0x4B0000bb = 2^23 + b
 template <int K> __device__ __forceinline__ float byte_to_float(unsigned w) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | K)) - 8388608.0f;
@@ -203,13 +207,21 @@ stencil_fast_kernel(const __grid_constant__ FastArgs a) {
             passed += __popc(maskA) + __popc(maskB);
         }
         // live-voxel bookkeeping for the O(E) garbage collection: one RED per warp, only when a weight crossed zero
+#ifdef BF_EMU_SEQUENTIAL
+        if (liveDelta != 0) atomicAdd(&a.live[ptr / BF_SDF_BLOCK_VOXELS], liveDelta);
+#else
         if (__any_sync(0xffffffffu, liveDelta != 0)) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) liveDelta += __shfl_xor_sync(0xffffffffu, liveDelta, o);
             if ((t & 31) == 0 && liveDelta != 0) atomicAdd(&a.live[ptr / BF_SDF_BLOCK_VOXELS], liveDelta);
         }
+#endif
     }
     // U statistics (voxel updates, the roofline's byte count): one 64-bit atomic per CTA
+#ifdef BF_EMU_SEQUENTIAL
+    if (passed) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[a.set + SET_U_LO]), (unsigned long long)passed); atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed); }
+    return;
+#endif
     passed = warp_sum_u(passed);
     __shared__ unsigned sPassed[4];
     if ((t & 31) == 0) sPassed[t >> 5] = passed;

@@ -88,8 +88,13 @@ class CUDASceneRepHashSDF:
     ``HashDataStruct::allocate`` does (VoxelUtilHashSDF.h:124-149) and handed to the library as
     raw device pointers."""
 
-    def __init__(self, params: BFHashParams, device="cuda:0"):
+    def __init__(self, params: BFHashParams, device="cuda:0", arithmetic: str = "fast"):
+        """arithmetic: "fast" (the library default: tolerance contract of bfTsdfSetArithmetic) or "exact" (bit-identical to the
+        reference's IEEE build and to the oracle).  The library setting is process-wide; this object re-asserts its own before every call."""
         import torch
+        if arithmetic not in ("fast", "exact"):
+            raise ValueError("arithmetic must be 'fast' or 'exact'")
+        self.arithmetic = arithmetic
         self._torch = torch
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -131,6 +136,7 @@ class CUDASceneRepHashSDF:
         torch = self._torch
         torch.cuda.set_device(self.device)
         self.lib.bfSetStream(C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        self.lib.bfTsdfSetArithmetic(1 if self.arithmetic == "fast" else 0)
 
     @staticmethod
     def _camera_data(depth, color) -> BFDepthCameraData:

@@ -197,6 +197,16 @@ size_t bfTsdfAuxBytes(const BFHashParams* hashParams);
 /* FL/DepthSensing/CUDASceneRepHashSDF.h:147-155 (reset) */
 int bfTsdfReset(BFHashDataStruct* hashData, const BFHashParams* hashParams);
 
+/* Arithmetic of the integrate / de-integrate / re-integration stencil (process-wide; returns the previous setting).
+ *   BF_TSDF_ARITH_FAST  (default, also BF_TSDF_ARITH=fast): tolerance contract -- allocated block set and weights identical, |d sdf| <= 1e-5 m,
+ *     colour +-1, except for a <= 1e-4 fraction of voxels on a pixel / truncation decision boundary; this is what the reference's shipped
+ *     --use_fast_math build is to its IEEE build (FriedLiver.vcxproj; FL/DepthSensing/CUDASceneRepHashSDF.cu:420-521).
+ *   BF_TSDF_ARITH_EXACT (BF_TSDF_ARITH=exact): every sdf / weight / colour word bit-identical to the reference's IEEE build and to
+ *     oracle/tsdf_oracle.c (~3x the instructions per voxel probe: two IEEE divides, individually rounded operations). */
+#define BF_TSDF_ARITH_EXACT 0
+#define BF_TSDF_ARITH_FAST 1
+int bfTsdfSetArithmetic(int mode);
+
 /* Per-block depth-range cull of the stencil (default off, see tsdf.cu; results are identical either way -- the cull only skips blocks none
  * of whose voxels can pass the reference's truncation test, .cu:433-449).  Returns the previous setting. */
 int bfTsdfSetBlockCull(int enable);

@@ -1,0 +1,191 @@
+"""The tolerance-arithmetic TSDF stencil (bundlefusion_b200/csrc/tsdf_fast.cu) executed on the CPU -- the very same source, compiled by g++
+against the shim of tests/cuda_emu with one CUDA thread run after the other (BF_EMU_SEQUENTIAL replaces the two warp reductions by plain
+atomics and the approximate reciprocal by a division) -- on the oracle's own host-side voxel hash, against the oracle's stencil.  Checks the
+kernel's LOGIC without a GPU: affine voxel -> camera chain, pixel / truncation decisions, word layout of the 4-voxel quads, integer colour
+blend, de-integration rounding, the fused old-pose / new-pose pass, live-voxel and U counters.  TEST INFRASTRUCTURE around a product source;
+the GPU statement is tests/test_tsdf_fast_gpu.py."""
+import ctypes as C
+import os
+import re
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from bundlefusion_b200 import _capi as capi
+from bundlefusion_b200 import synth
+from bundlefusion_b200.scene_rep import camera_params, default_hash_params, set_pose
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+F = np.float32
+
+_PRE = r'''
+#include "%(emu)s"
+struct uint4 { unsigned x, y, z, w; }; struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { return { x, y, z, w }; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const unsigned long long v = ((unsigned long long)y << 32) | x; unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline int __float2int_rz(float f) {                 // cvt.rzi.s32.f32: NaN -> 0, saturating
+    if (f != f) return 0; if (f >= 2147483648.0f) return 2147483647; if (f <= -2147483648.0f) return (int)0x80000000; return (int)f;
+}
+static inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+static inline unsigned warp_sum_u(unsigned v) { return v; }
+#define BF_CHECK(e) do { int _e = (int)(e); if (_e) return _e; } while (0)
+#define BF_EMU_SEQUENTIAL 1
+template <class K, class A> static void seq_launch(K kernel, unsigned grid, unsigned block, const A& a) {
+    emu::g_bar.n = 1; gridDim = dim3(grid); blockDim = dim3(block);
+    for (unsigned b = 0; b < grid; ++b) for (unsigned t = 0; t < block; ++t) { blockIdx = { b, 0, 0 }; threadIdx = { t, 0, 0 }; kernel(a); }
+}
+'''
+_POST = r'''
+extern "C" int emu_integrate_fast(const BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraParams* cp, const float* depth, const void* color,
+                                  int deIntegrate, unsigned count, unsigned* ctrs, int* live, int grid) {
+    return bf::launch_integrate_fast(hd, hp, cp, depth, color, deIntegrate != 0, false, count, ctrs, live, nullptr, bf::CTR_SET0, grid, nullptr);
+}
+extern "C" int emu_reintegrate_fast(const BFHashDataStruct* hd, const BFHashParams* hpOld, const BFHashParams* hpNew, const BFDepthCameraParams* cp, const float* depth,
+                                    const void* color, const void* work, unsigned* ctrs, int* live, int grid) {
+    return bf::launch_reintegrate_fast(hd, hpOld, hpNew, cp, depth, color, (const int4*)work, bf::CTR_SET0, ctrs, live, grid, nullptr);
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = open(os.path.join(ROOT, "bundlefusion_b200", "csrc", "tsdf_fast.cu")).read()
+    src = src.replace('#include "bf_common.cuh"', "")
+    src, n = re.subn(r"(\w+<\d>)<<<\s*([^,]+),\s*([^,]+),\s*[^,]+,\s*[^>]+>>>\((\w+)\)", r"seq_launch(\1, \2, \3, \4)", src)
+    assert n == 3, n
+    d = tempfile.mkdtemp(prefix="bf_fast_emu_")
+    cpp = os.path.join(d, "tsdf_fast_emu.cpp")
+    open(cpp, "w").write(_PRE % {"emu": os.path.join(ROOT, "tests", "cuda_emu", "cuda_emu.h")} + src + _POST)
+    so = os.path.join(d, "libtsdf_fast_emu.so")
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "tests", "cuda_emu"),
+                        "-I", os.path.join(ROOT, "bundlefusion_b200", "csrc"), cpp, "-o", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    L = C.CDLL(so)
+    shutil.rmtree(d, ignore_errors=True)
+    vp = C.c_void_p
+    L.emu_integrate_fast.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_uint, vp, vp, C.c_int]
+    L.emu_reintegrate_fast.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+    return L
+
+
+def _compare(a, b, sdf_tol):
+    """the tolerance contract of tests/test_tsdf_vs_reference_gpu.compare_states, on two oracle-format snapshots"""
+    ab, av = orc.canonical_blocks(a); bb, bv = orc.canonical_blocks(b)
+    np.testing.assert_array_equal(ab, bb)
+    aw, bw = av[..., 1].view(F), bv[..., 1].view(F)
+    n = aw.size
+    assert np.count_nonzero(aw != bw) <= max(2, 2e-5 * n)
+    same = (aw == bw) & (bw > 0)
+    dsdf = np.abs(av[..., 0].view(F)[same] - bv[..., 0].view(F)[same])
+    flips = np.count_nonzero(dsdf > sdf_tol)
+    assert flips <= max(3, 1e-4 * dsdf.size), (flips, dsdf.size, float(dsdf.max()))
+    ac = av[..., 2].copy().view(np.uint8).reshape(av.shape[:-1] + (4,))[same].astype(np.int32)
+    bc = bv[..., 2].copy().view(np.uint8).reshape(bv.shape[:-1] + (4,))[same].astype(np.int32)
+    dc = np.abs(ac - bc).max(axis=-1)
+    assert np.count_nonzero(dc > 1) <= max(3, 1e-4 * dsdf.size) + flips
+    return {"touched": int(dsdf.size), "weight_mismatch": int(np.count_nonzero(aw != bw)), "flips": int(flips), "max_dsdf_nonflip": float(dsdf[dsdf <= sdf_tol].max(initial=0)),
+            "colour_differs": int(np.count_nonzero(dc > 0))}
+
+
+class _FastOnOracle:
+    """oracle hash (alloc, compactify, GC on the host) with the emulated fast stencil doing the voxel updates"""
+
+    def __init__(self, L, hp):
+        self.L, self.o = L, orc.OracleSceneRepHashSDF(hp)
+        self.ctrs = np.zeros(64, np.uint32)
+        self.live = np.zeros(hp.m_numSDFBlocks, np.int32)
+
+    def _stencil(self, T, depth, color, cam, de):
+        o = self.o
+        o._set_pose(T)
+        depth = np.ascontiguousarray(depth, F)
+        if not de:
+            o.L.orc_tsdf_alloc(C.byref(o.hd), C.byref(o.hp), depth, C.byref(cam))
+        o.num_occupied = o.L.orc_tsdf_compactify(C.byref(o.hd), C.byref(o.hp), C.byref(cam))
+        self.ctrs[16:24] = 0
+        rc = self.L.emu_integrate_fast(C.byref(o.hd), C.byref(o.hp), C.byref(cam), depth.ctypes.data, color.ctypes.data, 1 if de else 0, o.num_occupied,
+                                       self.ctrs.ctypes.data, self.live.ctypes.data, 3)
+        assert rc == 0
+        return int(self.ctrs[20]) | (int(self.ctrs[21]) << 32)
+
+    def integrate(self, T, d, c, cam): return self._stencil(T, d, c, cam, False)
+    def deIntegrate(self, T, d, c, cam): return self._stencil(T, d, c, cam, True)
+
+
+def test_fast_stencil_emulated_stream_matches_oracle(emu):
+    W, H = 160, 120
+    cam = camera_params(W, H)
+    hp = default_hash_params(num_buckets=20011, num_sdf_blocks=30000)
+    ref = orc.OracleSceneRepHashSDF(hp)
+    fast = _FastOnOracle(emu, hp)
+    frames = [synth.make_frame(35 * i, W, H) for i in range(4)]
+    for d, c, T in frames:
+        ref.integrate(T, d, c, cam)
+        U = fast.integrate(T, d, np.ascontiguousarray(c), cam)
+        assert abs(U - ref.last_U) <= max(4, 1e-4 * ref.last_U)
+    s1 = _compare(fast.o.download(), ref.download(), 1e-5)
+    # live-voxel counters = voxels with weight > 0 per slot
+    v = fast.o.download()["voxels"]
+    np.testing.assert_array_equal(fast.live, (v[..., 1].view(F) > 0).sum(axis=1).astype(np.int32))
+    for k in (1, 3):
+        d, c, T = frames[k]
+        T2 = T.copy(); T2[:3, 3] += np.array([0.011, -0.006, 0.004], F)
+        ref.deIntegrate(T, d, c, cam); ref.integrate(T2, d, c, cam)
+        fast.deIntegrate(T, d, np.ascontiguousarray(c), cam); fast.integrate(T2, d, np.ascontiguousarray(c), cam)
+    d, c, T = frames[0]
+    ref.deIntegrate(T, d, c, cam); fast.deIntegrate(T, d, np.ascontiguousarray(c), cam)
+    s2 = _compare(fast.o.download(), ref.download(), 1e-4)
+    v = fast.o.download()["voxels"]
+    np.testing.assert_array_equal(fast.live, (v[..., 1].view(F) > 0).sum(axis=1).astype(np.int32))
+    ref.garbageCollect(); fast.o.garbageCollect()
+    assert fast.o.getHeapFreeCount() == ref.getHeapFreeCount()
+    print(s1, s2)
+
+
+def test_fast_fused_reintegration_emulated_equals_its_two_passes(emu):
+    """MODE 2 (old pose de-integrated, new pose integrated, one read-modify-write) must equal MODE 1 followed by MODE 0 of the same source
+    word for word: same probes, same update order per voxel."""
+    W, H = 160, 120
+    cam = camera_params(W, H)
+    hp = default_hash_params(num_buckets=20011, num_sdf_blocks=30000)
+    two, one = _FastOnOracle(emu, hp), _FastOnOracle(emu, hp)
+    frames = [synth.make_frame(35 * i, W, H) for i in range(3)]
+    for d, c, T in frames:
+        two.integrate(T, d, np.ascontiguousarray(c), cam); one.integrate(T, d, np.ascontiguousarray(c), cam)
+    d, c, T = frames[1]
+    c = np.ascontiguousarray(c)
+    T2 = (synth.se3_exp(np.array([0.004, -0.003, 0.002]), np.array([0.012, -0.007, 0.005])) @ T.astype(np.float64)).astype(F)
+    two.deIntegrate(T, d, c, cam); U2 = two.integrate(T2, d, c, cam)
+    # fused: alloc at the new pose, then a union work list {block, slot | flags} (bit 0: in the old pose's frustum list, bit 1: in the new one's)
+    o = one.o
+    hpOld = capi.BFHashParams(); C.memmove(C.byref(hpOld), C.byref(o.hp), C.sizeof(capi.BFHashParams)); set_pose(hpOld, T)
+    o._set_pose(T2)
+    depth = np.ascontiguousarray(d, F)
+    o.L.orc_tsdf_alloc(C.byref(o.hd), C.byref(o.hp), depth, C.byref(cam))
+    nOld = o.L.orc_tsdf_compactify(C.byref(o.hd), C.byref(hpOld), C.byref(cam)); inOld = {int(p) for p in o.compactified.reshape(-1, 8)[:nOld, 3]}
+    nNew = o.L.orc_tsdf_compactify(C.byref(o.hd), C.byref(o.hp), C.byref(cam)); inNew = {int(p) for p in o.compactified.reshape(-1, 8)[:nNew, 3]}
+    h = o.hash
+    used = np.array([i for i in np.nonzero(h[:, 3] != -2)[0] if int(h[i, 3]) in inOld or int(h[i, 3]) in inNew])
+    work = np.zeros((len(used), 4), np.int32)
+    work[:, :3] = h[used, :3]
+    work[:, 3] = [(int(h[i, 3]) // 512) | ((1 if int(h[i, 3]) in inOld else 0) << 28) | ((2 if int(h[i, 3]) in inNew else 0) << 28) for i in used]
+    one.ctrs[16:24] = 0; one.ctrs[16] = len(used); one.ctrs[17] = len(used)
+    rc = emu.emu_reintegrate_fast(C.byref(o.hd), C.byref(hpOld), C.byref(o.hp), C.byref(cam), depth.ctypes.data, c.ctypes.data, work.ctypes.data,
+                                  one.ctrs.ctypes.data, one.live.ctypes.data, 5)
+    assert rc == 0
+    ab, av = orc.canonical_blocks(one.o.download()); bb, bv = orc.canonical_blocks(two.o.download())
+    np.testing.assert_array_equal(ab, bb)
+    np.testing.assert_array_equal(av, bv)
+    np.testing.assert_array_equal(one.live, two.live)

@@ -54,7 +54,7 @@ def test_single_frame_parity(cuda_device):
     W, H = 160, 120
     cam, hp = camera_params(W, H), small_params()
     depth, color, T = synth.make_frame(3, W, H)
-    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device), orc.OracleSceneRepHashSDF(hp)
+    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact"), orc.OracleSceneRepHashSDF(hp)
     d, c = to_dev(torch, cuda_device, depth, color)
     gpu.integrate(T, d, c, cam)
     cpu.integrate(T, depth, color, cam)
@@ -69,7 +69,7 @@ def test_sequence_reintegration_gc_parity(cuda_device):
     import torch
     W, H = 160, 120
     cam, hp = camera_params(W, H), small_params()
-    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device), orc.OracleSceneRepHashSDF(hp)
+    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact"), orc.OracleSceneRepHashSDF(hp)
     frames = [synth.make_frame(40 * i, W, H) for i in range(5)]
     dev = [to_dev(torch, cuda_device, f[0], f[1]) for f in frames]
     for (depth, color, T), (d, c) in zip(frames, dev):
@@ -102,7 +102,7 @@ def test_full_resolution_frame_parity(cuda_device):
     import torch
     W, H = 640, 480
     cam, hp = camera_params(W, H), default_hash_params()
-    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device), orc.OracleSceneRepHashSDF(hp)
+    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact"), orc.OracleSceneRepHashSDF(hp)
     for idx in (0, 25):
         depth, color, T = synth.make_frame(idx, W, H)
         d, c = to_dev(torch, cuda_device, depth, color)
@@ -118,7 +118,7 @@ def test_roundtrip_and_idempotence_properties(cuda_device):
     import torch
     W, H = 640, 480
     cam, hp = camera_params(W, H), default_hash_params()
-    gpu = CUDASceneRepHashSDF(hp, cuda_device)
+    gpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact")
     depth, color, T = synth.make_frame(100, W, H)
     d, c = to_dev(torch, cuda_device, depth, color)
     free0 = gpu.getHeapFreeCount()
@@ -153,7 +153,7 @@ def test_overflow_chains_parity(cuda_device):
     T[:3, :3] = np.array([[-1, 0, 0], [0, 1, 0], [0, 0, -1]], F)
     T[:3, 3] = [-0.33, -0.21, -0.17]
     depth, color, _ = synth.make_frame(7, W, H)
-    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device), orc.OracleSceneRepHashSDF(hp)
+    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact"), orc.OracleSceneRepHashSDF(hp)
     d, c = to_dev(torch, cuda_device, depth, color)
     gpu.integrate(T, d, c, cam)
     cpu.integrate(T, depth, color, cam)
@@ -179,7 +179,7 @@ def test_reference_named_stubs_sequence(cuda_device):
     W, H = 160, 120
     cam, hp = camera_params(W, H), small_params()
     depth, color, T = synth.make_frame(9, W, H)
-    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device), orc.OracleSceneRepHashSDF(hp)
+    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact"), orc.OracleSceneRepHashSDF(hp)
     d, c = to_dev(torch, cuda_device, depth, color)
     L, hd, p = gpu.lib, gpu.m_hashData, gpu.m_hashParams
     L.bfSetStream(None)
@@ -224,7 +224,7 @@ def test_depth_only_frame_is_a_noop(cuda_device):
     W, H = 80, 60
     cam, hp = camera_params(W, H), small_params()
     depth, _ = synth.plane_frame(W, H, 1.0)
-    gpu = CUDASceneRepHashSDF(hp, cuda_device)
+    gpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact")
     gpu.integrate(np.eye(4, dtype=F), torch.from_numpy(depth).to(cuda_device), None, cam)
     snap = gpu.download()
     assert not snap["voxels"].any()
@@ -238,7 +238,7 @@ def test_overfull_table_keeps_invariants(cuda_device):
     W, H = 160, 120
     cam = camera_params(W, H)
     hp = small_params(num_buckets=509, num_sdf_blocks=1500)
-    gpu = CUDASceneRepHashSDF(hp, cuda_device)
+    gpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact")
     for idx in (7, 300, 600):
         depth, color, T = synth.make_frame(idx, W, H)
         d, c = to_dev(torch, cuda_device, depth, color)
@@ -254,7 +254,7 @@ def test_fused_reintegration_matches_two_pass_oracle(cuda_device):
     import torch
     W, H = 160, 120
     cam, hp = camera_params(W, H), small_params()
-    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device), orc.OracleSceneRepHashSDF(hp)
+    gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact"), orc.OracleSceneRepHashSDF(hp)
     frames = [synth.make_frame(35 * i, W, H) for i in range(6)]
     dl = [torch.from_numpy(f[0]).to(cuda_device) for f in frames]
     cl = [torch.from_numpy(f[1]).to(cuda_device) for f in frames]
@@ -301,7 +301,7 @@ def test_block_cull_is_conservative(cuda_device):
     for cull in (1, 0):
         prev = lib.bfTsdfSetBlockCull(cull)
         try:
-            gpu = CUDASceneRepHashSDF(hp, cuda_device)
+            gpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact")
             culled = 0
             for k, (d, c, T) in enumerate(frames):
                 dd, dc = to_dev(torch, cuda_device, d, c)
@@ -358,7 +358,7 @@ def test_spatial_shard_matches_oracle_and_unsharded(cuda_device):
     got_b, got_v = [], []
     for rank in range(2):
         hp = small_params(); hp.m_dummy = (2 << 32) | rank
-        gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device), orc.OracleSceneRepHashSDF(hp)
+        gpu, cpu = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact"), orc.OracleSceneRepHashSDF(hp)
         for d, c, T in frames:
             dd, dc = to_dev(torch, cuda_device, d, c)
             gpu.integrate(T, dd, dc, cam); cpu.integrate(T, d, c, cam)

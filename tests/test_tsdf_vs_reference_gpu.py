@@ -53,7 +53,7 @@ def test_stream_with_reintegration_matches_reference_cuda(cuda_device, fast_math
     W, H = 320, 240
     cam = camera_params(W, H)
     hp = default_hash_params(num_buckets=100003, num_sdf_blocks=60000)
-    ours = CUDASceneRepHashSDF(hp, cuda_device)
+    ours = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="exact")
     ref = ref_tsdf.ReferenceSceneRepHashSDF(hp, cuda_device, fast_math=fast_math)
     frames = [synth.make_frame(30 * i, W, H) for i in range(6)]
     dev = [(torch.from_numpy(f[0]).to(cuda_device), torch.from_numpy(f[1]).to(cuda_device)) for f in frames]
