@@ -50,6 +50,7 @@ struct SdCommon {
     int rowBase[SD_NLEV + 1];                   // prefix of image rows over the 12 levels
     BFSiftDetectParams P;
     float sigma0, dogThreshold, edgeT;
+    float levelSigma[SD_DOG];          // sigma0 * 2^(j / SD_DOG), host-evaluated
     int* rowCount; int* rowOffset;              // [rowBase[12]]
     int* levelRaw;                              // [12] key points per level after detection (min(count, fmax))
     int2* raw;                                  // [capBase[12]] (col, row)
@@ -243,7 +244,7 @@ sift_orient_kernel(const __grid_constant__ SdCommon s) {
     const float2* __restrict__ grad = s.oc[o].grad[j + 1];
     const int2 ik = s.raw[s.capBase[L] + k];
     const float kx = ik.x + 0.5f, ky = ik.y + 0.5f;
-    const float sigma = s.sigma0 * powf(2.0f, (float)j / (float)SD_DOG);
+    const float sigma = s.levelSigma[j];       // GetLevelSigma, evaluated by the host as in the reference (SiftPyramid.h)
     const float tenDegPerRad = 5.7295779513082320876798154814105f;
     const float gsigma = sigma * 1.5f, win = fabsf(sigma) * 1.5f * 2.0f;
     const float distThreshold = (float)(win * win + 0.5);
@@ -306,7 +307,7 @@ sift_reshape_kernel(const __grid_constant__ SdCommon s) {
     __shared__ int sScan[512];
     const int L = blockIdx.x, o = L / SD_DOG, j = L % SD_DOG, t = threadIdx.x, cap = s.fmax[o];
     const int n = limited_count(s.levelRaw, s.P.featureCountThreshold, L);
-    const float sigma = s.sigma0 * powf(2.0f, (float)j / (float)SD_DOG);
+    const float sigma = s.levelSigma[j];       // GetLevelSigma, evaluated by the host as in the reference (SiftPyramid.h)
     const float keyLocScale = (float)(1 << o);
     const float factor = (float)(2.0 * 3.14159265358979323846 / 65535.0);
     const bool scaleOk = sigma * keyLocScale >= s.P.minKeyScale;
@@ -436,6 +437,7 @@ static void sd_parse_param(SdWorkspace& ws) {                                   
     for (int i = 0; i <= 4; ++i) ws.sigmas[i + 1] = dsigma0 * powf(sigmak, (float)i);
     for (int i = 0; i < SD_LEVELS; ++i) { for (int k = 0; k < SD_MAX_FW; ++k) ws.taps[i][k] = 0.0f; sd_filter_kernel(ws.sigmas[i], ws.taps[i], &ws.fw[i]); }
     ws.c.sigma0 = sigma0;
+    for (int j = 0; j < SD_DOG; ++j) ws.c.levelSigma[j] = sigma0 * powf(2.0f, (float)j / (float)SD_DOG);
     ws.c.dogThreshold = 0.02f / SD_DOG;
     const float edge = 10.0f;
     ws.c.edgeT = (edge + 1) * (edge + 1) / edge;

@@ -1479,7 +1479,7 @@ static int do_integrate(BFHashDataStruct* hd, const BFHashParams* hp, const BFDe
     if (arith_fast() && variant == 0) {
         const int4* work = useListCount ? aux->work2[aux->parity] : nullptr;
         rc = launch_integrate_fast(hd, hp, cp, dd->d_depthData, dd->d_colorData, deIntegrate, useListCount, countOverride, aux->ctrs, aux->live, work, set,
-                                   grid_for(upper, fast_stencil_ctas_per_sm()), sb);
+                                   grid_for(upper, fast_stencil_ctas_per_sm(false)), sb);
         if (rc) return rc;
     } else if (variant == 0) {
         const int grid = grid_for(upper, aux->pipeOpen ? stencil_per_sm() : 16);
@@ -1594,7 +1594,7 @@ BF_API int bfTsdfReintegrateFrame(BFHashDataStruct* hd, const BFHashParams* hpOl
     ++g_launchCount;
     if (arith_fast()) {
         rc = launch_reintegrate_fast(hd, hpOld, hpNew, cp, dd->d_depthData, dd->d_colorData, aux->work2[aux->parity], set, aux->ctrs, aux->live,
-                                     grid_for(hpNew->m_numSDFBlocks, fast_stencil_ctas_per_sm()), sb);
+                                     grid_for(hpNew->m_numSDFBlocks, fast_stencil_ctas_per_sm(true)), sb);
         if (rc) return rc;
     } else {
         reintegrate_kernel<<<grid_for(hpNew->m_numSDFBlocks, aux->pipeOpen ? stencil_per_sm() : 16), 128, 0, sb>>>(

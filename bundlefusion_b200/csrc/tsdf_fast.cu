@@ -36,8 +36,12 @@ struct FastArgs {
     FastPose A, B;                   // MODE 0 / 1: A.  MODE 2: A = old pose (de-integrated), B = new pose (integrated)
 };
 
+// resident CTAs per SM the kernels are compiled for: the fused pass keeps two poses' probe sets live (<= 64 registers), the others 48
 #ifndef BF_FAST_MINBLOCKS
 #define BF_FAST_MINBLOCKS 10
+#endif
+#ifndef BF_FAST_MINBLOCKS_FUSED
+#define BF_FAST_MINBLOCKS_FUSED 8
 #endif
 
 #ifdef BF_EMU_SEQUENTIAL      // tests/test_tsdf_fast_emulated.py: this source executed on the CPU, one CUDA thread after the other
@@ -53,183 +57,224 @@ template <int K> __device__ __forceinline__ unsigned put_byte(unsigned acc, unsi
     return __byte_perm(acc, v, K == 0 ? 0x3214u : (K == 1 ? 0x3240u : 0x3410u));
 }
 
-struct Probe { float sdf; unsigned col; };
-
-// truncation test of one voxel at camera-space (X, Y, Z); .cu:433-463 without the (identity) clamp
-__device__ __forceinline__ bool probe_fast(const FastArgs& a, const FastPose& p, float X, float Y, float Z, Probe& out) {
-    const float rz = rcp_approx(Z);
-    const float sx = fmaf(X * rz, a.fx, a.mx5), sy = fmaf(Y * rz, a.fy, a.my5);
-    const unsigned ix = (unsigned)__float2int_rz(sx), iy = (unsigned)__float2int_rz(sy);       // cvt.rzi: (-1, 0) -> 0, NaN -> 0, as the reference's (int)
-    if (ix >= a.W || iy >= a.H) return false;
-    const unsigned idx = iy * a.W + ix;
-    const float d = __ldg(&a.depth[idx]);
-    if (!(d != -INFINITY && d < p.maxDist)) return false;
-    const float sdf = d - Z;
-    if (!(fabsf(sdf) < fmaf(p.truncScale, d, p.trunc0))) return false;
-    out.sdf = sdf;
-    out.col = __ldg(reinterpret_cast<const unsigned*>(a.color) + idx);
-    return true;
+// ---- probe phase, branch-free: projections and the depth gathers of all four voxels of a thread are independent of each other, so
+// the compiler can issue the loads back to back (memory-level parallelism) and interleave the arithmetic of the four chains ----
+struct ProbeSet {
+    float sdf[4];          // after decide(): depth - z of the voxels that pass
+    unsigned idx[4];       // pixel index, or 0xFFFFFFFF when the voxel projects outside the image
+    unsigned mask;         // bit k: voxel k passes the truncation test
+};
+__device__ __forceinline__ void project4(const FastArgs& a, const FastPose& p, float X, float Y, float Z, ProbeSet& ps, float (&z)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float Xk = fmaf((float)k, p.cx[0], X), Yk = fmaf((float)k, p.cy[0], Y), Zk = fmaf((float)k, p.cz[0], Z);
+        const float rz = rcp_approx(Zk);
+        const float sx = fmaf(Xk * rz, a.fx, a.mx5), sy = fmaf(Yk * rz, a.fy, a.my5);
+        const unsigned ix = (unsigned)__float2int_rz(sx), iy = (unsigned)__float2int_rz(sy);   // cvt.rzi: (-1, 0) -> 0, NaN -> 0, as the reference's (int)
+        const bool on = (ix < a.W) & (iy < a.H);
+        ps.idx[k] = on ? iy * a.W + ix : 0xFFFFFFFFu;
+        z[k] = Zk;
+        ps.sdf[k] = __ldg(&a.depth[on ? iy * a.W + ix : 0u]);            // unconditional load from a safe address; holds the DEPTH until decide()
+    }
+}
+// truncation test (.cu:433-463 without the identity clamp): depth valid, below the integration distance, |depth - z| < truncation(depth)
+__device__ __forceinline__ void decide4(const FastPose& p, ProbeSet& ps, const float (&z)[4]) {
+    ps.mask = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float d = ps.sdf[k];
+        const float sdf = d - z[k];
+        const bool pass = (ps.idx[k] != 0xFFFFFFFFu) & (d != -INFINITY) & (d < p.maxDist) & (fabsf(sdf) < fmaf(p.truncScale, d, p.trunc0));
+        ps.sdf[k] = sdf;
+        ps.mask |= pass ? (1u << k) : 0u;
+    }
 }
 
 // integrate one sample into (sdf, weight, colour) words; .cu:486-500
-__device__ __forceinline__ void integrate_fast(const FastPose& p, const Probe& s, unsigned& wSdf, unsigned& wWeight, unsigned& wColor) {
+__device__ __forceinline__ void integrate_fast(const FastPose& p, float sdf, unsigned col, unsigned& wSdf, unsigned& wWeight, unsigned& wColor) {
     const float oldSdf = __uint_as_float(wSdf), oldW = __uint_as_float(wWeight);
     const float den = oldW + 1.0f;
-    const float nSdf = fmaf(oldSdf, oldW, s.sdf) * rcp_approx(den);
+    const float nSdf = fmaf(oldSdf, oldW, sdf) * rcp_approx(den);
     unsigned nc = 0xFF000000u;
-    if (oldW == 0.0f) {
-        // colour = the sample, through clamp [0, 254.5] and the byte conversion: 255 -> 254
-        const unsigned c0 = s.col & 0xffu, c1 = (s.col >> 8) & 0xffu, c2 = (s.col >> 16) & 0xffu;
-        nc = put_byte<0>(nc, min(c0, 254u)); nc = put_byte<1>(nc, min(c1, 254u)); nc = put_byte<2>(nc, min(c2, 254u));
-    } else {
-        // round(0.2 c + 0.8 o) = floor((2 c + 8 o + 5) / 10): the fraction of (c + 4 o) / 5 is a multiple of 0.2, never a tie
+    // oldW == 0: colour = the sample (through clamp [0, 254.5] and the byte conversion: 255 -> 254); else
+    // round(0.2 c + 0.8 o) = floor((2 c + 8 o + 5) / 10): the fraction of (c + 4 o) / 5 is a multiple of 0.2, never a tie
+    const bool first = (oldW == 0.0f);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const unsigned c = (s.col >> (8 * k)) & 0xffu, o = (wColor >> (8 * k)) & 0xffu;
-            const unsigned q = __umulhi(8u * o + 2u * c + 5u, 429496730u);
-            const unsigned v = min(q, 254u);
-            nc = (k == 0) ? put_byte<0>(nc, v) : (k == 1 ? put_byte<1>(nc, v) : put_byte<2>(nc, v));
-        }
+    for (int k = 0; k < 3; ++k) {
+        const unsigned c = (col >> (8 * k)) & 0xffu, o = (wColor >> (8 * k)) & 0xffu;
+        const unsigned q = first ? c : __umulhi(8u * o + 2u * c + 5u, 429496730u);
+        const unsigned v = min(q, 254u);
+        nc = (k == 0) ? put_byte<0>(nc, v) : (k == 1 ? put_byte<1>(nc, v) : put_byte<2>(nc, v));
     }
     wSdf = __float_as_uint(nSdf); wWeight = __float_as_uint(fminf(p.wMax, den)); wColor = nc;
 }
 
 // de-integrate one sample; .cu:501-514
-__device__ __forceinline__ void deintegrate_fast(const Probe& s, unsigned& wSdf, unsigned& wWeight, unsigned& wColor) {
+__device__ __forceinline__ void deintegrate_fast(float sdf, unsigned col, unsigned& wSdf, unsigned& wWeight, unsigned& wColor) {
     const float oldSdf = __uint_as_float(wSdf), oldW = __uint_as_float(wWeight);
     const float den = oldW - 1.0f;
     if (!(den > 0.001f)) { wSdf = 0u; wWeight = 0u; wColor = 0u; return; }           // weight max(0, w - 1) <= 0.001: the voxel is cleared
     const float r = rcp_approx(den);
-    const float nSdf = fmaf(oldSdf, oldW, -s.sdf) * r;
+    const float nSdf = fmaf(oldSdf, oldW, -sdf) * r;
     // round((o w - c) / (w - 1)), half away from zero, clamped to [0, 254.5] -> byte.  The quotient is biased up by 2^-20 so that the
     // exact ties (w - 1 = 2, 4, ...) fall on the reference's side under an approximate reciprocal; then round-to-nearest via 2^23.
     const float rb = r * 1.00000095367431640625f;
     unsigned nc = 0xFF000000u;
     {
-        const float q = fminf(fmaxf(fmaf(byte_to_float<0>(wColor), oldW, -byte_to_float<0>(s.col)) * rb, 0.0f), 254.4f);
+        const float q = fminf(fmaxf(fmaf(byte_to_float<0>(wColor), oldW, -byte_to_float<0>(col)) * rb, 0.0f), 254.4f);
         nc = put_byte<0>(nc, __float_as_uint(q + 8388608.0f));
     }
     {
-        const float q = fminf(fmaxf(fmaf(byte_to_float<1>(wColor), oldW, -byte_to_float<1>(s.col)) * rb, 0.0f), 254.4f);
+        const float q = fminf(fmaxf(fmaf(byte_to_float<1>(wColor), oldW, -byte_to_float<1>(col)) * rb, 0.0f), 254.4f);
         nc = put_byte<1>(nc, __float_as_uint(q + 8388608.0f));
     }
     {
-        const float q = fminf(fmaxf(fmaf(byte_to_float<2>(wColor), oldW, -byte_to_float<2>(s.col)) * rb, 0.0f), 254.4f);
+        const float q = fminf(fmaxf(fmaf(byte_to_float<2>(wColor), oldW, -byte_to_float<2>(col)) * rb, 0.0f), 254.4f);
         nc = put_byte<2>(nc, __float_as_uint(q + 8388608.0f));
     }
     wSdf = __float_as_uint(nSdf); wWeight = __float_as_uint(den); wColor = nc;
 }
 
 template <int MODE>
-__device__ __forceinline__ void update_fast(const FastArgs& a, bool passA, const Probe& sA, bool passB, const Probe& sB,
+__device__ __forceinline__ void update_fast(const FastArgs& a, bool passA, float sdfA, unsigned colA, bool passB, float sdfB, unsigned colB,
                                             unsigned& wSdf, unsigned& wWeight, unsigned& wColor, int& liveDelta) {
     const bool wasLive = __uint_as_float(wWeight) > 0.0f;
-    if (MODE == 0) { integrate_fast(a.A, sA, wSdf, wWeight, wColor); }
-    else if (MODE == 1) { deintegrate_fast(sA, wSdf, wWeight, wColor); }
+    if (MODE == 0) { integrate_fast(a.A, sdfA, colA, wSdf, wWeight, wColor); }
+    else if (MODE == 1) { deintegrate_fast(sdfA, colA, wSdf, wWeight, wColor); }
     else {
-        if (passA) deintegrate_fast(sA, wSdf, wWeight, wColor);
-        if (passB) integrate_fast(a.B, sB, wSdf, wWeight, wColor);
+        if (passA) deintegrate_fast(sdfA, colA, wSdf, wWeight, wColor);
+        if (passB) integrate_fast(a.B, sdfB, colB, wSdf, wWeight, wColor);
     }
     liveDelta += (int)(__uint_as_float(wWeight) > 0.0f) - (int)wasLive;
 }
 
-// 128 threads per SDF block, 4 x-consecutive voxels (48 B = three 16-byte vectors) per thread; persistent grid over the work list.
+struct ThreadOffsets { float ax, ay, az, bx, by, bz; };
+
+// one SDF block: 128 threads, 4 x-consecutive voxels (48 B = three 16-byte vectors) per thread
 template <int MODE>
-__global__ void __launch_bounds__(128, BF_FAST_MINBLOCKS)
+__device__ __forceinline__ void process_block(const FastArgs& a, const ThreadOffsets& o, unsigned t, int bx, int by, int bz, unsigned ptr, unsigned fl, unsigned& passed) {
+    const float fbx = (float)(bx * BF_SDF_BLOCK_SIZE), fby = (float)(by * BF_SDF_BLOCK_SIZE), fbz = (float)(bz * BF_SDF_BLOCK_SIZE);
+    ProbeSet pA, pB;
+    float zA[4], zB[4];
+    pA.mask = 0; pB.mask = 0;
+    if (a.color == nullptr) return;                        // without colour nothing passes (.cu:441-448)
+    if (fl & 1u)
+        project4(a, a.A, fmaf(fbx, a.A.cx[0], fmaf(fby, a.A.cx[1], fmaf(fbz, a.A.cx[2], o.ax))), fmaf(fbx, a.A.cy[0], fmaf(fby, a.A.cy[1], fmaf(fbz, a.A.cy[2], o.ay))),
+                 fmaf(fbx, a.A.cz[0], fmaf(fby, a.A.cz[1], fmaf(fbz, a.A.cz[2], o.az))), pA, zA);
+    if (MODE == 2 && (fl & 2u))
+        project4(a, a.B, fmaf(fbx, a.B.cx[0], fmaf(fby, a.B.cx[1], fmaf(fbz, a.B.cx[2], o.bx))), fmaf(fbx, a.B.cy[0], fmaf(fby, a.B.cy[1], fmaf(fbz, a.B.cy[2], o.by))),
+                 fmaf(fbx, a.B.cz[0], fmaf(fby, a.B.cz[1], fmaf(fbz, a.B.cz[2], o.bz))), pB, zB);
+    if (fl & 1u) decide4(a.A, pA, zA);
+    if (MODE == 2 && (fl & 2u)) decide4(a.B, pB, zB);
+    const unsigned mask = pA.mask | pB.mask;
+    int liveDelta = 0;
+    if (mask) {
+        // colour gathers of the passing voxels (safe address otherwise) and the voxel quad: one batch of independent loads
+        const unsigned* colImg = reinterpret_cast<const unsigned*>(a.color);
+        unsigned cA[4], cB[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cA[k] = __ldg(&colImg[(pA.mask >> k) & 1u ? pA.idx[k] : 0u]);
+            if (MODE == 2) cB[k] = __ldg(&colImg[(pB.mask >> k) & 1u ? pB.idx[k] : 0u]);
+        }
+        uint4* const vp = reinterpret_cast<uint4*>(a.blocks + (size_t)ptr) + 3 * t;      // 48 B per thread, 16-B aligned
+        uint4 qa = vp[0], qb = vp[1], qc = vp[2];
+        // 4 voxels = 12 words: v0{a.x,a.y,a.z} v1{a.w,b.x,b.y} v2{b.z,b.w,c.x} v3{c.y,c.z,c.w}
+        if (mask & 1u) update_fast<MODE>(a, pA.mask & 1u, pA.sdf[0], cA[0], pB.mask & 1u, pB.sdf[0], cB[0], qa.x, qa.y, qa.z, liveDelta);
+        if (mask & 2u) update_fast<MODE>(a, pA.mask & 2u, pA.sdf[1], cA[1], pB.mask & 2u, pB.sdf[1], cB[1], qa.w, qb.x, qb.y, liveDelta);
+        if (mask & 4u) update_fast<MODE>(a, pA.mask & 4u, pA.sdf[2], cA[2], pB.mask & 4u, pB.sdf[2], cB[2], qb.z, qb.w, qc.x, liveDelta);
+        if (mask & 8u) update_fast<MODE>(a, pA.mask & 8u, pA.sdf[3], cA[3], pB.mask & 8u, pB.sdf[3], cB[3], qc.y, qc.z, qc.w, liveDelta);
+        if (mask & 0x3u) vp[0] = qa;                      // only the 16-byte pieces that hold an updated voxel
+        if (mask & 0x6u) vp[1] = qb;
+        if (mask & 0xCu) vp[2] = qc;
+        passed += __popc(pA.mask) + __popc(pB.mask);
+    }
+    // live-voxel bookkeeping for the O(E) garbage collection: one RED per warp, only when a weight crossed zero
+#ifdef BF_EMU_SEQUENTIAL
+    if (liveDelta != 0) atomicAdd(&a.live[ptr / BF_SDF_BLOCK_VOXELS], liveDelta);
+#else
+    if (__any_sync(0xffffffffu, liveDelta != 0)) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) liveDelta += __shfl_xor_sync(0xffffffffu, liveDelta, s);
+        if ((t & 31) == 0 && liveDelta != 0) atomicAdd(&a.live[ptr / BF_SDF_BLOCK_VOXELS], liveDelta);
+    }
+#endif
+}
+
+// Persistent grid.  With a work list (the library's own compactify) blocks are dealt out dynamically: a CTA starts on block blockIdx.x and
+// then draws tickets from a per-list counter (zeroed with the list's counter set), two iterations ahead, so that the atomic and the work-item
+// load it feeds are in flight while a block is being processed -- blocks differ 3x in cost (none / all voxels pass), a static deal leaves
+// a quarter of the SM-time idle at the tail.  Without a work list (reference-named stubs: d_hashCompactified, count from the caller) the
+// deal is static.
+template <int MODE, bool DYN>
+__global__ void __launch_bounds__(128, MODE == 2 ? BF_FAST_MINBLOCKS_FUSED : BF_FAST_MINBLOCKS)
 stencil_fast_kernel(const __grid_constant__ FastArgs a) {
     const unsigned listCount = a.useListCount ? a.ctrs[a.set + SET_COUNT] : a.countOverride;
-    const unsigned count = a.work ? a.ctrs[a.set + SET_WORK] : listCount;
+    const unsigned count = DYN ? a.ctrs[a.set + SET_WORK] : listCount;
     const unsigned t = threadIdx.x;
     if (blockIdx.x == 0 && t == 0) {
         if (a.useListCount) { a.listCounterOut[0] = (int)listCount; a.ctrs[CTR_E] = listCount; }
-        if (!a.work) atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_E_TOT_LO]), (unsigned long long)listCount);
+        if (!DYN) atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_E_TOT_LO]), (unsigned long long)listCount);
     }
     // this thread's first voxel inside a block: i = 4t -> x = (4t) % 8, y = (4t % 64) / 8, z = 4t / 64
     const float flx = (float)((4 * t) & 7), fly = (float)(((4 * t) & 63) >> 3), flz = (float)((4 * t) >> 6);
-    const float oAx = fmaf(flx, a.A.cx[0], fmaf(fly, a.A.cx[1], fmaf(flz, a.A.cx[2], a.A.cx[3])));
-    const float oAy = fmaf(flx, a.A.cy[0], fmaf(fly, a.A.cy[1], fmaf(flz, a.A.cy[2], a.A.cy[3])));
-    const float oAz = fmaf(flx, a.A.cz[0], fmaf(fly, a.A.cz[1], fmaf(flz, a.A.cz[2], a.A.cz[3])));
-    float oBx = 0.0f, oBy = 0.0f, oBz = 0.0f;
+    ThreadOffsets o;
+    o.ax = fmaf(flx, a.A.cx[0], fmaf(fly, a.A.cx[1], fmaf(flz, a.A.cx[2], a.A.cx[3])));
+    o.ay = fmaf(flx, a.A.cy[0], fmaf(fly, a.A.cy[1], fmaf(flz, a.A.cy[2], a.A.cy[3])));
+    o.az = fmaf(flx, a.A.cz[0], fmaf(fly, a.A.cz[1], fmaf(flz, a.A.cz[2], a.A.cz[3])));
+    o.bx = o.by = o.bz = 0.0f;
     if (MODE == 2) {
-        oBx = fmaf(flx, a.B.cx[0], fmaf(fly, a.B.cx[1], fmaf(flz, a.B.cx[2], a.B.cx[3])));
-        oBy = fmaf(flx, a.B.cy[0], fmaf(fly, a.B.cy[1], fmaf(flz, a.B.cy[2], a.B.cy[3])));
-        oBz = fmaf(flx, a.B.cz[0], fmaf(fly, a.B.cz[1], fmaf(flz, a.B.cz[2], a.B.cz[3])));
+        o.bx = fmaf(flx, a.B.cx[0], fmaf(fly, a.B.cx[1], fmaf(flz, a.B.cx[2], a.B.cx[3])));
+        o.by = fmaf(flx, a.B.cy[0], fmaf(fly, a.B.cy[1], fmaf(flz, a.B.cy[2], a.B.cy[3])));
+        o.bz = fmaf(flx, a.B.cz[0], fmaf(fly, a.B.cz[1], fmaf(flz, a.B.cz[2], a.B.cz[3])));
     }
     unsigned passed = 0;
-    int4 wNext = make_int4(0, 0, 0, 0);
-    if (a.work && blockIdx.x < count) wNext = __ldg(&a.work[blockIdx.x]);
-
-    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) {
-        int bx, by, bz; unsigned ptr, fl = 3u;
-        if (a.work) {
-            const int4 w = wNext;
-            if (b + gridDim.x < count) wNext = __ldg(&a.work[b + gridDim.x]);
-            bx = w.x; by = w.y; bz = w.z; ptr = ((unsigned)w.w & 0x0FFFFFFFu) * BF_SDF_BLOCK_VOXELS;
-            if (MODE == 2) fl = (unsigned)w.w >> 28;          // bit0: the old pose can touch this block, bit1: the new pose can
-        } else {
-            const BFHashEntry* ep = &a.list[b];
-            bx = __ldg(&ep->pos[0]); by = __ldg(&ep->pos[1]); bz = __ldg(&ep->pos[2]); ptr = (unsigned)__ldg(&ep->ptr);
+    if (DYN) {
+#ifndef BF_EMU_SEQUENTIAL
+        __shared__ int4 sWork[2];
+        const int4 kEnd = make_int4(0, 0, 0, -1);
+        unsigned* const ticket = &a.ctrs[a.set + SET_TICKET];
+        int4 wCur = (blockIdx.x < count) ? __ldg(&a.work[blockIdx.x]) : kEnd;
+        int4 wNext = kEnd; unsigned iAfter = 0xFFFFFFFFu;
+        if (t == 0) {
+            const unsigned i1 = gridDim.x + atomicAdd(ticket, 1u);
+            wNext = (i1 < count) ? __ldg(&a.work[i1]) : kEnd;
+            iAfter = gridDim.x + atomicAdd(ticket, 1u);
         }
-        const float fbx = (float)(bx * BF_SDF_BLOCK_SIZE), fby = (float)(by * BF_SDF_BLOCK_SIZE), fbz = (float)(bz * BF_SDF_BLOCK_SIZE);
-        Probe sA[4], sB[4];
-        unsigned maskA = 0, maskB = 0;
-        if (a.color != nullptr) {                             // without colour nothing passes (.cu:441-448)
-            if (fl & 1u) {
-                const float X = fmaf(fbx, a.A.cx[0], fmaf(fby, a.A.cx[1], fmaf(fbz, a.A.cx[2], oAx)));
-                const float Y = fmaf(fbx, a.A.cy[0], fmaf(fby, a.A.cy[1], fmaf(fbz, a.A.cy[2], oAy)));
-                const float Z = fmaf(fbx, a.A.cz[0], fmaf(fby, a.A.cz[1], fmaf(fbz, a.A.cz[2], oAz)));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (probe_fast(a, a.A, fmaf((float)k, a.A.cx[0], X), fmaf((float)k, a.A.cy[0], Y), fmaf((float)k, a.A.cz[0], Z), sA[k])) maskA |= 1u << k;
+        unsigned parity = 0;
+        while (wCur.w != -1) {
+            process_block<MODE>(a, o, t, wCur.x, wCur.y, wCur.z, ((unsigned)wCur.w & 0x0FFFFFFFu) * BF_SDF_BLOCK_VOXELS, MODE == 2 ? ((unsigned)wCur.w >> 28) : 3u, passed);
+            if (t == 0) {
+                sWork[parity] = wNext;
+                wNext = (iAfter < count) ? __ldg(&a.work[iAfter]) : kEnd;
+                iAfter = (iAfter < count) ? gridDim.x + atomicAdd(ticket, 1u) : 0xFFFFFFFFu;
             }
-            if (MODE == 2 && (fl & 2u)) {
-                const float X = fmaf(fbx, a.B.cx[0], fmaf(fby, a.B.cx[1], fmaf(fbz, a.B.cx[2], oBx)));
-                const float Y = fmaf(fbx, a.B.cy[0], fmaf(fby, a.B.cy[1], fmaf(fbz, a.B.cy[2], oBy)));
-                const float Z = fmaf(fbx, a.B.cz[0], fmaf(fby, a.B.cz[1], fmaf(fbz, a.B.cz[2], oBz)));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (probe_fast(a, a.B, fmaf((float)k, a.B.cx[0], X), fmaf((float)k, a.B.cy[0], Y), fmaf((float)k, a.B.cz[0], Z), sB[k])) maskB |= 1u << k;
-            }
+            __syncthreads();
+            wCur = sWork[parity];
+            parity ^= 1u;
         }
-        const unsigned mask = maskA | maskB;
-        int liveDelta = 0;
-        if (mask) {
-            uint4* const vp = reinterpret_cast<uint4*>(a.blocks + (size_t)ptr) + 3 * t;      // 48 B per thread, 16-B aligned
-            uint4 qa = vp[0], qb = vp[1], qc = vp[2];
-            // 4 voxels = 12 words: v0{a.x,a.y,a.z} v1{a.w,b.x,b.y} v2{b.z,b.w,c.x} v3{c.y,c.z,c.w}
-            if (mask & 1u) update_fast<MODE>(a, maskA & 1u, sA[0], maskB & 1u, sB[0], qa.x, qa.y, qa.z, liveDelta);
-            if (mask & 2u) update_fast<MODE>(a, maskA & 2u, sA[1], maskB & 2u, sB[1], qa.w, qb.x, qb.y, liveDelta);
-            if (mask & 4u) update_fast<MODE>(a, maskA & 4u, sA[2], maskB & 4u, sB[2], qb.z, qb.w, qc.x, liveDelta);
-            if (mask & 8u) update_fast<MODE>(a, maskA & 8u, sA[3], maskB & 8u, sB[3], qc.y, qc.z, qc.w, liveDelta);
-            if (mask & 0x3u) vp[0] = qa;                      // only the 16-byte pieces that hold an updated voxel
-            if (mask & 0x6u) vp[1] = qb;
-            if (mask & 0xCu) vp[2] = qc;
-            passed += __popc(maskA) + __popc(maskB);
-        }
-        // live-voxel bookkeeping for the O(E) garbage collection: one RED per warp, only when a weight crossed zero
-#ifdef BF_EMU_SEQUENTIAL
-        if (liveDelta != 0) atomicAdd(&a.live[ptr / BF_SDF_BLOCK_VOXELS], liveDelta);
 #else
-        if (__any_sync(0xffffffffu, liveDelta != 0)) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) liveDelta += __shfl_xor_sync(0xffffffffu, liveDelta, o);
-            if ((t & 31) == 0 && liveDelta != 0) atomicAdd(&a.live[ptr / BF_SDF_BLOCK_VOXELS], liveDelta);
+        for (unsigned b = blockIdx.x; b < count; b += gridDim.x) {      // sequential emulation: static deal (same set of blocks)
+            const int4 w = a.work[b];
+            process_block<MODE>(a, o, t, w.x, w.y, w.z, ((unsigned)w.w & 0x0FFFFFFFu) * BF_SDF_BLOCK_VOXELS, MODE == 2 ? ((unsigned)w.w >> 28) : 3u, passed);
         }
 #endif
+    } else {
+        for (unsigned b = blockIdx.x; b < count; b += gridDim.x) {
+            const BFHashEntry* ep = &a.list[b];
+            process_block<MODE>(a, o, t, __ldg(&ep->pos[0]), __ldg(&ep->pos[1]), __ldg(&ep->pos[2]), (unsigned)__ldg(&ep->ptr), 3u, passed);
+        }
     }
-    // U statistics (voxel updates, the roofline's byte count): one 64-bit atomic per CTA
+    // U statistics (voxel updates, the roofline's byte count): one 64-bit atomic per warp, no barrier at the end of the kernel
 #ifdef BF_EMU_SEQUENTIAL
     if (passed) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[a.set + SET_U_LO]), (unsigned long long)passed); atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed); }
-    return;
-#endif
+#else
     passed = warp_sum_u(passed);
-    __shared__ unsigned sPassed[4];
-    if ((t & 31) == 0) sPassed[t >> 5] = passed;
-    __syncthreads();
-    if (t == 0) {
-        const unsigned long long tot = (unsigned long long)sPassed[0] + sPassed[1] + sPassed[2] + sPassed[3];
-        if (tot) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[a.set + SET_U_LO]), tot); atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), tot); }
+    if ((t & 31) == 0 && passed) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[a.set + SET_U_LO]), (unsigned long long)passed);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed);
     }
+#endif
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
@@ -250,7 +295,7 @@ static void make_args(FastArgs* a, const BFHashDataStruct* hd, const BFDepthCame
     a->fx = cp->fx; a->fy = cp->fy; a->mx5 = cp->mx + 0.5f; a->my5 = cp->my + 0.5f;
 }
 
-int fast_stencil_ctas_per_sm() { return BF_FAST_MINBLOCKS; }
+int fast_stencil_ctas_per_sm(bool fused) { return fused ? BF_FAST_MINBLOCKS_FUSED : BF_FAST_MINBLOCKS; }
 
 int launch_integrate_fast(const BFHashDataStruct* hd, const BFHashParams* hp, const BFDepthCameraParams* cp, const float* depth, const void* color,
                           bool deIntegrate, bool useListCount, unsigned countOverride, unsigned* ctrs, int* live, const int4* work, int set,
@@ -258,8 +303,8 @@ int launch_integrate_fast(const BFHashDataStruct* hd, const BFHashParams* hp, co
     FastArgs a;
     make_args(&a, hd, cp, depth, color, useListCount, countOverride, ctrs, live, work, set);
     make_pose(hp, &a.A); a.B = a.A;
-    if (deIntegrate) stencil_fast_kernel<1><<<grid, 128, 0, s>>>(a);
-    else             stencil_fast_kernel<0><<<grid, 128, 0, s>>>(a);
+    if (work) { if (deIntegrate) stencil_fast_kernel<1, true><<<grid, 128, 0, s>>>(a); else stencil_fast_kernel<0, true><<<grid, 128, 0, s>>>(a); }
+    else      { if (deIntegrate) stencil_fast_kernel<1, false><<<grid, 128, 0, s>>>(a); else stencil_fast_kernel<0, false><<<grid, 128, 0, s>>>(a); }
     BF_CHECK(cudaGetLastError());
     return 0;
 }
@@ -269,7 +314,7 @@ int launch_reintegrate_fast(const BFHashDataStruct* hd, const BFHashParams* hpOl
     FastArgs a;
     make_args(&a, hd, cp, depth, color, true, 0, ctrs, live, work, set);
     make_pose(hpOld, &a.A); make_pose(hpNew, &a.B);
-    stencil_fast_kernel<2><<<grid, 128, 0, s>>>(a);
+    stencil_fast_kernel<2, true><<<grid, 128, 0, s>>>(a);
     BF_CHECK(cudaGetLastError());
     return 0;
 }

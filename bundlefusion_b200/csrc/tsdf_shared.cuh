@@ -12,7 +12,7 @@ enum { CTR_HIGH_WATER = 0, CTR_E = 3, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROP
        // two per-list counter sets (the list / work list of op k and of op k+1 are alive at the same time when alloc + compactify of
        // op k+1 run on the front lane while the stencil of op k runs on the back lane); a set is zeroed by the op that is about to fill it
        CTR_SET0 = 16, CTR_SET1 = 24, CTR_NUM = 32,
-       SET_COUNT = 0, SET_WORK = 1, SET_CULLED = 2, SET_U_LO = 4, SET_U_HI = 5, SET_WORDS = 8 };
+       SET_COUNT = 0, SET_WORK = 1, SET_CULLED = 2, SET_TICKET = 3 /* dynamic block deal of the fast stencil */, SET_U_LO = 4, SET_U_HI = 5, SET_WORDS = 8 };
 
 // tolerance-mode stencils (tsdf_fast.cu).  `work` may be NULL (the list is then d_hashCompactified[0..count)); useListCount /
 // countOverride as in tsdf.cu's integrate_kernel.
@@ -21,6 +21,6 @@ int launch_integrate_fast(const BFHashDataStruct* hd, const BFHashParams* hp, co
                           int grid, cudaStream_t s);
 int launch_reintegrate_fast(const BFHashDataStruct* hd, const BFHashParams* hpOld, const BFHashParams* hpNew, const BFDepthCameraParams* cp,
                             const float* depth, const void* color, const int4* work, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s);
-int fast_stencil_ctas_per_sm();
+int fast_stencil_ctas_per_sm(bool fused);
 
 }  // namespace bf

@@ -63,8 +63,8 @@ extern "C" int emu_reintegrate_fast(const BFHashDataStruct* hd, const BFHashPara
 def emu():
     src = open(os.path.join(ROOT, "bundlefusion_b200", "csrc", "tsdf_fast.cu")).read()
     src = src.replace('#include "bf_common.cuh"', "")
-    src, n = re.subn(r"(\w+<\d>)<<<\s*([^,]+),\s*([^,]+),\s*[^,]+,\s*[^>]+>>>\((\w+)\)", r"seq_launch(\1, \2, \3, \4)", src)
-    assert n == 3, n
+    src, n = re.subn(r"(\w+<\d, \w+>)<<<\s*([^,]+),\s*([^,]+),\s*[^,]+,\s*[^>]+>>>\((\w+)\)", r"seq_launch(\1, \2, \3, \4)", src)
+    assert n == 5, n
     d = tempfile.mkdtemp(prefix="bf_fast_emu_")
     cpp = os.path.join(d, "tsdf_fast_emu.cpp")
     open(cpp, "w").write(_PRE % {"emu": os.path.join(ROOT, "tests", "cuda_emu", "cuda_emu.h")} + src + _POST)
