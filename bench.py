@@ -146,7 +146,7 @@ def run_ours(args):
     hp = default_hash_params(num_buckets=WORKLOAD["hash_buckets"], num_sdf_blocks=WORKLOAD["sdf_blocks"], voxel_size=WORKLOAD["voxel_m"])
     if world > 1:
         hp.m_dummy = (world << 32) | rank            # spatial shard of the voxel hash: this rank owns blocks with owner(pos) == rank
-    scene = CUDASceneRepHashSDF(hp, dev)
+    scene = CUDASceneRepHashSDF(hp, dev, arithmetic=os.environ.get("BF_TSDF_ARITH", "fast"))       # "exact": the bit-identical kernels, for A/B runs
 
     B = WORKLOAD["frame_bank"]
     idx = [8 * i for i in range(B)]
@@ -306,7 +306,7 @@ def run_ours(args):
                        active_blocks=int(WORKLOAD["sdf_blocks"] - heap_free), in_frustum_blocks_last=int(stats["E"]), global_pcg_iters=int(sg["pcg"]), global_gn_iters=int(sg["gn"])),
         "e2e": {"value": round(K / (ms_e2e / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": int(bytes_out),
                 "note": "incoming frame copied from pinned host memory every step on an upload stream, one frame ahead of the fusion; re-integrated frames come from the device-resident frame store"},
-        "gpu_launches": int(launches), "roofline": roof, "clocks": summarize_clocks(clk_lines),
+        "gpu_launches": int(launches), "roofline": roof, "tsdf_arithmetic": scene.arithmetic, "clocks": summarize_clocks(clk_lines),
     }
     if args.no_ba:
         out["diagnostic"] = "--no-ba: bundle adjustment left out, not a bench value"
