@@ -219,19 +219,10 @@ __device__ void proj_error(unsigned idx, const VerifyArgs& a, const float* T, co
 // `val += __shfl_down(val, offset)` (a lane whose source is past the warp's end adds itself), contributions from the lanes with
 // threadIdx.x % 32 == 0.  The reference adds those with shared-memory atomics (scheduling order); here they are added in ascending (row, x) order.
 // See oracle/filter_oracle.c dense_block_total and tests/test_manager_reference_emulated.py.
-__global__ void __launch_bounds__(1024)
-sift_dense_verify_kernel(const __grid_constant__ VerifyArgs a) {
-    const unsigned p = blockIdx.x + a.startFrame, x = threadIdx.x, ty = threadIdx.y;
-    if (p == a.curFrame) return;
-    if (a.numFiltered[p] == 0) return;
-    __shared__ float sT[16], sTinv[16];
-    __shared__ float sAdd[64][3];
-    const unsigned t = ty * blockDim.x + x;
-    if (t < 16) sT[t] = a.fT[16 * (size_t)p + t];
-    __syncthreads();
-    if (t == 0) mat4_inverse_hd(sT, sTinv);
-    __syncthreads();
-    const BFCUDACachedFrame in = a.frames[p], model = a.frames[a.curFrame];
+// the reference's block total of one image pair (see above); every thread of the (W, ceil(H / 32)) block calls it, thread 0 gets (err, corr)
+__device__ __forceinline__ void dense_pair_total(const VerifyArgs& a, const float* sT, const float* sTinv, const BFCUDACachedFrame& in, const BFCUDACachedFrame& model,
+                                                 float (*sAdd)[3], float& err, float& corr) {
+    const unsigned x = threadIdx.x, ty = threadIdx.y, t = ty * blockDim.x + x;
     float s[3] = { 0.0f, 0.0f, 0.0f };
     for (unsigned i = 0; i < 32; ++i) {
         const unsigned y = ty * 32 + i;
@@ -248,14 +239,61 @@ sift_dense_verify_kernel(const __grid_constant__ VerifyArgs a) {
     const unsigned perRow = (blockDim.x + 31) / 32;
     if ((x & 31) == 0) for (int k = 0; k < 3; ++k) sAdd[ty * perRow + (x >> 5)][k] = s[k];
     __syncthreads();
+    err = 0.0f; corr = 0.0f;
     if (t == 0) {
         float tot[3] = { 0.0f, 0.0f, 0.0f };
         for (unsigned r = 0; r < blockDim.y; ++r) for (unsigned c = 0; c < perRow; ++c) for (int k = 0; k < 3; ++k) tot[k] += sAdd[r * perRow + c][k];
-        const float err = tot[0] / tot[1], corr = 0.5f * tot[2] / (float)(a.W * a.H);
+        err = tot[0] / tot[1]; corr = 0.5f * tot[2] / (float)(a.W * a.H);
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+sift_dense_verify_kernel(const __grid_constant__ VerifyArgs a) {
+    const unsigned p = blockIdx.x + a.startFrame;
+    if (p == a.curFrame) return;
+    if (a.numFiltered[p] == 0) return;
+    __shared__ float sT[16], sTinv[16];
+    __shared__ float sAdd[64][3];
+    const unsigned t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t < 16) sT[t] = a.fT[16 * (size_t)p + t];
+    __syncthreads();
+    if (t == 0) mat4_inverse_hd(sT, sTinv);
+    __syncthreads();
+    float err, corr;
+    dense_pair_total(a, sT, sTinv, a.frames[p], a.frames[a.curFrame], sAdd, err, corr);
+    if (t == 0) {
         if (a.stats) { a.stats[2 * p] = err; a.stats[2 * p + 1] = corr; }
         if (corr < a.corrThresh || err > a.errThresh || err != err) a.numFiltered[p] = 0;
     }
 }
+
+// VerifyTrajectoryCU_Kernel (SIFTImageManager.cu:1036-1130): block b < N (N - 1) / 2 looks at (b / N, b % N) -- the reference's decode, which
+// reaches only the pairs whose row-major index is below N (N - 1) / 2; kept, so that the verdict on a chunk is the reference's.
+struct TrajVerifyArgs { VerifyArgs v; unsigned numImages; const int* valid; const float* traj; int* validOpt; };
+__global__ void __launch_bounds__(1024)
+sift_verify_trajectory_kernel(const __grid_constant__ TrajVerifyArgs a) {
+    const unsigned img0 = blockIdx.x / a.numImages, img1 = blockIdx.x % a.numImages;
+    if (img0 >= img1) return;
+    if (a.valid[img0] == 0 || a.valid[img1] == 0) return;
+    __shared__ float sT[16], sTinv[16];
+    __shared__ float sAdd[64][3];
+    const unsigned t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        float inv1[16];
+        mat4_inverse_hd(a.traj + 16 * (size_t)img1, inv1);
+        const float* B = a.traj + 16 * (size_t)img0;
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) sT[4 * r + c] = inv1[4 * r] * B[c] + inv1[4 * r + 1] * B[4 + c] + inv1[4 * r + 2] * B[8 + c] + inv1[4 * r + 3] * B[12 + c];
+        mat4_inverse_hd(sT, sTinv);
+    }
+    __syncthreads();
+    float err, corr;
+    dense_pair_total(a.v, sT, sTinv, a.v.frames[img0], a.v.frames[img1], sAdd, err, corr);
+    if (t == 0) {
+        if (a.v.stats) { a.v.stats[2 * blockIdx.x] = err; a.v.stats[2 * blockIdx.x + 1] = corr; }
+        if (corr < a.v.corrThresh || err > a.v.errThresh || err != err) a.validOpt[0] = 0;
+    }
+}
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
 
 }  // namespace bf
 
@@ -297,6 +335,30 @@ BF_API int bfSiftFilterMatchesByDenseVerify(unsigned int curFrame, unsigned int 
     ++g_launchCount;
     const dim3 block(imageWidth, by);
     sift_dense_verify_kernel<<<numFrames - startFrame, block, 0, stream()>>>(a);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
+
+BF_API int bfSiftVerifyTrajectory(unsigned int numImages, const int32_t* d_validImages, const float* d_trajectory, unsigned int imageWidth, unsigned int imageHeight,
+                                  const float* intrinsics, const BFCUDACachedFrame* d_cachedFrames, float distThresh, float normalThresh, float colorThresh,
+                                  float errThresh, float corrThresh, float sensorDepthMin, float sensorDepthMax, int32_t* d_validOpt, float* d_statsOut) {
+    (void)colorThresh;
+    if (!d_validOpt) return (int)cudaErrorInvalidValue;
+    if (numImages < 2) { set_int_kernel<<<1, 1, 0, stream()>>>(d_validOpt, 0); BF_CHECK(cudaGetLastError()); return 0; }      // SIFTImageManager.cu:1138: returns 0
+    if (!d_validImages || !d_trajectory || !intrinsics || !d_cachedFrames || imageWidth == 0 || imageHeight == 0) return (int)cudaErrorInvalidValue;
+    TrajVerifyArgs a;
+    a.v.curFrame = 0; a.v.startFrame = 0; a.v.W = imageWidth; a.v.H = imageHeight;
+    a.v.numFiltered = nullptr; a.v.fT = nullptr; a.v.frames = d_cachedFrames; a.v.stats = d_statsOut;
+    for (int k = 0; k < 16; ++k) a.v.K[k] = intrinsics[k];
+    a.v.distThresh = distThresh; a.v.normalThresh = normalThresh; a.v.errThresh = errThresh; a.v.corrThresh = corrThresh;
+    a.v.dMin = sensorDepthMin; a.v.dMax = sensorDepthMax;
+    a.numImages = numImages; a.valid = d_validImages; a.traj = d_trajectory; a.validOpt = d_validOpt;
+    const unsigned by = (imageHeight + 31) / 32, nt = imageWidth * by;
+    if (nt % 32 != 0 || nt > 1024) return (int)cudaErrorInvalidValue;
+    g_launchCount += 2;
+    set_int_kernel<<<1, 1, 0, stream()>>>(d_validOpt, 1);
+    const dim3 block(imageWidth, by);
+    sift_verify_trajectory_kernel<<<numImages * (numImages - 1) / 2, block, 0, stream()>>>(a);
     BF_CHECK(cudaGetLastError());
     return 0;
 }

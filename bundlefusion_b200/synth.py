@@ -423,4 +423,4 @@ def make_dense_verify_problem(n_prev: int = 5, stride: int = 4, start: int = 200
         T[p] = rel
     fx, fy, mx, my = cache_intrinsics(W, H)
     K = np.array([[fx, 0, mx, 0], [0, fy, my, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
-    return {"caches": caches, "T": T, "K": K, "cur": cur, "P": n_prev + 1, "W": 80, "H": 60}
+    return {"caches": caches, "T": T, "K": K, "cur": cur, "P": n_prev + 1, "W": 80, "H": 60, "gt": gt}

@@ -110,6 +110,18 @@ int bfSiftFilterMatchesByDenseVerify(unsigned int curFrame, unsigned int startFr
                                      const BFCUDACachedFrame* d_cachedFrames, float distThresh, float normalThresh, float colorThresh, float errThresh,
                                      float corrThresh, float sensorDepthMin, float sensorDepthMax, float* d_statsOut);
 
+/* SIFTImageManager::VerifyTrajectoryCU(numImages, d_trajectory, imageWidth, imageHeight, intrinsics, d_cachedFrames, distThresh, normalThresh,
+ * colorThresh, errThresh, corrThresh, sensorDepthMin, sensorDepthMax) (FL/SiftGPU/SIFTImageManager.cu:1036-1150), the check Bundler::optimize runs
+ * on a chunk after its local solve (FL/Bundler.cpp:259-275): image pairs of the solved trajectory are warped into each other at the cache
+ * resolution (the same projective association and block total as bfSiftFilterMatchesByDenseVerify) and *d_validOpt becomes 0 when a pair has
+ * corr < corrThresh, err > errThresh or err NaN, else 1.  The reference launches N (N - 1) / 2 blocks and decodes block b as (b / N, b % N), so only
+ * the pairs whose row-major index is below N (N - 1) / 2 are examined -- kept.  numImages < 2: *d_validOpt = 0 (the
+ * reference returns 0).  d_trajectory: [numImages][16]; intrinsics: HOST 4x4 (cache resolution); d_statsOut: optional [N (N-1) / 2][2] (err, corr)
+ * by block index.  The verdict stays on the device (the reference copies it to the host at once).  Asynchronous. */
+int bfSiftVerifyTrajectory(unsigned int numImages, const int32_t* d_validImages, const float* d_trajectory, unsigned int imageWidth, unsigned int imageHeight,
+                           const float* intrinsics, const BFCUDACachedFrame* d_cachedFrames, float distThresh, float normalThresh, float colorThresh,
+                           float errThresh, float corrThresh, float sensorDepthMin, float sensorDepthMax, int32_t* d_validOpt, float* d_statsOut);
+
 /* SIFTImageManager::AddCurrToResidualsCU(curFrame, startFrame, numFrames, colorIntrinsicsInv) (FL/SiftGPU/SIFTImageManager.cu:610-685):
  * appends the filtered matches of every pair p in [startFrame, numFrames), p != curFrame, to the global correspondence list as
  * EntryJ { p, curFrame, Kinv (d_i (x_i, y_i, 1)), Kinv (d_j (x_j, y_j, 1)) } (+ their key-point index pairs) and advances

@@ -641,6 +641,46 @@ ORC_API void orc_sift_filter_dense_verify(unsigned curFrame, unsigned startFrame
     free(pix);
 }
 
+/* SIFTImageManager::VerifyTrajectoryCU (FL/SiftGPU/SIFTImageManager.cu:1036-1150): every launched block b < N (N - 1) / 2 decodes
+ * (img0, img1) = (b / N, b % N) -- so only the pairs whose row-major index is below N (N - 1) / 2 are looked at, kept --,
+ * skips img0 >= img1 and invalid images, warps frame img0 into img1 with trajectory[img1]^-1 * trajectory[img0] and back, forms the
+ * block total as the dense-verify filter does and returns 0 when any visited pair has corr < corrThresh, err > errThresh or err NaN.
+ * trajectory: [N][16] row-major.  stats (optional): [N*N][2] = (err, corr) of the visited pairs at b, else untouched. */
+ORC_API int orc_sift_verify_trajectory(unsigned numImages, const int32_t* validImages, const float* trajectory, unsigned W, unsigned H, const float* intrinsics,
+                                       const CachedFrame* frames, float distThresh, float normalThresh, float colorThresh, float errThresh, float corrThresh,
+                                       float dMin, float dMax, float* stats) {
+    (void)colorThresh;
+    if (numImages < 2) return 0;
+    int valid = 1;
+    float* pix = (float*)malloc(sizeof(float) * 3 * (size_t)W * H);
+    const unsigned numPairs = numImages * (numImages - 1) / 2;
+    for (unsigned b = 0; b < numPairs; ++b) {
+        const unsigned img0 = b / numImages, img1 = b % numImages;
+        if (img0 >= img1) continue;
+        if (validImages[img0] == 0 || validImages[img1] == 0) continue;
+        float inv1[16], T[16], Tinv[16];
+        mat4_inverse_subdet(trajectory + 16 * (size_t)img1, inv1);
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) {
+            const float* A = inv1; const float* Bm = trajectory + 16 * (size_t)img0;
+            T[4 * r + c] = A[4 * r] * Bm[c] + A[4 * r + 1] * Bm[4 + c] + A[4 * r + 2] * Bm[8 + c] + A[4 * r + 3] * Bm[12 + c];
+        }
+        mat4_inverse_subdet(T, Tinv);
+        for (unsigned idx = 0; idx < W * H; ++idx) {
+            float a[3], c[3];
+            proj_error(idx, W, H, distThresh, normalThresh, T, intrinsics, &frames[img0], &frames[img1], dMin, dMax, a);
+            proj_error(idx, W, H, distThresh, normalThresh, Tinv, intrinsics, &frames[img1], &frames[img0], dMin, dMax, c);
+            for (int k = 0; k < 3; ++k) pix[3 * (size_t)idx + k] = a[k] + c[k];
+        }
+        float tot[3];
+        if (!dense_block_total(pix, W, H, tot)) continue;
+        const float err = tot[0] / tot[1], corr = 0.5f * tot[2] / (float)(W * H);
+        if (stats) { stats[2 * b] = err; stats[2 * b + 1] = corr; }
+        if (corr < corrThresh || err > errThresh || err != err) valid = 0;
+    }
+    free(pix);
+    return valid;
+}
+
 /* ---- invalidation after a solve: InvalidateImageToImageCU_Kernel, CheckForInvalidFramesSimpleCU_Kernel / CheckForInvalidFramesCU_Kernel
  * (FL/SiftGPU/SIFTImageManager.cu:692-790).  entries: EntryJ records of 32 bytes.  The comprehensive variant is restated by its intent
  * (every still-valid correspondence touching an image with an empty table row), not by the reference's partial grid coverage. ---- */

@@ -558,6 +558,22 @@ def sift_filter_dense_verify(curFrame, startFrame, numFrames, W, H, intrinsics, 
     return nf, stats
 
 
+def sift_verify_trajectory(numImages, validImages, trajectory, W, H, intrinsics, frames, distThresh, normalThresh, colorThresh, errThresh, corrThresh, dMin, dMax):
+    """VerifyTrajectoryCU.  trajectory [N,4,4]; frames as for sift_filter_dense_verify.  Returns (valid 0/1, stats [N(N-1)/2, 2] by block index)."""
+    L = lib()
+    v = np.ascontiguousarray(validImages, np.int32); T = np.ascontiguousarray(trajectory, np.float32); K = np.ascontiguousarray(intrinsics, np.float32)
+    keep = [{k: np.ascontiguousarray(f[k], np.float32) for k in ("depth", "campos", "normals")} for f in frames]
+    recs = (_CachedFrame * len(keep))()
+    for r, f in zip(recs, keep):
+        r.depth, r.campos, r.normals = f["depth"].ctypes.data, f["campos"].ctypes.data, f["normals"].ctypes.data
+    stats = np.full((max(1, numImages * (numImages - 1) // 2), 2), -1.0, np.float32)
+    L.orc_sift_verify_trajectory.argtypes = [C.c_uint, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p] + [C.c_float] * 7 + [C.c_void_p]
+    L.orc_sift_verify_trajectory.restype = C.c_int
+    ok = L.orc_sift_verify_trajectory(numImages, v.ctypes.data, T.ctypes.data, W, H, K.ctypes.data, C.addressof(recs), distThresh, normalThresh, colorThresh,
+                                      errThresh, corrThresh, dMin, dMax, stats.ctypes.data)
+    return int(ok), stats
+
+
 # ---- SIFT detection (oracle/sift_detect_oracle.c) -----------------------------------------------------------------------------------
 class SiftDetectParams(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depthWidth", C.c_uint32), ("depthHeight", C.c_uint32), ("depthMin", C.c_float),

@@ -26,8 +26,9 @@ def same(a, b):
 
 @pytest.fixture(scope="module")
 def verify_emu():
-    L = build_emulated("sift_verify.cu", 2)
+    L = build_emulated("sift_verify.cu", 5)
     vp, u, f = C.c_void_p, C.c_uint, C.c_float
+    L.bfSiftVerifyTrajectory.argtypes = [u, vp, vp, u, u, C.POINTER(f), vp] + [f] * 7 + [vp, vp]
     L.bfSiftFilterMatchesBySurfaceArea.argtypes = [u, u, u, vp, vp, vp, C.POINTER(f), f, vp]
     L.bfSiftFilterMatchesByDenseVerify.argtypes = [u] * 5 + [C.POINTER(f), vp, vp, vp] + [f] * 7 + [vp]
     return L
@@ -86,6 +87,28 @@ def test_kabsch_filter_and_residuals_emulated(filter_emu):
     nfc = np.where(np.arange(P) == cur, 0, nf).astype(np.int32)
     assert filter_emu.bfSiftAddCurrToResiduals(cur, 0, P, ent.ctypes.data, eidx.ctypes.data, cnt.ctypes.data, nfc.ctypes.data, fi.ctypes.data, keys.ctypes.data, f16(pb["Kinv"])) == 0
     assert cnt[0] == len(ent_o) and ent[:32 * len(ent_o)].tobytes() == ent_o.tobytes() and np.array_equal(eidx[:len(ent_o)], idx_o)
+
+
+@pytest.mark.parametrize("break_pair", [False, True])
+def test_verify_trajectory_emulated(verify_emu, break_pair):
+    """bfSiftVerifyTrajectory (VerifyTrajectoryCU) under the emulation against the oracle; on a consistent trajectory whose last pose is the
+    identity, the pair (p, last) sees exactly what the dense-verification filter sees for pair p."""
+    from tests.test_verify_filters_gpu import trajectory_verify_case
+    pb, N, valid, traj = trajectory_verify_case(3, break_pair, None)
+    opt = dict(VERIFY, errThresh=0.05, corrThresh=0.001, dMin=0.1, dMax=3.0)
+    ok_o, st_o = orc.sift_verify_trajectory(N, valid, traj, pb["W"], pb["H"], pb["K"], pb["caches"], **opt)
+    keep = [{k: np.ascontiguousarray(f[k], np.float32) for k in ("depth", "campos", "normals")} for f in pb["caches"]]
+    recs = (capi.BFCUDACachedFrame * N)()
+    for r, f in zip(recs, keep):
+        r.d_depthDownsampled, r.d_cameraposDownsampled, r.d_normalsDownsampled = f["depth"].ctypes.data, f["campos"].ctypes.data, f["normals"].ctypes.data
+    ok = np.full(1, 9, np.int32); stats = np.full((N * (N - 1) // 2, 2), -1.0, np.float32); T = np.ascontiguousarray(traj, np.float32)
+    assert verify_emu.bfSiftVerifyTrajectory(N, valid.ctypes.data, T.ctypes.data, pb["W"], pb["H"], f16(pb["K"]), C.addressof(recs), opt["distThresh"], opt["normalThresh"],
+                                             opt["colorThresh"], opt["errThresh"], opt["corrThresh"], opt["dMin"], opt["dMax"], ok.ctypes.data, stats.ctypes.data) == 0
+    assert ok[0] == ok_o == (0 if break_pair else 1) and same(stats, st_o)
+    # pair (0, N - 1) = block N - 1: the filter's view of pair 0 with the transform trajectory[0]
+    num = np.full(N, 5, np.int32)
+    _, st_f = orc.sift_filter_dense_verify(N - 1, 0, N, pb["W"], pb["H"], pb["K"], num, traj, pb["caches"], **opt)
+    assert same(st_o[N - 1], st_f[0])
 
 
 @pytest.mark.parametrize("seed,numFrames", [(0, 1), (1, 7), (2, 300), (3, 1000)])

@@ -101,3 +101,53 @@ def test_dense_verify_invalid_frames_and_bad_transforms(gpu):
     nf_g, st_g = run_verify(gpu, cur, 0, P, pb["W"], pb["H"], pb["K"], num, T, caches, VERIFY)
     assert np.array_equal(nf_g, nf_o) and same(st_g, st_o)
     assert list(nf_g) == [0, 0, 0, 5] and np.isnan(st_g[2, 0])
+
+
+def run_verify_trajectory(L, N, valid, traj, W, H, K, caches, opt):
+    keep = []
+    recs = (capi.BFCUDACachedFrame * len(caches))()
+    for r, f in zip(recs, caches):
+        d, c, n = DevBuf(f["depth"].astype(np.float32)), DevBuf(f["campos"].astype(np.float32)), DevBuf(f["normals"].astype(np.float32))
+        keep += [d, c, n]
+        r.d_depthDownsampled, r.d_cameraposDownsampled, r.d_normalsDownsampled = d.ptr, c.ptr, n.ptr
+    d_recs = DevBuf(np.frombuffer(bytes(recs), np.uint8))
+    d_valid, d_T, d_ok = DevBuf(np.ascontiguousarray(valid, np.int32)), DevBuf(np.ascontiguousarray(traj, np.float32)), DevBuf(np.full(1, 7, np.int32))
+    d_stats = DevBuf(np.full((max(1, N * (N - 1) // 2), 2), -1.0, np.float32))
+    capi.check(L.bfSiftVerifyTrajectory(N, d_valid.ptr, d_T.ptr, W, H, _f16(K), d_recs.ptr, opt["distThresh"], opt["normalThresh"], opt["colorThresh"],
+                                        opt["errThresh"], opt["corrThresh"], opt["dMin"], opt["dMax"], d_ok.ptr, d_stats.ptr), "verify trajectory")
+    return int(d_ok.get()[0]), d_stats.get()
+
+
+def trajectory_verify_case(n_prev=4, break_pair=False, invalid=None):
+    """cached frames of a synthetic sweep with their true camera poses as the trajectory (so every pair agrees); break_pair moves one pose"""
+    pb = synth.make_dense_verify_problem(n_prev=n_prev)
+    N = pb["P"]
+    # trajectory[p] = frame p -> the current frame (index cur = N - 1), from the true poses: a consistent trajectory, trajectory[cur] = identity
+    traj = np.stack([np.linalg.inv(pb["gt"][pb["cur"]]) @ pb["gt"][p] for p in range(N)]).astype(np.float32)
+    traj[pb["cur"]] = np.eye(4, dtype=np.float32)
+    if break_pair:
+        traj[1] = traj[1].copy(); traj[1][:3, 3] += np.array([0.25, 0.0, 0.1], np.float32)
+    valid = np.ones(N, np.int32)
+    if invalid is not None:
+        valid[invalid] = 0
+    return pb, N, valid, traj
+
+
+@pytest.mark.parametrize("break_pair,invalid", [(False, None), (True, None), (True, 1)])
+def test_verify_trajectory_bit_exact(gpu, break_pair, invalid):
+    pb, N, valid, traj = trajectory_verify_case(4, break_pair, invalid)
+    opt = dict(VERIFY, errThresh=0.05, corrThresh=0.001, dMin=0.1, dMax=3.0)          # s_verifyOptErrThresh / CorrThresh, FL/Bundler.cpp:266
+    ok_o, st_o = orc.sift_verify_trajectory(N, valid, traj, pb["W"], pb["H"], pb["K"], pb["caches"], **opt)
+    ok_g, st_g = run_verify_trajectory(gpu, N, valid, traj, pb["W"], pb["H"], pb["K"], pb["caches"], opt)
+    assert ok_g == ok_o and same(st_g, st_o), (ok_g, ok_o, st_g, st_o)
+    assert ok_o == (0 if (break_pair and invalid is None) else 1)
+    # the reference's block decode reaches only row-major pair indices below N (N - 1) / 2: with N = 5, (0,1..4), (1,2..4); pair (2,3) is never looked at
+    visited = {(b // N, b % N) for b in range(N * (N - 1) // 2) if b // N < b % N}
+    assert (2, 3) not in visited and (1, 4) in visited
+    assert all((st_o[b, 0] != -1.0) == (((b // N, b % N) in visited) and valid[b // N] and valid[b % N]) for b in range(N * (N - 1) // 2))
+
+
+def test_verify_trajectory_too_few_images(gpu):
+    pb, N, valid, traj = trajectory_verify_case(4)
+    ok_g, _ = run_verify_trajectory(gpu, 1, valid, traj, pb["W"], pb["H"], pb["K"], pb["caches"], dict(VERIFY))
+    assert ok_g == 0
