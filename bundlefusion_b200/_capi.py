@@ -120,7 +120,7 @@ BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updat
 SIFT_SYMBOLS = ["bfSiftMatchBatch", "bfSiftSortKeyPointMatches", "bfSiftFilterKeyPointMatches", "bfSiftFilterMatchesBySurfaceArea", "bfSiftFilterMatchesByDenseVerify",
                 "bfSiftAddCurrToResiduals", "bfSiftWorkspaceBytes", "bfSiftReleaseWorkspace", "bfSiftDetect", "bfSiftDetectWorkspaceBytes",
                 "bfSiftDetectReleaseWorkspace", "bfSiftInvalidateImageToImage", "bfSiftCheckForInvalidFrames", "bfSiftFilterFrames",
-                "bfSiftAddCurrToResidualsIfMatched", "bfSiftVerifyTrajectory"]
+                "bfSiftAddCurrToResidualsIfMatched", "bfSiftVerifyTrajectory", "bfSiftFuseToGlobal"]
 
 SOLVER_SYMBOLS = [
     "solveBundlingStub", "buildVariablesToCorrespondencesTableCUDA", "evalMaxResidual", "countHighResiduals", "collectHighResiduals",

@@ -424,3 +424,42 @@ def make_dense_verify_problem(n_prev: int = 5, stride: int = 4, start: int = 200
     fx, fy, mx, my = cache_intrinsics(W, H)
     K = np.array([[fx, 0, mx, 0], [0, fy, my, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
     return {"caches": caches, "T": T, "K": K, "cur": cur, "P": n_prev + 1, "W": 80, "H": 60, "gt": gt}
+
+
+def make_fuse_problem(n_images: int = 6, n_points: int = 140, key_stride: int = 256, seed: int = 0, outlier_frac: float = 0.1, invalid_frac: float = 0.05):
+    """A solved chunk for SIFTImageManager::fuseToGlobal: n_points 3-D points seen by random subsets of n_images cameras near the origin, one key
+    per observation (image-major global index image * key_stride + key), correspondences between the observations of a point in image pairs
+    (a random subset of the pairs, so that tracks have to be chained), some of them displaced by > 3 cm (they join tracks without contributing a
+    position) and some invalidated.  Returns corr (EntryJ), keyIdx, transforms, keys, descs, numKeys, K."""
+    rng = np.random.default_rng(seed)
+    fx = 525.0; K = np.array([[fx, 0, 319.5, 0], [0, fx, 239.5, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
+    T = np.stack([se3_exp(rng.standard_normal(3) * 0.03, rng.standard_normal(3) * 0.05) for _ in range(n_images)]).astype(np.float32)
+    T[0] = np.eye(4, dtype=np.float32)
+    pts = np.c_[rng.uniform(-1, 1, n_points), rng.uniform(-0.7, 0.7, n_points), rng.uniform(1.0, 3.0, n_points)]
+    keys = np.zeros((n_images * key_stride, 4), np.float32); descs = rng.integers(0, 256, (n_images * key_stride, 128)).astype(np.uint8)
+    num = np.zeros(n_images, np.int32)
+    obs = {}                                                  # (point, image) -> (key index, camera-space position)
+    for i in range(n_images):
+        seen = np.nonzero(rng.random(n_points) < 0.6)[0]
+        rng.shuffle(seen)
+        Tinv = np.linalg.inv(T[i].astype(np.float64))
+        for p in seen[: key_stride]:
+            c = (Tinv @ np.r_[pts[p], 1.0])[:3].astype(np.float32)
+            k = int(num[i]); num[i] += 1
+            keys[i * key_stride + k] = (fx * c[0] / c[2] + 319.5, fx * c[1] / c[2] + 239.5, float(rng.choice([3.2, 6.4, 12.8])), c[2])
+            obs[(int(p), i)] = (i * key_stride + k, c)
+    dt = np.dtype([("i", "<u4"), ("j", "<u4"), ("pi", "<f4", (3,)), ("pj", "<f4", (3,))])
+    rows, kidx = [], []
+    for i in range(n_images):
+        for j in range(i + 1, n_images):
+            if rng.random() < 0.35:
+                continue                                       # this image pair was not matched
+            for p in range(n_points):
+                if (p, i) in obs and (p, j) in obs and rng.random() < 0.8:
+                    (ki, ci), (kj, cj) = obs[(p, i)], obs[(p, j)]
+                    cj2 = cj + (np.array([0.06, 0.0, 0.02], np.float32) if rng.random() < outlier_frac else 0)
+                    rows.append((i, j, ci, cj2.astype(np.float32))); kidx.append((ki, kj))
+    corr = np.array(rows, dtype=dt); kidx = np.array(kidx, np.uint32)
+    bad = rng.random(len(corr)) < invalid_frac
+    corr["i"][bad] = 0xFFFFFFFF; corr["j"][bad] = 0xFFFFFFFF
+    return {"corr": corr, "keyIdx": kidx, "transforms": T, "keys": keys, "descs": descs, "numKeys": num, "K": K, "keyStride": key_stride}

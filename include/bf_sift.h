@@ -186,6 +186,23 @@ int bfSiftAddCurrToResidualsIfMatched(unsigned int curFrame, unsigned int startF
                                       const uint32_t* d_currFilteredMatchKeyPointIndices, const BFSIFTKeyPoint* d_keyPoints, const float* colorIntrinsicsInv,
                                       const int32_t* d_lastMatchedFrame);
 
+/* SIFTImageManager::fuseToGlobal (FL/SiftGPU/SIFTImageManager.cpp:413-476; computeTracks / findTrack :366-411), the chunk -> keyframe fusion
+ * of the sparse features Bundler::fuseToGlobal runs after a chunk's local solve (FL/Bundler.cpp:384-390) -- in the reference on the HOST
+ * (device -> host copies of every key, descriptor, correspondence and pose of the chunk, a recursive walk, an upload).  Here: one launch,
+ * nothing leaves the device.  Correspondences of the chunk (EntryJ + their global key-point index pairs, count on the device) are grouped
+ * into tracks exactly as the reference's recursion visits them; each track with at least one member whose correspondence agrees within 3 cm
+ * under the solved poses yields one key point of the new keyframe: position = mean world position projected by colorIntrinsics into the
+ * chunk's first frame, depth = its z, scale and descriptor = those of the track's first-visited key.  Key k of image i has the global
+ * index i * keyStride + k (d_keyPoints / d_descriptors are indexed by it; d_numKeysPerImage[i] keys of image i are walked).
+ * d_transforms: [numImages][16] solved chunk poses; colorIntrinsics: HOST 4x4; maxCorr: capacity bound of the list (<= 4096), numImages *
+ * keyStride <= 16384.  Outputs: d_outKeyPoints / d_outDescriptors [maxKeys], *d_outNumKeys; d_status (optional): 1 if the explicit recursion
+ * stack overflowed (tracks deeper than 4096 keys).  More than maxKeys tracks: the first maxKeys in track order are kept (the reference sorts
+ * the keys -- not the descriptors -- by depth with an unstable sort; unreachable with <= 11 images x ~150 features).  Asynchronous. */
+int bfSiftFuseToGlobal(const BFEntryJ* d_corr, const uint32_t* d_corrKeyIndices, const int32_t* d_numCorr, const float* d_transforms, unsigned int numImages,
+                       const BFSIFTKeyPoint* d_keyPoints, const uint8_t* d_descriptors, const int32_t* d_numKeysPerImage, unsigned int keyStride,
+                       const float* colorIntrinsics, unsigned int maxCorr, BFSIFTKeyPoint* d_outKeyPoints, uint8_t* d_outDescriptors, int32_t* d_outNumKeys,
+                       unsigned int maxKeys, int32_t* d_status);
+
 /* device scratch the matcher holds (rowResult / rowDist per job); released by bfSiftReleaseWorkspace */
 size_t bfSiftWorkspaceBytes(void);
 int bfSiftReleaseWorkspace(void);

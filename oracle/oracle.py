@@ -574,6 +574,21 @@ def sift_verify_trajectory(numImages, validImages, trajectory, W, H, intrinsics,
     return int(ok), stats
 
 
+def sift_fuse_to_global(corr, keyIdx, transforms, keys, descs, numKeysPerImage, keyStride, K, maxKeys=1024):
+    """SIFTImageManager::fuseToGlobal (+ computeTracks).  corr: EntryJ structured array [C]; keyIdx [C,2] uint32 global key indices (image *
+    keyStride + key); transforms [N,4,4]; keys [N*keyStride,4] (x, y, scale, depth); descs [N*keyStride,128] uint8.  Returns (keys [n,4], descs [n,128])."""
+    L = lib()
+    corr = np.ascontiguousarray(corr); ki = np.ascontiguousarray(keyIdx, np.uint32); T = np.ascontiguousarray(transforms, np.float32)
+    kp = np.ascontiguousarray(keys, np.float32); ds = np.ascontiguousarray(descs, np.uint8); nk = np.ascontiguousarray(numKeysPerImage, np.int32)
+    Kc = np.ascontiguousarray(K, np.float32)
+    ok, od = np.zeros((maxKeys, 4), np.float32), np.zeros((maxKeys, 128), np.uint8)
+    L.orc_sift_fuse_to_global.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+    L.orc_sift_fuse_to_global.restype = C.c_int
+    n = L.orc_sift_fuse_to_global(corr.ctypes.data, ki.ctypes.data, len(corr), T.ctypes.data, len(T), kp.ctypes.data, ds.ctypes.data, nk.ctypes.data, keyStride,
+                                  Kc.ctypes.data, ok.ctypes.data, od.ctypes.data, maxKeys)
+    return ok[:n], od[:n]
+
+
 # ---- SIFT detection (oracle/sift_detect_oracle.c) -----------------------------------------------------------------------------------
 class SiftDetectParams(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depthWidth", C.c_uint32), ("depthHeight", C.c_uint32), ("depthMin", C.c_float),

@@ -13,6 +13,7 @@ def build_emulated(cu_name: str, expected_launches: int) -> C.CDLL:
     src = open(os.path.join(ROOT, "bundlefusion_b200", "csrc", cu_name)).read()
     src = src.replace('#include "bf_common.cuh"', "")
     src = re.sub(r"extern __shared__ float (\w+)\[\];", lambda m: "" if m.group(1) == "sm" else f"float* {m.group(1)} = sm;", src)      # dynamic shared memory: the shim's sm[]
+    src = re.sub(r"extern __shared__ (unsigned|int) (\w+)\[\];", lambda m: f"{m.group(1)}* {m.group(2)} = reinterpret_cast<{m.group(1)}*>(sm);", src)
     src, n = re.subn(r"(\w+(?:<\w+>)?)<<<\s*([^,]+),\s*([^,]+),\s*[^,]+,\s*[^>]+>>>\(", r"EMU_LAUNCH(\1, \2, \3, ", src)
     assert n == expected_launches, (cu_name, n)
     pre = ('#include "%s"\n' % os.path.join(ROOT, "tests", "cuda_emu", "cuda_emu.h") +

@@ -29,6 +29,9 @@
 
 struct float2 { float x, y; }; struct float4 { float x, y, z, w; }; struct int2 { int x, y; }; struct uint2 { unsigned x, y; };
 struct uchar4 { unsigned char x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; }; struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { return { x, y, z, w }; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return { x, y, z, w }; }
 static inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return { x, y, z, w }; }
 static inline float2 make_float2(float x, float y) { return { x, y }; }
 static inline float4 make_float4(float x, float y, float z, float w) { return { x, y, z, w }; }
@@ -62,6 +65,7 @@ alignas(16) inline float sm[64 * 1024];                                       //
 
 static inline void __syncthreads() { emu::g_bar.wait(); }
 static inline unsigned emu_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }      // linear id: warps are cut from it
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const unsigned o = *p; *p = o + v; return o; }
 static inline float atomicAdd(float* p, float v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const float o = *p; *p = o + v; return o; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }

@@ -24,8 +24,6 @@ F = np.float32
 
 _PRE = r'''
 #include "%(emu)s"
-struct uint4 { unsigned x, y, z, w; }; struct int4 { int x, y, z, w; };
-static inline int4 make_int4(int x, int y, int z, int w) { return { x, y, z, w }; }
 static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
