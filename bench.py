@@ -284,13 +284,15 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peaks, peak_kind = measured_peaks()
-    n_launch, n_timed, ns, U, E = int(prof[0]), int(prof[1]), int(prof[2]), int(prof[3]), int(prof[4])
-    alg_bytes = 24.0 * U + 20.0 * E + n_launch * 2.0 * W * H * 4.0            # 24 B x U + E x 20 B + 2 x W x H x 4 B per launch
+    n_launch, n_timed, ns, U, E, n_img = int(prof[0]), int(prof[1]), int(prof[2]), int(prof[3]), int(prof[4]), max(int(prof[5]), int(prof[0]))
+    # 24 B x U + 20 B x E + 2 x W x H x 4 B per frame image read (one per launch; a batch launch reads one per re-integration pair)
+    alg_bytes = 24.0 * U + 20.0 * E + n_img * 2.0 * W * H * 4.0
     ach = (alg_bytes * (n_timed / max(1, n_launch))) / max(1e-9, ns * 1e-9) / 1e9 if n_timed else 0.0
-    roof = {"kernel": "integrate_kernel<deIntegrate> (TSDF stencil)", "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"],
+    roof = {"kernel": "TSDF stencil (stencil_multi_kernel: a frame's re-integration batch in one pass; stencil_fast_kernel: single integrate)" if scene.arithmetic == "fast" else "integrate_kernel / reintegrate_kernel (bit-exact TSDF stencil)", "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"],
             "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
             "traffic": None, "launches": n_launch, "avg_launch_us": round(ns / max(1, n_timed) / 1e3, 2),
-            "algorithmic_bytes_per_launch": round(alg_bytes / max(1, n_launch)), "U_per_launch": round(U / max(1, n_launch)), "E_per_launch": round(E / max(1, n_launch))}
+            "algorithmic_bytes_per_launch": round(alg_bytes / max(1, n_launch)), "U_per_launch": round(U / max(1, n_launch)), "E_per_launch": round(E / max(1, n_launch)),
+            "frames_per_launch": round(n_img / max(1, n_launch), 2)}
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this command (profiles/), per launch
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_stencil_traffic.json")
     if os.path.exists(tpath):

@@ -11,6 +11,7 @@ BF_API void bfMat4Inverse(const float* m, float* out) { bf::mat4_inverse_hd(m, o
 namespace bf {
 int tsdf_lanes_begin(const BFHashDataStruct* hd, const BFHashParams* hp);     // tsdf.cu: two-lane replay bracket
 int tsdf_lanes_end(const BFHashDataStruct* hd);
+int tsdf_batching_usable();                                                     // tsdf.cu: batching on and fast arithmetic selected
 }
 
 static int run_ops(BFHashDataStruct* hd, BFHashParams* hp, const BFDepthCameraParams* cam, const BFTsdfOp* ops, int numOps,
@@ -31,8 +32,26 @@ static int run_ops(BFHashDataStruct* hd, BFHashParams* hp, const BFDepthCameraPa
                    const float* const* d_depthFrames, const uint8_t* const* d_colorFrames) {
     static int fuse = -1;        // BF_TSDF_FUSE_REINT=0 replays every op separately (A/B measurements)
     if (fuse < 0) { const char* e = getenv("BF_TSDF_FUSE_REINT"); fuse = (e && e[0] == '0') ? 0 : 1; }
+    const bool batch = fuse && d_colorFrames != nullptr && bf::tsdf_batching_usable() != 0;
     for (int i = 0; i < numOps; ++i) {
         const BFTsdfOp& op = ops[i];
+        if (batch) {
+            // a run of re-integration pairs (DepthSensing.cpp:867-895: up to s_maxFrameFixes of them per frame): one batch pass per <= 16 pairs
+            int n = 0;
+            while (i + 2 * n + 1 < numOps && n < 16 && ops[i + 2 * n].kind == BF_TSDF_OP_DEINTEGRATE && ops[i + 2 * n + 1].kind == BF_TSDF_OP_INTEGRATE &&
+                   ops[i + 2 * n + 1].frame == ops[i + 2 * n].frame && d_colorFrames[ops[i + 2 * n].frame] != nullptr) ++n;
+            if (n >= 2) {
+                BFTsdfReintegration pairs[16];
+                for (int k = 0; k < n; ++k) {
+                    pairs[k].frame = ops[i + 2 * k].frame;
+                    for (int e = 0; e < 16; ++e) { pairs[k].oldPose[e] = ops[i + 2 * k].pose[e]; pairs[k].newPose[e] = ops[i + 2 * k + 1].pose[e]; }
+                }
+                int rc = bfTsdfReintegrateBatch(hd, hp, cam, pairs, n, d_depthFrames, d_colorFrames);
+                if (rc) return rc;
+                i += 2 * n - 1;
+                continue;
+            }
+        }
         if (fuse && op.kind == BF_TSDF_OP_DEINTEGRATE && i + 1 < numOps && ops[i + 1].kind == BF_TSDF_OP_INTEGRATE && ops[i + 1].frame == op.frame) {
             // the reference's re-integration pair: one fused pass (bfTsdfReintegrateFrame)
             BFHashParams hpOld = *hp;

@@ -27,6 +27,7 @@
 #include "../../include/bf_tsdf.h"
 #include "bf_common.cuh"
 #include "tsdf_shared.cuh"
+#include "mat4.cuh"
 
 namespace bf {
 
@@ -64,6 +65,9 @@ struct TsdfAux {
     cudaEvent_t evFork = nullptr, evList[2] = { nullptr, nullptr }, evStencil[2] = { nullptr, nullptr };
     bool stencilPending[2] = { false, false };
     bool pipeOpen = false;
+    // batch re-integration (tsdf_reintegrate_batch): per slot the (batch id << 8 | op index) of the alloc launch that inserted the block,
+    // per work item the 2-bit-per-op frustum mask
+    unsigned* slotEpoch = nullptr; unsigned* workMask = nullptr; unsigned batchId = 0;
     const void* owner[3] = { nullptr, nullptr, nullptr };   // the caller's d_SDFBlocks / d_heap / d_hashCompactified: the key (d_hash) can be
                                                             // recycled by an allocator for another table; all four together identify one
 };
@@ -73,6 +77,7 @@ static bool g_profile = false;
 static std::vector<cudaEvent_t> g_evStart, g_evStop;
 static size_t g_evUsed = 0;
 static unsigned long long g_profLaunches = 0;
+static unsigned long long g_profFrames = 0;      // frame images the profiled stencil launches read (a batch launch reads one per pair)
 static const size_t kMaxProfiledLaunches = 16384;
 
 static std::mutex g_auxMutex;
@@ -135,12 +140,15 @@ __device__ __forceinline__ F3 depth_to_skeleton(const BFDepthCameraParams& cp, u
     return r;
 }
 // DepthCameraUtil.h:95-107,137-144 + VoxelUtilHashSDF.h:322-326
+__device__ __forceinline__ bool block_in_frustum_m(float vs, const BFFloat4x4& Minv, const BFDepthCameraParams& cp, I3 b);
 __device__ __forceinline__ bool block_in_frustum(const BFHashParams& hp, const BFDepthCameraParams& cp, I3 b) {
-    const float vs = hp.m_virtualVoxelSize;
+    return block_in_frustum_m(hp.m_virtualVoxelSize, hp.m_rigidTransformInverse, cp, b);
+}
+__device__ __forceinline__ bool block_in_frustum_m(float vs, const BFFloat4x4& Minv, const BFDepthCameraParams& cp, I3 b) {
     const float off = vs * 0.5f * ((float)BF_SDF_BLOCK_SIZE - 1.0f);
     const F3 w = { __fmaf_rn((float)(b.x * BF_SDF_BLOCK_SIZE), vs, off), __fmaf_rn((float)(b.y * BF_SDF_BLOCK_SIZE), vs, off),
                    __fmaf_rn((float)(b.z * BF_SDF_BLOCK_SIZE), vs, off) };
-    F3 pc = xform(hp.m_rigidTransformInverse, w);
+    F3 pc = xform(Minv, w);
     const float px = pc.x * cp.fx / pc.z + cp.mx;
     const float py = pc.y * cp.fy / pc.z + cp.my;
     const float w1 = (float)cp.m_imageWidth - 1.0f, h1 = (float)cp.m_imageHeight - 1.0f;
@@ -212,7 +220,10 @@ __device__ __forceinline__ void write_entry(BFHashEntry* e, I3 p, unsigned offse
 // Insert `pos` (VoxelUtilHashSDF.h:549-655 semantics: bucket slot first, else splice into the
 // bucket's overflow list).  Unlike the reference (try-lock, give up, host retries) this spins
 // until the block is present, so one launch reaches the reference's fixed point.
-__device__ void alloc_block(const BFHashDataStruct& hd, const BFHashParams& hp, int4* slotInfo, unsigned* ctrs, I3 pos) {
+// slotEpoch / tag (optional): batch re-integration -- a block inserted by THIS launch is tagged with (batch id << 8 | op index), so that the
+// multi-op stencil can tell which operations of the batch saw the block exist (tsdf_reintegrate_batch)
+struct AllocEpoch { unsigned* slotEpoch; unsigned tag; };
+__device__ void alloc_block(const BFHashDataStruct& hd, const BFHashParams& hp, int4* slotInfo, unsigned* ctrs, I3 pos, AllocEpoch ep = AllocEpoch{nullptr, 0u}) {
     const unsigned h = hash_pos(hp.m_hashNumBuckets, pos);
     if (find_entry<false>(hd.d_hash, hp, pos, h) >= 0) return;      // fast path, no lock
 
@@ -239,6 +250,7 @@ __device__ void alloc_block(const BFHashDataStruct& hd, const BFHashParams& hp, 
                 unsigned slot;
                 if (heap_pop(hd.d_heap, hd.d_heapCounter, &slot)) {
                     slotInfo[slot] = make_int4(pos.x, pos.y, pos.z, firstEmpty);
+                    if (ep.slotEpoch) ep.slotEpoch[slot] = ep.tag;
                     atomicMax(&ctrs[CTR_HIGH_WATER], slot + 1u);
                     write_entry(&hd.d_hash[firstEmpty], pos, BF_NO_OFFSET, (int)(slot * BF_SDF_BLOCK_VOXELS));
                 } else {
@@ -265,6 +277,7 @@ __device__ void alloc_block(const BFHashDataStruct& hd, const BFHashParams& hp, 
                         if (heap_pop(hd.d_heap, hd.d_heapCounter, &slot)) {
                             const unsigned lastOffset = (unsigned)__ldcg(reinterpret_cast<const int*>(&hd.d_hash[last]) + 4);
                             slotInfo[slot] = make_int4(pos.x, pos.y, pos.z, (int)i);
+                            if (ep.slotEpoch) ep.slotEpoch[slot] = ep.tag;
                             atomicMax(&ctrs[CTR_HIGH_WATER], slot + 1u);
                             write_entry(&hd.d_hash[i], pos, lastOffset, (int)(slot * BF_SDF_BLOCK_VOXELS));
                             __threadfence();
@@ -496,12 +509,12 @@ __device__ __forceinline__ bool dda_step(DDA& s, int& axis) {
 }
 // the reference's single-phase walk: every visited in-frustum block goes straight to the table (rare fallback)
 __device__ __noinline__ void alloc_pixel_direct(const BFHashDataStruct& hd, const BFHashParams& hp, const BFDepthCameraParams& cp,
-                                                const float* __restrict__ depth, unsigned x, unsigned y, int4* slotInfo, unsigned* ctrs) {
+                                                const float* __restrict__ depth, unsigned x, unsigned y, int4* slotInfo, unsigned* ctrs, AllocEpoch ep) {
     DDA s;
     if (!dda_setup(hp, cp, depth, x, y, s)) return;
 #pragma unroll 1
     for (unsigned iter = 0; iter < 1024; ++iter) {
-        if (block_in_frustum(hp, cp, s.cur) && owns_block(hp, s.cur)) alloc_block(hd, hp, slotInfo, ctrs, s.cur);
+        if (block_in_frustum(hp, cp, s.cur) && owns_block(hp, s.cur)) alloc_block(hd, hp, slotInfo, ctrs, s.cur, ep);
         int axis;
         if (!dda_step(s, axis)) return;
     }
@@ -509,7 +522,7 @@ __device__ __noinline__ void alloc_pixel_direct(const BFHashDataStruct& hd, cons
 
 __global__ void __launch_bounds__(256, 8)    // 32 regs: the whole 640x480 frame is resident in one wave
 alloc_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const __grid_constant__ BFDepthCameraParams cp,
-             const float* __restrict__ depth, int4* slotInfo, unsigned* ctrs, float2* tiles, int zeroSet) {
+             const float* __restrict__ depth, int4* slotInfo, unsigned* ctrs, float2* tiles, int zeroSet, AllocEpoch ep) {
     __shared__ unsigned long long sSet[BF_ALLOC_SET];
     __shared__ float2 sRed[8];
     const unsigned tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -571,9 +584,9 @@ alloc_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, const
         const unsigned long long key = sSet[i];
         if (key == 0ull) continue;
         const I3 b = unpack_block_key(key);
-        if (block_in_frustum(hp, cp, b) && owns_block(hp, b)) alloc_block(hd, hp, slotInfo, ctrs, b);
+        if (block_in_frustum(hp, cp, b) && owns_block(hp, b)) alloc_block(hd, hp, slotInfo, ctrs, b, ep);
     }
-    if (needDirect) alloc_pixel_direct(hd, hp, cp, depth, x, y, slotInfo, ctrs);   // set overflow / coordinates out of key range
+    if (needDirect) alloc_pixel_direct(hd, hp, cp, depth, x, y, slotInfo, ctrs, ep);   // set overflow / coordinates out of key range
 }
 
 // compactify: list of allocated AND in-frustum blocks (CUDASceneRepHashSDF.cu:324-366),
@@ -1035,6 +1048,66 @@ compactify_dual_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams
     }
 }
 
+// ---- batch re-integration: ONE list for up to BF_MULTI_MAX_OPS (de-integrate old pose, integrate new pose) pairs ---------------------------
+// The reference replays the pairs one after the other (FL/DepthSensing/DepthSensing.cpp:867-895), each with its own alloc / compactify /
+// kernel launches.  Here the allocs of all pairs run first (each tags the blocks IT inserts with its op index), then this kernel builds
+// one union list: per allocated block the 2-bit-per-op mask {in the old pose's frustum, in the new pose's frustum} for the ops that saw
+// the block exist (op index >= the block's tag; a block inserted by op j's alloc does not exist for ops < j in the reference's order),
+// and the multi-op stencil (tsdf_fast.cu) applies the ops to each voxel in order, in registers: one voxel read and write for the batch.
+struct MultiFrusta { int nOps; float voxelSize; BFFloat4x4 inv[2 * BF_MULTI_MAX_OPS]; };     // inv[2k] = old pose of op k (inverse), inv[2k+1] = new
+__global__ void __launch_bounds__(256)
+compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta fr, const __grid_constant__ BFDepthCameraParams cp,
+                        const int4* __restrict__ slotInfo, const unsigned* __restrict__ slotEpoch, unsigned batchId, unsigned* ctrs, int set,
+                        unsigned char* __restrict__ listFlags, int4* __restrict__ work, unsigned* __restrict__ workMask) {
+    const unsigned highWater = ctrs[CTR_HIGH_WATER];
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned lane = threadIdx.x & 31;
+    for (unsigned base = tid - lane; base < highWater; base += stride) {
+        const unsigned slot = base + lane;
+        unsigned mask = 0;
+        int4 info = make_int4(0, 0, 0, -1);
+        if (slot < highWater) {
+            info = __ldcg(&slotInfo[slot]);
+            if (info.w >= 0) {
+                const I3 b = { info.x, info.y, info.z };
+                const unsigned e = __ldcg(&slotEpoch[slot]);
+                const int first = ((e >> 8) == batchId) ? (int)(e & 0xffu) : 0;
+                for (int k = first; k < fr.nOps; ++k) {
+                    if (block_in_frustum_m(fr.voxelSize, fr.inv[2 * k], cp, b)) mask |= 1u << (2 * k);
+                    if (block_in_frustum_m(fr.voxelSize, fr.inv[2 * k + 1], cp, b)) mask |= 2u << (2 * k);
+                }
+            }
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, mask != 0);
+        if (ballot) {
+            // E of the batch = sum over ops of the blocks in either frustum = what the per-op lists would have held
+            unsigned nE = 0;
+            for (int k = 0; k < fr.nOps; ++k) nE += ((mask >> (2 * k)) & 1u) + ((mask >> (2 * k + 1)) & 1u);
+            for (int o = 16; o > 0; o >>= 1) nE += __shfl_xor_sync(0xffffffffu, nE, o);
+            unsigned warpBase = 0;
+            if (lane == 0) {
+                warpBase = atomicAdd(&ctrs[set + SET_COUNT], __popc(ballot));
+                atomicAdd(&ctrs[set + SET_WORK], __popc(ballot));
+                atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_E_TOT_LO]), (unsigned long long)nE);
+            }
+            warpBase = __shfl_sync(0xffffffffu, warpBase, 0);
+            if (mask) {
+                const unsigned k = warpBase + __popc(ballot & ((1u << lane) - 1u));
+                BFHashEntry en;
+                en.pos[0] = info.x; en.pos[1] = info.y; en.pos[2] = info.z;
+                en.ptr = (int)(slot * BF_SDF_BLOCK_VOXELS);
+                en.offset = hd.d_hash[info.w].offset;
+                hd.d_hashCompactified[k] = en;
+                // the reference's GC walks the list of the LAST integrate (DepthSensing.cpp:901): bit 1 = in the last op's new-pose frustum
+                listFlags[k] = (unsigned char)(((mask >> (2 * (fr.nOps - 1))) & 2u) | 1u);
+                work[k] = make_int4(info.x, info.y, info.z, (int)slot);
+                workMask[k] = mask;
+            }
+        }
+    }
+}
+
 // truncation test of one voxel against one pose; returns true and the clamped sdf / colour when it passes (.cu:433-463)
 __device__ __forceinline__ bool probe_voxel(const BFHashParams& hp, const BFDepthCameraParams& cp, const float* __restrict__ depthImg,
                                             const uchar4* __restrict__ colorImg, F3 world, float Wf, float Hf, float& sdfOut, uchar4& colOut) {
@@ -1286,6 +1359,7 @@ gc_live_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, con
 // ------------------------------------------------------------------------------------------
 static void free_aux(TsdfAux& a) {
     cudaFree(a.slotInfo); cudaFree(a.ctrs); cudaFree(a.live); cudaFree(a.listFlags); cudaFree(a.work2[0]); cudaFree(a.work2[1]); cudaFree(a.tiles);
+    cudaFree(a.slotEpoch); cudaFree(a.workMask);
     if (a.lane) cudaStreamDestroy(a.lane);
     if (a.evFork) cudaEventDestroy(a.evFork);
     for (int k = 0; k < 2; ++k) { if (a.evList[k]) cudaEventDestroy(a.evList[k]); if (a.evStencil[k]) cudaEventDestroy(a.evStencil[k]); }
@@ -1399,14 +1473,15 @@ static int join_lanes(TsdfAux* aux) {
 // withTiles: also leave the depth-tile min/max for the stencil's block cull (library sequences only; the reference-named
 // allocCUDA stub has no say over what is integrated afterwards).  zeroParity >= 0: the launch also zeroes that counter set
 // (the one the following compactify fills).
-static int do_alloc(BFHashDataStruct* hd, const BFHashParams* hp, const float* depth, const BFDepthCameraParams* cp, TsdfAux* aux, bool withTiles, int zeroParity) {
+static int do_alloc(BFHashDataStruct* hd, const BFHashParams* hp, const float* depth, const BFDepthCameraParams* cp, TsdfAux* aux, bool withTiles, int zeroParity,
+                    AllocEpoch ep = AllocEpoch{nullptr, 0u}) {
     dim3 block(BF_TILE, BF_TILE);
     dim3 grid((cp->m_imageWidth + block.x - 1) / block.x, (cp->m_imageHeight + block.y - 1) / block.y);
     if (withTiles) { int rc = ensure_tiles(aux, cp); if (rc) return rc; }
     if (zeroParity >= 0) { int rc = front_acquire_set(aux, (unsigned)zeroParity); if (rc) return rc; }
     ++g_launchCount;
     alloc_kernel<<<grid, block, 0, g_stream>>>(*hd, *hp, *cp, depth, aux->slotInfo, aux->ctrs, withTiles ? aux->tiles : nullptr,
-                                               zeroParity >= 0 ? set_of((unsigned)zeroParity) : -1);
+                                               zeroParity >= 0 ? set_of((unsigned)zeroParity) : -1, ep);
     BF_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1469,7 +1544,7 @@ static int do_integrate(BFHashDataStruct* hd, const BFHashParams* hp, const BFDe
     const cudaStream_t sb = back_lane(aux);
     int rc = stencil_begin(aux); if (rc) return rc;
     const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
-    if (g_profile) ++g_profLaunches;
+    if (g_profile) { ++g_profLaunches; ++g_profFrames; }
     if (timeIt) {
         if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
         BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], sb));
@@ -1586,7 +1661,7 @@ BF_API int bfTsdfReintegrateFrame(BFHashDataStruct* hd, const BFHashParams* hpOl
     const cudaStream_t sb = back_lane(aux);
     rc = stencil_begin(aux); if (rc) return rc;
     const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
-    if (g_profile) ++g_profLaunches;
+    if (g_profile) { ++g_profLaunches; ++g_profFrames; }
     if (timeIt) {
         if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
         BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], sb));
@@ -1604,6 +1679,76 @@ BF_API int bfTsdfReintegrateFrame(BFHashDataStruct* hd, const BFHashParams* hpOl
     if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], sb)); ++g_evUsed; }
     return stencil_end(aux);
 }
+
+// Up to BF_MULTI_MAX_OPS re-integration pairs {deIntegrate(frame f, old pose); integrate(frame f, new pose)} -- the loop body of
+// FL/DepthSensing/DepthSensing.cpp:867-895, replayed as: n alloc launches (op-tagged inserts), ONE union list, ONE stencil pass in which
+// every voxel of the list is read once, taken through the n pairs in order in registers, and written once.  Fast arithmetic only (the
+// bit-exact kernels keep the one-pair-per-pass path); voxels are bit-identical to the one-pair-per-pass fast path (same probe expression,
+// same per-voxel op order, blocks invisible to the ops that precede their insertion).  hp: pose-independent parameters; on return it holds
+// the last new pose, as after the reference's last integrate.
+static int g_batching = -1;
+static bool batching_on() {
+    if (g_batching < 0) { const char* e = getenv("BF_TSDF_BATCH"); g_batching = (e && e[0] == '0') ? 0 : 1; }
+    return g_batching == 1;
+}
+BF_API int bfTsdfSetBatching(int enable) { const int prev = batching_on() ? 1 : 0; g_batching = enable ? 1 : 0; return prev; }
+
+BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const BFDepthCameraParams* cp, const BFTsdfReintegration* pairs, int numPairs,
+                                  const float* const* d_depthFrames, const uint8_t* const* d_colorFrames) {
+    if (numPairs < 1 || numPairs > BF_MULTI_MAX_OPS || !d_colorFrames) return (int)cudaErrorInvalidValue;
+    TsdfAux* aux;
+    int rc = get_aux(hd, hp, &aux, true);
+    if (rc) return rc;
+    if (aux->work == nullptr) return (int)cudaErrorNotSupported;
+    if (!aux->slotEpoch) {
+        BF_CHECK(cudaMalloc(&aux->slotEpoch, sizeof(unsigned) * (size_t)aux->numSlots));
+        BF_CHECK(cudaMalloc(&aux->workMask, sizeof(unsigned) * (size_t)aux->numSlots));
+        BF_CHECK(cudaMemsetAsync(aux->slotEpoch, 0, sizeof(unsigned) * (size_t)aux->numSlots, g_stream));
+        aux->batchId = 0;
+    }
+    rc = join_lanes(aux); if (rc) return rc;            // the batch runs on the caller's stream, after every stencil in flight
+    aux->batchId = (aux->batchId + 1u) & 0x00FFFFFFu;
+    if (aux->batchId == 0) { BF_CHECK(cudaMemsetAsync(aux->slotEpoch, 0, sizeof(unsigned) * (size_t)aux->numSlots, g_stream)); aux->batchId = 1; }
+    static BFHashParams hpOld[BF_MULTI_MAX_OPS], hpNew[BF_MULTI_MAX_OPS];
+    static MultiFrusta fr;
+    BFMultiOpDesc desc[BF_MULTI_MAX_OPS];
+    fr.nOps = numPairs; fr.voxelSize = hp->m_virtualVoxelSize;
+    const unsigned newParity = aux->parity ^ 1u;
+    for (int k = 0; k < numPairs; ++k) {
+        hpOld[k] = *hp; hpNew[k] = *hp;
+        for (int e = 0; e < 16; ++e) { hpOld[k].m_rigidTransform.m[e] = pairs[k].oldPose[e]; hpNew[k].m_rigidTransform.m[e] = pairs[k].newPose[e]; }
+        mat4_inverse_hd(pairs[k].oldPose, hpOld[k].m_rigidTransformInverse.m);
+        mat4_inverse_hd(pairs[k].newPose, hpNew[k].m_rigidTransformInverse.m);
+        fr.inv[2 * k] = hpOld[k].m_rigidTransformInverse; fr.inv[2 * k + 1] = hpNew[k].m_rigidTransformInverse;
+        desc[k].hpOld = &hpOld[k]; desc[k].hpNew = &hpNew[k];
+        desc[k].depth = d_depthFrames[pairs[k].frame]; desc[k].color = d_colorFrames[pairs[k].frame];
+        if (!desc[k].color || !desc[k].depth) return (int)cudaErrorInvalidValue;
+        // the first alloc launch also zeroes the counter set the list is about to use
+        rc = do_alloc(hd, &hpNew[k], desc[k].depth, cp, aux, false, k == 0 ? (int)newParity : -1, AllocEpoch{aux->slotEpoch, (aux->batchId << 8) | (unsigned)k});
+        if (rc) return rc;
+    }
+    aux->parity = newParity;
+    aux->lastListDual = true;
+    const int set = set_of(aux->parity);
+    ++g_launchCount;
+    compactify_multi_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, fr, *cp, aux->slotInfo, aux->slotEpoch, aux->batchId, aux->ctrs, set,
+                                                                                                 aux->listFlags, aux->work2[aux->parity], aux->workMask);
+    BF_CHECK(cudaGetLastError());
+    const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
+    if (g_profile) { ++g_profLaunches; g_profFrames += (unsigned long long)numPairs; }
+    if (timeIt) {
+        if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
+        BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], g_stream));
+    }
+    ++g_launchCount;
+    rc = launch_reintegrate_multi_fast(hd, desc, numPairs, cp, aux->work2[aux->parity], aux->workMask, set, aux->ctrs, aux->live,
+                                       grid_for(hp->m_numSDFBlocks, fast_stencil_ctas_per_sm(true)), g_stream);
+    if (rc) return rc;
+    if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], g_stream)); ++g_evUsed; }
+    *hp = hpNew[numPairs - 1];
+    return 0;
+}
+namespace bf { int tsdf_batching_usable() { return (batching_on() && arith_fast()) ? 1 : 0; } }
 
 BF_API int bfTsdfGarbageCollect(BFHashDataStruct* hd, const BFHashParams* hp) {
     TsdfAux* aux;
@@ -1652,7 +1797,7 @@ BF_API unsigned long long bfGetLaunchCount(void) { return g_launchCount; }
 
 BF_API int bfTsdfSetProfiling(int enable) {
     g_profile = enable != 0;
-    g_evUsed = 0; g_profLaunches = 0;
+    g_evUsed = 0; g_profLaunches = 0; g_profFrames = 0;
     std::lock_guard<std::mutex> lk(g_auxMutex);
     for (auto& kv : g_aux) BF_CHECK(cudaMemsetAsync(kv.second.ctrs + CTR_U_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));   // restart the U / E sums
     return 0;
@@ -1672,10 +1817,11 @@ BF_API int bfTsdfGetProfile(const BFHashDataStruct* hd, unsigned long long out[8
     out[0] = g_profLaunches; out[1] = g_evUsed; out[2] = (unsigned long long)(ms * 1e6);
     out[3] = ((unsigned long long)c[CTR_U_TOT_HI] << 32) | c[CTR_U_TOT_LO];
     out[4] = ((unsigned long long)c[CTR_E_TOT_HI] << 32) | c[CTR_E_TOT_LO];
-    out[5] = out[6] = out[7] = 0;
+    out[5] = g_profFrames;          // frame images read by those launches (a batch launch reads one per re-integration pair)
+    out[6] = out[7] = 0;
     // restart accumulation
     BF_CHECK(cudaMemsetAsync(aux->ctrs + CTR_U_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
-    g_evUsed = 0; g_profLaunches = 0;
+    g_evUsed = 0; g_profLaunches = 0; g_profFrames = 0;
     return 0;
 }
 

@@ -28,12 +28,20 @@ struct FastPose {
     float cx[4], cy[4], cz[4];       // camera-space x, y, z of a voxel = c[0] vx + c[1] vy + c[2] vz + c[3]   (rows of Tinv * diag(voxelSize))
     float maxDist, trunc0, truncScale, wMax;
 };
+struct FastCam { unsigned W, H; float fx, fy, mx5, my5; };     // mx + 0.5, my + 0.5: the reference's int(proj + 0.5)
 struct FastArgs {
     BFVoxel* blocks; const BFHashEntry* list; int* listCounterOut; const int4* work;
     const float* depth; const uchar4* color; unsigned* ctrs; int* live;
-    unsigned W, H; int set; int useListCount; unsigned countOverride;
-    float fx, fy, mx5, my5;          // mx + 0.5, my + 0.5: the reference's int(proj + 0.5)
+    int set; int useListCount; unsigned countOverride;
+    FastCam cam;
     FastPose A, B;                   // MODE 0 / 1: A.  MODE 2: A = old pose (de-integrated), B = new pose (integrated)
+};
+struct MultiOp { FastPose A, B; const float* depth; const unsigned* color; };
+struct MultiArgs {
+    BFVoxel* blocks; const int4* work; const unsigned* workMask; unsigned* ctrs; int* live; int* listCounterOut;
+    int set; int nOps;
+    FastCam cam;
+    MultiOp ops[BF_MULTI_MAX_OPS];
 };
 
 // resident CTAs per SM the kernels are compiled for: the fused pass keeps two poses' probe sets live (<= 64 registers), the others 48
@@ -64,7 +72,12 @@ struct ProbeSet {
     unsigned idx[4];       // pixel index, or 0xFFFFFFFF when the voxel projects outside the image
     unsigned mask;         // bit k: voxel k passes the truncation test
 };
-__device__ __forceinline__ void project4(const FastArgs& a, const FastPose& p, float X, float Y, float Z, ProbeSet& ps, float (&z)[4]) {
+// (vx, vy, vz): integer voxel coordinates of the thread's first voxel, as floats.  Every fast kernel evaluates the SAME expression here, so a
+// voxel's pass / fail decision for a given (pose, frame) is the same bit for bit whichever kernel asks (integrate now, de-integrate later in a batch)
+__device__ __forceinline__ void project4(const FastCam& a, const float* __restrict__ depth, const FastPose& p, float vx, float vy, float vz, ProbeSet& ps, float (&z)[4]) {
+    const float X = fmaf(vx, p.cx[0], fmaf(vy, p.cx[1], fmaf(vz, p.cx[2], p.cx[3])));
+    const float Y = fmaf(vx, p.cy[0], fmaf(vy, p.cy[1], fmaf(vz, p.cy[2], p.cy[3])));
+    const float Z = fmaf(vx, p.cz[0], fmaf(vy, p.cz[1], fmaf(vz, p.cz[2], p.cz[3])));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const float Xk = fmaf((float)k, p.cx[0], X), Yk = fmaf((float)k, p.cy[0], Y), Zk = fmaf((float)k, p.cz[0], Z);
@@ -74,7 +87,7 @@ __device__ __forceinline__ void project4(const FastArgs& a, const FastPose& p, f
         const bool on = (ix < a.W) & (iy < a.H);
         ps.idx[k] = on ? iy * a.W + ix : 0xFFFFFFFFu;
         z[k] = Zk;
-        ps.sdf[k] = __ldg(&a.depth[on ? iy * a.W + ix : 0u]);            // unconditional load from a safe address; holds the DEPTH until decide()
+        ps.sdf[k] = __ldg(&depth[on ? iy * a.W + ix : 0u]);              // unconditional load from a safe address; holds the DEPTH until decide()
     }
 }
 // truncation test (.cu:433-463 without the identity clamp): depth valid, below the integration distance, |depth - z| < truncation(depth)
@@ -136,34 +149,43 @@ __device__ __forceinline__ void deintegrate_fast(float sdf, unsigned col, unsign
 }
 
 template <int MODE>
-__device__ __forceinline__ void update_fast(const FastArgs& a, bool passA, float sdfA, unsigned colA, bool passB, float sdfB, unsigned colB,
+__device__ __forceinline__ void update_fast(const FastPose& pA, const FastPose& pB, bool passA, float sdfA, unsigned colA, bool passB, float sdfB, unsigned colB,
                                             unsigned& wSdf, unsigned& wWeight, unsigned& wColor, int& liveDelta) {
     const bool wasLive = __uint_as_float(wWeight) > 0.0f;
-    if (MODE == 0) { integrate_fast(a.A, sdfA, colA, wSdf, wWeight, wColor); }
+    if (MODE == 0) { integrate_fast(pA, sdfA, colA, wSdf, wWeight, wColor); }
     else if (MODE == 1) { deintegrate_fast(sdfA, colA, wSdf, wWeight, wColor); }
     else {
         if (passA) deintegrate_fast(sdfA, colA, wSdf, wWeight, wColor);
-        if (passB) integrate_fast(a.B, sdfB, colB, wSdf, wWeight, wColor);
+        if (passB) integrate_fast(pB, sdfB, colB, wSdf, wWeight, wColor);
     }
     liveDelta += (int)(__uint_as_float(wWeight) > 0.0f) - (int)wasLive;
 }
 
-struct ThreadOffsets { float ax, ay, az, bx, by, bz; };
+struct ThreadVoxel { int lx, ly, lz; };          // this thread's first voxel inside a block: i = 4t -> x = (4t) % 8, y = (4t % 64) / 8, z = 4t / 64
+
+__device__ __forceinline__ void live_delta_commit(int* live, unsigned slot, unsigned t, int liveDelta) {
+    // live-voxel bookkeeping for the O(E) garbage collection: one RED per warp, only when a weight crossed zero
+#ifdef BF_EMU_SEQUENTIAL
+    if (liveDelta != 0) atomicAdd(&live[slot], liveDelta);
+#else
+    if (__any_sync(0xffffffffu, liveDelta != 0)) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) liveDelta += __shfl_xor_sync(0xffffffffu, liveDelta, s);
+        if ((t & 31) == 0 && liveDelta != 0) atomicAdd(&live[slot], liveDelta);
+    }
+#endif
+}
 
 // one SDF block: 128 threads, 4 x-consecutive voxels (48 B = three 16-byte vectors) per thread
 template <int MODE>
-__device__ __forceinline__ void process_block(const FastArgs& a, const ThreadOffsets& o, unsigned t, int bx, int by, int bz, unsigned ptr, unsigned fl, unsigned& passed) {
-    const float fbx = (float)(bx * BF_SDF_BLOCK_SIZE), fby = (float)(by * BF_SDF_BLOCK_SIZE), fbz = (float)(bz * BF_SDF_BLOCK_SIZE);
+__device__ __forceinline__ void process_block(const FastArgs& a, const ThreadVoxel& o, unsigned t, int bx, int by, int bz, unsigned ptr, unsigned fl, unsigned& passed) {
+    const float vx = (float)(bx * BF_SDF_BLOCK_SIZE + o.lx), vy = (float)(by * BF_SDF_BLOCK_SIZE + o.ly), vz = (float)(bz * BF_SDF_BLOCK_SIZE + o.lz);
     ProbeSet pA, pB;
     float zA[4], zB[4];
     pA.mask = 0; pB.mask = 0;
     if (a.color == nullptr) return;                        // without colour nothing passes (.cu:441-448)
-    if (fl & 1u)
-        project4(a, a.A, fmaf(fbx, a.A.cx[0], fmaf(fby, a.A.cx[1], fmaf(fbz, a.A.cx[2], o.ax))), fmaf(fbx, a.A.cy[0], fmaf(fby, a.A.cy[1], fmaf(fbz, a.A.cy[2], o.ay))),
-                 fmaf(fbx, a.A.cz[0], fmaf(fby, a.A.cz[1], fmaf(fbz, a.A.cz[2], o.az))), pA, zA);
-    if (MODE == 2 && (fl & 2u))
-        project4(a, a.B, fmaf(fbx, a.B.cx[0], fmaf(fby, a.B.cx[1], fmaf(fbz, a.B.cx[2], o.bx))), fmaf(fbx, a.B.cy[0], fmaf(fby, a.B.cy[1], fmaf(fbz, a.B.cy[2], o.by))),
-                 fmaf(fbx, a.B.cz[0], fmaf(fby, a.B.cz[1], fmaf(fbz, a.B.cz[2], o.bz))), pB, zB);
+    if (fl & 1u) project4(a.cam, a.depth, a.A, vx, vy, vz, pA, zA);
+    if (MODE == 2 && (fl & 2u)) project4(a.cam, a.depth, a.B, vx, vy, vz, pB, zB);
     if (fl & 1u) decide4(a.A, pA, zA);
     if (MODE == 2 && (fl & 2u)) decide4(a.B, pB, zB);
     const unsigned mask = pA.mask | pB.mask;
@@ -180,25 +202,59 @@ __device__ __forceinline__ void process_block(const FastArgs& a, const ThreadOff
         uint4* const vp = reinterpret_cast<uint4*>(a.blocks + (size_t)ptr) + 3 * t;      // 48 B per thread, 16-B aligned
         uint4 qa = vp[0], qb = vp[1], qc = vp[2];
         // 4 voxels = 12 words: v0{a.x,a.y,a.z} v1{a.w,b.x,b.y} v2{b.z,b.w,c.x} v3{c.y,c.z,c.w}
-        if (mask & 1u) update_fast<MODE>(a, pA.mask & 1u, pA.sdf[0], cA[0], pB.mask & 1u, pB.sdf[0], cB[0], qa.x, qa.y, qa.z, liveDelta);
-        if (mask & 2u) update_fast<MODE>(a, pA.mask & 2u, pA.sdf[1], cA[1], pB.mask & 2u, pB.sdf[1], cB[1], qa.w, qb.x, qb.y, liveDelta);
-        if (mask & 4u) update_fast<MODE>(a, pA.mask & 4u, pA.sdf[2], cA[2], pB.mask & 4u, pB.sdf[2], cB[2], qb.z, qb.w, qc.x, liveDelta);
-        if (mask & 8u) update_fast<MODE>(a, pA.mask & 8u, pA.sdf[3], cA[3], pB.mask & 8u, pB.sdf[3], cB[3], qc.y, qc.z, qc.w, liveDelta);
+        if (mask & 1u) update_fast<MODE>(a.A, a.B, pA.mask & 1u, pA.sdf[0], cA[0], pB.mask & 1u, pB.sdf[0], cB[0], qa.x, qa.y, qa.z, liveDelta);
+        if (mask & 2u) update_fast<MODE>(a.A, a.B, pA.mask & 2u, pA.sdf[1], cA[1], pB.mask & 2u, pB.sdf[1], cB[1], qa.w, qb.x, qb.y, liveDelta);
+        if (mask & 4u) update_fast<MODE>(a.A, a.B, pA.mask & 4u, pA.sdf[2], cA[2], pB.mask & 4u, pB.sdf[2], cB[2], qb.z, qb.w, qc.x, liveDelta);
+        if (mask & 8u) update_fast<MODE>(a.A, a.B, pA.mask & 8u, pA.sdf[3], cA[3], pB.mask & 8u, pB.sdf[3], cB[3], qc.y, qc.z, qc.w, liveDelta);
         if (mask & 0x3u) vp[0] = qa;                      // only the 16-byte pieces that hold an updated voxel
         if (mask & 0x6u) vp[1] = qb;
         if (mask & 0xCu) vp[2] = qc;
         passed += __popc(pA.mask) + __popc(pB.mask);
     }
-    // live-voxel bookkeeping for the O(E) garbage collection: one RED per warp, only when a weight crossed zero
-#ifdef BF_EMU_SEQUENTIAL
-    if (liveDelta != 0) atomicAdd(&a.live[ptr / BF_SDF_BLOCK_VOXELS], liveDelta);
-#else
-    if (__any_sync(0xffffffffu, liveDelta != 0)) {
+    live_delta_commit(a.live, ptr / BF_SDF_BLOCK_VOXELS, t, liveDelta);
+}
+
+// one SDF block of a batch: the ops whose mask bits are set are applied in order to the voxel quad held in registers
+__device__ __forceinline__ void process_block_multi(const MultiArgs& a, const ThreadVoxel& o, unsigned t, int4 w, unsigned opMask, unsigned& passed) {
+    const float vx = (float)(w.x * BF_SDF_BLOCK_SIZE + o.lx), vy = (float)(w.y * BF_SDF_BLOCK_SIZE + o.ly), vz = (float)(w.z * BF_SDF_BLOCK_SIZE + o.lz);
+    uint4* const vp = reinterpret_cast<uint4*>(a.blocks + (size_t)(unsigned)w.w * BF_SDF_BLOCK_VOXELS) + 3 * t;
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa, qc = qa;
+    bool loaded = false;
+    unsigned dirty = 0;
+    int liveDelta = 0;
+#pragma unroll 1
+    for (int k = 0; k < a.nOps; ++k) {
+        const unsigned fl = (opMask >> (2 * k)) & 3u;
+        if (!fl) continue;                                   // uniform for the CTA
+        const MultiOp& op = a.ops[k];
+        ProbeSet pA, pB;
+        float zA[4], zB[4];
+        pA.mask = 0; pB.mask = 0;
+        if (fl & 1u) project4(a.cam, op.depth, op.A, vx, vy, vz, pA, zA);
+        if (fl & 2u) project4(a.cam, op.depth, op.B, vx, vy, vz, pB, zB);
+        if (fl & 1u) decide4(op.A, pA, zA);
+        if (fl & 2u) decide4(op.B, pB, zB);
+        const unsigned mask = pA.mask | pB.mask;
+        if (mask) {
+            unsigned cA[4], cB[4];
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) liveDelta += __shfl_xor_sync(0xffffffffu, liveDelta, s);
-        if ((t & 31) == 0 && liveDelta != 0) atomicAdd(&a.live[ptr / BF_SDF_BLOCK_VOXELS], liveDelta);
+            for (int j = 0; j < 4; ++j) {
+                cA[j] = __ldg(&op.color[(pA.mask >> j) & 1u ? pA.idx[j] : 0u]);
+                cB[j] = __ldg(&op.color[(pB.mask >> j) & 1u ? pB.idx[j] : 0u]);
+            }
+            if (!loaded) { qa = vp[0]; qb = vp[1]; qc = vp[2]; loaded = true; }
+            if (mask & 1u) update_fast<2>(op.A, op.B, pA.mask & 1u, pA.sdf[0], cA[0], pB.mask & 1u, pB.sdf[0], cB[0], qa.x, qa.y, qa.z, liveDelta);
+            if (mask & 2u) update_fast<2>(op.A, op.B, pA.mask & 2u, pA.sdf[1], cA[1], pB.mask & 2u, pB.sdf[1], cB[1], qa.w, qb.x, qb.y, liveDelta);
+            if (mask & 4u) update_fast<2>(op.A, op.B, pA.mask & 4u, pA.sdf[2], cA[2], pB.mask & 4u, pB.sdf[2], cB[2], qb.z, qb.w, qc.x, liveDelta);
+            if (mask & 8u) update_fast<2>(op.A, op.B, pA.mask & 8u, pA.sdf[3], cA[3], pB.mask & 8u, pB.sdf[3], cB[3], qc.y, qc.z, qc.w, liveDelta);
+            dirty |= mask;
+            passed += __popc(pA.mask) + __popc(pB.mask);
+        }
     }
-#endif
+    if (dirty & 0x3u) vp[0] = qa;
+    if (dirty & 0x6u) vp[1] = qb;
+    if (dirty & 0xCu) vp[2] = qc;
+    live_delta_commit(a.live, (unsigned)w.w, t, liveDelta);
 }
 
 // Persistent grid.  With a work list (the library's own compactify) blocks are dealt out dynamically: a CTA starts on block blockIdx.x and
@@ -216,18 +272,8 @@ stencil_fast_kernel(const __grid_constant__ FastArgs a) {
         if (a.useListCount) { a.listCounterOut[0] = (int)listCount; a.ctrs[CTR_E] = listCount; }
         if (!DYN) atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_E_TOT_LO]), (unsigned long long)listCount);
     }
-    // this thread's first voxel inside a block: i = 4t -> x = (4t) % 8, y = (4t % 64) / 8, z = 4t / 64
-    const float flx = (float)((4 * t) & 7), fly = (float)(((4 * t) & 63) >> 3), flz = (float)((4 * t) >> 6);
-    ThreadOffsets o;
-    o.ax = fmaf(flx, a.A.cx[0], fmaf(fly, a.A.cx[1], fmaf(flz, a.A.cx[2], a.A.cx[3])));
-    o.ay = fmaf(flx, a.A.cy[0], fmaf(fly, a.A.cy[1], fmaf(flz, a.A.cy[2], a.A.cy[3])));
-    o.az = fmaf(flx, a.A.cz[0], fmaf(fly, a.A.cz[1], fmaf(flz, a.A.cz[2], a.A.cz[3])));
-    o.bx = o.by = o.bz = 0.0f;
-    if (MODE == 2) {
-        o.bx = fmaf(flx, a.B.cx[0], fmaf(fly, a.B.cx[1], fmaf(flz, a.B.cx[2], a.B.cx[3])));
-        o.by = fmaf(flx, a.B.cy[0], fmaf(fly, a.B.cy[1], fmaf(flz, a.B.cy[2], a.B.cy[3])));
-        o.bz = fmaf(flx, a.B.cz[0], fmaf(fly, a.B.cz[1], fmaf(flz, a.B.cz[2], a.B.cz[3])));
-    }
+    ThreadVoxel o;
+    o.lx = (int)((4 * t) & 7); o.ly = (int)(((4 * t) & 63) >> 3); o.lz = (int)((4 * t) >> 6);
     unsigned passed = 0;
     if (DYN) {
 #ifndef BF_EMU_SEQUENTIAL
@@ -277,6 +323,52 @@ stencil_fast_kernel(const __grid_constant__ FastArgs a) {
 #endif
 }
 
+// batch re-integration: the same persistent grid and dynamic deal over the union list, every block visited once for up to 16 ops
+__global__ void __launch_bounds__(128, BF_FAST_MINBLOCKS_FUSED)
+stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
+    const unsigned count = a.ctrs[a.set + SET_WORK];
+    const unsigned t = threadIdx.x;
+    if (blockIdx.x == 0 && t == 0) { const unsigned listCount = a.ctrs[a.set + SET_COUNT]; a.listCounterOut[0] = (int)listCount; a.ctrs[CTR_E] = listCount; }
+    ThreadVoxel o;
+    o.lx = (int)((4 * t) & 7); o.ly = (int)(((4 * t) & 63) >> 3); o.lz = (int)((4 * t) >> 6);
+    unsigned passed = 0;
+#ifndef BF_EMU_SEQUENTIAL
+    __shared__ int4 sWork[2];
+    __shared__ unsigned sMask[2];
+    const int4 kEnd = make_int4(0, 0, 0, -1);
+    unsigned* const ticket = &a.ctrs[a.set + SET_TICKET];
+    int4 wCur = kEnd; unsigned mCur = 0;
+    if (blockIdx.x < count) { wCur = __ldg(&a.work[blockIdx.x]); mCur = __ldg(&a.workMask[blockIdx.x]); }
+    int4 wNext = kEnd; unsigned mNext = 0, iAfter = 0xFFFFFFFFu;
+    if (t == 0) {
+        const unsigned i1 = gridDim.x + atomicAdd(ticket, 1u);
+        if (i1 < count) { wNext = __ldg(&a.work[i1]); mNext = __ldg(&a.workMask[i1]); }
+        iAfter = gridDim.x + atomicAdd(ticket, 1u);
+    }
+    unsigned parity = 0;
+    while (wCur.w != -1) {
+        process_block_multi(a, o, t, wCur, mCur, passed);
+        if (t == 0) {
+            sWork[parity] = wNext; sMask[parity] = mNext;
+            wNext = kEnd; mNext = 0;
+            if (iAfter < count) { wNext = __ldg(&a.work[iAfter]); mNext = __ldg(&a.workMask[iAfter]); iAfter = gridDim.x + atomicAdd(ticket, 1u); }
+            else iAfter = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        wCur = sWork[parity]; mCur = sMask[parity];
+        parity ^= 1u;
+    }
+    passed = warp_sum_u(passed);
+    if ((t & 31) == 0 && passed) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[a.set + SET_U_LO]), (unsigned long long)passed);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed);
+    }
+#else
+    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) process_block_multi(a, o, t, a.work[b], a.workMask[b], passed);
+    if (passed) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[a.set + SET_U_LO]), (unsigned long long)passed); atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed); }
+#endif
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------
 static void make_pose(const BFHashParams* hp, FastPose* p) {
     const float* M = hp->m_rigidTransformInverse.m;
@@ -291,8 +383,8 @@ static void make_args(FastArgs* a, const BFHashDataStruct* hd, const BFDepthCame
                       bool useListCount, unsigned countOverride, unsigned* ctrs, int* live, const int4* work, int set) {
     a->blocks = hd->d_SDFBlocks; a->list = hd->d_hashCompactified; a->listCounterOut = hd->d_hashCompactifiedCounter; a->work = work;
     a->depth = depth; a->color = reinterpret_cast<const uchar4*>(color); a->ctrs = ctrs; a->live = live;
-    a->W = cp->m_imageWidth; a->H = cp->m_imageHeight; a->set = set; a->useListCount = useListCount ? 1 : 0; a->countOverride = countOverride;
-    a->fx = cp->fx; a->fy = cp->fy; a->mx5 = cp->mx + 0.5f; a->my5 = cp->my + 0.5f;
+    a->set = set; a->useListCount = useListCount ? 1 : 0; a->countOverride = countOverride;
+    a->cam.W = cp->m_imageWidth; a->cam.H = cp->m_imageHeight; a->cam.fx = cp->fx; a->cam.fy = cp->fy; a->cam.mx5 = cp->mx + 0.5f; a->cam.my5 = cp->my + 0.5f;
 }
 
 int fast_stencil_ctas_per_sm(bool fused) { return fused ? BF_FAST_MINBLOCKS_FUSED : BF_FAST_MINBLOCKS; }
@@ -315,6 +407,22 @@ int launch_reintegrate_fast(const BFHashDataStruct* hd, const BFHashParams* hpOl
     make_args(&a, hd, cp, depth, color, true, 0, ctrs, live, work, set);
     make_pose(hpOld, &a.A); make_pose(hpNew, &a.B);
     stencil_fast_kernel<2, true><<<grid, 128, 0, s>>>(a);
+    BF_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_reintegrate_multi_fast(const BFHashDataStruct* hd, const BFMultiOpDesc* ops, int nOps, const BFDepthCameraParams* cp, const int4* work,
+                                  const unsigned* workMask, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s) {
+    if (nOps < 1 || nOps > BF_MULTI_MAX_OPS) return (int)cudaErrorInvalidValue;
+    static MultiArgs a;                      // ~2.5 KB: kept off the stack; filled and passed by value at the launch
+    a.blocks = hd->d_SDFBlocks; a.work = work; a.workMask = workMask; a.ctrs = ctrs; a.live = live; a.listCounterOut = hd->d_hashCompactifiedCounter;
+    a.set = set; a.nOps = nOps;
+    a.cam.W = cp->m_imageWidth; a.cam.H = cp->m_imageHeight; a.cam.fx = cp->fx; a.cam.fy = cp->fy; a.cam.mx5 = cp->mx + 0.5f; a.cam.my5 = cp->my + 0.5f;
+    for (int k = 0; k < nOps; ++k) {
+        make_pose(ops[k].hpOld, &a.ops[k].A); make_pose(ops[k].hpNew, &a.ops[k].B);
+        a.ops[k].depth = ops[k].depth; a.ops[k].color = reinterpret_cast<const unsigned*>(ops[k].color);
+    }
+    stencil_multi_kernel<<<grid, 128, 0, s>>>(a);
     BF_CHECK(cudaGetLastError());
     return 0;
 }

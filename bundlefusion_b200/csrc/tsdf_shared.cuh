@@ -23,4 +23,11 @@ int launch_reintegrate_fast(const BFHashDataStruct* hd, const BFHashParams* hpOl
                             const float* depth, const void* color, const int4* work, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s);
 int fast_stencil_ctas_per_sm(bool fused);
 
+// batch re-integration: up to BF_MULTI_MAX_OPS (old pose, new pose, frame) triples applied to every voxel of the union list in one pass.
+// work[i] = {block x, y, z, slot}, workMask[i] = 2 bits per op {old pose may touch the block, new pose may}; counts in ctrs[set + SET_*].
+#define BF_MULTI_MAX_OPS 16
+struct BFMultiOpDesc { const BFHashParams* hpOld; const BFHashParams* hpNew; const float* depth; const void* color; };
+int launch_reintegrate_multi_fast(const BFHashDataStruct* hd, const BFMultiOpDesc* ops, int nOps, const BFDepthCameraParams* cp, const int4* work,
+                                  const unsigned* workMask, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s);
+
 }  // namespace bf

@@ -233,6 +233,18 @@ int bfTsdfIntegrateFrame(BFHashDataStruct* hashData, const BFHashParams* hashPar
 int bfTsdfReintegrateFrame(BFHashDataStruct* hashData, const BFHashParams* hashParamsOldPose, const BFHashParams* hashParamsNewPose,
                            const BFDepthCameraData* depthCameraData, const BFDepthCameraParams* depthCameraParams);
 
+/* A batch of re-integrations -- numPairs (<= 16) x { deIntegrate(frame, oldPose); integrate(frame, newPose) }, the loop of
+ * FL/DepthSensing/DepthSensing.cpp:867-895 -- as numPairs alloc launches, ONE union list and ONE stencil pass: every voxel of the list is
+ * read once, taken through the pairs in order in registers, written once.  Blocks inserted by pair k's alloc are invisible to the pairs before
+ * k, as in the reference's order.  Fast arithmetic only (bfTsdfSetArithmetic); results are bit-identical to replaying the pairs one by one
+ * through bfTsdfReintegrateFrame in fast arithmetic.  hashParams carries the pose-independent parameters and returns holding the last new
+ * pose.  d_hashCompactified then holds the union list (its GC flags mark the last pair's new-pose frustum, the list the reference's GC walks).
+ * bfTsdfRunOps routes runs of >= 2 pairs here when batching is on (default; BF_TSDF_BATCH=0 / bfTsdfSetBatching(0) replays pair by pair). */
+typedef struct BFTsdfReintegration { int32_t frame; float oldPose[16]; float newPose[16]; } BFTsdfReintegration;
+int bfTsdfReintegrateBatch(BFHashDataStruct* hashData, BFHashParams* hashParams, const BFDepthCameraParams* depthCameraParams,
+                           const BFTsdfReintegration* pairs, int numPairs, const float* const* d_depthFrames, const uint8_t* const* d_colorFrames);
+int bfTsdfSetBatching(int enable);
+
 /* CUDASceneRepHashSDF::garbageCollect (h:110-126) over the last compactified list */
 int bfTsdfGarbageCollect(BFHashDataStruct* hashData, const BFHashParams* hashParams);
 
@@ -250,7 +262,8 @@ int bfTsdfGetLastFrameStats(const BFHashDataStruct* hashData, unsigned long long
  * bfGetLaunchCount   -- kernels this library has launched since load (all paths);
  * bfTsdfSetProfiling -- when enabled every integrate / de-integrate stencil launch is bracketed by CUDA events on the library stream;
  * bfTsdfGetProfile   -- out[0] stencil launches, out[1] launches timed, out[2] their summed duration (ns), out[3] sum of U,
- *                       out[4] sum of E over those launches; synchronises and restarts the accumulation. */
+ *                       out[4] sum of E over those launches, out[5] frame images those launches read (one per launch, one per pair for a
+ *                       batch launch); synchronises and restarts the accumulation. */
 unsigned long long bfGetLaunchCount(void);
 int bfTsdfSetProfiling(int enable);
 int bfTsdfGetProfile(const BFHashDataStruct* hashData, unsigned long long out[8]);

@@ -54,6 +54,12 @@ extern "C" int emu_reintegrate_fast(const BFHashDataStruct* hd, const BFHashPara
                                     const void* color, const void* work, unsigned* ctrs, int* live, int grid) {
     return bf::launch_reintegrate_fast(hd, hpOld, hpNew, cp, depth, color, (const int4*)work, bf::CTR_SET0, ctrs, live, grid, nullptr);
 }
+extern "C" int emu_reintegrate_multi(const BFHashDataStruct* hd, const BFHashParams* hpOld, const BFHashParams* hpNew, int nOps, const BFDepthCameraParams* cp,
+                                     const float* const* depth, const void* const* color, const void* work, const unsigned* workMask, unsigned* ctrs, int* live, int grid) {
+    bf::BFMultiOpDesc d[BF_MULTI_MAX_OPS];
+    for (int k = 0; k < nOps; ++k) { d[k].hpOld = hpOld + k; d[k].hpNew = hpNew + k; d[k].depth = depth[k]; d[k].color = color[k]; }
+    return bf::launch_reintegrate_multi_fast(hd, d, nOps, cp, (const int4*)work, workMask, bf::CTR_SET0, ctrs, live, grid, nullptr);
+}
 '''
 
 
@@ -63,6 +69,8 @@ def emu():
     src = src.replace('#include "bf_common.cuh"', "")
     src, n = re.subn(r"(\w+<\d, \w+>)<<<\s*([^,]+),\s*([^,]+),\s*[^,]+,\s*[^>]+>>>\((\w+)\)", r"seq_launch(\1, \2, \3, \4)", src)
     assert n == 5, n
+    src, n = re.subn(r"stencil_multi_kernel<<<\s*([^,]+),\s*([^,]+),\s*[^,]+,\s*[^>]+>>>\((\w+)\)", r"seq_launch(stencil_multi_kernel, \1, \2, \3)", src)
+    assert n == 1, n
     d = tempfile.mkdtemp(prefix="bf_fast_emu_")
     cpp = os.path.join(d, "tsdf_fast_emu.cpp")
     open(cpp, "w").write(_PRE % {"emu": os.path.join(ROOT, "tests", "cuda_emu", "cuda_emu.h")} + src + _POST)
@@ -75,6 +83,7 @@ def emu():
     vp = C.c_void_p
     L.emu_integrate_fast.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_uint, vp, vp, C.c_int]
     L.emu_reintegrate_fast.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+    L.emu_reintegrate_multi.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int]
     return L
 
 
@@ -187,3 +196,83 @@ def test_fast_fused_reintegration_emulated_equals_its_two_passes(emu):
     np.testing.assert_array_equal(ab, bb)
     np.testing.assert_array_equal(av, bv)
     np.testing.assert_array_equal(one.live, two.live)
+
+
+def _frustum_slots(o, hp_pose, cam):
+    """hash-entry ptr values of the blocks in the frustum list of a pose (the oracle's compactify)"""
+    n = o.L.orc_tsdf_compactify(C.byref(o.hd), C.byref(hp_pose), C.byref(cam))
+    return {int(p) for p in o.compactified.reshape(-1, 8)[:n, 3]}
+
+
+def test_batch_stencil_emulated_equals_pair_by_pair(emu):
+    """stencil_multi_kernel (all pairs of a batch applied per voxel in registers, one read / write) against the pair-by-pair fused passes of
+    the same source, word for word -- including the rule that a block inserted by pair k's alloc is invisible to the pairs before k."""
+    W, H = 160, 120
+    cam = camera_params(W, H)
+    hp = default_hash_params(num_buckets=20011, num_sdf_blocks=30000)
+    seq, bat = _FastOnOracle(emu, hp), _FastOnOracle(emu, hp)
+    frames = [synth.make_frame(35 * i, W, H) for i in range(4)]
+    for d, c, T in frames[:3]:
+        seq.integrate(T, d, np.ascontiguousarray(c), cam); bat.integrate(T, d, np.ascontiguousarray(c), cam)
+    # three pairs; the third re-integrates a frame towards a region nobody has looked at yet (frame 3's pose), so that its alloc inserts new blocks
+    moves = [(1, synth.se3_exp(np.array([0.004, -0.003, 0.002]), np.array([0.012, -0.007, 0.005]))),
+             (0, synth.se3_exp(np.array([-0.002, 0.005, 0.001]), np.array([-0.01, 0.004, 0.008]))),
+             (2, None)]
+    pairs = []
+    for f, M in moves:
+        d, c, T = frames[f]
+        T2 = frames[3][2] if M is None else (M @ T.astype(np.float64)).astype(F)
+        pairs.append((np.ascontiguousarray(d, F), np.ascontiguousarray(c), T, T2))
+
+    def hp_at(o, T):
+        q = capi.BFHashParams(); C.memmove(C.byref(q), C.byref(o.hp), C.sizeof(capi.BFHashParams)); set_pose(q, T); return q
+
+    def used_slots(o):
+        h = o.hash
+        return {int(p) for p in h[h[:, 3] != -2, 3]}
+
+    def work_list(o, masks):                      # masks: {ptr: mask}
+        h = o.hash
+        rows = [i for i in np.nonzero(h[:, 3] != -2)[0] if masks.get(int(h[i, 3]), 0)]
+        work = np.zeros((len(rows), 4), np.int32); wm = np.zeros(len(rows), np.uint32)
+        for n, i in enumerate(rows):
+            work[n, :3] = h[i, :3]; work[n, 3] = int(h[i, 3]) // 512; wm[n] = masks[int(h[i, 3])]
+        return work, wm
+
+    # pair by pair (what bfTsdfReintegrateFrame does): alloc(new), union list with per-pose flags, fused pass
+    for d, c, T, T2 in pairs:
+        o = seq.o
+        hpO, hpN = hp_at(o, T), hp_at(o, T2)
+        o._set_pose(T2); o.L.orc_tsdf_alloc(C.byref(o.hd), C.byref(o.hp), d, C.byref(cam))
+        inO, inN = _frustum_slots(o, hpO, cam), _frustum_slots(o, hpN, cam)
+        work, wm = work_list(o, {p: (1 if p in inO else 0) | (2 if p in inN else 0) for p in inO | inN})
+        work[:, 3] |= (wm.astype(np.int32) << 28)
+        seq.ctrs[16:24] = 0; seq.ctrs[16] = seq.ctrs[17] = len(work)
+        assert emu.emu_reintegrate_fast(C.byref(o.hd), C.byref(hpO), C.byref(hpN), C.byref(cam), d.ctypes.data, c.ctypes.data, work.ctypes.data, seq.ctrs.ctypes.data, seq.live.ctypes.data, 4) == 0
+    # batch: all allocs first (remember which alloc inserted which block), one union list with 2 bits per pair, one pass
+    o = bat.o
+    epoch = {}
+    for k, (d, c, T, T2) in enumerate(pairs):
+        before = used_slots(o)
+        o._set_pose(T2); o.L.orc_tsdf_alloc(C.byref(o.hd), C.byref(o.hp), d, C.byref(cam))
+        for p in used_slots(o) - before:
+            epoch[p] = k
+    assert any(v == 2 for v in epoch.values()), "the third pair is meant to insert new blocks"
+    masks = {}
+    hpOs = (capi.BFHashParams * 3)(); hpNs = (capi.BFHashParams * 3)()
+    for k, (d, c, T, T2) in enumerate(pairs):
+        hpOs[k], hpNs[k] = hp_at(o, T), hp_at(o, T2)
+        inO, inN = _frustum_slots(o, hpOs[k], cam), _frustum_slots(o, hpNs[k], cam)
+        for p in inO | inN:
+            if epoch.get(p, 0) <= k:
+                masks[p] = masks.get(p, 0) | ((1 if p in inO else 0) | (2 if p in inN else 0)) << (2 * k)
+    work, wm = work_list(o, masks)
+    dptr = (C.c_void_p * 3)(*[p[0].ctypes.data for p in pairs]); cptr = (C.c_void_p * 3)(*[p[1].ctypes.data for p in pairs])
+    bat.ctrs[16:24] = 0; bat.ctrs[16] = bat.ctrs[17] = len(work)
+    assert emu.emu_reintegrate_multi(C.byref(o.hd), C.addressof(hpOs), C.addressof(hpNs), 3, C.byref(cam), C.addressof(dptr), C.addressof(cptr), work.ctypes.data,
+                                     wm.ctypes.data, bat.ctrs.ctypes.data, bat.live.ctypes.data, 5) == 0
+    ab, av = orc.canonical_blocks(bat.o.download()); bb, bv = orc.canonical_blocks(seq.o.download())
+    np.testing.assert_array_equal(ab, bb)
+    np.testing.assert_array_equal(av, bv)
+    np.testing.assert_array_equal(bat.live, seq.live)
+    assert int(bat.ctrs[20]) == int(seq.ctrs[12])               # U of the batch = sum of the pairs' U (seq: the running total CTR_U_TOT_LO)

@@ -146,3 +146,57 @@ def test_fast_full_size_round_trip_properties(cuda_device):
     assert int(gpu.d_SDFBlocks.abs().max()) == 0
     h = gpu.download()["hash"]
     assert (h[:, 3] == -2).all()
+
+
+def test_batched_reintegration_equals_pair_by_pair(cuda_device):
+    """bfTsdfRunOps with batching (n alloc launches, one union list, one multi-op stencil pass per run of re-integration pairs) against the same
+    op list replayed pair by pair, both in fast arithmetic: voxels, block set and heap must be IDENTICAL bit for bit -- the batch changes how
+    often a voxel travels, not what happens to it; a block inserted by pair k's alloc stays invisible to the pairs before k."""
+    import torch
+    W, H = 320, 240
+    cam = camera_params(W, H)
+    hp = default_hash_params(num_buckets=100003, num_sdf_blocks=60000)
+    L = capi.lib()
+    frames, dl, cl = _frames(torch, cuda_device, 8, W, H, step=35)
+    rng = np.random.default_rng(11)
+    ops = [(capi.BF_TSDF_OP_INTEGRATE, i, frames[i][2]) for i in range(6)]
+    cur = [f[2] for f in frames]
+    def pair(k, big=False):
+        T = cur[k]
+        s = 0.05 if big else 0.01
+        T2 = (synth.se3_exp(rng.standard_normal(3) * s, rng.standard_normal(3) * 2 * s) @ T.astype(np.float64)).astype(F)
+        cur[k] = T2
+        return [(capi.BF_TSDF_OP_DEINTEGRATE, k, T), (capi.BF_TSDF_OP_INTEGRATE, k, T2)]
+    for k in (4, 2, 0, 5, 2, 1, 3):                      # frame 2 moves twice inside one batch
+        ops += pair(k)
+    ops.append((capi.BF_TSDF_OP_GARBAGE_COLLECT, 0, None))
+    ops.append((capi.BF_TSDF_OP_INTEGRATE, 6, frames[6][2]))
+    for k in (6, 0, 3):
+        ops += pair(k, big=True)                         # large moves: their allocs insert blocks the earlier pairs of the batch must not see
+    ops += [(capi.BF_TSDF_OP_GARBAGE_COLLECT, 0, None), (capi.BF_TSDF_OP_INTEGRATE, 7, frames[7][2])]
+    states = []
+    for batching in (1, 0):
+        prev = L.bfTsdfSetBatching(batching)
+        try:
+            sc = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="fast")
+            l0 = L.bfGetLaunchCount()
+            sc.runOps(ops, dl, cl, cam)
+            torch.cuda.synchronize()
+            states.append((orc.canonical_blocks(sc.download()), sc.getHeapFreeCount(), L.bfGetLaunchCount() - l0, sc.getLastFrameStats()))
+        finally:
+            L.bfTsdfSetBatching(prev)
+    (b1, v1), h1, n1, st1 = states[0]
+    (b0, v0), h0, n0, st0 = states[1]
+    np.testing.assert_array_equal(b1, b0)
+    np.testing.assert_array_equal(v1, v0)
+    assert h1 == h0 and n1 < n0
+    # and the whole thing within the tolerance contract of the oracle's pair-by-pair replay
+    cpu = orc.OracleSceneRepHashSDF(hp)
+    for kind, f, T in ops:
+        if kind == capi.BF_TSDF_OP_GARBAGE_COLLECT: cpu.garbageCollect()
+        elif kind == capi.BF_TSDF_OP_DEINTEGRATE: cpu.deIntegrate(T, frames[f][0], frames[f][1], cam)
+        else: cpu.integrate(T, frames[f][0], frames[f][1], cam)
+    sc = CUDASceneRepHashSDF(hp, cuda_device, arithmetic="fast")
+    sc.runOps(ops, dl, cl, cam)
+    print("batched fast vs oracle:", compare_states(sc.download(), cpu.download(), 10 * SDF_TOL), "launches batched / pair by pair:", n1, n0)
+    assert sc.getHeapFreeCount() == cpu.getHeapFreeCount()
