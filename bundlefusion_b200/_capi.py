@@ -299,6 +299,8 @@ def lib() -> C.CDLL:
     L.bfSolverWorkspaceBytes.argtypes = [C.c_uint, C.c_uint]
     L.bfSolverWorkspaceBytes.restype = C.c_size_t
     L.bfSolverReleaseWorkspace.argtypes = [P(BFSolverState)]
+    L.bfSiftVerifyTrajectory.argtypes = [C.c_uint, vp, vp, C.c_uint, C.c_uint, P(C.c_float), vp] + [C.c_float] * 7 + [vp, vp]
+    L.bfSiftFuseToGlobal.argtypes = [vp, vp, vp, vp, C.c_uint, vp, vp, vp, C.c_uint, P(C.c_float), C.c_uint, vp, vp, vp, C.c_uint, vp]
     L.bfSolverDebugDenseSystem.argtypes = [P(BFSolverState), C.c_uint, vp, vp]
     L.bfCacheStoreFrame.argtypes = [P(BFCacheParams), vp, vp, P(BFCUDACachedFrame)]
     L.bfIngestFrame.argtypes = [P(BFIngestParams), vp, vp, vp, vp]

@@ -1058,7 +1058,7 @@ struct MultiFrusta { int nOps; float voxelSize; BFFloat4x4 inv[2 * BF_MULTI_MAX_
 __global__ void __launch_bounds__(256)
 compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta fr, const __grid_constant__ BFDepthCameraParams cp,
                         const int4* __restrict__ slotInfo, const unsigned* __restrict__ slotEpoch, unsigned batchId, unsigned* ctrs, int set,
-                        unsigned char* __restrict__ listFlags, int4* __restrict__ work, unsigned* __restrict__ workMask) {
+                        unsigned char* __restrict__ listFlags, int4* __restrict__ work, unsigned* __restrict__ workMask, unsigned workCap) {
     const unsigned highWater = ctrs[CTR_HIGH_WATER];
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned stride = gridDim.x * blockDim.x;
@@ -1082,18 +1082,27 @@ compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta
         const unsigned ballot = __ballot_sync(0xffffffffu, mask != 0);
         if (ballot) {
             // E of the batch = sum over ops of the blocks in either frustum = what the per-op lists would have held
-            unsigned nE = 0;
-            for (int k = 0; k < fr.nOps; ++k) nE += ((mask >> (2 * k)) & 1u) + ((mask >> (2 * k + 1)) & 1u);
+            const unsigned bits = (unsigned)__popc(mask);
+            unsigned nE = bits;
             for (int o = 16; o > 0; o >>= 1) nE += __shfl_xor_sync(0xffffffffu, nE, o);
-            unsigned warpBase = 0;
+            // Work order: a block's cost grows with the number of (op, pose) probes it takes -- up to 2 nOps of them.  Heavy blocks (at
+            // least nOps probes) are listed from the front of the work array, light ones from its back, and the stencil deals the heavy ones
+            // first: the kernel then ends on cheap blocks instead of on a few 20-probe blocks (longest-processing-time-first).
+            const bool heavy = mask != 0 && bits >= (unsigned)fr.nOps;
+            const unsigned ballotH = __ballot_sync(0xffffffffu, heavy), ballotL = ballot & ~ballotH;
+            unsigned warpBase = 0, heavyBase = 0, lightBase = 0;
             if (lane == 0) {
                 warpBase = atomicAdd(&ctrs[set + SET_COUNT], __popc(ballot));
-                atomicAdd(&ctrs[set + SET_WORK], __popc(ballot));
+                if (ballotH) heavyBase = atomicAdd(&ctrs[set + SET_WORK], __popc(ballotH));
+                if (ballotL) lightBase = atomicAdd(&ctrs[set + SET_CULLED], __popc(ballotL));      // the batch has no cull: the slot counts the light items
                 atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_E_TOT_LO]), (unsigned long long)nE);
             }
             warpBase = __shfl_sync(0xffffffffu, warpBase, 0);
+            heavyBase = __shfl_sync(0xffffffffu, heavyBase, 0);
+            lightBase = __shfl_sync(0xffffffffu, lightBase, 0);
             if (mask) {
-                const unsigned k = warpBase + __popc(ballot & ((1u << lane) - 1u));
+                const unsigned below = (1u << lane) - 1u;
+                const unsigned k = warpBase + __popc(ballot & below);
                 BFHashEntry en;
                 en.pos[0] = info.x; en.pos[1] = info.y; en.pos[2] = info.z;
                 en.ptr = (int)(slot * BF_SDF_BLOCK_VOXELS);
@@ -1101,8 +1110,9 @@ compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta
                 hd.d_hashCompactified[k] = en;
                 // the reference's GC walks the list of the LAST integrate (DepthSensing.cpp:901): bit 1 = in the last op's new-pose frustum
                 listFlags[k] = (unsigned char)(((mask >> (2 * (fr.nOps - 1))) & 2u) | 1u);
-                work[k] = make_int4(info.x, info.y, info.z, (int)slot);
-                workMask[k] = mask;
+                const unsigned w = heavy ? heavyBase + __popc(ballotH & below) : (workCap - 1u) - (lightBase + __popc(ballotL & below));
+                work[w] = make_int4(info.x, info.y, info.z, (int)slot);
+                workMask[w] = mask;
             }
         }
     }
@@ -1732,7 +1742,7 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
     const int set = set_of(aux->parity);
     ++g_launchCount;
     compactify_multi_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, fr, *cp, aux->slotInfo, aux->slotEpoch, aux->batchId, aux->ctrs, set,
-                                                                                                 aux->listFlags, aux->work2[aux->parity], aux->workMask);
+                                                                                                 aux->listFlags, aux->work2[aux->parity], aux->workMask, aux->numSlots);
     BF_CHECK(cudaGetLastError());
     const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
     if (g_profile) { ++g_profLaunches; g_profFrames += (unsigned long long)numPairs; }
@@ -1741,7 +1751,7 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
         BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], g_stream));
     }
     ++g_launchCount;
-    rc = launch_reintegrate_multi_fast(hd, desc, numPairs, cp, aux->work2[aux->parity], aux->workMask, set, aux->ctrs, aux->live,
+    rc = launch_reintegrate_multi_fast(hd, desc, numPairs, cp, aux->work2[aux->parity], aux->workMask, aux->numSlots, set, aux->ctrs, aux->live,
                                        grid_for(hp->m_numSDFBlocks, fast_stencil_ctas_per_sm(true)), g_stream);
     if (rc) return rc;
     if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], g_stream)); ++g_evUsed; }

@@ -39,7 +39,7 @@ struct FastArgs {
 struct MultiOp { FastPose A, B; const float* depth; const unsigned* color; };
 struct MultiArgs {
     BFVoxel* blocks; const int4* work; const unsigned* workMask; unsigned* ctrs; int* live; int* listCounterOut;
-    int set; int nOps;
+    int set; int nOps; unsigned workCap;
     FastCam cam;
     MultiOp ops[BF_MULTI_MAX_OPS];
 };
@@ -326,23 +326,25 @@ stencil_fast_kernel(const __grid_constant__ FastArgs a) {
 // batch re-integration: the same persistent grid and dynamic deal over the union list, every block visited once for up to 16 ops
 __global__ void __launch_bounds__(128, BF_FAST_MINBLOCKS_FUSED)
 stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
-    const unsigned count = a.ctrs[a.set + SET_WORK];
+    // ticket i -> work item: the heavy items first (front of the array), then the light ones (from the back)
+    const unsigned nHeavy = a.ctrs[a.set + SET_WORK], nLight = a.ctrs[a.set + SET_CULLED], count = nHeavy + nLight;
     const unsigned t = threadIdx.x;
     if (blockIdx.x == 0 && t == 0) { const unsigned listCount = a.ctrs[a.set + SET_COUNT]; a.listCounterOut[0] = (int)listCount; a.ctrs[CTR_E] = listCount; }
     ThreadVoxel o;
     o.lx = (int)((4 * t) & 7); o.ly = (int)(((4 * t) & 63) >> 3); o.lz = (int)((4 * t) >> 6);
     unsigned passed = 0;
+#define BF_MULTI_ITEM(i) ((i) < nHeavy ? (i) : a.workCap - 1u - ((i) - nHeavy))
 #ifndef BF_EMU_SEQUENTIAL
     __shared__ int4 sWork[2];
     __shared__ unsigned sMask[2];
     const int4 kEnd = make_int4(0, 0, 0, -1);
     unsigned* const ticket = &a.ctrs[a.set + SET_TICKET];
     int4 wCur = kEnd; unsigned mCur = 0;
-    if (blockIdx.x < count) { wCur = __ldg(&a.work[blockIdx.x]); mCur = __ldg(&a.workMask[blockIdx.x]); }
+    if (blockIdx.x < count) { const unsigned j = BF_MULTI_ITEM(blockIdx.x); wCur = __ldg(&a.work[j]); mCur = __ldg(&a.workMask[j]); }
     int4 wNext = kEnd; unsigned mNext = 0, iAfter = 0xFFFFFFFFu;
     if (t == 0) {
         const unsigned i1 = gridDim.x + atomicAdd(ticket, 1u);
-        if (i1 < count) { wNext = __ldg(&a.work[i1]); mNext = __ldg(&a.workMask[i1]); }
+        if (i1 < count) { const unsigned j = BF_MULTI_ITEM(i1); wNext = __ldg(&a.work[j]); mNext = __ldg(&a.workMask[j]); }
         iAfter = gridDim.x + atomicAdd(ticket, 1u);
     }
     unsigned parity = 0;
@@ -351,7 +353,7 @@ stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
         if (t == 0) {
             sWork[parity] = wNext; sMask[parity] = mNext;
             wNext = kEnd; mNext = 0;
-            if (iAfter < count) { wNext = __ldg(&a.work[iAfter]); mNext = __ldg(&a.workMask[iAfter]); iAfter = gridDim.x + atomicAdd(ticket, 1u); }
+            if (iAfter < count) { const unsigned j = BF_MULTI_ITEM(iAfter); wNext = __ldg(&a.work[j]); mNext = __ldg(&a.workMask[j]); iAfter = gridDim.x + atomicAdd(ticket, 1u); }
             else iAfter = 0xFFFFFFFFu;
         }
         __syncthreads();
@@ -364,9 +366,10 @@ stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
         atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed);
     }
 #else
-    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) process_block_multi(a, o, t, a.work[b], a.workMask[b], passed);
+    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) { const unsigned j = BF_MULTI_ITEM(b); process_block_multi(a, o, t, a.work[j], a.workMask[j], passed); }
     if (passed) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[a.set + SET_U_LO]), (unsigned long long)passed); atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed); }
 #endif
+#undef BF_MULTI_ITEM
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
@@ -412,11 +415,11 @@ int launch_reintegrate_fast(const BFHashDataStruct* hd, const BFHashParams* hpOl
 }
 
 int launch_reintegrate_multi_fast(const BFHashDataStruct* hd, const BFMultiOpDesc* ops, int nOps, const BFDepthCameraParams* cp, const int4* work,
-                                  const unsigned* workMask, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s) {
+                                  const unsigned* workMask, unsigned workCap, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s) {
     if (nOps < 1 || nOps > BF_MULTI_MAX_OPS) return (int)cudaErrorInvalidValue;
     static MultiArgs a;                      // ~2.5 KB: kept off the stack; filled and passed by value at the launch
     a.blocks = hd->d_SDFBlocks; a.work = work; a.workMask = workMask; a.ctrs = ctrs; a.live = live; a.listCounterOut = hd->d_hashCompactifiedCounter;
-    a.set = set; a.nOps = nOps;
+    a.set = set; a.nOps = nOps; a.workCap = workCap;
     a.cam.W = cp->m_imageWidth; a.cam.H = cp->m_imageHeight; a.cam.fx = cp->fx; a.cam.fy = cp->fy; a.cam.mx5 = cp->mx + 0.5f; a.cam.my5 = cp->my + 0.5f;
     for (int k = 0; k < nOps; ++k) {
         make_pose(ops[k].hpOld, &a.ops[k].A); make_pose(ops[k].hpNew, &a.ops[k].B);

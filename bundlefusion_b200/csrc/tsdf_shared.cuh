@@ -24,10 +24,11 @@ int launch_reintegrate_fast(const BFHashDataStruct* hd, const BFHashParams* hpOl
 int fast_stencil_ctas_per_sm(bool fused);
 
 // batch re-integration: up to BF_MULTI_MAX_OPS (old pose, new pose, frame) triples applied to every voxel of the union list in one pass.
-// work[i] = {block x, y, z, slot}, workMask[i] = 2 bits per op {old pose may touch the block, new pose may}; counts in ctrs[set + SET_*].
+// work[i] = {block x, y, z, slot}, workMask[i] = 2 bits per op {old pose may touch the block, new pose may}.  Heavy items (>= nOps probes) sit
+// at [0, ctrs[set + SET_WORK]), light ones at [workCap - ctrs[set + SET_CULLED], workCap) from the back; the stencil deals the heavy ones first.
 #define BF_MULTI_MAX_OPS 16
 struct BFMultiOpDesc { const BFHashParams* hpOld; const BFHashParams* hpNew; const float* depth; const void* color; };
 int launch_reintegrate_multi_fast(const BFHashDataStruct* hd, const BFMultiOpDesc* ops, int nOps, const BFDepthCameraParams* cp, const int4* work,
-                                  const unsigned* workMask, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s);
+                                  const unsigned* workMask, unsigned workCap, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s);
 
 }  // namespace bf

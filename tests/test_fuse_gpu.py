@@ -24,13 +24,20 @@ def gpu():
     return L
 
 
-@pytest.mark.parametrize("seed,n_images,n_points,stride", [(0, 6, 140, 256), (1, 11, 150, 1024), (2, 3, 40, 64), (5, 11, 400, 1024)])
+@pytest.mark.parametrize("seed,n_images,n_points,stride", [(0, 6, 140, 256), (1, 11, 150, 1024), (2, 3, 40, 64), (5, 11, 160, 1024)])
 def test_fuse_to_global_bit_exact(gpu, seed, n_images, n_points, stride):
     pb = synth.make_fuse_problem(seed=seed, n_images=n_images, n_points=n_points, key_stride=stride)
     ko, do = orc.sift_fuse_to_global(pb["corr"], pb["keyIdx"], pb["transforms"], pb["keys"], pb["descs"], pb["numKeys"], pb["keyStride"], pb["K"])
     kg, dg, st = run_fuse(gpu, pb, to_dev=DevBuf, from_dev=lambda b: b.get())
     assert st == 0 and len(kg) == len(ko) > 10
     assert np.array_equal(kg.view(np.uint32), ko.view(np.uint32)) and np.array_equal(dg, do)
+
+
+def test_fuse_to_global_rejects_lists_beyond_its_capacity(gpu):
+    pb = synth.make_fuse_problem(seed=5, n_images=11, n_points=400, key_stride=1024)      # > 4096 correspondences: more than any chunk can hold (25 x 55)
+    assert len(pb["corr"]) > 4096
+    with pytest.raises(AssertionError):
+        run_fuse(gpu, pb, to_dev=DevBuf, from_dev=lambda b: b.get())
 
 
 def test_fuse_to_global_empty_and_capped(gpu):

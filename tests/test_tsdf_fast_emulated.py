@@ -55,10 +55,10 @@ extern "C" int emu_reintegrate_fast(const BFHashDataStruct* hd, const BFHashPara
     return bf::launch_reintegrate_fast(hd, hpOld, hpNew, cp, depth, color, (const int4*)work, bf::CTR_SET0, ctrs, live, grid, nullptr);
 }
 extern "C" int emu_reintegrate_multi(const BFHashDataStruct* hd, const BFHashParams* hpOld, const BFHashParams* hpNew, int nOps, const BFDepthCameraParams* cp,
-                                     const float* const* depth, const void* const* color, const void* work, const unsigned* workMask, unsigned* ctrs, int* live, int grid) {
+                                     const float* const* depth, const void* const* color, const void* work, const unsigned* workMask, unsigned workCap, unsigned* ctrs, int* live, int grid) {
     bf::BFMultiOpDesc d[BF_MULTI_MAX_OPS];
     for (int k = 0; k < nOps; ++k) { d[k].hpOld = hpOld + k; d[k].hpNew = hpNew + k; d[k].depth = depth[k]; d[k].color = color[k]; }
-    return bf::launch_reintegrate_multi_fast(hd, d, nOps, cp, (const int4*)work, workMask, bf::CTR_SET0, ctrs, live, grid, nullptr);
+    return bf::launch_reintegrate_multi_fast(hd, d, nOps, cp, (const int4*)work, workMask, workCap, bf::CTR_SET0, ctrs, live, grid, nullptr);
 }
 '''
 
@@ -83,7 +83,7 @@ def emu():
     vp = C.c_void_p
     L.emu_integrate_fast.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_uint, vp, vp, C.c_int]
     L.emu_reintegrate_fast.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
-    L.emu_reintegrate_multi.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+    L.emu_reintegrate_multi.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_uint, vp, vp, C.c_int]
     return L
 
 
@@ -240,6 +240,7 @@ def test_batch_stencil_emulated_equals_pair_by_pair(emu):
         return work, wm
 
     # pair by pair (what bfTsdfReintegrateFrame does): alloc(new), union list with per-pose flags, fused pass
+    u_seq = 0
     for d, c, T, T2 in pairs:
         o = seq.o
         hpO, hpN = hp_at(o, T), hp_at(o, T2)
@@ -249,6 +250,7 @@ def test_batch_stencil_emulated_equals_pair_by_pair(emu):
         work[:, 3] |= (wm.astype(np.int32) << 28)
         seq.ctrs[16:24] = 0; seq.ctrs[16] = seq.ctrs[17] = len(work)
         assert emu.emu_reintegrate_fast(C.byref(o.hd), C.byref(hpO), C.byref(hpN), C.byref(cam), d.ctypes.data, c.ctypes.data, work.ctypes.data, seq.ctrs.ctypes.data, seq.live.ctypes.data, 4) == 0
+        u_seq += int(seq.ctrs[20])
     # batch: all allocs first (remember which alloc inserted which block), one union list with 2 bits per pair, one pass
     o = bat.o
     epoch = {}
@@ -267,12 +269,20 @@ def test_batch_stencil_emulated_equals_pair_by_pair(emu):
             if epoch.get(p, 0) <= k:
                 masks[p] = masks.get(p, 0) | ((1 if p in inO else 0) | (2 if p in inN else 0)) << (2 * k)
     work, wm = work_list(o, masks)
+    # the layout compactify_multi_kernel produces: heavy items (>= nOps probes) from the front, light ones from the back of a capacity-sized array
+    cap = len(work) + 7
+    heavy = np.array([bin(int(m)).count("1") >= 3 for m in wm])
+    W2, M2 = np.zeros((cap, 4), np.int32), np.zeros(cap, np.uint32)
+    nH, nL = int(heavy.sum()), int((~heavy).sum())
+    W2[:nH], M2[:nH] = work[heavy], wm[heavy]
+    W2[cap - nL:], M2[cap - nL:] = work[~heavy][::-1], wm[~heavy][::-1]
+    assert nH > 0 and nL > 0
     dptr = (C.c_void_p * 3)(*[p[0].ctypes.data for p in pairs]); cptr = (C.c_void_p * 3)(*[p[1].ctypes.data for p in pairs])
-    bat.ctrs[16:24] = 0; bat.ctrs[16] = bat.ctrs[17] = len(work)
-    assert emu.emu_reintegrate_multi(C.byref(o.hd), C.addressof(hpOs), C.addressof(hpNs), 3, C.byref(cam), C.addressof(dptr), C.addressof(cptr), work.ctypes.data,
-                                     wm.ctypes.data, bat.ctrs.ctypes.data, bat.live.ctypes.data, 5) == 0
+    bat.ctrs[16:24] = 0; bat.ctrs[16] = len(work); bat.ctrs[17] = nH; bat.ctrs[18] = nL
+    assert emu.emu_reintegrate_multi(C.byref(o.hd), C.addressof(hpOs), C.addressof(hpNs), 3, C.byref(cam), C.addressof(dptr), C.addressof(cptr), W2.ctypes.data,
+                                     M2.ctypes.data, cap, bat.ctrs.ctypes.data, bat.live.ctypes.data, 5) == 0
     ab, av = orc.canonical_blocks(bat.o.download()); bb, bv = orc.canonical_blocks(seq.o.download())
     np.testing.assert_array_equal(ab, bb)
     np.testing.assert_array_equal(av, bv)
     np.testing.assert_array_equal(bat.live, seq.live)
-    assert int(bat.ctrs[20]) == int(seq.ctrs[12])               # U of the batch = sum of the pairs' U (seq: the running total CTR_U_TOT_LO)
+    assert int(bat.ctrs[20]) == u_seq                            # U of the batch = sum of the pairs' U
