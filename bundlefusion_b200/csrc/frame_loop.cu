@@ -360,7 +360,6 @@ static int sba_align(Loop& L, Bundler& b, unsigned maxNumIters, unsigned numPCGi
     par.denseDepthMin = 0.5f; par.denseDepthMax = 4.0f; par.denseOverlapCheckSubsampleFactor = 4;
     par.weightSparse = sv.wS[0]; par.weightDenseDepth = sv.wD[0]; par.weightDenseColor = sv.wC[0];
     par.useDense = (par.weightDenseDepth > 0 || par.weightDenseColor > 0) ? 1 : 0; par.useDenseDepthAllPairwise = 1;
-    st_assign:
     sv.st.d_xRot = sv.d_xRot; sv.st.d_xTrans = sv.d_xTrans;
     FL_OK(bfSolverSolve(&in, &sv.st, &par));
     sv.lastInput = in; sv.lastPar = par;
@@ -400,7 +399,6 @@ static int sba_align(Loop& L, Bundler& b, unsigned maxNumIters, unsigned numPCGi
         }
     }
     return 0;
-    goto st_assign;
 }
 
 // Bundler::optimize (FL/Bundler.cpp:251-283)

@@ -77,7 +77,9 @@ static bool g_profile = false;
 static std::vector<cudaEvent_t> g_evStart, g_evStop;
 static size_t g_evUsed = 0;
 static unsigned long long g_profLaunches = 0;
-static unsigned long long g_profFrames = 0;      // frame images the profiled stencil launches read (a batch launch reads one per pair)
+static unsigned long long g_profFrames = 0;
+static unsigned long long g_profBatchLaunches = 0, g_profBatchFrames = 0;
+static std::vector<unsigned char> g_evIsBatch;      // frame images the profiled stencil launches read (a batch launch reads one per pair)
 static const size_t kMaxProfiledLaunches = 16384;
 
 static std::mutex g_auxMutex;
@@ -1096,6 +1098,7 @@ compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta
                 if (ballotH) heavyBase = atomicAdd(&ctrs[set + SET_WORK], __popc(ballotH));
                 if (ballotL) lightBase = atomicAdd(&ctrs[set + SET_CULLED], __popc(ballotL));      // the batch has no cull: the slot counts the light items
                 atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_E_TOT_LO]), (unsigned long long)nE);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_EB_TOT_LO]), (unsigned long long)nE);
             }
             warpBase = __shfl_sync(0xffffffffu, warpBase, 0);
             heavyBase = __shfl_sync(0xffffffffu, heavyBase, 0);
@@ -1557,6 +1560,7 @@ static int do_integrate(BFHashDataStruct* hd, const BFHashParams* hp, const BFDe
     if (g_profile) { ++g_profLaunches; ++g_profFrames; }
     if (timeIt) {
         if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
+        if (g_evIsBatch.size() > g_evUsed) g_evIsBatch[g_evUsed] = 0;
         BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], sb));
     }
     ++g_launchCount;
@@ -1674,6 +1678,7 @@ BF_API int bfTsdfReintegrateFrame(BFHashDataStruct* hd, const BFHashParams* hpOl
     if (g_profile) { ++g_profLaunches; ++g_profFrames; }
     if (timeIt) {
         if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
+        if (g_evIsBatch.size() > g_evUsed) g_evIsBatch[g_evUsed] = 0;
         BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], sb));
     }
     ++g_launchCount;
@@ -1745,9 +1750,11 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
                                                                                                  aux->listFlags, aux->work2[aux->parity], aux->workMask, aux->numSlots);
     BF_CHECK(cudaGetLastError());
     const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
-    if (g_profile) { ++g_profLaunches; g_profFrames += (unsigned long long)numPairs; }
+    if (g_profile) { ++g_profLaunches; g_profFrames += (unsigned long long)numPairs; ++g_profBatchLaunches; g_profBatchFrames += (unsigned long long)numPairs; }
     if (timeIt) {
         if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
+        if (g_evIsBatch.size() <= g_evUsed) g_evIsBatch.resize(g_evUsed + 1, 0);
+        g_evIsBatch[g_evUsed] = 1;
         BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], g_stream));
     }
     ++g_launchCount;
@@ -1807,31 +1814,53 @@ BF_API unsigned long long bfGetLaunchCount(void) { return g_launchCount; }
 
 BF_API int bfTsdfSetProfiling(int enable) {
     g_profile = enable != 0;
-    g_evUsed = 0; g_profLaunches = 0; g_profFrames = 0;
+    g_evUsed = 0; g_profLaunches = 0; g_profFrames = 0; g_profBatchLaunches = 0; g_profBatchFrames = 0;
+    std::fill(g_evIsBatch.begin(), g_evIsBatch.end(), 0);
     std::lock_guard<std::mutex> lk(g_auxMutex);
-    for (auto& kv : g_aux) BF_CHECK(cudaMemsetAsync(kv.second.ctrs + CTR_U_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));   // restart the U / E sums
+    for (auto& kv : g_aux) {                    // restart the U / E sums
+        BF_CHECK(cudaMemsetAsync(kv.second.ctrs + CTR_U_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
+        BF_CHECK(cudaMemsetAsync(kv.second.ctrs + CTR_UB_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
+    }
     return 0;
 }
 
 // out[0] = stencil launches since bfTsdfSetProfiling(1), out[1] = launches that were timed, out[2] = their summed duration in ns,
 // out[3] = sum of U (voxels rewritten) over ALL launches since the last reset, out[4] = sum of E (blocks visited).  Synchronises.
-BF_API int bfTsdfGetProfile(const BFHashDataStruct* hd, unsigned long long out[8]) {
+// out[0..5] as bfTsdfGetProfile (all stencil launches); out[8] batch launches, out[9] of them timed, out[10] their summed duration (ns),
+// out[11] U of the batch launches, out[12] their E, out[13] frame images they read
+BF_API int bfTsdfGetProfileEx(const BFHashDataStruct* hd, unsigned long long out[16]) {
     TsdfAux* aux;
     int rc = get_aux(hd, nullptr, &aux, false);
     if (rc) return rc;
     BF_CHECK(cudaStreamSynchronize(g_stream));
-    double ms = 0.0;
-    for (size_t i = 0; i < g_evUsed; ++i) { float t = 0.0f; BF_CHECK(cudaEventElapsedTime(&t, g_evStart[i], g_evStop[i])); ms += t; }
+    double ms = 0.0, msB = 0.0; unsigned long long nB = 0;
+    for (size_t i = 0; i < g_evUsed; ++i) {
+        float t = 0.0f; BF_CHECK(cudaEventElapsedTime(&t, g_evStart[i], g_evStop[i])); ms += t;
+        if (i < g_evIsBatch.size() && g_evIsBatch[i]) { msB += t; ++nB; }
+    }
     unsigned c[CTR_NUM];
     BF_CHECK(cudaMemcpy(c, aux->ctrs, sizeof(c), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 16; ++k) out[k] = 0;
     out[0] = g_profLaunches; out[1] = g_evUsed; out[2] = (unsigned long long)(ms * 1e6);
     out[3] = ((unsigned long long)c[CTR_U_TOT_HI] << 32) | c[CTR_U_TOT_LO];
     out[4] = ((unsigned long long)c[CTR_E_TOT_HI] << 32) | c[CTR_E_TOT_LO];
     out[5] = g_profFrames;          // frame images read by those launches (a batch launch reads one per re-integration pair)
-    out[6] = out[7] = 0;
+    out[8] = g_profBatchLaunches; out[9] = nB; out[10] = (unsigned long long)(msB * 1e6);
+    out[11] = ((unsigned long long)c[CTR_UB_TOT_HI] << 32) | c[CTR_UB_TOT_LO];
+    out[12] = ((unsigned long long)c[CTR_EB_TOT_HI] << 32) | c[CTR_EB_TOT_LO];
+    out[13] = g_profBatchFrames;
     // restart accumulation
     BF_CHECK(cudaMemsetAsync(aux->ctrs + CTR_U_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
-    g_evUsed = 0; g_profLaunches = 0; g_profFrames = 0;
+    BF_CHECK(cudaMemsetAsync(aux->ctrs + CTR_UB_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
+    g_evUsed = 0; g_profLaunches = 0; g_profFrames = 0; g_profBatchLaunches = 0; g_profBatchFrames = 0;
+    std::fill(g_evIsBatch.begin(), g_evIsBatch.end(), 0);
+    return 0;
+}
+BF_API int bfTsdfGetProfile(const BFHashDataStruct* hd, unsigned long long out[8]) {
+    unsigned long long o[16];
+    const int rc = bfTsdfGetProfileEx(hd, o);
+    if (rc) return rc;
+    for (int k = 0; k < 8; ++k) out[k] = o[k];
     return 0;
 }
 

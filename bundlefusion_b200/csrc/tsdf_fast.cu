@@ -364,6 +364,7 @@ stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
     if ((t & 31) == 0 && passed) {
         atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[a.set + SET_U_LO]), (unsigned long long)passed);
         atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_UB_TOT_LO]), (unsigned long long)passed);
     }
 #else
     for (unsigned b = blockIdx.x; b < count; b += gridDim.x) { const unsigned j = BF_MULTI_ITEM(b); process_block_multi(a, o, t, a.work[j], a.workMask[j], passed); }

@@ -60,9 +60,42 @@ def _raycast(T: np.ndarray, W: int, H: int, fx: float, fy: float, mx: float, my:
     return t, p, obj, axis                                                           # t == camera-space z
 
 
+RICH_FREQS = (4.0, 9.0, 20.0, 45.0)         # lattice cells per metre of the four octaves of the "rich" texture
+
+
+def _lattice_hash(ix, iy, iz, salt):
+    """integer lattice point -> pseudo-random value in [0, 1); int64 arithmetic, the same formula as synth_gpu"""
+    h = (ix * 73856093) ^ (iy * 19349669) ^ (iz * 83492791) ^ salt
+    h = (h * 2654435761) & 0xFFFFFFFF
+    h = ((h ^ (h >> 15)) * 2246822519) & 0xFFFFFFFF
+    h = h ^ (h >> 13)
+    return (h & 0xFFFFFF).astype(np.float64) / float(1 << 24)
+
+
+def rich_texture(p: np.ndarray) -> np.ndarray:
+    """World-anchored multi-scale value noise in [0, 1] (trilinear, smooth-stepped lattice noise, four octaves): blobs from ~2 cm to ~25 cm,
+    so that a difference-of-Gaussians detector finds features at every pyramid level from any viewpoint -- the sinusoid texture of make_frame
+    yields ~14 SIFT key points per 320x240 frame, this one hundreds."""
+    acc = np.zeros(p.shape[:-1])
+    for o, f in enumerate(RICH_FREQS):
+        q = p * f
+        i0 = np.floor(q).astype(np.int64)
+        t = q - i0
+        t = t * t * (3.0 - 2.0 * t)
+        v = 0.0
+        for dx in (0, 1):
+            for dy in (0, 1):
+                for dz in (0, 1):
+                    w = (t[..., 0] if dx else 1 - t[..., 0]) * (t[..., 1] if dy else 1 - t[..., 1]) * (t[..., 2] if dz else 1 - t[..., 2])
+                    v = v + w * _lattice_hash(i0[..., 0] + dx, i0[..., 1] + dy, i0[..., 2] + dz, 1013 * (o + 1))
+        acc += v - 0.5
+    return np.clip(0.5 + 0.55 * acc, 0.0, 1.0)
+
+
 def make_frame(i: int, W: int = 640, H: int = 480, n_total: int = 5000, seed: int = 1234,
-               noise: bool = True, dropout: float = 0.02, pose: np.ndarray | None = None):
-    """Returns (depth float32 [H,W], color uint8 [H,W,4], pose float32 [4,4])."""
+               noise: bool = True, dropout: float = 0.02, pose: np.ndarray | None = None, texture: str = "sinusoid"):
+    """Returns (depth float32 [H,W], color uint8 [H,W,4], pose float32 [4,4]).  texture: "sinusoid"  or "rich"
+    (rich_texture: enough SIFT features for the frame loop to track on)."""
     T = lissajous_pose(i, n_total) if pose is None else np.asarray(pose, dtype=np.float32)
     fx = fy = 525.0 * W / 640.0
     mx, my = (W - 1) / 2.0, (H - 1) / 2.0
@@ -75,7 +108,10 @@ def make_frame(i: int, W: int = 640, H: int = 480, n_total: int = 5000, seed: in
         depth[rng.random(z.shape) < dropout] = -np.inf
     depth[~np.isfinite(z)] = -np.inf
     # procedural texture: sinusoids in world coordinates, different phase per surface
-    tex = 0.5 + 0.5 * np.sin(7.0 * p[..., 0] + 0.5 * axis) * np.sin(5.0 * p[..., 1] + 1.3) * np.sin(6.0 * p[..., 2] + obj)
+    if texture == "rich":
+        tex = rich_texture(p)
+    else:
+        tex = 0.5 + 0.5 * np.sin(7.0 * p[..., 0] + 0.5 * axis) * np.sin(5.0 * p[..., 1] + 1.3) * np.sin(6.0 * p[..., 2] + obj)
     base = np.array([[200, 180, 160], [220, 80, 60], [60, 200, 90], [70, 90, 230]], dtype=np.float64)[obj]
     rgb = np.clip(base * (0.35 + 0.65 * tex[..., None]), 0, 255).astype(np.uint8)
     color = np.concatenate([rgb, np.full((H, W, 1), 255, np.uint8)], axis=-1)

@@ -8,7 +8,29 @@ import numpy as np
 from . import synth
 
 
-def make_frames(indices, W=640, H=480, n_total=5000, seed=1234, device="cuda:0", noise=True, dropout=0.02):
+def _rich_texture(torch, p):
+    """synth.rich_texture in torch (same lattice hash, same octaves)"""
+    acc = torch.zeros(p.shape[:-1], dtype=torch.float64, device=p.device)
+    for o, f in enumerate(synth.RICH_FREQS):
+        q = p * f
+        i0 = torch.floor(q).to(torch.int64)
+        t = q - i0
+        t = t * t * (3.0 - 2.0 * t)
+        v = torch.zeros_like(acc)
+        for dx in (0, 1):
+            for dy in (0, 1):
+                for dz in (0, 1):
+                    w = (t[..., 0] if dx else 1 - t[..., 0]) * (t[..., 1] if dy else 1 - t[..., 1]) * (t[..., 2] if dz else 1 - t[..., 2])
+                    h = ((i0[..., 0] + dx) * 73856093) ^ ((i0[..., 1] + dy) * 19349669) ^ ((i0[..., 2] + dz) * 83492791) ^ (1013 * (o + 1))
+                    h = (h * 2654435761) & 0xFFFFFFFF
+                    h = ((h ^ (h >> 15)) * 2246822519) & 0xFFFFFFFF
+                    h = h ^ (h >> 13)
+                    v = v + w * ((h & 0xFFFFFF).to(torch.float64) / float(1 << 24))
+        acc = acc + (v - 0.5)
+    return torch.clamp(0.5 + 0.55 * acc, 0.0, 1.0)
+
+
+def make_frames(indices, W=640, H=480, n_total=5000, seed=1234, device="cuda:0", noise=True, dropout=0.02, texture="sinusoid"):
     """Returns (depth [B,H,W] float32, color [B,H,W,4] uint8, poses [B,4,4] float32 numpy) on `device`."""
     import torch
     dev = torch.device(device)
@@ -50,7 +72,10 @@ def make_frames(indices, W=640, H=480, n_total=5000, seed=1234, device="cuda:0",
         if dropout > 0:
             dep = torch.where(torch.rand(z.shape, generator=gen, device=dev) < dropout, torch.full_like(dep, float("-inf")), dep)
         depth[b] = dep
-        tex = 0.5 + 0.5 * torch.sin(7.0 * p[..., 0] + 0.5 * axis) * torch.sin(5.0 * p[..., 1] + 1.3) * torch.sin(6.0 * p[..., 2] + obj)
+        if texture == "rich":
+            tex = _rich_texture(torch, p)
+        else:
+            tex = 0.5 + 0.5 * torch.sin(7.0 * p[..., 0] + 0.5 * axis) * torch.sin(5.0 * p[..., 1] + 1.3) * torch.sin(6.0 * p[..., 2] + obj)
         rgb = torch.clamp(base[obj] * (0.35 + 0.65 * tex[..., None]), 0, 255).to(torch.uint8)
         color[b, ..., :3] = rgb
         color[b, ..., 3] = 255

@@ -265,6 +265,9 @@ int bfTsdfGetLastFrameStats(const BFHashDataStruct* hashData, unsigned long long
  *                       out[4] sum of E over those launches, out[5] frame images those launches read (one per launch, one per pair for a
  *                       batch launch); synchronises and restarts the accumulation. */
 unsigned long long bfGetLaunchCount(void);
+/* bfTsdfGetProfile plus the batch launches alone: out[8] batch launches, out[9] timed, out[10] their duration (ns), out[11] their U, out[12] their E,
+ * out[13] frame images they read (out[6..7], out[14..15] = 0) */
+int bfTsdfGetProfileEx(const BFHashDataStruct* hashData, unsigned long long out[16]);
 int bfTsdfSetProfiling(int enable);
 int bfTsdfGetProfile(const BFHashDataStruct* hashData, unsigned long long out[8]);
 
