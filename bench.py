@@ -29,6 +29,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 W, H = 640, 480
+LOOP_WORKLOAD = {
+    "workload": "configs[1]: synthetic 640x480 RGB-D stream through the whole frame loop (one bfFrameLoopStep per frame: ingest, SIFT detect, dense "
+                "cache, descriptor match + Kabsch / surface-area / dense-verify filters against the chunk, SIFT pose, <= 10 re-integrations + GC, "
+                "integrate; per 10-frame chunk local BA 11 frames sparse + dense 2 GN x 100 PCG with verification, fuse to keyframe, match against "
+                "all keyframes, global BA 3 GN x 150 PCG, trajectory update feeding the re-integration queue); hashed TSDF 1 cm voxels, 4M-block "
+                "heap, 4M buckets; the timed steps continue a stream of `preroll_frames` frames",
+    "frame": [W, H], "voxel_m": 0.010, "sdf_blocks": 4000000, "hash_buckets": 4000000, "reintegrations_per_frame": 10, "chunk": 10,
+    "texture": "world-anchored 4-octave value noise (synth.rich_texture): ~180 SIFT features per frame; camera on the Lissajous path of SURVEY 8d",
+    "l2_policy": "inputs larger than L2: every step reads a new 2.46 MB frame and re-integrates 10 stored frames (24.6 MB) against a voxel working set of several hundred MB; no explicit flush",
+}
 WORKLOAD = {
     "workload": "configs[1]: 640x480 RGB-D stream, hashed TSDF (1 cm voxels, 4M-block heap, 4M buckets), per frame 1 integrate + 10 "
                 "re-integrations (de-integrate + integrate) + GC; per 10-frame chunk 1 local BA (11 frames, 2 GN x 100 PCG) + 1 global BA "
@@ -45,7 +55,7 @@ METRIC = "frames/sec (TSDF integrate + global BA solve) on synthetic 640x480 RGB
 def clocks_sampler(stop_evt, out, gpu_index):
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     try:
-        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(gpu_index)],
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(gpu_index)],
                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except Exception:
         return
@@ -322,6 +332,135 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------------------------------------
+def run_loop(args):
+    """headline workload: the frame loop, one bfFrameLoopStep per frame"""
+    import torch
+    import torch.distributed as dist
+
+    from bundlefusion_b200 import _capi as capi
+    from bundlefusion_b200 import synth_gpu
+    from bundlefusion_b200.frame_loop import FrameLoop, default_params
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = capi.lib()
+    K, Wm, pre = args.steps, args.warmup, args.preroll
+    total = pre + Wm + 3 * K                       # pre-roll, warm-up, timed pass, profiled pass, end-to-end pass: one continuous stream
+    P = default_params(W, H)
+    P.maxNumFrames = total + 8
+    P.maxNumImages = total // 10 + 8
+    P.maxGlobalResiduals = 25 * P.maxNumImages * 48
+    P.hash.m_hashNumBuckets = LOOP_WORKLOAD["hash_buckets"]; P.hash.m_numSDFBlocks = LOOP_WORKLOAD["sdf_blocks"]
+    if world > 1:
+        P.hash.m_dummy = (world << 32) | rank                   # spatial shard of the voxel hash: this rank integrates the blocks it owns
+    clk_lines, stop_evt = [], threading.Event()
+    th = threading.Thread(target=clocks_sampler, args=(stop_evt, clk_lines, local), daemon=True); th.start()
+    loop = FrameLoop(P, dev)
+    # frame bank on the device, generated in slices (input generation, never timed); the stream advances 2 frames of the Lissajous path per step
+    depth = torch.empty(total, H, W, dtype=torch.float32, device=dev); color = torch.empty(total, H, W, 4, dtype=torch.uint8, device=dev)
+    for s0 in range(0, total, 64):
+        idx = [args.stride * i for i in range(s0, min(total, s0 + 64))]
+        d, c, _ = synth_gpu.make_frames(idx, W, H, device=str(dev), texture="rich")
+        depth[s0:s0 + len(idx)] = d; color[s0:s0 + len(idx)] = c
+    torch.cuda.synchronize()
+    f_e2e0 = pre + Wm + 2 * K
+    h_depth = depth[f_e2e0:f_e2e0 + K].cpu().pin_memory(); h_color = color[f_e2e0:f_e2e0 + K].cpu().pin_memory()
+    stats = {"valid": 0, "local": 0, "local_valid": 0, "global": 0, "reint": 0, "kp": 0, "n": 0}
+
+    def note(st):
+        stats["n"] += 1; stats["valid"] += st.validTransform; stats["reint"] += st.numReintegrated; stats["kp"] += st.numKeyPoints
+        stats["local"] += 1 if st.localSolved >= 0 else 0; stats["local_valid"] += st.localValid; stats["global"] += st.globalSolved
+
+    for f in range(pre):                                   # pre-roll: the state a long stream is in (keyframes, trajectory, populated hash)
+        loop.step(depth[f], color[f])
+    torch.cuda.synchronize()
+
+    def timed(f0, n, e2e, profile):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            L.bfTsdfSetProfiling(1)
+        l0 = L.bfGetLaunchCount()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(n):
+            st = loop.step(h_depth[k], h_color[k]) if e2e else loop.step(depth[f0 + k], color[f0 + k])
+            if not profile:
+                note(st)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item()); dist.barrier()
+        return ms, L.bfGetLaunchCount() - l0
+
+    timed(pre, Wm, False, False)
+    for k in stats: stats[k] = 0
+    clk_mark0 = len(clk_lines)
+    ms, launches = timed(pre + Wm, K, False, False)
+    clk_mark1 = len(clk_lines)
+    c_before = loop.counters()
+    prev_lanes = L.bfTsdfSetLanes(0)                       # the stencil is timed alone on its stream: the burst HBM peak is its roof
+    timed(pre + Wm + K, K, False, True)
+    L.bfTsdfSetLanes(prev_lanes)
+    prof = (ctypes.c_ulonglong * 16)()
+    capi.check(L.bfTsdfGetProfileEx(L.bfFrameLoopGetHashData(loop._h), prof), "bfTsdfGetProfileEx")
+    L.bfTsdfSetProfiling(0)
+    clk_mark2 = len(clk_lines)
+    ms_e2e, _ = timed(f_e2e0, K, True, False)
+    stop_evt.set()
+    heap_free = loop.heap_free()
+    cnt = loop.counters()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, peak_kind = measured_peaks()
+    use_batch = int(prof[9]) > 0
+    n_launch, n_timed, ns, U, E, n_img = (int(prof[9]), int(prof[9]), int(prof[10]), int(prof[11]), int(prof[12]), int(prof[13])) if use_batch else \
+                                         (int(prof[0]), int(prof[1]), int(prof[2]), int(prof[3]), int(prof[4]), max(int(prof[5]), int(prof[0])))
+    alg_bytes = 24.0 * U + 20.0 * E + n_img * 2.0 * W * H * 4.0        # SURVEY 8d: 24 B x U + 20 B x E + 2 x W x H x 4 B per frame image read
+    ach = (alg_bytes * (n_timed / max(1, n_launch))) / max(1e-9, ns * 1e-9) / 1e9 if n_timed else 0.0
+    roof = {"kernel": "stencil_multi_kernel (TSDF stencil: a frame's re-integration batch, every voxel of the union list read and written once)" if use_batch else "stencil_fast_kernel",
+            "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
+            "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None, "launches": n_launch, "avg_launch_us": round(ns / max(1, n_timed) / 1e3, 2),
+            "algorithmic_bytes_per_launch": round(alg_bytes / max(1, n_launch)), "U_per_launch": round(U / max(1, n_launch)), "E_per_launch": round(E / max(1, n_launch)),
+            "frames_per_launch": round(n_img / max(1, n_launch), 2),
+            "avg_launch_us_device_timer": round(int(prof[14]) / max(1, n_timed) / 1e3, 2) if use_batch and int(prof[14]) else None,
+            "all_stencil_launches": {"launches": int(prof[0]), "avg_launch_us": round(int(prof[2]) / max(1, int(prof[1])) / 1e3, 2)},
+            "mvoxels_per_s": round(512.0 * E / max(1e-9, ns * 1e-9) / 1e6, 1)}
+    tpath = os.path.join(ROOT, "profiles", "r2_stencil_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)); roof["traffic"] = tj.get("dram_bytes_per_launch"); roof["traffic_note"] = tj.get("note")
+    steps_meas = max(1, stats["n"])
+    out = {
+        "metric": METRIC, "value": round(K / (ms / 1e3), 2), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(LOOP_WORKLOAD, preroll_frames=pre, frame_stride=args.stride,
+                       parallelism=("single GPU" if world == 1 else f"voxel hash sharded over {world} GPUs by block owner (each rank integrates its blocks); SIFT / bundling replicated per rank (deterministic inputs, no exchange)"),
+                       active_blocks=int(LOOP_WORKLOAD["sdf_blocks"] - heap_free), keyframes=cnt["keyframes"], global_pcg_iters_last_solve=cnt["global_pcg_iters"],
+                       in_timed_steps={"frames_with_pose": stats["valid"], "reintegrations_per_frame": round(stats["reint"] / steps_meas, 2), "keypoints_per_frame": round(stats["kp"] / steps_meas, 1),
+                                       "local_solves": stats["local"], "local_solves_accepted": stats["local_valid"], "global_solves": stats["global"]},
+                       host_syncs_per_frame=round((cnt["host_syncs"]) / max(1, cnt["frames"]), 2)),
+        "e2e": {"value": round(K / (ms_e2e / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": W * H * 8, "d2h_bytes_per_step": 120 + 64 + 8,
+                "note": "bfFrameLoopStep with HOST (pinned) depth + colour pointers: the upload happens inside the call, as CUDAImageManager::process uploads on arrival; read back per step: the status block (pose of the frame), the SIFT pose and the match verdict"},
+        "gpu_launches": int(launches), "roofline": roof, "tsdf_arithmetic": "fast",
+        "clocks": summarize_clocks(clk_lines[clk_mark0:clk_mark1]), "clocks_profile_pass": summarize_clocks(clk_lines[clk_mark1:clk_mark2]),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_arm(1, 0, quiet=True, n_reint=2)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
 # ------------------------------------------------------------------------------------------------------------------------
 def cpu_arm(steps, warmup, quiet=False, n_reint=None):
     """The reference's algorithm on the host cores: oracle port (liboracle_fast.so: -O3 -march=native, OpenMP over blocks for the
@@ -386,18 +525,23 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true", help="diagnostic: leave the bundle-adjustment solves out (the JSON line is then NOT a bench value)")
+    ap.add_argument("--workload", default="loop", choices=["loop", "ops"], help="loop: the whole frame loop (headline); ops: TSDF op replay + synthetic BA problems (round-1 bench, kept for A/B)")
+    ap.add_argument("--preroll", type=int, default=600, help="frames streamed through the loop before warm-up (state of a long stream)")
+    ap.add_argument("--stride", type=int, default=2, help="Lissajous path frames per step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.workload == "ops":
         run_ours(args)
+    else:
+        run_loop(args)
 
 
 if __name__ == "__main__":

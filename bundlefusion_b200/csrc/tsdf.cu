@@ -79,7 +79,8 @@ static size_t g_evUsed = 0;
 static unsigned long long g_profLaunches = 0;
 static unsigned long long g_profFrames = 0;
 static unsigned long long g_profBatchLaunches = 0, g_profBatchFrames = 0;
-static std::vector<unsigned char> g_evIsBatch;      // frame images the profiled stencil launches read (a batch launch reads one per pair)
+static std::vector<unsigned char> g_evIsBatch;
+static unsigned long long* g_ktime = nullptr;        // [kMaxProfiledLaunches][2] in-kernel %globaltimer brackets of the profiled batch launches      // frame images the profiled stencil launches read (a batch launch reads one per pair)
 static const size_t kMaxProfiledLaunches = 16384;
 
 static std::mutex g_auxMutex;
@@ -1755,11 +1756,14 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
         if (g_evStart.size() <= g_evUsed) { cudaEvent_t a, b; BF_CHECK(cudaEventCreate(&a)); BF_CHECK(cudaEventCreate(&b)); g_evStart.push_back(a); g_evStop.push_back(b); }
         if (g_evIsBatch.size() <= g_evUsed) g_evIsBatch.resize(g_evUsed + 1, 0);
         g_evIsBatch[g_evUsed] = 1;
+        if (!g_ktime) BF_CHECK(cudaMalloc(&g_ktime, sizeof(unsigned long long) * 2 * kMaxProfiledLaunches));
+        BF_CHECK(cudaMemsetAsync(g_ktime + 2 * g_evUsed, 0xff, sizeof(unsigned long long), g_stream));
+        BF_CHECK(cudaMemsetAsync(g_ktime + 2 * g_evUsed + 1, 0, sizeof(unsigned long long), g_stream));
         BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], g_stream));
     }
     ++g_launchCount;
     rc = launch_reintegrate_multi_fast(hd, desc, numPairs, cp, aux->work2[aux->parity], aux->workMask, aux->numSlots, set, aux->ctrs, aux->live,
-                                       grid_for(hp->m_numSDFBlocks, fast_stencil_ctas_per_sm(true)), g_stream);
+                                       grid_for(hp->m_numSDFBlocks, fast_stencil_ctas_per_sm(true)), g_stream, timeIt ? g_ktime + 2 * g_evUsed : nullptr);
     if (rc) return rc;
     if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], g_stream)); ++g_evUsed; }
     *hp = hpNew[numPairs - 1];
@@ -1849,6 +1853,13 @@ BF_API int bfTsdfGetProfileEx(const BFHashDataStruct* hd, unsigned long long out
     out[11] = ((unsigned long long)c[CTR_UB_TOT_HI] << 32) | c[CTR_UB_TOT_LO];
     out[12] = ((unsigned long long)c[CTR_EB_TOT_HI] << 32) | c[CTR_EB_TOT_LO];
     out[13] = g_profBatchFrames;
+    if (g_ktime && g_evUsed) {          // out[14]: the batch launches' duration by the in-kernel %globaltimer brackets (first CTA start -> last CTA end), ns
+        std::vector<unsigned long long> kt(2 * g_evUsed);
+        BF_CHECK(cudaMemcpy(kt.data(), g_ktime, sizeof(unsigned long long) * 2 * g_evUsed, cudaMemcpyDeviceToHost));
+        unsigned long long sum = 0;
+        for (size_t i = 0; i < g_evUsed; ++i) if (i < g_evIsBatch.size() && g_evIsBatch[i] && kt[2 * i + 1] > kt[2 * i]) sum += kt[2 * i + 1] - kt[2 * i];
+        out[14] = sum;
+    }
     // restart accumulation
     BF_CHECK(cudaMemsetAsync(aux->ctrs + CTR_U_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
     BF_CHECK(cudaMemsetAsync(aux->ctrs + CTR_UB_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));

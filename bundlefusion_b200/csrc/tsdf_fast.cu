@@ -40,6 +40,7 @@ struct MultiOp { FastPose A, B; const float* depth; const unsigned* color; };
 struct MultiArgs {
     BFVoxel* blocks; const int4* work; const unsigned* workMask; unsigned* ctrs; int* live; int* listCounterOut;
     int set; int nOps; unsigned workCap;
+    unsigned long long* ktime;       // optional {min CTA start, max CTA end} in %globaltimer ns (measurement only)
     FastCam cam;
     MultiOp ops[BF_MULTI_MAX_OPS];
 };
@@ -333,6 +334,9 @@ stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
     ThreadVoxel o;
     o.lx = (int)((4 * t) & 7); o.ly = (int)(((4 * t) & 63) >> 3); o.lz = (int)((4 * t) >> 6);
     unsigned passed = 0;
+#ifndef BF_EMU_SEQUENTIAL
+    if (a.ktime && t == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMin(&a.ktime[0], g); }
+#endif
 #define BF_MULTI_ITEM(i) ((i) < nHeavy ? (i) : a.workCap - 1u - ((i) - nHeavy))
 #ifndef BF_EMU_SEQUENTIAL
     __shared__ int4 sWork[2];
@@ -366,6 +370,7 @@ stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
         atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed);
         atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_UB_TOT_LO]), (unsigned long long)passed);
     }
+    if (a.ktime && t == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMax(&a.ktime[1], g); }
 #else
     for (unsigned b = blockIdx.x; b < count; b += gridDim.x) { const unsigned j = BF_MULTI_ITEM(b); process_block_multi(a, o, t, a.work[j], a.workMask[j], passed); }
     if (passed) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[a.set + SET_U_LO]), (unsigned long long)passed); atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed); }
@@ -416,11 +421,11 @@ int launch_reintegrate_fast(const BFHashDataStruct* hd, const BFHashParams* hpOl
 }
 
 int launch_reintegrate_multi_fast(const BFHashDataStruct* hd, const BFMultiOpDesc* ops, int nOps, const BFDepthCameraParams* cp, const int4* work,
-                                  const unsigned* workMask, unsigned workCap, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s) {
+                                  const unsigned* workMask, unsigned workCap, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s, unsigned long long* ktime) {
     if (nOps < 1 || nOps > BF_MULTI_MAX_OPS) return (int)cudaErrorInvalidValue;
     static MultiArgs a;                      // ~2.5 KB: kept off the stack; filled and passed by value at the launch
     a.blocks = hd->d_SDFBlocks; a.work = work; a.workMask = workMask; a.ctrs = ctrs; a.live = live; a.listCounterOut = hd->d_hashCompactifiedCounter;
-    a.set = set; a.nOps = nOps; a.workCap = workCap;
+    a.set = set; a.nOps = nOps; a.workCap = workCap; a.ktime = ktime;
     a.cam.W = cp->m_imageWidth; a.cam.H = cp->m_imageHeight; a.cam.fx = cp->fx; a.cam.fy = cp->fy; a.cam.mx5 = cp->mx + 0.5f; a.cam.my5 = cp->my + 0.5f;
     for (int k = 0; k < nOps; ++k) {
         make_pose(ops[k].hpOld, &a.ops[k].A); make_pose(ops[k].hpNew, &a.ops[k].B);

@@ -29,6 +29,7 @@ int fast_stencil_ctas_per_sm(bool fused);
 #define BF_MULTI_MAX_OPS 16
 struct BFMultiOpDesc { const BFHashParams* hpOld; const BFHashParams* hpNew; const float* depth; const void* color; };
 int launch_reintegrate_multi_fast(const BFHashDataStruct* hd, const BFMultiOpDesc* ops, int nOps, const BFDepthCameraParams* cp, const int4* work,
-                                  const unsigned* workMask, unsigned workCap, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s);
+                                  const unsigned* workMask, unsigned workCap, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s,
+                                  unsigned long long* ktime = nullptr);
 
 }  // namespace bf
