@@ -67,7 +67,7 @@ struct TsdfAux {
     bool pipeOpen = false;
     // batch re-integration (tsdf_reintegrate_batch): per slot the (batch id << 8 | op index) of the alloc launch that inserted the block,
     // per work item the 2-bit-per-op frustum mask
-    unsigned* slotEpoch = nullptr; unsigned* workMask = nullptr; unsigned batchId = 0;
+    unsigned* slotEpoch = nullptr; unsigned* workMask = nullptr; unsigned* workMask2 = nullptr; unsigned batchId = 0;
     const void* owner[3] = { nullptr, nullptr, nullptr };   // the caller's d_SDFBlocks / d_heap / d_hashCompactified: the key (d_hash) can be
                                                             // recycled by an allocator for another table; all four together identify one
 };
@@ -1061,7 +1061,8 @@ struct MultiFrusta { int nOps; float voxelSize; BFFloat4x4 inv[2 * BF_MULTI_MAX_
 __global__ void __launch_bounds__(256)
 compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta fr, const __grid_constant__ BFDepthCameraParams cp,
                         const int4* __restrict__ slotInfo, const unsigned* __restrict__ slotEpoch, unsigned batchId, unsigned* ctrs, int set,
-                        unsigned char* __restrict__ listFlags, int4* __restrict__ work, unsigned* __restrict__ workMask, unsigned workCap) {
+                        unsigned char* __restrict__ listFlags, int4* __restrict__ workA, int4* __restrict__ workB, unsigned* __restrict__ maskA,
+                        unsigned* __restrict__ maskB, unsigned workCap) {
     const unsigned highWater = ctrs[CTR_HIGH_WATER];
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned stride = gridDim.x * blockDim.x;
@@ -1088,22 +1089,25 @@ compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta
             const unsigned bits = (unsigned)__popc(mask);
             unsigned nE = bits;
             for (int o = 16; o > 0; o >>= 1) nE += __shfl_xor_sync(0xffffffffu, nE, o);
-            // Work order: a block's cost grows with the number of (op, pose) probes it takes -- up to 2 nOps of them.  Heavy blocks (at
-            // least nOps probes) are listed from the front of the work array, light ones from its back, and the stencil deals the heavy ones
-            // first: the kernel then ends on cheap blocks instead of on a few 20-probe blocks (longest-processing-time-first).
-            const bool heavy = mask != 0 && bits >= (unsigned)fr.nOps;
-            const unsigned ballotH = __ballot_sync(0xffffffffu, heavy), ballotL = ballot & ~ballotH;
-            unsigned warpBase = 0, heavyBase = 0, lightBase = 0;
+            // Work order: a block's cost grows with the number of (op, pose) probes it takes -- up to 2 nOps of them, ~60 k cycles for a CTA at
+            // 20.  Items go to four buckets by cost quartile and the stencil deals the costliest bucket first (longest-processing-time-first), so
+            // the kernel ends on cheap blocks and its tail is a quartile-0 block, not a 20-probe one.
+            const unsigned n2 = 2u * (unsigned)fr.nOps;
+            const int q = (mask == 0) ? -1 : (4u * bits > 3u * n2 ? 3 : (2u * bits > n2 ? 2 : (4u * bits > n2 ? 1 : 0)));
+            const unsigned b3 = __ballot_sync(0xffffffffu, q == 3), b2 = __ballot_sync(0xffffffffu, q == 2), b1 = __ballot_sync(0xffffffffu, q == 1), b0 = __ballot_sync(0xffffffffu, q == 0);
+            unsigned warpBase = 0, base3 = 0, base2 = 0, base1 = 0, base0 = 0;
             if (lane == 0) {
                 warpBase = atomicAdd(&ctrs[set + SET_COUNT], __popc(ballot));
-                if (ballotH) heavyBase = atomicAdd(&ctrs[set + SET_WORK], __popc(ballotH));
-                if (ballotL) lightBase = atomicAdd(&ctrs[set + SET_CULLED], __popc(ballotL));      // the batch has no cull: the slot counts the light items
+                if (b3) base3 = atomicAdd(&ctrs[set + SET_WORK], __popc(b3));
+                if (b2) base2 = atomicAdd(&ctrs[set + SET_CULLED], __popc(b2));      // the batch has no cull: the slot counts quartile-2 items
+                if (b1) base1 = atomicAdd(&ctrs[set + SET_Q1], __popc(b1));
+                if (b0) base0 = atomicAdd(&ctrs[set + SET_Q0], __popc(b0));
                 atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_E_TOT_LO]), (unsigned long long)nE);
                 atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_EB_TOT_LO]), (unsigned long long)nE);
             }
             warpBase = __shfl_sync(0xffffffffu, warpBase, 0);
-            heavyBase = __shfl_sync(0xffffffffu, heavyBase, 0);
-            lightBase = __shfl_sync(0xffffffffu, lightBase, 0);
+            base3 = __shfl_sync(0xffffffffu, base3, 0); base2 = __shfl_sync(0xffffffffu, base2, 0);
+            base1 = __shfl_sync(0xffffffffu, base1, 0); base0 = __shfl_sync(0xffffffffu, base0, 0);
             if (mask) {
                 const unsigned below = (1u << lane) - 1u;
                 const unsigned k = warpBase + __popc(ballot & below);
@@ -1114,9 +1118,12 @@ compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta
                 hd.d_hashCompactified[k] = en;
                 // the reference's GC walks the list of the LAST integrate (DepthSensing.cpp:901): bit 1 = in the last op's new-pose frustum
                 listFlags[k] = (unsigned char)(((mask >> (2 * (fr.nOps - 1))) & 2u) | 1u);
-                const unsigned w = heavy ? heavyBase + __popc(ballotH & below) : (workCap - 1u) - (lightBase + __popc(ballotL & below));
-                work[w] = make_int4(info.x, info.y, info.z, (int)slot);
-                workMask[w] = mask;
+                int4* const wArr = (q >= 2) ? workA : workB;
+                unsigned* const mArr = (q >= 2) ? maskA : maskB;
+                const unsigned w = (q == 3) ? base3 + __popc(b3 & below) : (q == 2) ? (workCap - 1u) - (base2 + __popc(b2 & below))
+                                 : (q == 1) ? base1 + __popc(b1 & below) : (workCap - 1u) - (base0 + __popc(b0 & below));
+                wArr[w] = make_int4(info.x, info.y, info.z, (int)slot);
+                mArr[w] = mask;
             }
         }
     }
@@ -1373,7 +1380,7 @@ gc_live_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, con
 // ------------------------------------------------------------------------------------------
 static void free_aux(TsdfAux& a) {
     cudaFree(a.slotInfo); cudaFree(a.ctrs); cudaFree(a.live); cudaFree(a.listFlags); cudaFree(a.work2[0]); cudaFree(a.work2[1]); cudaFree(a.tiles);
-    cudaFree(a.slotEpoch); cudaFree(a.workMask);
+    cudaFree(a.slotEpoch); cudaFree(a.workMask); cudaFree(a.workMask2);
     if (a.lane) cudaStreamDestroy(a.lane);
     if (a.evFork) cudaEventDestroy(a.evFork);
     for (int k = 0; k < 2; ++k) { if (a.evList[k]) cudaEventDestroy(a.evList[k]); if (a.evStencil[k]) cudaEventDestroy(a.evStencil[k]); }
@@ -1719,6 +1726,7 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
     if (!aux->slotEpoch) {
         BF_CHECK(cudaMalloc(&aux->slotEpoch, sizeof(unsigned) * (size_t)aux->numSlots));
         BF_CHECK(cudaMalloc(&aux->workMask, sizeof(unsigned) * (size_t)aux->numSlots));
+        BF_CHECK(cudaMalloc(&aux->workMask2, sizeof(unsigned) * (size_t)aux->numSlots));
         BF_CHECK(cudaMemsetAsync(aux->slotEpoch, 0, sizeof(unsigned) * (size_t)aux->numSlots, g_stream));
         aux->batchId = 0;
     }
@@ -1748,7 +1756,7 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
     const int set = set_of(aux->parity);
     ++g_launchCount;
     compactify_multi_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, fr, *cp, aux->slotInfo, aux->slotEpoch, aux->batchId, aux->ctrs, set,
-                                                                                                 aux->listFlags, aux->work2[aux->parity], aux->workMask, aux->numSlots);
+                                                                                                 aux->listFlags, aux->work2[aux->parity], aux->work2[aux->parity ^ 1u], aux->workMask, aux->workMask2, aux->numSlots);
     BF_CHECK(cudaGetLastError());
     const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
     if (g_profile) { ++g_profLaunches; g_profFrames += (unsigned long long)numPairs; ++g_profBatchLaunches; g_profBatchFrames += (unsigned long long)numPairs; }
@@ -1762,7 +1770,7 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
         BF_CHECK(cudaEventRecord(g_evStart[g_evUsed], g_stream));
     }
     ++g_launchCount;
-    rc = launch_reintegrate_multi_fast(hd, desc, numPairs, cp, aux->work2[aux->parity], aux->workMask, aux->numSlots, set, aux->ctrs, aux->live,
+    rc = launch_reintegrate_multi_fast(hd, desc, numPairs, cp, aux->work2[aux->parity], aux->work2[aux->parity ^ 1u], aux->workMask, aux->workMask2, aux->numSlots, set, aux->ctrs, aux->live,
                                        grid_for(hp->m_numSDFBlocks, fast_stencil_ctas_per_sm(true)), g_stream, timeIt ? g_ktime + 2 * g_evUsed : nullptr);
     if (rc) return rc;
     if (timeIt) { BF_CHECK(cudaEventRecord(g_evStop[g_evUsed], g_stream)); ++g_evUsed; }

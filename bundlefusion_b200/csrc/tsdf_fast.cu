@@ -38,7 +38,7 @@ struct FastArgs {
 };
 struct MultiOp { FastPose A, B; const float* depth; const unsigned* color; };
 struct MultiArgs {
-    BFVoxel* blocks; const int4* work; const unsigned* workMask; unsigned* ctrs; int* live; int* listCounterOut;
+    BFVoxel* blocks; const int4* workA; const int4* workB; const unsigned* maskA; const unsigned* maskB; unsigned* ctrs; int* live; int* listCounterOut;
     int set; int nOps; unsigned workCap;
     unsigned long long* ktime;       // optional {min CTA start, max CTA end} in %globaltimer ns (measurement only)
     FastCam cam;
@@ -149,6 +149,33 @@ __device__ __forceinline__ void deintegrate_fast(float sdf, unsigned col, unsign
     wSdf = __float_as_uint(nSdf); wWeight = __float_as_uint(den); wColor = nc;
 }
 
+// de-integrate sample D then integrate sample I of the same voxel (the re-integration pair, both poses pass): the two updates of
+// .cu:486-514 composed.  sdf: ((s w - sD) / (w - 1) (w - 1) + sI) / w = (s w - sD + sI) / w -- one reciprocal, and the weight returns to w;
+// colour: the de-integrated value is still rounded to a whole level before the 0.2 / 0.8 blend (as the byte the reference stores in between),
+// but stays in a float register.  A voxel the de-integration clears (w - 1 <= 0.001) takes sample I as its first.
+__device__ __forceinline__ void reintegrate_fast(const FastPose& pB, float sdfD, unsigned colD, float sdfI, unsigned colI, unsigned& wSdf, unsigned& wWeight, unsigned& wColor) {
+    const float oldSdf = __uint_as_float(wSdf), oldW = __uint_as_float(wWeight);
+    const float den = oldW - 1.0f;
+    unsigned nc = 0xFF000000u;
+    if (!(den > 0.001f)) {
+        nc = put_byte<0>(nc, min(colI & 0xffu, 254u)); nc = put_byte<1>(nc, min((colI >> 8) & 0xffu, 254u)); nc = put_byte<2>(nc, min((colI >> 16) & 0xffu, 254u));
+        wSdf = __float_as_uint(sdfI); wWeight = __float_as_uint(fminf(pB.wMax, 1.0f)); wColor = nc;
+        return;
+    }
+    const float nSdf = fmaf(oldSdf, oldW, sdfI - sdfD) * rcp_approx(oldW);
+    const float rb = rcp_approx(den) * 1.00000095367431640625f;          // see deintegrate_fast
+#define BF_REINT_CHANNEL(K)                                                                                                                   \
+    {                                                                                                                                         \
+        const float qd = fminf(fmaxf(fmaf(byte_to_float<K>(wColor), oldW, -byte_to_float<K>(colD)) * rb, 0.0f), 254.4f);                      \
+        const float cd = (qd + 8388608.0f) - 8388608.0f;                              /* the de-integrated level, a whole number <= 254 */    \
+        const float q = fmaf(0.2f, byte_to_float<K>(colI), 0.8f * cd);                 /* fraction a multiple of 0.2: never a tie; <= 254.2 */  \
+        nc = put_byte<K>(nc, __float_as_uint(q + 8388608.0f));                                                                               \
+    }
+    BF_REINT_CHANNEL(0) BF_REINT_CHANNEL(1) BF_REINT_CHANNEL(2)
+#undef BF_REINT_CHANNEL
+    wSdf = __float_as_uint(nSdf); wWeight = __float_as_uint(fminf(pB.wMax, oldW)); wColor = nc;
+}
+
 template <int MODE>
 __device__ __forceinline__ void update_fast(const FastPose& pA, const FastPose& pB, bool passA, float sdfA, unsigned colA, bool passB, float sdfB, unsigned colB,
                                             unsigned& wSdf, unsigned& wWeight, unsigned& wColor, int& liveDelta) {
@@ -156,8 +183,9 @@ __device__ __forceinline__ void update_fast(const FastPose& pA, const FastPose& 
     if (MODE == 0) { integrate_fast(pA, sdfA, colA, wSdf, wWeight, wColor); }
     else if (MODE == 1) { deintegrate_fast(sdfA, colA, wSdf, wWeight, wColor); }
     else {
-        if (passA) deintegrate_fast(sdfA, colA, wSdf, wWeight, wColor);
-        if (passB) integrate_fast(pB, sdfB, colB, wSdf, wWeight, wColor);
+        if (passA && passB) reintegrate_fast(pB, sdfA, colA, sdfB, colB, wSdf, wWeight, wColor);
+        else if (passA) deintegrate_fast(sdfA, colA, wSdf, wWeight, wColor);
+        else integrate_fast(pB, sdfB, colB, wSdf, wWeight, wColor);
     }
     liveDelta += (int)(__uint_as_float(wWeight) > 0.0f) - (int)wasLive;
 }
@@ -327,8 +355,9 @@ stencil_fast_kernel(const __grid_constant__ FastArgs a) {
 // batch re-integration: the same persistent grid and dynamic deal over the union list, every block visited once for up to 16 ops
 __global__ void __launch_bounds__(128, BF_FAST_MINBLOCKS_FUSED)
 stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
-    // ticket i -> work item: the heavy items first (front of the array), then the light ones (from the back)
-    const unsigned nHeavy = a.ctrs[a.set + SET_WORK], nLight = a.ctrs[a.set + SET_CULLED], count = nHeavy + nLight;
+    // ticket i -> work item: the four cost buckets in order, costliest first (layout: tsdf_shared.cuh)
+    const unsigned n3 = a.ctrs[a.set + SET_WORK], n2 = a.ctrs[a.set + SET_CULLED], n1 = a.ctrs[a.set + SET_Q1], n0 = a.ctrs[a.set + SET_Q0];
+    const unsigned e3 = n3, e2 = n3 + n2, e1 = e2 + n1, count = e1 + n0;
     const unsigned t = threadIdx.x;
     if (blockIdx.x == 0 && t == 0) { const unsigned listCount = a.ctrs[a.set + SET_COUNT]; a.listCounterOut[0] = (int)listCount; a.ctrs[CTR_E] = listCount; }
     ThreadVoxel o;
@@ -337,18 +366,25 @@ stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
 #ifndef BF_EMU_SEQUENTIAL
     if (a.ktime && t == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMin(&a.ktime[0], g); }
 #endif
-#define BF_MULTI_ITEM(i) ((i) < nHeavy ? (i) : a.workCap - 1u - ((i) - nHeavy))
+#define BF_MULTI_LOAD(i, W, M)                                                                                              \
+    do {                                                                                                                    \
+        const unsigned _i = (i);                                                                                            \
+        if (_i < e3)      { W = __ldg(&a.workA[_i]);                          M = __ldg(&a.maskA[_i]); }                    \
+        else if (_i < e2) { const unsigned _j = a.workCap - 1u - (_i - e3); W = __ldg(&a.workA[_j]); M = __ldg(&a.maskA[_j]); } \
+        else if (_i < e1) { const unsigned _j = _i - e2;                     W = __ldg(&a.workB[_j]); M = __ldg(&a.maskB[_j]); } \
+        else              { const unsigned _j = a.workCap - 1u - (_i - e1); W = __ldg(&a.workB[_j]); M = __ldg(&a.maskB[_j]); } \
+    } while (0)
 #ifndef BF_EMU_SEQUENTIAL
     __shared__ int4 sWork[2];
     __shared__ unsigned sMask[2];
     const int4 kEnd = make_int4(0, 0, 0, -1);
     unsigned* const ticket = &a.ctrs[a.set + SET_TICKET];
     int4 wCur = kEnd; unsigned mCur = 0;
-    if (blockIdx.x < count) { const unsigned j = BF_MULTI_ITEM(blockIdx.x); wCur = __ldg(&a.work[j]); mCur = __ldg(&a.workMask[j]); }
+    if (blockIdx.x < count) BF_MULTI_LOAD(blockIdx.x, wCur, mCur);
     int4 wNext = kEnd; unsigned mNext = 0, iAfter = 0xFFFFFFFFu;
     if (t == 0) {
         const unsigned i1 = gridDim.x + atomicAdd(ticket, 1u);
-        if (i1 < count) { const unsigned j = BF_MULTI_ITEM(i1); wNext = __ldg(&a.work[j]); mNext = __ldg(&a.workMask[j]); }
+        if (i1 < count) BF_MULTI_LOAD(i1, wNext, mNext);
         iAfter = gridDim.x + atomicAdd(ticket, 1u);
     }
     unsigned parity = 0;
@@ -357,7 +393,7 @@ stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
         if (t == 0) {
             sWork[parity] = wNext; sMask[parity] = mNext;
             wNext = kEnd; mNext = 0;
-            if (iAfter < count) { const unsigned j = BF_MULTI_ITEM(iAfter); wNext = __ldg(&a.work[j]); mNext = __ldg(&a.workMask[j]); iAfter = gridDim.x + atomicAdd(ticket, 1u); }
+            if (iAfter < count) { BF_MULTI_LOAD(iAfter, wNext, mNext); iAfter = gridDim.x + atomicAdd(ticket, 1u); }
             else iAfter = 0xFFFFFFFFu;
         }
         __syncthreads();
@@ -372,10 +408,10 @@ stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
     }
     if (a.ktime && t == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMax(&a.ktime[1], g); }
 #else
-    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) { const unsigned j = BF_MULTI_ITEM(b); process_block_multi(a, o, t, a.work[j], a.workMask[j], passed); }
+    for (unsigned b = blockIdx.x; b < count; b += gridDim.x) { int4 w; unsigned m; BF_MULTI_LOAD(b, w, m); process_block_multi(a, o, t, w, m, passed); }
     if (passed) { atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[a.set + SET_U_LO]), (unsigned long long)passed); atomicAdd(reinterpret_cast<unsigned long long*>(&a.ctrs[CTR_U_TOT_LO]), (unsigned long long)passed); }
 #endif
-#undef BF_MULTI_ITEM
+#undef BF_MULTI_LOAD
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
@@ -420,11 +456,12 @@ int launch_reintegrate_fast(const BFHashDataStruct* hd, const BFHashParams* hpOl
     return 0;
 }
 
-int launch_reintegrate_multi_fast(const BFHashDataStruct* hd, const BFMultiOpDesc* ops, int nOps, const BFDepthCameraParams* cp, const int4* work,
-                                  const unsigned* workMask, unsigned workCap, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s, unsigned long long* ktime) {
+int launch_reintegrate_multi_fast(const BFHashDataStruct* hd, const BFMultiOpDesc* ops, int nOps, const BFDepthCameraParams* cp, const int4* workA, const int4* workB,
+                                  const unsigned* maskA, const unsigned* maskB, unsigned workCap, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s,
+                                  unsigned long long* ktime) {
     if (nOps < 1 || nOps > BF_MULTI_MAX_OPS) return (int)cudaErrorInvalidValue;
     static MultiArgs a;                      // ~2.5 KB: kept off the stack; filled and passed by value at the launch
-    a.blocks = hd->d_SDFBlocks; a.work = work; a.workMask = workMask; a.ctrs = ctrs; a.live = live; a.listCounterOut = hd->d_hashCompactifiedCounter;
+    a.blocks = hd->d_SDFBlocks; a.workA = workA; a.workB = workB; a.maskA = maskA; a.maskB = maskB; a.ctrs = ctrs; a.live = live; a.listCounterOut = hd->d_hashCompactifiedCounter;
     a.set = set; a.nOps = nOps; a.workCap = workCap; a.ktime = ktime;
     a.cam.W = cp->m_imageWidth; a.cam.H = cp->m_imageHeight; a.cam.fx = cp->fx; a.cam.fy = cp->fy; a.cam.mx5 = cp->mx + 0.5f; a.cam.my5 = cp->my + 0.5f;
     for (int k = 0; k < nOps; ++k) {

@@ -55,10 +55,10 @@ extern "C" int emu_reintegrate_fast(const BFHashDataStruct* hd, const BFHashPara
     return bf::launch_reintegrate_fast(hd, hpOld, hpNew, cp, depth, color, (const int4*)work, bf::CTR_SET0, ctrs, live, grid, nullptr);
 }
 extern "C" int emu_reintegrate_multi(const BFHashDataStruct* hd, const BFHashParams* hpOld, const BFHashParams* hpNew, int nOps, const BFDepthCameraParams* cp,
-                                     const float* const* depth, const void* const* color, const void* work, const unsigned* workMask, unsigned workCap, unsigned* ctrs, int* live, int grid) {
+                                     const float* const* depth, const void* const* color, const void* workA, const void* workB, const unsigned* maskA, const unsigned* maskB, unsigned workCap, unsigned* ctrs, int* live, int grid) {
     bf::BFMultiOpDesc d[BF_MULTI_MAX_OPS];
     for (int k = 0; k < nOps; ++k) { d[k].hpOld = hpOld + k; d[k].hpNew = hpNew + k; d[k].depth = depth[k]; d[k].color = color[k]; }
-    return bf::launch_reintegrate_multi_fast(hd, d, nOps, cp, (const int4*)work, workMask, workCap, bf::CTR_SET0, ctrs, live, grid, nullptr);
+    return bf::launch_reintegrate_multi_fast(hd, d, nOps, cp, (const int4*)workA, (const int4*)workB, maskA, maskB, workCap, bf::CTR_SET0, ctrs, live, grid, nullptr);
 }
 '''
 
@@ -83,7 +83,7 @@ def emu():
     vp = C.c_void_p
     L.emu_integrate_fast.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_uint, vp, vp, C.c_int]
     L.emu_reintegrate_fast.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
-    L.emu_reintegrate_multi.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_uint, vp, vp, C.c_int]
+    L.emu_reintegrate_multi.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_uint, vp, vp, C.c_int]
     return L
 
 
@@ -162,8 +162,9 @@ def test_fast_stencil_emulated_stream_matches_oracle(emu):
 
 
 def test_fast_fused_reintegration_emulated_equals_its_two_passes(emu):
-    """MODE 2 (old pose de-integrated, new pose integrated, one read-modify-write) must equal MODE 1 followed by MODE 0 of the same source
-    word for word: same probes, same update order per voxel."""
+    """MODE 2 (old pose de-integrated, new pose integrated, one read-modify-write) against MODE 1 followed by MODE 0 of the same source: same
+    probes, same decisions, so weights and colours are identical word for word; the sdf of a voxel both poses touch comes from the composed
+    update (s w - sD + sI) / w instead of two divisions and may differ in the last bits."""
     W, H = 160, 120
     cam = camera_params(W, H)
     hp = default_hash_params(num_buckets=20011, num_sdf_blocks=30000)
@@ -194,7 +195,9 @@ def test_fast_fused_reintegration_emulated_equals_its_two_passes(emu):
     assert rc == 0
     ab, av = orc.canonical_blocks(one.o.download()); bb, bv = orc.canonical_blocks(two.o.download())
     np.testing.assert_array_equal(ab, bb)
-    np.testing.assert_array_equal(av, bv)
+    np.testing.assert_array_equal(av[..., 1], bv[..., 1])                     # weights
+    np.testing.assert_array_equal(av[..., 2], bv[..., 2])                     # colours
+    assert np.abs(av[..., 0].view(F) - bv[..., 0].view(F)).max() < 2e-7
     np.testing.assert_array_equal(one.live, two.live)
 
 
@@ -269,18 +272,21 @@ def test_batch_stencil_emulated_equals_pair_by_pair(emu):
             if epoch.get(p, 0) <= k:
                 masks[p] = masks.get(p, 0) | ((1 if p in inO else 0) | (2 if p in inN else 0)) << (2 * k)
     work, wm = work_list(o, masks)
-    # the layout compactify_multi_kernel produces: heavy items (>= nOps probes) from the front, light ones from the back of a capacity-sized array
+    # the layout compactify_multi_kernel produces: four cost buckets (quartiles of the 2 x 3 = 6 possible probes) in two capacity-sized arrays
     cap = len(work) + 7
-    heavy = np.array([bin(int(m)).count("1") >= 3 for m in wm])
-    W2, M2 = np.zeros((cap, 4), np.int32), np.zeros(cap, np.uint32)
-    nH, nL = int(heavy.sum()), int((~heavy).sum())
-    W2[:nH], M2[:nH] = work[heavy], wm[heavy]
-    W2[cap - nL:], M2[cap - nL:] = work[~heavy][::-1], wm[~heavy][::-1]
-    assert nH > 0 and nL > 0
+    bits = np.array([bin(int(m)).count("1") for m in wm])
+    q = np.where(4 * bits > 3 * 6, 3, np.where(2 * bits > 6, 2, np.where(4 * bits > 6, 1, 0)))
+    WA, WB, MA, MB = np.zeros((cap, 4), np.int32), np.zeros((cap, 4), np.int32), np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    n = [int((q == k).sum()) for k in range(4)]
+    WA[:n[3]], MA[:n[3]] = work[q == 3], wm[q == 3]
+    if n[2]: WA[cap - n[2]:], MA[cap - n[2]:] = work[q == 2][::-1], wm[q == 2][::-1]
+    WB[:n[1]], MB[:n[1]] = work[q == 1], wm[q == 1]
+    if n[0]: WB[cap - n[0]:], MB[cap - n[0]:] = work[q == 0][::-1], wm[q == 0][::-1]
+    assert sum(1 for k in n if k > 0) >= 3, n
     dptr = (C.c_void_p * 3)(*[p[0].ctypes.data for p in pairs]); cptr = (C.c_void_p * 3)(*[p[1].ctypes.data for p in pairs])
-    bat.ctrs[16:24] = 0; bat.ctrs[16] = len(work); bat.ctrs[17] = nH; bat.ctrs[18] = nL
-    assert emu.emu_reintegrate_multi(C.byref(o.hd), C.addressof(hpOs), C.addressof(hpNs), 3, C.byref(cam), C.addressof(dptr), C.addressof(cptr), W2.ctypes.data,
-                                     M2.ctypes.data, cap, bat.ctrs.ctypes.data, bat.live.ctypes.data, 5) == 0
+    bat.ctrs[16:24] = 0; bat.ctrs[16] = len(work); bat.ctrs[17] = n[3]; bat.ctrs[18] = n[2]; bat.ctrs[22] = n[1]; bat.ctrs[23] = n[0]
+    assert emu.emu_reintegrate_multi(C.byref(o.hd), C.addressof(hpOs), C.addressof(hpNs), 3, C.byref(cam), C.addressof(dptr), C.addressof(cptr), WA.ctypes.data, WB.ctypes.data,
+                                     MA.ctypes.data, MB.ctypes.data, cap, bat.ctrs.ctypes.data, bat.live.ctypes.data, 5) == 0
     ab, av = orc.canonical_blocks(bat.o.download()); bb, bv = orc.canonical_blocks(seq.o.download())
     np.testing.assert_array_equal(ab, bb)
     np.testing.assert_array_equal(av, bv)
