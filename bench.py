@@ -374,12 +374,19 @@ def run_loop(args):
     h_depth = depth[f_e2e0:f_e2e0 + K].cpu().pin_memory(); h_color = color[f_e2e0:f_e2e0 + K].cpu().pin_memory()
     stats = {"valid": 0, "local": 0, "local_valid": 0, "global": 0, "reint": 0, "kp": 0, "n": 0}
 
+    trace = []
+
     def note(st):
+        if args.trace:
+            trace.append((int(st.frame), int(st.validTransform), int(st.numKeyPoints), int(st.lastMatchedFrame), int(st.numLocalCorrespondences), int(st.numReintegrated),
+                          int(st.localSolved), int(st.localValid), int(st.numKeyframes), int(st.numGlobalCorrespondences), int(st.globalSolved), int(st.globalRemoved), int(st.globalTrackingLost)))
         stats["n"] += 1; stats["valid"] += st.validTransform; stats["reint"] += st.numReintegrated; stats["kp"] += st.numKeyPoints
         stats["local"] += 1 if st.localSolved >= 0 else 0; stats["local_valid"] += st.localValid; stats["global"] += st.globalSolved
 
     for f in range(pre):                                   # pre-roll: the state a long stream is in (keyframes, trajectory, populated hash)
-        loop.step(depth[f], color[f])
+        st = loop.step(depth[f], color[f])
+        if args.trace:
+            note(st)
     torch.cuda.synchronize()
 
     def timed(f0, n, e2e, profile):
@@ -415,8 +422,17 @@ def run_loop(args):
     capi.check(L.bfTsdfGetProfileEx(L.bfFrameLoopGetHashData(loop._h), prof), "bfTsdfGetProfileEx")
     L.bfTsdfSetProfiling(0)
     clk_mark2 = len(clk_lines)
+    stats_timed = dict(stats)
     ms_e2e, _ = timed(f_e2e0, K, True, False)
+    stats_e2e = {k: stats[k] - stats_timed[k] for k in stats}
+    stats = stats_timed
     stop_evt.set()
+    if args.trace and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.trace)), exist_ok=True)
+        with open(args.trace, "w") as fp:
+            fp.write("frame valid keypoints lastMatched localCorr reint localSolved localValid keyframes globalCorr globalSolved globalRemoved trackingLost\n")
+            for t in trace:
+                fp.write(" ".join(str(v) for v in t) + "\n")
     heap_free = loop.heap_free()
     cnt = loop.counters()
     if rank != 0:
@@ -436,7 +452,8 @@ def run_loop(args):
             "frames_per_launch": round(n_img / max(1, n_launch), 2),
             "avg_launch_us_device_timer": round(int(prof[14]) / max(1, n_timed) / 1e3, 2) if use_batch and int(prof[14]) else None,
             "all_stencil_launches": {"launches": int(prof[0]), "avg_launch_us": round(int(prof[2]) / max(1, int(prof[1])) / 1e3, 2)},
-            "mvoxels_per_s": round(512.0 * E / max(1e-9, ns * 1e-9) / 1e6, 1)}
+            "mvoxels_per_s": round(512.0 * E / max(1e-9, ns * 1e-9) / 1e6, 1),
+            "block_pose_entries_culled_per_launch": round(int(prof[15]) / max(1, n_launch)) if use_batch else None}
     tpath = os.path.join(ROOT, "profiles", "r2_stencil_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath)); roof["traffic"] = tj.get("dram_bytes_per_launch"); roof["traffic_note"] = tj.get("note")
@@ -451,6 +468,7 @@ def run_loop(args):
                                        "local_solves": stats["local"], "local_solves_accepted": stats["local_valid"], "global_solves": stats["global"]},
                        host_syncs_per_frame=round((cnt["host_syncs"]) / max(1, cnt["frames"]), 2)),
         "e2e": {"value": round(K / (ms_e2e / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": W * H * 8, "d2h_bytes_per_step": 120 + 64 + 8,
+                "frames_with_pose": stats_e2e["valid"], "local_solves": stats_e2e["local"], "global_solves": stats_e2e["global"],
                 "note": "bfFrameLoopStep with HOST (pinned) depth + colour pointers: the upload happens inside the call, as CUDAImageManager::process uploads on arrival; read back per step: the status block (pose of the frame), the SIFT pose and the match verdict"},
         "gpu_launches": int(launches), "roofline": roof, "tsdf_arithmetic": "fast",
         "clocks": summarize_clocks(clk_lines[clk_mark0:clk_mark1]), "clocks_profile_pass": summarize_clocks(clk_lines[clk_mark1:clk_mark2]),
@@ -532,6 +550,7 @@ def main():
     ap.add_argument("--no-ba", action="store_true", help="diagnostic: leave the bundle-adjustment solves out (the JSON line is then NOT a bench value)")
     ap.add_argument("--workload", default="loop", choices=["loop", "ops"], help="loop: the whole frame loop (headline); ops: TSDF op replay + synthetic BA problems (round-1 bench, kept for A/B)")
     ap.add_argument("--preroll", type=int, default=600, help="frames streamed through the loop before warm-up (state of a long stream)")
+    ap.add_argument("--trace", default=None, help="diagnostic: write the per-frame status of every step (pre-roll included) to this file")
     ap.add_argument("--stride", type=int, default=2, help="Lissajous path frames per step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -103,7 +103,7 @@ TSDF_SYMBOLS = [
     "garbageCollectIdentifyCUDA", "garbageCollectFreeCUDA",
     "bfSetStream", "bfGetStream", "bfGetLastErrorString", "bfTsdfAuxBytes", "bfTsdfReset", "bfTsdfIntegrateFrame",
     "bfTsdfGarbageCollect", "bfTsdfGetHeapFreeCount", "bfTsdfGetNumOccupiedBlocks", "bfTsdfGetLastFrameStats",
-    "bfTsdfReleaseAux", "bfTsdfReintegrateFrame", "bfGetLaunchCount", "bfTsdfSetProfiling", "bfTsdfGetProfile", "bfTsdfGetProfileEx", "bfTsdfSetBlockCull", "bfTsdfSetLanes", "bfTsdfSetArithmetic", "bfTsdfReintegrateBatch", "bfTsdfSetBatching",
+    "bfTsdfReleaseAux", "bfTsdfReintegrateFrame", "bfGetLaunchCount", "bfTsdfSetProfiling", "bfTsdfGetProfile", "bfTsdfGetProfileEx", "bfTsdfSetBlockCull", "bfTsdfSetLanes", "bfTsdfSetArithmetic", "bfTsdfReintegrateBatch", "bfTsdfSetBatching", "bfTsdfSetBatchCull",
 ]
 
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
@@ -256,6 +256,8 @@ def lib() -> C.CDLL:
     L.bfTsdfAuxBytes.restype = C.c_size_t
     L.bfTsdfReset.argtypes = [P(BFHashDataStruct), P(BFHashParams)]
     L.bfTsdfSetBatching.argtypes = [C.c_int]
+    L.bfTsdfSetBatchCull.argtypes = [C.c_int]
+    L.bfTsdfSetBatchCull.restype = C.c_int
     L.bfTsdfSetBatching.restype = C.c_int
     L.bfTsdfSetArithmetic.argtypes = [C.c_int]
     L.bfTsdfSetArithmetic.restype = C.c_int

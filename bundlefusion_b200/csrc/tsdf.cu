@@ -55,6 +55,8 @@ struct TsdfAux {
     int4* work = nullptr;            // [numSDFBlocks] stencil work list {bx,by,bz, slot | pose bits << 28}: list entries that survive the depth-range cull
     float2* tiles = nullptr;         // [tilesCap] per 16x16-pixel tile {min, max} of the depths the stencil would accept
     unsigned tilesCap = 0;
+    float2* tilesMulti = nullptr;    // [BF_MULTI_MAX_OPS][tilesMultiPer]: depth tiles of the frames of a re-integration batch
+    unsigned tilesMultiPer = 0;
     bool liveValid = false;          // false once something outside integrate/de-integrate changed weights
     unsigned numSlots = 0;
     unsigned parity = 0;             // which of the two compactify counters is live
@@ -385,13 +387,12 @@ depth_tiles_kernel(const __grid_constant__ BFHashParams hp, const __grid_constan
 // projection by a pixel rectangle with a pixel of slack, the depths under it by the tile min/max, all with a 1 mm (+ relative)
 // margin that dwarfs the fp32 rounding of the per-voxel projection.  Results are therefore unchanged; ~35 % of the in-frustum
 // blocks of a scan (looking past / short of the surface, or at invalid depth) never reach the stencil.
-__device__ __forceinline__ bool block_can_pass(const BFHashParams& hp, const BFDepthCameraParams& cp, const float2* __restrict__ tiles, int tilesX, I3 b) {
-    const float s = hp.m_truncScale, T = hp.m_truncation, vs = hp.m_virtualVoxelSize;
+__device__ __forceinline__ bool block_can_pass_m(float s, float T, float vs, const BFFloat4x4& Minv, const BFDepthCameraParams& cp, const float2* __restrict__ tiles, int tilesX, I3 b) {
     if (!(s >= 0.0f && s < 1.0f && T >= 0.0f && cp.fx > 0.0f && cp.fy > 0.0f && vs > 0.0f)) return true;
-    const float* M = hp.m_rigidTransformInverse.m;
+    const float* M = Minv.m;
     const float h = 0.5f * ((float)BF_SDF_BLOCK_SIZE - 1.0f) * vs;
     const F3 c = { (float)(b.x * BF_SDF_BLOCK_SIZE) * vs + h, (float)(b.y * BF_SDF_BLOCK_SIZE) * vs + h, (float)(b.z * BF_SDF_BLOCK_SIZE) * vs + h };
-    const F3 pc = xform(hp.m_rigidTransformInverse, c);
+    const F3 pc = xform(Minv, c);
     const float eps = 1e-3f + 1e-5f * (fabsf(c.x) + fabsf(c.y) + fabsf(c.z) + fabsf(M[3]) + fabsf(M[7]) + fabsf(M[11]));
     const float ex = (fabsf(M[0]) + fabsf(M[1]) + fabsf(M[2])) * h + eps;
     const float ey = (fabsf(M[4]) + fabsf(M[5]) + fabsf(M[6])) * h + eps;
@@ -413,6 +414,9 @@ __device__ __forceinline__ bool block_can_pass(const BFHashParams& hp, const BFD
         for (int tx = tx0; tx <= tx1; ++tx) { const float2 t = __ldg(&tiles[ty * tilesX + tx]); dmin = fminf(dmin, t.x); dmax = fmaxf(dmax, t.y); }
     if (!(dmax >= dmin)) return false;                      // no acceptable depth under the footprint
     return !(zmin >= dmax * (1.0f + s) + T + eps || zmax <= dmin * (1.0f - s) - T - eps);
+}
+__device__ __forceinline__ bool block_can_pass(const BFHashParams& hp, const BFDepthCameraParams& cp, const float2* __restrict__ tiles, int tilesX, I3 b) {
+    return block_can_pass_m(hp.m_truncScale, hp.m_truncation, hp.m_virtualVoxelSize, hp.m_rigidTransformInverse, cp, tiles, tilesX, b);
 }
 __device__ __forceinline__ I3 unpack_block_key(unsigned long long key) {
     const int lim = 1 << 20;
@@ -1057,19 +1061,23 @@ compactify_dual_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams
 // one union list: per allocated block the 2-bit-per-op mask {in the old pose's frustum, in the new pose's frustum} for the ops that saw
 // the block exist (op index >= the block's tag; a block inserted by op j's alloc does not exist for ops < j in the reference's order),
 // and the multi-op stencil (tsdf_fast.cu) applies the ops to each voxel in order, in registers: one voxel read and write for the batch.
-struct MultiFrusta { int nOps; float voxelSize; BFFloat4x4 inv[2 * BF_MULTI_MAX_OPS]; };     // inv[2k] = old pose of op k (inverse), inv[2k+1] = new
+struct MultiFrusta { int nOps; float voxelSize; float truncScale, truncation; int tilesX; unsigned tilesPerOp; BFFloat4x4 inv[2 * BF_MULTI_MAX_OPS]; };     // inv[2k] = old pose of op k (inverse), inv[2k+1] = new
 __global__ void __launch_bounds__(256)
 compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta fr, const __grid_constant__ BFDepthCameraParams cp,
                         const int4* __restrict__ slotInfo, const unsigned* __restrict__ slotEpoch, unsigned batchId, unsigned* ctrs, int set,
                         unsigned char* __restrict__ listFlags, int4* __restrict__ workA, int4* __restrict__ workB, unsigned* __restrict__ maskA,
-                        unsigned* __restrict__ maskB, unsigned workCap) {
+                        unsigned* __restrict__ maskB, unsigned workCap, const float2* __restrict__ tiles) {
+    // tiles (optional): per op the 16x16-pixel {min, max} of the depths its frame offers (depth tiles, above).  A (block, op, pose) whose voxels provably
+    // all fail the truncation test is dropped from the WORK mask -- its probes would all fail, the voxels stay as they are -- while list membership, the
+    // GC flags and the E statistics keep the frustum mask: same results, fewer probes (in a scanned room more than half of the in-frustum blocks of an
+    // old frame are beyond its integration distance, hidden behind nearer surfaces or at invalid depth).
     const unsigned highWater = ctrs[CTR_HIGH_WATER];
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned stride = gridDim.x * blockDim.x;
     const unsigned lane = threadIdx.x & 31;
     for (unsigned base = tid - lane; base < highWater; base += stride) {
         const unsigned slot = base + lane;
-        unsigned mask = 0;
+        unsigned mask = 0, wmask = 0;
         int4 info = make_int4(0, 0, 0, -1);
         if (slot < highWater) {
             info = __ldcg(&slotInfo[slot]);
@@ -1078,22 +1086,29 @@ compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta
                 const unsigned e = __ldcg(&slotEpoch[slot]);
                 const int first = ((e >> 8) == batchId) ? (int)(e & 0xffu) : 0;
                 for (int k = first; k < fr.nOps; ++k) {
-                    if (block_in_frustum_m(fr.voxelSize, fr.inv[2 * k], cp, b)) mask |= 1u << (2 * k);
-                    if (block_in_frustum_m(fr.voxelSize, fr.inv[2 * k + 1], cp, b)) mask |= 2u << (2 * k);
+                    const float2* const tk = tiles ? tiles + (size_t)k * fr.tilesPerOp : nullptr;
+                    if (block_in_frustum_m(fr.voxelSize, fr.inv[2 * k], cp, b)) {
+                        mask |= 1u << (2 * k);
+                        if (!tk || block_can_pass_m(fr.truncScale, fr.truncation, fr.voxelSize, fr.inv[2 * k], cp, tk, fr.tilesX, b)) wmask |= 1u << (2 * k);
+                    }
+                    if (block_in_frustum_m(fr.voxelSize, fr.inv[2 * k + 1], cp, b)) {
+                        mask |= 2u << (2 * k);
+                        if (!tk || block_can_pass_m(fr.truncScale, fr.truncation, fr.voxelSize, fr.inv[2 * k + 1], cp, tk, fr.tilesX, b)) wmask |= 2u << (2 * k);
+                    }
                 }
             }
         }
         const unsigned ballot = __ballot_sync(0xffffffffu, mask != 0);
         if (ballot) {
             // E of the batch = sum over ops of the blocks in either frustum = what the per-op lists would have held
-            const unsigned bits = (unsigned)__popc(mask);
-            unsigned nE = bits;
-            for (int o = 16; o > 0; o >>= 1) nE += __shfl_xor_sync(0xffffffffu, nE, o);
+            const unsigned bits = (unsigned)__popc(wmask);
+            unsigned nE = (unsigned)__popc(mask), nW = bits;
+            for (int o = 16; o > 0; o >>= 1) { nE += __shfl_xor_sync(0xffffffffu, nE, o); nW += __shfl_xor_sync(0xffffffffu, nW, o); }
             // Work order: a block's cost grows with the number of (op, pose) probes it takes -- up to 2 nOps of them, ~60 k cycles for a CTA at
             // 20.  Items go to four buckets by cost quartile and the stencil deals the costliest bucket first (longest-processing-time-first), so
             // the kernel ends on cheap blocks and its tail is a quartile-0 block, not a 20-probe one.
             const unsigned n2 = 2u * (unsigned)fr.nOps;
-            const int q = (mask == 0) ? -1 : (4u * bits > 3u * n2 ? 3 : (2u * bits > n2 ? 2 : (4u * bits > n2 ? 1 : 0)));
+            const int q = (wmask == 0) ? -1 : (4u * bits > 3u * n2 ? 3 : (2u * bits > n2 ? 2 : (4u * bits > n2 ? 1 : 0)));
             const unsigned b3 = __ballot_sync(0xffffffffu, q == 3), b2 = __ballot_sync(0xffffffffu, q == 2), b1 = __ballot_sync(0xffffffffu, q == 1), b0 = __ballot_sync(0xffffffffu, q == 0);
             unsigned warpBase = 0, base3 = 0, base2 = 0, base1 = 0, base0 = 0;
             if (lane == 0) {
@@ -1104,6 +1119,7 @@ compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta
                 if (b0) base0 = atomicAdd(&ctrs[set + SET_Q0], __popc(b0));
                 atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_E_TOT_LO]), (unsigned long long)nE);
                 atomicAdd(reinterpret_cast<unsigned long long*>(&ctrs[CTR_EB_TOT_LO]), (unsigned long long)nE);
+                if (nE != nW) atomicAdd(&ctrs[CTR_CULLB], nE - nW);
             }
             warpBase = __shfl_sync(0xffffffffu, warpBase, 0);
             base3 = __shfl_sync(0xffffffffu, base3, 0); base2 = __shfl_sync(0xffffffffu, base2, 0);
@@ -1118,12 +1134,14 @@ compactify_multi_kernel(BFHashDataStruct hd, const __grid_constant__ MultiFrusta
                 hd.d_hashCompactified[k] = en;
                 // the reference's GC walks the list of the LAST integrate (DepthSensing.cpp:901): bit 1 = in the last op's new-pose frustum
                 listFlags[k] = (unsigned char)(((mask >> (2 * (fr.nOps - 1))) & 2u) | 1u);
-                int4* const wArr = (q >= 2) ? workA : workB;
-                unsigned* const mArr = (q >= 2) ? maskA : maskB;
-                const unsigned w = (q == 3) ? base3 + __popc(b3 & below) : (q == 2) ? (workCap - 1u) - (base2 + __popc(b2 & below))
-                                 : (q == 1) ? base1 + __popc(b1 & below) : (workCap - 1u) - (base0 + __popc(b0 & below));
-                wArr[w] = make_int4(info.x, info.y, info.z, (int)slot);
-                mArr[w] = mask;
+                if (q >= 0) {
+                    int4* const wArr = (q >= 2) ? workA : workB;
+                    unsigned* const mArr = (q >= 2) ? maskA : maskB;
+                    const unsigned w = (q == 3) ? base3 + __popc(b3 & below) : (q == 2) ? (workCap - 1u) - (base2 + __popc(b2 & below))
+                                     : (q == 1) ? base1 + __popc(b1 & below) : (workCap - 1u) - (base0 + __popc(b0 & below));
+                    wArr[w] = make_int4(info.x, info.y, info.z, (int)slot);
+                    mArr[w] = wmask;
+                }
             }
         }
     }
@@ -1379,7 +1397,7 @@ gc_live_kernel(BFHashDataStruct hd, const __grid_constant__ BFHashParams hp, con
 // host side
 // ------------------------------------------------------------------------------------------
 static void free_aux(TsdfAux& a) {
-    cudaFree(a.slotInfo); cudaFree(a.ctrs); cudaFree(a.live); cudaFree(a.listFlags); cudaFree(a.work2[0]); cudaFree(a.work2[1]); cudaFree(a.tiles);
+    cudaFree(a.slotInfo); cudaFree(a.ctrs); cudaFree(a.live); cudaFree(a.listFlags); cudaFree(a.work2[0]); cudaFree(a.work2[1]); cudaFree(a.tiles); cudaFree(a.tilesMulti);
     cudaFree(a.slotEpoch); cudaFree(a.workMask); cudaFree(a.workMask2);
     if (a.lane) cudaStreamDestroy(a.lane);
     if (a.evFork) cudaEventDestroy(a.evFork);
@@ -1495,13 +1513,13 @@ static int join_lanes(TsdfAux* aux) {
 // allocCUDA stub has no say over what is integrated afterwards).  zeroParity >= 0: the launch also zeroes that counter set
 // (the one the following compactify fills).
 static int do_alloc(BFHashDataStruct* hd, const BFHashParams* hp, const float* depth, const BFDepthCameraParams* cp, TsdfAux* aux, bool withTiles, int zeroParity,
-                    AllocEpoch ep = AllocEpoch{nullptr, 0u}) {
+                    AllocEpoch ep = AllocEpoch{nullptr, 0u}, float2* tilesOut = nullptr) {
     dim3 block(BF_TILE, BF_TILE);
     dim3 grid((cp->m_imageWidth + block.x - 1) / block.x, (cp->m_imageHeight + block.y - 1) / block.y);
     if (withTiles) { int rc = ensure_tiles(aux, cp); if (rc) return rc; }
     if (zeroParity >= 0) { int rc = front_acquire_set(aux, (unsigned)zeroParity); if (rc) return rc; }
     ++g_launchCount;
-    alloc_kernel<<<grid, block, 0, g_stream>>>(*hd, *hp, *cp, depth, aux->slotInfo, aux->ctrs, withTiles ? aux->tiles : nullptr,
+    alloc_kernel<<<grid, block, 0, g_stream>>>(*hd, *hp, *cp, depth, aux->slotInfo, aux->ctrs, tilesOut ? tilesOut : (withTiles ? aux->tiles : nullptr),
                                                zeroParity >= 0 ? set_of((unsigned)zeroParity) : -1, ep);
     BF_CHECK(cudaGetLastError());
     return 0;
@@ -1715,6 +1733,13 @@ static bool batching_on() {
     return g_batching == 1;
 }
 BF_API int bfTsdfSetBatching(int enable) { const int prev = batching_on() ? 1 : 0; g_batching = enable ? 1 : 0; return prev; }
+// Batch cull (compactify_multi_kernel): on by default; BF_TSDF_BATCH_CULL=0 or bfTsdfSetBatchCull(0) switches it off.  Results are identical either way.
+static int g_batchCull = -1;
+static bool batch_cull_on() {
+    if (g_batchCull < 0) { const char* e = getenv("BF_TSDF_BATCH_CULL"); g_batchCull = (e && e[0] == '0') ? 0 : 1; }
+    return g_batchCull == 1;
+}
+BF_API int bfTsdfSetBatchCull(int enable) { const int prev = batch_cull_on() ? 1 : 0; g_batchCull = enable ? 1 : 0; return prev; }
 
 BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const BFDepthCameraParams* cp, const BFTsdfReintegration* pairs, int numPairs,
                                   const float* const* d_depthFrames, const uint8_t* const* d_colorFrames) {
@@ -1736,7 +1761,14 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
     static BFHashParams hpOld[BF_MULTI_MAX_OPS], hpNew[BF_MULTI_MAX_OPS];
     static MultiFrusta fr;
     BFMultiOpDesc desc[BF_MULTI_MAX_OPS];
-    fr.nOps = numPairs; fr.voxelSize = hp->m_virtualVoxelSize;
+    fr.nOps = numPairs; fr.voxelSize = hp->m_virtualVoxelSize; fr.truncScale = hp->m_truncScale; fr.truncation = hp->m_truncation;
+    fr.tilesX = tiles_x(cp); fr.tilesPerOp = (unsigned)(tiles_x(cp) * tiles_y(cp));
+    const bool cull = batch_cull_on();
+    if (cull && aux->tilesMultiPer < fr.tilesPerOp) {
+        if (aux->tilesMulti) { BF_CHECK(cudaStreamSynchronize(g_stream)); BF_CHECK(cudaFree(aux->tilesMulti)); aux->tilesMulti = nullptr; aux->tilesMultiPer = 0; }
+        BF_CHECK(cudaMalloc(&aux->tilesMulti, sizeof(float2) * (size_t)fr.tilesPerOp * BF_MULTI_MAX_OPS));
+        aux->tilesMultiPer = fr.tilesPerOp;
+    }
     const unsigned newParity = aux->parity ^ 1u;
     for (int k = 0; k < numPairs; ++k) {
         hpOld[k] = *hp; hpNew[k] = *hp;
@@ -1748,7 +1780,8 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
         desc[k].depth = d_depthFrames[pairs[k].frame]; desc[k].color = d_colorFrames[pairs[k].frame];
         if (!desc[k].color || !desc[k].depth) return (int)cudaErrorInvalidValue;
         // the first alloc launch also zeroes the counter set the list is about to use
-        rc = do_alloc(hd, &hpNew[k], desc[k].depth, cp, aux, false, k == 0 ? (int)newParity : -1, AllocEpoch{aux->slotEpoch, (aux->batchId << 8) | (unsigned)k});
+        rc = do_alloc(hd, &hpNew[k], desc[k].depth, cp, aux, false, k == 0 ? (int)newParity : -1, AllocEpoch{aux->slotEpoch, (aux->batchId << 8) | (unsigned)k},
+                      cull ? aux->tilesMulti + (size_t)k * fr.tilesPerOp : nullptr);
         if (rc) return rc;
     }
     aux->parity = newParity;
@@ -1756,7 +1789,8 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
     const int set = set_of(aux->parity);
     ++g_launchCount;
     compactify_multi_kernel<<<grid_for((hp->m_numSDFBlocks + 255) / 256, 4), 256, 0, g_stream>>>(*hd, fr, *cp, aux->slotInfo, aux->slotEpoch, aux->batchId, aux->ctrs, set,
-                                                                                                 aux->listFlags, aux->work2[aux->parity], aux->work2[aux->parity ^ 1u], aux->workMask, aux->workMask2, aux->numSlots);
+                                                                                                 aux->listFlags, aux->work2[aux->parity], aux->work2[aux->parity ^ 1u], aux->workMask, aux->workMask2, aux->numSlots,
+                                                                                                 cull ? aux->tilesMulti : nullptr);
     BF_CHECK(cudaGetLastError());
     const bool timeIt = g_profile && g_evUsed < kMaxProfiledLaunches;
     if (g_profile) { ++g_profLaunches; g_profFrames += (unsigned long long)numPairs; ++g_profBatchLaunches; g_profBatchFrames += (unsigned long long)numPairs; }
@@ -1832,6 +1866,7 @@ BF_API int bfTsdfSetProfiling(int enable) {
     for (auto& kv : g_aux) {                    // restart the U / E sums
         BF_CHECK(cudaMemsetAsync(kv.second.ctrs + CTR_U_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
         BF_CHECK(cudaMemsetAsync(kv.second.ctrs + CTR_UB_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
+        BF_CHECK(cudaMemsetAsync(kv.second.ctrs + CTR_CULLB, 0, sizeof(unsigned), g_stream));
     }
     return 0;
 }
@@ -1861,6 +1896,7 @@ BF_API int bfTsdfGetProfileEx(const BFHashDataStruct* hd, unsigned long long out
     out[11] = ((unsigned long long)c[CTR_UB_TOT_HI] << 32) | c[CTR_UB_TOT_LO];
     out[12] = ((unsigned long long)c[CTR_EB_TOT_HI] << 32) | c[CTR_EB_TOT_LO];
     out[13] = g_profBatchFrames;
+    out[15] = c[CTR_CULLB];         // (block, op, pose) probes the batch cull removed (E counts them: they are in-frustum)
     if (g_ktime && g_evUsed) {          // out[14]: the batch launches' duration by the in-kernel %globaltimer brackets (first CTA start -> last CTA end), ns
         std::vector<unsigned long long> kt(2 * g_evUsed);
         BF_CHECK(cudaMemcpy(kt.data(), g_ktime, sizeof(unsigned long long) * 2 * g_evUsed, cudaMemcpyDeviceToHost));
@@ -1871,6 +1907,7 @@ BF_API int bfTsdfGetProfileEx(const BFHashDataStruct* hd, unsigned long long out
     // restart accumulation
     BF_CHECK(cudaMemsetAsync(aux->ctrs + CTR_U_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
     BF_CHECK(cudaMemsetAsync(aux->ctrs + CTR_UB_TOT_LO, 0, 4 * sizeof(unsigned), g_stream));
+    BF_CHECK(cudaMemsetAsync(aux->ctrs + CTR_CULLB, 0, sizeof(unsigned), g_stream));
     g_evUsed = 0; g_profLaunches = 0; g_profFrames = 0; g_profBatchLaunches = 0; g_profBatchFrames = 0;
     std::fill(g_evIsBatch.begin(), g_evIsBatch.end(), 0);
     return 0;

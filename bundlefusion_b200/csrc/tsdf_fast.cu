@@ -25,7 +25,9 @@
 namespace bf {
 
 struct FastPose {
-    float cx[4], cy[4], cz[4];       // camera-space x, y, z of a voxel = c[0] vx + c[1] vy + c[2] vz + c[3]   (rows of Tinv * diag(voxelSize))
+    // camera-space z of a voxel = cz[0] vx + cz[1] vy + cz[2] vz + cz[3] (row of Tinv * diag(voxelSize)); cx / cy: the rows for x / y times the focal
+    // length, so that the pixel coordinate is (cx . v) / z + mx -- one multiply-add after the reciprocal
+    float cx[4], cy[4], cz[4];
     float maxDist, trunc0, truncScale, wMax;
 };
 struct FastCam { unsigned W, H; float fx, fy, mx5, my5; };     // mx + 0.5, my + 0.5: the reference's int(proj + 0.5)
@@ -70,35 +72,47 @@ template <int K> __device__ __forceinline__ unsigned put_byte(unsigned acc, unsi
 // the compiler can issue the loads back to back (memory-level parallelism) and interleave the arithmetic of the four chains ----
 struct ProbeSet {
     float sdf[4];          // after decide(): depth - z of the voxels that pass
-    unsigned idx[4];       // pixel index, or 0xFFFFFFFF when the voxel projects outside the image
+    unsigned idx[4];       // pixel index (0 when the voxel projects outside the image; such a voxel never passes)
     unsigned mask;         // bit k: voxel k passes the truncation test
 };
+// the image pointer in an ordinary (non-uniform) register pair: the gather's address is then one IMAD.WIDE (base + 4 idx) instead of a LEA / LEA.HI.X
+// pair off a uniform base
+__device__ __forceinline__ const float* in_vector_regs(const float* p) {
+#ifndef BF_EMU_SEQUENTIAL
+    asm("" : "+l"(p));
+#endif
+    return p;
+}
 // (vx, vy, vz): integer voxel coordinates of the thread's first voxel, as floats.  Every fast kernel evaluates the SAME expression here, so a
 // voxel's pass / fail decision for a given (pose, frame) is the same bit for bit whichever kernel asks (integrate now, de-integrate later in a batch)
-__device__ __forceinline__ void project4(const FastCam& a, const float* __restrict__ depth, const FastPose& p, float vx, float vy, float vz, ProbeSet& ps, float (&z)[4]) {
+__device__ __forceinline__ void project4(const FastCam& a, const float* __restrict__ depthU, const FastPose& p, float vx, float vy, float vz, ProbeSet& ps, float (&z)[4]) {
+    const float* const depth = in_vector_regs(depthU);
     const float X = fmaf(vx, p.cx[0], fmaf(vy, p.cx[1], fmaf(vz, p.cx[2], p.cx[3])));
     const float Y = fmaf(vx, p.cy[0], fmaf(vy, p.cy[1], fmaf(vz, p.cy[2], p.cy[3])));
     const float Z = fmaf(vx, p.cz[0], fmaf(vy, p.cz[1], fmaf(vz, p.cz[2], p.cz[3])));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float Xk = fmaf((float)k, p.cx[0], X), Yk = fmaf((float)k, p.cy[0], Y), Zk = fmaf((float)k, p.cz[0], Z);
+        const float Xk = k ? fmaf((float)k, p.cx[0], X) : X, Yk = k ? fmaf((float)k, p.cy[0], Y) : Y, Zk = k ? fmaf((float)k, p.cz[0], Z) : Z;
         const float rz = rcp_approx(Zk);
-        const float sx = fmaf(Xk * rz, a.fx, a.mx5), sy = fmaf(Yk * rz, a.fy, a.my5);
+        const float sx = fmaf(Xk, rz, a.mx5), sy = fmaf(Yk, rz, a.my5);
         const unsigned ix = (unsigned)__float2int_rz(sx), iy = (unsigned)__float2int_rz(sy);   // cvt.rzi: (-1, 0) -> 0, NaN -> 0, as the reference's (int)
         const bool on = (ix < a.W) & (iy < a.H);
-        ps.idx[k] = on ? iy * a.W + ix : 0xFFFFFFFFu;
+        const unsigned idx = on ? iy * a.W + ix : 0u;
+        ps.idx[k] = idx;
         z[k] = Zk;
-        ps.sdf[k] = __ldg(&depth[on ? iy * a.W + ix : 0u]);              // unconditional load from a safe address; holds the DEPTH until decide()
+        const float d = __ldg(&depth[idx]);                              // unconditional load from a safe address
+        ps.sdf[k] = on ? d : -INFINITY;                                  // holds the DEPTH until decide(); off screen = no depth
     }
 }
-// truncation test (.cu:433-463 without the identity clamp): depth valid, below the integration distance, |depth - z| < truncation(depth)
+// truncation test (.cu:433-463 without the identity clamp): depth valid, below the integration distance, |depth - z| < truncation(depth).
+// An invalid depth (-inf) fails the band test by itself: |sdf| = inf is not below trunc0 + truncScale * (-inf) = -inf (or trunc0 when the scale is 0).
 __device__ __forceinline__ void decide4(const FastPose& p, ProbeSet& ps, const float (&z)[4]) {
     ps.mask = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const float d = ps.sdf[k];
         const float sdf = d - z[k];
-        const bool pass = (ps.idx[k] != 0xFFFFFFFFu) & (d != -INFINITY) & (d < p.maxDist) & (fabsf(sdf) < fmaf(p.truncScale, d, p.trunc0));
+        const bool pass = (d < p.maxDist) & (fabsf(sdf) < fmaf(p.truncScale, d, p.trunc0));
         ps.sdf[k] = sdf;
         ps.mask |= pass ? (1u << k) : 0u;
     }
@@ -149,44 +163,48 @@ __device__ __forceinline__ void deintegrate_fast(float sdf, unsigned col, unsign
     wSdf = __float_as_uint(nSdf); wWeight = __float_as_uint(den); wColor = nc;
 }
 
-// de-integrate sample D then integrate sample I of the same voxel (the re-integration pair, both poses pass): the two updates of
-// .cu:486-514 composed.  sdf: ((s w - sD) / (w - 1) (w - 1) + sI) / w = (s w - sD + sI) / w -- one reciprocal, and the weight returns to w;
-// colour: the de-integrated value is still rounded to a whole level before the 0.2 / 0.8 blend (as the byte the reference stores in between),
-// but stays in a float register.  A voxel the de-integration clears (w - 1 <= 0.001) takes sample I as its first.
-__device__ __forceinline__ void reintegrate_fast(const FastPose& pB, float sdfD, unsigned colD, float sdfI, unsigned colI, unsigned& wSdf, unsigned& wWeight, unsigned& wColor) {
+// The three cases of a re-integration pair on one voxel -- only the old pose passes (de-integrate), only the new one (integrate), both (composed) --
+// as ONE branch-free expression, a = passA, b = passB as 0 / 1:  sdf = (s w - a sD + b sI) / (w - a + b), weight = w - a, + 1 clamped to wMax if b,
+// colour de-integrated if a (kept as a whole level in a float), then blended if b.  A warp whose lanes disagree on the case (voxels at the edge of
+// either pose's truncation band: about every second warp) executes this once instead of up to three divergent bodies.  Each case evaluates to the
+// same value as integrate_fast / deintegrate_fast (and, for both, their composition with one reciprocal: ((s w - sD) / (w - 1) (w - 1) + sI) / w) up to the rounding of the shared sdf numerator (< 2e-7 m).
+__device__ __forceinline__ void update_pair(const FastPose& pB, bool passA, float sdfD, unsigned colD, bool passB, float sdfI, unsigned colI,
+                                            unsigned& wSdf, unsigned& wWeight, unsigned& wColor, int& liveDelta) {
     const float oldSdf = __uint_as_float(wSdf), oldW = __uint_as_float(wWeight);
-    const float den = oldW - 1.0f;
+    const bool wasLive = oldW > 0.0f;
+    const float wd0 = passA ? oldW - 1.0f : oldW;
+    const bool cleared = passA & !(wd0 > 0.001f);                       // the de-integration empties the voxel (.cu:505-513)
+    const float wd = cleared ? 0.0f : wd0;
+    const float num = cleared ? (passB ? sdfI : 0.0f) : fmaf(oldSdf, oldW, (passB ? sdfI : 0.0f) - (passA ? sdfD : 0.0f));
+    const float den = passB ? wd + 1.0f : wd;
+    const float nSdf = (den > 0.0f) ? num * rcp_approx(den) : 0.0f;
+    const float nW = passB ? fminf(pB.wMax, den) : wd;
+    const float rb = rcp_approx(wd0) * 1.00000095367431640625f;          // see deintegrate_fast; unused (selected away) when !passA or cleared
+    const bool first = (wd == 0.0f);
     unsigned nc = 0xFF000000u;
-    if (!(den > 0.001f)) {
-        nc = put_byte<0>(nc, min(colI & 0xffu, 254u)); nc = put_byte<1>(nc, min((colI >> 8) & 0xffu, 254u)); nc = put_byte<2>(nc, min((colI >> 16) & 0xffu, 254u));
-        wSdf = __float_as_uint(sdfI); wWeight = __float_as_uint(fminf(pB.wMax, 1.0f)); wColor = nc;
-        return;
-    }
-    const float nSdf = fmaf(oldSdf, oldW, sdfI - sdfD) * rcp_approx(oldW);
-    const float rb = rcp_approx(den) * 1.00000095367431640625f;          // see deintegrate_fast
-#define BF_REINT_CHANNEL(K)                                                                                                                   \
+#define BF_PAIR_CHANNEL(K)                                                                                                                    \
     {                                                                                                                                         \
-        const float qd = fminf(fmaxf(fmaf(byte_to_float<K>(wColor), oldW, -byte_to_float<K>(colD)) * rb, 0.0f), 254.4f);                      \
-        const float cd = (qd + 8388608.0f) - 8388608.0f;                              /* the de-integrated level, a whole number <= 254 */    \
-        const float q = fmaf(0.2f, byte_to_float<K>(colI), 0.8f * cd);                 /* fraction a multiple of 0.2: never a tie; <= 254.2 */  \
-        nc = put_byte<K>(nc, __float_as_uint(q + 8388608.0f));                                                                               \
+        const float c0 = byte_to_float<K>(wColor);                                                                                            \
+        const float qd = fminf(fmaxf(fmaf(c0, oldW, -byte_to_float<K>(colD)) * rb, 0.0f), 254.4f);                                            \
+        const float c1 = passA ? (cleared ? 0.0f : (qd + 8388608.0f) - 8388608.0f) : c0;      /* whole level <= 254 */                        \
+        const float ci = byte_to_float<K>(colI);                                                                                              \
+        const float q = first ? fminf(ci, 254.0f) : fmaf(0.2f, ci, 0.8f * c1);                 /* fraction a multiple of 0.2: never a tie */    \
+        nc = put_byte<K>(nc, __float_as_uint((passB ? q : c1) + 8388608.0f));                                                                \
     }
-    BF_REINT_CHANNEL(0) BF_REINT_CHANNEL(1) BF_REINT_CHANNEL(2)
-#undef BF_REINT_CHANNEL
-    wSdf = __float_as_uint(nSdf); wWeight = __float_as_uint(fminf(pB.wMax, oldW)); wColor = nc;
+    BF_PAIR_CHANNEL(0) BF_PAIR_CHANNEL(1) BF_PAIR_CHANNEL(2)
+#undef BF_PAIR_CHANNEL
+    const bool zero = cleared & !passB;                                  // cleared voxels are all-zero words (.cu:509-512)
+    wSdf = zero ? 0u : __float_as_uint(nSdf); wWeight = zero ? 0u : __float_as_uint(nW); wColor = zero ? 0u : nc;
+    liveDelta += (int)(nW > 0.0f) - (int)wasLive;
 }
 
 template <int MODE>
 __device__ __forceinline__ void update_fast(const FastPose& pA, const FastPose& pB, bool passA, float sdfA, unsigned colA, bool passB, float sdfB, unsigned colB,
                                             unsigned& wSdf, unsigned& wWeight, unsigned& wColor, int& liveDelta) {
+    if (MODE == 2) { update_pair(pB, passA, sdfA, colA, passB, sdfB, colB, wSdf, wWeight, wColor, liveDelta); return; }
     const bool wasLive = __uint_as_float(wWeight) > 0.0f;
-    if (MODE == 0) { integrate_fast(pA, sdfA, colA, wSdf, wWeight, wColor); }
-    else if (MODE == 1) { deintegrate_fast(sdfA, colA, wSdf, wWeight, wColor); }
-    else {
-        if (passA && passB) reintegrate_fast(pB, sdfA, colA, sdfB, colB, wSdf, wWeight, wColor);
-        else if (passA) deintegrate_fast(sdfA, colA, wSdf, wWeight, wColor);
-        else integrate_fast(pB, sdfB, colB, wSdf, wWeight, wColor);
-    }
+    if (MODE == 0) integrate_fast(pA, sdfA, colA, wSdf, wWeight, wColor);
+    else deintegrate_fast(sdfA, colA, wSdf, wWeight, wColor);
     liveDelta += (int)(__uint_as_float(wWeight) > 0.0f) - (int)wasLive;
 }
 
@@ -272,10 +290,10 @@ __device__ __forceinline__ void process_block_multi(const MultiArgs& a, const Th
                 cB[j] = __ldg(&op.color[(pB.mask >> j) & 1u ? pB.idx[j] : 0u]);
             }
             if (!loaded) { qa = vp[0]; qb = vp[1]; qc = vp[2]; loaded = true; }
-            if (mask & 1u) update_fast<2>(op.A, op.B, pA.mask & 1u, pA.sdf[0], cA[0], pB.mask & 1u, pB.sdf[0], cB[0], qa.x, qa.y, qa.z, liveDelta);
-            if (mask & 2u) update_fast<2>(op.A, op.B, pA.mask & 2u, pA.sdf[1], cA[1], pB.mask & 2u, pB.sdf[1], cB[1], qa.w, qb.x, qb.y, liveDelta);
-            if (mask & 4u) update_fast<2>(op.A, op.B, pA.mask & 4u, pA.sdf[2], cA[2], pB.mask & 4u, pB.sdf[2], cB[2], qb.z, qb.w, qc.x, liveDelta);
-            if (mask & 8u) update_fast<2>(op.A, op.B, pA.mask & 8u, pA.sdf[3], cA[3], pB.mask & 8u, pB.sdf[3], cB[3], qc.y, qc.z, qc.w, liveDelta);
+            if (mask & 1u) update_pair(op.B, pA.mask & 1u, pA.sdf[0], cA[0], pB.mask & 1u, pB.sdf[0], cB[0], qa.x, qa.y, qa.z, liveDelta);
+            if (mask & 2u) update_pair(op.B, pA.mask & 2u, pA.sdf[1], cA[1], pB.mask & 2u, pB.sdf[1], cB[1], qa.w, qb.x, qb.y, liveDelta);
+            if (mask & 4u) update_pair(op.B, pA.mask & 4u, pA.sdf[2], cA[2], pB.mask & 4u, pB.sdf[2], cB[2], qb.z, qb.w, qc.x, liveDelta);
+            if (mask & 8u) update_pair(op.B, pA.mask & 8u, pA.sdf[3], cA[3], pB.mask & 8u, pB.sdf[3], cB[3], qc.y, qc.z, qc.w, liveDelta);
             dirty |= mask;
             passed += __popc(pA.mask) + __popc(pB.mask);
         }
@@ -415,13 +433,15 @@ stencil_multi_kernel(const __grid_constant__ MultiArgs a) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
-static void make_pose(const BFHashParams* hp, FastPose* p) {
+static void make_pose(const BFHashParams* hp, const BFDepthCameraParams* cp, FastPose* p) {
     const float* M = hp->m_rigidTransformInverse.m;
     const double vs = (double)hp->m_virtualVoxelSize;
-    for (int c = 0; c < 3; ++c) {
-        p->cx[c] = (float)((double)M[0 + c] * vs); p->cy[c] = (float)((double)M[4 + c] * vs); p->cz[c] = (float)((double)M[8 + c] * vs);
+    const double fx = cp->fx, fy = cp->fy;
+    for (int c = 0; c < 4; ++c) {
+        const double s = c < 3 ? vs : 1.0;
+        const double rx = (double)M[0 + c] * s, ry = (double)M[4 + c] * s, rz = (double)M[8 + c] * s;
+        p->cx[c] = (float)(fx * rx); p->cy[c] = (float)(fy * ry); p->cz[c] = (float)rz;
     }
-    p->cx[3] = M[3]; p->cy[3] = M[7]; p->cz[3] = M[11];
     p->maxDist = hp->m_maxIntegrationDistance; p->trunc0 = hp->m_truncation; p->truncScale = hp->m_truncScale; p->wMax = (float)hp->m_integrationWeightMax;
 }
 static void make_args(FastArgs* a, const BFHashDataStruct* hd, const BFDepthCameraParams* cp, const float* depth, const void* color,
@@ -439,7 +459,7 @@ int launch_integrate_fast(const BFHashDataStruct* hd, const BFHashParams* hp, co
                           int grid, cudaStream_t s) {
     FastArgs a;
     make_args(&a, hd, cp, depth, color, useListCount, countOverride, ctrs, live, work, set);
-    make_pose(hp, &a.A); a.B = a.A;
+    make_pose(hp, cp, &a.A); a.B = a.A;
     if (work) { if (deIntegrate) stencil_fast_kernel<1, true><<<grid, 128, 0, s>>>(a); else stencil_fast_kernel<0, true><<<grid, 128, 0, s>>>(a); }
     else      { if (deIntegrate) stencil_fast_kernel<1, false><<<grid, 128, 0, s>>>(a); else stencil_fast_kernel<0, false><<<grid, 128, 0, s>>>(a); }
     BF_CHECK(cudaGetLastError());
@@ -450,7 +470,7 @@ int launch_reintegrate_fast(const BFHashDataStruct* hd, const BFHashParams* hpOl
                             const float* depth, const void* color, const int4* work, int set, unsigned* ctrs, int* live, int grid, cudaStream_t s) {
     FastArgs a;
     make_args(&a, hd, cp, depth, color, true, 0, ctrs, live, work, set);
-    make_pose(hpOld, &a.A); make_pose(hpNew, &a.B);
+    make_pose(hpOld, cp, &a.A); make_pose(hpNew, cp, &a.B);
     stencil_fast_kernel<2, true><<<grid, 128, 0, s>>>(a);
     BF_CHECK(cudaGetLastError());
     return 0;
@@ -465,7 +485,7 @@ int launch_reintegrate_multi_fast(const BFHashDataStruct* hd, const BFMultiOpDes
     a.set = set; a.nOps = nOps; a.workCap = workCap; a.ktime = ktime;
     a.cam.W = cp->m_imageWidth; a.cam.H = cp->m_imageHeight; a.cam.fx = cp->fx; a.cam.fy = cp->fy; a.cam.mx5 = cp->mx + 0.5f; a.cam.my5 = cp->my + 0.5f;
     for (int k = 0; k < nOps; ++k) {
-        make_pose(ops[k].hpOld, &a.ops[k].A); make_pose(ops[k].hpNew, &a.ops[k].B);
+        make_pose(ops[k].hpOld, cp, &a.ops[k].A); make_pose(ops[k].hpNew, cp, &a.ops[k].B);
         a.ops[k].depth = ops[k].depth; a.ops[k].color = reinterpret_cast<const unsigned*>(ops[k].color);
     }
     stencil_multi_kernel<<<grid, 128, 0, s>>>(a);

@@ -8,7 +8,7 @@
 
 namespace bf {
 
-enum { CTR_HIGH_WATER = 0, CTR_E = 3, CTR_UB_TOT_LO = 4, CTR_UB_TOT_HI = 5, CTR_EB_TOT_LO = 6, CTR_EB_TOT_HI = 7 /* U / E of the batch launches alone */, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROPPED = 10, CTR_U_TOT_LO = 12, CTR_U_TOT_HI = 13, CTR_E_TOT_LO = 14, CTR_E_TOT_HI = 15,
+enum { CTR_HIGH_WATER = 0, CTR_E = 3, CTR_UB_TOT_LO = 4, CTR_UB_TOT_HI = 5, CTR_EB_TOT_LO = 6, CTR_EB_TOT_HI = 7 /* U / E of the batch launches alone */, CTR_FREED = 8, CTR_HEAP_FAIL = 9, CTR_DROPPED = 10, CTR_CULLB = 11 /* (block, op, pose) probes the batch cull removed, 32-bit running sum */, CTR_U_TOT_LO = 12, CTR_U_TOT_HI = 13, CTR_E_TOT_LO = 14, CTR_E_TOT_HI = 15,
        // two per-list counter sets (the list / work list of op k and of op k+1 are alive at the same time when alloc + compactify of
        // op k+1 run on the front lane while the stencil of op k runs on the back lane); a set is zeroed by the op that is about to fill it
        CTR_SET0 = 16, CTR_SET1 = 24, CTR_NUM = 32,

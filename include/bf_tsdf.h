@@ -244,6 +244,11 @@ typedef struct BFTsdfReintegration { int32_t frame; float oldPose[16]; float new
 int bfTsdfReintegrateBatch(BFHashDataStruct* hashData, BFHashParams* hashParams, const BFDepthCameraParams* depthCameraParams,
                            const BFTsdfReintegration* pairs, int numPairs, const float* const* d_depthFrames, const uint8_t* const* d_colorFrames);
 int bfTsdfSetBatching(int enable);
+/* Batch cull: while building the union list of a batch, a (block, pair, pose) whose voxels provably all fail the truncation test against the pair's
+ * frame (16x16-pixel depth min / max under the block's screen footprint, left behind by the pair's alloc launch; conservative margins) is not
+ * handed to the stencil.  Results are identical with it on (default) or off (BF_TSDF_BATCH_CULL=0 / bfTsdfSetBatchCull(0)); E (in-frustum blocks)
+ * still counts the culled entries, bfTsdfGetProfileEx out[15] reports how many probes were removed.  Returns the previous setting. */
+int bfTsdfSetBatchCull(int enable);
 
 /* CUDASceneRepHashSDF::garbageCollect (h:110-126) over the last compactified list */
 int bfTsdfGarbageCollect(BFHashDataStruct* hashData, const BFHashParams* hashParams);
@@ -266,7 +271,8 @@ int bfTsdfGetLastFrameStats(const BFHashDataStruct* hashData, unsigned long long
  *                       batch launch); synchronises and restarts the accumulation. */
 unsigned long long bfGetLaunchCount(void);
 /* bfTsdfGetProfile plus the batch launches alone: out[8] batch launches, out[9] timed, out[10] their duration (ns), out[11] their U, out[12] their E,
- * out[13] frame images they read (out[6..7], out[14..15] = 0) */
+ * out[13] frame images they read, out[14] their duration by in-kernel %globaltimer brackets (first CTA start to last CTA end, ns),
+ * out[15] (block, pair, pose) entries the batch cull removed (32-bit running sum); out[6..7] = 0 */
 int bfTsdfGetProfileEx(const BFHashDataStruct* hashData, unsigned long long out[16]);
 int bfTsdfSetProfiling(int enable);
 int bfTsdfGetProfile(const BFHashDataStruct* hashData, unsigned long long out[8]);
