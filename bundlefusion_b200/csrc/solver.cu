@@ -34,7 +34,7 @@ extern unsigned long long g_launchCount;      // defined in tsdf.cu (bfGetLaunch
 #define BF_FLOAT_EPSILON 0.000001f      // FL/SolverUtil.h:9
 #define BF_MAX_ROW 8192                 // longest variable row the in-smem row sort handles
 #define BF_SOLVER_THREADS 256
-#define BF_DENSE_MAX_IMAGES 64          // the dense term is built for chunk-sized problems (local BA: 11 images)
+#define BF_DENSE_MAX_IMAGES 4096        // dense term: N^2 pair tables + one 90-sum record per image pair (allocated on first use, sized by the workspace)
 
 __device__ void mat4_mul(const float* a, const float* b, float* o) {
 #pragma unroll
@@ -78,10 +78,18 @@ struct SolverWs {
     float* partials = nullptr;    // [2][maxGrid]
     float* p2 = nullptr;          // [2][N][3] second search-direction buffer (rot, trans): p ping-pongs so that the update of p
                                   // can be fused into the next mat-vec (2 grid barriers per PCG iteration instead of 3)
-    // dense depth / colour term (N <= BF_DENSE_MAX_IMAGES): pair weights, per-pair 90-sum records, assembled dense system
-    float* pairW = nullptr;       // [Nd*Nd]
-    float* pairOut = nullptr;     // [Nd*Nd][90]
-    float* denseJtJ = nullptr;    // [(6 Nd)^2]  (translation-first ordering per image, as the reference)
+    // dense depth / colour term, block-sparse: the reference keeps a dense (6N)^2 matrix (576 MB at N = 2000, read in full by every PCG
+    // iteration); here only the image pairs that carry weight exist.  Allocated by ensure_dense() on the first dense solve, Nd = maxImages.
+    unsigned denseCap = 0;        // Nd the dense buffers were sized for (0: not allocated)
+    float* pairW = nullptr;       // [Nd*Nd]   weight of pair (i < j), 0 = none
+    int*   pairIdx = nullptr;     // [Nd*Nd]   index of pair (i < j) in the pair list
+    int*   pairCnt = nullptr;     // [2][Nd]   per image: pairs it leads (j > i), pairs it is part of
+    int*   pairRowStart = nullptr;// [Nd+1]    pair list offsets by leading image (the list is sorted by (i, j))
+    int2*  pairIJ = nullptr;      // [maxPairs]
+    float* pairOut = nullptr;     // [maxPairs][90] per pair: J_i^T J_i (21, upper triangle), J_j^T J_j (21), J_i^T J_j (36), J_i^T r (6), J_j^T r (6)
+    int*   dnbrStart = nullptr;   // [Nd+1]    per image: its pairs, ascending in the other image
+    int2*  dnbr = nullptr;        // [2 maxPairs] {other image, pair index}
+    float* denseDiag = nullptr;   // [Nd][36]  diagonal 6x6 blocks (translation-first ordering per image, as the reference)
     float* denseJtr = nullptr;    // [6 Nd]
     unsigned* scal = nullptr;     // [SC_NUM]
     int maxGrid = 0;
@@ -91,7 +99,8 @@ struct SolverWs {
 static void free_ws(SolverWs& w) {
     cudaFree(w.rowCount); cudaFree(w.rowStart); cudaFree(w.cursor); cudaFree(w.entries); cudaFree(w.nbrs); cudaFree(w.segCount); cudaFree(w.segs);
     cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.p2); cudaFree(w.scal);
-    cudaFree(w.pairW); cudaFree(w.pairOut); cudaFree(w.denseJtJ); cudaFree(w.denseJtr);
+    cudaFree(w.pairW); cudaFree(w.pairIdx); cudaFree(w.pairCnt); cudaFree(w.pairRowStart); cudaFree(w.pairIJ); cudaFree(w.pairOut); cudaFree(w.dnbrStart); cudaFree(w.dnbr);
+    cudaFree(w.denseDiag); cudaFree(w.denseJtr);
 }
 static std::mutex g_wsMutex;
 static std::map<const void*, SolverWs> g_ws;
@@ -124,18 +133,27 @@ static int get_ws(const BFSolverState* st, unsigned maxImages, unsigned maxCorr,
     BF_WS_ALLOC(w.partials, sizeof(float) * 2 * w.maxGrid);
     BF_WS_ALLOC(w.p2, sizeof(float) * 6 * maxImages);
     BF_WS_ALLOC(w.scal, sizeof(unsigned) * SC_NUM);
-    {
-        const size_t Nd = BF_DENSE_MAX_IMAGES;
-        BF_WS_ALLOC(w.pairW, sizeof(float) * Nd * Nd);
-        BF_WS_ALLOC(w.pairOut, sizeof(float) * Nd * Nd * 90);
-        BF_WS_ALLOC(w.denseJtJ, sizeof(float) * 36 * Nd * Nd);
-        BF_WS_ALLOC(w.denseJtr, sizeof(float) * 6 * Nd);
-    }
-#undef BF_WS_ALLOC
     auto res = g_ws.emplace(st->d_deltaRot, w);
     *out = &res.first->second;
     return 0;
 }
+static int ensure_dense(SolverWs* w) {
+    if (w->denseCap >= w->maxImages) return 0;
+    const size_t Nd = w->maxImages, maxPairs = Nd * (Nd - 1) / 2 + 1;
+    BF_WS_ALLOC(w->pairW, sizeof(float) * Nd * Nd);
+    BF_WS_ALLOC(w->pairIdx, sizeof(int) * Nd * Nd);
+    BF_WS_ALLOC(w->pairCnt, sizeof(int) * 2 * Nd);
+    BF_WS_ALLOC(w->pairRowStart, sizeof(int) * (Nd + 1));
+    BF_WS_ALLOC(w->pairIJ, sizeof(int2) * maxPairs);
+    BF_WS_ALLOC(w->pairOut, sizeof(float) * 90 * maxPairs);
+    BF_WS_ALLOC(w->dnbrStart, sizeof(int) * (Nd + 1));
+    BF_WS_ALLOC(w->dnbr, sizeof(int2) * 2 * maxPairs);
+    BF_WS_ALLOC(w->denseDiag, sizeof(float) * 36 * Nd);
+    BF_WS_ALLOC(w->denseJtr, sizeof(float) * 6 * Nd);
+    w->denseCap = (unsigned)Nd;
+    return 0;
+}
+#undef BF_WS_ALLOC
 
 // ---- preparation: variable rows (CSR), reference-format table, neighbour segments ----------------------------
 __device__ __forceinline__ bool corr_valid(const BFEntryJ& c) { return c.imgIdx_i != 0xFFFFFFFFu; }
@@ -285,7 +303,7 @@ struct GnArgs {
     float* offBlk; float* segMom; float* diagBlk; float* partials; unsigned* scal;
     float* p2Rot; float* p2Trans;
     float wSparse; unsigned nLin; int isLastGn; int maxGrid;
-    const float* denseJtJ; const float* denseJtr; int useDense;       // dense term: assembled system (NULL / 0 when off)
+    const int* dnbrStart; const int2* dnbr; const float* pairOut; const float* denseDiag; const float* denseJtr; int useDense;       // dense term, block-sparse (NULL / 0 when off)
 };
 
 // 6x6 block times 6-vector (rot,trans order)
@@ -480,16 +498,21 @@ gn_iteration_kernel(const GnArgs a) {
                 const V3 pt = fly ? ld3(a.zTrans, o) + ld3(prvT, o) * beta : ld3(a.pTrans, o);
                 blk_mv(&a.offBlk[36 * (size_t)(rs + sI)], pr, pt, y);
             }
-            if (denseOn) {      // dense J^T J p (applyJTJDenseDevice, SolverBundlingDenseUtil.h:371-411): lanes over column blocks
-                const unsigned dim = 6 * N;
-                for (unsigned o = 1 + lane; o < N; o += 32) {
-                    const float* B = &a.denseJtJ[(size_t)(v * 6) * dim + o * 6];
+            if (denseOn) {      // dense J^T J p (applyJTJDenseDevice, SolverBundlingDenseUtil.h:371-411) over the pairs image v is part of; record
+                                // coordinates are translation-first: p_rec = (trans, rot), y_rec[0..2] -> trans rows, y_rec[3..5] -> rot rows
+                const int e1 = a.dnbrStart[v + 1];
+                for (int e = a.dnbrStart[v] + (int)lane; e < e1; e += 32) {
+                    const int2 nb = a.dnbr[e];
+                    const unsigned o = (unsigned)nb.x;
+                    if (o == 0) continue;
+                    const float* B = &a.pairOut[(size_t)nb.y * 90 + 42];                 // J_lo^T J_hi, [a over lo][b over hi]
                     const V3 pr = fly ? ld3(a.zRot, o) + ld3(prvR, o) * beta : ld3(a.pRot, o);
                     const V3 pt = fly ? ld3(a.zTrans, o) + ld3(prvT, o) * beta : ld3(a.pTrans, o);
+                    const int sa = (v < o) ? 6 : 1, sb = (v < o) ? 1 : 6;               // v is the pair's hi image: the transposed block
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
-                        y[3 + r] += B[r * dim + 0] * pt.x + B[r * dim + 1] * pt.y + B[r * dim + 2] * pt.z + B[r * dim + 3] * pr.x + B[r * dim + 4] * pr.y + B[r * dim + 5] * pr.z;
-                        y[r] += B[(3 + r) * dim + 0] * pt.x + B[(3 + r) * dim + 1] * pt.y + B[(3 + r) * dim + 2] * pt.z + B[(3 + r) * dim + 3] * pr.x + B[(3 + r) * dim + 4] * pr.y + B[(3 + r) * dim + 5] * pr.z;
+                        y[3 + r] += B[r * sa + 0 * sb] * pt.x + B[r * sa + 1 * sb] * pt.y + B[r * sa + 2 * sb] * pt.z + B[r * sa + 3 * sb] * pr.x + B[r * sa + 4 * sb] * pr.y + B[r * sa + 5 * sb] * pr.z;
+                        y[r] += B[(3 + r) * sa + 0 * sb] * pt.x + B[(3 + r) * sa + 1 * sb] * pt.y + B[(3 + r) * sa + 2 * sb] * pt.z + B[(3 + r) * sa + 3 * sb] * pr.x + B[(3 + r) * sa + 4 * sb] * pr.y + B[(3 + r) * sa + 5 * sb] * pr.z;
                     }
                 }
             }
@@ -500,6 +523,14 @@ gn_iteration_kernel(const GnArgs a) {
                 const V3 pt = fly ? ld3(a.zTrans, v) + ld3(prvT, v) * beta : ld3(a.pTrans, v);
                 if (fly) { st3(curR, v, pr); st3(curT, v, pt); }
                 blk_mv(&a.diagBlk[36 * (size_t)v], pr, pt, y);
+                if (denseOn) {
+                    const float* D = &a.denseDiag[36 * (size_t)v];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        y[3 + r] += D[r * 6 + 0] * pt.x + D[r * 6 + 1] * pt.y + D[r * 6 + 2] * pt.z + D[r * 6 + 3] * pr.x + D[r * 6 + 4] * pr.y + D[r * 6 + 5] * pr.z;
+                        y[r] += D[(3 + r) * 6 + 0] * pt.x + D[(3 + r) * 6 + 1] * pt.y + D[(3 + r) * 6 + 2] * pt.z + D[(3 + r) * 6 + 3] * pr.x + D[(3 + r) * 6 + 4] * pr.y + D[(3 + r) * 6 + 5] * pr.z;
+                    }
+                }
                 st3(a.ApRot, v, mk(y[0], y[1], y[2])); st3(a.ApTrans, v, mk(y[3], y[4], y[5]));
                 pAp += pr.x * y[0] + pr.y * y[1] + pr.z * y[2] + pt.x * y[3] + pt.y * y[4] + pt.z * y[5];
             }
@@ -584,7 +615,7 @@ struct DenseArgs {
     unsigned N, W, H; float fx, fy, mx, my;
     float distThresh, normalThresh, colorThresh, colorGradientMin, depthMin, depthMax;
     unsigned subsample; int usePairwise; float wDepth, wColor;
-    float* pairW; float* pairOut; float* JtJ; float* Jtr; unsigned* scal;
+    float* pairW; int* pairIdx; int* pairCnt; int* pairRowStart; int2* pairIJ; float* pairOut; int* dnbrStart; int2* dnbr; float* diag; float* Jtr; unsigned* scal;
 };
 __device__ __forceinline__ V3 rot3(const float* m, V3 v) { return mk(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); }
 __device__ __forceinline__ V3 depth_to_cam(const DenseArgs& d, int x, int y, float depth) {
@@ -745,13 +776,60 @@ __device__ __forceinline__ void accum_rows(float* acc, const float* ri, const fl
 #pragma unroll
     for (int a = 0; a < 6; ++a) { if (hasI) acc[78 + a] += ri[a] * res * w; if (hasJ) acc[84 + a] += rj[a] * res * w; }
 }
+// ---- pair list: the weighted pairs in (i, j) order, and per image the pairs it is part of ----
+// one warp per image v: pairs it leads (j > v) and pairs it is part of
+__global__ void dense_pair_count_kernel(const DenseArgs d) {
+    if (d.scal[SC_DONE] != 0) return;
+    const unsigned v = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31, N = d.N;
+    if (v >= N) return;
+    int lead = 0, all = 0;
+    for (unsigned o = lane; o < N; o += 32) {
+        if (o == v) continue;
+        const bool w = (o < v ? d.pairW[o * N + v] : d.pairW[v * N + o]) != 0.0f;
+        all += w ? 1 : 0; lead += (w && o > v) ? 1 : 0;
+    }
+    for (int s = 16; s > 0; s >>= 1) { lead += __shfl_xor_sync(0xffffffffu, lead, s); all += __shfl_xor_sync(0xffffffffu, all, s); }
+    if (lane == 0) { d.pairCnt[v] = lead; d.pairCnt[N + v] = all; }
+}
+// exclusive scans of the two counts (one CTA; N <= 4096)
+__global__ void __launch_bounds__(1024)
+dense_pair_scan_kernel(const DenseArgs d) {
+    if (d.scal[SC_DONE] != 0) return;
+    __shared__ int sA[1024], sB[1024];
+    const unsigned N = d.N, t = threadIdx.x, per = (N + 1023) / 1024;
+    int a = 0, b = 0;
+    for (unsigned k = t * per; k < N && k < (t + 1) * per; ++k) { a += d.pairCnt[k]; b += d.pairCnt[N + k]; }
+    sA[t] = a; sB[t] = b;
+    __syncthreads();
+    if (t == 0) { int ra = 0, rb = 0; for (int k = 0; k < 1024; ++k) { const int x = sA[k], y = sB[k]; sA[k] = ra; sB[k] = rb; ra += x; rb += y; } d.pairRowStart[N] = ra; d.dnbrStart[N] = rb; }
+    __syncthreads();
+    a = sA[t]; b = sB[t];
+    for (unsigned k = t * per; k < N && k < (t + 1) * per; ++k) { d.pairRowStart[k] = a; d.dnbrStart[k] = b; a += d.pairCnt[k]; b += d.pairCnt[N + k]; }
+}
+// one warp per image i: its pairs (i, j > i) in ascending j
+__global__ void dense_pair_fill_kernel(const DenseArgs d) {
+    if (d.scal[SC_DONE] != 0) return;
+    const unsigned i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31, N = d.N;
+    if (i >= N) return;
+    int k = d.pairRowStart[i];
+    for (unsigned j0 = i + 1; j0 < N; j0 += 32) {
+        const unsigned j = j0 + lane;
+        const bool w = j < N && d.pairW[i * N + j] != 0.0f;
+        const unsigned bal = __ballot_sync(0xffffffffu, w);
+        if (w) { const int kk = k + __popc(bal & ((1u << lane) - 1u)); d.pairIJ[kk] = make_int2((int)i, (int)j); d.pairIdx[i * N + j] = kk; }
+        k += __popc(bal);
+    }
+}
 __global__ void __launch_bounds__(128)
 dense_build_kernel(const DenseArgs d) {
     __shared__ float sAcc[4][90];
-    const unsigned i = blockIdx.x, j = blockIdx.y, N = d.N;
-    if (d.scal[SC_DONE] != 0 || i >= j) return;
+    const unsigned N = d.N;
+    if (d.scal[SC_DONE] != 0) return;
+    const int P = d.pairRowStart[N];
+  for (int pk = (int)blockIdx.x; pk < P; pk += (int)gridDim.x) {
+    const int2 ij = d.pairIJ[pk];
+    const unsigned i = (unsigned)ij.x, j = (unsigned)ij.y;
     const float pairW = d.pairW[i * N + j];
-    if (pairW == 0.0f) return;
     const BFCUDACachedFrame fi = d.frames[i], fj = d.frames[j];
     const float* Ti = &d.T[16 * i]; const float* Tj = &d.T[16 * j]; const float* Tii = &d.Tinv[16 * i]; const float* Tji = &d.Tinv[16 * j];
     float tr[16]; mat4_mul(Tii, Tj, tr);
@@ -818,46 +896,54 @@ dense_build_kernel(const DenseArgs d) {
 #pragma unroll
     for (int k = 0; k < 90; ++k) { const float v = warp_sum(acc[k]); if ((threadIdx.x & 31) == 0) sAcc[threadIdx.x >> 5][k] = v; }
     __syncthreads();
-    if (threadIdx.x < 90) d.pairOut[(size_t)(i * N + j) * 90 + threadIdx.x] = sAcc[0][threadIdx.x] + sAcc[1][threadIdx.x] + sAcc[2][threadIdx.x] + sAcc[3][threadIdx.x];
+    if (threadIdx.x < 90) d.pairOut[(size_t)pk * 90 + threadIdx.x] = sAcc[0][threadIdx.x] + sAcc[1][threadIdx.x] + sAcc[2][threadIdx.x] + sAcc[3][threadIdx.x];
+    __syncthreads();
+  }
 }
-// dense system in the reference's layout: entry (row, col) of the (6N)^2 matrix, translation-first per image, symmetric
+// Per image v (one 64-thread CTA): its pair list {other image, pair index} in ascending other image, the diagonal 6x6 block and J^T r as the sums of
+// its pairs' records in that order (the order the dense (6N)^2 assembly of the reference's layout sums them in) -- translation first per image.
 __device__ __forceinline__ int tri_index(int a, int b) { if (a > b) { const int t = a; a = b; b = t; } return a * 6 - (a * (a - 1)) / 2 + (b - a); }   // (a<=b) -> 0..20
-__global__ void dense_assemble_kernel(const DenseArgs d) {
-    const unsigned N = d.N, dim = 6 * N;
+__global__ void __launch_bounds__(64)
+dense_assemble_kernel(const DenseArgs d) {
+    const unsigned N = d.N, v = blockIdx.x, t = threadIdx.x;
     if (d.scal[SC_DONE] != 0) return;
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < dim * dim + dim; e += gridDim.x * blockDim.x) {
-        if (e >= dim * dim) {            // J^T r
-            const unsigned r = e - dim * dim, v = r / 6, a = r % 6;
-            float sum = 0.0f;
-            for (unsigned o = 0; o < N; ++o) {
-                if (o == v) continue;
-                const unsigned lo = o < v ? o : v, hi = o < v ? v : o;
-                if (d.pairW[lo * N + hi] == 0.0f) continue;
-                sum += d.pairOut[(size_t)(lo * N + hi) * 90 + (v == lo ? 78 : 84) + a];
-            }
-            d.Jtr[r] = sum;
-            continue;
+    const int e0 = d.dnbrStart[v], e1 = d.dnbrStart[v + 1];
+    if (t < 32) {
+        int k = e0;
+        for (unsigned o0 = 0; o0 < N; o0 += 32) {
+            const unsigned o = o0 + t;
+            const bool w = o < N && o != v && (o < v ? d.pairW[o * N + v] : d.pairW[v * N + o]) != 0.0f;
+            const unsigned bal = __ballot_sync(0xffffffffu, w);
+            if (w) d.dnbr[k + __popc(bal & ((1u << t) - 1u))] = make_int2((int)o, o < v ? d.pairIdx[o * N + v] : d.pairIdx[v * N + o]);
+            k += __popc(bal);
         }
-        const unsigned row = e / dim, col = e % dim, rv = row / 6, cv = col / 6, ra = row % 6, cb = col % 6;
-        float val = 0.0f;
-        if (rv == cv) {
-            for (unsigned o = 0; o < N; ++o) {
-                if (o == rv) continue;
-                const unsigned lo = o < rv ? o : rv, hi = o < rv ? rv : o;
-                if (d.pairW[lo * N + hi] == 0.0f) continue;
-                val += d.pairOut[(size_t)(lo * N + hi) * 90 + (rv == lo ? 0 : 21) + tri_index((int)ra, (int)cb)];
-            }
-        } else {
-            const unsigned lo = rv < cv ? rv : cv, hi = rv < cv ? cv : rv;
-            if (d.pairW[lo * N + hi] != 0.0f) {
-                // ij record: [a over image lo (=i)][b over image hi (=j)]
-                const unsigned a = (rv == lo) ? ra : cb, b = (rv == lo) ? cb : ra;
-                val = d.pairOut[(size_t)(lo * N + hi) * 90 + 42 + a * 6 + b];
-            }
-        }
-        d.JtJ[e] = val;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.scal[SC_DENSE_ON] = (d.scal[SC_DENSE_OVERLAP] > 0) ? 1u : 0u;
+    __syncthreads();
+    if (t < 36) {
+        const int a = (int)t / 6, b = (int)t % 6, tri = tri_index(a, b);
+        float val = 0.0f;
+        for (int e = e0; e < e1; ++e) { const int2 nb = d.dnbr[e]; val += d.pairOut[(size_t)nb.y * 90 + ((unsigned)nb.x > v ? 0 : 21) + tri]; }
+        d.diag[36 * (size_t)v + t] = val;
+    } else if (t < 42) {
+        const int a = (int)t - 36;
+        float sum = 0.0f;
+        for (int e = e0; e < e1; ++e) { const int2 nb = d.dnbr[e]; sum += d.pairOut[(size_t)nb.y * 90 + ((unsigned)nb.x > v ? 78 : 84) + a]; }
+        d.Jtr[6 * v + a] = sum;
+    }
+    if (v == 0 && t == 0) d.scal[SC_DENSE_ON] = (d.scal[SC_DENSE_OVERLAP] > 0) ? 1u : 0u;
+}
+// test accessor: the block-sparse system scattered into the reference's dense layout ((6N)^2 row-major, zeroed by the caller)
+__global__ void dense_scatter_kernel(unsigned N, const int* dnbrStart, const int2* dnbr, const float* pairOut, const float* diag, float* JtJ) {
+    const unsigned v = blockIdx.x, dim = 6 * N;
+    for (unsigned t = threadIdx.x; t < 36; t += blockDim.x) JtJ[(size_t)(6 * v + t / 6) * dim + 6 * v + t % 6] = diag[36 * (size_t)v + t];
+    for (int e = dnbrStart[v]; e < dnbrStart[v + 1]; ++e) {
+        const int2 nb = dnbr[e];
+        const unsigned o = (unsigned)nb.x;
+        for (unsigned t = threadIdx.x; t < 36; t += blockDim.x) {
+            const unsigned ra = t / 6, cb = t % 6;
+            JtJ[(size_t)(6 * v + ra) * dim + 6 * o + cb] = pairOut[(size_t)nb.y * 90 + 42 + (v < o ? ra * 6 + cb : cb * 6 + ra)];
+        }
+    }
 }
 
 // ---- small kernels behind the reference-named stubs -------------------------------------------------------------
@@ -1002,8 +1088,10 @@ static int run_gn(const BFSolverInput* in, const BFSolverState* st, const BFSolv
     a.wSparse = in->weightsSparse[nIter]; a.nLin = par->nLinIterations; a.isLastGn = isLast ? 1 : 0; a.maxGrid = ws->maxGrid;
     const float wDepth = in->weightsDenseDepth ? in->weightsDenseDepth[nIter] : 0.0f, wColor = in->weightsDenseColor ? in->weightsDenseColor[nIter] : 0.0f;
     const bool dense = (wDepth > 0.0f || wColor > 0.0f) && in->d_cacheFrames != nullptr;
-    a.denseJtJ = ws->denseJtJ; a.denseJtr = ws->denseJtr; a.useDense = dense ? 1 : 0;
+    a.dnbrStart = nullptr; a.dnbr = nullptr; a.pairOut = nullptr; a.denseDiag = nullptr; a.denseJtr = nullptr; a.useDense = dense ? 1 : 0;
     if (dense) {
+        { const int rc = ensure_dense(ws); if (rc) return rc; }
+        a.dnbrStart = ws->dnbrStart; a.dnbr = ws->dnbr; a.pairOut = ws->pairOut; a.denseDiag = ws->denseDiag; a.denseJtr = ws->denseJtr;
         // BuildDenseSystem (SolverBundling.cu:308-471) for this iteration's poses: 1 pose kernel + 3 dense kernels, no host sync
         DenseArgs d;
         d.frames = in->d_cacheFrames; d.valid = in->d_validImages; d.T = st->d_xTransforms; d.Tinv = st->d_xTransformInverses;
@@ -1013,14 +1101,19 @@ static int run_gn(const BFSolverInput* in, const BFSolverState* st, const BFSolv
         d.colorGradientMin = par->denseColorGradientMin; d.depthMin = par->denseDepthMin; d.depthMax = par->denseDepthMax;
         d.subsample = par->denseOverlapCheckSubsampleFactor ? par->denseOverlapCheckSubsampleFactor : 1; d.usePairwise = par->useDenseDepthAllPairwise ? 1 : 0;
         d.wDepth = wDepth; d.wColor = wColor;
-        d.pairW = ws->pairW; d.pairOut = ws->pairOut; d.JtJ = ws->denseJtJ; d.Jtr = ws->denseJtr; d.scal = ws->scal;
+        d.pairW = ws->pairW; d.pairIdx = ws->pairIdx; d.pairCnt = ws->pairCnt; d.pairRowStart = ws->pairRowStart; d.pairIJ = ws->pairIJ; d.pairOut = ws->pairOut;
+        d.dnbrStart = ws->dnbrStart; d.dnbr = ws->dnbr; d.diag = ws->denseDiag; d.Jtr = ws->denseJtr; d.scal = ws->scal;
         dense_begin_kernel<<<(a.N + 127) / 128, 128, 0, stream()>>>(st->d_xRot, st->d_xTrans, a.N, st->d_xTransforms, st->d_xTransformInverses, ws->scal);
         dense_pair_weight_kernel<<<dim3(a.N, a.N), 512, 0, stream()>>>(d);
-        dense_build_kernel<<<dim3(a.N, a.N), 128, 0, stream()>>>(d);
-        const unsigned entries = 36 * a.N * a.N + 6 * a.N;
-        dense_assemble_kernel<<<(entries + 255) / 256, 256, 0, stream()>>>(d);
+        dense_pair_count_kernel<<<(a.N + 7) / 8, 256, 0, stream()>>>(d);
+        dense_pair_scan_kernel<<<1, 1024, 0, stream()>>>(d);
+        dense_pair_fill_kernel<<<(a.N + 7) / 8, 256, 0, stream()>>>(d);
+        const unsigned long long maxPairs = (unsigned long long)a.N * (a.N - 1) / 2;
+        const unsigned buildGrid = (unsigned)std::min<unsigned long long>(maxPairs, (unsigned long long)num_sms() * 8);
+        dense_build_kernel<<<buildGrid ? buildGrid : 1, 128, 0, stream()>>>(d);
+        dense_assemble_kernel<<<a.N, 64, 0, stream()>>>(d);
         BF_CHECK(cudaGetLastError());
-        g_launchCount += 4;
+        g_launchCount += 7;
     }
     void* args[] = { (void*)&a };
     ++g_launchCount;
@@ -1077,7 +1170,7 @@ static int solve_impl(const BFSolverInput* in, const BFSolverState* st, const BF
     for (unsigned k = 0; k < par->nNonLinearIterations; ++k)
         if (((in->weightsDenseDepth && in->weightsDenseDepth[k] > 0.0f) || (in->weightsDenseColor && in->weightsDenseColor[k] > 0.0f)) &&
             in->d_cacheFrames != nullptr && in->numberOfImages > BF_DENSE_MAX_IMAGES) {
-            set_last_error("bfSolverSolve: the dense depth/colour term is built for <= 64 images (chunk-sized problems) in this round", cudaErrorNotSupported);
+            set_last_error("bfSolverSolve: the dense depth/colour term keeps N^2 pair tables: <= 4096 images", cudaErrorNotSupported);
             return (int)cudaErrorNotSupported;
         }
     if (in->maxCorrPerImage == 0 || in->maxCorrPerImage > BF_MAX_ROW) {      // CUDASolverBundling.cpp:39 clamps it to [1000, 4000]
@@ -1152,9 +1245,13 @@ BF_API int bfSolverReleaseWorkspace(const BFSolverState* st) {
 BF_API int bfSolverDebugDenseSystem(const BFSolverState* st, unsigned int numImages, float* d_JtJ, float* d_Jtr) {
     SolverWs* ws = nullptr;
     { std::lock_guard<std::mutex> lk(g_wsMutex); auto it = g_ws.find(st->d_deltaRot); if (it != g_ws.end()) ws = &it->second; }
-    if (!ws || numImages > BF_DENSE_MAX_IMAGES) return (int)cudaErrorInvalidValue;
+    if (!ws || !ws->denseCap || numImages > ws->denseCap) return (int)cudaErrorInvalidValue;
     const size_t dim = 6 * (size_t)numImages;
-    if (d_JtJ) BF_CHECK(cudaMemcpyAsync(d_JtJ, ws->denseJtJ, sizeof(float) * dim * dim, cudaMemcpyDeviceToDevice, stream()));
+    if (d_JtJ) {
+        BF_CHECK(cudaMemsetAsync(d_JtJ, 0, sizeof(float) * dim * dim, stream()));
+        dense_scatter_kernel<<<numImages, 64, 0, stream()>>>(numImages, ws->dnbrStart, ws->dnbr, ws->pairOut, ws->denseDiag, d_JtJ);
+        BF_CHECK(cudaGetLastError());
+    }
     if (d_Jtr) BF_CHECK(cudaMemcpyAsync(d_Jtr, ws->denseJtr, sizeof(float) * dim, cudaMemcpyDeviceToDevice, stream()));
     return 0;
 }

@@ -200,3 +200,14 @@ def test_local_chunk_sparse_plus_dense_matches_oracle(cuda_device):
         o = orc.solve(prob["corr"], prob["init_rot"], prob["init_trans"], 2, 100, [1.0, 1.0], [1.0, 2.0], wC, prob["caches"], prob["intrinsics"])
         assert g["stats"]["dense_weighted_pairs"] == o["weighted_pairs"] > 10
         assert rel_l2(np.c_[g["rot"], g["trans"]], np.c_[o["rot"], o["trans"]]) < 1e-4
+
+
+def test_dense_term_beyond_64_images_matches_oracle(cuda_device):
+    """Row a13 at keyframe scale: the dense term is kept block-sparse (one record per weighted image pair, no (6N)^2 matrix), so it has no 64-image
+    limit.  72 frames, sparse + dense depth + colour, against the oracle (which builds the reference's dense matrix)."""
+    prob = synth.make_dense_ba_problem(72, stride=1, start=60, corr_per_pair=8, W=320, H=240)
+    wS, wD, wC = [1.0, 1.0], [1.0, 2.0], [0.1, 0.1]
+    g = gpu_solve_dense(cuda_device, prob, 2, 40, wS, wD, wC)
+    o = orc.solve(prob["corr"], prob["init_rot"], prob["init_trans"], 2, 40, wS, wD, wC, prob["caches"], prob["intrinsics"])
+    assert g["stats"]["dense_overlap_pairs"] == o["overlap_pairs"] and g["stats"]["dense_weighted_pairs"] == o["weighted_pairs"] > 500
+    assert rel_l2(np.c_[g["rot"], g["trans"]], np.c_[o["rot"], o["trans"]]) < 1e-4

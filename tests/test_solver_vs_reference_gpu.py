@@ -195,6 +195,33 @@ def test_dense_system_matches_reference_cuda(cuda_device):
     assert blk < 1e-4
 
 
+def test_dense_term_beyond_64_images_matches_reference_cuda(cuda_device):
+    """The dense term at N = 72 (> the 64 images the first version stopped at), where the reference's dense (6N)^2 matrix still fits comfortably:
+    (a) this library's block-sparse system, scattered into the reference's layout, against the reference's d_denseJtJ / d_denseJtr entry for entry;
+    (b) the solved poses of a sparse + dense depth + colour solve."""
+    import torch
+    N = 72
+    prob = synth.make_dense_ba_problem(N, stride=1, start=60, corr_per_pair=8, W=320, H=240)
+    cache = DeviceCache(prob["caches"], prob["intrinsics"], cuda_device)
+    x_ref, _, s = run_ref(cuda_device, prob, prob["corr"][:0], 1, 0, [0.0], [1.0], [0.1], cache=cache, fast=False)
+    JtJ_ref = s._bufs["d_denseJtJ"].cpu().numpy().reshape(6 * N, 6 * N); Jtr_ref = s._bufs["d_denseJtr"].cpu().numpy()
+    corr_t, rot, trans, valid = _dev_inputs(cuda_device, prob, prob["corr"][:0])
+    sv = CUDASolverBundling(N, 1000 * N, cuda_device)
+    sv.solve(corr_t, 0, valid, N, 1, 0, [0.0], [1.0], [0.1], d_rotationAnglesUnknowns=rot, d_translationUnknowns=trans, cudaCache=cache)
+    d_JtJ = torch.zeros(36 * N * N, device=cuda_device); d_Jtr = torch.zeros(6 * N, device=cuda_device)
+    capi.check(sv.lib.bfSolverDebugDenseSystem(C.byref(sv.m_solverState), N, C.c_void_p(d_JtJ.data_ptr()), C.c_void_p(d_Jtr.data_ptr())), "bfSolverDebugDenseSystem")
+    torch.cuda.synchronize()
+    JtJ_our, Jtr_our = d_JtJ.cpu().numpy().reshape(6 * N, 6 * N), d_Jtr.cpu().numpy()
+    assert np.count_nonzero(JtJ_ref[6:, 6:]) > 36 * 500
+    assert rel_l2(JtJ_our[6:, 6:], JtJ_ref[6:, 6:]) < TOL and rel_l2(Jtr_our[6:], Jtr_ref[6:]) < TOL
+    assert np.array_equal(JtJ_our[6:, 6:] != 0, JtJ_ref[6:, 6:] != 0), "same block sparsity as the reference's dense matrix"
+    wS, wD, wC = [1.0, 1.0], [1.0, 2.0], [0.1, 0.1]
+    x_ref, _, s = run_ref(cuda_device, prob, prob["corr"], 2, 40, wS, wD, wC, cache=cache, fast=False)
+    x_our, st = run_ours(cuda_device, prob, prob["corr"], 2, 40, wS, wD, wC, cache=cache)
+    assert st["dense_overlap_pairs"] == int(s._bufs["d_numDenseOverlappingImages"].cpu().numpy()[0])
+    assert rel_l2(x_our, x_ref) < TOL
+
+
 def test_max_residual_and_pose_stubs_match_reference_cuda(cuda_device):
     import torch
     dev = cuda_device
