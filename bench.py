@@ -412,11 +412,18 @@ def run_loop(args):
     timed(pre, Wm, False, False)
     for k in stats: stats[k] = 0
     clk_mark0 = len(clk_lines)
+    if args.cuda_profiler:
+        torch.cuda.profiler.start()
     ms, launches = timed(pre + Wm, K, False, False)
+    if args.cuda_profiler:
+        torch.cuda.profiler.stop()
     clk_mark1 = len(clk_lines)
     c_before = loop.counters()
     prev_lanes = L.bfTsdfSetLanes(0)                       # the stencil is timed alone on its stream: the burst HBM peak is its roof
+    loop.set_profiling(True)
     timed(pre + Wm + K, K, False, True)
+    stages = loop.stage_times()
+    loop.set_profiling(False)
     L.bfTsdfSetLanes(prev_lanes)
     prof = (ctypes.c_ulonglong * 16)()
     capi.check(L.bfTsdfGetProfileEx(L.bfFrameLoopGetHashData(loop._h), prof), "bfTsdfGetProfileEx")
@@ -471,6 +478,7 @@ def run_loop(args):
                 "frames_with_pose": stats_e2e["valid"], "local_solves": stats_e2e["local"], "global_solves": stats_e2e["global"],
                 "note": "bfFrameLoopStep with HOST (pinned) depth + colour pointers: the upload happens inside the call, as CUDAImageManager::process uploads on arrival; read back per step: the status block (pose of the frame), the SIFT pose and the match verdict"},
         "gpu_launches": int(launches), "roofline": roof, "tsdf_arithmetic": "fast",
+        "stages_ms_per_step": dict(stages, note="profiled pass (one extra host synchronisation per step, TSDF lanes off): device time line between stage boundaries, mean per step"),
         "clocks": summarize_clocks(clk_lines[clk_mark0:clk_mark1]), "clocks_profile_pass": summarize_clocks(clk_lines[clk_mark1:clk_mark2]),
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -549,7 +557,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true", help="diagnostic: leave the bundle-adjustment solves out (the JSON line is then NOT a bench value)")
     ap.add_argument("--workload", default="loop", choices=["loop", "ops"], help="loop: the whole frame loop (headline); ops: TSDF op replay + synthetic BA problems (round-1 bench, kept for A/B)")
-    ap.add_argument("--preroll", type=int, default=600, help="frames streamed through the loop before warm-up (state of a long stream)")
+    ap.add_argument("--cuda-profiler", action="store_true", help="bracket the timed pass with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
+    ap.add_argument("--preroll", type=int, default=250, help="frames streamed through the loop before warm-up (state of a long stream)")
     ap.add_argument("--trace", default=None, help="diagnostic: write the per-frame status of every step (pre-roll included) to this file")
     ap.add_argument("--stride", type=int, default=2, help="Lissajous path frames per step")
     args = ap.parse_args()

@@ -237,7 +237,23 @@ struct Loop {
     int* h_pin = nullptr;
     unsigned long long counters[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     BFFrameLoopStatus status;
+    // stage profile (bfFrameLoopSetProfiling): events at the stage boundaries of a step, elapsed times summed per stage
+    bool profile = false; cudaEvent_t stageEv[BF_FRAMELOOP_STAGES + 1] = {}; bool stageHit[BF_FRAMELOOP_STAGES + 1] = {}; double stageMs[BF_FRAMELOOP_STAGES] = {}; unsigned long long profiledSteps = 0;
 };
+// boundary k = end of stage k - 1 / start of stage k
+static void mark(Loop& L, int k) { if (L.profile && L.stageEv[k]) { cudaEventRecord(L.stageEv[k], stream()); L.stageHit[k] = true; } }
+static void stage_collect(Loop& L) {
+    if (!L.profile) return;
+    cudaStreamSynchronize(stream());
+    int prev = -1;
+    for (int k = 0; k <= BF_FRAMELOOP_STAGES; ++k) {
+        if (!L.stageHit[k]) continue;
+        if (prev >= 0) { float ms = 0.0f; if (cudaEventElapsedTime(&ms, L.stageEv[prev], L.stageEv[k]) == cudaSuccess) L.stageMs[k - 1] += ms; }   // a skipped stage's time belongs to the one that ran
+        prev = k;
+    }
+    for (int k = 0; k <= BF_FRAMELOOP_STAGES; ++k) L.stageHit[k] = false;
+    ++L.profiledSteps;
+}
 
 static int sync_stream(Loop& L) { ++L.counters[6]; BF_CHECK(cudaStreamSynchronize(stream())); return 0; }
 
@@ -453,13 +469,16 @@ static int process_input(Loop& L, unsigned curFrame) {
         fl_resample_intensity_kernel<<<grd, blk, 0, stream()>>>(L.d_intensity, P.siftWidth, P.siftHeight, reinterpret_cast<const uchar4*>(L.d_colorRaw), P.colorWidth, P.colorHeight);
         BF_CHECK(cudaGetLastError()); ++g_launchCount;
     }
+    mark(L, 1);
     // detectFeatures (FL/Bundler.cpp:91-101): keys of the new local image
     const unsigned li = loc.sm.numImages;
     FL_OK(bfSiftDetect(&L.detect, L.d_intensity, L.d_depthFilt, loc.sm.keysOf(li), loc.sm.descsOf(li), loc.sm.d_numKeys + li, nullptr));
     BF_CHECK(cudaMemcpyAsync(L.h_pin, loc.sm.d_numKeys + li, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    mark(L, 2);
     // storeCachedFrame
     FL_OK(loc.cache.storeFrame(L.d_depthRaw, L.d_colorRaw));
     FL_OK(sync_stream(L));
+    mark(L, 3);
     const int nk = std::min(L.h_pin[0], (int)P.maxNumKeysPerImage);
     loc.sm.addImage(nk);
     L.status.numKeyPoints = (unsigned)nk;
@@ -495,6 +514,7 @@ static int process_input(Loop& L, unsigned curFrame) {
     } else if (curFrame == 0) mat_identity(L.currIntegrate);
     if (isLastLocal) prepare_local_solve(L, curFrame, false);
     L.lastFrameProcessed = (int)curFrame;
+    mark(L, 4);
     return 0;
 }
 
@@ -834,12 +854,18 @@ BF_API void bfFrameLoopDestroy(BFFrameLoop* loop) {
 }
 
 static int step_common(Loop& L, bool gotFrame, unsigned curFrame, BFFrameLoopStatus* status) {
+    mark(L, 4);
     FL_OK(reconstruct(L, gotFrame, curFrame));
+    mark(L, 5);
     if (L.useSolve) {                                   // OnlineBundler::process (:410-416)
         FL_OK(optimize_local(L));
+        mark(L, 6);
         FL_OK(process_global(L));
+        mark(L, 7);
         FL_OK(optimize_global(L));
     }
+    mark(L, 8);
+    stage_collect(L);
     fill_status_tail(L);
     if (status) *status = L.status;
     return 0;
@@ -855,6 +881,7 @@ BF_API int bfFrameLoopStep(BFFrameLoop* loop, const float* depth, const uint8_t*
     L.status.frame = curFrame; L.status.localSolved = -1; L.status.lastMatchedFrame = -1;
     // CUDAImageManager::process (FL/CUDAImageManager.cpp:22-158): upload, erode + filter + resample into the frame store
     const size_t dB = sizeof(float) * (size_t)P.depthWidth * P.depthHeight, cB = (size_t)4 * P.colorWidth * P.colorHeight;
+    mark(L, 0);
     BF_CHECK(cudaMemcpyAsync(L.d_depthRaw, depth, dB, onHost ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream()));
     BF_CHECK(cudaMemcpyAsync(L.d_colorRaw, color, cB, onHost ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream()));
     FL_OK(bfIngestFrame(&L.ingest, L.d_depthRaw, L.d_colorRaw, L.d_frameDepth[curFrame], L.d_frameColor[curFrame]));
@@ -886,6 +913,22 @@ BF_API unsigned int bfFrameLoopGetTrajectory(BFFrameLoop* loop, float* h_out, un
 }
 BF_API const BFHashDataStruct* bfFrameLoopGetHashData(const BFFrameLoop* loop) { return loop ? &reinterpret_cast<const Loop*>(loop)->hd : nullptr; }
 BF_API const BFHashParams* bfFrameLoopGetHashParams(const BFFrameLoop* loop) { return loop ? &reinterpret_cast<const Loop*>(loop)->hp : nullptr; }
+BF_API int bfFrameLoopSetProfiling(BFFrameLoop* loop, int enable) {
+    if (!loop) return (int)cudaErrorInvalidValue;
+    Loop& L = *reinterpret_cast<Loop*>(loop);
+    if (enable) for (int k = 0; k <= BF_FRAMELOOP_STAGES; ++k) if (!L.stageEv[k]) BF_CHECK(cudaEventCreate(&L.stageEv[k]));
+    L.profile = enable != 0;
+    for (int k = 0; k < BF_FRAMELOOP_STAGES; ++k) L.stageMs[k] = 0.0;
+    for (int k = 0; k <= BF_FRAMELOOP_STAGES; ++k) L.stageHit[k] = false;
+    L.profiledSteps = 0;
+    return 0;
+}
+BF_API unsigned long long bfFrameLoopGetStageTimes(const BFFrameLoop* loop, double outMs[BF_FRAMELOOP_STAGES]) {
+    if (!loop) return 0;
+    const Loop& L = *reinterpret_cast<const Loop*>(loop);
+    for (int k = 0; k < BF_FRAMELOOP_STAGES; ++k) outMs[k] = L.stageMs[k];
+    return L.profiledSteps;
+}
 BF_API void bfFrameLoopGetCounters(const BFFrameLoop* loop, unsigned long long out[8]) {
     if (!loop) return;
     memcpy(out, reinterpret_cast<const Loop*>(loop)->counters, sizeof(unsigned long long) * 8);

@@ -29,6 +29,7 @@ struct SiftJobDev {
     int* rowResult; float* rowDist;    // row pass: outputs; column pass: inputs (indexed by image-1 feature)
     int* numMatches; float* outDist; uint2* outIdx;
     uint2 offset;
+    int* colResult; int* done;         // column pass: match of each image-2 feature (-1 none), CTAs of the job that have finished
 };
 
 // Winner among equal maxima, exactly as the reference's 32 strided lanes + fold-upper-half-into-lower tree pick it (see
@@ -172,15 +173,39 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
             if (!kColumnPass) {
                 job.rowResult[r] = res;                    // RowMatch_Kernel, ProgramCU.cu:1823-1829
                 job.rowDist[r] = dist;
-            } else if (res >= 0 && job.rowResult[res] == r) {            // ColMatch_Kernel, :1900-1915 (here A = image 2, r = its feature)
-                const int addr = atomicAdd(job.numMatches, 1);           // keeps counting past the cap, as the reference's
-                if (addr < BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW) {
-                    job.outIdx[addr] = make_uint2((unsigned)res + job.offset.x, (unsigned)r + job.offset.y);
-                    job.outDist[addr] = job.rowDist[res];
-                }
+            } else {                                                     // ColMatch_Kernel, :1900-1915 (here A = image 2, r = its feature)
+                job.colResult[r] = (res >= 0 && job.rowResult[res] == r) ? res : -1;
             }
         }
     }
+    if (!kColumnPass) return;
+    // The reference appends its matches with an atomicAdd: beyond the 128-slot cap the kept subset depends on the scheduling.  Here the job's last
+    // CTA to finish compacts the per-feature results in ascending image-2 feature: the first 128 are kept, the counter still holds the total.
+    __shared__ int sLast, sWarp[4];
+    __threadfence();
+    __syncthreads();
+    if (t == 0) sLast = (atomicAdd(job.done, 1) == (nA + SM_BM - 1) / SM_BM - 1) ? 1 : 0;
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    int base = 0;
+    for (int r0 = 0; r0 < nA; r0 += 128) {
+        const int r = r0 + (int)t;
+        const int res = (r < nA) ? __ldcg(&job.colResult[r]) : -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, res >= 0);
+        if (lane == 0) sWarp[warp] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (unsigned w = 0; w < warp; ++w) off += sWarp[w];
+        const int slot = off + __popc(bal & ((1u << lane) - 1u));
+        if (res >= 0 && slot < BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW) {
+            job.outIdx[slot] = make_uint2((unsigned)res + job.offset.x, (unsigned)r + job.offset.y);
+            job.outDist[slot] = job.rowDist[res];
+        }
+        base += sWarp[0] + sWarp[1] + sWarp[2] + sWarp[3];
+        __syncthreads();
+    }
+    if (t == 0) { *job.numMatches = base; *job.done = 0; }
 }
 
 // SortKeyPointMatchesCU_Kernel (SIFTImageManager.cu:59-145): one CTA per image pair, 128 slots, bitonic network in shared memory on
@@ -221,6 +246,8 @@ struct SiftWs {
     cudaEvent_t evCopied = nullptr;
     cudaEvent_t evDone = nullptr;                // the last batch's column pass has finished (the workspace is shared by every caller)
     int* rowResult = nullptr; float* rowDist = nullptr; size_t rowCap = 0;
+    int* colResult = nullptr; size_t colCap = 0;
+    int* done = nullptr;
 };
 static SiftWs g_sift;
 static std::mutex g_siftMutex;
@@ -232,18 +259,20 @@ using namespace bf;
 BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distmax, float ratiomax) {
     if (numJobs <= 0) return 0;
     std::lock_guard<std::mutex> lk(g_siftMutex);
-    size_t rows = 0;
+    size_t rows = 0, cols = 0;
     int maxN1 = 0, maxN2 = 0;
     for (int i = 0; i < numJobs; ++i) {
-        if (jobs[i].num1 > 0 && jobs[i].num2 > 0) { rows += (size_t)jobs[i].num1; maxN1 = jobs[i].num1 > maxN1 ? jobs[i].num1 : maxN1; maxN2 = jobs[i].num2 > maxN2 ? jobs[i].num2 : maxN2; }
+        if (jobs[i].num1 > 0 && jobs[i].num2 > 0) { rows += (size_t)jobs[i].num1; cols += (size_t)jobs[i].num2; maxN1 = jobs[i].num1 > maxN1 ? jobs[i].num1 : maxN1; maxN2 = jobs[i].num2 > maxN2 ? jobs[i].num2 : maxN2; }
         if (jobs[i].num1 >= (1 << 24) || jobs[i].num2 >= (1 << 24)) return (int)cudaErrorInvalidValue;       // index field of the packed key
     }
     cudaStream_t s = stream();
     if (!g_sift.evDone) BF_CHECK(cudaEventCreateWithFlags(&g_sift.evDone, cudaEventDisableTiming));
     BF_CHECK(cudaStreamWaitEvent(s, g_sift.evDone, 0));       // a previous batch (possibly on another stream) still owns rowResult / the job table
     if ((size_t)numJobs > g_sift.jobCap) {
-        if (g_sift.dJobs) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dJobs)); BF_CHECK(cudaFreeHost(g_sift.hJobs)); }
+        if (g_sift.dJobs) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dJobs)); BF_CHECK(cudaFreeHost(g_sift.hJobs)); BF_CHECK(cudaFree(g_sift.done)); }
         g_sift.jobCap = (size_t)numJobs * 2;
+        BF_CHECK(cudaMalloc(&g_sift.done, sizeof(int) * g_sift.jobCap));
+        BF_CHECK(cudaMemsetAsync(g_sift.done, 0, sizeof(int) * g_sift.jobCap, s));          // each job's last CTA leaves its counter at 0 again
         BF_CHECK(cudaMalloc(&g_sift.dJobs, sizeof(SiftJobDev) * 2 * g_sift.jobCap));      // [row-pass jobs | column-pass jobs]
         BF_CHECK(cudaMallocHost(&g_sift.hJobs, sizeof(SiftJobDev) * 2 * g_sift.jobCap));
         if (!g_sift.evCopied) BF_CHECK(cudaEventCreateWithFlags(&g_sift.evCopied, cudaEventDisableTiming));
@@ -256,8 +285,13 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
         BF_CHECK(cudaMalloc(&g_sift.rowResult, sizeof(int) * g_sift.rowCap));
         BF_CHECK(cudaMalloc(&g_sift.rowDist, sizeof(float) * g_sift.rowCap));
     }
+    if (cols > g_sift.colCap) {
+        if (g_sift.colResult) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.colResult)); }
+        g_sift.colCap = cols * 2;
+        BF_CHECK(cudaMalloc(&g_sift.colResult, sizeof(int) * g_sift.colCap));
+    }
     SiftJobDev* h = g_sift.hJobs;
-    size_t off = 0;
+    size_t off = 0, coff = 0;
     for (int i = 0; i < numJobs; ++i) {
         const BFSiftMatchJob& j = jobs[i];
         const bool live = j.num1 > 0 && j.num2 > 0;
@@ -266,10 +300,11 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
         r.rowResult = g_sift.rowResult + off; r.rowDist = g_sift.rowDist + off;
         r.numMatches = j.out.d_numMatches; r.outDist = j.out.d_distances; r.outIdx = reinterpret_cast<uint2*>(j.out.d_keyPointIndices);
         r.offset = make_uint2(j.keyPointOffset[0], j.keyPointOffset[1]);
+        r.colResult = g_sift.colResult + coff; r.done = g_sift.done + i;
         SiftJobDev c = r;                                   // column pass: image 2 owns the sweep, image 1 is swept
         c.desA = j.d_des2; c.nA = r.nB; c.desB = j.d_des1; c.nB = r.nA;
         h[i] = r; h[(size_t)numJobs + i] = c;
-        if (live) off += (size_t)j.num1;
+        if (live) { off += (size_t)j.num1; coff += (size_t)j.num2; }
     }
     BF_CHECK(cudaMemcpyAsync(g_sift.dJobs, h, sizeof(SiftJobDev) * 2 * (size_t)numJobs, cudaMemcpyHostToDevice, s));
     BF_CHECK(cudaEventRecord(g_sift.evCopied, s));
@@ -295,11 +330,11 @@ BF_API int bfSiftSortKeyPointMatches(unsigned int curFrame, unsigned int startFr
 
 BF_API size_t bfSiftWorkspaceBytes(void) {
     std::lock_guard<std::mutex> lk(g_siftMutex);
-    return sizeof(SiftJobDev) * 2 * g_sift.jobCap + (sizeof(int) + sizeof(float)) * g_sift.rowCap;
+    return sizeof(SiftJobDev) * 2 * g_sift.jobCap + (sizeof(int) + sizeof(float)) * g_sift.rowCap + sizeof(int) * (g_sift.colCap + g_sift.jobCap);
 }
 BF_API int bfSiftReleaseWorkspace(void) {
     std::lock_guard<std::mutex> lk(g_siftMutex);
-    cudaFree(g_sift.dJobs); cudaFree(g_sift.rowResult); cudaFree(g_sift.rowDist);
+    cudaFree(g_sift.dJobs); cudaFree(g_sift.rowResult); cudaFree(g_sift.rowDist); cudaFree(g_sift.colResult); cudaFree(g_sift.done);
     if (g_sift.hJobs) cudaFreeHost(g_sift.hJobs);
     if (g_sift.evCopied) cudaEventDestroy(g_sift.evCopied);
     if (g_sift.evDone) cudaEventDestroy(g_sift.evDone);

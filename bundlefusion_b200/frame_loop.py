@@ -73,6 +73,9 @@ def _bind(L):
     L.bfFrameLoopGetHashParams.restype = C.POINTER(BFHashParams)
     L.bfFrameLoopGetCounters.argtypes = [vp, C.c_ulonglong * 8]
     L.bfFrameLoopGetCounters.restype = None
+    L.bfFrameLoopSetProfiling.argtypes = [vp, C.c_int]
+    L.bfFrameLoopGetStageTimes.argtypes = [vp, C.c_double * 8]
+    L.bfFrameLoopGetStageTimes.restype = C.c_ulonglong
     L._frameloop_bound = True
     return L
 
@@ -121,6 +124,17 @@ class FrameLoop:
         c = (C.c_ulonglong * 8)()
         self.lib.bfFrameLoopGetCounters(self._h, c)
         return dict(zip(("frames", "integrations", "reintegrations", "local_solves", "global_solves", "global_pcg_iters", "host_syncs", "keyframes"), [int(x) for x in c]))
+
+    STAGES = ("upload_ingest", "sift_detect", "dense_cache_and_count", "match_filters_sift_pose", "tsdf_reintegrate_integrate", "local_solve", "fuse_keyframe_match", "global_solve_trajectory")
+
+    def set_profiling(self, enable: bool) -> None:
+        capi.check(self.lib.bfFrameLoopSetProfiling(self._h, 1 if enable else 0), "bfFrameLoopSetProfiling")
+
+    def stage_times(self) -> dict:
+        """mean milliseconds per step and stage (device time line) since set_profiling(True)"""
+        t = (C.c_double * 8)()
+        n = int(self.lib.bfFrameLoopGetStageTimes(self._h, t))
+        return {"steps": n, **{k: round(t[i] / max(1, n), 4) for i, k in enumerate(self.STAGES)}}
 
     def heap_free(self) -> int:
         out = C.c_uint(0)

@@ -116,6 +116,14 @@ const BFHashParams* bfFrameLoopGetHashParams(const BFFrameLoop* loop);
  * out[5] PCG iterations (global, last solve), out[6] host synchronisations, out[7] keyframes */
 void bfFrameLoopGetCounters(const BFFrameLoop* loop, unsigned long long out[8]);
 
+/* Stage profile (measurement only; adds one host synchronisation per step while on).  Stages of a step, in order:
+ *   0 upload + ingest      1 SIFT detection      2 dense cache (+ wait for the key-point count)      3 match + filters + SIFT pose
+ *   4 re-integration + GC + integration      5 local solve (+ verification)      6 fuse to keyframe + keyframe matching      7 global solve + trajectory update
+ * bfFrameLoopGetStageTimes: milliseconds on the device time line summed per stage since bfFrameLoopSetProfiling(loop, 1); returns the steps covered. */
+#define BF_FRAMELOOP_STAGES 8
+int bfFrameLoopSetProfiling(BFFrameLoop* loop, int enable);
+unsigned long long bfFrameLoopGetStageTimes(const BFFrameLoop* loop, double outMs[BF_FRAMELOOP_STAGES]);
+
 #ifdef __cplusplus
 }
 #endif

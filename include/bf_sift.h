@@ -53,6 +53,8 @@ typedef struct BFSiftMatchJob {
 } BFSiftMatchJob;
 
 /* Matches numJobs image pairs (jobs: HOST array) in two launches, asynchronously on the library stream (bfSetStream).
+ * Matches are stored in ascending image-2 feature; when a pair has more than 128 the first 128 in that order are kept and the counter holds the
+ * total (the reference appends with an atomicAdd: which 128 survive there depends on the scheduling -- this is one of its outcomes, always the same).
  * A job with num1 <= 0 or num2 <= 0 only zeroes its counter (SiftMatch.cpp:162-165).  Returns 0 or a cudaError_t. */
 int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distmax, float ratiomax);
 

@@ -1,7 +1,8 @@
 """GPU parity tests of the SIFT descriptor matcher (row a18) through the C-ABI against the CPU oracle.  The dot products are exact
 integers on both sides, so the SET of matches (and the counter) must be identical; the stored distance goes through acosf, whose
-CUDA and glibc implementations may differ in the last bit (tolerance 2e-7).  Append order is race-dependent (atomicAdd, as in the
-reference), so stored matches are compared as sets -- and in the over-cap case only the counter and membership are checked."""
+CUDA and glibc implementations may differ in the last bit (tolerance 2e-7).  The reference appends with an atomicAdd (order, and beyond the
+128-slot cap the kept subset, race-dependent); this library stores the matches in ascending image-2 feature and keeps the first 128 -- a
+deterministic member of the outcomes the reference can produce.  Stored matches are compared with the oracle's as sets."""
 import numpy as np
 import pytest
 
@@ -59,6 +60,10 @@ def test_cap_and_empty(cuda_device):
     gi, gd, gc = gpu_match(cuda_device, d, d.copy())
     assert gc == 400 and len(gi) == 128                                       # the counter keeps counting, 128 are stored
     assert np.all(gi[:, 0] == gi[:, 1]) and len(set(gi[:, 0].tolist())) == 128
+    assert gi[:, 1].tolist() == list(range(128)), "beyond the cap: the 128 matches with the lowest image-2 feature, in that order"
+    for _ in range(3):                                                         # and the same every time
+        g2 = gpu_match(cuda_device, d, d.copy())
+        assert np.array_equal(g2[0], gi) and np.array_equal(g2[1], gd) and g2[2] == gc
     assert gpu_match(cuda_device, d[:0], d)[2] == 0 and gpu_match(cuda_device, d, d[:0])[2] == 0
     z = np.zeros((10, 128), np.uint8)
     assert gpu_match(cuda_device, z, d[:10])[2] == 0
