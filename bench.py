@@ -363,6 +363,8 @@ def run_loop(args):
     clk_lines, stop_evt = [], threading.Event()
     th = threading.Thread(target=clocks_sampler, args=(stop_evt, clk_lines, local), daemon=True); th.start()
     loop = FrameLoop(P, dev)
+    overlap = os.environ.get("BF_LOOP_OVERLAP", "1") != "0"
+    loop.set_overlap(overlap)
     # frame bank on the device, generated in slices (input generation, never timed); the stream advances 2 frames of the Lissajous path per step
     depth = torch.empty(total, H, W, dtype=torch.float32, device=dev); color = torch.empty(total, H, W, 4, dtype=torch.uint8, device=dev)
     for s0 in range(0, total, 64):
@@ -402,6 +404,7 @@ def run_loop(args):
             st = loop.step(h_depth[k], h_color[k]) if e2e else loop.step(depth[f0 + k], color[f0 + k])
             if not profile:
                 note(st)
+        loop.join()                                        # the timed region covers the reconstruction stream's work of its last frame
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
@@ -478,12 +481,103 @@ def run_loop(args):
                 "frames_with_pose": stats_e2e["valid"], "local_solves": stats_e2e["local"], "global_solves": stats_e2e["global"],
                 "note": "bfFrameLoopStep with HOST (pinned) depth + colour pointers: the upload happens inside the call, as CUDAImageManager::process uploads on arrival; read back per step: the status block (pose of the frame), the SIFT pose and the match verdict"},
         "gpu_launches": int(launches), "roofline": roof, "tsdf_arithmetic": "fast",
+        "streams": "two (bundling on the library stream, reconstruction on the loop's second stream; events keep the single-threaded order's dependencies)" if overlap else "one",
         "stages_ms_per_step": dict(stages, note="profiled pass (one extra host synchronisation per step, TSDF lanes off): device time line between stage boundaries, mean per step"),
         "clocks": summarize_clocks(clk_lines[clk_mark0:clk_mark1]), "clocks_profile_pass": summarize_clocks(clk_lines[clk_mark1:clk_mark2]),
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_arm(1, 0, quiet=True, n_reint=2)
     print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+# ------------------------------------------------------------------------------------------------------------------------
+def run_sweep(args):
+    """configs[3] of BASELINE.json: integrate / de-integrate throughput against the number of active voxels, the voxel hash sharded over the ranks by block
+    owner (each rank allocates and fuses the blocks it owns; the frame and the pose pair come from rank 0 over NCCL every step).  One re-integration
+    (de-integrate at the old pose + integrate at the new one, fused pass) per step.  Strong scaling: the same frames and voxel sizes at every N."""
+    import torch
+    import torch.distributed as dist
+
+    from bundlefusion_b200 import _capi as capi
+    from bundlefusion_b200 import synth_gpu
+    from bundlefusion_b200.scene_rep import CUDASceneRepHashSDF, camera_params, default_hash_params
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = capi.lib()
+    cam = camera_params(W, H)
+    K, Wm, B = args.steps, args.warmup, 24
+    idx = [8 * i for i in range(B)]
+    depth, color, poses = synth_gpu.make_frames(idx, W, H, device=str(dev))           # the same bank on every rank (deterministic); the timed steps use rank 0's copy
+    rng = np.random.Generator(np.random.MT19937(5))
+    rows = []
+    for vs in (0.04, 0.02, 0.01, 0.006, 0.004):
+        hp = default_hash_params(num_buckets=4_000_000, num_sdf_blocks=3_000_000, voxel_size=vs)
+        if world > 1:
+            hp.m_dummy = (world << 32) | rank
+        scene = CUDASceneRepHashSDF(hp, dev)
+        cur = [np.array(p, np.float32) for p in poses]
+        for i in range(B):
+            scene.integrate(cur[i], depth[i], color[i], cam)
+        slot_d = torch.empty_like(depth[0]); slot_c = torch.empty_like(color[0]); pose_t = torch.zeros(32, device=dev)
+        deltas = []
+        for k in range(Wm + K):
+            d = np.eye(4, dtype=np.float32); d[:3, 3] = rng.standard_normal(3).astype(np.float32) * 0.004
+            deltas.append(d)
+
+        def step(k):
+            f = k % B
+            new = (deltas[k] @ cur[f]).astype(np.float32)
+            if world > 1:                                   # NCCL pose + frame broadcast from rank 0 (BASELINE configs[3])
+                if rank == 0:
+                    slot_d.copy_(depth[f]); slot_c.copy_(color[f]); pose_t.copy_(torch.from_numpy(np.concatenate([cur[f].reshape(-1), new.reshape(-1)])).to(dev))
+                dist.broadcast(slot_d, 0); dist.broadcast(slot_c, 0); dist.broadcast(pose_t, 0)
+                pp = pose_t.cpu().numpy(); old_p, new_p = pp[:16].reshape(4, 4), pp[16:].reshape(4, 4)
+                scene.runOps([(1, 0, old_p), (0, 0, new_p)], [slot_d], [slot_c], cam)
+            else:
+                scene.runOps([(1, f, cur[f]), (0, f, new)], [depth[i] for i in range(B)], [color[i] for i in range(B)], cam)
+            cur[f] = new
+
+        for k in range(Wm):
+            step(k)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        L.bfTsdfSetProfiling(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(Wm, Wm + K):
+            step(k)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        prof = (ctypes.c_ulonglong * 16)()
+        hd = scene.getHashData()
+        capi.check(L.bfTsdfGetProfileEx(ctypes.byref(hd), prof), "bfTsdfGetProfileEx")
+        L.bfTsdfSetProfiling(0)
+        t = torch.tensor([ms, float(prof[3]), float(prof[4]), float(prof[2]) / max(1, int(prof[1]))], device=dev, dtype=torch.float64)
+        if world > 1:
+            mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms, U, E, st_ns = float(mx[0]), float(sm[1]), float(sm[2]), float(mx[3])
+        else:
+            ms, U, E, st_ns = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        occupied = scene.getNumOccupiedBlocks()
+        rows.append({"voxel_m": vs, "active_voxels_per_op_M": round(512.0 * E / (2 * K) / 1e6, 2), "ms_per_reintegration": round(ms / K, 4),
+                     "mvoxels_per_s": round(512.0 * E / (ms * 1e-3) / 1e6, 1), "updates_per_s_M": round(U / (ms * 1e-3) / 1e6, 1),
+                     "stencil_us_max_rank": round(st_ns / 1e3, 2), "occupied_blocks_this_rank": int(occupied)})
+        scene.close()
+        del scene
+        torch.cuda.empty_cache()
+    if rank == 0:
+        print(json.dumps({"metric": "Mvoxels/s, TSDF de-integrate + integrate (BASELINE configs[3] sweep)", "unit": "Mvoxels/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                          "value": rows[-1]["mvoxels_per_s"], "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "f32",
+                          "config": {"workload": "one re-integration per step of a 24-frame bank at voxel sizes 4 cm ... 4 mm; Mvoxels = 512 x in-frustum blocks (both ops), summed over the ranks; time = max over ranks",
+                                     "parallelism": "single GPU" if world == 1 else f"voxel hash sharded over {world} GPUs by block owner; frame + pose pair broadcast from rank 0 (NCCL) every step"},
+                          "sweep": rows}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -556,7 +650,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true", help="diagnostic: leave the bundle-adjustment solves out (the JSON line is then NOT a bench value)")
-    ap.add_argument("--workload", default="loop", choices=["loop", "ops"], help="loop: the whole frame loop (headline); ops: TSDF op replay + synthetic BA problems (round-1 bench, kept for A/B)")
+    ap.add_argument("--workload", default="loop", choices=["loop", "ops", "sweep"], help="loop: the whole frame loop (headline); ops: TSDF op replay + synthetic BA problems (round-1 bench, kept for A/B)")
     ap.add_argument("--cuda-profiler", action="store_true", help="bracket the timed pass with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     ap.add_argument("--preroll", type=int, default=250, help="frames streamed through the loop before warm-up (state of a long stream)")
     ap.add_argument("--trace", default=None, help="diagnostic: write the per-frame status of every step (pre-roll included) to this file")
@@ -568,6 +662,8 @@ def main():
         run_reference(args)
     elif args.workload == "ops":
         run_ours(args)
+    elif args.workload == "sweep":
+        run_sweep(args)
     else:
         run_loop(args)
 

@@ -237,6 +237,9 @@ struct Loop {
     int* h_pin = nullptr;
     unsigned long long counters[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     BFFrameLoopStatus status;
+    // reconstruction stream: the TSDF work of frame f runs beside process() of frame f and processInput() of frame f + 1, as the reference's
+    // reconstruction and bundling threads do; the data dependencies of the single-threaded order are kept by events
+    cudaStream_t tsdfStream = nullptr; cudaEvent_t evMain = nullptr, evTsdf = nullptr; bool overlap = false, tsdfPending = false;
     // stage profile (bfFrameLoopSetProfiling): events at the stage boundaries of a step, elapsed times summed per stage
     bool profile = false; cudaEvent_t stageEv[BF_FRAMELOOP_STAGES + 1] = {}; bool stageHit[BF_FRAMELOOP_STAGES + 1] = {}; double stageMs[BF_FRAMELOOP_STAGES] = {}; unsigned long long profiledSteps = 0;
 };
@@ -701,8 +704,20 @@ static int reconstruct(Loop& L, bool gotFrame, unsigned curFrame) {
             memcpy(L.status.transform, ninf, 64);
         }
     }
-    if (P.reconstructionEnabled)
-        FL_OK(bfTsdfRunOps(&L.hd, &L.hp, &L.cam, ops.data(), (int)ops.size(), L.depthPtrs.data(), L.colorPtrs.data()));
+    if (P.reconstructionEnabled) {
+        // inputs of this call that live on the main stream: the frame store (ingest of this frame) -- the poses and the op list are host data
+        const bool side = L.overlap && !L.profile && L.tsdfStream;
+        cudaStream_t mainStream = stream();
+        if (side) { BF_CHECK(cudaEventRecord(L.evMain, mainStream)); BF_CHECK(cudaStreamWaitEvent(L.tsdfStream, L.evMain, 0)); bfSetStream(L.tsdfStream); }
+        const int rc = bfTsdfRunOps(&L.hd, &L.hp, &L.cam, ops.data(), (int)ops.size(), L.depthPtrs.data(), L.colorPtrs.data());
+        if (side) { cudaEventRecord(L.evTsdf, L.tsdfStream); L.tsdfPending = true; bfSetStream(mainStream); }
+        if (rc) return rc;
+    }
+    return 0;
+}
+// the main stream waits for the reconstruction stream (asynchronously): before anything on it reads the voxel hash, and at the end of a timed region
+static int join_tsdf(Loop& L) {
+    if (L.tsdfPending) { BF_CHECK(cudaStreamWaitEvent(stream(), L.evTsdf, 0)); L.tsdfPending = false; }
     return 0;
 }
 
@@ -845,8 +860,12 @@ BF_API int bfFrameLoopCreate(const BFFrameLoopParams* params, BFFrameLoop** out)
 BF_API void bfFrameLoopDestroy(BFFrameLoop* loop) {
     if (!loop) return;
     Loop* L = reinterpret_cast<Loop*>(loop);
+    if (L->tsdfStream) cudaStreamSynchronize(L->tsdfStream);
     cudaStreamSynchronize(stream());
     bfTsdfReleaseAux(&L->hd);
+    if (L->tsdfStream) cudaStreamDestroy(L->tsdfStream);
+    if (L->evMain) cudaEventDestroy(L->evMain);
+    if (L->evTsdf) cudaEventDestroy(L->evTsdf);
     bfSolverReleaseWorkspace(&L->local.solver.st); bfSolverReleaseWorkspace(&L->optLocal.solver.st); bfSolverReleaseWorkspace(&L->global.solver.st);
     if (L->tm) bfTrajectoryDestroy(L->tm);
     if (L->h_pin) cudaFreeHost(L->h_pin);
@@ -911,7 +930,27 @@ BF_API unsigned int bfFrameLoopGetTrajectory(BFFrameLoop* loop, float* h_out, un
     memcpy(h_out, all.data(), (size_t)m * 64);
     return m;
 }
-BF_API const BFHashDataStruct* bfFrameLoopGetHashData(const BFFrameLoop* loop) { return loop ? &reinterpret_cast<const Loop*>(loop)->hd : nullptr; }
+BF_API const BFHashDataStruct* bfFrameLoopGetHashData(const BFFrameLoop* loop) {
+    if (!loop) return nullptr;
+    join_tsdf(*const_cast<Loop*>(reinterpret_cast<const Loop*>(loop)));          // work the caller queues on the library stream after this call sees the fused model
+    return &reinterpret_cast<const Loop*>(loop)->hd;
+}
+BF_API int bfFrameLoopJoin(BFFrameLoop* loop) { return loop ? join_tsdf(*reinterpret_cast<Loop*>(loop)) : (int)cudaErrorInvalidValue; }
+BF_API int bfFrameLoopSetOverlap(BFFrameLoop* loop, int enable) {
+    if (!loop) return (int)cudaErrorInvalidValue;
+    Loop& L = *reinterpret_cast<Loop*>(loop);
+    const int prev = L.overlap ? 1 : 0;
+    if (enable && !L.tsdfStream) {
+        int lo = 0, hi = 0;
+        BF_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        BF_CHECK(cudaStreamCreateWithPriority(&L.tsdfStream, cudaStreamNonBlocking, lo));          // lowest priority: the bundling chain is the latency-critical one
+        BF_CHECK(cudaEventCreateWithFlags(&L.evMain, cudaEventDisableTiming));
+        BF_CHECK(cudaEventCreateWithFlags(&L.evTsdf, cudaEventDisableTiming));
+    }
+    if (!enable) { const int rc = join_tsdf(L); if (rc) return rc; }
+    L.overlap = enable != 0;
+    return prev;
+}
 BF_API const BFHashParams* bfFrameLoopGetHashParams(const BFFrameLoop* loop) { return loop ? &reinterpret_cast<const Loop*>(loop)->hp : nullptr; }
 BF_API int bfFrameLoopSetProfiling(BFFrameLoop* loop, int enable) {
     if (!loop) return (int)cudaErrorInvalidValue;

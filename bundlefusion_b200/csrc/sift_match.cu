@@ -60,6 +60,51 @@ __device__ __forceinline__ void top2_merge(Top2& s, int ov1, unsigned ok1, int o
 }
 __device__ __forceinline__ float dist_of(int dot) { return acosf(fminf((float)dot * 0.000003814697265625f, 1.0f)); }
 
+// the end of a feature's sweep: distance / ratio tests, then the row result (RowMatch_Kernel, ProgramCU.cu:1823-1829) or the mutual-best check of
+// the column pass (ColMatch_Kernel, :1900-1915; here A = image 2, r = its feature)
+template <bool kColumnPass>
+__device__ __forceinline__ void finish_feature(const SiftJobDev& job, int r, const Top2& st, float distmax, float ratiomax) {
+    if (r >= job.nA) return;
+    const int vmax = st.v1, vnxt = st.v2;
+    const int idx = (vmax > 0) ? (int)(st.k1 & 0x00FFFFFFu) : -1;
+    const float dist = dist_of(vmax), distn = dist_of(vnxt);
+    const int res = (dist < distmax && dist < distn * ratiomax) ? idx : -1;
+    if (!kColumnPass) { job.rowResult[r] = res; job.rowDist[r] = dist; }
+    else job.colResult[r] = (res >= 0 && job.rowResult[res] == r) ? res : -1;
+}
+// The reference appends its matches with an atomicAdd: beyond the 128-slot cap the kept subset depends on the scheduling.  Here the job's last
+// CTA to finish compacts the per-feature results in ascending image-2 feature: the first 128 are kept, the counter still holds the total.
+// 128 threads; ctasOfJob: CTAs of this launch that work on the job.
+__device__ __forceinline__ void compact_job(const SiftJobDev& job, int ctasOfJob) {
+    __shared__ int sLast, sWarp[4];
+    const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int nA = job.nA;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) sLast = (atomicAdd(job.done, 1) == ctasOfJob - 1) ? 1 : 0;
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    int base = 0;
+    for (int r0 = 0; r0 < nA; r0 += 128) {
+        const int r = r0 + (int)t;
+        const int res = (r < nA) ? __ldcg(&job.colResult[r]) : -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, res >= 0);
+        if (lane == 0) sWarp[warp] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (unsigned w = 0; w < warp; ++w) off += sWarp[w];
+        const int slot = off + __popc(bal & ((1u << lane) - 1u));
+        if (res >= 0 && slot < BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW) {
+            job.outIdx[slot] = make_uint2((unsigned)res + job.offset.x, (unsigned)r + job.offset.y);
+            job.outDist[slot] = job.rowDist[res];
+        }
+        base += sWarp[0] + sWarp[1] + sWarp[2] + sWarp[3];
+        __syncthreads();
+    }
+    if (t == 0) { *job.numMatches = base; *job.done = 0; }
+}
+
 #define SM_BM 64              // features of A per CTA (4 warps x 16)
 #define SM_BN 64              // features of B per sweep step
 #define SM_PITCH 144          // bytes per staged descriptor row: 128 + 16 -> the 8 rows a fragment load touches hit 32 distinct banks
@@ -163,49 +208,126 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
     }
     if (q == 0) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int r = row0 + (int)warp * 16 + (int)g + 8 * h;
-            if (r >= nA) continue;
-            const int vmax = st[h].v1, vnxt = st[h].v2;
-            const int idx = (vmax > 0) ? (int)(st[h].k1 & 0x00FFFFFFu) : -1;
-            const float dist = dist_of(vmax), distn = dist_of(vnxt);
-            const int res = (dist < distmax && dist < distn * ratiomax) ? idx : -1;
-            if (!kColumnPass) {
-                job.rowResult[r] = res;                    // RowMatch_Kernel, ProgramCU.cu:1823-1829
-                job.rowDist[r] = dist;
-            } else {                                                     // ColMatch_Kernel, :1900-1915 (here A = image 2, r = its feature)
-                job.colResult[r] = (res >= 0 && job.rowResult[res] == r) ? res : -1;
+        for (int h = 0; h < 2; ++h) finish_feature<kColumnPass>(job, row0 + (int)warp * 16 + (int)g + 8 * h, st[h], distmax, ratiomax);
+    }
+    if (kColumnPass) compact_job(job, (nA + SM_BM - 1) / SM_BM);
+}
+
+// ---- tcgen05 version of the sweep -------------------------------------------------------------------------------------------------------------
+// One CTA = 128 features of A (one per thread = one TMEM lane) against all of B in tiles of 128: the tile's 128 x 128 x 128 u8 x u8 -> s32 products are
+// four tcgen05.mma (kind::i8, M 128, N 128, K 32) issued by one thread, operands in shared memory in the canonical K-major 128-byte-swizzle layout
+// (a descriptor row is exactly one 128-byte swizzle row), accumulators in tensor memory, two accumulator buffers so that the products of tile j + 1
+// run while tile j is read back (tcgen05.ld, 32 lanes x 32 columns per instruction: a thread receives ITS feature's 32 products) and folded into the
+// running best / second best.  No cross-lane merge at the end: a feature lives in one thread.
+#define TC_BM 128
+#define TC_BN 128
+#define TC_TILE_BYTES (128 * 128)
+#define TC_SMEM_BYTES (3 * TC_TILE_BYTES + 1024 + 60 * 1024)      // A, two B buffers, alignment slack; padded so that at most two CTAs (2 x 256 TMEM columns) share an SM
+#define TC_IDESC 0x08200020u        // UMMA instruction descriptor: D s32 (2 << 4), A / B unsigned 8-bit K-major, N 128 (16 << 17), M 128 (8 << 24)
+
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {            // K-major, SWIZZLE_128B: LBO field 1, SBO 1024 B (8 rows), version 1
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (unsigned spin = 0; !ok; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 28)) __trap();                     // a lost completion must not hang the device
+    }
+}
+// 128 rows x 128 bytes, global (row-major) -> shared, 16-byte chunk c of row r at (r / 8) * 1024 + (r % 8) * 128 + ((c ^ (r % 8)) * 16); rows >= n are zero
+__device__ __forceinline__ void tc_fill_tile(unsigned char* dst, const uint8_t* __restrict__ src, int row0, int n, unsigned t) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned v = t + 128u * k, r = v >> 3, c = v & 7u;
+        const uint4 x = (row0 + (int)r < n) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)(row0 + r) * 128) + c) : make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7u) * 128 + ((c ^ (r & 7u)) << 4)) = x;
+    }
+}
+__device__ __forceinline__ void tc_issue_tile(uint32_t tmemD, uint32_t sA, uint32_t sB) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                              // K = 128 bytes = 4 x 32: the descriptors advance 32 bytes inside the swizzled row
+        const uint64_t da = umma_desc_sw128(sA + 32u * k), db = umma_desc_sw128(sB + 32u * k);
+        const uint32_t accum = k ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                     :: "r"(tmemD), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accum), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+    }
+}
+template <bool kColumnPass>
+__global__ void __launch_bounds__(128)
+sift_best_tc_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratiomax) {
+    const SiftJobDev job = jobs[blockIdx.y];
+    const int nA = job.nA, nB = job.nB;
+    const int row0 = blockIdx.x * TC_BM;
+    if (!kColumnPass && blockIdx.x == 0 && threadIdx.x == 0) *job.numMatches = 0;       // SiftMatch.cpp:163 / ProgramCU.cu:1928
+    if (nA <= 0 || nB <= 0 || row0 >= nA) return;
+
+    extern __shared__ unsigned char tcSmemRaw[];
+    __shared__ __align__(8) unsigned long long sBar[2];
+    __shared__ uint32_t sTmem;
+    unsigned char* const smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tcSmemRaw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* const sA = smem; unsigned char* const sB0 = smem + TC_TILE_BYTES; unsigned char* const sB1 = smem + 2 * TC_TILE_BYTES;
+    const unsigned t = threadIdx.x, warp = t >> 5;
+    const uint32_t bar0 = smem_u32(&sBar[0]), bar1 = smem_u32(&sBar[1]);
+
+    tc_fill_tile(sA, job.desA, row0, nA, t);
+    tc_fill_tile(sB0, job.desB, 0, nB, t);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {                                          // 2 accumulator buffers x 128 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(&sTmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // the tiles were written with ordinary stores; the tensor core reads them through the async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = sTmem;
+    const int T = (nB + TC_BN - 1) / TC_BN;
+    if (t == 0) {
+        tc_issue_tile(tmem, smem_u32(sA), smem_u32(sB0));
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar0) : "memory");
+    }
+    Top2 st = { 0, 0xFFFFFFFFu, 0 };       // a dot product must be > 0 to be a candidate (the reference starts from max = 0 with a strict '>')
+    for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) {
+            // buffer (j + 1) & 1 of B was read by the products of tile j - 1 and accumulator buffer (j + 1) & 1 by its read-back: both finished in iteration j - 1
+            unsigned char* const sBn = ((j + 1) & 1) ? sB1 : sB0;
+            tc_fill_tile(sBn, job.desB, (j + 1) * TC_BN, nB, t);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (t == 0) {
+                tc_issue_tile(tmem + (uint32_t)(((j + 1) & 1) * TC_BN), smem_u32(sA), smem_u32(sBn));
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(((j + 1) & 1) ? bar1 : bar0) : "memory");
             }
         }
-    }
-    if (!kColumnPass) return;
-    // The reference appends its matches with an atomicAdd: beyond the 128-slot cap the kept subset depends on the scheduling.  Here the job's last
-    // CTA to finish compacts the per-feature results in ascending image-2 feature: the first 128 are kept, the counter still holds the total.
-    __shared__ int sLast, sWarp[4];
-    __threadfence();
-    __syncthreads();
-    if (t == 0) sLast = (atomicAdd(job.done, 1) == (nA + SM_BM - 1) / SM_BM - 1) ? 1 : 0;
-    __syncthreads();
-    if (!sLast) return;
-    __threadfence();
-    int base = 0;
-    for (int r0 = 0; r0 < nA; r0 += 128) {
-        const int r = r0 + (int)t;
-        const int res = (r < nA) ? __ldcg(&job.colResult[r]) : -1;
-        const unsigned bal = __ballot_sync(0xffffffffu, res >= 0);
-        if (lane == 0) sWarp[warp] = __popc(bal);
-        __syncthreads();
-        int off = base;
-        for (unsigned w = 0; w < warp; ++w) off += sWarp[w];
-        const int slot = off + __popc(bal & ((1u << lane) - 1u));
-        if (res >= 0 && slot < BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW) {
-            job.outIdx[slot] = make_uint2((unsigned)res + job.offset.x, (unsigned)r + job.offset.y);
-            job.outDist[slot] = job.rowDist[res];
+        mbar_wait((j & 1) ? bar1 : bar0, (uint32_t)((j >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem + ((warp * 32u) << 16) + (uint32_t)((j & 1) * TC_BN);       // this warp's 32 lanes, this tile's columns
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            uint32_t v[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                           "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                           "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                         : "r"(taddr + (uint32_t)c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int col0 = j * TC_BN + c0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) top2_update<kColumnPass>(st, (int)v[e], (unsigned)(col0 + e));      // padded columns give 0: never a candidate
         }
-        base += sWarp[0] + sWarp[1] + sWarp[2] + sWarp[3];
-        __syncthreads();
     }
-    if (t == 0) { *job.numMatches = base; *job.done = 0; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+    finish_feature<kColumnPass>(job, row0 + (int)t, st, distmax, ratiomax);
+    if (kColumnPass) compact_job(job, (nA + TC_BM - 1) / TC_BM);
 }
 
 // SortKeyPointMatchesCU_Kernel (SIFTImageManager.cu:59-145): one CTA per image pair, 128 slots, bitonic network in shared memory on
@@ -308,12 +430,29 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
     }
     BF_CHECK(cudaMemcpyAsync(g_sift.dJobs, h, sizeof(SiftJobDev) * 2 * (size_t)numJobs, cudaMemcpyHostToDevice, s));
     BF_CHECK(cudaEventRecord(g_sift.evCopied, s));
-    const int gx1 = maxN1 > 0 ? (maxN1 + SM_BM - 1) / SM_BM : 1, gx2 = maxN2 > 0 ? (maxN2 + SM_BM - 1) / SM_BM : 1;
     g_launchCount += 2;
-    sift_best_kernel<false><<<dim3(gx1, numJobs), 128, 0, s>>>(g_sift.dJobs, distmax, ratiomax);
-    BF_CHECK(cudaGetLastError());
-    sift_best_kernel<true><<<dim3(gx2, numJobs), 128, 0, s>>>(g_sift.dJobs + numJobs, distmax, ratiomax);
-    BF_CHECK(cudaGetLastError());
+    static int path = -1;               // BF_SIFT_MATCH=mma selects the warp-level mma.sync sweep (kept for A / B measurements); default: tcgen05
+    if (path < 0) {
+        const char* e = getenv("BF_SIFT_MATCH");
+        path = (e && e[0] == 'm') ? 0 : 1;
+        if (path == 1) {
+            BF_CHECK(cudaFuncSetAttribute(sift_best_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            BF_CHECK(cudaFuncSetAttribute(sift_best_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        }
+    }
+    if (path == 1) {
+        const int gx1 = maxN1 > 0 ? (maxN1 + TC_BM - 1) / TC_BM : 1, gx2 = maxN2 > 0 ? (maxN2 + TC_BM - 1) / TC_BM : 1;
+        sift_best_tc_kernel<false><<<dim3(gx1, numJobs), 128, TC_SMEM_BYTES, s>>>(g_sift.dJobs, distmax, ratiomax);
+        BF_CHECK(cudaGetLastError());
+        sift_best_tc_kernel<true><<<dim3(gx2, numJobs), 128, TC_SMEM_BYTES, s>>>(g_sift.dJobs + numJobs, distmax, ratiomax);
+        BF_CHECK(cudaGetLastError());
+    } else {
+        const int gx1 = maxN1 > 0 ? (maxN1 + SM_BM - 1) / SM_BM : 1, gx2 = maxN2 > 0 ? (maxN2 + SM_BM - 1) / SM_BM : 1;
+        sift_best_kernel<false><<<dim3(gx1, numJobs), 128, 0, s>>>(g_sift.dJobs, distmax, ratiomax);
+        BF_CHECK(cudaGetLastError());
+        sift_best_kernel<true><<<dim3(gx2, numJobs), 128, 0, s>>>(g_sift.dJobs + numJobs, distmax, ratiomax);
+        BF_CHECK(cudaGetLastError());
+    }
     BF_CHECK(cudaEventRecord(g_sift.evDone, s));
     return 0;
 }

@@ -73,6 +73,8 @@ def _bind(L):
     L.bfFrameLoopGetHashParams.restype = C.POINTER(BFHashParams)
     L.bfFrameLoopGetCounters.argtypes = [vp, C.c_ulonglong * 8]
     L.bfFrameLoopGetCounters.restype = None
+    L.bfFrameLoopSetOverlap.argtypes = [vp, C.c_int]
+    L.bfFrameLoopJoin.argtypes = [vp]
     L.bfFrameLoopSetProfiling.argtypes = [vp, C.c_int]
     L.bfFrameLoopGetStageTimes.argtypes = [vp, C.c_double * 8]
     L.bfFrameLoopGetStageTimes.restype = C.c_ulonglong
@@ -126,6 +128,14 @@ class FrameLoop:
         return dict(zip(("frames", "integrations", "reintegrations", "local_solves", "global_solves", "global_pcg_iters", "host_syncs", "keyframes"), [int(x) for x in c]))
 
     STAGES = ("upload_ingest", "sift_detect", "dense_cache_and_count", "match_filters_sift_pose", "tsdf_reintegrate_integrate", "local_solve", "fuse_keyframe_match", "global_solve_trajectory")
+
+    def set_overlap(self, enable: bool) -> bool:
+        """TSDF work on the loop's second stream (the reference's reconstruction thread); returns the previous setting"""
+        return bool(self.lib.bfFrameLoopSetOverlap(self._h, 1 if enable else 0))
+
+    def join(self) -> None:
+        self._bind_stream()
+        capi.check(self.lib.bfFrameLoopJoin(self._h), "bfFrameLoopJoin")
 
     def set_profiling(self, enable: bool) -> None:
         capi.check(self.lib.bfFrameLoopSetProfiling(self._h, 1 if enable else 0), "bfFrameLoopSetProfiling")

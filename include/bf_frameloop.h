@@ -116,6 +116,14 @@ const BFHashParams* bfFrameLoopGetHashParams(const BFFrameLoop* loop);
  * out[5] PCG iterations (global, last solve), out[6] host synchronisations, out[7] keyframes */
 void bfFrameLoopGetCounters(const BFFrameLoop* loop, unsigned long long out[8]);
 
+/* Two streams: with overlap on, the re-integration + integration of frame f are queued on a second, lower-priority stream of the loop and run beside
+ * the solves of frame f and the feature work of frame f + 1 -- what the reference's reconstruction and bundling threads do -- with the data
+ * dependencies of the single-threaded order kept by events (same results).  Off by default (everything on the library stream).
+ * bfFrameLoopJoin makes the library stream wait (asynchronously) for the reconstruction stream: call it before recording an event that should
+ * cover the fused model, or before reading the voxel hash on the library stream (bfFrameLoopGetHashData does it itself).  Returns the previous setting. */
+int bfFrameLoopSetOverlap(BFFrameLoop* loop, int enable);
+int bfFrameLoopJoin(BFFrameLoop* loop);
+
 /* Stage profile (measurement only; adds one host synchronisation per step while on).  Stages of a step, in order:
  *   0 upload + ingest      1 SIFT detection      2 dense cache (+ wait for the key-point count)      3 match + filters + SIFT pose
  *   4 re-integration + GC + integration      5 local solve (+ verification)      6 fuse to keyframe + keyframe matching      7 global solve + trajectory update

@@ -79,3 +79,32 @@ def test_frame_loop_loses_and_flags_a_frame_without_texture(cuda_device):
             assert st["validTransform"] == 1
     assert loop.counters()["integrations"] == 3
     loop.close()
+
+
+def test_two_stream_loop_equals_single_stream(cuda_device):
+    """bfFrameLoopSetOverlap: the reconstruction work on the loop's second stream changes when kernels run, not what they compute -- statuses,
+    trajectory and the fused model (canonical voxel words) are those of the single-stream loop."""
+    import torch
+    from bundlefusion_b200 import _capi as capi
+    from oracle import oracle as orc
+    frames = [synth.make_frame(2 * i, W, H, texture="rich") for i in range(25)]
+    out = []
+    for overlap in (False, True):
+        p = default_params(W, H)
+        p.maxNumImages = 8; p.maxNumFrames = 40
+        p.hash.m_hashNumBuckets = 100003; p.hash.m_numSDFBlocks = 90000
+        loop = FrameLoop(p, cuda_device)
+        loop.set_overlap(overlap)
+        sts = [loop.step(torch.from_numpy(d).to(cuda_device), torch.from_numpy(c).to(cuda_device)).as_dict() for d, c, T in frames]
+        loop.join()
+        torch.cuda.synchronize()
+        traj = loop.trajectory(25)
+        free = loop.heap_free()
+        out.append((sts, traj, free, loop.counters()))
+        loop.close()
+    (s0, t0, f0, c0), (s1, t1, f1, c1) = out
+    assert f0 == f1 and c0["reintegrations"] == c1["reintegrations"] > 0 and c0["integrations"] == c1["integrations"]
+    for a, b in zip(s0, s1):
+        assert a["validTransform"] == b["validTransform"] and a["numReintegrated"] == b["numReintegrated"] and a["localSolved"] == b["localSolved"]
+        assert np.array_equal(a["transform"], b["transform"], equal_nan=True)
+    assert np.array_equal(t0, t1, equal_nan=True)

@@ -207,7 +207,8 @@ def test_dense_term_beyond_64_images_matches_oracle(cuda_device):
     limit.  72 frames, sparse + dense depth + colour, against the oracle (which builds the reference's dense matrix)."""
     prob = synth.make_dense_ba_problem(72, stride=1, start=60, corr_per_pair=8, W=320, H=240)
     wS, wD, wC = [1.0, 1.0], [1.0, 2.0], [0.1, 0.1]
-    g = gpu_solve_dense(cuda_device, prob, 2, 40, wS, wD, wC)
-    o = orc.solve(prob["corr"], prob["init_rot"], prob["init_trans"], 2, 40, wS, wD, wC, prob["caches"], prob["intrinsics"])
+    # 2 x 15 PCG iterations: past ~25 the float32 PCG of this system sits on its noise floor and the summation order alone moves the result by 1e-5 ... 1e-3
+    g = gpu_solve_dense(cuda_device, prob, 2, 15, wS, wD, wC)
+    o = orc.solve(prob["corr"], prob["init_rot"], prob["init_trans"], 2, 15, wS, wD, wC, prob["caches"], prob["intrinsics"])
     assert g["stats"]["dense_overlap_pairs"] == o["overlap_pairs"] and g["stats"]["dense_weighted_pairs"] == o["weighted_pairs"] > 500
     assert rel_l2(np.c_[g["rot"], g["trans"]], np.c_[o["rot"], o["trans"]]) < 1e-4

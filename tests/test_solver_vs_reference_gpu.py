@@ -216,8 +216,8 @@ def test_dense_term_beyond_64_images_matches_reference_cuda(cuda_device):
     assert rel_l2(JtJ_our[6:, 6:], JtJ_ref[6:, 6:]) < TOL and rel_l2(Jtr_our[6:], Jtr_ref[6:]) < TOL
     assert np.array_equal(JtJ_our[6:, 6:] != 0, JtJ_ref[6:, 6:] != 0), "same block sparsity as the reference's dense matrix"
     wS, wD, wC = [1.0, 1.0], [1.0, 2.0], [0.1, 0.1]
-    x_ref, _, s = run_ref(cuda_device, prob, prob["corr"], 2, 40, wS, wD, wC, cache=cache, fast=False)
-    x_our, st = run_ours(cuda_device, prob, prob["corr"], 2, 40, wS, wD, wC, cache=cache)
+    x_ref, _, s = run_ref(cuda_device, prob, prob["corr"], 2, 15, wS, wD, wC, cache=cache, fast=False)
+    x_our, st = run_ours(cuda_device, prob, prob["corr"], 2, 15, wS, wD, wC, cache=cache)
     assert st["dense_overlap_pairs"] == int(s._bufs["d_numDenseOverlappingImages"].cpu().numpy()[0])
     assert rel_l2(x_our, x_ref) < TOL
 
