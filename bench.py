@@ -486,6 +486,9 @@ def run_loop(args):
         "clocks": summarize_clocks(clk_lines[clk_mark0:clk_mark1]), "clocks_profile_pass": summarize_clocks(clk_lines[clk_mark1:clk_mark2]),
     }
     if world == 1 and not args.no_cpu_baseline:
+        loop.close(); del loop, depth, color
+        torch.cuda.empty_cache()
+        out["reference_cuda"] = reference_cuda_leg(dev)
         out["cpu_baseline"] = cpu_arm(1, 0, quiet=True, n_reint=2)
     print(json.dumps(out))
     if world > 1:
@@ -580,6 +583,100 @@ def run_sweep(args):
                           "sweep": rows}))
     if world > 1:
         dist.destroy_process_group()
+
+# ------------------------------------------------------------------------------------------------------------------------
+def reference_cuda_leg(dev, n_frames=12):
+    """The reference's OWN CUDA for the TSDF + bundle-adjustment share of a step -- its kernels and host loops (oracle/_ref: the reference sources
+    compiled for sm_100a with --use_fast_math, as it ships), driven exactly like this library on the same inputs, same box, same run: per frame
+    1 integrate + 10 x (de-integrate + integrate) + garbage collection; per 10 frames one local BA (11 frames, sparse + dense, 2 x 100) and one global BA
+    (500 keyframes, sparse, 3 x 150).  Wall clock with a device synchronise on both sides (the reference's host loops synchronise internally).
+    A reported baseline like cpu_baseline: bounded sample, rank 0, N = 1."""
+    import torch
+    try:
+        from oracle import ref_solver, ref_tsdf
+        if not (ref_tsdf.available(True) and ref_solver.available(True)):
+            return {"unavailable": "oracle/_ref libraries not built (they need /root/reference at build time)"}
+    except Exception as e:                                  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    from bundlefusion_b200 import synth, synth_gpu
+    from bundlefusion_b200.scene_rep import CUDASceneRepHashSDF, camera_params, default_hash_params
+    from bundlefusion_b200.solver import CUDASolverBundling, DeviceCache
+
+    def wall(fn, reps):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    cam = camera_params(W, H)
+    hp = default_hash_params(num_buckets=1 << 21, num_sdf_blocks=1 << 20, voxel_size=0.01)
+    B = 24
+    depth, color, poses = synth_gpu.make_frames([8 * i for i in range(B)], W, H, device=str(dev))
+    rng = np.random.Generator(np.random.MT19937(3))
+    out = {}
+    for name in ("reference_cuda", "this_repo"):
+        s = ref_tsdf.ReferenceSceneRepHashSDF(hp, dev, fast_math=True) if name == "reference_cuda" else CUDASceneRepHashSDF(hp, dev)
+        s.reset()
+        cur = [np.array(p, np.float32) for p in poses]
+        for i in range(B):
+            s.integrate(cur[i], depth[i], color[i], cam)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for f in range(n_frames):
+            ops = []
+            for k in range(10):
+                i = (7 * f + k) % B
+                d = np.eye(4, dtype=np.float32); d[:3, 3] = rng.standard_normal(3).astype(np.float32) * 0.004
+                new = (d @ cur[i]).astype(np.float32)
+                ops += [(1, i, cur[i]), (0, i, new)]
+                cur[i] = new
+            ops.append((2, 0, None))
+            ops.append((0, f % B, cur[f % B]))
+            if name == "this_repo":
+                s.runOps(ops, [depth[i] for i in range(B)], [color[i] for i in range(B)], cam)
+            else:
+                for kind, i, T in ops:                      # the reference's loop: one host-synchronising call per operation
+                    if kind == 2: s.garbageCollect()
+                    elif kind == 1: s.deIntegrate(T, depth[i], color[i], cam)
+                    else: s.integrate(T, depth[i], color[i], cam)
+        torch.cuda.synchronize()
+        out[name] = {"tsdf_ms_per_frame": (time.perf_counter() - t0) / n_frames * 1e3}
+        del s
+    # bundle adjustment: the local chunk and the global problem of the ops workload
+    loc = synth.make_dense_ba_problem(11, stride=3, W=320, H=240)
+    glo = synth.make_ba_problem(WORKLOAD["global_keyframes"], degree=WORKLOAD["global_degree"], corr_per_pair=25, noise=0.002, seed=32, stride=10)
+    cache = DeviceCache(loc["caches"], loc["intrinsics"], dev)
+    for tag, prob, gn, pcg, wS, wD, wC, ch in (("local_ba_ms", loc, 2, 100, [1.0, 1.0], [1.0, 2.0], [0.0, 0.0], cache), ("global_ba_ms", glo, 3, 150, [1.0] * 3, None, None, None)):
+        N = len(prob["init_rot"]); nC = len(prob["corr"])
+        corr = torch.from_numpy(prob["corr"].view(np.uint8).reshape(-1).copy()).to(dev)
+        r0 = torch.from_numpy(prob["init_rot"]).to(dev); t0_ = torch.from_numpy(prob["init_trans"]).to(dev)
+        valid = torch.ones(N, dtype=torch.int32, device=dev)
+        rot, trans = r0.clone(), t0_.clone()
+        ours = CUDASolverBundling(N, max(nC, 1000 * N), dev)
+        ref = ref_solver.ReferenceSolverBundling(N, max(nC, 1000 * N), dev, fast_math=True)
+        c2 = corr.clone()
+
+        def run_ours():
+            rot.copy_(r0); trans.copy_(t0_)
+            ours.solve(corr, nC, valid, N, gn, pcg, wS, wD, wC, d_rotationAnglesUnknowns=rot, d_translationUnknowns=trans, cudaCache=ch)
+
+        def run_ref():
+            rot.copy_(r0); trans.copy_(t0_)
+            ref.solve(c2, nC, valid, N, gn, pcg, wS, wD, wC, d_rot=rot, d_trans=trans, cudaCache=ch)
+
+        run_ours(); run_ref()
+        out["this_repo"][tag] = wall(run_ours, 3); out["reference_cuda"][tag] = wall(run_ref, 3)
+    for name in out:
+        o = out[name]
+        o["ms_per_frame"] = o["tsdf_ms_per_frame"] + (o["local_ba_ms"] + o["global_ba_ms"]) / 10.0
+        o["frames_per_s"] = 1e3 / o["ms_per_frame"]
+        for k in list(o):
+            o[k] = round(o[k], 3)
+    return {"value": out["reference_cuda"]["frames_per_s"], "unit": "frames/s", "this_repo_same_sample": out["this_repo"]["frames_per_s"],
+            "speedup": round(out["this_repo"]["frames_per_s"] / out["reference_cuda"]["frames_per_s"], 2), "parts": out,
+            "kind": "the reference's CUDA kernels and host loops (oracle/_ref: its sources built for sm_100a with --use_fast_math) on this box, TSDF + bundle-adjustment share of a step (the stages the reference's stub surface covers), serial on one stream, wall clock",
+            "sample": f"{n_frames} frames of 1 integrate + 10 re-integrations + GC at 1 cm voxels; 3 repetitions of the local (11 frames, sparse + dense) and global (500 keyframes) solves"}
 
 # ------------------------------------------------------------------------------------------------------------------------
 def cpu_arm(steps, warmup, quiet=False, n_reint=None):
