@@ -518,7 +518,7 @@ def run_sweep(args):
     depth, color, poses = synth_gpu.make_frames(idx, W, H, device=str(dev))           # the same bank on every rank (deterministic); the timed steps use rank 0's copy
     rng = np.random.Generator(np.random.MT19937(5))
     rows = []
-    for vs in (0.04, 0.02, 0.01, 0.006, 0.004):
+    for vs in (0.04, 0.02, 0.01, 0.006, 0.004, 0.003, 0.002):
         hp = default_hash_params(num_buckets=4_000_000, num_sdf_blocks=3_000_000, voxel_size=vs)
         if world > 1:
             hp.m_dummy = (world << 32) | rank
@@ -578,7 +578,7 @@ def run_sweep(args):
     if rank == 0:
         print(json.dumps({"metric": "Mvoxels/s, TSDF de-integrate + integrate (BASELINE configs[3] sweep)", "unit": "Mvoxels/s", "n_gpus": world, "steps": K, "warmup": Wm,
                           "value": rows[-1]["mvoxels_per_s"], "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "f32",
-                          "config": {"workload": "one re-integration per step of a 24-frame bank at voxel sizes 4 cm ... 4 mm; Mvoxels = 512 x in-frustum blocks (both ops), summed over the ranks; time = max over ranks",
+                          "config": {"workload": "one re-integration per step of a 24-frame bank at voxel sizes 4 cm ... 2 mm; Mvoxels = 512 x in-frustum blocks (both ops), summed over the ranks; time = max over ranks",
                                      "parallelism": "single GPU" if world == 1 else f"voxel hash sharded over {world} GPUs by block owner; frame + pose pair broadcast from rank 0 (NCCL) every step"},
                           "sweep": rows}))
     if world > 1:
