@@ -13,6 +13,9 @@
 //    tests, the mutual-best check against the row pass, and the append;
 //  * all pairs of a frame are ONE batch: two launches in total instead of (2 copies + 3 launches + 1 memset) per pair.
 // Round 1 uses the warp-level mma.sync path; the tcgen05 / TMEM version of the contraction is round-2 work.
+#include <cuda.h>
+
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -30,6 +33,7 @@ struct SiftJobDev {
     int* numMatches; float* outDist; uint2* outIdx;
     uint2 offset;
     int* colResult; int* done;         // column pass: match of each image-2 feature (-1 none), CTAs of the job that have finished
+    const CUtensorMap* mapA; const CUtensorMap* mapB;      // TMA sweep: [n][128 B] tensor maps of the two descriptor arrays (box 128 x 128, 128-byte swizzle, zero fill past n)
 };
 
 // Winner among equal maxima, exactly as the reference's 32 strided lanes + fold-upper-half-into-lower tree pick it (see
@@ -74,10 +78,10 @@ __device__ __forceinline__ void finish_feature(const SiftJobDev& job, int r, con
 }
 // The reference appends its matches with an atomicAdd: beyond the 128-slot cap the kept subset depends on the scheduling.  Here the job's last
 // CTA to finish compacts the per-feature results in ascending image-2 feature: the first 128 are kept, the counter still holds the total.
-// 128 threads; ctasOfJob: CTAs of this launch that work on the job.
+// Any block of <= 8 warps (all of them call); ctasOfJob: CTAs of this launch that work on the job.
 __device__ __forceinline__ void compact_job(const SiftJobDev& job, int ctasOfJob) {
-    __shared__ int sLast, sWarp[4];
-    const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ int sLast, sWarp[8];
+    const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5, nWarps = blockDim.x >> 5;
     const int nA = job.nA;
     __threadfence();
     __syncthreads();
@@ -86,7 +90,7 @@ __device__ __forceinline__ void compact_job(const SiftJobDev& job, int ctasOfJob
     if (!sLast) return;
     __threadfence();
     int base = 0;
-    for (int r0 = 0; r0 < nA; r0 += 128) {
+    for (int r0 = 0; r0 < nA; r0 += (int)blockDim.x) {
         const int r = r0 + (int)t;
         const int res = (r < nA) ? __ldcg(&job.colResult[r]) : -1;
         const unsigned bal = __ballot_sync(0xffffffffu, res >= 0);
@@ -99,7 +103,7 @@ __device__ __forceinline__ void compact_job(const SiftJobDev& job, int ctasOfJob
             job.outIdx[slot] = make_uint2((unsigned)res + job.offset.x, (unsigned)r + job.offset.y);
             job.outDist[slot] = job.rowDist[res];
         }
-        base += sWarp[0] + sWarp[1] + sWarp[2] + sWarp[3];
+        for (unsigned w = 0; w < nWarps; ++w) base += sWarp[w];
         __syncthreads();
     }
     if (t == 0) { *job.numMatches = base; *job.done = 0; }
@@ -330,6 +334,114 @@ sift_best_tc_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ra
     if (kColumnPass) compact_job(job, (nA + TC_BM - 1) / TC_BM);
 }
 
+// ---- tcgen05 + TMA version: warp-specialised ---------------------------------------------------------------------------------------------------
+// 160 threads: warps 0-3 own the 128 features (thread = TMEM lane) and do nothing but read accumulators back and keep best / second best; warp 4's
+// first lane is the whole data path -- it asks the TMA unit for the A tile and, four tiles ahead, for the B tiles (cp.async.bulk.tensor.2d straight
+// into the 128-byte-swizzled layout the tensor core reads; rows past the end of a descriptor array arrive as zeros), and issues the four tcgen05.mma
+// of a tile as soon as its bytes have landed and the accumulator buffer is free.  Nobody copies descriptors through registers, nobody waits at a CTA
+// barrier inside the sweep: the hand-offs are mbarriers (TMA -> MMA: full[s]; MMA -> TMA: empty[s]; MMA -> read-back: tmemFull[b]; read-back -> MMA:
+// tmemEmpty[b]).
+#define TMA_STAGES 4
+#define TMA_SMEM_BYTES ((1 + TMA_STAGES) * TC_TILE_BYTES + 1024 + 24 * 1024)     // A + four B stages + alignment slack; padded to two CTAs per SM (2 x 256 TMEM columns)
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* map, int row, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(0), "r"(row) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory"); }
+
+template <bool kColumnPass>
+__global__ void __launch_bounds__(160)
+sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratiomax) {
+    const SiftJobDev job = jobs[blockIdx.y];
+    const int nA = job.nA, nB = job.nB;
+    const int row0 = blockIdx.x * TC_BM;
+    if (!kColumnPass && blockIdx.x == 0 && threadIdx.x == 0) *job.numMatches = 0;       // SiftMatch.cpp:163 / ProgramCU.cu:1928
+    if (nA <= 0 || nB <= 0 || row0 >= nA) return;
+
+    extern __shared__ unsigned char tcSmemRaw[];
+    __shared__ __align__(8) unsigned long long sBar[1 + 2 * TMA_STAGES + 4];     // fullA, full[S], empty[S], tmemFull[2], tmemEmpty[2]
+    __shared__ uint32_t sTmem;
+    unsigned char* const smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tcSmemRaw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sA = smem_u32(smem), sB = sA + TC_TILE_BYTES;
+    const unsigned t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t bFullA = smem_u32(&sBar[0]), bFull = smem_u32(&sBar[1]), bEmpty = smem_u32(&sBar[1 + TMA_STAGES]),
+                   bTFull = smem_u32(&sBar[1 + 2 * TMA_STAGES]), bTEmpty = smem_u32(&sBar[3 + 2 * TMA_STAGES]);
+    if (t == 0) {
+        mbar_init(bFullA, 1);
+        for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(bFull + 8 * s, 1); mbar_init(bEmpty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bTFull + 8 * b, 1); mbar_init(bTEmpty + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(&sTmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = sTmem;
+    const int T = (nB + TC_BN - 1) / TC_BN;
+    Top2 st = { 0, 0xFFFFFFFFu, 0 };
+
+    if (warp == 4) {
+        if (lane == 0) {
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(reinterpret_cast<uint64_t>(job.mapA)) : "memory");
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(reinterpret_cast<uint64_t>(job.mapB)) : "memory");
+            mbar_expect_tx(bFullA, TC_TILE_BYTES);
+            tma_load_tile(sA, job.mapA, row0, bFullA);
+            const int nPre = T < TMA_STAGES ? T : TMA_STAGES;
+            for (int j = 0; j < nPre; ++j) { mbar_expect_tx(bFull + 8 * j, TC_TILE_BYTES); tma_load_tile(sB + (uint32_t)j * TC_TILE_BYTES, job.mapB, j * TC_BN, bFull + 8 * j); }
+            mbar_wait(bFullA, 0);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % TMA_STAGES, b = j & 1;
+                mbar_wait(bFull + 8 * s, (uint32_t)((j / TMA_STAGES) & 1));
+                if (j >= 2) mbar_wait(bTEmpty + 8 * b, (uint32_t)(((j >> 1) - 1) & 1));       // the read-back of tile j - 2 has left accumulator buffer b
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tc_issue_tile(tmem + (uint32_t)(b * TC_BN), sA, sB + (uint32_t)s * TC_TILE_BYTES);
+                umma_commit(bTFull + 8 * b);
+                umma_commit(bEmpty + 8 * s);
+                if (j + TMA_STAGES < T) {
+                    mbar_wait(bEmpty + 8 * s, (uint32_t)((j / TMA_STAGES) & 1));                 // tile j's products have read stage s
+                    mbar_expect_tx(bFull + 8 * s, TC_TILE_BYTES);
+                    tma_load_tile(sB + (uint32_t)s * TC_TILE_BYTES, job.mapB, (j + TMA_STAGES) * TC_BN, bFull + 8 * s);
+                }
+            }
+        }
+    } else {
+        for (int j = 0; j < T; ++j) {
+            const int b = j & 1;
+            mbar_wait(bTFull + 8 * b, (uint32_t)((j >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem + ((warp * 32u) << 16) + (uint32_t)(b * TC_BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                uint32_t v[32];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                               "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                               "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                             : "r"(taddr + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int col0 = j * TC_BN + c0;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) top2_update<kColumnPass>(st, (int)v[e], (unsigned)(col0 + e));      // rows past nB are zero-filled by the TMA: never a candidate
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bTEmpty + 8 * b);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+    if (t < TC_BM) finish_feature<kColumnPass>(job, row0 + (int)t, st, distmax, ratiomax);
+    if (kColumnPass) compact_job(job, (nA + TC_BM - 1) / TC_BM);
+}
+
 // SortKeyPointMatchesCU_Kernel (SIFTImageManager.cu:59-145): one CTA per image pair, 128 slots, bitonic network in shared memory on
 // the total order (distance, image-2 feature, image-1 feature); padding sorts last.
 __global__ void __launch_bounds__(BF_MAX_MATCHES_PER_IMAGE_PAIR_RAW)
@@ -370,8 +482,37 @@ struct SiftWs {
     int* rowResult = nullptr; float* rowDist = nullptr; size_t rowCap = 0;
     int* colResult = nullptr; size_t colCap = 0;
     int* done = nullptr;
+    CUtensorMap* dMaps = nullptr; CUtensorMap* hMaps = nullptr; size_t mapCap = 0;      // two tensor maps per job (device table + pinned staging)
+    std::map<std::pair<const void*, int>, CUtensorMap> mapCache;                        // encoded maps by (array, rows): a keyframe's descriptors recur every frame
 };
 static SiftWs g_sift;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+// [rows][128] bytes, box 128 bytes x 128 rows, 128-byte swizzle, rows past the end read as zeros
+static bool descriptor_map(const uint8_t* base, int rows, CUtensorMap* out) {
+    auto key = std::make_pair((const void*)base, rows);
+    auto it = g_sift.mapCache.find(key);
+    if (it != g_sift.mapCache.end()) { *out = it->second; return true; }
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (reinterpret_cast<uintptr_t>(base) & 15u) || rows <= 0) return false;
+    const cuuint64_t dims[2] = { 128, (cuuint64_t)rows }, strides[1] = { 128 };
+    const cuuint32_t box[2] = { 128, 128 }, estr[2] = { 1, 1 };
+    if (fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    if (g_sift.mapCache.size() > 65536) g_sift.mapCache.clear();
+    g_sift.mapCache.emplace(key, *out);
+    return true;
+}
 static std::mutex g_siftMutex;
 
 }  // namespace bf
@@ -412,6 +553,26 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
         g_sift.colCap = cols * 2;
         BF_CHECK(cudaMalloc(&g_sift.colResult, sizeof(int) * g_sift.colCap));
     }
+    // BF_SIFT_MATCH: "mma" = warp-level mma.sync sweep, "tc" = tcgen05 with descriptors staged through registers, default = tcgen05 + TMA (falls back
+    // to "tc" for a batch whose arrays cannot be described by tensor maps: base not 16-byte aligned, or no driver entry point)
+    static int path = -1;
+    if (path < 0) {
+        const char* e = getenv("BF_SIFT_MATCH");
+        path = (e && e[0] == 'm') ? 0 : ((e && e[0] == 't' && e[1] == 'c') ? 1 : 2);
+        if (path >= 1) {
+            BF_CHECK(cudaFuncSetAttribute(sift_best_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            BF_CHECK(cudaFuncSetAttribute(sift_best_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            BF_CHECK(cudaFuncSetAttribute(sift_best_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+            BF_CHECK(cudaFuncSetAttribute(sift_best_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+        }
+    }
+    bool mapsOk = (path == 2);
+    if (mapsOk && (size_t)numJobs > g_sift.mapCap) {
+        if (g_sift.dMaps) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dMaps)); BF_CHECK(cudaFreeHost(g_sift.hMaps)); }
+        g_sift.mapCap = (size_t)numJobs * 2;
+        BF_CHECK(cudaMalloc(&g_sift.dMaps, sizeof(CUtensorMap) * 2 * g_sift.mapCap));
+        BF_CHECK(cudaMallocHost(&g_sift.hMaps, sizeof(CUtensorMap) * 2 * g_sift.mapCap));
+    }
     SiftJobDev* h = g_sift.hJobs;
     size_t off = 0, coff = 0;
     for (int i = 0; i < numJobs; ++i) {
@@ -423,24 +584,27 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
         r.numMatches = j.out.d_numMatches; r.outDist = j.out.d_distances; r.outIdx = reinterpret_cast<uint2*>(j.out.d_keyPointIndices);
         r.offset = make_uint2(j.keyPointOffset[0], j.keyPointOffset[1]);
         r.colResult = g_sift.colResult + coff; r.done = g_sift.done + i;
+        r.mapA = nullptr; r.mapB = nullptr;
+        if (mapsOk && live) {
+            if (descriptor_map(j.d_des1, j.num1, &g_sift.hMaps[2 * i]) && descriptor_map(j.d_des2, j.num2, &g_sift.hMaps[2 * i + 1])) { r.mapA = g_sift.dMaps + 2 * i; r.mapB = g_sift.dMaps + 2 * i + 1; }
+            else mapsOk = false;
+        }
         SiftJobDev c = r;                                   // column pass: image 2 owns the sweep, image 1 is swept
-        c.desA = j.d_des2; c.nA = r.nB; c.desB = j.d_des1; c.nB = r.nA;
+        c.desA = j.d_des2; c.nA = r.nB; c.desB = j.d_des1; c.nB = r.nA; c.mapA = r.mapB; c.mapB = r.mapA;
         h[i] = r; h[(size_t)numJobs + i] = c;
         if (live) { off += (size_t)j.num1; coff += (size_t)j.num2; }
     }
+    if (mapsOk) BF_CHECK(cudaMemcpyAsync(g_sift.dMaps, g_sift.hMaps, sizeof(CUtensorMap) * 2 * (size_t)numJobs, cudaMemcpyHostToDevice, s));
     BF_CHECK(cudaMemcpyAsync(g_sift.dJobs, h, sizeof(SiftJobDev) * 2 * (size_t)numJobs, cudaMemcpyHostToDevice, s));
     BF_CHECK(cudaEventRecord(g_sift.evCopied, s));
     g_launchCount += 2;
-    static int path = -1;               // BF_SIFT_MATCH=mma selects the warp-level mma.sync sweep (kept for A / B measurements); default: tcgen05
-    if (path < 0) {
-        const char* e = getenv("BF_SIFT_MATCH");
-        path = (e && e[0] == 'm') ? 0 : 1;
-        if (path == 1) {
-            BF_CHECK(cudaFuncSetAttribute(sift_best_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-            BF_CHECK(cudaFuncSetAttribute(sift_best_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        }
-    }
-    if (path == 1) {
+    if (path == 2 && mapsOk) {
+        const int gx1 = maxN1 > 0 ? (maxN1 + TC_BM - 1) / TC_BM : 1, gx2 = maxN2 > 0 ? (maxN2 + TC_BM - 1) / TC_BM : 1;
+        sift_best_tma_kernel<false><<<dim3(gx1, numJobs), 160, TMA_SMEM_BYTES, s>>>(g_sift.dJobs, distmax, ratiomax);
+        BF_CHECK(cudaGetLastError());
+        sift_best_tma_kernel<true><<<dim3(gx2, numJobs), 160, TMA_SMEM_BYTES, s>>>(g_sift.dJobs + numJobs, distmax, ratiomax);
+        BF_CHECK(cudaGetLastError());
+    } else if (path >= 1) {
         const int gx1 = maxN1 > 0 ? (maxN1 + TC_BM - 1) / TC_BM : 1, gx2 = maxN2 > 0 ? (maxN2 + TC_BM - 1) / TC_BM : 1;
         sift_best_tc_kernel<false><<<dim3(gx1, numJobs), 128, TC_SMEM_BYTES, s>>>(g_sift.dJobs, distmax, ratiomax);
         BF_CHECK(cudaGetLastError());
@@ -473,7 +637,8 @@ BF_API size_t bfSiftWorkspaceBytes(void) {
 }
 BF_API int bfSiftReleaseWorkspace(void) {
     std::lock_guard<std::mutex> lk(g_siftMutex);
-    cudaFree(g_sift.dJobs); cudaFree(g_sift.rowResult); cudaFree(g_sift.rowDist); cudaFree(g_sift.colResult); cudaFree(g_sift.done);
+    cudaFree(g_sift.dJobs); cudaFree(g_sift.rowResult); cudaFree(g_sift.rowDist); cudaFree(g_sift.colResult); cudaFree(g_sift.done); cudaFree(g_sift.dMaps);
+    if (g_sift.hMaps) cudaFreeHost(g_sift.hMaps);
     if (g_sift.hJobs) cudaFreeHost(g_sift.hJobs);
     if (g_sift.evCopied) cudaEventDestroy(g_sift.evCopied);
     if (g_sift.evDone) cudaEventDestroy(g_sift.evDone);
