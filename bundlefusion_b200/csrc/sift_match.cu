@@ -217,6 +217,40 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
     if (kColumnPass) compact_job(job, (nA + SM_BM - 1) / SM_BM);
 }
 
+// ---- branch-free best / second best over a 32-column slice held in registers (the tcgen05 read-back: a thread owns a whole feature) ----
+// State: best value, its preference word lo = 0xFFFFFFFF - tie key (larger = preferred among equal values), second largest VALUE of the multiset.
+// The slice is folded by four independent chains (columns e mod 4) that are merged afterwards: no data-dependent branch, four-way instruction-level
+// parallelism -- the per-element `if` of top2_update costs a divergent branch per product, which is what bounded all three sweeps at ~3 us per pair.
+struct Top2P { int v1; unsigned lo; int v2; };
+__device__ __forceinline__ void top2p_fold(Top2P& s, int v, unsigned lo) {
+    const bool gt = (v > s.v1) | ((v == s.v1) & (lo > s.lo));
+    s.v2 = max(s.v2, min(s.v1, v));
+    s.v1 = gt ? v : s.v1; s.lo = gt ? lo : s.lo;
+}
+__device__ __forceinline__ void top2p_merge(Top2P& a, const Top2P& b) {
+    const bool gt = (b.v1 > a.v1) | ((b.v1 == a.v1) & (b.lo > a.lo));
+    a.v2 = max(max(a.v2, b.v2), min(a.v1, b.v1));
+    a.v1 = gt ? b.v1 : a.v1; a.lo = gt ? b.lo : a.lo;
+}
+__host__ __device__ constexpr unsigned brev5_c(unsigned x) { return ((x & 1u) << 4) | ((x & 2u) << 2) | (x & 4u) | ((x & 8u) >> 2) | ((x & 16u) >> 4); }
+// colBase: first column of the slice, a multiple of 32.  Tie key of column c (tie_key): rows (brev5(c % 32) << 24) | c, columns (brev5((c / 4) % 32) << 24) | c;
+// with c = colBase + e both split into a per-element constant and a per-slice term.
+template <bool kColumnPass>
+__device__ __forceinline__ void top2p_slice(Top2P& st, const uint32_t (&v)[32], unsigned colBase) {
+    const unsigned sliceTerm = kColumnPass ? (((__brev((colBase >> 2) & 31u) >> 27) << 24) + colBase) : colBase;
+    Top2P c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { c[k].v1 = 0; c[k].lo = 0u; c[k].v2 = 0; }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        const unsigned ce = 0xFFFFFFFFu - ((kColumnPass ? brev5_c((unsigned)e >> 2) : brev5_c((unsigned)e)) << 24) - (unsigned)e;
+        top2p_fold(c[e & 3], (int)v[e], ce - sliceTerm);
+    }
+    top2p_merge(c[0], c[1]); top2p_merge(c[2], c[3]); top2p_merge(c[0], c[2]);
+    top2p_merge(st, c[0]);
+}
+__device__ __forceinline__ Top2 top2p_finish(const Top2P& s) { Top2 r; r.v1 = s.v1; r.k1 = 0xFFFFFFFFu - s.lo; r.v2 = s.v2; return r; }
+
 // ---- tcgen05 version of the sweep -------------------------------------------------------------------------------------------------------------
 // One CTA = 128 features of A (one per thread = one TMEM lane) against all of B in tiles of 128: the tile's 128 x 128 x 128 u8 x u8 -> s32 products are
 // four tcgen05.mma (kind::i8, M 128, N 128, K 32) issued by one thread, operands in shared memory in the canonical K-major 128-byte-swizzle layout
@@ -295,7 +329,7 @@ sift_best_tc_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ra
         tc_issue_tile(tmem, smem_u32(sA), smem_u32(sB0));
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar0) : "memory");
     }
-    Top2 st = { 0, 0xFFFFFFFFu, 0 };       // a dot product must be > 0 to be a candidate (the reference starts from max = 0 with a strict '>')
+    Top2P st = { 0, 0u, 0 };               // a dot product must be > 0 to be a candidate (the reference starts from max = 0 with a strict '>')
     for (int j = 0; j < T; ++j) {
         if (j + 1 < T) {
             // buffer (j + 1) & 1 of B was read by the products of tile j - 1 and accumulator buffer (j + 1) & 1 by its read-back: both finished in iteration j - 1
@@ -322,15 +356,13 @@ sift_best_tc_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ra
                            "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                          : "r"(taddr + (uint32_t)c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int col0 = j * TC_BN + c0;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) top2_update<kColumnPass>(st, (int)v[e], (unsigned)(col0 + e));      // padded columns give 0: never a candidate
+            top2p_slice<kColumnPass>(st, v, (unsigned)(j * TC_BN + c0));                                  // padded columns give 0: never a candidate
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
-    finish_feature<kColumnPass>(job, row0 + (int)t, st, distmax, ratiomax);
+    finish_feature<kColumnPass>(job, row0 + (int)t, top2p_finish(st), distmax, ratiomax);
     if (kColumnPass) compact_job(job, (nA + TC_BM - 1) / TC_BM);
 }
 
@@ -385,7 +417,7 @@ sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float r
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sTmem;
     const int T = (nB + TC_BN - 1) / TC_BN;
-    Top2 st = { 0, 0xFFFFFFFFu, 0 };
+    Top2P st = { 0, 0u, 0 };
 
     if (warp == 4) {
         if (lane == 0) {
@@ -426,9 +458,7 @@ sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float r
                                "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                              : "r"(taddr + (uint32_t)c0));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int col0 = j * TC_BN + c0;
-#pragma unroll
-                for (int e = 0; e < 32; ++e) top2_update<kColumnPass>(st, (int)v[e], (unsigned)(col0 + e));      // rows past nB are zero-filled by the TMA: never a candidate
+                top2p_slice<kColumnPass>(st, v, (unsigned)(j * TC_BN + c0));                              // rows past nB are zero-filled by the TMA: never a candidate
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -438,7 +468,7 @@ sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float r
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
-    if (t < TC_BM) finish_feature<kColumnPass>(job, row0 + (int)t, st, distmax, ratiomax);
+    if (t < TC_BM) finish_feature<kColumnPass>(job, row0 + (int)t, top2p_finish(st), distmax, ratiomax);
     if (kColumnPass) compact_job(job, (nA + TC_BM - 1) / TC_BM);
 }
 

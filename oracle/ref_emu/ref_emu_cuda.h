@@ -17,13 +17,11 @@
 #define __inline__ inline
 
 // ---- vector types beyond cuda_emu.h ----
-struct float3 { float x, y, z; }; struct int3 { int x, y, z; }; struct int4 { int x, y, z, w; }; struct uint4 { unsigned x, y, z, w; };
+struct float3 { float x, y, z; }; struct int3 { int x, y, z; };        // int4 / uint4 and their make_ functions: cuda_emu.h
 struct uchar3 { unsigned char x, y, z; }; struct ushort2 { unsigned short x, y; };
 static inline float3 make_float3(float x, float y, float z) { return { x, y, z }; }
 static inline int3 make_int3(int x, int y, int z) { return { x, y, z }; }
-static inline int4 make_int4(int x, int y, int z, int w) { return { x, y, z, w }; }
 static inline uint3 make_uint3(unsigned x, unsigned y, unsigned z) { return { x, y, z }; }
-static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return { x, y, z, w }; }
 
 #define CUDA_VERSION 12090
 #define CUDART_VERSION 12090
@@ -49,7 +47,6 @@ static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrt(float x) { return 1.0f / sqrtf(x); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline int atomicAdd(int* p, int v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const int o = *p; *p = o + v; return o; }
-static inline unsigned atomicAdd(unsigned* p, unsigned v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const unsigned o = *p; *p = o + v; return o; }
 static inline float __shfl_down(float v, int d, int = 32) { return __shfl_down_sync(0xFFFFFFFFu, v, d); }
 static inline float __shfl_xor(float v, int m, int = 32) { return __shfl_xor_sync(0xFFFFFFFFu, v, m); }
 static const int warpSize = 32;
