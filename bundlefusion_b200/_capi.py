@@ -126,7 +126,7 @@ SOLVER_SYMBOLS = [
     "solveBundlingStub", "buildVariablesToCorrespondencesTableCUDA", "evalMaxResidual", "countHighResiduals", "collectHighResiduals",
     "convertLiePosesToMatricesCU", "convertMatricesToPosesCU", "convertPosesToMatricesCU",
     "bfSolverSolve", "bfSolverGetStats", "bfSolverMaxResidual", "bfSolverWorkspaceBytes", "bfSolverReleaseWorkspace",
-    "bfSolverDebugDenseSystem",
+    "bfSolverDebugDenseSystem", "bfSolverPeerCreate", "bfSolverPeerConnect", "bfSolverPeerDisconnect",
 ]
 
 
@@ -305,6 +305,9 @@ def lib() -> C.CDLL:
     L.bfSiftVerifyTrajectory.argtypes = [C.c_uint, vp, vp, C.c_uint, C.c_uint, P(C.c_float), vp] + [C.c_float] * 7 + [vp, vp]
     L.bfSiftFuseToGlobal.argtypes = [vp, vp, vp, vp, C.c_uint, vp, vp, vp, C.c_uint, P(C.c_float), C.c_uint, vp, vp, vp, C.c_uint, vp]
     L.bfSolverDebugDenseSystem.argtypes = [P(BFSolverState), C.c_uint, vp, vp]
+    L.bfSolverPeerCreate.argtypes = [P(BFSolverState), C.c_uint, C.c_uint, vp]
+    L.bfSolverPeerConnect.argtypes = [P(BFSolverState), C.c_int, C.c_int, C.c_char_p]
+    L.bfSolverPeerDisconnect.argtypes = [P(BFSolverState)]
     L.bfCacheStoreFrame.argtypes = [P(BFCacheParams), vp, vp, P(BFCUDACachedFrame)]
     L.bfIngestFrame.argtypes = [P(BFIngestParams), vp, vp, vp, vp]
     L.computeSiftTransformCU.argtypes = [vp, vp, vp, C.c_uint, vp, C.c_uint, C.c_uint, vp]

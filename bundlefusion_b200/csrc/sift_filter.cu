@@ -201,15 +201,35 @@ __device__ int compute_reprojection(f3* src, f3* tgt, unsigned n, float* res, fl
         const float dz = (T[8] * src[i].x + T[9] * src[i].y + T[10] * src[i].z + T[11]) - tgt[i].z;
         res[i] = dx * dx + dy * dy + dz * dz;
     }
-    for (unsigned i = 0; i < n; ++i)                /* sortKabschResiduals, :368-377 */
-        for (unsigned j = i; j < n; ++j)
-            if (res[i] > res[j]) {
-                float t = res[i]; res[i] = res[j]; res[j] = t;
-                f3 s = src[i]; src[i] = src[j]; src[j] = s;
-                s = tgt[i]; tgt[i] = tgt[j]; tgt[j] = s;
-                uint32_t a = idx[2 * i], b = idx[2 * i + 1]; idx[2 * i] = idx[2 * j]; idx[2 * i + 1] = idx[2 * j + 1]; idx[2 * j] = a; idx[2 * j + 1] = b;
-                t = dist[i]; dist[i] = dist[j]; dist[j] = t;
-            }
+    /* sortKabschResiduals, :368-377: the reference's exchange sort makes ~n^2 / 2 dependent shared-memory round trips per fit.  Its result is the
+     * ascending order; only among EQUAL residuals does the arrangement depend on its particular swap sequence.  So: insertion sort (the list is nearly
+     * sorted from the previous fit: ~n steps), and when two neighbours of the result compare equal, the reference's own sequence from the saved input. */
+    {
+        unsigned char pos[MAX_FILTERED];                                               /* where each element stood before the sort */
+        for (unsigned i = 0; i < n; ++i) pos[i] = (unsigned char)i;
+        for (unsigned i = 1; i < n; ++i) {
+            const float r = res[i]; const f3 a = src[i], b = tgt[i]; const uint32_t ia = idx[2 * i], ib = idx[2 * i + 1]; const float d = dist[i]; const unsigned char pi = pos[i];
+            unsigned j = i;
+            while (j > 0 && res[j - 1] > r) { res[j] = res[j - 1]; src[j] = src[j - 1]; tgt[j] = tgt[j - 1]; idx[2 * j] = idx[2 * j - 2]; idx[2 * j + 1] = idx[2 * j - 1]; dist[j] = dist[j - 1]; pos[j] = pos[j - 1]; --j; }
+            res[j] = r; src[j] = a; tgt[j] = b; idx[2 * j] = ia; idx[2 * j + 1] = ib; dist[j] = d; pos[j] = pi;
+        }
+        bool tie = false;
+        for (unsigned i = 1; i < n; ++i) tie |= !(res[i] > res[i - 1]);               /* equal (or unordered: NaN) neighbours */
+        if (tie) {
+            f3 s0[MAX_FILTERED], t0[MAX_FILTERED]; float r0[MAX_FILTERED], d0[MAX_FILTERED]; uint32_t i0[2 * MAX_FILTERED];
+            for (unsigned i = 0; i < n; ++i) { const unsigned o = pos[i]; s0[o] = src[i]; t0[o] = tgt[i]; r0[o] = res[i]; d0[o] = dist[i]; i0[2 * o] = idx[2 * i]; i0[2 * o + 1] = idx[2 * i + 1]; }
+            for (unsigned i = 0; i < n; ++i) { src[i] = s0[i]; tgt[i] = t0[i]; res[i] = r0[i]; dist[i] = d0[i]; idx[2 * i] = i0[2 * i]; idx[2 * i + 1] = i0[2 * i + 1]; }
+            for (unsigned i = 0; i < n; ++i)
+                for (unsigned j = i; j < n; ++j)
+                    if (res[i] > res[j]) {
+                        float t = res[i]; res[i] = res[j]; res[j] = t;
+                        f3 s = src[i]; src[i] = src[j]; src[j] = s;
+                        s = tgt[i]; tgt[i] = tgt[j]; tgt[j] = s;
+                        uint32_t a = idx[2 * i], b = idx[2 * i + 1]; idx[2 * i] = idx[2 * j]; idx[2 * i + 1] = idx[2 * j + 1]; idx[2 * j] = a; idx[2 * j + 1] = b;
+                        t = dist[i]; dist[i] = dist[j]; dist[j] = t;
+                    }
+        }
+    }
     const float c1 = evs[0] / evs[1];
     float e[3];
     covariance_eigs(src, n, e); const float cp = e[0] / e[1];
@@ -251,7 +271,9 @@ __device__ unsigned filter_pair(const KeyPoint* kp, uint32_t* idx, float* dist, 
             idx[2 * cur] = idx[2 * i0]; idx[2 * cur + 1] = idx[2 * i0 + 1]; dist[cur] = dist[i0];
             ++cur;
             if (cur >= 3) {
-                key_points_3d(kp, idx, cur, src, tgt, Ki);
+                // getKeySourceAndTargetPoints recomputes all cur points from their indices; src / tgt follow idx through every sort, so only the points of
+                // the first fit (cur == 3) and, afterwards, of the match just added are not in place already -- same values, 2 key-point loads instead of 2 cur
+                if (cur == 3) key_points_3d(kp, idx, 3, src, tgt, Ki); else key_points_3d(kp, idx + 2 * (cur - 1), 1, src + (cur - 1), tgt + (cur - 1), Ki);
                 valid = compute_reprojection(src, tgt, cur, res, T, idx, dist);
                 const int b = valid;
                 float prevT[16]; for (int k = 0; k < 16; ++k) prevT[k] = T[k];

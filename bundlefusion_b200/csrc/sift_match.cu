@@ -218,38 +218,52 @@ sift_best_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratio
 }
 
 // ---- branch-free best / second best over a 32-column slice held in registers (the tcgen05 read-back: a thread owns a whole feature) ----
-// State: best value, its preference word lo = 0xFFFFFFFF - tie key (larger = preferred among equal values), second largest VALUE of the multiset.
-// The slice is folded by four independent chains (columns e mod 4) that are merged afterwards: no data-dependent branch, four-way instruction-level
-// parallelism -- the per-element `if` of top2_update costs a divergent branch per product, which is what bounded all three sweeps at ~3 us per pair.
-struct Top2P { int v1; unsigned lo; int v2; };
-__device__ __forceinline__ void top2p_fold(Top2P& s, int v, unsigned lo) {
-    const bool gt = (v > s.v1) | ((v == s.v1) & (lo > s.lo));
-    s.v2 = max(s.v2, min(s.v1, v));
-    s.v1 = gt ? v : s.v1; s.lo = gt ? lo : s.lo;
-}
-__device__ __forceinline__ void top2p_merge(Top2P& a, const Top2P& b) {
-    const bool gt = (b.v1 > a.v1) | ((b.v1 == a.v1) & (b.lo > a.lo));
-    a.v2 = max(max(a.v2, b.v2), min(a.v1, b.v1));
-    a.v1 = gt ? b.v1 : a.v1; a.lo = gt ? b.lo : a.lo;
-}
-__host__ __device__ constexpr unsigned brev5_c(unsigned x) { return ((x & 1u) << 4) | ((x & 2u) << 2) | (x & 4u) | ((x & 8u) >> 2) | ((x & 16u) >> 4); }
-// colBase: first column of the slice, a multiple of 32.  Tie key of column c (tie_key): rows (brev5(c % 32) << 24) | c, columns (brev5((c / 4) % 32) << 24) | c;
-// with c = colBase + e both split into a per-element constant and a per-slice term.
+// A product v (< 2^23: 128 x 255 x 255) and the preference of its column among equal products are packed into ONE 32-bit word, x = 32 v + R(e), so that
+// the running best and the second largest value of the multiset cost three integer min / max per product (m = max(b, x); s = max(s, min(b, x)); b = m)
+// plus one multiply-add on the FMA pipe for the packing -- the per-product `if` of top2_update costs a divergent branch, a 64-bit (value, key) compare
+// seven ALU-pipe operations, and the ALU pipe is what bounds the read-back (ncu: 86 %, profiles/r2_sift_match_ncu.txt).
+// The reference's tie rule (tie_key): among equal products the smallest (bit-reversed "lane", column) wins, lane = column % 32 for rows and
+// (column / 4) % 32 for columns.  Inside a 32-column slice (first column a multiple of 32) that is a fixed 5-bit rank R(e) of the slice position e; across
+// slices it is decided once per slice (top2q_merge): rows -- same rank order, then the earlier slice; columns -- the two low bits of the bit-reversed lane
+// come from the slice's position in its 128-column tile, then the earlier tile.
+struct Top2Q { int kBest; int bBest; int slice; int s2; };           // merge key and packed word of the best product, its slice, packed second
+__host__ __device__ constexpr int brev5_c(int x) { return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4); }
+__host__ __device__ constexpr int brev3_c(int x) { return ((x & 1) << 2) | (x & 2) | ((x & 4) >> 2); }
+template <bool kColumnPass> __host__ __device__ constexpr int rank_of(int e) { return kColumnPass ? (((7 - brev3_c(e >> 2)) << 2) | (3 - (e & 3))) : (31 - brev5_c(e)); }
+__device__ __forceinline__ int mad_fma_pipe(int a, int b, int c) { int d; asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 template <bool kColumnPass>
-__device__ __forceinline__ void top2p_slice(Top2P& st, const uint32_t (&v)[32], unsigned colBase) {
-    const unsigned sliceTerm = kColumnPass ? (((__brev((colBase >> 2) & 31u) >> 27) << 24) + colBase) : colBase;
-    Top2P c[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { c[k].v1 = 0; c[k].lo = 0u; c[k].v2 = 0; }
+__device__ __forceinline__ void top2q_slice(Top2Q& st, const uint32_t (&v)[32], int sliceIdx, int thirtyTwo) {
+    int b[4] = { 0, 0, 0, 0 }, s[4] = { 0, 0, 0, 0 };
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
-        const unsigned ce = 0xFFFFFFFFu - ((kColumnPass ? brev5_c((unsigned)e >> 2) : brev5_c((unsigned)e)) << 24) - (unsigned)e;
-        top2p_fold(c[e & 3], (int)v[e], ce - sliceTerm);
+        const int x = mad_fma_pipe((int)v[e], thirtyTwo, rank_of<kColumnPass>(e));      // `thirtyTwo` is a run-time 32: a literal would turn this into an ALU-pipe shift-add
+        const int k = e & 3;
+        s[k] = max(s[k], min(b[k], x));
+        b[k] = max(b[k], x);
     }
-    top2p_merge(c[0], c[1]); top2p_merge(c[2], c[3]); top2p_merge(c[0], c[2]);
-    top2p_merge(st, c[0]);
+    // four chains -> one (packed words are distinct unless zero, so max / min on them is the multiset's best / second)
+    const int b01 = max(b[0], b[1]), s01 = max(max(s[0], s[1]), min(b[0], b[1]));
+    const int b23 = max(b[2], b[3]), s23 = max(max(s[2], s[3]), min(b[2], b[3]));
+    const int bb = max(b01, b23), ss = max(max(s01, s23), min(b01, b23));
+    // into the running state
+    const int key = kColumnPass ? ((bb & ~3) | (3 - (((sliceIdx & 1) << 1) | ((sliceIdx >> 1) & 1)))) : bb;       // columns: 3 - brev2(slice position in its tile)
+    const bool gt = key > st.kBest;                                       // equal keys: the earlier slice keeps it
+    st.s2 = max(max(st.s2, ss), min(st.bBest, bb));
+    st.kBest = gt ? key : st.kBest; st.bBest = gt ? bb : st.bBest; st.slice = gt ? sliceIdx : st.slice;
 }
-__device__ __forceinline__ Top2 top2p_finish(const Top2P& s) { Top2 r; r.v1 = s.v1; r.k1 = 0xFFFFFFFFu - s.lo; r.v2 = s.v2; return r; }
+// back to the (value, tie key, second value) form finish_feature takes
+template <bool kColumnPass>
+__device__ __forceinline__ Top2 top2q_finish(const Top2Q& st) {
+    Top2 r;
+    r.v1 = st.bBest >> 5; r.v2 = st.s2 >> 5;
+    const int rank = st.bBest & 31;
+    int e = 0;
+    if (kColumnPass) { const int hi = 7 - (rank >> 2); e = (brev3_c(hi) << 2) | (3 - (rank & 3)); }
+    else e = brev5_c(31 - rank);
+    const unsigned col = (unsigned)st.slice * 32u + (unsigned)e;
+    r.k1 = tie_key<kColumnPass>(col);
+    return r;
+}
 
 // ---- tcgen05 version of the sweep -------------------------------------------------------------------------------------------------------------
 // One CTA = 128 features of A (one per thread = one TMEM lane) against all of B in tiles of 128: the tile's 128 x 128 x 128 u8 x u8 -> s32 products are
@@ -329,7 +343,8 @@ sift_best_tc_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ra
         tc_issue_tile(tmem, smem_u32(sA), smem_u32(sB0));
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar0) : "memory");
     }
-    Top2P st = { 0, 0u, 0 };               // a dot product must be > 0 to be a candidate (the reference starts from max = 0 with a strict '>')
+    Top2Q st = { 0, 0, 0, 0 };             // a dot product must be > 0 to be a candidate (the reference starts from max = 0 with a strict '>')
+    const int thirtyTwo = 32 + (nA >> 30);    // 32, opaque to the compiler
     for (int j = 0; j < T; ++j) {
         if (j + 1 < T) {
             // buffer (j + 1) & 1 of B was read by the products of tile j - 1 and accumulator buffer (j + 1) & 1 by its read-back: both finished in iteration j - 1
@@ -356,13 +371,13 @@ sift_best_tc_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ra
                            "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                          : "r"(taddr + (uint32_t)c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            top2p_slice<kColumnPass>(st, v, (unsigned)(j * TC_BN + c0));                                  // padded columns give 0: never a candidate
+            top2q_slice<kColumnPass>(st, v, (j * TC_BN + c0) >> 5, thirtyTwo);                            // padded columns give 0: never a candidate
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
-    finish_feature<kColumnPass>(job, row0 + (int)t, top2p_finish(st), distmax, ratiomax);
+    finish_feature<kColumnPass>(job, row0 + (int)t, top2q_finish<kColumnPass>(st), distmax, ratiomax);
     if (kColumnPass) compact_job(job, (nA + TC_BM - 1) / TC_BM);
 }
 
@@ -417,7 +432,8 @@ sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float r
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sTmem;
     const int T = (nB + TC_BN - 1) / TC_BN;
-    Top2P st = { 0, 0u, 0 };
+    Top2Q st = { 0, 0, 0, 0 };
+    const int thirtyTwo = 32 + (nA >> 30);    // 32, opaque to the compiler
 
     if (warp == 4) {
         if (lane == 0) {
@@ -458,7 +474,7 @@ sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float r
                                "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                              : "r"(taddr + (uint32_t)c0));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                top2p_slice<kColumnPass>(st, v, (unsigned)(j * TC_BN + c0));                              // rows past nB are zero-filled by the TMA: never a candidate
+                top2q_slice<kColumnPass>(st, v, (j * TC_BN + c0) >> 5, thirtyTwo);                        // rows past nB are zero-filled by the TMA: never a candidate
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -468,7 +484,7 @@ sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float r
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
-    if (t < TC_BM) finish_feature<kColumnPass>(job, row0 + (int)t, top2p_finish(st), distmax, ratiomax);
+    if (t < TC_BM) finish_feature<kColumnPass>(job, row0 + (int)t, top2q_finish<kColumnPass>(st), distmax, ratiomax);
     if (kColumnPass) compact_job(job, (nA + TC_BM - 1) / TC_BM);
 }
 

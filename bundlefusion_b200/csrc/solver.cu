@@ -34,6 +34,7 @@ extern unsigned long long g_launchCount;      // defined in tsdf.cu (bfGetLaunch
 #define BF_FLOAT_EPSILON 0.000001f      // FL/SolverUtil.h:9
 #define BF_MAX_ROW 8192                 // longest variable row the in-smem row sort handles
 #define BF_SOLVER_THREADS 256
+#define BF_SOLVER_MAX_PEERS 8
 #define BF_DENSE_MAX_IMAGES 4096        // dense term: N^2 pair tables + one 90-sum record per image pair (allocated on first use, sized by the workspace)
 
 __device__ void mat4_mul(const float* a, const float* b, float* o) {
@@ -93,6 +94,8 @@ struct SolverWs {
     float* denseJtr = nullptr;    // [6 Nd]
     unsigned* scal = nullptr;     // [SC_NUM]
     int maxGrid = 0;
+    // sharded solve (bfSolverPeerCreate / Connect): this rank's exchange region (cudaMalloc'd, opened by the peers through CUDA IPC) and theirs
+    int rank = 0, world = 1; float* region = nullptr; float* peer[BF_SOLVER_MAX_PEERS] = {}; bool peerOpened[BF_SOLVER_MAX_PEERS] = {}; unsigned peerSeq = 0;
     const void* owner[4] = { nullptr, nullptr, nullptr, nullptr };   // the caller's d_deltaTrans / d_rRot / d_pRot / d_Ap_XRot: a recycled
                                                                      // d_deltaRot address with other neighbours is another solver object
 };
@@ -101,6 +104,8 @@ static void free_ws(SolverWs& w) {
     cudaFree(w.offBlk); cudaFree(w.segMom); cudaFree(w.diagBlk); cudaFree(w.partials); cudaFree(w.p2); cudaFree(w.scal);
     cudaFree(w.pairW); cudaFree(w.pairIdx); cudaFree(w.pairCnt); cudaFree(w.pairRowStart); cudaFree(w.pairIJ); cudaFree(w.pairOut); cudaFree(w.dnbrStart); cudaFree(w.dnbr);
     cudaFree(w.denseDiag); cudaFree(w.denseJtr);
+    for (int g = 0; g < BF_SOLVER_MAX_PEERS; ++g) if (w.peerOpened[g]) cudaIpcCloseMemHandle(w.peer[g]);
+    cudaFree(w.region);
 }
 static std::mutex g_wsMutex;
 static std::map<const void*, SolverWs> g_ws;
@@ -304,7 +309,15 @@ struct GnArgs {
     float* p2Rot; float* p2Trans;
     float wSparse; unsigned nLin; int isLastGn; int maxGrid;
     const int* dnbrStart; const int2* dnbr; const float* pairOut; const float* denseDiag; const float* denseJtr; int useDense;       // dense term, block-sparse (NULL / 0 when off)
+    // rows sharded over GPUs (world > 1): this rank computes A p for the rows v with v % world == rank and stores them straight into EVERY rank's exchange
+    // region over NVLink; peer[g] = base of rank g's region (peer[rank]: the local one).  seqBase: barrier sequence numbers already used.
+    int rank, world; float* peer[BF_SOLVER_MAX_PEERS]; unsigned seqBase; unsigned peerMaxN;
 };
+// exchange region of a rank (floats): ap[2][6 maxN] (rot 3 maxN, trans 3 maxN; double-buffered by PCG iteration parity), partials[2][MAX_PEERS * maxGrid], flags[MAX_PEERS]
+__host__ __device__ inline size_t peer_region_floats(unsigned maxN, int maxGrid) { return (size_t)12 * maxN + (size_t)2 * BF_SOLVER_MAX_PEERS * maxGrid + BF_SOLVER_MAX_PEERS; }
+__device__ __forceinline__ float* peer_ap(float* base, unsigned maxN, unsigned par) { return base + (size_t)par * 6 * maxN; }
+__device__ __forceinline__ float* peer_partials(float* base, unsigned maxN, int maxGrid, unsigned par) { return base + (size_t)12 * maxN + (size_t)par * BF_SOLVER_MAX_PEERS * maxGrid; }
+__device__ __forceinline__ unsigned* peer_flags(float* base, unsigned maxN, int maxGrid) { return reinterpret_cast<unsigned*>(base + (size_t)12 * maxN + (size_t)2 * BF_SOLVER_MAX_PEERS * maxGrid); }
 
 // 6x6 block times 6-vector (rot,trans order)
 __device__ __forceinline__ void blk_mv(const float* __restrict__ B, V3 pr, V3 pt, float* y) {
@@ -349,6 +362,27 @@ struct GridBarrier {
         if (kCluster) { __threadfence(); cg::this_cluster().sync(); } else cg::this_grid().sync();
     }
 };
+
+// Barrier over all GPUs of a sharded solve.  Every thread's remote stores are made visible system-wide, the local grid arrives, one CTA publishes this
+// rank's sequence number in every rank's flag array (release), every CTA waits on its OWN region until all ranks have published it (acquire).
+template <class Grid>
+__device__ __forceinline__ void peer_barrier(const GnArgs& a, unsigned seq, Grid& grid) {
+    __threadfence_system();
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x < (unsigned)a.world) {
+        unsigned* f = peer_flags(a.peer[threadIdx.x], a.peerMaxN, a.maxGrid) + a.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(f), "r"(seq) : "memory");
+    }
+    if (threadIdx.x < (unsigned)a.world) {
+        const unsigned* f = peer_flags(a.peer[a.rank], a.peerMaxN, a.maxGrid) + threadIdx.x;
+        unsigned v, spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (++spins > (1u << 27)) __trap();                 // a missing rank must not hang the device
+        } while ((int)(v - seq) < 0);
+    }
+    __syncthreads();
+}
 
 template <bool kCluster, int kThreads>
 __global__ void __launch_bounds__(kThreads)
@@ -471,6 +505,7 @@ gn_iteration_kernel(const GnArgs a) {
     grid.sync();
     float rDotzOld = grid_sum_after_sync(a.partials + a.maxGrid, gridDim.x, sRed);
 
+    const bool peerMode = !kCluster && a.world > 1;
     // (3) PCG iterations (SolverBundling.cu:1024-1108): rows are dealt to warps; lanes split a row's segments
     const unsigned warpsPerBlock = blockDim.x / 32, gwarp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nwarps = gridDim.x * warpsPerBlock;
     const unsigned lane = threadIdx.x & 31;
@@ -486,9 +521,12 @@ gn_iteration_kernel(const GnArgs a) {
         const bool fly = lin > 0;
         float* const curR = (lin & 1) ? a.p2Rot : a.pRot;   float* const curT = (lin & 1) ? a.p2Trans : a.pTrans;    // p_k of the rows this thread owns
         const float* const prvR = (lin & 1) ? a.pRot : a.p2Rot; const float* const prvT = (lin & 1) ? a.pTrans : a.p2Trans;    // p_{k-1}, complete
-        // A: Ap = H p, partial p.Ap
+        // A: Ap = H p, partial p.Ap.  Sharded: this rank's rows only (v = rank + world k), each result stored into every rank's exchange region.
         float pAp = 0.0f;
-        for (unsigned v = 1 + gwarp; v < N; v += nwarps) {
+        const unsigned par = lin & 1u;
+        for (unsigned kRow = gwarp; ; kRow += nwarps) {
+            const unsigned v = peerMode ? (unsigned)a.rank + (unsigned)a.world * (kRow + (a.rank == 0 ? 1u : 0u)) : 1u + kRow;
+            if (v >= N) break;
             const int ns = a.segCount[v], rs = a.rowStart[v];
             float y[6] = { 0, 0, 0, 0, 0, 0 };
             for (int sI = lane; sI < ns; sI += 32) {
@@ -521,7 +559,7 @@ gn_iteration_kernel(const GnArgs a) {
             if (lane == 0) {
                 const V3 pr = fly ? ld3(a.zRot, v) + ld3(prvR, v) * beta : ld3(a.pRot, v);
                 const V3 pt = fly ? ld3(a.zTrans, v) + ld3(prvT, v) * beta : ld3(a.pTrans, v);
-                if (fly) { st3(curR, v, pr); st3(curT, v, pt); }
+                if (fly && !peerMode) { st3(curR, v, pr); st3(curT, v, pt); }       // sharded: step B forms and stores p_k for every row itself
                 blk_mv(&a.diagBlk[36 * (size_t)v], pr, pt, y);
                 if (denseOn) {
                     const float* D = &a.denseDiag[36 * (size_t)v];
@@ -531,23 +569,53 @@ gn_iteration_kernel(const GnArgs a) {
                         y[r] += D[(3 + r) * 6 + 0] * pt.x + D[(3 + r) * 6 + 1] * pt.y + D[(3 + r) * 6 + 2] * pt.z + D[(3 + r) * 6 + 3] * pr.x + D[(3 + r) * 6 + 4] * pr.y + D[(3 + r) * 6 + 5] * pr.z;
                     }
                 }
-                st3(a.ApRot, v, mk(y[0], y[1], y[2])); st3(a.ApTrans, v, mk(y[3], y[4], y[5]));
+                if (!peerMode) { st3(a.ApRot, v, mk(y[0], y[1], y[2])); st3(a.ApTrans, v, mk(y[3], y[4], y[5])); }
+                else
+                    for (int g = 0; g < a.world; ++g) {           // 24 bytes per row and rank over NVLink; ordered before the flag by the fence in peer_barrier
+                        float* ap = peer_ap(a.peer[g], a.peerMaxN, par);
+                        st3(ap, v, mk(y[0], y[1], y[2])); st3(ap + 3 * (size_t)a.peerMaxN, v, mk(y[3], y[4], y[5]));
+                    }
                 pAp += pr.x * y[0] + pr.y * y[1] + pr.z * y[2] + pt.x * y[3] + pt.y * y[4] + pt.z * y[5];
             }
         }
         pAp = block_sum(pAp, sRed);
-        if (threadIdx.x == 0) a.partials[blockIdx.x] = pAp;
-        grid.sync();
-        const float dotProduct = grid_sum_after_sync(a.partials, gridDim.x, sRed);
+        float dotProduct;
+        if (!peerMode) {
+            if (threadIdx.x == 0) a.partials[blockIdx.x] = pAp;
+            grid.sync();
+            dotProduct = grid_sum_after_sync(a.partials, gridDim.x, sRed);
+        } else {
+            if (threadIdx.x < (unsigned)a.world) peer_partials(a.peer[threadIdx.x], a.peerMaxN, a.maxGrid, par)[(size_t)a.rank * a.maxGrid + blockIdx.x] = pAp;   // pAp is uniform in the CTA
+            peer_barrier(a, a.seqBase + lin + 1u, grid);
+            // every rank adds the same world x grid partial sums in the same order: identical bits everywhere
+            const float* pp = peer_partials(a.peer[a.rank], a.peerMaxN, a.maxGrid, par);
+            if (threadIdx.x < 32) {
+                float acc = 0.0f;
+                for (unsigned e = threadIdx.x; e < (unsigned)a.world * gridDim.x; e += 32) acc += __ldcg(&pp[(size_t)(e / gridDim.x) * a.maxGrid + (e % gridDim.x)]);
+                acc = warp_sum(acc);
+                if (threadIdx.x == 0) sRed[0] = acc;
+            }
+            __syncthreads();
+            dotProduct = sRed[0];
+            __syncthreads();
+        }
         // B: step, residual, preconditioned residual, partial z.r
         float alpha = 0.0f;
         if (dotProduct > BF_FLOAT_EPSILON) alpha = rDotzOld / dotProduct;
         float zr = 0.0f;
+        const float* const apR = peerMode ? peer_ap(a.peer[a.rank], a.peerMaxN, par) : a.ApRot;
+        const float* const apT = peerMode ? peer_ap(a.peer[a.rank], a.peerMaxN, par) + 3 * (size_t)a.peerMaxN : a.ApTrans;
         for (unsigned v = tid; v < N; v += nth) {
             if (v == 0) continue;
-            st3(a.deltaRot, v, ld3(a.deltaRot, v) + ld3(curR, v) * alpha);
-            st3(a.deltaTrans, v, ld3(a.deltaTrans, v) + ld3(curT, v) * alpha);
-            const V3 rR = ld3(a.rRot, v) - ld3(a.ApRot, v) * alpha, rT = ld3(a.rTrans, v) - ld3(a.ApTrans, v) * alpha;
+            V3 pkR, pkT;
+            if (peerMode) {      // the expression the mat-vec read: p_k = z + beta p_{k-1}, materialised here for every row (the owner-only store does not reach the other ranks)
+                pkR = fly ? ld3(a.zRot, v) + ld3(prvR, v) * beta : ld3(a.pRot, v);
+                pkT = fly ? ld3(a.zTrans, v) + ld3(prvT, v) * beta : ld3(a.pTrans, v);
+                if (fly) { st3(curR, v, pkR); st3(curT, v, pkT); }
+            } else { pkR = ld3(curR, v); pkT = ld3(curT, v); }
+            st3(a.deltaRot, v, ld3(a.deltaRot, v) + pkR * alpha);
+            st3(a.deltaTrans, v, ld3(a.deltaTrans, v) + pkT * alpha);
+            const V3 rR = ld3(a.rRot, v) - V3(mk(__ldcg(&apR[3 * v]), __ldcg(&apR[3 * v + 1]), __ldcg(&apR[3 * v + 2]))) * alpha, rT = ld3(a.rTrans, v) - V3(mk(__ldcg(&apT[3 * v]), __ldcg(&apT[3 * v + 1]), __ldcg(&apT[3 * v + 2]))) * alpha;
             st3(a.rRot, v, rR); st3(a.rTrans, v, rT);
             const V3 zR = mulv(ld3(a.precRot, v), rR), zT = mulv(ld3(a.precTrans, v), rT);
             st3(a.zRot, v, zR); st3(a.zTrans, v, zT);
@@ -1089,6 +1157,9 @@ static int run_gn(const BFSolverInput* in, const BFSolverState* st, const BFSolv
     const float wDepth = in->weightsDenseDepth ? in->weightsDenseDepth[nIter] : 0.0f, wColor = in->weightsDenseColor ? in->weightsDenseColor[nIter] : 0.0f;
     const bool dense = (wDepth > 0.0f || wColor > 0.0f) && in->d_cacheFrames != nullptr;
     a.dnbrStart = nullptr; a.dnbr = nullptr; a.pairOut = nullptr; a.denseDiag = nullptr; a.denseJtr = nullptr; a.useDense = dense ? 1 : 0;
+    a.rank = ws->rank; a.world = ws->world; a.seqBase = ws->peerSeq; a.peerMaxN = ws->maxImages;
+    for (int g = 0; g < BF_SOLVER_MAX_PEERS; ++g) a.peer[g] = ws->peer[g];
+    if (ws->world > 1) ws->peerSeq += par->nLinIterations + 2;          // every rank launches the same sequence: the numbers agree
     if (dense) {
         { const int rc = ensure_dense(ws); if (rc) return rc; }
         a.dnbrStart = ws->dnbrStart; a.dnbr = ws->dnbr; a.pairOut = ws->pairOut; a.denseDiag = ws->denseDiag; a.denseJtr = ws->denseJtr;
@@ -1236,6 +1307,48 @@ BF_API int bfSolverReleaseWorkspace(const BFSolverState* st) {
     if (it == g_ws.end()) return 0;
     free_ws(it->second);
     g_ws.erase(it);
+    return 0;
+}
+
+// ---- sharded solve over the GPUs of one box ---------------------------------------------------------------------------------------------------------
+BF_API int bfSolverPeerCreate(const BFSolverState* st, unsigned int maxImages, unsigned int maxCorr, void* ipcHandleOut64) {
+    SolverWs* ws;
+    unsigned cap = 1024;
+    while (cap < maxCorr) cap <<= 1;
+    int rc = get_ws(st, maxImages, cap, &ws);
+    if (rc) return rc;
+    if (!ws->region) {
+        const size_t bytes = sizeof(float) * peer_region_floats(ws->maxImages, ws->maxGrid);
+        BF_CHECK(cudaMalloc(&ws->region, bytes));
+        BF_CHECK(cudaMemset(ws->region, 0, bytes));
+    }
+    cudaIpcMemHandle_t h;
+    BF_CHECK(cudaIpcGetMemHandle(&h, ws->region));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(ipcHandleOut64, &h, 64);
+    return 0;
+}
+BF_API int bfSolverPeerConnect(const BFSolverState* st, int rank, int world, const void* ipcHandles) {
+    SolverWs* ws = nullptr;
+    { std::lock_guard<std::mutex> lk(g_wsMutex); auto it = g_ws.find(st->d_deltaRot); if (it != g_ws.end()) ws = &it->second; }
+    if (!ws || !ws->region || world < 1 || world > BF_SOLVER_MAX_PEERS || rank < 0 || rank >= world) return (int)cudaErrorInvalidValue;
+    for (int g = 0; g < world; ++g) {
+        if (g == rank) { ws->peer[g] = ws->region; continue; }
+        cudaIpcMemHandle_t h; memcpy(&h, static_cast<const char*>(ipcHandles) + 64 * (size_t)g, 64);
+        void* p = nullptr;
+        BF_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ws->peer[g] = static_cast<float*>(p); ws->peerOpened[g] = true;
+    }
+    ws->rank = rank; ws->world = world; ws->peerSeq = 0;
+    return 0;
+}
+BF_API int bfSolverPeerDisconnect(const BFSolverState* st) {
+    SolverWs* ws = nullptr;
+    { std::lock_guard<std::mutex> lk(g_wsMutex); auto it = g_ws.find(st->d_deltaRot); if (it != g_ws.end()) ws = &it->second; }
+    if (!ws) return 0;
+    BF_CHECK(cudaStreamSynchronize(stream()));
+    for (int g = 0; g < BF_SOLVER_MAX_PEERS; ++g) { if (ws->peerOpened[g]) { cudaIpcCloseMemHandle(ws->peer[g]); ws->peerOpened[g] = false; } ws->peer[g] = nullptr; }
+    ws->rank = 0; ws->world = 1;
     return 0;
 }
 

@@ -45,6 +45,7 @@ class CUDASolverBundling:
             raise RuntimeError("CUDASolverBundling needs a CUDA device (no CPU fallback)")
         self.lib = capi.lib()
         self.m_maxNumberOfImages = maxNumberOfImages
+        self.m_maxNumResiduals = maxNumResiduals
         self.m_maxCorrPerImage = int(min(max(maxNumResiduals // maxNumberOfImages, 1000), 4000))   # cpp:39
         self.m_verifyOptDistThresh, self.m_verifyOptPercentThresh = 0.02, 0.05                       # cpp:35-36
         self.m_maxResidualThresh = max_res_thresh                                                    # s_optMaxResThresh
@@ -142,6 +143,24 @@ class CUDASolverBundling:
             out = self.d_maxOut.cpu().numpy()
             self._maxRes = (float(out[0]), int(out[1:2].view(np.int32)[0]))
         self._last = (si, par)
+
+    def connect_peers(self, group=None):
+        """Shard this solver's PCG over the ranks of a torch.distributed group (one process per GPU of one box): exchange regions are opened through
+        CUDA IPC, rows are dealt to the ranks, every rank then calls solve() with identical inputs (include/bf_solver.h: bfSolverPeer*)."""
+        import torch.distributed as dist
+        self._bind_stream()
+        h = (C.c_char * 64)()
+        capi.check(self.lib.bfSolverPeerCreate(C.byref(self.m_solverState), C.c_uint(self.m_maxNumberOfImages), C.c_uint(self.m_maxNumResiduals), h), "bfSolverPeerCreate")
+        world = dist.get_world_size(group); rank = dist.get_rank(group)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h.raw), group=group)
+        blob = b"".join(handles)
+        capi.check(self.lib.bfSolverPeerConnect(C.byref(self.m_solverState), rank, world, blob), "bfSolverPeerConnect")
+        dist.barrier(group=group)
+        return rank, world
+
+    def disconnect_peers(self):
+        capi.check(self.lib.bfSolverPeerDisconnect(C.byref(self.m_solverState)), "bfSolverPeerDisconnect")
 
     def getMaxResidual(self):
         """(max residual, correspondence index), cpp:41-44."""

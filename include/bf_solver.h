@@ -183,6 +183,19 @@ int bfSolverReleaseWorkspace(const BFSolverState* state);
  * (FL/Solver/SolverBundling.cu:308-471).  Either output may be NULL.  Asynchronous device-to-device copies. */
 int bfSolverDebugDenseSystem(const BFSolverState* state, unsigned int numberOfImages, float* d_JtJ, float* d_Jtr);
 
+/* ---- one solve sharded over the GPUs of a box (one process per GPU) ----
+ * The rows of the block-sparse J^T J are dealt to the ranks (row v to rank v mod world).  Inside the persistent PCG kernel a rank computes (J^T J p)(v)
+ * for its rows only and stores each 6-vector straight into every rank's exchange buffer over NVLink (peer stores), with its partial p.Ap sums; one
+ * barrier across the GPUs per iteration (release / acquire flags in peer memory), after which every rank holds the whole vector and forms the same
+ * dot products in the same order -- the replicated state (poses, residuals, directions) stays bit-identical on all ranks, no further exchange, and the
+ * 6N pose update is everywhere when the kernel ends.  What is replicated: the per-iteration vector updates (6N) and the per-GN-iteration block build.
+ * Set-up, once per solver object (all ranks, same sizes): bfSolverPeerCreate -> all-gather the 64-byte handles (e.g. torch.distributed) ->
+ * bfSolverPeerConnect(rank, world, handles[world][64]).  Every rank then calls bfSolverSolve with IDENTICAL inputs.  Requires peer access between the
+ * devices (NVLink / NVSwitch) and world <= 8.  The sparse term only is sharded (the dense term's rows follow the same ownership). */
+int bfSolverPeerCreate(const BFSolverState* state, unsigned int maxImages, unsigned int maxCorrespondences, void* ipcHandleOut64);
+int bfSolverPeerConnect(const BFSolverState* state, int rank, int world, const void* ipcHandles);
+int bfSolverPeerDisconnect(const BFSolverState* state);
+
 #ifdef __cplusplus
 }
 #endif
