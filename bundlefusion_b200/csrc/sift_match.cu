@@ -78,9 +78,9 @@ __device__ __forceinline__ void finish_feature(const SiftJobDev& job, int r, con
 }
 // The reference appends its matches with an atomicAdd: beyond the 128-slot cap the kept subset depends on the scheduling.  Here the job's last
 // CTA to finish compacts the per-feature results in ascending image-2 feature: the first 128 are kept, the counter still holds the total.
-// Any block of <= 8 warps (all of them call); ctasOfJob: CTAs of this launch that work on the job.
+// Any block of <= 16 warps (all of them call); ctasOfJob: CTAs of this launch that work on the job.
 __device__ __forceinline__ void compact_job(const SiftJobDev& job, int ctasOfJob) {
-    __shared__ int sLast, sWarp[8];
+    __shared__ int sLast, sWarp[16];
     const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5, nWarps = blockDim.x >> 5;
     const int nA = job.nA;
     __threadfence();
@@ -382,7 +382,8 @@ sift_best_tc_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ra
 }
 
 // ---- tcgen05 + TMA version: warp-specialised ---------------------------------------------------------------------------------------------------
-// 160 threads: warps 0-3 own the 128 features (thread = TMEM lane) and do nothing but read accumulators back and keep best / second best; warp 4's
+// 288 threads: warps 0-7 own the 128 features (thread = TMEM lane; two warps per lane quarter, each reading half of a tile's columns) and do nothing
+// but read accumulators back and keep best / second best; warp 8's
 // first lane is the whole data path -- it asks the TMA unit for the A tile and, four tiles ahead, for the B tiles (cp.async.bulk.tensor.2d straight
 // into the 128-byte-swizzled layout the tensor core reads; rows past the end of a descriptor array arrive as zeros), and issues the four tcgen05.mma
 // of a tile as soon as its bytes have landed and the accumulator buffer is free.  Nobody copies descriptors through registers, nobody waits at a CTA
@@ -401,7 +402,7 @@ __device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* m
 __device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory"); }
 
 template <bool kColumnPass>
-__global__ void __launch_bounds__(160)
+__global__ void __launch_bounds__(288)
 sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float ratiomax) {
     const SiftJobDev job = jobs[blockIdx.y];
     const int nA = job.nA, nB = job.nB;
@@ -420,7 +421,7 @@ sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float r
     if (t == 0) {
         mbar_init(bFullA, 1);
         for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(bFull + 8 * s, 1); mbar_init(bEmpty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bTFull + 8 * b, 1); mbar_init(bTEmpty + 8 * b, 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bTFull + 8 * b, 1); mbar_init(bTEmpty + 8 * b, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -435,7 +436,7 @@ sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float r
     Top2Q st = { 0, 0, 0, 0 };
     const int thirtyTwo = 32 + (nA >> 30);    // 32, opaque to the compiler
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(reinterpret_cast<uint64_t>(job.mapA)) : "memory");
             asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" :: "l"(reinterpret_cast<uint64_t>(job.mapB)) : "memory");
@@ -464,9 +465,9 @@ sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float r
             const int b = j & 1;
             mbar_wait(bTFull + 8 * b, (uint32_t)((j >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem + ((warp * 32u) << 16) + (uint32_t)(b * TC_BN);
+            const uint32_t taddr = tmem + (((warp & 3u) * 32u) << 16) + (uint32_t)(b * TC_BN);       // a warp reaches the 32 TMEM lanes of its index mod 4
 #pragma unroll 1
-            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            for (int c0 = (int)(warp >> 2) * 64; c0 < (int)(warp >> 2) * 64 + 64; c0 += 32) {          // warps 0-3: columns 0-63 of the tile, warps 4-7: 64-127
                 uint32_t v[32];
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
@@ -484,7 +485,17 @@ sift_best_tma_kernel(const SiftJobDev* __restrict__ jobs, float distmax, float r
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
-    if (t < TC_BM) finish_feature<kColumnPass>(job, row0 + (int)t, top2q_finish<kColumnPass>(st), distmax, ratiomax);
+    // a feature's two halves (threads t and t + 128) become one state: larger key wins, equal keys -> the earlier slice; second = largest of the rest
+    __shared__ Top2Q sHalf[TC_BM];
+    if (t >= TC_BM && t < 2 * TC_BM) sHalf[t - TC_BM] = st;
+    __syncthreads();
+    if (t < TC_BM) {
+        const Top2Q o = sHalf[t];
+        const bool gt = (o.kBest > st.kBest) | ((o.kBest == st.kBest) & (o.slice < st.slice));
+        st.s2 = max(max(st.s2, o.s2), min(st.bBest, o.bBest));
+        st.kBest = gt ? o.kBest : st.kBest; st.bBest = gt ? o.bBest : st.bBest; st.slice = gt ? o.slice : st.slice;
+        finish_feature<kColumnPass>(job, row0 + (int)t, top2q_finish<kColumnPass>(st), distmax, ratiomax);
+    }
     if (kColumnPass) compact_job(job, (nA + TC_BM - 1) / TC_BM);
 }
 
@@ -646,9 +657,9 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
     g_launchCount += 2;
     if (path == 2 && mapsOk) {
         const int gx1 = maxN1 > 0 ? (maxN1 + TC_BM - 1) / TC_BM : 1, gx2 = maxN2 > 0 ? (maxN2 + TC_BM - 1) / TC_BM : 1;
-        sift_best_tma_kernel<false><<<dim3(gx1, numJobs), 160, TMA_SMEM_BYTES, s>>>(g_sift.dJobs, distmax, ratiomax);
+        sift_best_tma_kernel<false><<<dim3(gx1, numJobs), 288, TMA_SMEM_BYTES, s>>>(g_sift.dJobs, distmax, ratiomax);
         BF_CHECK(cudaGetLastError());
-        sift_best_tma_kernel<true><<<dim3(gx2, numJobs), 160, TMA_SMEM_BYTES, s>>>(g_sift.dJobs + numJobs, distmax, ratiomax);
+        sift_best_tma_kernel<true><<<dim3(gx2, numJobs), 288, TMA_SMEM_BYTES, s>>>(g_sift.dJobs + numJobs, distmax, ratiomax);
         BF_CHECK(cudaGetLastError());
     } else if (path >= 1) {
         const int gx1 = maxN1 > 0 ? (maxN1 + TC_BM - 1) / TC_BM : 1, gx2 = maxN2 > 0 ? (maxN2 + TC_BM - 1) / TC_BM : 1;
