@@ -762,7 +762,7 @@ def run_reference(args):
     wall = time.perf_counter() - t0
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
            "steps": K, "warmup": Wm, "ms_per_step": round(1e3 / base["value"], 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, note="CPU arm: oracle port of the reference algorithm on the host cores (the reference ships no CPU path of its own; its CUDA path, rebuilt for sm_100a, is timed on the same box in profiles/r1_reference_cuda_same_box.md)"),
+           "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, note="CPU arm: oracle port of the reference algorithm on the host cores (the reference ships no CPU path of its own; its CUDA path, rebuilt for sm_100a, is timed in the default arm's `reference_cuda` entry).  It covers the TSDF + bundle-adjustment SHARE of the default arm's step only -- 1 integrate + 10 re-integrations + GC per frame, one local and one global solve per 10 frames -- not ingest / SIFT detection / matching / filters, which the default arm's frame loop also runs: the ratio to this arm understates the CPU cost of the same work"),
            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": round(wall, 1)}
     print(json.dumps(out))
 
