@@ -352,7 +352,8 @@ def run_loop(args):
         dist.init_process_group("nccl", device_id=dev)
     L = capi.lib()
     K, Wm, pre = args.steps, args.warmup, args.preroll
-    total = pre + Wm + 3 * K                       # pre-roll, warm-up, timed pass, profiled pass, end-to-end pass: one continuous stream
+    Kp = max(K, 100)                               # the profiled pass (roofline of the stencil, stage times) always covers >= 100 launches, whatever --steps
+    total = pre + Wm + 2 * K + Kp                  # pre-roll, warm-up, timed pass, profiled pass, end-to-end pass: one continuous stream
     P = default_params(W, H)
     P.maxNumFrames = total + 8
     P.maxNumImages = total // 10 + 8
@@ -372,7 +373,8 @@ def run_loop(args):
         d, c, _ = synth_gpu.make_frames(idx, W, H, device=str(dev), texture="rich")
         depth[s0:s0 + len(idx)] = d; color[s0:s0 + len(idx)] = c
     torch.cuda.synchronize()
-    f_e2e0 = pre + Wm + 2 * K
+    f_e2e0 = pre + Wm + K + Kp
+    ahead = os.environ.get("BF_LOOP_AHEAD", "1") != "0"      # bfFrameLoopStepAhead: frame k + 1 of a pass is announced while frame k is stepped
     h_depth = depth[f_e2e0:f_e2e0 + K].cpu().pin_memory(); h_color = color[f_e2e0:f_e2e0 + K].cpu().pin_memory()
     stats = {"valid": 0, "local": 0, "local_valid": 0, "global": 0, "reint": 0, "kp": 0, "n": 0}
 
@@ -386,7 +388,7 @@ def run_loop(args):
         stats["local"] += 1 if st.localSolved >= 0 else 0; stats["local_valid"] += st.localValid; stats["global"] += st.globalSolved
 
     for f in range(pre):                                   # pre-roll: the state a long stream is in (keyframes, trajectory, populated hash)
-        st = loop.step(depth[f], color[f])
+        st = loop.step(depth[f], color[f], *((depth[f + 1], color[f + 1]) if ahead and f + 1 < pre else (None, None)))
         if args.trace:
             note(st)
     torch.cuda.synchronize()
@@ -401,7 +403,11 @@ def run_loop(args):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for k in range(n):
-            st = loop.step(h_depth[k], h_color[k]) if e2e else loop.step(depth[f0 + k], color[f0 + k])
+            la = ahead and not profile and k + 1 < n       # look-ahead stays inside the pass: its first frame is never prefetched, its last announces nothing
+            if e2e:
+                st = loop.step(h_depth[k], h_color[k], *((h_depth[k + 1], h_color[k + 1]) if la else (None, None)))
+            else:
+                st = loop.step(depth[f0 + k], color[f0 + k], *((depth[f0 + k + 1], color[f0 + k + 1]) if la else (None, None)))
             if not profile:
                 note(st)
         loop.join()                                        # the timed region covers the reconstruction stream's work of its last frame
@@ -424,7 +430,7 @@ def run_loop(args):
     c_before = loop.counters()
     prev_lanes = L.bfTsdfSetLanes(0)                       # the stencil is timed alone on its stream: the burst HBM peak is its roof
     loop.set_profiling(True)
-    timed(pre + Wm + K, K, False, True)
+    timed(pre + Wm + K, Kp, False, True)
     stages = loop.stage_times()
     loop.set_profiling(False)
     L.bfTsdfSetLanes(prev_lanes)
@@ -481,8 +487,10 @@ def run_loop(args):
                 "frames_with_pose": stats_e2e["valid"], "local_solves": stats_e2e["local"], "global_solves": stats_e2e["global"],
                 "note": "bfFrameLoopStep with HOST (pinned) depth + colour pointers: the upload happens inside the call, as CUDAImageManager::process uploads on arrival; read back per step: the status block (pose of the frame), the SIFT pose and the match verdict"},
         "gpu_launches": int(launches), "roofline": roof, "tsdf_arithmetic": "fast",
-        "streams": "two (bundling on the library stream, reconstruction on the loop's second stream; events keep the single-threaded order's dependencies)" if overlap else "one",
-        "stages_ms_per_step": dict(stages, note="profiled pass (one extra host synchronisation per step, TSDF lanes off): device time line between stage boundaries, mean per step"),
+        "streams": ("three" if ahead and overlap else "two" if ahead or overlap else "one") + " (bundling on the library stream" + ("; reconstruction on the loop's second stream" if overlap else "") +
+                   ("; the NEXT frame's upload / ingest / SIFT detection / dense cache on the loop's feature stream (bfFrameLoopStepAhead, frames announced inside a pass only)" if ahead else "") +
+                   "; events keep the single-threaded order's dependencies, results identical: tests/test_frame_loop_gpu.py)",
+        "stages_ms_per_step": dict(stages, note="profiled pass (>= 100 steps, serial on one stream, one extra host synchronisation per step, TSDF lanes off): device time line between stage boundaries, mean per step"),
         "clocks": summarize_clocks(clk_lines[clk_mark0:clk_mark1]), "clocks_profile_pass": summarize_clocks(clk_lines[clk_mark1:clk_mark2]),
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -240,6 +240,14 @@ struct Loop {
     // reconstruction stream: the TSDF work of frame f runs beside process() of frame f and processInput() of frame f + 1, as the reference's
     // reconstruction and bundling threads do; the data dependencies of the single-threaded order are kept by events
     cudaStream_t tsdfStream = nullptr; cudaEvent_t evMain = nullptr, evTsdf = nullptr; bool overlap = false, tsdfPending = false;
+    // feature stream (bfFrameLoopStepAhead): upload, ingest, SIFT detection and dense cache of frame f + 1 are queued on a third stream while frame f is
+    // matched, solved and fused -- the hand-over the reference makes between CUDAImageManager::process on the reconstruction thread and the bundling
+    // thread (RUN_MULTITHREADED).  Destinations of that work (frame store slot, key / descriptor slot, cache slot of the chunk the frame will belong
+    // to) are fixed by host state alone, so they are known one frame early; nothing frame f still reads is written.
+    cudaStream_t featStream = nullptr; cudaEvent_t evStepStart = nullptr, evFeat = nullptr; bool featUsed = false;
+    struct Ahead { bool valid = false; unsigned frame = 0; const float* depth = nullptr; const uint8_t* color = nullptr; Bundler* b = nullptr; unsigned li = 0; } ahead;
+    bool aheadWanted = false, aheadArmed = false; const float* nextDepth = nullptr; const uint8_t* nextColor = nullptr; int nextOnHost = 0;
+    Bundler* aheadTarget = nullptr; unsigned aheadLi = 0;
     // stage profile (bfFrameLoopSetProfiling): events at the stage boundaries of a step, elapsed times summed per stage
     bool profile = false; cudaEvent_t stageEv[BF_FRAMELOOP_STAGES + 1] = {}; bool stageHit[BF_FRAMELOOP_STAGES + 1] = {}; double stageMs[BF_FRAMELOOP_STAGES] = {}; unsigned long long profiledSteps = 0;
 };
@@ -258,7 +266,10 @@ static void stage_collect(Loop& L) {
     ++L.profiledSteps;
 }
 
-static int sync_stream(Loop& L) { ++L.counters[6]; BF_CHECK(cudaStreamSynchronize(stream())); return 0; }
+static const int PIN_FEAT = 3072;            // h_pin slot the feature stream's key-point count lands in (h_pin: 4096 ints; 16 .. 2016 carry valid flags)
+static int launch_ahead(Loop& L);
+// every host wait on the library stream: if the next frame's feature work is armed, it is queued first, so that it runs while the host waits
+static int sync_stream(Loop& L) { if (L.aheadArmed) FL_OK(launch_ahead(L)); ++L.counters[6]; BF_CHECK(cudaStreamSynchronize(stream())); return 0; }
 
 // ---- Bundler::matchAndFilter (FL/Bundler.cpp:103-249) ----------------------------------------------------------------------------------------
 // returns lastMatchedFrame (or -1) in *lastMatched; one host synchronisation at the end (verdict + correspondence count)
@@ -461,11 +472,17 @@ static void prepare_local_solve(Loop& L, unsigned curFrame, bool isSequenceEnd) 
     std::swap(L.pLocal, L.pOptLocal);
 }
 
-// OnlineBundler::processInput (FL/OnlineBundler.cpp:167-227) for a NEW frame whose raw images are in d_depthRaw / d_colorRaw
-static int process_input(Loop& L, unsigned curFrame) {
+// The device work of a new frame that depends on nothing but the frame itself -- CUDAImageManager::process (FL/CUDAImageManager.cpp:22-158: upload,
+// erode + filter + resample into the frame store), getCurrentFrame's intensity image, Bundler::detectFeatures (FL/Bundler.cpp:91-101) into key slot
+// `li` of bundler `b`, Bundler::storeCachedFrame -- queued on the CURRENT library stream; the key-point count is copied to *h_count (pinned).
+static int front_half(Loop& L, unsigned frame, const float* depth, const uint8_t* color, int onHost, Bundler& b, unsigned li, int* h_count) {
     const BFFrameLoopParams& P = L.P;
-    const bool isLastLocal = is_last_local_frame(L, curFrame);
-    Bundler& loc = *L.pLocal;
+    const size_t dB = sizeof(float) * (size_t)P.depthWidth * P.depthHeight, cB = (size_t)4 * P.colorWidth * P.colorHeight;
+    BF_CHECK(cudaMemcpyAsync(L.d_depthRaw, depth, dB, onHost ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream()));
+    BF_CHECK(cudaMemcpyAsync(L.d_colorRaw, color, cB, onHost ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream()));
+    FL_OK(bfIngestFrame(&L.ingest, L.d_depthRaw, L.d_colorRaw, L.d_frameDepth[frame], L.d_frameColor[frame]));
+    float* depthFilt = L.d_frameDepth[frame];
+    if (L.needSensorResFilter) { FL_OK(bfIngestFrame(&L.ingestSensorRes, L.d_depthRaw, L.d_colorRaw, L.d_depthFilt, L.d_colorRaw)); depthFilt = L.d_depthFilt; }
     // getCurrentFrame: intensity at SIFT resolution
     {
         dim3 blk(16, 16), grd((P.siftWidth + 15) / 16, (P.siftHeight + 15) / 16);
@@ -473,16 +490,34 @@ static int process_input(Loop& L, unsigned curFrame) {
         BF_CHECK(cudaGetLastError()); ++g_launchCount;
     }
     mark(L, 1);
-    // detectFeatures (FL/Bundler.cpp:91-101): keys of the new local image
-    const unsigned li = loc.sm.numImages;
-    FL_OK(bfSiftDetect(&L.detect, L.d_intensity, L.d_depthFilt, loc.sm.keysOf(li), loc.sm.descsOf(li), loc.sm.d_numKeys + li, nullptr));
-    BF_CHECK(cudaMemcpyAsync(L.h_pin, loc.sm.d_numKeys + li, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    FL_OK(bfSiftDetect(&L.detect, L.d_intensity, depthFilt, b.sm.keysOf(li), b.sm.descsOf(li), b.sm.d_numKeys + li, nullptr));
+    BF_CHECK(cudaMemcpyAsync(h_count, b.sm.d_numKeys + li, sizeof(int), cudaMemcpyDeviceToHost, stream()));
     mark(L, 2);
-    // storeCachedFrame
-    FL_OK(loc.cache.storeFrame(L.d_depthRaw, L.d_colorRaw));
-    FL_OK(sync_stream(L));
-    mark(L, 3);
-    const int nk = std::min(L.h_pin[0], (int)P.maxNumKeysPerImage);
+    FL_OK(b.cache.storeFrame(L.d_depthRaw, L.d_colorRaw));
+    return 0;
+}
+
+// the front half of the NEXT frame on the feature stream (armed by bfFrameLoopStepAhead once this frame's bookkeeping has fixed the destinations)
+static int launch_ahead(Loop& L) {
+    L.aheadArmed = false;
+    cudaStream_t mainStream = stream();
+    BF_CHECK(cudaStreamWaitEvent(L.featStream, L.evStepStart, 0));      // after everything the library stream held when this step began (earlier users of the slots)
+    bfSetStream(L.featStream);
+    int rc = front_half(L, L.numFrames, L.nextDepth, L.nextColor, L.nextOnHost, *L.aheadTarget, L.aheadLi, L.h_pin + PIN_FEAT);
+    if (!rc) { const cudaError_t e = cudaEventRecord(L.evFeat, L.featStream); if (e != cudaSuccess) { set_last_error("frame loop: cudaEventRecord(evFeat)", e); rc = (int)e; } }
+    bfSetStream(mainStream);
+    if (rc) return rc;
+    L.ahead.valid = true; L.ahead.frame = L.numFrames; L.ahead.depth = L.nextDepth; L.ahead.color = L.nextColor; L.ahead.b = L.aheadTarget; L.ahead.li = L.aheadLi;
+    L.featUsed = true;
+    return 0;
+}
+
+// OnlineBundler::processInput (FL/OnlineBundler.cpp:167-227) for a NEW frame whose features (key slot of the current chunk, `nk` of them) and cache frame are in place
+static int process_input(Loop& L, unsigned curFrame, int nkDetected) {
+    const BFFrameLoopParams& P = L.P;
+    const bool isLastLocal = is_last_local_frame(L, curFrame);
+    Bundler& loc = *L.pLocal;
+    const int nk = std::min(nkDetected, (int)P.maxNumKeysPerImage);
     loc.sm.addImage(nk);
     L.status.numKeyPoints = (unsigned)nk;
     const unsigned curLocalFrame = loc.sm.curFrame;
@@ -494,6 +529,12 @@ static int process_input(Loop& L, unsigned curFrame) {
         BF_CHECK(cudaMemcpyAsync(o.sm.d_numKeys + oi, loc.sm.d_numKeys + curLocalFrame, sizeof(int), cudaMemcpyDeviceToDevice, stream()));
         o.sm.addImage(nk);
         FL_OK(o.cache.copyFrom(loc.cache, curLocalFrame));
+    }
+    if (L.aheadWanted) {                                  // where the next frame's features go is settled: the chunk that will be current, its next slot
+        L.aheadWanted = false;
+        L.aheadTarget = isLastLocal ? L.pOptLocal : L.pLocal;           // prepare_local_solve (below) swaps the two on a chunk's last frame
+        L.aheadLi = L.aheadTarget->sm.numImages;
+        L.aheadArmed = true;                               // queued at the first host wait of this step (sync_stream), or at the end of this function
     }
     L.lastFrameValid = true;
     L.status.lastMatchedFrame = -1;
@@ -515,6 +556,7 @@ static int process_input(Loop& L, unsigned curFrame) {
             memcpy(L.currIntegrate, L.h_pin + 32, 64);
         }
     } else if (curFrame == 0) mat_identity(L.currIntegrate);
+    if (L.aheadArmed) FL_OK(launch_ahead(L));
     if (isLastLocal) prepare_local_solve(L, curFrame, false);
     L.lastFrameProcessed = (int)curFrame;
     mark(L, 4);
@@ -718,6 +760,7 @@ static int reconstruct(Loop& L, bool gotFrame, unsigned curFrame) {
 // the main stream waits for the reconstruction stream (asynchronously): before anything on it reads the voxel hash, and at the end of a timed region
 static int join_tsdf(Loop& L) {
     if (L.tsdfPending) { BF_CHECK(cudaStreamWaitEvent(stream(), L.evTsdf, 0)); L.tsdfPending = false; }
+    if (L.ahead.valid) BF_CHECK(cudaStreamWaitEvent(stream(), L.evFeat, 0));       // an announced frame's feature work, if any, is covered too
     return 0;
 }
 
@@ -861,9 +904,13 @@ BF_API void bfFrameLoopDestroy(BFFrameLoop* loop) {
     if (!loop) return;
     Loop* L = reinterpret_cast<Loop*>(loop);
     if (L->tsdfStream) cudaStreamSynchronize(L->tsdfStream);
+    if (L->featStream) cudaStreamSynchronize(L->featStream);
     cudaStreamSynchronize(stream());
     bfTsdfReleaseAux(&L->hd);
     if (L->tsdfStream) cudaStreamDestroy(L->tsdfStream);
+    if (L->featStream) cudaStreamDestroy(L->featStream);
+    if (L->evStepStart) cudaEventDestroy(L->evStepStart);
+    if (L->evFeat) cudaEventDestroy(L->evFeat);
     if (L->evMain) cudaEventDestroy(L->evMain);
     if (L->evTsdf) cudaEventDestroy(L->evTsdf);
     bfSolverReleaseWorkspace(&L->local.solver.st); bfSolverReleaseWorkspace(&L->optLocal.solver.st); bfSolverReleaseWorkspace(&L->global.solver.st);
@@ -890,31 +937,69 @@ static int step_common(Loop& L, bool gotFrame, unsigned curFrame, BFFrameLoopSta
     return 0;
 }
 
-BF_API int bfFrameLoopStep(BFFrameLoop* loop, const float* depth, const uint8_t* color, int onHost, BFFrameLoopStatus* status) {
-    if (!loop || !depth || !color) return (int)cudaErrorInvalidValue;
-    Loop& L = *reinterpret_cast<Loop*>(loop);
+static int ensure_feature_stream(Loop& L) {
+    if (L.featStream) return 0;
+    int lo = 0, hi = 0;
+    BF_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    BF_CHECK(cudaStreamCreateWithPriority(&L.featStream, cudaStreamNonBlocking, lo));              // below the bundling chain, which stays the latency-critical one
+    BF_CHECK(cudaEventCreateWithFlags(&L.evStepStart, cudaEventDisableTiming));
+    BF_CHECK(cudaEventCreateWithFlags(&L.evFeat, cudaEventDisableTiming));
+    return 0;
+}
+
+static int step_frame(Loop& L, const float* depth, const uint8_t* color, const float* nextDepth, const uint8_t* nextColor, int onHost, BFFrameLoopStatus* status) {
     const BFFrameLoopParams& P = L.P;
     if (L.numFrames >= P.maxNumFrames) return (int)cudaErrorMemoryAllocation;
     const unsigned curFrame = L.numFrames;
     memset(&L.status, 0, sizeof(L.status));
     L.status.frame = curFrame; L.status.localSolved = -1; L.status.lastMatchedFrame = -1;
-    // CUDAImageManager::process (FL/CUDAImageManager.cpp:22-158): upload, erode + filter + resample into the frame store
-    const size_t dB = sizeof(float) * (size_t)P.depthWidth * P.depthHeight, cB = (size_t)4 * P.colorWidth * P.colorHeight;
-    mark(L, 0);
-    BF_CHECK(cudaMemcpyAsync(L.d_depthRaw, depth, dB, onHost ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream()));
-    BF_CHECK(cudaMemcpyAsync(L.d_colorRaw, color, cB, onHost ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream()));
-    FL_OK(bfIngestFrame(&L.ingest, L.d_depthRaw, L.d_colorRaw, L.d_frameDepth[curFrame], L.d_frameColor[curFrame]));
-    if (L.needSensorResFilter) { uint8_t* scratch = L.d_frameColor[curFrame]; (void)scratch; FL_OK(bfIngestFrame(&L.ingestSensorRes, L.d_depthRaw, L.d_colorRaw, L.d_depthFilt, L.d_colorRaw)); }
-    else L.d_depthFilt = L.d_frameDepth[curFrame];
+    Bundler& loc = *L.pLocal;
+    const unsigned li = loc.sm.numImages;
+    int nk = 0;
+    if (L.ahead.valid) {
+        // this frame's front half was queued on the feature stream during the previous step: it must be the frame announced there
+        if (L.ahead.frame != curFrame || L.ahead.depth != depth || L.ahead.color != color || L.ahead.b != &loc || L.ahead.li != li) {
+            set_last_error("bfFrameLoopStep: the frame differs from the one announced as `next` by the previous bfFrameLoopStepAhead", cudaErrorInvalidValue);
+            return (int)cudaErrorInvalidValue;
+        }
+        L.ahead.valid = false;
+        ++L.counters[6];
+        BF_CHECK(cudaEventSynchronize(L.evFeat));                       // the key-point count is on the host, keys / descriptors / cache frame / frame store slot are written
+        nk = L.h_pin[PIN_FEAT];
+    } else {
+        if (L.featUsed) BF_CHECK(cudaStreamWaitEvent(stream(), L.evFeat, 0));          // raw-image buffers and the detector workspace were last used on the feature stream
+        mark(L, 0);
+        FL_OK(front_half(L, curFrame, depth, color, onHost, loc, li, L.h_pin));
+        FL_OK(sync_stream(L));
+        nk = L.h_pin[0];
+    }
+    mark(L, 3);
     ++L.numFrames; ++L.counters[0];
-    FL_OK(process_input(L, curFrame));
+    L.aheadWanted = false; L.aheadArmed = false;
+    if (nextDepth && nextColor && !L.profile && L.numFrames < P.maxNumFrames) {
+        FL_OK(ensure_feature_stream(L));
+        BF_CHECK(cudaEventRecord(L.evStepStart, stream()));
+        L.nextDepth = nextDepth; L.nextColor = nextColor; L.nextOnHost = onHost; L.aheadWanted = true;
+    }
+    FL_OK(process_input(L, curFrame, nk));
     return step_common(L, true, curFrame, status);
+}
+
+BF_API int bfFrameLoopStep(BFFrameLoop* loop, const float* depth, const uint8_t* color, int onHost, BFFrameLoopStatus* status) {
+    if (!loop || !depth || !color) return (int)cudaErrorInvalidValue;
+    return step_frame(*reinterpret_cast<Loop*>(loop), depth, color, nullptr, nullptr, onHost, status);
+}
+
+BF_API int bfFrameLoopStepAhead(BFFrameLoop* loop, const float* depth, const uint8_t* color, const float* nextDepth, const uint8_t* nextColor, int onHost, BFFrameLoopStatus* status) {
+    if (!loop || !depth || !color) return (int)cudaErrorInvalidValue;
+    return step_frame(*reinterpret_cast<Loop*>(loop), depth, color, nextDepth, nextColor, onHost, status);
 }
 
 BF_API int bfFrameLoopStepPastEnd(BFFrameLoop* loop, BFFrameLoopStatus* status) {
     if (!loop) return (int)cudaErrorInvalidValue;
     Loop& L = *reinterpret_cast<Loop*>(loop);
     if (L.numFrames == 0) return (int)cudaErrorInvalidValue;
+    if (L.ahead.valid) { set_last_error("bfFrameLoopStepPastEnd: a frame announced by bfFrameLoopStepAhead is still pending", cudaErrorInvalidValue); return (int)cudaErrorInvalidValue; }
     memset(&L.status, 0, sizeof(L.status));
     L.status.frame = L.numFrames - 1; L.status.localSolved = -1; L.status.lastMatchedFrame = -1;
     process_input_past_end(L);

@@ -2,9 +2,9 @@
 //
 // Behavioural source (what, not how): FL/SiftGPU/SIFTImageManager.cu:186-316 (FilterKeyPointMatchesCU), FL/SiftGPU/cuda_kabsch.h:110-502,
 // FL/SiftGPU/cuda_EigenValue.h:9-39.  The per-pair algorithm is inherently sequential (greedy insertion with re-fits), so, as in the
-// reference, one thread walks a pair's raw matches; pairs run in parallel, one warp-sized CTA each, arrays in shared memory.  The
-// device functions below follow oracle/filter_oracle.c operation for operation (this TU is built -fmad=false), including the reference's
-// own 3x3 SVD (the fast approximate one of cuda_svd3.h, with rsqrt taken as 1 / sqrtf).
+// reference, a pair's raw matches are walked in order; pairs run in parallel, one warp each, arrays in shared memory -- and inside a fit the warp's
+// lanes carry the independent sums (see "The per-pair algorithm on ONE WARP" below), each in the serial order.  The device functions follow
+// oracle/filter_oracle.c operation for operation (this TU is built -fmad=false), including the reference's own 3x3 SVD (the fast approximate one of cuda_svd3.h, with rsqrt taken as 1 / sqrtf).
 #include "../../include/bf_sift.h"
 #include "bf_common.cuh"
 #include "mat4.cuh"
@@ -151,17 +151,19 @@ __device__ void svd3(const float H[9], float U[9], float s[3], float V[9]) {
 /* matNxM<3,3>::det, cuda_SimpleMatrixUtil.h:1544-1559 */
 __device__ float det3(const float m[9]) { return m[0] * m[4] * m[8] + m[1] * m[5] * m[6] + m[2] * m[3] * m[7] - m[6] * m[4] * m[2] - m[7] * m[5] * m[0] - m[8] * m[3] * m[1]; }
 
-/* kabsch(), cuda_kabsch.h:110-176: T (4x4 row-major) with T src ~ tgt; evs = singular values of the covariance, descending */
-__device__ void kabsch(const f3* src, const f3* tgt, unsigned n, float T[16], float evs[3]) {
-    float p0[3] = { 0, 0, 0 }, q0[3] = { 0, 0, 0 };
-    for (unsigned i = 0; i < n; ++i) { p0[0] += src[i].x; p0[1] += src[i].y; p0[2] += src[i].z; q0[0] += tgt[i].x; q0[1] += tgt[i].y; q0[2] += tgt[i].z; }
-    for (int k = 0; k < 3; ++k) { p0[k] /= (float)n; q0[k] /= (float)n; }
-    float H[9] = { 0 };
-    for (unsigned i = 0; i < n; ++i) {
-        const float p[3] = { src[i].x - p0[0], src[i].y - p0[1], src[i].z - p0[2] }, q[3] = { tgt[i].x - q0[0], tgt[i].y - q0[1], tgt[i].z - q0[2] };
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) H[3 * r + c] += p[r] * q[c];
-    }
-    for (int k = 0; k < 9; ++k) H[k] /= (float)n;
+/* ---- The per-pair algorithm on ONE WARP ---------------------------------------------------------------------------------------------------
+ * filterKeyPointMatches (cuda_kabsch.h:417-502) is a greedy loop -- add a match, re-fit, drop the worst while the fit is bad -- and the reference runs
+ * it on one thread per image pair.  The loop is sequential, the work inside a fit is not: the 6 mean components, the 9 covariance entries of the Kabsch
+ * fit, the n residuals, the ranks of the sort, the 2 x 9 covariance entries of the condition test and the `addMatch` distance tests are independent
+ * chains.  Each chain goes to one lane and is evaluated there in the reference's order (ascending point index, one rounding per operation; this TU is
+ * built -fmad=false), so every sum has the bits of the serial evaluation; the 3x3 SVD and the small matrix products run redundantly on all lanes
+ * (uniform, nothing to broadcast).  Control flow is uniform across the warp (decisions come from shared memory or from ballots).  Arrays live in
+ * shared memory, phases are separated by __syncwarp(). */
+#define FULL 0xFFFFFFFFu
+
+/* kabsch(), cuda_kabsch.h:110-176, from the means (p0 | q0) and the covariance H: T (4x4 row-major) with T src ~ tgt; evs = singular values, descending */
+__device__ void kabsch_from_moments(const float m[6], const float H[9], float T[16], float evs[3]) {
+    const float* p0 = m; const float* q0 = m + 3;
     float U[9], V[9];
     svd3(H, U, evs, V);
     { float t; if (evs[0] < evs[1]) { t = evs[0]; evs[0] = evs[1]; evs[1] = t; } if (evs[1] < evs[2]) { t = evs[1]; evs[1] = evs[2]; evs[2] = t; }
@@ -178,87 +180,117 @@ __device__ void kabsch(const f3* src, const f3* tgt, unsigned n, float T[16], fl
     }
     T[12] = T[13] = T[14] = 0.0f; T[15] = 1.0f;
 }
-/* covarianceSVD(), cuda_kabsch.h:178-198 */
-__device__ void covariance_eigs(const f3* pts, unsigned n, float e[3]) {
-    float p0[3] = { 0, 0, 0 };
-    for (unsigned i = 0; i < n; ++i) { p0[0] += pts[i].x; p0[1] += pts[i].y; p0[2] += pts[i].z; }
-    for (int k = 0; k < 3; ++k) p0[k] /= (float)n;
-    float C[9] = { 0 };
-    for (unsigned i = 0; i < n; ++i) {
-        const float p[3] = { pts[i].x - p0[0], pts[i].y - p0[1], pts[i].z - p0[2] };
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C[3 * r + c] += p[r] * p[c];
+__device__ __forceinline__ float f3_get(const f3* p, unsigned i, int c) { return (&p[i].x)[c]; }
+
+/* means of src (lanes 0..2) and tgt (lanes 3..5) over the first n points, every lane gets all six: p0[k] = (((0 + x0) + x1) + ...) / n as the serial loop */
+__device__ __forceinline__ void warp_means(const f3* src, const f3* tgt, unsigned n, unsigned lane, float m[6]) {
+    float acc = 0.0f;
+    if (lane < 6) {
+        const f3* pts = lane < 3 ? src : tgt; const int c = (int)(lane % 3);
+        for (unsigned i = 0; i < n; ++i) acc += f3_get(pts, i, c);
+        acc /= (float)n;
     }
-    for (int k = 0; k < 9; ++k) C[k] /= (float)n;
-    sym_eigenvalues(C, e);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) m[k] = __shfl_sync(FULL, acc, k);
 }
-/* ComputeReprojection(), cuda_kabsch.h:381-414 */
-__device__ int compute_reprojection(f3* src, f3* tgt, unsigned n, float* res, float T[16], uint32_t* idx /*[.][2]*/, float* dist) {
-    float evs[3];
-    kabsch(src, tgt, n, T, evs);
-    for (unsigned i = 0; i < n; ++i) {
-        const float dx = (T[0] * src[i].x + T[1] * src[i].y + T[2] * src[i].z + T[3]) - tgt[i].x;
-        const float dy = (T[4] * src[i].x + T[5] * src[i].y + T[6] * src[i].z + T[7]) - tgt[i].y;
-        const float dz = (T[8] * src[i].x + T[9] * src[i].y + T[10] * src[i].z + T[11]) - tgt[i].z;
-        res[i] = dx * dx + dy * dy + dz * dz;
-    }
-    /* sortKabschResiduals, :368-377: the reference's exchange sort makes ~n^2 / 2 dependent shared-memory round trips per fit.  Its result is the
-     * ascending order; only among EQUAL residuals does the arrangement depend on its particular swap sequence.  So: insertion sort (the list is nearly
-     * sorted from the previous fit: ~n steps), and when two neighbours of the result compare equal, the reference's own sequence from the saved input. */
-    {
-        unsigned char pos[MAX_FILTERED];                                               /* where each element stood before the sort */
-        for (unsigned i = 0; i < n; ++i) pos[i] = (unsigned char)i;
-        for (unsigned i = 1; i < n; ++i) {
-            const float r = res[i]; const f3 a = src[i], b = tgt[i]; const uint32_t ia = idx[2 * i], ib = idx[2 * i + 1]; const float d = dist[i]; const unsigned char pi = pos[i];
-            unsigned j = i;
-            while (j > 0 && res[j - 1] > r) { res[j] = res[j - 1]; src[j] = src[j - 1]; tgt[j] = tgt[j - 1]; idx[2 * j] = idx[2 * j - 2]; idx[2 * j + 1] = idx[2 * j - 1]; dist[j] = dist[j - 1]; pos[j] = pos[j - 1]; --j; }
-            res[j] = r; src[j] = a; tgt[j] = b; idx[2 * j] = ia; idx[2 * j + 1] = ib; dist[j] = d; pos[j] = pi;
+
+/* ComputeReprojection(), cuda_kabsch.h:381-414, on one warp: fit, residuals, sort by residual, condition numbers.  T / the return value are uniform. */
+__device__ int compute_reprojection(f3* src, f3* tgt, unsigned n, float* res, float T[16], uint32_t* idx /*[.][2]*/, float* dist, unsigned lane) {
+    float m[6], H[9], evs[3];
+    __syncwarp();
+    warp_means(src, tgt, n, lane, m);
+    {   /* covariance of the fit (cuda_kabsch.h:121-131): entry (r, c) on lane 3 r + c */
+        float h = 0.0f;
+        if (lane < 9) {
+            const int r = (int)lane / 3, c = (int)lane % 3;
+            for (unsigned i = 0; i < n; ++i) { const float p = f3_get(src, i, r) - m[r], q = f3_get(tgt, i, c) - m[3 + c]; h += p * q; }
+            h /= (float)n;
         }
-        bool tie = false;
-        for (unsigned i = 1; i < n; ++i) tie |= !(res[i] > res[i - 1]);               /* equal (or unordered: NaN) neighbours */
-        if (tie) {
-            f3 s0[MAX_FILTERED], t0[MAX_FILTERED]; float r0[MAX_FILTERED], d0[MAX_FILTERED]; uint32_t i0[2 * MAX_FILTERED];
-            for (unsigned i = 0; i < n; ++i) { const unsigned o = pos[i]; s0[o] = src[i]; t0[o] = tgt[i]; r0[o] = res[i]; d0[o] = dist[i]; i0[2 * o] = idx[2 * i]; i0[2 * o + 1] = idx[2 * i + 1]; }
-            for (unsigned i = 0; i < n; ++i) { src[i] = s0[i]; tgt[i] = t0[i]; res[i] = r0[i]; dist[i] = d0[i]; idx[2 * i] = i0[2 * i]; idx[2 * i + 1] = i0[2 * i + 1]; }
-            for (unsigned i = 0; i < n; ++i)
-                for (unsigned j = i; j < n; ++j)
-                    if (res[i] > res[j]) {
-                        float t = res[i]; res[i] = res[j]; res[j] = t;
-                        f3 s = src[i]; src[i] = src[j]; src[j] = s;
-                        s = tgt[i]; tgt[i] = tgt[j]; tgt[j] = s;
-                        uint32_t a = idx[2 * i], b = idx[2 * i + 1]; idx[2 * i] = idx[2 * j]; idx[2 * i + 1] = idx[2 * j + 1]; idx[2 * j] = a; idx[2 * j + 1] = b;
-                        t = dist[i]; dist[i] = dist[j]; dist[j] = t;
-                    }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) H[k] = __shfl_sync(FULL, h, k);
+    }
+    kabsch_from_moments(m, H, T, evs);
+    /* residual of point `lane` and its rank.  sortKabschResiduals (:368-377) is an exchange sort; its result is the ascending order, and only among EQUAL
+     * (or unordered: NaN) residuals does the arrangement depend on its particular swap sequence -- then that sequence is replayed, by one lane. */
+    float r = 0.0f; f3 a = { 0, 0, 0 }, b = { 0, 0, 0 }; uint32_t ia = 0, ib = 0; float d = 0.0f;
+    if (lane < n) {
+        a = src[lane]; b = tgt[lane]; ia = idx[2 * lane]; ib = idx[2 * lane + 1]; d = dist[lane];
+        const float dx = (T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3]) - b.x;
+        const float dy = (T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7]) - b.y;
+        const float dz = (T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11]) - b.z;
+        r = dx * dx + dy * dy + dz * dz;
+        res[lane] = r;
+    }
+    __syncwarp();
+    bool bad = false; unsigned rank = 0;
+    if (lane < n) {
+        bad = (r != r);
+        for (unsigned j = 0; j < n; ++j) {
+            const float rj = res[j];
+            if (rj < r) ++rank;
+            else if (j != lane && !(rj > r)) bad = true;                              /* equal or unordered */
         }
     }
+    const bool replay = __ballot_sync(FULL, bad) != 0u;
+    if (!replay) {
+        if (lane < n) { res[rank] = r; src[rank] = a; tgt[rank] = b; idx[2 * rank] = ia; idx[2 * rank + 1] = ib; dist[rank] = d; }      /* all reads happened before the barrier above */
+    } else if (lane == 0) {
+        for (unsigned i = 0; i < n; ++i)
+            for (unsigned j = i; j < n; ++j)
+                if (res[i] > res[j]) {
+                    float t = res[i]; res[i] = res[j]; res[j] = t;
+                    f3 s = src[i]; src[i] = src[j]; src[j] = s;
+                    s = tgt[i]; tgt[i] = tgt[j]; tgt[j] = s;
+                    uint32_t x = idx[2 * i], y = idx[2 * i + 1]; idx[2 * i] = idx[2 * j]; idx[2 * i + 1] = idx[2 * j + 1]; idx[2 * j] = x; idx[2 * j + 1] = y;
+                    t = dist[i]; dist[i] = dist[j]; dist[j] = t;
+                }
+    }
+    __syncwarp();
+    /* covarianceSVD() of the (sorted) source and target points, :178-198: entry (r, c) of the source covariance on lane 3 r + c, of the target's on lane 9 + 3 r + c */
+    warp_means(src, tgt, n, lane, m);
+    float cs = 0.0f;
+    if (lane < 18) {
+        const f3* pts = lane < 9 ? src : tgt; const float* p0 = lane < 9 ? m : m + 3;
+        const int e = (int)lane % 9, rr = e / 3, cc = e % 3;
+        for (unsigned i = 0; i < n; ++i) { const float p = f3_get(pts, i, rr) - p0[rr], q = f3_get(pts, i, cc) - p0[cc]; cs += p * q; }
+        cs /= (float)n;
+    }
+    float C[9], e3[3];
+    const int base = lane < 16 ? 0 : 9;                                               /* lanes 0..15 evaluate the source's eigenvalues, 16..31 the target's */
+#pragma unroll
+    for (int k = 0; k < 9; ++k) C[k] = __shfl_sync(FULL, cs, base + k);
+    sym_eigenvalues(C, e3);
+    const float ratio = e3[0] / e3[1];
+    const float cp = __shfl_sync(FULL, ratio, 0), cq = __shfl_sync(FULL, ratio, 16);
     const float c1 = evs[0] / evs[1];
-    float e[3];
-    covariance_eigs(src, n, e); const float cp = e[0] / e[1];
-    covariance_eigs(tgt, n, e); const float cq = e[0] / e[1];
     if (c1 != c1 || cp != cp || cq != cq || fabsf(c1) > KABSCH_CONDITION_THRESH || fabsf(cp) > KABSCH_CONDITION_THRESH || fabsf(cq) > KABSCH_CONDITION_THRESH) return 0;
     return 1;
 }
-__device__ int add_match(uint32_t ax, uint32_t ay, const KeyPoint* kp, const uint32_t* idx, unsigned cur) {         /* addMatch, :233-247 */
-    for (unsigned i = 0; i < cur; ++i) {
-        const float dix = kp[ax].px - kp[idx[2 * i]].px, diy = kp[ax].py - kp[idx[2 * i]].py;
-        const float djx = kp[ay].px - kp[idx[2 * i + 1]].px, djy = kp[ay].py - kp[idx[2 * i + 1]].py;
-        if (sqrtf(dix * dix + diy * diy) <= 5.0f || sqrtf(djx * djx + djy * djy) <= 5.0f) return 0;
+/* addMatch, :233-247: the candidate is refused when it lies within 5 pixels of a kept match in either image; kept match i on lane i */
+__device__ int add_match(uint32_t ax, uint32_t ay, const KeyPoint* kp, const uint32_t* idx, unsigned cur, unsigned lane) {
+    bool hit = false;
+    if (lane < cur) {
+        const float dix = kp[ax].px - kp[idx[2 * lane]].px, diy = kp[ax].py - kp[idx[2 * lane]].py;
+        const float djx = kp[ay].px - kp[idx[2 * lane + 1]].px, djy = kp[ay].py - kp[idx[2 * lane + 1]].py;
+        hit = sqrtf(dix * dix + diy * diy) <= 5.0f || sqrtf(djx * djx + djy * djy) <= 5.0f;
     }
-    return 1;
+    return __ballot_sync(FULL, hit) == 0u;
 }
-__device__ void key_points_3d(const KeyPoint* kp, const uint32_t* idx, unsigned n, f3* src, f3* tgt, const float* Ki) {   /* getKeySourceAndTargetPoints, :249-321 */
-    for (unsigned i = 0; i < n; ++i)
-        for (int s = 0; s < 2; ++s) {
-            const KeyPoint* k = &kp[idx[2 * i + s]];
-            const float v[3] = { k->depth * k->px, k->depth * k->py, k->depth * 1.0f };
-            f3 o = { Ki[0] * v[0] + Ki[1] * v[1] + Ki[2] * v[2] + Ki[3], Ki[4] * v[0] + Ki[5] * v[1] + Ki[6] * v[2] + Ki[7], Ki[8] * v[0] + Ki[9] * v[1] + Ki[10] * v[2] + Ki[11] };
-            if (s == 0) src[i] = o; else tgt[i] = o;
-        }
+/* getKeySourceAndTargetPoints, :249-321, for matches [first, first + n): lane 2 i + s computes point i of image s */
+__device__ void key_points_3d(const KeyPoint* kp, const uint32_t* idx, unsigned first, unsigned n, f3* src, f3* tgt, const float* Ki, unsigned lane) {
+    if (lane < 2 * n) {
+        const unsigned i = first + lane / 2; const int s = (int)(lane & 1u);
+        const KeyPoint* k = &kp[idx[2 * i + s]];
+        const float v[3] = { k->depth * k->px, k->depth * k->py, k->depth * 1.0f };
+        f3 o = { Ki[0] * v[0] + Ki[1] * v[1] + Ki[2] * v[2] + Ki[3], Ki[4] * v[0] + Ki[5] * v[1] + Ki[6] * v[2] + Ki[7], Ki[8] * v[0] + Ki[9] * v[1] + Ki[10] * v[2] + Ki[11] };
+        if (s == 0) src[i] = o; else tgt[i] = o;
+    }
 }
 
 /* filterKeyPointMatches, cuda_kabsch.h:417-502.  idx / dist: the pair's raw matches (sorted by distance), modified in place; returns the
- * number of filtered matches (their indices / distances in the first slots), T = the transform estimate. */
+ * number of filtered matches (their indices / distances in the first slots), T = the transform estimate.  Called by all 32 lanes of the pair's warp. */
 __device__ unsigned filter_pair(const KeyPoint* kp, uint32_t* idx, float* dist, unsigned numRaw, float T[16], const float* Ki, unsigned minNum, float maxRes2,
-                                f3* src, f3* tgt, float* res) {
+                                f3* src, f3* tgt, float* res, unsigned lane) {
     unsigned i0 = 0, cur = 0;
     float curMax = 100.0f;
     int valid = 0;
@@ -267,14 +299,16 @@ __device__ unsigned filter_pair(const KeyPoint* kp, uint32_t* idx, float* dist, 
         if (i0 == numRaw || cur >= MAX_FILTERED) {
             if (cur < minNum || curMax >= maxRes2 || !valid) cur = 0;
             break;
-        } else if (add_match(idx[2 * i0], idx[2 * i0 + 1], kp, idx, cur)) {
-            idx[2 * cur] = idx[2 * i0]; idx[2 * cur + 1] = idx[2 * i0 + 1]; dist[cur] = dist[i0];
+        } else if (add_match(idx[2 * i0], idx[2 * i0 + 1], kp, idx, cur, lane)) {
+            __syncwarp();
+            if (lane == 0) { idx[2 * cur] = idx[2 * i0]; idx[2 * cur + 1] = idx[2 * i0 + 1]; dist[cur] = dist[i0]; }
+            __syncwarp();
             ++cur;
             if (cur >= 3) {
                 // getKeySourceAndTargetPoints recomputes all cur points from their indices; src / tgt follow idx through every sort, so only the points of
                 // the first fit (cur == 3) and, afterwards, of the match just added are not in place already -- same values, 2 key-point loads instead of 2 cur
-                if (cur == 3) key_points_3d(kp, idx, 3, src, tgt, Ki); else key_points_3d(kp, idx + 2 * (cur - 1), 1, src + (cur - 1), tgt + (cur - 1), Ki);
-                valid = compute_reprojection(src, tgt, cur, res, T, idx, dist);
+                if (cur == 3) key_points_3d(kp, idx, 0, 3, src, tgt, Ki, lane); else key_points_3d(kp, idx, cur - 1, 1, src, tgt, Ki, lane);
+                valid = compute_reprojection(src, tgt, cur, res, T, idx, dist, lane);
                 const int b = valid;
                 float prevT[16]; for (int k = 0; k < 16; ++k) prevT[k] = T[k];
                 curMax = res[cur - 1];
@@ -283,7 +317,7 @@ __device__ unsigned filter_pair(const KeyPoint* kp, uint32_t* idx, float* dist, 
                     for (int i = (int)cur - 1; i >= 3; --i) {
                         lastRes = res[i];
                         --cur;
-                        valid = compute_reprojection(src, tgt, cur, res, T, idx, dist);
+                        valid = compute_reprojection(src, tgt, cur, res, T, idx, dist, lane);
                         curMax = res[cur - 1];
                         if (cur == 3 && (curMax > maxRes2 || (b && !valid))) { ++cur; curMax = lastRes; valid = b; for (int k = 0; k < 16; ++k) T[k] = prevT[k]; break; }
                         if (curMax < maxRes2) break;
@@ -318,12 +352,15 @@ sift_filter_kernel(const __grid_constant__ FilterArgs a) {
     __shared__ unsigned sCount;
     for (unsigned k = t; k < n; k += 32) { const uint2 v = a.idxs[(size_t)p * MAX_RAW + k]; sIdx[2 * k] = v.x; sIdx[2 * k + 1] = v.y; sDist[k] = a.dists[(size_t)p * MAX_RAW + k]; }
     __syncwarp();
-    if (t == 0) {
+    {
         float T[16], Ti[16];
-        sCount = filter_pair(a.kp, sIdx, sDist, n, T, a.Ki, a.minNum, a.maxRes2, sSrc, sTgt, sRes);
-        mat4_inverse_hd(T, Ti);
-        for (int k = 0; k < 16; ++k) { a.fT[16 * (size_t)p + k] = T[k]; a.fTinv[16 * (size_t)p + k] = Ti[k]; }
-        a.numFiltered[p] = (int)sCount;
+        const unsigned cnt = filter_pair(a.kp, sIdx, sDist, n, T, a.Ki, a.minNum, a.maxRes2, sSrc, sTgt, sRes, t);      // the whole warp; T and the count are uniform
+        if (t == 0) {
+            sCount = cnt;
+            mat4_inverse_hd(T, Ti);
+            for (int k = 0; k < 16; ++k) { a.fT[16 * (size_t)p + k] = T[k]; a.fTinv[16 * (size_t)p + k] = Ti[k]; }
+            a.numFiltered[p] = (int)cnt;
+        }
     }
     __syncwarp();
     const unsigned c = sCount;

@@ -64,6 +64,7 @@ def _bind(L):
     L.bfFrameLoopDestroy.argtypes = [vp]
     L.bfFrameLoopDestroy.restype = None
     L.bfFrameLoopStep.argtypes = [vp, vp, vp, C.c_int, C.POINTER(BFFrameLoopStatus)]
+    L.bfFrameLoopStepAhead.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.POINTER(BFFrameLoopStatus)]
     L.bfFrameLoopStepPastEnd.argtypes = [vp, C.POINTER(BFFrameLoopStatus)]
     L.bfFrameLoopGetTrajectory.argtypes = [vp, vp, C.c_uint]
     L.bfFrameLoopGetTrajectory.restype = C.c_uint
@@ -104,11 +105,19 @@ class FrameLoop:
         t.cuda.set_device(self.device)
         self.lib.bfSetStream(C.c_void_p(t.cuda.current_stream(self.device).cuda_stream))
 
-    def step(self, depth, color) -> BFFrameLoopStatus:
+    def step(self, depth, color, next_depth=None, next_color=None) -> BFFrameLoopStatus:
+        """one frame; with (next_depth, next_color) -- the frame the NEXT call will pass -- that frame's upload, ingest, SIFT detection and dense cache
+        are queued on the loop's feature stream during this call (bfFrameLoopStepAhead; same results)"""
         self._bind_stream()
         st = BFFrameLoopStatus()
         on_host = 0 if depth.is_cuda else 1
-        capi.check(self.lib.bfFrameLoopStep(self._h, C.c_void_p(depth.data_ptr()), C.c_void_p(color.data_ptr()), on_host, C.byref(st)), "bfFrameLoopStep")
+        if next_depth is None:
+            capi.check(self.lib.bfFrameLoopStep(self._h, C.c_void_p(depth.data_ptr()), C.c_void_p(color.data_ptr()), on_host, C.byref(st)), "bfFrameLoopStep")
+        else:
+            if next_depth.is_cuda != depth.is_cuda:
+                raise ValueError("the announced frame must live where the current one does (both device or both host)")
+            capi.check(self.lib.bfFrameLoopStepAhead(self._h, C.c_void_p(depth.data_ptr()), C.c_void_p(color.data_ptr()), C.c_void_p(next_depth.data_ptr()),
+                                                     C.c_void_p(next_color.data_ptr()), on_host, C.byref(st)), "bfFrameLoopStepAhead")
         return st
 
     def step_past_end(self) -> BFFrameLoopStatus:

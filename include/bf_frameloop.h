@@ -103,6 +103,16 @@ void bfFrameLoopDestroy(BFFrameLoop* loop);
  * CUDAImageManager::process uploads on arrival; else they are device pointers.  Returns 0 or a cudaError_t; *status (optional) is filled. */
 int bfFrameLoopStep(BFFrameLoop* loop, const float* depth, const uint8_t* color, int onHost, BFFrameLoopStatus* status);
 
+/* The same step with look-ahead: (nextDepth, nextColor) is the frame the NEXT call will pass as (depth, color) -- a recorded stream knows it, a live sensor
+ * driver knows it once the following frame has arrived.  While this frame is matched, filtered, solved and fused, the work of the next frame that depends
+ * on nothing but the frame itself (upload, CUDAImageManager::process, SIFT detection, dense cache: FL/CUDAImageManager.cpp:22-158, FL/Bundler.cpp:91-101,
+ * FL/CUDACache.cpp:45-86) is queued on a third stream of the loop -- the overlap the reference gets from its reconstruction and bundling threads
+ * (RUN_MULTITHREADED: the image manager processes frame f + 1 while the bundler works on frame f).  Results are identical to bfFrameLoopStep: the same kernels
+ * on the same inputs, their destinations (frame-store slot, key / descriptor slot and cache slot of the chunk the frame will belong to) being fixed by
+ * host state one frame early.  The next call MUST pass the announced pointers (else cudaErrorInvalidValue); the buffers must stay valid and unchanged until
+ * that call returns.  nextDepth == NULL: plain bfFrameLoopStep.  Look-ahead is suspended while the stage profile is on. */
+int bfFrameLoopStepAhead(BFFrameLoop* loop, const float* depth, const uint8_t* color, const float* nextDepth, const uint8_t* nextColor, int onHost, BFFrameLoopStatus* status);
+
 /* After the last frame: the reference keeps calling processInput / process with no new frame (FL/OnlineBundler.cpp:170-197) so that the last,
  * partial chunk is solved and re-integration drains.  One such turn per call. */
 int bfFrameLoopStepPastEnd(BFFrameLoop* loop, BFFrameLoopStatus* status);

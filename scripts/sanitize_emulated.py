@@ -25,5 +25,5 @@ subprocess.run = run
 import pytest  # noqa: E402
 
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-files = sorted(os.path.join(root, "tests", f) for f in os.listdir(os.path.join(root, "tests")) if f.endswith("_emulated.py") and "reference" not in f)
+files = sys.argv[2:] or sorted(os.path.join(root, "tests", f) for f in os.listdir(os.path.join(root, "tests")) if f.endswith("_emulated.py") and "reference" not in f)
 sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider"] + files))

@@ -140,3 +140,41 @@ def test_filter_frames_and_conditional_residuals_emulated(filter_emu, seed, numF
         assert filter_emu.bfSiftAddCurrToResidualsIfMatched(cur, 0, P, ent.ctypes.data, eidx.ctypes.data, cnt.ctypes.data, nfc.ctypes.data, fi.ctypes.data, keys.ctypes.data,
                                                             f16(pb["Kinv"]), lm.ctypes.data) == 0
         assert cnt[0] == expect and ent[:32 * expect].tobytes() == ent_o[:expect].tobytes() and not ent[32 * expect:].any()
+
+
+def _filter_emulated_equals_oracle(filter_emu, pb):
+    P, cur = pb["P"], pb["cur"]
+    o = orc.sift_filter_matches(cur, 0, P, pb["keys"], pb["num"], pb["dists"], pb["idxs"], pb["Kinv"])
+    keys = np.ascontiguousarray(pb["keys"], np.float32); num = np.ascontiguousarray(pb["num"], np.int32)
+    d = np.ascontiguousarray(pb["dists"], np.float32); ix = np.ascontiguousarray(pb["idxs"], np.uint32)
+    nf = np.full(P, -7, np.int32); fd = np.zeros((P, 25), np.float32); fi = np.zeros((P, 25, 2), np.uint32); T = np.zeros((P, 16), np.float32); Ti = np.zeros((P, 16), np.float32)
+    assert filter_emu.bfSiftFilterKeyPointMatches(cur, 0, P, keys.ctypes.data, num.ctypes.data, d.ctypes.data, ix.ctypes.data, nf.ctypes.data, fd.ctypes.data, fi.ctypes.data,
+                                                  T.ctypes.data, Ti.ctypes.data, f16(pb["Kinv"]), 5, 0.0004) == 0
+    for p in range(P - 1):
+        assert nf[p] == o[0][p] and np.array_equal(fi[p], o[2][p]) and np.array_equal(fd[p], o[1][p]) and same(T[p].reshape(4, 4), o[3][p]), p
+    return [int(x) for x in nf[:P - 1]]
+
+
+@pytest.mark.parametrize("case", ["outliers", "invalid-depth", "quantised", "zero-residuals"])
+def test_kabsch_filter_warp_cooperative_paths_emulated(filter_emu, case):
+    """The Kabsch filter spreads the sums of a fit over the lanes of the pair's warp (csrc/sift_filter.cu).  Cases that steer it through every branch:
+    many outliers (removal loop, rejected pairs), invalid depths (NaN residuals: the reference's exchange sort is replayed), exact geometry on a coarse
+    grid and identical frames (equal / zero residuals: replay as well) -- each bit-identical to the serial oracle."""
+    if case == "outliers":
+        pb = synth.make_filter_problem(n_pairs=5, n_inliers=25, n_outliers=40, noise=0.006, seed=21)
+    elif case == "invalid-depth":
+        pb = synth.make_filter_problem(n_pairs=4, n_inliers=40, n_outliers=10, noise=0.002, seed=31)
+        bad = np.random.default_rng(31).random(len(pb["keys"])) < 0.08
+        pb["keys"][bad, 3] = -np.inf
+    else:
+        pb = synth.make_filter_problem(n_pairs=4, n_inliers=30, n_outliers=6, noise=0.0, seed=41 if case == "quantised" else 43)
+        k = pb["keys"]; k[:, 0] = np.round(k[:, 0]); k[:, 1] = np.round(k[:, 1]); k[:, 3] = np.round(k[:, 3] * 4) / 4
+        if case == "zero-residuals":
+            n = pb["n"]
+            for p in range(pb["P"] - 1):
+                k[p * n:(p + 1) * n] = k[pb["cur"] * n:(pb["cur"] + 1) * n]
+    counts = _filter_emulated_equals_oracle(filter_emu, pb)
+    if case == "zero-residuals":
+        assert all(c == 25 for c in counts)
+    if case == "invalid-depth":
+        assert all(c == 0 for c in counts)

@@ -108,3 +108,62 @@ def test_two_stream_loop_equals_single_stream(cuda_device):
         assert a["validTransform"] == b["validTransform"] and a["numReintegrated"] == b["numReintegrated"] and a["localSolved"] == b["localSolved"]
         assert np.array_equal(a["transform"], b["transform"], equal_nan=True)
     assert np.array_equal(t0, t1, equal_nan=True)
+
+
+def test_lookahead_loop_equals_plain_loop(cuda_device):
+    """bfFrameLoopStepAhead: the next frame's upload / ingest / SIFT detection / dense cache run on the loop's feature stream while the current frame is
+    matched, solved and fused.  Same kernels, same inputs, destinations fixed one frame early: every status field, the trajectory, the heap and the
+    counters are those of the plain loop -- over two chunk boundaries (where the chunk the next frame belongs to changes), with device and with pinned
+    host frames, with and without the reconstruction stream."""
+    import torch
+    frames = [synth.make_frame(2 * i, W, H, texture="rich") for i in range(25)]
+    dev_frames = [(torch.from_numpy(d).to(cuda_device), torch.from_numpy(c).to(cuda_device)) for d, c, T in frames]
+    host_frames = [(torch.from_numpy(d).pin_memory(), torch.from_numpy(c).pin_memory()) for d, c, T in frames]
+    out = []
+    for mode in ("plain", "ahead", "ahead+overlap", "ahead-host", "ahead-every-other"):
+        p = default_params(W, H)
+        p.maxNumImages = 8; p.maxNumFrames = 40
+        p.hash.m_hashNumBuckets = 100003; p.hash.m_numSDFBlocks = 90000
+        loop = FrameLoop(p, cuda_device)
+        loop.set_overlap(mode == "ahead+overlap")
+        fr = host_frames if mode == "ahead-host" else dev_frames
+        sts = []
+        for i, (d, c) in enumerate(fr):
+            announce = mode != "plain" and i + 1 < len(fr) and not (mode == "ahead-every-other" and i % 2)
+            sts.append(loop.step(d, c, *(fr[i + 1] if announce else (None, None))).as_dict())
+        loop.join()
+        torch.cuda.synchronize()
+        out.append((mode, sts, loop.trajectory(25), loop.heap_free(), loop.counters()))
+        loop.close()
+    _, s0, t0, f0, c0 = out[0]
+    assert c0["local_solves"] == 2 and c0["reintegrations"] > 0
+    for mode, s1, t1, f1, c1 in out[1:]:
+        assert f0 == f1, mode
+        for k in ("frames", "integrations", "reintegrations", "local_solves", "global_solves", "keyframes"):
+            assert c0[k] == c1[k], (mode, k)
+        for a, b in zip(s0, s1):
+            for k in a:
+                if k == "transform":
+                    assert np.array_equal(a[k], b[k], equal_nan=True), (mode, a["frame"])
+                else:
+                    assert a[k] == b[k], (mode, a["frame"], k, a[k], b[k])
+        assert np.array_equal(t0, t1, equal_nan=True), mode
+
+
+def test_lookahead_rejects_a_frame_that_was_not_announced(cuda_device):
+    import torch
+    from bundlefusion_b200 import _capi as capi
+    p = default_params(W, H)
+    p.maxNumImages = 8; p.maxNumFrames = 16
+    p.hash.m_hashNumBuckets = 50021; p.hash.m_numSDFBlocks = 40000
+    loop = FrameLoop(p, cuda_device)
+    fr = [synth.make_frame(2 * i, W, H, texture="rich") for i in range(3)]
+    t = [(torch.from_numpy(d).to(cuda_device), torch.from_numpy(c).to(cuda_device)) for d, c, T in fr]
+    loop.step(t[0][0], t[0][1], t[1][0], t[1][1])
+    with pytest.raises(Exception):
+        loop.step(t[2][0], t[2][1])                      # frame 1 was announced
+    with pytest.raises(Exception):
+        loop.step_past_end()
+    st = loop.step(t[1][0], t[1][1]).as_dict()           # the announced frame is still accepted
+    assert st["frame"] == 1 and st["validTransform"] == 1
+    loop.close()
