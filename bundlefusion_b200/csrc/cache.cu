@@ -4,7 +4,7 @@
 // header).  The reference filters, back-projects and takes normals of the WHOLE 640x480 image (3 full-resolution float / float4
 // intermediates, ~15 MB of traffic, 8 launches) and then keeps 80x60 samples of it.  Here ONE launch evaluates, for each of the
 // 4 800 cache pixels, exactly the values the reference would have sampled: the range-gated Gaussian of the depth at the five
-// full-resolution pixels the position and its normal need, and -- in one CTA, through shared memory -- the resampled intensity,
+// full-resolution pixels the position and its normal need, and -- in 8x8 tiles through shared memory -- the resampled intensity,
 // its Gaussian and the Sobel derivatives.  ~100 KB of traffic.
 //
 // Arithmetic contract (bit-exact with oracle/cache_oracle.c, see its header): this TU is built -fmad=false; fmaf only where written;
@@ -64,45 +64,62 @@ __device__ float4 campos_from(const CacheArgs& a, int x, int y, float d) {
 }
 __device__ float4 campos_at(const CacheArgs& a, int x, int y) { return campos_from(a, x, y, depth_filtered(a, x, y)); }
 
+#define BF_CACHE_IT 8                                                        // intensity tile edge (cache pixels)
+#define BF_CACHE_RDIM (BF_CACHE_IT + 2 + 2 * BF_CACHE_MAX_RI)                // tile + the Sobel ring + the Gaussian halo
+#define BF_CACHE_FDIM (BF_CACHE_IT + 2)
+
 __global__ void __launch_bounds__(256)
-cache_store_kernel(const __grid_constant__ CacheArgs a) {
-    extern __shared__ float sI[];                            // CTA 0: [w*h] resampled intensity | [w*h] filtered intensity
+cache_store_kernel(const __grid_constant__ CacheArgs a, int nIntensityTiles) {
     const int w = (int)a.p.width, h = (int)a.p.height, npx = w * h;
-    if (blockIdx.x == 0) {
-        // ---- intensity path: resample -> Gaussian -> Sobel / 8, one CTA, through shared memory ----
-        float* sH = sI; float* sF = sI + npx;
+    if ((int)blockIdx.x < nIntensityTiles) {
+        // ---- intensity path: resample -> Gaussian -> Sobel / 8 on an 8x8 tile of the cache image.  The CTA recomputes what its tile needs of its
+        // neighbours' pixels (resampled intensity on the tile + Sobel ring + Gaussian halo, filtered intensity on the tile + Sobel ring): every value
+        // is the same expression of the same inputs whichever CTA evaluates it, so the image is the one a single pass over it produces ----
+        __shared__ float sH[BF_CACHE_RDIM * BF_CACHE_RDIM];      // resampled intensity
+        __shared__ float sF[BF_CACHE_FDIM * BF_CACHE_FDIM];      // filtered intensity
+        const int tilesX = (w + BF_CACHE_IT - 1) / BF_CACHE_IT;
+        const int tx0 = ((int)blockIdx.x % tilesX) * BF_CACHE_IT, ty0 = ((int)blockIdx.x / tilesX) * BF_CACHE_IT;
+        const int r = a.rI > 0 ? a.rI : 0, dimR = BF_CACHE_IT + 2 + 2 * r, rx0 = tx0 - 1 - r, ry0 = ty0 - 1 - r;
         const int CW = (int)a.p.inputColorWidth, CH = (int)a.p.inputColorHeight;
         const float cw = (float)(CW - 1) / (float)(w - 1), ch = (float)(CH - 1) / (float)(h - 1);
-        for (int i = threadIdx.x; i < npx; i += blockDim.x) {
-            const unsigned xi = src_index((unsigned)(i % w), cw), yi = src_index((unsigned)(i / w), ch);
+        for (int e = threadIdx.x; e < dimR * dimR; e += blockDim.x) {
+            const int x = rx0 + e % dimR, y = ry0 + e / dimR;
             float v = 0.0f;
-            if (xi < (unsigned)CW && yi < (unsigned)CH) {
-                const uchar4 c = __ldg(&a.color[yi * CW + xi]);
-                v = __fmaf_rn(0.114f, (float)c.z, __fmaf_rn(0.299f, (float)c.x, 0.587f * (float)c.y)) / 255.0f;   // convertToIntensity, :196-199
+            if (x >= 0 && x < w && y >= 0 && y < h) {
+                const unsigned xi = src_index((unsigned)x, cw), yi = src_index((unsigned)y, ch);
+                if (xi < (unsigned)CW && yi < (unsigned)CH) {
+                    const uchar4 c = __ldg(&a.color[yi * CW + xi]);
+                    v = __fmaf_rn(0.114f, (float)c.z, __fmaf_rn(0.299f, (float)c.x, 0.587f * (float)c.y)) / 255.0f;   // convertToIntensity, :196-199
+                }
             }
-            sH[i] = v;
+            sH[e] = v;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < npx; i += blockDim.x) {
-            float v = sH[i];
+        for (int e = threadIdx.x; e < BF_CACHE_FDIM * BF_CACHE_FDIM; e += blockDim.x) {
+            const int fx = e % BF_CACHE_FDIM, fy = e / BF_CACHE_FDIM, x = tx0 - 1 + fx, y = ty0 - 1 + fy;
+            if (x < 0 || x >= w || y < 0 || y >= h) continue;
+            const int cx = fx + r, cy = fy + r;                  // the pixel's position in sH
+            float v = sH[cy * dimR + cx];
             if (a.rI >= 0) {                                  // gaussFilterIntensityDevice, :811-848
-                const int x = i % w, y = i / w, r = a.rI, span = 2 * r + 1;
+                const int span = 2 * r + 1;
                 float sum = 0.0f, sumW = 0.0f;
-                for (int m = x - r; m <= x + r; ++m)
-                    for (int n = y - r; n <= y + r; ++n)
-                        if (m >= 0 && n >= 0 && m < w && n < h) { const float wgt = a.wI[(m - x + r) * span + (n - y + r)]; sumW += wgt; sum += wgt * sH[n * w + m]; }
+                for (int m = -r; m <= r; ++m)
+                    for (int n = -r; n <= r; ++n)
+                        if (x + m >= 0 && y + n >= 0 && x + m < w && y + n < h) { const float wgt = a.wI[(m + r) * span + (n + r)]; sumW += wgt; sum += wgt * sH[(cy + n) * dimR + cx + m]; }
                 v = (sumW > 0.0f) ? sum / sumW : 0.0f;
             }
-            sF[i] = v;
-            a.oIntensity[i] = v;
+            sF[e] = v;
+            if (fx >= 1 && fx <= BF_CACHE_IT && fy >= 1 && fy <= BF_CACHE_IT) a.oIntensity[y * w + x] = v;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < npx; i += blockDim.x) {  // computeIntensityDerivatives_Kernel, :260-296
-            const int x = i % w, y = i / w;
+        for (int e = threadIdx.x; e < BF_CACHE_IT * BF_CACHE_IT; e += blockDim.x) {  // computeIntensityDerivatives_Kernel, :260-296
+            const int fx = 1 + e % BF_CACHE_IT, fy = 1 + e / BF_CACHE_IT, x = tx0 - 1 + fx, y = ty0 - 1 + fy;
+            if (x >= w || y >= h) continue;
             float2 o = make_float2(-INFINITY, -INFINITY);
             if (x > 0 && x < w - 1 && y > 0 && y < h - 1) {
-                const float p00 = sF[(y - 1) * w + x - 1], p01 = sF[y * w + x - 1], p02 = sF[(y + 1) * w + x - 1], p10 = sF[(y - 1) * w + x],
-                            p12 = sF[(y + 1) * w + x], p20 = sF[(y - 1) * w + x + 1], p21 = sF[y * w + x + 1], p22 = sF[(y + 1) * w + x + 1];
+                const float* c = sF + fy * BF_CACHE_FDIM + fx;
+                const float p00 = c[-BF_CACHE_FDIM - 1], p01 = c[-1], p02 = c[BF_CACHE_FDIM - 1], p10 = c[-BF_CACHE_FDIM],
+                            p12 = c[BF_CACHE_FDIM], p20 = c[-BF_CACHE_FDIM + 1], p21 = c[1], p22 = c[BF_CACHE_FDIM + 1];
                 if (!(p00 == -INFINITY || p01 == -INFINITY || p02 == -INFINITY || p10 == -INFINITY || p12 == -INFINITY || p20 == -INFINITY ||
                       p21 == -INFINITY || p22 == -INFINITY)) {
                     const float rU = (-1.0f) * p00 + (1.0f) * p20 + (-2.0f) * p01 + (2.0f) * p21 + (-1.0f) * p02 + (1.0f) * p22;
@@ -110,12 +127,12 @@ cache_store_kernel(const __grid_constant__ CacheArgs a) {
                     o = make_float2(rU / 8.0f, rV / 8.0f);
                 }
             }
-            a.oDerivs[i] = o;
+            a.oDerivs[y * w + x] = o;
         }
         return;
     }
     // ---- depth path: one thread per cache pixel ----
-    const int i = (int)(blockIdx.x - 1) * (int)blockDim.x + (int)threadIdx.x;
+    const int i = ((int)blockIdx.x - nIntensityTiles) * (int)blockDim.x + (int)threadIdx.x;
     if (i >= npx) return;
     const int W = (int)a.p.inputDepthWidth, H = (int)a.p.inputDepthHeight;
     const float sw = (float)(W - 1) / (float)(w - 1), sh = (float)(H - 1) / (float)(h - 1);
@@ -174,12 +191,9 @@ BF_API int bfCacheStoreFrame(const BFCacheParams* params, const float* d_depth, 
             a.wI[(dx + a.rI) * (2 * a.rI + 1) + (dy + a.rI)] = expf(-((float)(dx * dx + dy * dy) / (2.0f * s * s)));
     }
     const int npx = (int)(params->width * params->height);
-    const size_t smem = sizeof(float) * 2 * (size_t)npx;
-    if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
-    static size_t smemSet = 0;
-    if (smem > 48 * 1024 && smem > smemSet) { BF_CHECK(cudaFuncSetAttribute(cache_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smemSet = smem; }
+    const int nTiles = (int)((params->width + BF_CACHE_IT - 1) / BF_CACHE_IT) * (int)((params->height + BF_CACHE_IT - 1) / BF_CACHE_IT);
     ++g_launchCount;
-    cache_store_kernel<<<1 + (npx + 255) / 256, 256, smem, stream()>>>(a);
+    cache_store_kernel<<<nTiles + (npx + 255) / 256, 256, 0, stream()>>>(a, nTiles);
     BF_CHECK(cudaGetLastError());
     return 0;
 }

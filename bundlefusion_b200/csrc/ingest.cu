@@ -31,6 +31,66 @@ struct IngestArgs {
 
 __device__ __forceinline__ unsigned src_index(unsigned o, float scale) { return (unsigned)__fmaf_rn((float)o, scale, 0.5f); }
 
+// ---- the application's configuration (two 7x7 erosions, 9x9 Gaussian: zParametersDefault.txt) with compile-time extents ----------------------
+// Same operations in the same order as the generic loops of ingest_kernel; what changes is what the compiler can do with them: the 49 / 81 taps are
+// unrolled (tile addresses become immediate offsets, the Gaussian weights immediate constant-bank operands), the element <-> (tx, ty) maps divide by
+// constants, and a tile whose halo lies inside the image (234 of the 300 tiles of a 640x480 frame) runs without the per-tap bounds tests.
+#define BF_ING_FS 3
+#define BF_ING_FR 4
+#define BF_ING_FDIM (BF_ING_T + 2 * (2 * BF_ING_FS + BF_ING_FR))
+
+template <int IT, bool BORDER>
+__device__ __forceinline__ void erode_pass_fast(const float* __restrict__ in, float* __restrict__ out, int x0, int y0, int W, int H, float dThresh, float fracReq) {
+    constexpr int S = BF_ING_FS, DIM = BF_ING_FDIM, M0 = (IT + 1) * S, WD = DIM - 2 * M0;
+    const float sumWin = (float)(unsigned)((2 * S + 1) * (2 * S + 1));
+    for (int e = threadIdx.x; e < WD * WD; e += blockDim.x) {
+        const int tx = M0 + e % WD, ty = M0 + e / WD, gx = x0 + tx, gy = y0 + ty;
+        if (BORDER && (gx < 0 || gx >= W || gy < 0 || gy >= H)) continue;
+        const float* c = in + ty * DIM + tx;
+        const float old = c[0];
+        unsigned count = 0;
+#pragma unroll
+        for (int i = -S; i <= S; ++i) {
+            const bool rowIn = !BORDER || (gy + i >= 0 && gy + i < H);
+#pragma unroll
+            for (int j = -S; j <= S; ++j)
+                if (rowIn && (!BORDER || (gx + j >= 0 && gx + j < W))) {
+                    const float d = c[i * DIM + j];
+                    if (d == -INFINITY || d == 0.0f || fabsf(d - old) > dThresh) ++count;
+                }
+        }
+        out[ty * DIM + tx] = ((float)count / sumWin >= fracReq) ? -INFINITY : old;
+    }
+}
+
+template <bool BORDER>
+__device__ __forceinline__ void gauss_pass_fast(const IngestArgs& a, const float* __restrict__ in, float* __restrict__ out, int x0, int y0, int W, int H) {
+    constexpr int R = BF_ING_FR, SPAN = 2 * R + 1, DIM = BF_ING_FDIM, HALO = 2 * BF_ING_FS + BF_ING_FR;
+    const float sigmaR = a.p.depthSigmaR;
+    for (int e = threadIdx.x; e < BF_ING_T * BF_ING_T; e += blockDim.x) {
+        const int tx = HALO + e % BF_ING_T, ty = HALO + e / BF_ING_T, gx = x0 + tx, gy = y0 + ty;
+        if (gx >= W || gy >= H) continue;
+        const float* cp = in + ty * DIM + tx;
+        const float c = cp[0];
+        float res = -INFINITY;
+        if (c != -INFINITY) {
+            float sum = 0.0f, sumW = 0.0f;
+#pragma unroll
+            for (int m = -R; m <= R; ++m) {
+                const bool colIn = !BORDER || (gx + m >= 0 && gx + m < W);
+#pragma unroll
+                for (int n = -R; n <= R; ++n)
+                    if (colIn && (!BORDER || (gy + n >= 0 && gy + n < H))) {
+                        const float cur = cp[n * DIM + m];
+                        if (cur != -INFINITY && fabsf(c - cur) < sigmaR) { const float wgt = a.wG[(m + R) * SPAN + (n + R)]; sumW += wgt; sum += wgt * cur; }
+                    }
+            }
+            if (sumW > 0.0f) res = sum / sumW;
+        }
+        out[ty * DIM + tx] = res;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 ingest_kernel(const __grid_constant__ IngestArgs a) {
     extern __shared__ float sm[];
@@ -57,53 +117,70 @@ ingest_kernel(const __grid_constant__ IngestArgs a) {
         bufA[e] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? __ldg(&a.depthRaw[gy * W + gx]) : 0.0f;
     }
     __syncthreads();
-    // ---- erosions (erodeDepthMapDevice, :701-741): pass k is valid on the tile shrunk by (k + 1) * s ----
-    float* in = bufA; float* out = bufB;
-    const int s = a.s;
-    const float sumWin = (float)(unsigned)((2 * s + 1) * (2 * s + 1));
-    for (int it = 0; it < a.iters; ++it) {
-        const int m0 = (it + 1) * s, m1 = dim - (it + 1) * s;
-        for (int e = threadIdx.x; e < dim * dim; e += blockDim.x) {
-            const int tx = e % dim, ty = e / dim, gx = x0 + tx, gy = y0 + ty;
-            if (tx < m0 || tx >= m1 || ty < m0 || ty >= m1 || gx < 0 || gx >= W || gy < 0 || gy >= H) continue;
-            unsigned count = 0;
-            const float old = in[e];
-            for (int i = -s; i <= s; ++i)
-                for (int j = -s; j <= s; ++j)
-                    if (gx + j >= 0 && gx + j < W && gy + i >= 0 && gy + i < H) {
-                        const float d = in[(ty + i) * dim + tx + j];
-                        if (d == -INFINITY || d == 0.0f || fabsf(d - old) > a.p.erodeDThresh) ++count;
+    float* out;
+    if (a.iters == 2 && a.s == BF_ING_FS && a.r == BF_ING_FR) {
+        // the application's configuration, compile-time extents (see erode_pass_fast / gauss_pass_fast); a tile is a border tile if its halo leaves the image
+        const bool border = x0 < 0 || y0 < 0 || x0 + dim > W || y0 + dim > H;
+        if (border) {
+            erode_pass_fast<0, true>(bufA, bufB, x0, y0, W, H, a.p.erodeDThresh, a.p.erodeFracReq); __syncthreads();
+            erode_pass_fast<1, true>(bufB, bufA, x0, y0, W, H, a.p.erodeDThresh, a.p.erodeFracReq); __syncthreads();
+            gauss_pass_fast<true>(a, bufA, bufB, x0, y0, W, H);
+        } else {
+            erode_pass_fast<0, false>(bufA, bufB, x0, y0, W, H, a.p.erodeDThresh, a.p.erodeFracReq); __syncthreads();
+            erode_pass_fast<1, false>(bufB, bufA, x0, y0, W, H, a.p.erodeDThresh, a.p.erodeFracReq); __syncthreads();
+            gauss_pass_fast<false>(a, bufA, bufB, x0, y0, W, H);
+        }
+        out = bufB;
+        __syncthreads();
+    } else {
+        // ---- erosions (erodeDepthMapDevice, :701-741): pass k is valid on the tile shrunk by (k + 1) * s ----
+        float* in = bufA; out = bufB;
+        const int s = a.s;
+        const float sumWin = (float)(unsigned)((2 * s + 1) * (2 * s + 1));
+        for (int it = 0; it < a.iters; ++it) {
+            const int m0 = (it + 1) * s, m1 = dim - (it + 1) * s;
+            for (int e = threadIdx.x; e < dim * dim; e += blockDim.x) {
+                const int tx = e % dim, ty = e / dim, gx = x0 + tx, gy = y0 + ty;
+                if (tx < m0 || tx >= m1 || ty < m0 || ty >= m1 || gx < 0 || gx >= W || gy < 0 || gy >= H) continue;
+                unsigned count = 0;
+                const float old = in[e];
+                for (int i = -s; i <= s; ++i)
+                    for (int j = -s; j <= s; ++j)
+                        if (gx + j >= 0 && gx + j < W && gy + i >= 0 && gy + i < H) {
+                            const float d = in[(ty + i) * dim + tx + j];
+                            if (d == -INFINITY || d == 0.0f || fabsf(d - old) > a.p.erodeDThresh) ++count;
+                        }
+                out[e] = ((float)count / sumWin >= a.p.erodeFracReq) ? -INFINITY : old;
+            }
+            __syncthreads();
+            float* t = in; in = out; out = t;
+        }
+        // ---- range-gated Gaussian (gaussFilterDepthMapDevice, :759-794) on the 32x32 core, result into `out` ----
+        {
+            const int r = a.r, span = 2 * r + 1;
+            for (int e = threadIdx.x; e < BF_ING_T * BF_ING_T; e += blockDim.x) {
+                const int tx = halo + e % BF_ING_T, ty = halo + e / BF_ING_T, gx = x0 + tx, gy = y0 + ty;
+                if (gx >= W || gy >= H) continue;
+                const float c = in[ty * dim + tx];
+                float res = c;
+                if (r >= 0) {
+                    res = -INFINITY;
+                    if (c != -INFINITY) {
+                        float sum = 0.0f, sumW = 0.0f;
+                        for (int m = -r; m <= r; ++m)
+                            for (int n = -r; n <= r; ++n)
+                                if (gx + m >= 0 && gy + n >= 0 && gx + m < W && gy + n < H) {
+                                    const float cur = in[(ty + n) * dim + tx + m];
+                                    if (cur != -INFINITY && fabsf(c - cur) < a.p.depthSigmaR) { const float wgt = a.wG[(m + r) * span + (n + r)]; sumW += wgt; sum += wgt * cur; }
+                                }
+                        if (sumW > 0.0f) res = sum / sumW;
                     }
-            out[e] = ((float)count / sumWin >= a.p.erodeFracReq) ? -INFINITY : old;
+                }
+                out[ty * dim + tx] = res;
+            }
         }
         __syncthreads();
-        float* t = in; in = out; out = t;
     }
-    // ---- range-gated Gaussian (gaussFilterDepthMapDevice, :759-794) on the 32x32 core, result into `out` ----
-    {
-        const int r = a.r, span = 2 * r + 1;
-        for (int e = threadIdx.x; e < BF_ING_T * BF_ING_T; e += blockDim.x) {
-            const int tx = halo + e % BF_ING_T, ty = halo + e / BF_ING_T, gx = x0 + tx, gy = y0 + ty;
-            if (gx >= W || gy >= H) continue;
-            const float c = in[ty * dim + tx];
-            float res = c;
-            if (r >= 0) {
-                res = -INFINITY;
-                if (c != -INFINITY) {
-                    float sum = 0.0f, sumW = 0.0f;
-                    for (int m = -r; m <= r; ++m)
-                        for (int n = -r; n <= r; ++n)
-                            if (gx + m >= 0 && gy + n >= 0 && gx + m < W && gy + n < H) {
-                                const float cur = in[(ty + n) * dim + tx + m];
-                                if (cur != -INFINITY && fabsf(c - cur) < a.p.depthSigmaR) { const float wgt = a.wG[(m + r) * span + (n + r)]; sumW += wgt; sum += wgt * cur; }
-                            }
-                    if (sumW > 0.0f) res = sum / sumW;
-                }
-            }
-            out[ty * dim + tx] = res;
-        }
-    }
-    __syncthreads();
     // ---- write: copy, or the integration pixels whose nearest source pixel is in this tile's core (resampleFloat_Kernel, :93-110) ----
     const int cx0 = (int)blockIdx.x * BF_ING_T, cy0 = (int)blockIdx.y * BF_ING_T;
     if (W == w && H == h) {
