@@ -402,7 +402,9 @@ def run_loop(args):
         l0 = L.bfGetLaunchCount()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        steptimes = [] if (os.environ.get("BF_LOOP_STEPTIMES") and not profile) else None
         for k in range(n):
+            t_step0 = time.perf_counter() if steptimes is not None else 0.0
             la = ahead and not profile and k + 1 < n       # look-ahead stays inside the pass: its first frame is never prefetched, its last announces nothing
             if e2e:
                 st = loop.step(h_depth[k], h_color[k], *((h_depth[k + 1], h_color[k + 1]) if la else (None, None)))
@@ -410,6 +412,11 @@ def run_loop(args):
                 st = loop.step(depth[f0 + k], color[f0 + k], *((depth[f0 + k + 1], color[f0 + k + 1]) if la else (None, None)))
             if not profile:
                 note(st)
+            if steptimes is not None:
+                steptimes.append((int(st.frame), round((time.perf_counter() - t_step0) * 1e3, 3), int(st.localSolved), int(st.globalSolved), int(st.globalRemoved), int(st.numKeyframes)))
+        if steptimes is not None and rank == 0:             # diagnostic: host wall time of every step call of this pass
+            with open(os.environ["BF_LOOP_STEPTIMES"], "a") as fp:
+                fp.write(f"# pass f0={f0} n={n} e2e={e2e}\n" + "".join(" ".join(str(v) for v in t) + "\n" for t in steptimes))
         loop.join()                                        # the timed region covers the reconstruction stream's work of its last frame
         b.record()
         torch.cuda.synchronize()

@@ -222,7 +222,7 @@ struct Loop {
     float* d_completeTrajectory = nullptr; float* d_localTrajectories = nullptr; float* d_siftTrajectory = nullptr; float* d_currIntegrateTransform = nullptr;
     int* d_imageInvalidateList = nullptr;
     std::vector<int> invalidImagesList; std::vector<std::vector<int>> localTrajectoriesValid;
-    std::vector<float> completeHost;
+    float* h_complete = nullptr;                  // pinned: the complete trajectory as the TrajectoryManager reads it (maxNumFrames poses)
     // BundlerState (OnlineBundlerHelper.h:74-110)
     enum { DO_NOTHING = 0, PROCESS = 1, INVALIDATE = 2 };
     int lastFrameProcessed = -1; bool lastFrameValid = false; int localToSolve = -1; int lastLocalSolved = -1; unsigned numFramesPastEnd = 0;
@@ -672,10 +672,9 @@ static int update_trajectory(Loop& L, unsigned curFrame) {
     Bundler& g = L.global;
     BF_CHECK(cudaMemcpyAsync(L.d_imageInvalidateList, L.invalidImagesList.data(), sizeof(int) * curFrame, cudaMemcpyHostToDevice, stream()));
     updateTrajectoryCU(g.d_trajectory, g.sm.numImages, L.d_completeTrajectory, curFrame, L.d_localTrajectories, L.P.submapSize + 1, g.sm.numImages, L.d_imageInvalidateList);
-    L.completeHost.resize((size_t)curFrame * 16);
-    BF_CHECK(cudaMemcpyAsync(L.completeHost.data(), L.d_completeTrajectory, 64 * (size_t)curFrame, cudaMemcpyDeviceToHost, stream()));
+    BF_CHECK(cudaMemcpyAsync(L.h_complete, L.d_completeTrajectory, 64 * (size_t)curFrame, cudaMemcpyDeviceToHost, stream()));
     FL_OK(sync_stream(L));
-    bfTrajectoryUpdateOptimizedTransform(L.tm, L.completeHost.data(), curFrame);
+    bfTrajectoryUpdateOptimizedTransform(L.tm, L.h_complete, curFrame);
     L.numCompleteTransforms = curFrame;
     return 0;
 }
@@ -892,10 +891,19 @@ BF_API int bfFrameLoopCreate(const BFFrameLoopParams* params, BFFrameLoop** out)
         if ((rc = bfTsdfReset(&L.hd, &L.hp))) break;
         cudaError_t e = cudaMallocHost(&L.h_pin, sizeof(int) * 4096);
         if (e != cudaSuccess) { rc = (int)e; break; }
+        e = cudaMallocHost(&L.h_complete, sizeof(float) * 16 * (size_t)P.maxNumFrames);
+        if (e != cudaSuccess) { rc = (int)e; break; }
+        // Library-private workspaces at their final size NOW: growing one later means cudaFree + cudaMalloc in the middle of a frame, and with the loop's other
+        // streams busy that was measured as a single 0.5 s stall (profiles/r2_lookahead_stall_steptimes.txt).  Matcher: one job per keyframe at most;
+        // solvers: the chunk's and the keyframe set's residual capacities (the keyframe solver's capped at 1 M entries up front, it doubles beyond)
+        if ((rc = bfSiftReserveWorkspace(std::max(P.maxNumImages, P.submapSize + 1), P.maxNumKeysPerImage))) break;
+        if ((rc = bfSolverReserveWorkspace(&L.local.solver.st, L.local.solver.maxImages, L.local.solver.maxResiduals, P.useLocalDense ? 1 : 0))) break;
+        if ((rc = bfSolverReserveWorkspace(&L.optLocal.solver.st, L.optLocal.solver.maxImages, L.optLocal.solver.maxResiduals, P.useLocalDense ? 1 : 0))) break;
+        if ((rc = bfSolverReserveWorkspace(&L.global.solver.st, L.global.solver.maxImages, std::min(L.global.solver.maxResiduals, 1u << 20), 0))) break;
         e = cudaStreamSynchronize(stream());
         if (e != cudaSuccess) { rc = (int)e; break; }
     } while (0);
-    if (rc) { if (L.tm) bfTrajectoryDestroy(L.tm); if (L.h_pin) cudaFreeHost(L.h_pin); delete Lp; return rc; }
+    if (rc) { if (L.tm) bfTrajectoryDestroy(L.tm); if (L.h_pin) cudaFreeHost(L.h_pin); if (L.h_complete) cudaFreeHost(L.h_complete); delete Lp; return rc; }
     *out = reinterpret_cast<BFFrameLoop*>(Lp);
     return 0;
 }
@@ -916,6 +924,7 @@ BF_API void bfFrameLoopDestroy(BFFrameLoop* loop) {
     bfSolverReleaseWorkspace(&L->local.solver.st); bfSolverReleaseWorkspace(&L->optLocal.solver.st); bfSolverReleaseWorkspace(&L->global.solver.st);
     if (L->tm) bfTrajectoryDestroy(L->tm);
     if (L->h_pin) cudaFreeHost(L->h_pin);
+    if (L->h_complete) cudaFreeHost(L->h_complete);
     delete L;
 }
 

@@ -22,6 +22,7 @@
 // Arithmetic: filter taps come from the host (expf once per tap) and are applied with fmaf in tap order -- the pyramid, the DoG, the
 // extrema and the gradient magnitudes are bit-identical to the oracle; atan2f / expf / sinf / cosf are CUDA's (a few ulp from glibc's)
 // and histogram sums are taken in scheduling order (shared-memory atomics), so orientations and descriptors agree to ~1e-6 relative.
+#include <algorithm>
 #include <cmath>
 
 #include "../../include/bf_sift.h"
@@ -331,11 +332,14 @@ sift_reshape_kernel(const __grid_constant__ SdCommon s) {
 }
 
 // ---- ComputeDescriptor_Kernel + NormalizeDescriptor_Kernel + CreateGlobalKeyPointList + ConvertDescriptorToUChar: one CTA per feature ----
-__global__ void __launch_bounds__(128)
+// 16 warps, one per cell of the 4x4 grid: a cell's samples vote only into the cell's own 8 bins, so the cells are independent and run side by side
+// (the reference walks them one after the other with 128 threads; the sums are order-free there too: shared-memory atomics).  The first 128 threads
+// then normalise and convert.
+#define SD_DESC_THREADS 512
+__global__ void __launch_bounds__(SD_DESC_THREADS)
 sift_describe_kernel(const __grid_constant__ SdCommon s, const float* __restrict__ depth, BFSIFTKeyPoint* keyPoints, uint8_t* descriptors, int* numKeyPoints, int* levelCounts) {
     __shared__ float des[128];
     __shared__ float sRed[4];
-    int L, k; slot_job(s, (int)blockIdx.x, L, k);
     const int t = threadIdx.x;
     // LimitFeatureCount(1) and the output position: levels in order, features in list order
     int n[SD_NLEV], total = 0;
@@ -345,14 +349,15 @@ sift_describe_kernel(const __grid_constant__ SdCommon s, const float* __restrict
         *numKeyPoints = total < (int)s.P.maxKeyPoints ? total : (int)s.P.maxKeyPoints;
         if (levelCounts) for (int i = 0; i < SD_NLEV; ++i) levelCounts[i] = n[i];
     }
-    if (k >= n[L]) return;
-    int out = k;
-    for (int i = 0; i < L; ++i) out += n[i];
-    if (out >= (int)s.P.maxKeyPoints) return;
+    // the grid walks the output positions: nothing is launched for empty list slots
+    const int nOut = total < (int)s.P.maxKeyPoints ? total : (int)s.P.maxKeyPoints;
+  for (int out = (int)blockIdx.x; out < nOut; out += (int)gridDim.x) {
+    int L = 0, k = out;
+    while (k >= n[L]) { k -= n[L]; ++L; }
     const int o = L / SD_DOG, j = L % SD_DOG, w = s.oc[o].w, h = s.oc[o].h;
     const float2* __restrict__ grad = s.oc[o].grad[j + 1];
     const float4 key = s.fin[s.capBase[L] + k];
-    des[t] = 0.0f;
+    if (t < 128) des[t] = 0.0f;
     __syncthreads();
     const float rpi = (float)(4.0 / 3.14159265358979323846);
     const float spt = fabsf(key.z * 3.0f);
@@ -360,14 +365,15 @@ sift_describe_kernel(const __grid_constant__ SdCommon s, const float* __restrict
     const float anglef = (double)key.w > 3.14159265358979323846 ? (float)(key.w - (2.0 * 3.14159265358979323846)) : key.w;
     const float cspt = cs * spt, sspt = sn * spt, crspt = cs / spt, srspt = sn / spt;
     const float bsz = fabsf(cspt) + fabsf(sspt);
-    for (int b = 0; b < 16; ++b) {                       // 16 cells; the 128 threads share each cell's window
+    {                                                    // cell b = this warp; its 32 lanes share the cell's window
+        const int b = t >> 5, lane = t & 31;
         const int ix = b & 3, iy = b >> 2;
         const float ox = ix - 1.5f, oy = iy - 1.5f;
         const float ptx = cspt * ox - sspt * oy + key.x, pty = cspt * oy + sspt * ox + key.y;
         const float xmin = fmaxf(1.5f, floorf(ptx - bsz) + 0.5f), ymin = fmaxf(1.5f, floorf(pty - bsz) + 0.5f);
         const float xmax = fminf(w - 1.5f, floorf(ptx + bsz) + 0.5f), ymax = fminf(h - 1.5f, floorf(pty + bsz) + 0.5f);
         const unsigned xlen = f2u_gpu(roundf(xmax - xmin + 1)), ylen = f2u_gpu(roundf(ymax - ymin + 1)), size = xlen * ylen;
-        for (unsigned i = t; i < size; i += 128) {
+        for (unsigned i = lane; i < size; i += 32) {
             const float x = (float)(i % xlen) + xmin, y = (float)(i / xlen) + ymin;
             const float dx = x - ptx, dy = y - pty;
             const float nx = crspt * dx + srspt * dy, ny = crspt * dy - srspt * dx;
@@ -388,17 +394,17 @@ sift_describe_kernel(const __grid_constant__ SdCommon s, const float* __restrict
         }
     }
     __syncthreads();
-    float v = des[t];
-    for (int pass = 0; pass < 2; ++pass) {               // normalise, clamp at 0.2, normalise
+    float v = t < 128 ? des[t] : 0.0f;
+    for (int pass = 0; pass < 2; ++pass) {               // normalise, clamp at 0.2, normalise (threads 0..127 carry the 128 bins)
         float sq = v * v;
         for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, off);
-        if ((t & 31) == 0) sRed[t >> 5] = sq;
+        if (t < 128 && (t & 31) == 0) sRed[t >> 5] = sq;
         __syncthreads();
         const float inv = 1.0f / sqrtf(sRed[0] + sRed[1] + sRed[2] + sRed[3]);
         v = pass == 0 ? fminf(0.2f, v * inv) : v * inv;
         __syncthreads();
     }
-    descriptors[(size_t)out * 128 + t] = (uint8_t)(int)(512 * v + 0.5);
+    if (t < 128) descriptors[(size_t)out * 128 + t] = (uint8_t)(int)(512 * v + 0.5);
     if (t == 0) {                                        // CreateGlobalKeyPointList_Kernel
         const float keyLocScale = (float)(1 << o);
         const float posX = keyLocScale * (key.x - 0.5f) + 0.5f, posY = keyLocScale * (key.y - 0.5f) + 0.5f;
@@ -407,6 +413,8 @@ sift_describe_kernel(const __grid_constant__ SdCommon s, const float* __restrict
         kp.pos[0] = posX; kp.pos[1] = posY; kp.scale = keyLocScale * key.z; kp.depth = __ldg(&depth[(size_t)iyd * s.P.depthWidth + ixd]);
         keyPoints[out] = kp;
     }
+    __syncthreads();                                     // des / sRed are reused by the CTA's next feature
+  }
 }
 
 // ---- host side ----
@@ -527,7 +535,8 @@ BF_API int bfSiftDetect(const BFSiftDetectParams* params, const float* d_intensi
     sift_key_rows_kernel<true><<<rows, 128, 0, st>>>(ws.c, d_depth);
     sift_orient_kernel<<<slots, 64, 0, st>>>(ws.c);
     sift_reshape_kernel<<<SD_NLEV, 512, 0, st>>>(ws.c);
-    sift_describe_kernel<<<slots, 128, 0, st>>>(ws.c, d_depth, d_keyPoints, d_descriptors, d_numKeyPoints, d_levelCounts);
+    const int descGrid = std::min(slots, num_sms() * 4);                 // grid-stride over the features that exist: four 512-thread CTAs per SM
+    sift_describe_kernel<<<descGrid, SD_DESC_THREADS, 0, st>>>(ws.c, d_depth, d_keyPoints, d_descriptors, d_numKeyPoints, d_levelCounts);
     BF_CHECK(cudaGetLastError());
     return 0;
 }

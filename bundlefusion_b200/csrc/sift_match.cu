@@ -572,6 +572,43 @@ static bool descriptor_map(const uint8_t* base, int rows, CUtensorMap* out) {
 }
 static std::mutex g_siftMutex;
 
+// grows the matcher's scratch to hold `jobs` jobs with `rows` image-1 and `cols` image-2 features in total; `exact`: called with a batch's own numbers
+// (capacities double so that a growing keyframe set rarely reallocates), else a reservation (bfSiftReserveWorkspace: capacities as given)
+static int sift_reserve(cudaStream_t s, size_t jobs, size_t rows, size_t cols, bool fromBatch) {
+    if (jobs > g_sift.jobCap) {
+        if (g_sift.dJobs) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dJobs)); BF_CHECK(cudaFreeHost(g_sift.hJobs)); BF_CHECK(cudaFree(g_sift.done)); }
+        g_sift.jobCap = fromBatch ? jobs * 2 : jobs;
+        BF_CHECK(cudaMalloc(&g_sift.done, sizeof(int) * g_sift.jobCap));
+        BF_CHECK(cudaMemsetAsync(g_sift.done, 0, sizeof(int) * g_sift.jobCap, s));          // each job's last CTA leaves its counter at 0 again
+        BF_CHECK(cudaMalloc(&g_sift.dJobs, sizeof(SiftJobDev) * 2 * g_sift.jobCap));      // [row-pass jobs | column-pass jobs]
+        BF_CHECK(cudaMallocHost(&g_sift.hJobs, sizeof(SiftJobDev) * 2 * g_sift.jobCap));
+        if (!g_sift.evCopied) BF_CHECK(cudaEventCreateWithFlags(&g_sift.evCopied, cudaEventDisableTiming));
+    } else if (fromBatch) {
+        BF_CHECK(cudaEventSynchronize(g_sift.evCopied));      // the previous call's upload (normally long done) before the staging is rewritten
+    }
+    if (rows > g_sift.rowCap) {
+        if (g_sift.rowResult) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.rowResult)); BF_CHECK(cudaFree(g_sift.rowDist)); }
+        g_sift.rowCap = fromBatch ? rows * 2 : rows;
+        BF_CHECK(cudaMalloc(&g_sift.rowResult, sizeof(int) * g_sift.rowCap));
+        BF_CHECK(cudaMalloc(&g_sift.rowDist, sizeof(float) * g_sift.rowCap));
+    }
+    if (cols > g_sift.colCap) {
+        if (g_sift.colResult) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.colResult)); }
+        g_sift.colCap = fromBatch ? cols * 2 : cols;
+        BF_CHECK(cudaMalloc(&g_sift.colResult, sizeof(int) * g_sift.colCap));
+    }
+    return 0;
+}
+static int sift_reserve_maps(cudaStream_t s, size_t jobs, bool fromBatch) {
+    if (jobs > g_sift.mapCap) {
+        if (g_sift.dMaps) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dMaps)); BF_CHECK(cudaFreeHost(g_sift.hMaps)); }
+        g_sift.mapCap = fromBatch ? jobs * 2 : jobs;
+        BF_CHECK(cudaMalloc(&g_sift.dMaps, sizeof(CUtensorMap) * 2 * g_sift.mapCap));
+        BF_CHECK(cudaMallocHost(&g_sift.hMaps, sizeof(CUtensorMap) * 2 * g_sift.mapCap));
+    }
+    return 0;
+}
+
 }  // namespace bf
 
 using namespace bf;
@@ -588,28 +625,7 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
     cudaStream_t s = stream();
     if (!g_sift.evDone) BF_CHECK(cudaEventCreateWithFlags(&g_sift.evDone, cudaEventDisableTiming));
     BF_CHECK(cudaStreamWaitEvent(s, g_sift.evDone, 0));       // a previous batch (possibly on another stream) still owns rowResult / the job table
-    if ((size_t)numJobs > g_sift.jobCap) {
-        if (g_sift.dJobs) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dJobs)); BF_CHECK(cudaFreeHost(g_sift.hJobs)); BF_CHECK(cudaFree(g_sift.done)); }
-        g_sift.jobCap = (size_t)numJobs * 2;
-        BF_CHECK(cudaMalloc(&g_sift.done, sizeof(int) * g_sift.jobCap));
-        BF_CHECK(cudaMemsetAsync(g_sift.done, 0, sizeof(int) * g_sift.jobCap, s));          // each job's last CTA leaves its counter at 0 again
-        BF_CHECK(cudaMalloc(&g_sift.dJobs, sizeof(SiftJobDev) * 2 * g_sift.jobCap));      // [row-pass jobs | column-pass jobs]
-        BF_CHECK(cudaMallocHost(&g_sift.hJobs, sizeof(SiftJobDev) * 2 * g_sift.jobCap));
-        if (!g_sift.evCopied) BF_CHECK(cudaEventCreateWithFlags(&g_sift.evCopied, cudaEventDisableTiming));
-    } else {
-        BF_CHECK(cudaEventSynchronize(g_sift.evCopied));      // the previous call's upload (normally long done) before the staging is rewritten
-    }
-    if (rows > g_sift.rowCap) {
-        if (g_sift.rowResult) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.rowResult)); BF_CHECK(cudaFree(g_sift.rowDist)); }
-        g_sift.rowCap = rows * 2;
-        BF_CHECK(cudaMalloc(&g_sift.rowResult, sizeof(int) * g_sift.rowCap));
-        BF_CHECK(cudaMalloc(&g_sift.rowDist, sizeof(float) * g_sift.rowCap));
-    }
-    if (cols > g_sift.colCap) {
-        if (g_sift.colResult) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.colResult)); }
-        g_sift.colCap = cols * 2;
-        BF_CHECK(cudaMalloc(&g_sift.colResult, sizeof(int) * g_sift.colCap));
-    }
+    { const int rcR = sift_reserve(s, (size_t)numJobs, rows, cols, true); if (rcR) return rcR; }
     // BF_SIFT_MATCH: "mma" = warp-level mma.sync sweep, "tc" = tcgen05 with descriptors staged through registers, default = tcgen05 + TMA (falls back
     // to "tc" for a batch whose arrays cannot be described by tensor maps: base not 16-byte aligned, or no driver entry point)
     static int path = -1;
@@ -624,12 +640,7 @@ BF_API int bfSiftMatchBatch(const BFSiftMatchJob* jobs, int numJobs, float distm
         }
     }
     bool mapsOk = (path == 2);
-    if (mapsOk && (size_t)numJobs > g_sift.mapCap) {
-        if (g_sift.dMaps) { BF_CHECK(cudaStreamSynchronize(s)); BF_CHECK(cudaFree(g_sift.dMaps)); BF_CHECK(cudaFreeHost(g_sift.hMaps)); }
-        g_sift.mapCap = (size_t)numJobs * 2;
-        BF_CHECK(cudaMalloc(&g_sift.dMaps, sizeof(CUtensorMap) * 2 * g_sift.mapCap));
-        BF_CHECK(cudaMallocHost(&g_sift.hMaps, sizeof(CUtensorMap) * 2 * g_sift.mapCap));
-    }
+    if (mapsOk) { const int rcM = sift_reserve_maps(s, (size_t)numJobs, true); if (rcM) return rcM; }
     SiftJobDev* h = g_sift.hJobs;
     size_t off = 0, coff = 0;
     for (int i = 0; i < numJobs; ++i) {
@@ -691,6 +702,17 @@ BF_API int bfSiftSortKeyPointMatches(unsigned int curFrame, unsigned int startFr
 BF_API size_t bfSiftWorkspaceBytes(void) {
     std::lock_guard<std::mutex> lk(g_siftMutex);
     return sizeof(SiftJobDev) * 2 * g_sift.jobCap + (sizeof(int) + sizeof(float)) * g_sift.rowCap + sizeof(int) * (g_sift.colCap + g_sift.jobCap);
+}
+BF_API int bfSiftReserveWorkspace(unsigned int maxJobs, unsigned int maxKeysPerImage) {
+    if (maxJobs == 0 || maxKeysPerImage == 0) return (int)cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lk(g_siftMutex);
+    cudaStream_t s = stream();
+    if (!g_sift.evDone) BF_CHECK(cudaEventCreateWithFlags(&g_sift.evDone, cudaEventDisableTiming));
+    BF_CHECK(cudaStreamWaitEvent(s, g_sift.evDone, 0));
+    const size_t n = (size_t)maxJobs * maxKeysPerImage;
+    int rc = sift_reserve(s, maxJobs, n, n, false);
+    if (!rc) rc = sift_reserve_maps(s, maxJobs, false);
+    return rc;
 }
 BF_API int bfSiftReleaseWorkspace(void) {
     std::lock_guard<std::mutex> lk(g_siftMutex);

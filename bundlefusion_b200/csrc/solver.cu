@@ -1297,6 +1297,16 @@ BF_API int bfSolverMaxResidual(const BFSolverInput* in, const BFSolverState* st,
     return 0;
 }
 
+BF_API int bfSolverReserveWorkspace(const BFSolverState* st, unsigned int maxImages, unsigned int maxRes, int withDenseTerm) {
+    if (!st || maxImages < 1) return (int)cudaErrorInvalidValue;
+    SolverWs* ws;
+    unsigned cap = 1024;                                  // the capacity bfSolverSolve would ask for at maxRes correspondences
+    while (cap < maxRes) cap <<= 1;
+    const int rc = get_ws(st, maxImages, cap, &ws);
+    if (rc) return rc;
+    return withDenseTerm ? ensure_dense(ws) : 0;
+}
+
 BF_API size_t bfSolverWorkspaceBytes(unsigned int maxImages, unsigned int maxRes) {
     const size_t E = 2 * (size_t)maxRes;
     return sizeof(int) * (3 * (size_t)maxImages + 1 + 2 * E + maxImages) + sizeof(Segment) * E + sizeof(float) * (36 + 20) * E + sizeof(float) * 36 * maxImages;

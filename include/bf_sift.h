@@ -208,6 +208,9 @@ int bfSiftFuseToGlobal(const BFEntryJ* d_corr, const uint32_t* d_corrKeyIndices,
 /* device scratch the matcher holds (rowResult / rowDist per job); released by bfSiftReleaseWorkspace */
 size_t bfSiftWorkspaceBytes(void);
 int bfSiftReleaseWorkspace(void);
+/* sizes that scratch for batches of up to maxJobs image pairs of up to maxKeysPerImage features each, so that no later bfSiftMatchBatch has to grow it
+ * (growing frees and re-allocates device and pinned host memory: device-wide synchronisation in the middle of a frame) */
+int bfSiftReserveWorkspace(unsigned int maxJobs, unsigned int maxKeysPerImage);
 
 #ifdef __cplusplus
 }

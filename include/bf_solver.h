@@ -177,6 +177,11 @@ int bfSolverMaxResidual(const BFSolverInput* input, const BFSolverState* state, 
 /* bytes of private workspace the library holds for a solver of this size */
 size_t bfSolverWorkspaceBytes(unsigned int maxNumberOfImages, unsigned int maxNumResiduals);
 int bfSolverReleaseWorkspace(const BFSolverState* state);
+/* Creates (or grows) the library-private workspace of `state` for up to maxNumberOfImages images and maxNumResiduals correspondences now, so that no
+ * later bfSolverSolve has to: a solve whose correspondence count crosses the workspace's capacity frees and re-allocates it (cudaFree / cudaMalloc:
+ * device-wide synchronisation, measured at hundreds of milliseconds when other streams are busy).  withDenseTerm != 0 also creates the pair tables of
+ * the dense depth / colour term.  A caller with a steady-state loop (csrc/frame_loop.cu) reserves at start-up. */
+int bfSolverReserveWorkspace(const BFSolverState* state, unsigned int maxNumberOfImages, unsigned int maxNumResiduals, int withDenseTerm);
 
 /* Test / diagnosis accessor: the dense depth/colour normal equations of the last Gauss-Newton iteration that built them, in the
  * reference's layout -- what it keeps in SolverState::d_denseJtJ [(6N)^2, row-major, translation first per image] and d_denseJtr [6N]

@@ -18,7 +18,7 @@ def build_emulated(cu_name: str, expected_launches: int) -> C.CDLL:
     assert n == expected_launches, (cu_name, n)
     pre = ('#include "%s"\n' % os.path.join(ROOT, "tests", "cuda_emu", "cuda_emu.h") +
            "#define BF_CHECK(e) do { int _e = (int)(e); if (_e) return _e; } while (0)\n#define BF_SAFE(e) do { (void)(e); } while (0)\n"
-           "namespace bf { unsigned long long g_launchCount = 0; static inline cudaStream_t stream() { return nullptr; } }\n")
+           "namespace bf { unsigned long long g_launchCount = 0; static inline cudaStream_t stream() { return nullptr; } static inline int num_sms() { return 2; } }\n")
     d = tempfile.mkdtemp(prefix="bf_emu_")
     cpp = os.path.join(d, cu_name.replace(".cu", "_emu.cpp"))
     open(cpp, "w").write(pre + src)
