@@ -108,6 +108,24 @@ TSDF_SYMBOLS = [
 
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
 
+RAYCAST_SYMBOLS = ["updateConstantRayCastParams", "rayIntervalSplatCUDA", "resetRayIntervalSplatCUDA", "renderCS",
+                   "bfRayCastSplat", "bfRayCastRender", "bfRayCastComputeNormals", "bfRayCastRenderPose"]
+
+
+class BFRayCastParams(C.Structure):
+    """include/bf_raycast.h (FL/DepthSensing/CUDARayCastParams.h:8-27), 192 bytes"""
+    _fields_ = [("m_viewMatrix", BFFloat4x4), ("m_viewMatrixInverse", BFFloat4x4),
+                ("mx", C.c_float), ("my", C.c_float), ("fx", C.c_float), ("fy", C.c_float),
+                ("m_width", C.c_uint32), ("m_height", C.c_uint32), ("m_numOccupiedSDFBlocks", C.c_uint32), ("m_maxNumVertices", C.c_uint32),
+                ("m_splatMinimum", C.c_int32), ("m_minDepth", C.c_float), ("m_maxDepth", C.c_float), ("m_rayIncrement", C.c_float),
+                ("m_thresSampleDist", C.c_float), ("m_thresDist", C.c_float), ("m_useGradients", C.c_uint8), ("m_pad", C.c_uint8 * 3), ("dummy0", C.c_uint32)]
+
+
+class BFRayCastData(C.Structure):
+    """include/bf_raycast.h (FL/DepthSensing/RayCastSDFUtil.h:296-302): seven device pointers"""
+    _fields_ = [("d_depth", C.c_void_p), ("d_depth4", C.c_void_p), ("d_normals", C.c_void_p), ("d_colors", C.c_void_p), ("d_vertexBuffer", C.c_void_p),
+                ("d_rayIntervalSplatMin", C.c_void_p), ("d_rayIntervalSplatMax", C.c_void_p)]
+
 CACHE_SYMBOLS = ["bfCacheStoreFrame"]
 INGEST_SYMBOLS = ["bfIngestFrame"]
 BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updateTrajectoryCU", "bfTrajectorySelectReintegration",

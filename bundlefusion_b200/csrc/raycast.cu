@@ -17,6 +17,9 @@
 // v * (1 / sqrtf(v.v)) (the reference's rsqrtf is an approximate instruction).
 #include <cmath>
 
+#include <cstring>
+
+#include "../../include/bf_host.h"
 #include "../../include/bf_raycast.h"
 #include "bf_common.cuh"
 
@@ -310,7 +313,7 @@ raycast_splat_kernel(const __grid_constant__ RcArgs a) {
         for (int k = (int)lane; k < n; k += 32) {
             const size_t px = (size_t)(j0 + k / nx) * W + (size_t)(i0 + k % nx);
             if (nearOk) atomicMin(reinterpret_cast<unsigned*>(a.d.d_rayIntervalSplatMin) + px, __float_as_uint(dNear));
-            if (farOk) atomicMax(reinterpret_cast<int*>(a.d.d_rayIntervalSplatMax) + px, __float_as_int(dFar));
+            if (farOk) atomicMax(reinterpret_cast<int*>(a.d.d_rayIntervalSplatMax) + px, (int)__float_as_uint(dFar));
         }
     }
 }
@@ -398,9 +401,8 @@ BF_API int bfRayCastRenderPose(const BFHashDataStruct* hashData, const BFHashPar
     if (!rayCastParams || !rigidTransform) return (int)cudaErrorInvalidValue;
     // CUDARayCastSDF::rayIntervalSplatting (cpp:86-98): view = inverse of the rigid transform
     float inv[16];
-    extern int bfInvertRigidHost(const float*, float*);
     for (int k = 0; k < 16; ++k) rayCastParams->m_viewMatrixInverse.m[k] = rigidTransform[k];
-    if (bfInvertMatrix4x4(rigidTransform, inv)) return (int)cudaErrorInvalidValue;
+    bfMat4Inverse(rigidTransform, inv);                    // mat4f::getInverse as the host does it (include/bf_host.h)
     for (int k = 0; k < 16; ++k) rayCastParams->m_viewMatrix.m[k] = inv[k];
     int rc = do_splat(hashData, hashParams, cameraParams, rayCastData, rayCastParams);
     if (!rc) rc = do_render(hashData, hashParams, rayCastData, rayCastParams);

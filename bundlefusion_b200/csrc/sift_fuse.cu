@@ -6,10 +6,10 @@
 // recursively into tracks, averages each track's world position, projects it into the chunk's first frame and uploads the fused key points
 // with one representative descriptor each as the next keyframe of the global manager.
 //
-// Here the whole thing is one launch of one CTA and nothing leaves the device: the lists are built in shared memory, ONE thread replays the
-// reference's recursion with an explicit stack (the visiting order decides which key represents a track and which correspondence supplies a
-// member's position, so it is reproduced, not parallelised: <= 1 375 correspondences per chunk, a few microseconds), then the tracks are
-// reduced, compacted and their descriptors gathered by all threads.  Output and count stay on the device for the global matcher.
+// Here the whole thing is one launch of one CTA and nothing leaves the device: the lists are built in shared memory, all threads pick out the keys
+// that have correspondences at all, ONE thread replays the reference's recursion over those with an explicit stack (the visiting order decides which
+// key represents a track and which correspondence supplies a member's position, so it is reproduced, not parallelised: <= 1 375 correspondences per
+// chunk), then the tracks are reduced, compacted and their descriptors gathered by all threads.  Output and count stay on the device for the global matcher.
 // Arithmetic as the reference's host code: individually rounded IEEE operations (this TU is built -fmad=false -prec-div=true -prec-sqrt=true),
 // float4x4 * float3 as ((m0 x + m1 y) + m2 z) + m3.  Bit-identical to oracle/fuse_oracle.c.
 #include "../../include/bf_sift.h"
@@ -49,9 +49,10 @@ sift_fuse_kernel(const __grid_constant__ FuseArgs a) {
     unsigned* stackKey = trackStart + (C + 1);    // [FUSE_STACK]
     unsigned* stackPos = stackKey + FUSE_STACK;   // [FUSE_STACK]
     unsigned* scan = stackPos + FUSE_STACK;       // [FUSE_THREADS]
-    unsigned char* marker = reinterpret_cast<unsigned char*>(scan + FUSE_THREADS);       // [M]
+    unsigned* rootList = scan + FUSE_THREADS;     // [2C]      keys with a non-empty list, in (image, key) order: the only roots that can start a track
+    unsigned char* marker = reinterpret_cast<unsigned char*>(rootList + 2 * C);          // [M]
     unsigned char* errOk = marker + ((M + 3) & ~3u);                                      // [C]
-    __shared__ unsigned sNumTracks, sOverflow;
+    __shared__ unsigned sNumTracks, sOverflow, sNumRoots, sTotal;
 
     for (unsigned k = t; k <= M; k += FUSE_THREADS) start[k] = 0;
     for (unsigned k = t; k < M; k += FUSE_THREADS) marker[k] = 0;
@@ -95,6 +96,7 @@ sift_fuse_kernel(const __grid_constant__ FuseArgs a) {
         // the END pointer of the key (start[key + 1]) leaves every list ascending and turns start[key + 1] into the BEGIN of key's list;
         // its end is then the begin of the next key's list, start[key + 2] (the total for the last key).
         const unsigned total = start[M];
+        sTotal = total;                                  // start[M] is about to become the begin of the last key's list
         for (int c = (int)C - 1; c >= 0; --c) {
             const BFEntryJ e = a.corr[c];
             if (e.imgIdx_i == 0xFFFFFFFFu) continue;
@@ -102,12 +104,48 @@ sift_fuse_kernel(const __grid_constant__ FuseArgs a) {
             const unsigned sy = --start[k.y + 1]; adjKey[sy] = k.x; adjCE[sy] = 2u * (unsigned)c + 1u;
             const unsigned sx = --start[k.x + 1]; adjKey[sx] = k.y; adjCE[sx] = 2u * (unsigned)c;
         }
-        // findTrack for every key in (image, key) order (:401-410), the recursion replaced by an explicit stack
+    }
+    __syncthreads();
+    // findTrack is called for every key in (image, key) order (:401-410), but a key without correspondences starts and joins nothing: all threads pick
+    // out, in that order, the keys whose list is not empty (of ~2 000 keys of a chunk a few hundred), so that the serial walk below touches only those
+    {
+        const unsigned total = sTotal;
+        const unsigned per = (M + FUSE_THREADS - 1) / FUSE_THREADS;
+        unsigned local = 0;
+        for (unsigned q = 0; q < per; ++q) {
+            const unsigned k = t * per + q;
+            if (k < M) {
+                const unsigned img = k / a.keyStride, kk = k % a.keyStride;
+                const bool live = kk < (unsigned)max(a.numKeys[img], 0) && start[k + 1] < ((k + 1 < M) ? start[k + 2] : total);
+                local += live ? 1u : 0u;
+            }
+        }
+        scan[t] = local;
+        __syncthreads();
+        for (unsigned off = 1; off < FUSE_THREADS; off <<= 1) {
+            const unsigned v = (t >= off) ? scan[t - off] : 0u;
+            __syncthreads();
+            scan[t] += v;
+            __syncthreads();
+        }
+        unsigned o = scan[t] - local;
+        for (unsigned q = 0; q < per; ++q) {
+            const unsigned k = t * per + q;
+            if (k < M) {
+                const unsigned img = k / a.keyStride, kk = k % a.keyStride;
+                if (kk < (unsigned)max(a.numKeys[img], 0) && start[k + 1] < ((k + 1 < M) ? start[k + 2] : total)) rootList[o++] = k;
+            }
+        }
+        if (t == FUSE_THREADS - 1) sNumRoots = scan[t];
+        __syncthreads();
+    }
+    if (t == 0) {
+        // the recursion of findTrack replaced by an explicit stack, roots in the reference's order
+        const unsigned total = sTotal, nRoots = sNumRoots;
         unsigned nItems = 0, nTracks = 0;
-        for (unsigned i = 0; i < a.numImages; ++i) {
-            const unsigned nk = (unsigned)max(a.numKeys[i], 0);
-            for (unsigned kk = 0; kk < nk && kk < a.keyStride; ++kk) {
-                const unsigned root = i * a.keyStride + kk;
+        for (unsigned r = 0; r < nRoots; ++r) {
+            {
+                const unsigned root = rootList[r];
                 const unsigned first = nItems;
                 unsigned sp = 1;
                 stackKey[0] = root; stackPos[0] = start[root + 1];
@@ -204,7 +242,7 @@ BF_API int bfSiftFuseToGlobal(const BFEntryJ* d_corr, const uint32_t* d_corrKeyI
     a.keys = d_keyPoints; a.descs = d_descriptors; a.numKeys = d_numKeysPerImage; a.keyStride = keyStride;
     for (int k = 0; k < 16; ++k) a.K[k] = colorIntrinsics[k];
     a.outKeys = d_outKeyPoints; a.outDescs = d_outDescriptors; a.outNum = d_outNumKeys; a.maxKeys = maxKeys; a.status = d_status;
-    const size_t words = (size_t)(M + 1) + 6 * (size_t)maxCorr + (maxCorr + 1) + 2 * FUSE_STACK + FUSE_THREADS;
+    const size_t words = (size_t)(M + 1) + 8 * (size_t)maxCorr + (maxCorr + 1) + 2 * FUSE_STACK + FUSE_THREADS;
     const size_t bytes = words * 4 + ((M + 3) & ~3u) + ((maxCorr + 3) & ~3u);
     static size_t attr = 0;
     if (bytes > attr) { BF_CHECK(cudaFuncSetAttribute(sift_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); attr = bytes; }

@@ -45,6 +45,8 @@ cudaStream_t stream() { return g_stream; }
 static BFHashParams g_hashParams;           // updateConstantHashParams
 static BFDepthCameraParams g_camParams;     // updateConstantDepthCameraParams
 static BFDepthCameraData g_bound = {nullptr, nullptr};   // bindInputDepthColorTextures
+const BFHashParams* bound_hash_params() { return &g_hashParams; }                  // for the reference-named stubs of other translation units (raycast.cu)
+const BFDepthCameraParams* bound_camera_params() { return &g_camParams; }
 
 // library-private per-hash scratch ("aux"), keyed by the d_hash pointer
 struct TsdfAux {

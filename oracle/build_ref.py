@@ -97,6 +97,7 @@ def main():
     build_sift_emulated()
     build_mgr_emulated()
     build_trajectory_host()
+    build_raycast_emulated()
     print("oracle/_ref built:", sorted(os.listdir(OUT)))
     return 0
 
@@ -279,6 +280,45 @@ def build_mgr_emulated():
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-8000:])
         raise RuntimeError("building libref_mgr_emulated.so failed")
+
+
+def build_raycast_emulated():
+    """The reference's ray-cast kernels (FL/DepthSensing/CUDARayCastSDF.cu with RayCastSDFUtil.h, VoxelUtilHashSDF.h, CUDAConstant.cu) compiled by g++ against
+    the CUDA emulation -> libref_raycast_emulated.so (wrapper: oracle/ref_raycast_wrap.cu).  Runs on the CPU: pins row N3's oracle without a GPU and without
+    Direct3D.  Patches on the scratch copies: launch syntax; renderCS binds its two interval textures to cudaArrays that Direct3D rendered -- here they are
+    linear float images bound with cudaBindTexture2D; the HashEntry alignment attribute where gcc honours it (see main()); the matNxM specialisation."""
+    root = os.path.join(TMP, "rcemu")
+    os.makedirs(root)
+    ds, sg = os.path.join(REF, "Source", "DepthSensing"), os.path.join(REF, "Source", "SiftGPU")
+    for f in ("CUDAConstant.cu", "CUDARayCastSDF.cu", "RayCastSDFUtil.h", "VoxelUtilHashSDF.h", "DepthCameraUtil.h", "CUDAHashParams.h", "CUDADepthCameraParams.h", "CUDARayCastParams.h"):
+        shutil.copy(os.path.join(ds, f), root)
+    for f in ("cuda_SimpleMatrixUtil.h", "cudaUtil.h"):
+        shutil.copy(os.path.join(sg, f), root)
+    patch(os.path.join(root, "cuda_SimpleMatrixUtil.h"),
+          [(r"\ninline __device__ __host__ matNxM<4, 1>::operator float4\(\)", "\ntemplate<> inline __device__ __host__ matNxM<4, 1>::operator float4()", 1)])
+    for f in ("CUDAHashParams.h", "CUDADepthCameraParams.h", "CUDARayCastParams.h"):
+        q = os.path.join(root, f)
+        open(q, "w", encoding="latin-1").write("#pragma once\n" + open(os.path.join(ds, f), encoding="latin-1").read())
+    patch(os.path.join(root, "VoxelUtilHashSDF.h"), [(r"__align__\(16\)\s*struct HashEntry", "struct __align__(16) HashEntry", 1)])
+    # `-gradientForPoint(...)`: cutil_math's unary minus takes a non-const reference, which MSVC / nvcc bind to a temporary and g++ does not
+    patch(os.path.join(root, "RayCastSDFUtil.h"), [(r"float3 normal = -gradientForPoint\(hash, currentIso\);", "float3 g_ = gradientForPoint(hash, currentIso); float3 normal = -g_;", 1)])
+    launch = (r"([A-Za-z_]\w*(?:<[^<>()]*>)?)\s*<<\s*<\s*([^;]*?)\s*>>\s*>\s*\(", r"EMU_KERNEL(\1, \2)(", None)
+    patch(os.path.join(root, "CUDARayCastSDF.cu"), [
+        launch,
+        (r"cudaBindTextureToArray\(rayMinTextureRef, rayCastData\.d_rayIntervalSplatMinArray, channelDesc\);",
+         "cudaBindTexture2D(0, &rayMinTextureRef, (const void*)rayCastData.d_rayIntervalSplatMinArray, &channelDesc, rayCastParams.m_width, rayCastParams.m_height, rayCastParams.m_width * sizeof(float));", 1),
+        (r"cudaBindTextureToArray\(rayMaxTextureRef, rayCastData\.d_rayIntervalSplatMaxArray, channelDesc\);",
+         "cudaBindTexture2D(0, &rayMaxTextureRef, (const void*)rayCastData.d_rayIntervalSplatMaxArray, &channelDesc, rayCastParams.m_width, rayCastParams.m_height, rayCastParams.m_width * sizeof(float));", 1)])
+    unit = os.path.join(root, "ref_raycast_wrap_emu.cpp")
+    shutil.copy(os.path.join(HERE, "ref_raycast_wrap.cu"), unit)
+    emu_dir = os.path.join(HERE, "ref_emu")
+    cmd = ["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-D__CUDACC__", "-D__NVCC__",
+           "-I", emu_dir, "-I", os.path.join(os.path.dirname(HERE), "tests", "cuda_emu"), "-I", root, "-I", os.path.join(REF, "Include", "cutil", "inc"),
+           unit, "-o", os.path.join(OUT, "libref_raycast_emulated.so"), "-lm"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-8000:])
+        raise RuntimeError("building libref_raycast_emulated.so failed")
 
 
 def build_trajectory_host():

@@ -645,3 +645,49 @@ def sift_filter_frames(curFrame, startFrame, numFrames, numFiltered, validImages
     L.orc_sift_filter_frames.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
     L.orc_sift_filter_frames.restype = C.c_int
     return L.orc_sift_filter_frames(curFrame, startFrame, numFrames, nf.ctypes.data, v.ctypes.data), v
+
+
+# ---- ray cast of the hashed TSDF (oracle/raycast_oracle.c) ----------------------------------------------
+def raycast_set_pose(p, T):
+    """CUDARayCastSDF::rayIntervalSplatting (cpp:86-98): view matrix = inverse of the rigid transform (float32 cofactor inverse, as the host's mat4f)"""
+    from bundlefusion_b200.scene_rep import mat4_inverse_f32, mat4_to_c
+    T = np.ascontiguousarray(T, np.float32)
+    p.m_viewMatrixInverse = mat4_to_c(T)
+    p.m_viewMatrix = mat4_to_c(mat4_inverse_f32(T))
+
+
+def raycast_splat(scene: "OracleSceneRepHashSDF", cam, p, splat_minimum: int) -> np.ndarray:
+    """one interval image ([height, width] float32, -inf = nothing drawn) from the scene's last compactified list"""
+    L = lib()
+    out = np.zeros((p.m_height, p.m_width), np.float32)
+    p.m_splatMinimum = splat_minimum
+    L.orc_raycast_splat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
+    L.orc_raycast_splat.restype = None
+    L.orc_raycast_splat(C.addressof(scene.hp), C.addressof(cam), C.addressof(p), scene.compactified.ctypes.data, int(scene.num_occupied), out.ctypes.data)
+    return out
+
+
+def raycast_render(scene: "OracleSceneRepHashSDF", p, ray_min: np.ndarray, ray_max: np.ndarray) -> dict:
+    L = lib()
+    H, W = p.m_height, p.m_width
+    o = {"depth": np.zeros((H, W), np.float32), "depth4": np.zeros((H, W, 4), np.float32), "normals": np.zeros((H, W, 4), np.float32), "colors": np.zeros((H, W, 4), np.float32)}
+    L.orc_raycast_render.argtypes = [C.c_void_p] * 9
+    L.orc_raycast_render.restype = None
+    rmin, rmax = np.ascontiguousarray(ray_min, np.float32), np.ascontiguousarray(ray_max, np.float32)
+    L.orc_raycast_render(C.addressof(scene.hd), C.addressof(scene.hp), C.addressof(p), rmin.ctypes.data, rmax.ctypes.data, o["depth"].ctypes.data, o["depth4"].ctypes.data,
+                         o["normals"].ctypes.data, o["colors"].ctypes.data)
+    if not p.m_useGradients:
+        L.orc_raycast_normals.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p]
+        L.orc_raycast_normals.restype = None
+        L.orc_raycast_normals(o["depth4"].ctypes.data, W, H, o["normals"].ctypes.data)
+    return o
+
+
+def raycast_frame(scene: "OracleSceneRepHashSDF", cam, p, T) -> dict:
+    """CUDARayCastSDF::render: interval splat (both directions), ray march, normals"""
+    raycast_set_pose(p, T)
+    rmin = raycast_splat(scene, cam, p, 1)
+    rmax = raycast_splat(scene, cam, p, 0)
+    o = raycast_render(scene, p, rmin, rmax)
+    o["ray_min"], o["ray_max"] = rmin, rmax
+    return o

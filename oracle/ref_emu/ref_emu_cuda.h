@@ -47,6 +47,11 @@ static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrt(float x) { return 1.0f / sqrtf(x); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline int atomicAdd(int* p, int v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const int o = *p; *p = o + v; return o; }
+static inline int atomicCAS(int* p, int cmp, int v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const int o = *p; if (o == cmp) *p = v; return o; }
+static inline int atomicExch(int* p, int v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const int o = *p; *p = v; return o; }
+static inline unsigned atomicSub(unsigned* p, unsigned v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const unsigned o = *p; *p = o - v; return o; }
+static inline uchar3 make_uchar3(float x, float y, float z) { return { (unsigned char)x, (unsigned char)y, (unsigned char)z }; }     // in-range values: truncation, as cvt.rzi
+enum { cudaTextureType1D = 1, cudaTextureType2D = 2 };
 static inline float __shfl_down(float v, int d, int = 32) { return __shfl_down_sync(0xFFFFFFFFu, v, d); }
 static inline float __shfl_xor(float v, int m, int = 32) { return __shfl_xor_sync(0xFFFFFFFFu, v, m); }
 static const int warpSize = 32;
@@ -81,6 +86,7 @@ static inline cudaError_t cudaFreeArray(cudaArray*) { return 0; }
 static inline cudaError_t cudaMemcpy2DToArray(cudaArray*, size_t, size_t, const void*, size_t, size_t, size_t, int) { return 1; }
 static inline cudaError_t cudaMemcpyFromArray(void*, const cudaArray*, size_t, size_t, size_t, int) { return 1; }
 static inline cudaError_t cudaGetChannelDesc(cudaChannelFormatDesc*, const cudaArray*) { return 1; }
+static inline cudaChannelFormatDesc cudaCreateChannelDesc(int x, int y, int z, int w, int f) { return cudaChannelFormatDesc{ x, y, z, w, f }; }
 
 // ---- texture references over linear memory (point sampling; out-of-range 1-D fetches return zero, 2-D coordinates clamp) ----
 struct textureReference { const void* ptr = nullptr; size_t bytes = 0; int width = 0, height = 0; size_t pitch = 0; cudaChannelFormatDesc channelDesc{}; int filterMode = 0; };

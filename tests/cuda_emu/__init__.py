@@ -9,7 +9,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def build_emulated(cu_name: str, expected_launches: int) -> C.CDLL:
+def build_emulated(cu_name: str, expected_launches: int, extra_pre: str = "") -> C.CDLL:
     src = open(os.path.join(ROOT, "bundlefusion_b200", "csrc", cu_name)).read()
     src = src.replace('#include "bf_common.cuh"', "")
     src = re.sub(r"extern __shared__ float (\w+)\[\];", lambda m: "" if m.group(1) == "sm" else f"float* {m.group(1)} = sm;", src)      # dynamic shared memory: the shim's sm[]
@@ -21,7 +21,7 @@ def build_emulated(cu_name: str, expected_launches: int) -> C.CDLL:
            "namespace bf { unsigned long long g_launchCount = 0; static inline cudaStream_t stream() { return nullptr; } static inline int num_sms() { return 2; } }\n")
     d = tempfile.mkdtemp(prefix="bf_emu_")
     cpp = os.path.join(d, cu_name.replace(".cu", "_emu.cpp"))
-    open(cpp, "w").write(pre + src)
+    open(cpp, "w").write(pre + extra_pre + src)
     so = os.path.join(d, "lib" + cu_name.replace(".cu", "_emu.so"))
     r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "tests", "cuda_emu"), "-I", os.path.join(ROOT, "bundlefusion_b200", "csrc"),
                         cpp, "-o", so], capture_output=True, text=True)

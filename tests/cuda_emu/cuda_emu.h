@@ -67,6 +67,11 @@ static inline void __syncthreads() { emu::g_bar.wait(); }
 static inline unsigned emu_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }      // linear id: warps are cut from it
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const unsigned o = *p; *p = o + v; return o; }
 static inline float atomicAdd(float* p, float v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const float o = *p; *p = o + v; return o; }
+static inline unsigned atomicMin(unsigned* p, unsigned v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const unsigned o = *p; if (v < o) *p = v; return o; }
+static inline int atomicMax(int* p, int v) { std::lock_guard<std::mutex> lk(emu::g_atomic); const int o = *p; if (v > o) *p = v; return o; }
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline int __float2int_rz(float v) { if (v != v) return 0; if (v >= 2147483648.0f) return INT32_MAX; if (v <= -2147483648.0f) return INT32_MIN; return (int)v; }     // cvt.rzi.s32.f32
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }

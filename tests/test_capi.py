@@ -53,6 +53,13 @@ def test_symbol_list_matches_header():
     assert sorted(set(_declared_symbols("bf_cache.h"))) == sorted(set(capi.CACHE_SYMBOLS))
     assert sorted(set(_declared_symbols("bf_ingest.h"))) == sorted(set(capi.INGEST_SYMBOLS))
     assert sorted(set(_declared_symbols("bf_bundler.h"))) == sorted(set(capi.BUNDLER_SYMBOLS))
+    assert sorted(set(_declared_symbols("bf_raycast.h"))) == sorted(set(capi.RAYCAST_SYMBOLS))
+
+
+def test_raycast_pod_layouts():
+    assert C.sizeof(capi.BFRayCastParams) == 192 and capi.BFRayCastParams.mx.offset == 128 and capi.BFRayCastParams.m_splatMinimum.offset == 160
+    assert capi.BFRayCastParams.m_useGradients.offset == 184 and capi.BFRayCastParams.dummy0.offset == 188       # FL/DepthSensing/CUDARayCastParams.h:8-27
+    assert C.sizeof(capi.BFRayCastData) == 56
 
 
 def test_sift_pod_layouts():
