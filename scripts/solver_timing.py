@@ -5,7 +5,7 @@ import numpy as np, torch
 from bundlefusion_b200 import synth
 from bundlefusion_b200.solver import CUDASolverBundling
 dev = torch.device("cuda:0")
-for (N, deg, gn, pcg) in [(11, 10, 2, 100), (500, 15, 3, 150), (2000, 15, 3, 150)]:
+for (N, deg, gn, pcg) in [(11, 10, 2, 100), (32, 10, 3, 150), (64, 12, 3, 150), (128, 15, 3, 150), (500, 15, 3, 150), (2000, 15, 3, 150)]:
     prob = synth.make_ba_problem(N, degree=deg, corr_per_pair=25, noise=0.002, seed=32, stride=10 if N <= 500 else 2)
     corr = torch.from_numpy(prob["corr"].view(np.uint8).reshape(-1).copy()).to(dev)
     r0 = torch.from_numpy(prob["init_rot"]).to(dev); t0 = torch.from_numpy(prob["init_trans"]).to(dev)
