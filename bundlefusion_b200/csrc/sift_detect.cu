@@ -80,29 +80,64 @@ sift_level_kernel(const __grid_constant__ LevelArgs a) {
     float* sH = sm + iw * iw;                             // [iw][ow]   H pass: every input row, output columns
     float* sOut = sH + iw * ow;                           // [ow][ow]
     const int x0 = (int)blockIdx.x * SD_TILE - 1, y0 = (int)blockIdx.y * SD_TILE - 1;      // image coordinates of output (0, 0) of the tile
-    // stage the input with clamp-to-edge addressing (fetch_index clamps in FilterH / FilterV)
-    for (int e = threadIdx.x; e < iw * iw; e += blockDim.x) {
-        const int gx = clampi(x0 - half + e % iw, 0, a.w - 1), gy = clampi(y0 - half + e / iw, 0, a.h - 1);
-        float v;
-        if (a.subsample) { const int sx = (gx << 1) < a.srcW - 1 ? (gx << 1) : a.srcW - 1; v = __ldg(&a.src[(size_t)(gy << 1) * a.srcW + sx]); }   // DownsampleKernel
-        else v = __ldg(&a.src[(size_t)gy * a.srcW + gx]);
-        sIn[e] = v;
+    // stage the input with clamp-to-edge addressing (fetch_index clamps in FilterH / FilterV).  A warp takes whole tile rows and a lane up to four columns of
+    // a row pair: eight independent loads are in flight per thread before the first is stored -- with one CTA per SM (the small octaves) a load's latency
+    // is otherwise paid once per element -- and no index is divided
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+        for (int r = 2 * warp; r < iw; r += 2 * nwarp) {
+            float v[2][4];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int gy = clampi(y0 - half + r + rr, 0, a.h - 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = lane + 32 * k;
+                    v[rr][k] = 0.0f;
+                    if (c < iw && r + rr < iw) {
+                        const int gx = clampi(x0 - half + c, 0, a.w - 1);
+                        if (a.subsample) { const int sx = (gx << 1) < a.srcW - 1 ? (gx << 1) : a.srcW - 1; v[rr][k] = __ldg(&a.src[(size_t)(gy << 1) * a.srcW + sx]); }   // DownsampleKernel
+                        else v[rr][k] = __ldg(&a.src[(size_t)gy * a.srcW + gx]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const int c = lane + 32 * k; if (c < iw && r + rr < iw) sIn[(r + rr) * iw + c] = v[rr][k]; }
+        }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < iw * ow; e += blockDim.x) {
-        const int r = e / ow, c = e % ow;
-        // output column x0 + c clamps its taps in IMAGE coordinates: tap i reads clamp(x0 + c - half + i); the staged tile holds
-        // clamp(x0 - half + t) at position t, so for in-image output columns position c + i is exactly that pixel
-        float v = 0.0f;
-        for (int i = 0; i < a.fw; ++i) v = fmaf(sIn[r * iw + c + i], a.taps[i], v);
-        sH[e] = v;
+    // H pass, then V pass.  An output is a chain of fw dependent fused multiply-adds in tap order (the order is the contract); a thread carries four
+    // outputs through the tap loop at once so that four chains overlap.
+    // Output column x0 + c clamps its taps in IMAGE coordinates: tap i reads clamp(x0 + c - half + i); the staged tile holds clamp(x0 - half + t) at
+    // position t, so for in-image output columns position c + i is exactly that pixel.
+    for (int base = threadIdx.x; base < iw * ow; base += 4 * (int)blockDim.x) {
+        float acc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+        int src[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int e = base + u * (int)blockDim.x; src[u] = e < iw * ow ? (e / ow) * iw + e % ow : 0; }
+        for (int i = 0; i < a.fw; ++i) {
+            const float t = a.taps[i];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmaf(sIn[src[u] + i], t, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int e = base + u * (int)blockDim.x; if (e < iw * ow) sH[e] = acc[u]; }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < ow * ow; e += blockDim.x) {
-        const int r = e / ow, c = e % ow;
-        float v = 0.0f;
-        for (int i = 0; i < a.fw; ++i) v = fmaf(sH[(r + i) * ow + c], a.taps[i], v);
-        sOut[e] = v;
+    for (int base = threadIdx.x; base < ow * ow; base += 4 * (int)blockDim.x) {
+        float acc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+        int src[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int e = base + u * (int)blockDim.x; src[u] = e < ow * ow ? e : 0; }          // sH[(r + i) * ow + c] = sH[e + i * ow]
+        for (int i = 0; i < a.fw; ++i) {
+            const float t = a.taps[i];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmaf(sH[src[u] + i * ow], t, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int e = base + u * (int)blockDim.x; if (e < ow * ow) sOut[e] = acc[u]; }
     }
     __syncthreads();
     for (int e = threadIdx.x; e < SD_TILE * SD_TILE; e += blockDim.x) {

@@ -50,7 +50,9 @@ sift_fuse_kernel(const __grid_constant__ FuseArgs a) {
     unsigned* stackPos = stackKey + FUSE_STACK;   // [FUSE_STACK]
     unsigned* scan = stackPos + FUSE_STACK;       // [FUSE_THREADS]
     unsigned* rootList = scan + FUSE_THREADS;     // [2C]      keys with a non-empty list, in (image, key) order: the only roots that can start a track
-    unsigned char* marker = reinterpret_cast<unsigned char*>(rootList + 2 * C);          // [M]
+    unsigned* ckx = rootList + 2 * C;             // [C]       key of the correspondence in image i (0xFFFFFFFF: invalid correspondence) ...
+    unsigned* cky = ckx + C;                      // [C]       ... and in image j: staged by all threads so that the serial list fill reads shared memory only
+    unsigned char* marker = reinterpret_cast<unsigned char*>(cky + C);                   // [M]
     unsigned char* errOk = marker + ((M + 3) & ~3u);                                      // [C]
     __shared__ unsigned sNumTracks, sOverflow, sNumRoots, sTotal;
 
@@ -62,8 +64,10 @@ sift_fuse_kernel(const __grid_constant__ FuseArgs a) {
     for (unsigned c = t; c < C; c += FUSE_THREADS) {
         const BFEntryJ e = a.corr[c];
         unsigned char ok = 0;
+        ckx[c] = 0xFFFFFFFFu; cky[c] = 0xFFFFFFFFu;
         if (e.imgIdx_i != 0xFFFFFFFFu) {
             const uint2 k = a.keyIdx[c];
+            ckx[c] = k.x; cky[c] = k.y;
             atomicAdd(&start[k.x + 1], 1u); atomicAdd(&start[k.y + 1], 1u);
             float pa[3], pb[3];
             xform3(a.T + 16 * (size_t)e.imgIdx_i, e.pos_i, pa); xform3(a.T + 16 * (size_t)e.imgIdx_j, e.pos_j, pb);
@@ -98,11 +102,10 @@ sift_fuse_kernel(const __grid_constant__ FuseArgs a) {
         const unsigned total = start[M];
         sTotal = total;                                  // start[M] is about to become the begin of the last key's list
         for (int c = (int)C - 1; c >= 0; --c) {
-            const BFEntryJ e = a.corr[c];
-            if (e.imgIdx_i == 0xFFFFFFFFu) continue;
-            const uint2 k = a.keyIdx[c];
-            const unsigned sy = --start[k.y + 1]; adjKey[sy] = k.x; adjCE[sy] = 2u * (unsigned)c + 1u;
-            const unsigned sx = --start[k.x + 1]; adjKey[sx] = k.y; adjCE[sx] = 2u * (unsigned)c;
+            const unsigned kx = ckx[c], ky = cky[c];
+            if (kx == 0xFFFFFFFFu) continue;
+            const unsigned sy = --start[ky + 1]; adjKey[sy] = kx; adjCE[sy] = 2u * (unsigned)c + 1u;
+            const unsigned sx = --start[kx + 1]; adjKey[sx] = ky; adjCE[sx] = 2u * (unsigned)c;
         }
     }
     __syncthreads();
@@ -242,7 +245,7 @@ BF_API int bfSiftFuseToGlobal(const BFEntryJ* d_corr, const uint32_t* d_corrKeyI
     a.keys = d_keyPoints; a.descs = d_descriptors; a.numKeys = d_numKeysPerImage; a.keyStride = keyStride;
     for (int k = 0; k < 16; ++k) a.K[k] = colorIntrinsics[k];
     a.outKeys = d_outKeyPoints; a.outDescs = d_outDescriptors; a.outNum = d_outNumKeys; a.maxKeys = maxKeys; a.status = d_status;
-    const size_t words = (size_t)(M + 1) + 8 * (size_t)maxCorr + (maxCorr + 1) + 2 * FUSE_STACK + FUSE_THREADS;
+    const size_t words = (size_t)(M + 1) + 10 * (size_t)maxCorr + (maxCorr + 1) + 2 * FUSE_STACK + FUSE_THREADS;
     const size_t bytes = words * 4 + ((M + 3) & ~3u) + ((maxCorr + 3) & ~3u);
     static size_t attr = 0;
     if (bytes > attr) { BF_CHECK(cudaFuncSetAttribute(sift_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); attr = bytes; }
