@@ -167,7 +167,10 @@ __device__ __forceinline__ bool cmp_rows(const float* img, int idx, float v, flo
     return false;
 }
 
-__device__ bool key_test(const SdCommon& s, const float* depth, int o, int j, int row, int col) {
+// The test in two parts so that a thread can have the first loads of several pixels in flight: key_where gives the two addresses every pixel's test
+// starts with (its depth sample and its own DoG value; false: the pixel is out of range), key_test runs the rejections on the loaded values.  All of them
+// are pure rejections, so loading d and v before the range tests changes nothing.
+__device__ __forceinline__ bool key_where(const SdCommon& s, int o, int row, int col, int& depthIdx, int& index) {
     const SdPyr& oc = s.oc[o];
     const int w = oc.w;
     if (!(row > 0 && col > 0 && row < oc.h - 2 && col < w - 2)) return false;
@@ -176,11 +179,17 @@ __device__ bool key_test(const SdCommon& s, const float* depth, int o, int j, in
     const int dxp = (int)roundf((keyLocScale * (float)col + 0.5f) * (float)(P.depthWidth - 1) / (float)(P.width - 1));
     const int dyp = (int)roundf((keyLocScale * (float)row + 0.5f) * (float)(P.depthHeight - 1) / (float)(P.height - 1));
     if (dxp < 0 || dxp >= (int)P.depthWidth || dyp < 0 || dyp >= (int)P.depthHeight) return false;
-    const float d = __ldg(&depth[(size_t)dyp * P.depthWidth + dxp]);
+    depthIdx = dyp * (int)P.depthWidth + dxp;
+    index = row * w + col;
+    return true;
+}
+__device__ bool key_test(const SdCommon& s, int o, int j, int row, int col, float d, float v) {
+    const SdPyr& oc = s.oc[o];
+    const int w = oc.w;
+    const BFSiftDetectParams& P = s.P;
     if (d == -INFINITY || d < P.depthMin || d > P.depthMax) return false;
     const float* dogP = oc.dog[j + 1]; const float* dogC = oc.dog[j + 2]; const float* dogN = oc.dog[j + 3];
     const int index = row * w + col, up = index - w, dn = index + w;
-    const float v = __ldg(&dogC[index]);
     if (fabsf(v) <= s.dogThreshold) return false;
     const float l = __ldg(&dogC[index - 1]), r = __ldg(&dogC[index + 1]);
     float nmax = fmaxf(l, r), nmin = fminf(l, r);
@@ -215,9 +224,27 @@ sift_key_rows_kernel(const __grid_constant__ SdCommon s, const float* __restrict
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) sBase = kEmit ? s.rowOffset[blockIdx.x] : 0;
     __syncthreads();
+    // this thread's pixels: columns t, t + 128, ...  First the two loads every test starts with, for all of them (independent, in flight together);
+    // then the tests, which go on to further loads only for the few pixels that pass the threshold
+    const float* __restrict__ dogC = s.oc[o].dog[j + 2];
+    unsigned hitMask = 0;
+    for (int c0 = 0; c0 < w; c0 += 128 * 8) {
+        float dv[8], vv[8]; bool ok[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int col = c0 + 128 * k + t;
+            int di = 0, ix = 0;
+            ok[k] = col < w && key_where(s, o, row, col, di, ix);
+            dv[k] = ok[k] ? __ldg(&depth[di]) : 0.0f;
+            vv[k] = ok[k] ? __ldg(&dogC[ix]) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (ok[k] && key_test(s, o, j, row, c0 + 128 * k + t, dv[k], vv[k])) hitMask |= 1u << ((c0 >> 7) + k);
+    }
     for (int c0 = 0; c0 < w; c0 += 128) {
         const int col = c0 + t;
-        const bool hit = col < w && key_test(s, depth, o, j, row, col);
+        const bool hit = (hitMask >> (c0 >> 7)) & 1u;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
         if (lane == 0) sWarp[warp] = __popc(m);
         __syncthreads();
@@ -535,7 +562,7 @@ using namespace bf;
 BF_API int bfSiftDetect(const BFSiftDetectParams* params, const float* d_intensity, const float* d_depth, BFSIFTKeyPoint* d_keyPoints, uint8_t* d_descriptors,
                         int32_t* d_numKeyPoints, int32_t* d_levelCounts) {
     if (!params || !d_intensity || !d_depth || !d_keyPoints || !d_descriptors || !d_numKeyPoints) return (int)cudaErrorInvalidValue;
-    if ((params->width & 31u) || params->width < 64 || params->height < 64 || (params->height & 7u) || params->maxKeyPoints == 0) return (int)cudaErrorInvalidValue;
+    if ((params->width & 31u) || params->width < 64 || params->width > 4096 || params->height < 64 || (params->height & 7u) || params->maxKeyPoints == 0) return (int)cudaErrorInvalidValue;   // width <= 4096: a row's hit flags are one 32-bit mask per thread
     const int rc = sd_ensure(params);
     if (rc) return rc;
     SdWorkspace& ws = g_sd;
