@@ -24,17 +24,12 @@ F = np.float32
 
 _PRE = r'''
 #include "%(emu)s"
-static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
-static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     const unsigned long long v = ((unsigned long long)y << 32) | x; unsigned r = 0;
     for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
     return r;
 }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
-static inline int __float2int_rz(float f) {                 // cvt.rzi.s32.f32: NaN -> 0, saturating
-    if (f != f) return 0; if (f >= 2147483648.0f) return 2147483647; if (f <= -2147483648.0f) return (int)0x80000000; return (int)f;
-}
 static inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 static inline unsigned warp_sum_u(unsigned v) { return v; }
