@@ -34,7 +34,7 @@ __device__ __forceinline__ unsigned src_index(unsigned o, float scale) { return 
 // ---- the application's configuration (two 7x7 erosions, 9x9 Gaussian: zParametersDefault.txt) with compile-time extents ----------------------
 // Same operations in the same order as the generic loops of ingest_kernel; what changes is what the compiler can do with them: the 49 / 81 taps are
 // unrolled (tile addresses become immediate offsets, the Gaussian weights immediate constant-bank operands), the element <-> (tx, ty) maps divide by
-// constants, and a tile whose halo lies inside the image (234 of the 300 tiles of a 640x480 frame) runs without the per-tap bounds tests.
+// constants, and no tap tests the image bounds: pixels outside the image are staged as NaN, which no tap test accepts (see the staging comment).
 #define BF_ING_FS 3
 #define BF_ING_FR 4
 #define BF_ING_FDIM (BF_ING_T + 2 * (2 * BF_ING_FS + BF_ING_FR))
@@ -45,20 +45,17 @@ __device__ __forceinline__ void erode_pass_fast(const float* __restrict__ in, fl
     const float sumWin = (float)(unsigned)((2 * S + 1) * (2 * S + 1));
     for (int e = threadIdx.x; e < WD * WD; e += blockDim.x) {
         const int tx = M0 + e % WD, ty = M0 + e / WD, gx = x0 + tx, gy = y0 + ty;
-        if (BORDER && (gx < 0 || gx >= W || gy < 0 || gy >= H)) continue;
+        if (BORDER && (gx < 0 || gx >= W || gy < 0 || gy >= H)) { out[ty * DIM + tx] = nanf(""); continue; }      // stays "outside" for the next pass
         const float* c = in + ty * DIM + tx;
         const float old = c[0];
         unsigned count = 0;
 #pragma unroll
-        for (int i = -S; i <= S; ++i) {
-            const bool rowIn = !BORDER || (gy + i >= 0 && gy + i < H);
+        for (int i = -S; i <= S; ++i)
 #pragma unroll
-            for (int j = -S; j <= S; ++j)
-                if (rowIn && (!BORDER || (gx + j >= 0 && gx + j < W))) {
-                    const float d = c[i * DIM + j];
-                    if (d == -INFINITY || d == 0.0f || fabsf(d - old) > dThresh) ++count;
-                }
-        }
+            for (int j = -S; j <= S; ++j) {
+                const float d = c[i * DIM + j];                              // an out-of-image tap is NaN: none of the three tests holds
+                if (d == -INFINITY || d == 0.0f || fabsf(d - old) > dThresh) ++count;
+            }
         out[ty * DIM + tx] = ((float)count / sumWin >= fracReq) ? -INFINITY : old;
     }
 }
@@ -76,15 +73,12 @@ __device__ __forceinline__ void gauss_pass_fast(const IngestArgs& a, const float
         if (c != -INFINITY) {
             float sum = 0.0f, sumW = 0.0f;
 #pragma unroll
-            for (int m = -R; m <= R; ++m) {
-                const bool colIn = !BORDER || (gx + m >= 0 && gx + m < W);
+            for (int m = -R; m <= R; ++m)
 #pragma unroll
-                for (int n = -R; n <= R; ++n)
-                    if (colIn && (!BORDER || (gy + n >= 0 && gy + n < H))) {
-                        const float cur = cp[n * DIM + m];
-                        if (cur != -INFINITY && fabsf(c - cur) < sigmaR) { const float wgt = a.wG[(m + R) * SPAN + (n + R)]; sumW += wgt; sum += wgt * cur; }
-                    }
-            }
+                for (int n = -R; n <= R; ++n) {
+                    const float cur = cp[n * DIM + m];                       // out-of-image: NaN, |c - NaN| < sigmaR is false
+                    if (cur != -INFINITY && fabsf(c - cur) < sigmaR) { const float wgt = a.wG[(m + R) * SPAN + (n + R)]; sumW += wgt; sum += wgt * cur; }
+                }
             if (sumW > 0.0f) res = sum / sumW;
         }
         out[ty * DIM + tx] = res;
@@ -111,10 +105,12 @@ ingest_kernel(const __grid_constant__ IngestArgs a) {
             if (xi < (unsigned)CW && yi < (unsigned)CH) a.colorOut[i] = __ldg(&a.colorRaw[yi * CW + xi]);
         }
     }
-    // ---- depth: stage the raw tile + halo (elements outside the image are never read back: every consumer tests the bounds) ----
+    // ---- depth: stage the raw tile + halo.  Elements outside the image hold NaN: the generic passes never read them (they test the bounds), the
+    // compile-time passes read them and need no bounds test -- a NaN tap is not -inf, not 0, and no comparison with it holds, so it is skipped exactly as
+    // the reference's bounds test skips it (and an in-image NaN behaves as it does in the reference) ----
     for (int e = threadIdx.x; e < dim * dim; e += blockDim.x) {
         const int gx = x0 + e % dim, gy = y0 + e / dim;
-        bufA[e] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? __ldg(&a.depthRaw[gy * W + gx]) : 0.0f;
+        bufA[e] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? __ldg(&a.depthRaw[gy * W + gx]) : nanf("");     // outside the image: NaN fails every tap test below by itself
     }
     __syncthreads();
     float* out;
