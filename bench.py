@@ -362,7 +362,8 @@ def run_loop(args):
     if world > 1:
         P.hash.m_dummy = (world << 32) | rank                   # spatial shard of the voxel hash: this rank integrates the blocks it owns
     clk_lines, stop_evt = [], threading.Event()
-    th = threading.Thread(target=clocks_sampler, args=(stop_evt, clk_lines, local), daemon=True); th.start()
+    if rank == 0:                                              # the line is rank 0's: one nvidia-smi loop per box, not one per rank (NVML queries contend with the ranks' launches)
+        th = threading.Thread(target=clocks_sampler, args=(stop_evt, clk_lines, local), daemon=True); th.start()
     loop = FrameLoop(P, dev)
     overlap = os.environ.get("BF_LOOP_OVERLAP", "1") != "0"
     loop.set_overlap(overlap)
