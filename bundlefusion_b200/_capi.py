@@ -108,6 +108,9 @@ TSDF_SYMBOLS = [
 
 HOST_SYMBOLS = ["bfMat4Inverse", "bfTsdfRunOps"]
 
+SENS_SYMBOLS = ["bfSensOpen", "bfSensReadFrame", "bfSensReadFrameRaw", "bfSensClose", "bfSensCreate", "bfSensAppendFrame", "bfSensFinish",
+                "bfSensDecodeJpeg", "bfSensDecodePng", "bfSensErrorString"]
+
 RAYCAST_SYMBOLS = ["updateConstantRayCastParams", "rayIntervalSplatCUDA", "resetRayIntervalSplatCUDA", "renderCS",
                    "bfRayCastSplat", "bfRayCastRender", "bfRayCastComputeNormals", "bfRayCastRenderPose"]
 

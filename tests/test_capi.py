@@ -54,6 +54,7 @@ def test_symbol_list_matches_header():
     assert sorted(set(_declared_symbols("bf_ingest.h"))) == sorted(set(capi.INGEST_SYMBOLS))
     assert sorted(set(_declared_symbols("bf_bundler.h"))) == sorted(set(capi.BUNDLER_SYMBOLS))
     assert sorted(set(_declared_symbols("bf_raycast.h"))) == sorted(set(capi.RAYCAST_SYMBOLS))
+    assert sorted(set(_declared_symbols("bf_sens.h"))) == sorted(set(capi.SENS_SYMBOLS))
 
 
 def test_raycast_pod_layouts():
