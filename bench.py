@@ -127,10 +127,10 @@ class Workload:
         return ops
 
 
-def make_ba_problems():
+def make_ba_problems(global_keyframes=None, global_degree=None):
     from bundlefusion_b200 import synth
     loc = synth.make_dense_ba_problem(11, stride=3, start=100, corr_per_pair=25, noise=0.002, seed=31)    # sparse + dense 80x60 caches
-    glo = synth.make_ba_problem(WORKLOAD["global_keyframes"], degree=WORKLOAD["global_degree"], corr_per_pair=25, noise=0.002, seed=32, stride=10)
+    glo = synth.make_ba_problem(global_keyframes or WORKLOAD["global_keyframes"], degree=global_degree or WORKLOAD["global_degree"], corr_per_pair=25, noise=0.002, seed=32, stride=10)
     return loc, glo
 
 
@@ -723,6 +723,9 @@ def reference_cuda_leg(dev, n_frames=12):
             "sample": f"{n_frames} frames of 1 integrate + 10 re-integrations + GC at 1 cm voxels; 3 repetitions of the local (11 frames, sparse + dense) and global (500 keyframes) solves"}
 
 # ------------------------------------------------------------------------------------------------------------------------
+LOOP_KEYFRAMES_CPU = 40          # keyframes of the CPU arm's global solve: the middle of what the loop's timed stretches hold (25 .. 55 after a 250-frame pre-roll)
+
+
 def cpu_arm(steps, warmup, quiet=False, n_reint=None):
     """The reference's algorithm on the host cores: oracle port (liboracle_fast.so: -O3 -march=native, OpenMP over blocks for the
     integrate stencil; alloc / compactify / solver single-threaded as restated).  The heap is sized for the sample (400k blocks)
@@ -740,7 +743,7 @@ def cpu_arm(steps, warmup, quiet=False, n_reint=None):
     for d, c, T in frames:
         scene.integrate(T, d, c, cam)
     wl = Workload([f[2] for f in frames])
-    loc, glo = make_ba_problems()
+    loc, glo = make_ba_problems(LOOP_KEYFRAMES_CPU, 10)
     def ba():
         orc.solve(loc["corr"], loc["init_rot"], loc["init_trans"], 2, 100, [1.0, 1.0], [1.0, 2.0], [0.0, 0.0], loc["caches"], loc["intrinsics"], fast=True)
         orc.solve_sparse(glo["corr"], glo["init_rot"], glo["init_trans"], 3, 150, fast=True)
@@ -758,14 +761,40 @@ def cpu_arm(steps, warmup, quiet=False, n_reint=None):
         step(f, False)
     t_tsdf = (time.perf_counter() - t0) / steps
     t0 = time.perf_counter(); ba(); t_ba = time.perf_counter() - t0
+    t_feat, t_chunk_feat, n_keys = cpu_feature_share(orc, synth)
     # scale the TSDF part to the full 10 re-integrations per frame if a reduced sample was timed
     passes_timed, passes_full = 2 * n_re + 1, 2 * WORKLOAD["reintegrations_per_frame"] + 1
-    per_frame = t_tsdf * passes_full / passes_timed + t_ba / WORKLOAD["chunk"]
+    per_frame = t_tsdf * passes_full / passes_timed + t_ba / WORKLOAD["chunk"] + t_feat + t_chunk_feat / WORKLOAD["chunk"]
     cores = os.cpu_count() or 1
     return {"value": round(1.0 / per_frame, 4), "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": f"{steps} frame(s) x ({n_re} re-integrations + 1 integrate + GC) at 640x480 scaled to {WORKLOAD['reintegrations_per_frame']} re-integrations, "
-                      f"+ 1 local and 1 global BA solve / {WORKLOAD['chunk']} frames; TSDF {t_tsdf:.2f} s per sampled frame, BA {t_ba:.2f} s per chunk; "
-                      f"OpenMP threads = {cores} on the integrate stencil and the alloc ray walk; hash insertions, compactify, GC and the bundle adjustment single-threaded as restated"}
+                      f"+ 1 local (11 frames, sparse + dense) and 1 global ({LOOP_KEYFRAMES_CPU} keyframes, {len(glo['corr'])} correspondences) BA solve / {WORKLOAD['chunk']} frames; TSDF {t_tsdf:.2f} s per sampled frame, BA {t_ba:.2f} s per chunk; "
+                      f"feature share of a frame (ingest, SIFT detection: {n_keys} key points, dense cache, descriptor match against 5 frames of the chunk) {t_feat:.2f} s on 2 sampled frames, "
+                      f"keyframe matching against 30 keyframes {t_chunk_feat:.2f} s per chunk (match filters left out: < 1 ms per frame on one core); "
+                      f"OpenMP threads = {cores} on the integrate stencil and the alloc ray walk; hash insertions, compactify, GC, the bundle adjustment and the feature stages single-threaded as restated"}
+
+
+def cpu_feature_share(orc, synth):
+    """seconds per frame of the frame's feature stages on the host (oracle port, one core), and seconds per chunk of the keyframe matching"""
+    fr = [synth.make_frame(2 * i, W, H, texture="rich") for i in range(3)]
+    K = np.eye(4, dtype=np.float32); K[0, 0] = K[1, 1] = 525.0 * W / 640.0; K[0, 2] = (W - 1) / 2.0; K[1, 2] = (H - 1) / 2.0
+    des, n_keys = [], 0
+    t0 = time.perf_counter()
+    for d, c, T in fr[:2]:
+        dd, cc = orc.ingest_frame(d, c, W, H)                                                      # CUDAImageManager::process
+        inten = ((0.299 * c[..., 0].astype(np.float32) + 0.587 * c[..., 1].astype(np.float32) + 0.114 * c[..., 2].astype(np.float32)) / 255.0).astype(np.float32)
+        kp, de, _ = orc.sift_detect(inten, dd, depthMin=0.1, depthMax=4.0)                         # Bundler::detectFeatures
+        orc.cache_store_frame(d, c, K, 80, 60)                                                     # CUDACache::storeFrame
+        des.append(de); n_keys = len(de)
+    t_front = (time.perf_counter() - t0) / 2
+    t0 = time.perf_counter()
+    for _ in range(5):                                                                             # a chunk's frame meets 1 .. 10 earlier frames: 5.5 on average
+        orc.sift_match(des[0], des[1], fast=True)
+    t_match = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(30):                                                                            # a keyframe against the keyframes so far (25 .. 55 on the bench stream)
+        orc.sift_match(des[0], des[1], fast=True)
+    return t_front + t_match, time.perf_counter() - t0, n_keys
 
 
 def run_reference(args):
@@ -778,7 +807,7 @@ def run_reference(args):
     wall = time.perf_counter() - t0
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
            "steps": K, "warmup": Wm, "ms_per_step": round(1e3 / base["value"], 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, note="CPU arm: oracle port of the reference algorithm on the host cores (the reference ships no CPU path of its own; its CUDA path, rebuilt for sm_100a, is timed in the default arm's `reference_cuda` entry).  It covers the TSDF + bundle-adjustment SHARE of the default arm's step only -- 1 integrate + 10 re-integrations + GC per frame, one local and one global solve per 10 frames -- not ingest / SIFT detection / matching / filters, which the default arm's frame loop also runs: the ratio to this arm understates the CPU cost of the same work"),
+           "dtype": "f32", "data": "synthetic", "config": dict(LOOP_WORKLOAD, note="CPU arm: oracle port of the reference algorithm on the host cores (the reference ships no CPU path of its own; its CUDA path, rebuilt for sm_100a, is timed in the default arm's `reference_cuda` entry).  It times the stages of the default arm's step by bounded samples -- per frame 1 integrate + 10 re-integrations + GC, ingest, SIFT detection, dense cache, descriptor matching against the chunk; per 10 frames one local and one global solve and the keyframe matching -- and adds them up; the match filters (sub-millisecond per frame on one core) and the host sequencing are left out"),
            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": round(wall, 1)}
     print(json.dumps(out))
 
