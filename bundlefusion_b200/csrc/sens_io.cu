@@ -134,22 +134,46 @@ int huff_decode(BitReader& br, const Huff& h) {
 int extend(int v, int t) { return (t && v < (1 << (t - 1))) ? v - (1 << t) + 1 : v; }          // T.81 F.2.2.1
 const uint8_t kZigzag[64] = { 0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
                               35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
-struct IdctTable { float c[8][8]; IdctTable() { for (int x = 0; x < 8; ++x) for (int u = 0; u < 8; ++u) c[x][u] = (float)((u == 0 ? std::sqrt(0.125) : 0.5) * std::cos((2 * x + 1) * u * M_PI / 16.0)); } };
-void idct_block(const float in[64], uint8_t* out, size_t stride) {                              // s(y, x) = sum_v sum_u C(y, v) C(x, u) S(v, u), T.81 A.3.3
-    static const IdctTable T;
-    float tmp[64];
-    for (int v = 0; v < 8; ++v) {
-        const float* s = in + 8 * v;
-        if (s[1] == 0 && s[2] == 0 && s[3] == 0 && s[4] == 0 && s[5] == 0 && s[6] == 0 && s[7] == 0) { const float d = s[0] * T.c[0][0]; for (int x = 0; x < 8; ++x) tmp[8 * v + x] = d; continue; }
-        for (int x = 0; x < 8; ++x) { float a = 0; for (int u = 0; u < 8; ++u) a += T.c[x][u] * s[u]; tmp[8 * v + x] = a; }
+// The inverse DCT of the reference's decoder (stb_image v2.08, vendored by mLib: a fixed-point rendering of the Loeffler-Ligtenberg-Moschytz flow graph, 12
+// fractional bits, two extra bits kept between the passes), restated so that decoded pixels are the reference's, bit for bit: decoders are free to differ in the
+// last level here, and SIFT would see the difference.  Input: de-quantised coefficients as 16-bit integers in natural order.
+#define BF_F2F(x) ((int)(((x) * 4096 + 0.5)))
+struct Lines { int x0, x1, x2, x3, t0, t1, t2, t3; };
+static inline Lines idct_1d(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7) {
+    int p2 = s2, p3 = s6;
+    int p1 = (p2 + p3) * BF_F2F(0.5411961f);
+    int t2 = p1 + p3 * BF_F2F(-1.847759065f), t3 = p1 + p2 * BF_F2F(0.765366865f);
+    p2 = s0; p3 = s4;
+    int t0 = (p2 + p3) << 12, t1 = (p2 - p3) << 12;
+    Lines L;
+    L.x0 = t0 + t3; L.x3 = t0 - t3; L.x1 = t1 + t2; L.x2 = t1 - t2;
+    t0 = s7; t1 = s5; t2 = s3; t3 = s1;
+    p3 = t0 + t2; int p4 = t1 + t3; p1 = t0 + t3; p2 = t1 + t2;
+    const int p5 = (p3 + p4) * BF_F2F(1.175875602f);
+    t0 = t0 * BF_F2F(0.298631336f); t1 = t1 * BF_F2F(2.053119869f); t2 = t2 * BF_F2F(3.072711026f); t3 = t3 * BF_F2F(1.501321110f);
+    p1 = p5 + p1 * BF_F2F(-0.899976223f); p2 = p5 + p2 * BF_F2F(-2.562915447f); p3 = p3 * BF_F2F(-1.961570560f); p4 = p4 * BF_F2F(-0.390180644f);
+    L.t3 = t3 + p1 + p4; L.t2 = t2 + p2 + p3; L.t1 = t1 + p2 + p4; L.t0 = t0 + p1 + p3;
+    return L;
+}
+static inline uint8_t clamp_u8(int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+void idct_block(const short d[64], uint8_t* out, size_t stride) {
+    int val[64];
+    for (int i = 0; i < 8; ++i) {                    // columns; a column whose AC terms are all zero is its DC term, scaled like the others
+        const short* c = d + i; int* v = val + i;
+        if (c[8] == 0 && c[16] == 0 && c[24] == 0 && c[32] == 0 && c[40] == 0 && c[48] == 0 && c[56] == 0) { const int dc = c[0] << 2; for (int k = 0; k < 8; ++k) v[8 * k] = dc; continue; }
+        Lines L = idct_1d(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56]);
+        L.x0 += 512; L.x1 += 512; L.x2 += 512; L.x3 += 512;                                   // 12 bits down to 2: round at bit 10
+        v[0] = (L.x0 + L.t3) >> 10; v[56] = (L.x0 - L.t3) >> 10; v[8] = (L.x1 + L.t2) >> 10; v[48] = (L.x1 - L.t2) >> 10;
+        v[16] = (L.x2 + L.t1) >> 10; v[40] = (L.x2 - L.t1) >> 10; v[24] = (L.x3 + L.t0) >> 10; v[32] = (L.x3 - L.t0) >> 10;
     }
-    for (int x = 0; x < 8; ++x)
-        for (int y = 0; y < 8; ++y) {
-            float a = 0;
-            for (int v = 0; v < 8; ++v) a += T.c[y][v] * tmp[8 * v + x];
-            const int q = (int)std::lrintf(a) + 128;
-            out[(size_t)y * stride + x] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
-        }
+    for (int i = 0; i < 8; ++i) {                    // rows: 12 + 2 + 3 bits to remove, level shift by 128 folded into the rounding constant
+        const int* v = val + 8 * i; uint8_t* o = out + (size_t)i * stride;
+        Lines L = idct_1d(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        const int bias = 65536 + (128 << 17);
+        L.x0 += bias; L.x1 += bias; L.x2 += bias; L.x3 += bias;
+        o[0] = clamp_u8((L.x0 + L.t3) >> 17); o[7] = clamp_u8((L.x0 - L.t3) >> 17); o[1] = clamp_u8((L.x1 + L.t2) >> 17); o[6] = clamp_u8((L.x1 - L.t2) >> 17);
+        o[2] = clamp_u8((L.x2 + L.t1) >> 17); o[5] = clamp_u8((L.x2 - L.t1) >> 17); o[3] = clamp_u8((L.x3 + L.t0) >> 17); o[4] = clamp_u8((L.x3 - L.t0) >> 17);
+    }
 }
 struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; int bw = 0, bh = 0; size_t stride = 0; std::vector<uint8_t> plane; };
 
@@ -158,7 +182,7 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
     uint16_t qt[4][64]; bool qset[4] = { false, false, false, false };
     Huff hdc[4], hac[4];
     std::vector<Comp> comps;
-    int width = 0, height = 0, hmax = 1, vmax = 1, restart = 0, adobeTransform = -1;
+    int width = 0, height = 0, hmax = 1, vmax = 1, restart = 0;
     bool haveFrame = false, decoded = false;
     size_t at = 2;
     while (at + 4 <= n) {
@@ -212,7 +236,6 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
             if (!rgb) return BF_SENS_OK;
         } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) return BF_SENS_ERR_UNSUPPORTED;    // progressive, lossless, arithmetic
         else if (m == 0xDD) { if (sl < 2) return BF_SENS_ERR_FORMAT; restart = (s[0] << 8) | s[1]; }
-        else if (m == 0xEE && sl >= 12 && !memcmp(s, "Adobe", 5)) adobeTransform = s[11];
         else if (m == 0xDA) {                                                         // SOS + entropy-coded segment
             if (!haveFrame || sl < 1) return BF_SENS_ERR_FORMAT;
             const int ns = s[0];
@@ -247,11 +270,11 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
                         const int nbx = inter ? c->h : 1, nby = inter ? c->v : 1;
                         for (int by = 0; by < nby; ++by)
                             for (int bx = 0; bx < nbx; ++bx) {
-                                float blk[64]; for (int k = 0; k < 64; ++k) blk[k] = 0.0f;
+                                short blk[64]; for (int k = 0; k < 64; ++k) blk[k] = 0;
                                 const int t = huff_decode(br, hdc[c->td]);
                                 if (t < 0 || t > 11) return BF_SENS_ERR_FORMAT;
                                 c->pred += extend(br.bits(t), t);
-                                blk[0] = (float)(c->pred * (int)qt[c->tq][0]);
+                                blk[0] = (short)(c->pred * (int)qt[c->tq][0]);
                                 for (int k = 1; k < 64;) {
                                     const int rs = huff_decode(br, hac[c->ta]);
                                     if (rs < 0) return BF_SENS_ERR_FORMAT;
@@ -259,7 +282,7 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
                                     if (sz == 0) { if (r == 15) { k += 16; continue; } break; }
                                     k += r;
                                     if (k > 63) return BF_SENS_ERR_FORMAT;
-                                    blk[kZigzag[k]] = (float)(extend(br.bits(sz), sz) * (int)qt[c->tq][k]);
+                                    blk[kZigzag[k]] = (short)(extend(br.bits(sz), sz) * (int)qt[c->tq][k]);
                                     ++k;
                                 }
                                 const int gx = (inter ? mx * c->h : mx) + bx, gy = (inter ? my * c->v : my) + by;
@@ -275,47 +298,56 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
         at += len;
     }
     if (!haveFrame || !decoded) return BF_SENS_ERR_FORMAT;
-    // ---- up-sample to full resolution (triangle filter for 2:1, as libjpeg's "fancy" up-sampling and stb_image's default), colour conversion ----
-    const size_t fw = (size_t)comps[0].bw * 8 / comps[0].h * hmax;                    // full width of the MCU-padded image
-    std::vector<std::vector<uint8_t>> full(comps.size());
-    for (size_t ci = 0; ci < comps.size(); ++ci) {
-        Comp& c = comps[ci];
-        const int sx = hmax / c.h, sy = vmax / c.v;
-        const size_t cw = c.stride, chh = (size_t)c.bh * 8;
-        const size_t uw = ((size_t)width * c.h + hmax - 1) / hmax, uh = ((size_t)height * c.v + vmax - 1) / vmax;      // the component's true (un-padded) size
-        if (sx == 1 && sy == 1) { full[ci].swap(c.plane); continue; }
-        std::vector<uint8_t>& o = full[ci];
-        o.assign(fw * chh * sy, 0);
-        std::vector<int> colsum(cw);
-        for (size_t oy = 0; oy < uh * sy; ++oy) {
-            const size_t iy = oy / sy;
-            // vertical: 3/4 of the nearer row + 1/4 of the farther one (replicated at the edges); sy == 1: the row itself, scaled by 4 to share the code
-            size_t far = iy;
-            if (sy == 2) { if (oy & 1) far = iy + 1 < uh ? iy + 1 : iy; else far = iy > 0 ? iy - 1 : iy; }
-            const uint8_t* rn = c.plane.data() + iy * cw; const uint8_t* rf = c.plane.data() + far * cw;
-            for (size_t x = 0; x < uw; ++x) colsum[x] = sy == 2 ? 3 * rn[x] + rf[x] : 4 * rn[x];
-            uint8_t* orow = o.data() + oy * fw;
-            if (sx == 1) { for (size_t x = 0; x < uw; ++x) orow[x] = (uint8_t)((colsum[x] + 2) >> 2); continue; }
-            for (size_t x = 0; x < uw; ++x) {
-                const int t = colsum[x], l = x > 0 ? colsum[x - 1] : t, r = x + 1 < uw ? colsum[x + 1] : t;
-                if (sy == 2) { orow[2 * x] = (uint8_t)((3 * t + l + 8) >> 4); orow[2 * x + 1] = (uint8_t)((3 * t + r + 7) >> 4); }                 // h2v2: 16ths of the 2-D triangle
-                else { orow[2 * x] = (uint8_t)((3 * (t >> 2) + (l >> 2) + 1) >> 2); orow[2 * x + 1] = (uint8_t)((3 * (t >> 2) + (r >> 2) + 2) >> 2); }   // h2v1: quarters, libjpeg's rounding pattern
+    // ---- up-sample and convert, row by row, with the reference decoder's arithmetic (stb_image v2.08: load_jpeg_image and its resample_row_* / YCbCr kernels):
+    // vertically 3/4 of the nearer chroma row + 1/4 of the farther one, horizontally the same triangle on those sums; fixed-point JFIF conversion ----
+    std::vector<std::vector<uint8_t>> line(comps.size());
+    for (size_t ci = 0; ci < comps.size(); ++ci) line[ci].assign((size_t)width + 8, 0);
+    for (int y = 0; y < height; ++y) {
+        const uint8_t* row[3] = { nullptr, nullptr, nullptr };
+        for (size_t ci = 0; ci < comps.size(); ++ci) {
+            Comp& c = comps[ci];
+            const int hs = hmax / c.h, vs = vmax / c.v;
+            const int lores = (width + hs - 1) / hs;                                          // samples of this component under the image's width
+            const int ch = (height * c.v + vmax - 1) / vmax;                                  // its rows under the image's height
+            int iy = y / vs, fy = iy;
+            if (vs == 2) { fy = (y & 1) ? (iy + 1 < ch ? iy + 1 : iy) : (iy > 0 ? iy - 1 : iy); }
+            const uint8_t* nr = c.plane.data() + (size_t)iy * c.stride; const uint8_t* fr = c.plane.data() + (size_t)fy * c.stride;
+            uint8_t* o = line[ci].data();
+            if (hs == 1 && vs == 1) { row[ci] = nr; continue; }
+            if (hs == 1) { for (int i = 0; i < lores; ++i) o[i] = (uint8_t)((3 * nr[i] + fr[i] + 2) >> 2); }
+            else if (vs == 1) {                                                               // two samples per input sample along the row
+                if (lores == 1) o[0] = o[1] = nr[0];
+                else {
+                    o[0] = nr[0]; o[1] = (uint8_t)((nr[0] * 3 + nr[1] + 2) >> 2);
+                    int i = 1;
+                    for (; i < lores - 1; ++i) { const int n3 = 3 * nr[i] + 2; o[2 * i] = (uint8_t)((n3 + nr[i - 1]) >> 2); o[2 * i + 1] = (uint8_t)((n3 + nr[i + 1]) >> 2); }
+                    o[2 * i] = (uint8_t)((nr[lores - 2] * 3 + nr[lores - 1] + 2) >> 2);          // as the reference's decoder weights its last pair
+                    o[2 * i + 1] = nr[lores - 1];
+                }
+            } else {
+                if (lores == 1) o[0] = o[1] = (uint8_t)((3 * nr[0] + fr[0] + 2) >> 2);
+                else {
+                    int t1 = 3 * nr[0] + fr[0];
+                    o[0] = (uint8_t)((t1 + 2) >> 2);
+                    for (int i = 1; i < lores; ++i) { const int t0 = t1; t1 = 3 * nr[i] + fr[i]; o[2 * i - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4); o[2 * i] = (uint8_t)((3 * t1 + t0 + 8) >> 4); }
+                    o[2 * lores - 1] = (uint8_t)((t1 + 2) >> 2);
+                }
             }
+            row[ci] = o;
         }
-    }
-    const size_t s0 = comps[0].h == hmax && comps[0].v == vmax ? comps[0].stride : fw;
-    for (int y = 0; y < height; ++y)
+        uint8_t* o = rgb + (size_t)3 * width * y;
+        if (comps.size() == 1) { for (int x = 0; x < width; ++x) o[3 * x] = o[3 * x + 1] = o[3 * x + 2] = row[0][x]; continue; }
+#define BF_FIX(x) (((int)((x) * 4096.0f + 0.5f)) << 8)
         for (int x = 0; x < width; ++x) {
-            uint8_t* o = rgb + 3 * ((size_t)y * width + x);
-            const int Y = full[0][(size_t)y * s0 + x];
-            if (comps.size() == 1) { o[0] = o[1] = o[2] = (uint8_t)Y; continue; }
-            const size_t s1 = comps[1].h == hmax && comps[1].v == vmax ? comps[1].stride : fw, s2 = comps[2].h == hmax && comps[2].v == vmax ? comps[2].stride : fw;
-            const int cb = full[1][(size_t)y * s1 + x], cr = full[2][(size_t)y * s2 + x];
-            if (adobeTransform == 0) { o[0] = (uint8_t)Y; o[1] = (uint8_t)cb; o[2] = (uint8_t)cr; continue; }              // Adobe marker: components are RGB
-            const float r = Y + 1.402f * (cr - 128), g = Y - 0.344136f * (cb - 128) - 0.714136f * (cr - 128), b = Y + 1.772f * (cb - 128);      // JFIF (ITU-T T.871)
-            const int ri = (int)std::lrintf(r), gi = (int)std::lrintf(g), bi = (int)std::lrintf(b);
-            o[0] = (uint8_t)(ri < 0 ? 0 : (ri > 255 ? 255 : ri)); o[1] = (uint8_t)(gi < 0 ? 0 : (gi > 255 ? 255 : gi)); o[2] = (uint8_t)(bi < 0 ? 0 : (bi > 255 ? 255 : bi));
+            const int yf = (row[0][x] << 20) + (1 << 19), cb = row[1][x] - 128, cr = row[2][x] - 128;
+            int r = yf + cr * BF_FIX(1.40200f);
+            int g = yf + (cr * -BF_FIX(0.71414f)) + ((cb * -BF_FIX(0.34414f)) & 0xffff0000);
+            int b = yf + cb * BF_FIX(1.77200f);
+            r >>= 20; g >>= 20; b >>= 20;
+            o[3 * x] = clamp_u8(r); o[3 * x + 1] = clamp_u8(g); o[3 * x + 2] = clamp_u8(b);
         }
+#undef BF_FIX
+    }
     return BF_SENS_OK;
 }
 

@@ -6,10 +6,11 @@
  *   ml::SensorData::loadFromFile / saveToFile, RGBDFrame::loadFromFile / saveToFile      ext-depthcamera/sensorData.h:676-700, 1040-1048, 1187-1227   (on-disk layout, version 4)
  *   RGBDFrame::decompressDepthAlloc / decompressColorAlloc                                ext-depthcamera/sensorData.h:540-600, 640-668
  *   SensorDataReader::processDepth (ushort -> metres, 0 -> -inf; RGB -> RGBX)             FL/SensorDataReader.cpp:100-117
- * mLib decodes through a vendored stb_image (JPEG / PNG / zlib).  Here: zlib from the system library, PNG (8-bit grey / RGB / RGBA, non-interlaced) and
+ * mLib decodes through a vendored stb_image v2.08 (JPEG / PNG / zlib).  Here: zlib from the system library, PNG (8-bit grey / RGB / RGBA, non-interlaced) and
  * baseline JPEG (sequential DCT, Huffman, up to 2x2 chroma subsampling, restart markers) decoded by this library's own code; progressive JPEG and OCCI
- * depth are reported as unsupported.  JPEG decoders agree to within a level or two (IDCT and chroma up-sampling are not normative); the test compares
- * with libjpeg's output under that tolerance.
+ * depth are reported as unsupported.  JPEG decoding is not normative in its last bit (IDCT, chroma up-sampling, colour conversion) and SIFT sees that bit:
+ * the decoder restates the reference decoder's fixed-point pipeline and is bit-identical to it (tests/test_sens_reference_stb.py: golden outputs of the
+ * reference's stb_image compiled from /root/reference; libjpeg's output is compared under a tolerance of 3 levels besides).
  *
  * Host-only code: no CUDA call is made by this header's functions; buffers are host memory (pin them to hand them to bfFrameLoopStep with onHost = 1).
  */

@@ -98,6 +98,7 @@ def main():
     build_mgr_emulated()
     build_trajectory_host()
     build_raycast_emulated()
+    build_sens_host()
     print("oracle/_ref built:", sorted(os.listdir(OUT)))
     return 0
 
@@ -319,6 +320,18 @@ def build_raycast_emulated():
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-8000:])
         raise RuntimeError("building libref_raycast_emulated.so failed")
+
+
+def build_sens_host():
+    """The codecs behind the reference's `.sens` payloads: the stb_image / stb_image_write headers mLib vendors (external/mLib/include/ext-depthcamera/sensorData/),
+    compiled by g++ where they lie -> libref_sens_host.so (wrapper: oracle/ref_sens_host.cpp).  Pins include/bf_sens.h's JPEG / PNG / zlib handling against the
+    reference's decoder without a GPU."""
+    ext = os.path.join(os.path.dirname(REF), "external", "mLib", "include", "ext-depthcamera")
+    cmd = ["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-shared", "-fPIC", "-I", ext, os.path.join(HERE, "ref_sens_host.cpp"), "-o", os.path.join(OUT, "libref_sens_host.so")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-6000:])
+        raise RuntimeError("building libref_sens_host.so failed")
 
 
 def build_trajectory_host():

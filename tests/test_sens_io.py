@@ -141,7 +141,7 @@ def test_reads_jpeg_colour_like_libjpeg(tmp_path, sub, q):
         du, cu = r.frame_raw(i)
         ref = pil_decode(enc(c))                                                  # libjpeg's decode of the same bytes
         diff = np.abs(cu.astype(np.int32) - ref.astype(np.int32))
-        # the IDCT and the chroma up-sampling are not normative: decoders agree to a level or two (this one evaluates the IDCT from its definition in float)
+        # the IDCT and the chroma up-sampling are not normative: decoders agree to a level or two (this one follows the reference's stb_image, not libjpeg)
         assert diff.max() <= 3 and diff.mean() < (0.35 if q >= 85 else 0.8), (diff.max(), diff.mean())     # coarser quantisation: more pixels where two correct IDCTs round apart
         assert np.array_equal(du, d)
 
@@ -154,14 +154,16 @@ def test_decoders_on_odd_sizes_grey_restart_markers_and_errors():
     for kw in (dict(quality=90, subsampling=2), dict(quality=90, subsampling=1), dict(quality=92, subsampling=0)):
         bio = io.BytesIO(); Image.fromarray(img).save(bio, "JPEG", **kw)
         got, ref = sens.decode_jpeg(bio.getvalue()), pil_decode(bio.getvalue())
-        assert got.shape == ref.shape and np.abs(got.astype(int) - ref.astype(int)).max() <= 3
+        # odd sizes: the reference's decoder (stb_image, followed here bit for bit -- test_sens_reference_stb.py) up-samples from the chroma samples under the image
+        # and replicates at the right / bottom border, libjpeg from the padded MCU: the last chroma pair may differ, the interior may not
+        assert got.shape == ref.shape and np.abs(got.astype(int) - ref.astype(int))[:-2, :-2].max() <= 3
     grey = np.asarray(Image.fromarray(img).convert("L"))
     bio = io.BytesIO(); Image.fromarray(grey).save(bio, "JPEG", quality=90)
     got = sens.decode_jpeg(bio.getvalue())
     assert np.abs(got[..., 0].astype(int) - np.asarray(Image.open(io.BytesIO(bio.getvalue()))).astype(int)).max() <= 1 and np.array_equal(got[..., 0], got[..., 2])
     bio = io.BytesIO(); Image.fromarray(img).save(bio, "JPEG", quality=90, subsampling=2, restart_marker_blocks=3)        # DRI + RSTn
     if b"\xff\xdd" in bio.getvalue():
-        assert np.abs(sens.decode_jpeg(bio.getvalue()).astype(int) - pil_decode(bio.getvalue()).astype(int)).max() <= 3
+        assert np.abs(sens.decode_jpeg(bio.getvalue()).astype(int) - pil_decode(bio.getvalue()).astype(int))[:-2, :-2].max() <= 3
     bio = io.BytesIO(); Image.fromarray(img).save(bio, "JPEG", quality=90, progressive=True)
     with pytest.raises(RuntimeError, match="unsupported"):
         sens.decode_jpeg(bio.getvalue())
