@@ -129,6 +129,23 @@ class BFRayCastData(C.Structure):
     _fields_ = [("d_depth", C.c_void_p), ("d_depth4", C.c_void_p), ("d_normals", C.c_void_p), ("d_colors", C.c_void_p), ("d_vertexBuffer", C.c_void_p),
                 ("d_rayIntervalSplatMin", C.c_void_p), ("d_rayIntervalSplatMax", C.c_void_p)]
 
+MARCHINGCUBES_SYMBOLS = ["resetMarchingCubesCUDA", "extractIsoSurfaceCUDA", "bfMarchingCubesExtract", "bfMarchingCubesCreate", "bfMarchingCubesDestroy",
+                         "bfMarchingCubesExtractIsoSurface", "bfMarchingCubesClearMeshBuffer", "bfMarchingCubesGetSoup", "bfMarchingCubesSaveMesh",
+                         "bfMeshMergeCloseVertices", "bfMeshRemoveDuplicateFaces", "bfMeshSavePly"]
+
+
+class BFMarchingCubesParams(C.Structure):
+    """include/bf_marchingcubes.h (FL/DepthSensing/MarchingCubesSDFUtil.h:9-23), 64 bytes"""
+    _fields_ = [("m_boxEnabled", C.c_uint8), ("m_pad", C.c_uint8 * 3), ("m_minCorner", C.c_float * 3), ("m_maxNumTriangles", C.c_uint32), ("m_maxCorner", C.c_float * 3),
+                ("m_sdfBlockSize", C.c_uint32), ("m_hashNumBuckets", C.c_uint32), ("m_hashBucketSize", C.c_uint32),
+                ("m_threshMarchingCubes", C.c_float), ("m_threshMarchingCubes2", C.c_float), ("dummy", C.c_float * 3)]
+
+
+class BFMarchingCubesData(C.Structure):
+    """include/bf_marchingcubes.h (FL/DepthSensing/MarchingCubesSDFUtil.h:281-286)"""
+    _fields_ = [("d_params", C.c_void_p), ("d_numTriangles", C.c_void_p), ("d_triangles", C.c_void_p), ("m_bIsOnGPU", C.c_uint8)]
+
+
 CACHE_SYMBOLS = ["bfCacheStoreFrame"]
 INGEST_SYMBOLS = ["bfIngestFrame"]
 BUNDLER_SYMBOLS = ["computeSiftTransformCU", "initNextGlobalTransformCU", "updateTrajectoryCU", "bfTrajectorySelectReintegration",

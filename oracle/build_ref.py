@@ -99,6 +99,7 @@ def main():
     build_trajectory_host()
     build_raycast_emulated()
     build_sens_host()
+    build_marchingcubes_emulated()
     print("oracle/_ref built:", sorted(os.listdir(OUT)))
     return 0
 
@@ -320,6 +321,40 @@ def build_raycast_emulated():
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-8000:])
         raise RuntimeError("building libref_raycast_emulated.so failed")
+
+
+def build_marchingcubes_emulated():
+    """The reference's iso-surface kernel (FL/DepthSensing/CUDAMarchingCubesSDF.cu with MarchingCubesSDFUtil.h, Tables.h, RayCastSDFUtil.h, VoxelUtilHashSDF.h,
+    CUDAConstant.cu) compiled by g++ against the CUDA emulation -> libref_marchingcubes_emulated.so (wrapper: oracle/ref_marchingcubes_wrap.cu).  Runs on the CPU:
+    pins row N4's marching-cubes oracle (and the triangle table) without a GPU.  Patches on the scratch copies: launch syntax, the HashEntry alignment attribute,
+    the matNxM specialisation -- as for the ray cast."""
+    root = os.path.join(TMP, "mcemu")
+    os.makedirs(root)
+    ds, sg = os.path.join(REF, "Source", "DepthSensing"), os.path.join(REF, "Source", "SiftGPU")
+    for f in ("CUDAConstant.cu", "CUDAMarchingCubesSDF.cu", "MarchingCubesSDFUtil.h", "Tables.h", "RayCastSDFUtil.h", "VoxelUtilHashSDF.h", "DepthCameraUtil.h", "CUDAHashParams.h",
+              "CUDADepthCameraParams.h", "CUDARayCastParams.h"):
+        shutil.copy(os.path.join(ds, f), root)
+    for f in ("cuda_SimpleMatrixUtil.h", "cudaUtil.h"):
+        shutil.copy(os.path.join(sg, f), root)
+    patch(os.path.join(root, "cuda_SimpleMatrixUtil.h"),
+          [(r"\ninline __device__ __host__ matNxM<4, 1>::operator float4\(\)", "\ntemplate<> inline __device__ __host__ matNxM<4, 1>::operator float4()", 1)])
+    for f in ("CUDAHashParams.h", "CUDADepthCameraParams.h", "CUDARayCastParams.h"):
+        q = os.path.join(root, f)
+        open(q, "w", encoding="latin-1").write("#pragma once\n" + open(os.path.join(ds, f), encoding="latin-1").read())
+    patch(os.path.join(root, "VoxelUtilHashSDF.h"), [(r"__align__\(16\)\s*struct HashEntry", "struct __align__(16) HashEntry", 1)])
+    patch(os.path.join(root, "RayCastSDFUtil.h"), [(r"float3 normal = -gradientForPoint\(hash, currentIso\);", "float3 g_ = gradientForPoint(hash, currentIso); float3 normal = -g_;", 1)])
+    launch = (r"([A-Za-z_]\w*(?:<[^<>()]*>)?)\s*<<\s*<\s*([^;]*?)\s*>>\s*>\s*\(", r"EMU_KERNEL(\1, \2)(", None)
+    patch(os.path.join(root, "CUDAMarchingCubesSDF.cu"), [launch])
+    unit = os.path.join(root, "ref_marchingcubes_wrap_emu.cpp")
+    shutil.copy(os.path.join(HERE, "ref_marchingcubes_wrap.cu"), unit)
+    emu_dir = os.path.join(HERE, "ref_emu")
+    cmd = ["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-D__CUDACC__", "-D__NVCC__",
+           "-I", emu_dir, "-I", os.path.join(os.path.dirname(HERE), "tests", "cuda_emu"), "-I", root, "-I", os.path.join(REF, "Include", "cutil", "inc"),
+           unit, "-o", os.path.join(OUT, "libref_marchingcubes_emulated.so"), "-lm"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-8000:])
+        raise RuntimeError("building libref_marchingcubes_emulated.so failed")
 
 
 def build_sens_host():

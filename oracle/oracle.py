@@ -691,3 +691,25 @@ def raycast_frame(scene: "OracleSceneRepHashSDF", cam, p, T) -> dict:
     o = raycast_render(scene, p, rmin, rmax)
     o["ray_min"], o["ray_max"] = rmin, rmax
     return o
+
+
+# ---- iso-surface extraction (oracle/marchingcubes_oracle.c; SURVEY.md section 8f, row N4, second half) ------------------------------------
+def marchingcubes_tables():
+    """(edgeTable [256], triTable [256, 16]) as the reference's Tables.h lays them out (-1 padded)"""
+    L = lib()
+    edge = np.zeros(256, np.int32); tri = np.zeros((256, 16), np.int32)
+    L.orc_marchingcubes_tables.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_marchingcubes_tables.restype = None
+    L.orc_marchingcubes_tables(edge.ctypes.data, tri.ctypes.data)
+    return edge, tri
+
+
+def marchingcubes_extract(scene: "OracleSceneRepHashSDF", p):
+    """extractIsoSurfaceKernel over the scene's hash table -> (triangles [n, 3, 6] float32: position xyz + colour rgb per vertex, triangles the cells produced)"""
+    L = lib()
+    tri = np.zeros((int(p.m_maxNumTriangles), 3, 6), np.float32)
+    found = C.c_ulonglong(0)
+    L.orc_marchingcubes_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_marchingcubes_extract.restype = C.c_uint
+    n = L.orc_marchingcubes_extract(C.addressof(scene.hd), C.addressof(scene.hp), C.addressof(p), tri.ctypes.data, C.byref(found))
+    return tri[:n].copy(), int(found.value)

@@ -113,6 +113,16 @@ static int trilinear(const BFHashDataStruct* hd, const BFHashParams* hp, f3 pos,
     return 1;
 }
 
+/* the two samplers by themselves, for marchingcubes_oracle.c (same library, not exported) */
+int orc_rc_trilinear(const BFHashDataStruct* hd, const BFHashParams* hp, float x, float y, float z, float* dist, uint8_t color[3]) {
+    const f3 p = { x, y, z };
+    return trilinear(hd, hp, p, dist, color);
+}
+BFVoxel orc_rc_voxel(const BFHashDataStruct* hd, const BFHashParams* hp, float x, float y, float z) {
+    const f3 p = { x, y, z };
+    return get_voxel(hd, hp, p);
+}
+
 /* findIntersectionBisection, RayCastSDFUtil.h:148-170 (three steps of regula falsi) */
 static int bisection(const BFHashDataStruct* hd, const BFHashParams* hp, f3 camPos, f3 dir, float d0, float r0, float d1, float r1, float* alpha, uint8_t color[3]) {
     float a = r0, aDist = d0, b = r1, bDist = d1, c = 0.0f;
@@ -283,8 +293,10 @@ ORC_API void orc_raycast_splat(const BFHashParams* hp, const BFDepthCameraParams
         if (!(X0 < X1) || !(Y0 < Y1)) continue;
         /* first / last pixel whose centre is inside: i + 0.5 >= X0  <=>  i >= ceil(X0 - 0.5) */
         float fi0 = ceilf(X0 - 0.5f), fi1 = ceilf(X1 - 0.5f), fj0 = ceilf(Y0 - 0.5f), fj1 = ceilf(Y1 - 0.5f);
-        if (fi0 < 0.0f) fi0 = 0.0f; if (fj0 < 0.0f) fj0 = 0.0f;
-        if (fi1 > (float)W) fi1 = (float)W; if (fj1 > (float)H) fj1 = (float)H;
+        if (fi0 < 0.0f) fi0 = 0.0f;
+        if (fj0 < 0.0f) fj0 = 0.0f;
+        if (fi1 > (float)W) fi1 = (float)W;
+        if (fj1 > (float)H) fj1 = (float)H;
         for (int j = (int)fj0; j < (int)fj1; ++j)
             for (int i = (int)fi0; i < (int)fi1; ++i) {
                 float* o = &out[(size_t)j * W + i];

@@ -10,7 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 
 
 def build_emulated(cu_name: str, expected_launches: int, extra_pre: str = "") -> C.CDLL:
-    src = open(os.path.join(ROOT, "bundlefusion_b200", "csrc", cu_name)).read()
+    csrc = os.path.join(ROOT, "bundlefusion_b200", "csrc")
+    src = open(os.path.join(csrc, cu_name)).read()
+    # the library's own device headers are spliced in (they include bf_common.cuh, which the shim replaces)
+    src = re.sub(r'#include "(\w+\.cuh)"', lambda m: m.group(0) if m.group(1) == "bf_common.cuh" else open(os.path.join(csrc, m.group(1))).read().replace("#pragma once", ""), src)
     src = src.replace('#include "bf_common.cuh"', "")
     src = re.sub(r"extern __shared__ float (\w+)\[\];", lambda m: "" if m.group(1) == "sm" else f"float* {m.group(1)} = sm;", src)      # dynamic shared memory: the shim's sm[]
     src = re.sub(r"extern __shared__ (unsigned|int) (\w+)\[\];", lambda m: f"{m.group(1)}* {m.group(2)} = reinterpret_cast<{m.group(1)}*>(sm);", src)

@@ -55,12 +55,20 @@ def test_symbol_list_matches_header():
     assert sorted(set(_declared_symbols("bf_bundler.h"))) == sorted(set(capi.BUNDLER_SYMBOLS))
     assert sorted(set(_declared_symbols("bf_raycast.h"))) == sorted(set(capi.RAYCAST_SYMBOLS))
     assert sorted(set(_declared_symbols("bf_sens.h"))) == sorted(set(capi.SENS_SYMBOLS))
+    assert sorted(set(_declared_symbols("bf_marchingcubes.h"))) == sorted(set(capi.MARCHINGCUBES_SYMBOLS))
 
 
 def test_raycast_pod_layouts():
     assert C.sizeof(capi.BFRayCastParams) == 192 and capi.BFRayCastParams.mx.offset == 128 and capi.BFRayCastParams.m_splatMinimum.offset == 160
     assert capi.BFRayCastParams.m_useGradients.offset == 184 and capi.BFRayCastParams.dummy0.offset == 188       # FL/DepthSensing/CUDARayCastParams.h:8-27
     assert C.sizeof(capi.BFRayCastData) == 56
+
+
+def test_marchingcubes_pod_layouts():
+    P = capi.BFMarchingCubesParams                                       # FL/DepthSensing/MarchingCubesSDFUtil.h:9-23
+    assert C.sizeof(P) == 64 and P.m_minCorner.offset == 4 and P.m_maxNumTriangles.offset == 16 and P.m_maxCorner.offset == 20 and P.m_sdfBlockSize.offset == 32
+    assert P.m_threshMarchingCubes.offset == 44 and P.m_threshMarchingCubes2.offset == 48
+    assert C.sizeof(capi.BFMarchingCubesData) == 32
 
 
 def test_sift_pod_layouts():
