@@ -100,6 +100,7 @@ def main():
     build_raycast_emulated()
     build_sens_host()
     build_marchingcubes_emulated()
+    build_mesh_host()
     print("oracle/_ref built:", sorted(os.listdir(OUT)))
     return 0
 
@@ -355,6 +356,38 @@ def build_marchingcubes_emulated():
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-8000:])
         raise RuntimeError("building libref_marchingcubes_emulated.so failed")
+
+
+def build_mesh_host():
+    """The host half of the reference's mesh export: mLib's MeshDataf (mergeCloseVertices, removeDuplicateFaces, applyTransform) and MeshIOf::saveToFile, driven by
+    the statements of CUDAMarchingCubesHashSDF::copyTrianglesToCPU / ::saveMesh (wrapper: oracle/ref_mesh_host.cpp) -> libref_mesh_host.so.  mLib's core headers
+    are copied to scratch and get the seven one-line patches g++ needs (MSVC accepts the originals): a missing `typename`, calls of a member that does not exist
+    inside never-instantiated templates (closeStream), a `w` in vec6::toString, unqualified dependent-base members in distanceField3.h, a typedef used before its
+    declaration in material.h, `ios_base::open_mode`, `auto&` bound to a temporary in MeshData::isConsistent.  None touches the mesh clean-up or the PLY writer.  C++17: mLib's face iterators declare a copy constructor from a non-const reference, which only
+    guaranteed copy elision lets g++ accept."""
+    root = os.path.join(TMP, "meshhost")
+    os.makedirs(root)
+    mlib = os.path.join(os.path.dirname(REF), "external", "mLib", "include")
+    for d in sorted(os.listdir(mlib)):
+        if d.startswith("core-"):
+            shutil.copytree(os.path.join(mlib, d), os.path.join(root, d))
+    for f in ("mLibCore.h", "mLibCore.cpp"):
+        shutil.copy(os.path.join(mlib, f), root)
+    patch(os.path.join(root, "core-util", "binaryDataStream.h"), [(r"\n(\s*)BinaryDataBuffer::Mode mode = ", r"\n\1typename BinaryDataBuffer::Mode mode = ", 1), (r"in\.closeStream\(\);", "", None)])
+    patch(os.path.join(root, "core-math", "vec6.h"), [(r"std::to_string\(z\) \+ separator \+ std::to_string\(w\) \+ separator \+", "std::to_string(z) + separator +", 1)])
+    patch(os.path.join(root, "core-base", "distanceField3.h"), [(r"z < m_dimZ; z\+\+", "z < this->m_dimZ; z++", None), (r"y < m_dimY; y\+\+", "y < this->m_dimY; y++", None),
+                                                                (r"x < m_dimX; x\+\+", "x < this->m_dimX; x++", None)])
+    patch(os.path.join(root, "core-mesh", "material.h"), [(r"const Materialf& m0, const Materialf& m1", "const Material& m0, const Material& m1", 2)])
+    patch(os.path.join(root, "core-util", "binaryDataBuffer.h"), [(r"std::ios_base::open_mode", "std::ios_base::openmode", None)])          # the pre-standard name, gone in C++17
+    patch(os.path.join(root, "core-mesh", "meshData.h"), [(r"for \(auto& face : m_FaceIndices", "for (auto&& face : m_FaceIndices", 3)])    # isConsistent: reference to a temporary (MSVC extension)
+    cmd = ["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-shared", "-fPIC", "-I", root, os.path.join(HERE, "ref_mesh_host.cpp"),
+           os.path.join(os.path.dirname(mlib), "src", "core-base", "common.cpp"), os.path.join(os.path.dirname(mlib), "src", "core-util", "utility.cpp"),      # warning / error hooks, util::
+           "-include", "sys/types.h", "-include", "sys/stat.h", "-include", "unistd.h", "-include", "dirent.h", "-DLINUX",
+           "-include", "mLibCore.h", "-o", os.path.join(OUT, "libref_mesh_host.so")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-6000:])
+        raise RuntimeError("building libref_mesh_host.so failed")
 
 
 def build_sens_host():
