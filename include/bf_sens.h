@@ -10,7 +10,8 @@
  * baseline JPEG (sequential DCT, Huffman, up to 2x2 chroma subsampling, restart markers) decoded by this library's own code; progressive JPEG and OCCI
  * depth are reported as unsupported.  JPEG decoding is not normative in its last bit (IDCT, chroma up-sampling, colour conversion) and SIFT sees that bit:
  * the decoder restates the reference decoder's fixed-point pipeline and is bit-identical to it (tests/test_sens_reference_stb.py: golden outputs of the
- * reference's stb_image compiled from /root/reference; libjpeg's output is compared under a tolerance of 3 levels besides).
+ * reference's stb_image compiled from /root/reference; libjpeg's output is compared under a tolerance of 3 levels besides).  The container: files written by the
+ * reference's ml::SensorData are read field for field, the writer's raw-depth file equals the reference's byte for byte (tests/test_sens_reference_sensordata.py).
  *
  * Host-only code: no CUDA call is made by this header's functions; buffers are host memory (pin them to hand them to bfFrameLoopStep with onHost = 1).
  */

@@ -101,6 +101,7 @@ def main():
     build_sens_host()
     build_marchingcubes_emulated()
     build_mesh_host()
+    build_sensordata_host()
     print("oracle/_ref built:", sorted(os.listdir(OUT)))
     return 0
 
@@ -358,20 +359,18 @@ def build_marchingcubes_emulated():
         raise RuntimeError("building libref_marchingcubes_emulated.so failed")
 
 
-def build_mesh_host():
-    """The host half of the reference's mesh export: mLib's MeshDataf (mergeCloseVertices, removeDuplicateFaces, applyTransform) and MeshIOf::saveToFile, driven by
-    the statements of CUDAMarchingCubesHashSDF::copyTrianglesToCPU / ::saveMesh (wrapper: oracle/ref_mesh_host.cpp) -> libref_mesh_host.so.  mLib's core headers
-    are copied to scratch and get the seven one-line patches g++ needs (MSVC accepts the originals): a missing `typename`, calls of a member that does not exist
-    inside never-instantiated templates (closeStream), a `w` in vec6::toString, unqualified dependent-base members in distanceField3.h, a typedef used before its
-    declaration in material.h, `ios_base::open_mode`, `auto&` bound to a temporary in MeshData::isConsistent.  None touches the mesh clean-up or the PLY writer.  C++17: mLib's face iterators declare a copy constructor from a non-const reference, which only
-    guaranteed copy elision lets g++ accept."""
-    root = os.path.join(TMP, "meshhost")
+def prepare_mlib_scratch(root):
+    """scratch copy of mLib's core headers (+ ext-depthcamera) with the seven one-line patches g++ needs (MSVC accepts the originals): a missing `typename`, calls of a
+    member that does not exist inside never-instantiated templates (closeStream), a `w` in vec6::toString, unqualified dependent-base members in distanceField3.h, a
+    typedef used before its declaration in material.h, `ios_base::open_mode`, `auto&` bound to a temporary in MeshData::isConsistent.  None touches the mesh clean-up,
+    the PLY writer or the SensorData container.  Returns the g++ command prefix (C++17: mLib's face iterators declare a copy constructor from a non-const reference,
+    which only guaranteed copy elision lets g++ accept) and the two mLib source files every user needs (warning / error hooks, util::)."""
     os.makedirs(root)
     mlib = os.path.join(os.path.dirname(REF), "external", "mLib", "include")
     for d in sorted(os.listdir(mlib)):
-        if d.startswith("core-"):
+        if d.startswith("core-") or d == "ext-depthcamera":
             shutil.copytree(os.path.join(mlib, d), os.path.join(root, d))
-    for f in ("mLibCore.h", "mLibCore.cpp"):
+    for f in ("mLibCore.h", "mLibDepthCamera.h"):
         shutil.copy(os.path.join(mlib, f), root)
     patch(os.path.join(root, "core-util", "binaryDataStream.h"), [(r"\n(\s*)BinaryDataBuffer::Mode mode = ", r"\n\1typename BinaryDataBuffer::Mode mode = ", 1), (r"in\.closeStream\(\);", "", None)])
     patch(os.path.join(root, "core-math", "vec6.h"), [(r"std::to_string\(z\) \+ separator \+ std::to_string\(w\) \+ separator \+", "std::to_string(z) + separator +", 1)])
@@ -380,14 +379,33 @@ def build_mesh_host():
     patch(os.path.join(root, "core-mesh", "material.h"), [(r"const Materialf& m0, const Materialf& m1", "const Material& m0, const Material& m1", 2)])
     patch(os.path.join(root, "core-util", "binaryDataBuffer.h"), [(r"std::ios_base::open_mode", "std::ios_base::openmode", None)])          # the pre-standard name, gone in C++17
     patch(os.path.join(root, "core-mesh", "meshData.h"), [(r"for \(auto& face : m_FaceIndices", "for (auto&& face : m_FaceIndices", 3)])    # isConsistent: reference to a temporary (MSVC extension)
-    cmd = ["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-shared", "-fPIC", "-I", root, os.path.join(HERE, "ref_mesh_host.cpp"),
-           os.path.join(os.path.dirname(mlib), "src", "core-base", "common.cpp"), os.path.join(os.path.dirname(mlib), "src", "core-util", "utility.cpp"),      # warning / error hooks, util::
-           "-include", "sys/types.h", "-include", "sys/stat.h", "-include", "unistd.h", "-include", "dirent.h", "-DLINUX",
-           "-include", "mLibCore.h", "-o", os.path.join(OUT, "libref_mesh_host.so")]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    src = os.path.join(os.path.dirname(mlib), "src")
+    return (["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-shared", "-fPIC", "-DLINUX", "-I", root,
+             "-include", "sys/types.h", "-include", "sys/stat.h", "-include", "unistd.h", "-include", "dirent.h", "-include", "mLibCore.h"],
+            [os.path.join(src, "core-base", "common.cpp"), os.path.join(src, "core-util", "utility.cpp")])
+
+
+def build_mesh_host():
+    """The host half of the reference's mesh export: mLib's MeshDataf (mergeCloseVertices, removeDuplicateFaces, applyTransform) and MeshIOf::saveToFile, driven by
+    the statements of CUDAMarchingCubesHashSDF::copyTrianglesToCPU / ::saveMesh (wrapper: oracle/ref_mesh_host.cpp) -> libref_mesh_host.so, g++ on mLib's headers
+    where they lie (prepare_mlib_scratch)."""
+    cmd, srcs = prepare_mlib_scratch(os.path.join(TMP, "meshhost"))
+    r = subprocess.run(cmd + [os.path.join(HERE, "ref_mesh_host.cpp")] + srcs + ["-o", os.path.join(OUT, "libref_mesh_host.so")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-6000:])
         raise RuntimeError("building libref_mesh_host.so failed")
+
+
+def build_sensordata_host():
+    """The reference's `.sens` container class ml::SensorData (ext-depthcamera/sensorData.h; wrapper: oracle/ref_sensordata_host.cpp) -> libref_sensordata_host.so:
+    writes files as the reference's recorder does (raw colour; JPEG / PNG compression is the Windows-only uplink codec) and reads files as its player does."""
+    cmd, srcs = prepare_mlib_scratch(os.path.join(TMP, "sensdatahost"))
+    stb = os.path.join(os.path.dirname(REF), "external", "mLib", "include", "mLibDepthCamera.cpp")                    # the stb_image / stb_image_write implementations (inside namespace stb)
+    r = subprocess.run(cmd + ["-include", "assert.h", "-include", "stdarg.h", "-include", "limits.h", os.path.join(HERE, "ref_sensordata_host.cpp"), stb] + srcs +
+                       ["-o", os.path.join(OUT, "libref_sensordata_host.so")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-6000:])
+        raise RuntimeError("building libref_sensordata_host.so failed")
 
 
 def build_sens_host():
