@@ -79,7 +79,7 @@ def test_marching_cubes_matches_oracle_bit_for_bit(cuda_device, tmp_path):
     v1, f1 = read_ply(first)
     v2, f2 = read_ply(second)
     # the merged mesh: every cell edge vertex once instead of once per adjoining triangle; (almost) every triangle survives
-    assert len(v1) < len(want) and 0.98 * len(want) < len(f1) <= len(want) and f1["i"].max() == len(v1) - 1
+    assert len(v1) < len(want) and 0.98 * len(want) < len(f1) <= len(want) and f1["i"].max() <= len(v1) - 1 and f1["i"].min() == 0
     assert len(v2) == len(v1) and np.allclose(v2["p"], 2.0 * v1["p"], rtol=1e-6, atol=0) and np.array_equal(v2["c"], v1["c"])
     mc.close(); gpu.close()
 

@@ -110,7 +110,7 @@ def test_emulated_kernel_matches_oracle_bit_for_bit(emu):
     assert len(capped) == 1000 and all(r.tobytes() in full for r in canon(capped))
 
 
-def test_emulated_reference_named_stubs_and_host_class(emu):
+def test_emulated_reference_named_stubs_and_host_class(emu, tmp_path):
     sc, cam, frames = golden_scene()
     p = golden_params(sc.hp, scene_box(sc))
     want, _ = orc.marchingcubes_extract(sc, p)
@@ -139,6 +139,26 @@ def test_emulated_reference_named_stubs_and_host_class(emu):
     pos = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), (nv, 3)); col = np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_float)), (nv, 4))
     first = np.concatenate([pos[:3 * len(want)], col[:3 * len(want), :3]], axis=1).reshape(len(want), 3, 6)
     assert np.array_equal(canon(first), canon(want)) and np.all(col[:, 3] == 1.0)
+    # saveMesh: the buffer (both extractions, in their order) merged, de-duplicated and written; the buffer is cleared; an existing name counts up
+    from tests.test_mesh_reference_host import TRANSFORM, library_save
+    soup = np.concatenate([pos, col[:, :3]], axis=1).reshape(-1, 3, 6).copy()
+    emu.bfMarchingCubesSaveMesh.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
+    out = C.create_string_buffer(4096)
+    path = str(tmp_path / "scans" / "scan.ply")
+    assert emu.bfMarchingCubesSaveMesh(h, path.encode(), None, 0, out, 4096) == 0 and out.value.decode() == path
+    assert emu.bfMarchingCubesGetSoup(h, None, None) == 0
+    library_save(soup, None, str(tmp_path / "want.ply"))
+    assert open(path, "rb").read() == open(str(tmp_path / "want.ply"), "rb").read()
+    assert emu.bfMarchingCubesExtractIsoSurface(h, C.addressof(sc.hd), C.addressof(sc.hp), lo, hi, 1) == 0
+    nv = emu.bfMarchingCubesGetSoup(h, C.byref(pp), C.byref(cp))
+    pos = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), (nv, 3)); col = np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_float)), (nv, 4))
+    soup = np.concatenate([pos, col[:, :3]], axis=1).reshape(-1, 3, 6).copy()
+    T = np.ascontiguousarray(TRANSFORM)
+    assert emu.bfMarchingCubesSaveMesh(h, path.encode(), T.ctypes.data, 0, out, 4096) == 0 and out.value.decode() == str(tmp_path / "scans" / "scan1.ply")
+    library_save(soup, TRANSFORM, str(tmp_path / "want_t.ply"))
+    assert open(out.value.decode(), "rb").read() == open(str(tmp_path / "want_t.ply"), "rb").read()
+    assert emu.bfMarchingCubesSaveMesh(h, path.encode(), None, 1, out, 4096) == 0 and out.value.decode() == path          # overwrite: an empty mesh under the first name
+    assert b"element vertex 0" in open(path, "rb").read()
     emu.bfMarchingCubesDestroy(h)
 
 
