@@ -6,7 +6,7 @@
 // 4x4 inverse by cofactor expansion in fp32, as the reference's float4x4::getInverse does on the host
 // (FL/SiftGPU/cuda_SimpleMatrixUtil.h:980-1100).  Written from the textbook adjugate formula:
 // inv = adj(M) / det(M), cofactors expanded as 2x2 sub-determinant products.
-BF_API void bfMat4Inverse(const float* m, float* out) { bf::mat4_inverse_hd(m, out); }
+BF_API void bfMat4Inverse(const float* m, float* out) { bf::mat4_inverse_ref(m, out); }          // the reference's host formula, bit for bit (mat4.cuh)
 
 namespace bf {
 int tsdf_lanes_begin(const BFHashDataStruct* hd, const BFHashParams* hp);     // tsdf.cu: two-lane replay bracket

@@ -5,8 +5,38 @@
 
 namespace bf {
 
-// 4x4 inverse by cofactor expansion in fp32, as the reference's float4x4::getInverse does (FL/SiftGPU/cuda_SimpleMatrixUtil.h:980-1100).
-// Written from the textbook adjugate formula: inv = adj(M) / det(M), cofactors expanded as 2x2 sub-determinant products.
+// The inverse as the reference's HOST forms it: float4x4::getInverse (FL/SiftGPU/cuda_SimpleMatrixUtil.h:980-1100) and mLib's mat4f::getInverse
+// (external/mLib/include/core-math/matrix4x4.h:587-710) are the same expansion -- every adjugate entry a sum of six triple products, each product evaluated
+// left to right, the determinant from the first row, one reciprocal -- compiled without contraction by the reference's host compiler.  The pose inverses the
+// host hands to the kernels (setLastRigidTransform, FL/DepthSensing/CUDASceneRepHashSDF.h:128-134; the ray cast's view matrix, CUDARayCastSDF.cpp:92) are
+// formed with this one, so that they equal the reference's bit for bit (tests/test_mat4_inverse_reference.py: against both reference implementations, g++).
+// The order of the 96 products is the formula's (the one MESA's gluInvertMatrix made common); entry (r, c) of the adjugate below is row-major index 4r + c.
+__host__ __device__ inline void mat4_inverse_ref(const float* m, float* out) {
+    float a[16];
+    a[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    a[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    a[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    a[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    a[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    a[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    a[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    a[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    a[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    a[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    a[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    a[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    a[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    a[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    a[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    a[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const float det = m[0] * a[0] + m[1] * a[4] + m[2] * a[8] + m[3] * a[12];
+    const float r = 1.0f / det;
+    for (int i = 0; i < 16; ++i) out[i] = a[i] * r;
+}
+
+// The inverse the DEVICE-side filters take (sift_filter.cu, sift_verify.cu, trajectory.cu): the adjugate through 2x2 sub-determinants -- 40 products instead of
+// 96.  The reference's kernels call float4x4::getInverse there, which nvcc contracts into FMAs in an order of its own choosing; neither form reproduces that, the
+// two agree to a few ulp (oracle/filter_oracle.c: mat4_inverse_subdet).
 __host__ __device__ inline void mat4_inverse_hd(const float* m, float* out) {
     // 2x2 sub-determinants of the lower two rows (s*) and upper two rows (c*)
     const float a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3];

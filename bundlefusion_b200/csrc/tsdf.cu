@@ -1775,8 +1775,8 @@ BF_API int bfTsdfReintegrateBatch(BFHashDataStruct* hd, BFHashParams* hp, const 
     for (int k = 0; k < numPairs; ++k) {
         hpOld[k] = *hp; hpNew[k] = *hp;
         for (int e = 0; e < 16; ++e) { hpOld[k].m_rigidTransform.m[e] = pairs[k].oldPose[e]; hpNew[k].m_rigidTransform.m[e] = pairs[k].newPose[e]; }
-        mat4_inverse_hd(pairs[k].oldPose, hpOld[k].m_rigidTransformInverse.m);
-        mat4_inverse_hd(pairs[k].newPose, hpNew[k].m_rigidTransformInverse.m);
+        mat4_inverse_ref(pairs[k].oldPose, hpOld[k].m_rigidTransformInverse.m);          // as setLastRigidTransform forms it on the reference's host
+        mat4_inverse_ref(pairs[k].newPose, hpNew[k].m_rigidTransformInverse.m);
         fr.inv[2 * k] = hpOld[k].m_rigidTransformInverse; fr.inv[2 * k + 1] = hpNew[k].m_rigidTransformInverse;
         desc[k].hpOld = &hpOld[k]; desc[k].hpNew = &hpNew[k];
         desc[k].depth = d_depthFrames[pairs[k].frame]; desc[k].color = d_colorFrames[pairs[k].frame];

@@ -18,7 +18,8 @@
 extern "C" {
 #endif
 
-/* general 4x4 inverse, fp32 cofactor expansion (cuda_SimpleMatrixUtil.h:980-1100); row-major in/out */
+/* general 4x4 inverse in fp32 as the reference's host forms it: float4x4::getInverse (cuda_SimpleMatrixUtil.h:980-1100) = mat4f::getInverse (mLib
+ * core-math/matrix4x4.h:587-710), every product and sum in their order, bit for bit (tests/test_mat4_inverse_reference.py); row-major in/out */
 void bfMat4Inverse(const float* m16, float* out16);
 
 enum { BF_TSDF_OP_INTEGRATE = 0, BF_TSDF_OP_DEINTEGRATE = 1, BF_TSDF_OP_GARBAGE_COLLECT = 2 };

@@ -53,6 +53,16 @@ def lib(fast: bool = False) -> C.CDLL:
     return L
 
 
+def mat4_inverse(T) -> np.ndarray:
+    """the reference's host 4x4 inverse (float4x4::getInverse = mat4f::getInverse; oracle/solver_oracle.c: orc_mat4_inverse), float32 [4, 4]"""
+    L = lib()
+    fp = C.POINTER(C.c_float)
+    m = np.ascontiguousarray(T, np.float32).reshape(16); out = np.zeros(16, np.float32)
+    L.orc_mat4_inverse.argtypes = [fp, fp]; L.orc_mat4_inverse.restype = None
+    L.orc_mat4_inverse(m.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    return out.reshape(4, 4)
+
+
 class OracleSceneRepHashSDF:
     """The same call surface as bundlefusion_b200.scene_rep.CUDASceneRepHashSDF, on host arrays."""
 
@@ -93,8 +103,11 @@ class OracleSceneRepHashSDF:
         self.num_occupied = 0
 
     def _set_pose(self, T):
-        from bundlefusion_b200.scene_rep import set_pose
-        set_pose(self.hp, T)
+        """setLastRigidTransform (FL/DepthSensing/CUDASceneRepHashSDF.h:128-134): the pose and its host-computed inverse (the reference's formula: orc_mat4_inverse)"""
+        T = np.ascontiguousarray(T, np.float32).reshape(4, 4)
+        inv = mat4_inverse(T)
+        for k in range(16):
+            self.hp.m_rigidTransform.m[k] = float(T.reshape(16)[k]); self.hp.m_rigidTransformInverse.m[k] = float(inv.reshape(16)[k])
 
     def integrate(self, T, depth: np.ndarray, color: np.ndarray | None, cam: BFDepthCameraParams):
         self._set_pose(T)
@@ -650,10 +663,10 @@ def sift_filter_frames(curFrame, startFrame, numFrames, numFiltered, validImages
 # ---- ray cast of the hashed TSDF (oracle/raycast_oracle.c) ----------------------------------------------
 def raycast_set_pose(p, T):
     """CUDARayCastSDF::rayIntervalSplatting (cpp:86-98): view matrix = inverse of the rigid transform (float32 cofactor inverse, as the host's mat4f)"""
-    from bundlefusion_b200.scene_rep import mat4_inverse_f32, mat4_to_c
-    T = np.ascontiguousarray(T, np.float32)
-    p.m_viewMatrixInverse = mat4_to_c(T)
-    p.m_viewMatrix = mat4_to_c(mat4_inverse_f32(T))
+    T = np.ascontiguousarray(T, np.float32).reshape(4, 4)
+    inv = mat4_inverse(T)
+    for k in range(16):
+        p.m_viewMatrixInverse.m[k] = float(T.reshape(16)[k]); p.m_viewMatrix.m[k] = float(inv.reshape(16)[k])
 
 
 def raycast_splat(scene: "OracleSceneRepHashSDF", cam, p, splat_minimum: int) -> np.ndarray:

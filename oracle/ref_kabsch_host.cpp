@@ -50,3 +50,11 @@ REF_API void refHostEigenValues3(const float* m9, float* evs) {
     const float3 e = computeEigenValues(m);
     evs[0] = e.x; evs[1] = e.y; evs[2] = e.z;
 }
+
+// float4x4::getInverse, cuda_SimpleMatrixUtil.h:980-1100 (what setLastRigidTransform calls on the host, FL/DepthSensing/CUDASceneRepHashSDF.h:130)
+REF_API void refHostFloat4x4Inverse(const float* m16, float* out16) {
+    float4x4 m;
+    for (int i = 0; i < 16; ++i) m.entries[i] = m16[i];
+    const float4x4 r = m.getInverse();
+    for (int i = 0; i < 16; ++i) out16[i] = r.entries[i];
+}

@@ -47,3 +47,9 @@ extern "C" int ref_mesh_save(const float* triangles, unsigned nTriangles, const 
     }
     return 0;
 }
+
+// mat4f::getInverse, mLib core-math/matrix4x4.h:587-710 (the ray cast's view matrix, FL/DepthSensing/CUDARayCastSDF.cpp:92)
+extern "C" void ref_mlib_mat4_inverse(const float* m16, float* out16) {
+    const mat4f r = mat4f(m16).getInverse();
+    memcpy(out16, r.getData(), 64);
+}

@@ -44,7 +44,7 @@ def main():
     ref.garbageCollect()
     snap = ref.download()
     b, v = orc.canonical_blocks(snap)
-    np.savez_compressed(os.path.join(out, "tsdf_reference_ieee.npz"), blocks=b, crcs=block_crcs(v), first_voxels=v[:4], heap_free=np.int64(ref.getHeapFreeCount()),
+    np.savez_compressed(os.path.join(out, "tsdf_reference_ieee.npz"), pose_inverse=np.bytes_(b"reference host formula (bfMat4Inverse)"), blocks=b, crcs=block_crcs(v), first_voxels=v[:4], heap_free=np.int64(ref.getHeapFreeCount()),
                         case=np.bytes_(repr(c)))
     # ---- solver through the reference's kernels (IEEE build) ----
     s = BA_SPARSE

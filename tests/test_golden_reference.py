@@ -24,12 +24,39 @@ def _load(name):
     return np.load(p)
 
 
+def _inverse_subdeterminants(T):
+    """The 4x4 inverse through 2x2 sub-determinants, float32, each operation rounded: how the pose inverses handed to the reference's kernels were formed when
+    tsdf_reference_ieee.npz was generated on the B200 (round 1).  The library now forms them as the reference's host does (tests/test_mat4_inverse_reference.py); the
+    kernels' parity does not depend on which inverse they are handed, the stored voxel words do -- so this test hands the oracle the inverses the generator used."""
+    f = np.float32
+    a = [f(x) for x in np.asarray(T, F).reshape(16)]
+    a00, a01, a02, a03, a10, a11, a12, a13, a20, a21, a22, a23, a30, a31, a32, a33 = a
+    s0, s1, s2 = a00 * a11 - a10 * a01, a00 * a12 - a10 * a02, a00 * a13 - a10 * a03
+    s3, s4, s5 = a01 * a12 - a11 * a02, a01 * a13 - a11 * a03, a02 * a13 - a12 * a03
+    c5, c4, c3 = a22 * a33 - a32 * a23, a21 * a33 - a31 * a23, a21 * a32 - a31 * a22
+    c2, c1, c0 = a20 * a33 - a30 * a23, a20 * a32 - a30 * a22, a20 * a31 - a30 * a21
+    det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0
+    r = f(1.0) / det
+    out = [(a11 * c5 - a12 * c4 + a13 * c3) * r, (-a01 * c5 + a02 * c4 - a03 * c3) * r, (a31 * s5 - a32 * s4 + a33 * s3) * r, (-a21 * s5 + a22 * s4 - a23 * s3) * r,
+           (-a10 * c5 + a12 * c2 - a13 * c1) * r, (a00 * c5 - a02 * c2 + a03 * c1) * r, (-a30 * s5 + a32 * s2 - a33 * s1) * r, (a20 * s5 - a22 * s2 + a23 * s1) * r,
+           (a10 * c4 - a11 * c2 + a13 * c0) * r, (-a00 * c4 + a01 * c2 - a03 * c0) * r, (a30 * s4 - a31 * s2 + a33 * s0) * r, (-a20 * s4 + a21 * s2 - a23 * s0) * r,
+           (-a10 * c3 + a11 * c1 - a12 * c0) * r, (a00 * c3 - a01 * c1 + a02 * c0) * r, (-a30 * s3 + a31 * s1 - a32 * s0) * r, (a20 * s3 - a21 * s1 + a22 * s0) * r]
+    return np.array(out, F).reshape(4, 4)
+
+
 def test_tsdf_oracle_equals_reference_kernels():
     g = _load("tsdf_reference_ieee.npz")
     c = eval(bytes(g["case"]).decode())
     cam = camera_params(c["W"], c["H"])
     hp = default_hash_params(num_buckets=c["num_buckets"], num_sdf_blocks=c["num_sdf_blocks"])
     o = orc.OracleSceneRepHashSDF(hp)
+    if "pose_inverse" not in g.files:                       # generated before the library's host inverse followed the reference's formula
+
+        def set_pose(T, hp=o.hp):
+            T = np.ascontiguousarray(T, F).reshape(4, 4); inv = _inverse_subdeterminants(T)
+            for k in range(16):
+                hp.m_rigidTransform.m[k] = float(T.reshape(16)[k]); hp.m_rigidTransformInverse.m[k] = float(inv.reshape(16)[k])
+        o._set_pose = set_pose
     frames = [synth.make_frame(i, c["W"], c["H"]) for i in c["frames"]]
     for d, col, T in frames:
         o.integrate(T, d, col, cam)

@@ -102,7 +102,7 @@ namespace bf { static BFHashParams g_emuHp; static BFDepthCameraParams g_emuCp;
 const BFHashParams* bound_hash_params() { return &g_emuHp; } const BFDepthCameraParams* bound_camera_params() { return &g_emuCp; } }
 extern "C" void updateConstantHashParams(const BFHashParams* p) { bf::g_emuHp = *p; }
 extern "C" void updateConstantDepthCameraParams(const BFDepthCameraParams* p) { bf::g_emuCp = *p; }
-extern "C" void bfMat4Inverse(const float* m, float* o) { bf::mat4_inverse_hd(m, o); }
+extern "C" void bfMat4Inverse(const float* m, float* o) { bf::mat4_inverse_ref(m, o); }
 '''
 
 
