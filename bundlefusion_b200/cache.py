@@ -83,10 +83,7 @@ class CUDACache:
 
 
 def intrinsics_inverse(K) -> np.ndarray:
-    """Closed-form float32 inverse of [[fx,0,mx,0],[0,fy,my,0],[0,0,1,0],[0,0,0,1]] (mat4f::getInverse on that pattern)."""
-    K = np.asarray(K, np.float32).reshape(4, 4)
-    fx, fy, mx, my = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
-    Ki = np.eye(4, dtype=np.float32)
-    Ki[0, 0] = np.float32(1.0) / fx; Ki[1, 1] = np.float32(1.0) / fy
-    Ki[0, 2] = -mx / fx; Ki[1, 2] = -my / fy
-    return Ki
+    """mat4f::getInverse of an intrinsics matrix, as FL/CUDACache.cpp:25, 38 and FL/Bundler.cpp:25 form it: the general 4x4 inverse (bfMat4Inverse -- the reference's formula bit for
+    bit).  The closed form 1 / fx, -mx / fx is NOT the same float for every calibration (fy / (fx * fy) rounds differently from 1 / fx)."""
+    from .scene_rep import mat4_inverse_f32
+    return mat4_inverse_f32(np.asarray(K, np.float32).reshape(4, 4))

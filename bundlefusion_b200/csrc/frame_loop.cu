@@ -68,11 +68,9 @@ struct Arena {
 };
 
 static void mat_identity(float* m) { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0f : 0.0f; }
-// inverse of an intrinsics-shaped matrix [[fx,0,mx,0],[0,fy,my,0],[0,0,1,0],[0,0,0,1]] (what mat4f::getInverse returns on that pattern)
-static void intrinsics_inverse(const float* K, float* Ki) {
-    mat_identity(Ki);
-    Ki[0] = 1.0f / K[0]; Ki[5] = 1.0f / K[5]; Ki[2] = -K[2] / K[0]; Ki[6] = -K[6] / K[5];
-}
+// mat4f::getInverse of an intrinsics matrix (FL/CUDACache.cpp:25, 38; FL/Bundler.cpp:25): the general inverse in the reference's operation order -- the closed form
+// 1 / fx, -mx / fx rounds differently for some calibrations
+static void intrinsics_inverse(const float* K, float* Ki) { mat4_inverse_ref(K, Ki); }
 
 // ---- CUDACache ------------------------------------------------------------------------------------------------------------------------
 struct Cache {

@@ -404,14 +404,13 @@ def cache_store_frame(depth: np.ndarray, color: np.ndarray, K, cw: int = 80, ch:
                       depthDownSigmaD: float = 1.0, depthDownSigmaR: float = 0.05) -> dict:
     """CUDACache::storeFrame for one frame; K = 4x4 input intrinsics.  Returns host arrays keyed like synth.make_cache_frame."""
     from bundlefusion_b200._capi import BFCacheParams
-    from bundlefusion_b200.cache import intrinsics_inverse
     L = lib()
     depth = np.ascontiguousarray(depth, np.float32); color = np.ascontiguousarray(color, np.uint8)
     p = BFCacheParams()
     p.inputDepthHeight, p.inputDepthWidth = depth.shape
     p.inputColorHeight, p.inputColorWidth = color.shape[:2]
     p.width, p.height = cw, ch
-    Ki = intrinsics_inverse(K)
+    Ki = mat4_inverse(np.asarray(K, np.float32).reshape(4, 4))          # m_inputIntrinsics.getInverse(), FL/CUDACache.cpp:38
     for k in range(16):
         p.inputIntrinsicsInv[k] = float(Ki.reshape(-1)[k])
     p.filterIntensitySigma, p.filterDepthSigmaD, p.filterDepthSigmaR = colorDownSigma, depthDownSigmaD, depthDownSigmaR

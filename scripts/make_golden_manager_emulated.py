@@ -78,7 +78,8 @@ def main():
     print("dense", out["dense_nf"].tolist())
     for k, (depth, color, K, W, H) in enumerate(image_cases()):
         cw, ch = 80, 60
-        Kinv = np.linalg.inv(K).astype(F)
+        from oracle import oracle as orc
+        Kinv = orc.mat4_inverse(np.asarray(K, F))                      # m_inputIntrinsics.getInverse() as the reference's host forms it (FL/CUDACache.cpp:38)
         b = {"depth": np.zeros((ch, cw), F), "campos": np.zeros((ch, cw, 4), F), "intensity": np.zeros((ch, cw), F), "derivs": np.zeros((ch, cw, 2), F),
              "normalsU": np.zeros((ch, cw, 4), np.uint8), "normals": np.zeros((ch, cw, 4), F)}
         fr = RefFrame(*[b[n].ctypes.data for n in ("depth", "campos", "intensity", "derivs", "normalsU", "normals")])
