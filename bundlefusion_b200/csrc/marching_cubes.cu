@@ -197,9 +197,18 @@ __global__ void mc_clamp_kernel(unsigned* count, unsigned maxNumTriangles, const
     if (*count > cap) *count = cap;                                                                                     // appendTriangle, MarchingCubesSDFUtil.h:252-263
 }
 
-static int do_extract(const BFHashDataStruct* hd, const BFHashParams* hp, const BFMarchingCubesParams* p, const BFMarchingCubesParams* d_params, BFMarchingCubesTriangle* tri, unsigned* count) {
+// the kernel is written for the reference's compile-time geometry (SDF_BLOCK_SIZE 8, HASH_BUCKET_SIZE 4: VoxelUtilHashSDF.h:38-41); parameters that say otherwise are refused
+static int check_args(const BFHashDataStruct* hd, const BFHashParams* hp, const BFMarchingCubesParams* p, const BFMarchingCubesTriangle* tri, const unsigned* count) {
     if (!hd || !hp || !p || !tri || !count) return (int)cudaErrorInvalidValue;
-    if (hp->m_hashNumBuckets == 0) return (int)cudaErrorInvalidValue;
+    if (hp->m_hashNumBuckets == 0 || !(hp->m_virtualVoxelSize > 0.0f)) return (int)cudaErrorInvalidValue;
+    if ((p->m_sdfBlockSize != 0 && p->m_sdfBlockSize != BF_SDF_BLOCK_SIZE) || (p->m_hashBucketSize != 0 && p->m_hashBucketSize != BF_HASH_BUCKET_SIZE)) return (int)cudaErrorInvalidValue;
+    if (p->m_hashNumBuckets != 0 && p->m_hashNumBuckets != hp->m_hashNumBuckets) return (int)cudaErrorInvalidValue;          // the grid of the reference's launch and the table disagree
+    return 0;
+}
+
+static int do_extract(const BFHashDataStruct* hd, const BFHashParams* hp, const BFMarchingCubesParams* p, const BFMarchingCubesParams* d_params, BFMarchingCubesTriangle* tri, unsigned* count) {
+    const int bad = check_args(hd, hp, p, tri, count);
+    if (bad) return bad;
     McArgs a;
     a.hd = *hd; a.hp = *hp; a.p = *p; a.d_params = d_params; a.tri = tri; a.count = count;
     const size_t chunks = ((size_t)hp->m_hashNumBuckets * BF_HASH_BUCKET_SIZE + BF_MC_THREADS - 1) / BF_MC_THREADS;
@@ -327,7 +336,8 @@ BF_API void extractIsoSurfaceCUDA(const BFHashDataStruct* hashData, const BFRayC
 }
 BF_API int bfMarchingCubesExtract(const BFHashDataStruct* hashData, const BFHashParams* hashParams, const BFMarchingCubesParams* params, BFMarchingCubesTriangle* d_triangles,
                                   uint32_t* d_numTriangles) {
-    if (!d_numTriangles) return (int)cudaErrorInvalidValue;
+    const int bad = check_args(hashData, hashParams, params, d_triangles, d_numTriangles);
+    if (bad) return bad;
     ++g_launchCount;
     mc_reset_kernel<<<1, 1, 0, stream()>>>(d_numTriangles);
     return do_extract(hashData, hashParams, params, nullptr, d_triangles, d_numTriangles);

@@ -71,6 +71,26 @@ def test_marchingcubes_pod_layouts():
     assert C.sizeof(capi.BFMarchingCubesData) == 32
 
 
+def test_marchingcubes_refuses_other_geometries_before_any_cuda_call():
+    """argument checks run on the host: no GPU needed to see them"""
+    L = capi.lib()
+    L.bfMarchingCubesExtract.argtypes = [C.c_void_p] * 5
+    hd, hp, p = capi.BFHashDataStruct(), capi.BFHashParams(), capi.BFMarchingCubesParams()
+    hp.m_hashNumBuckets = 1009; hp.m_virtualVoxelSize = 0.01
+    p.m_maxNumTriangles = 10; p.m_sdfBlockSize = 8; p.m_hashBucketSize = 4; p.m_hashNumBuckets = 1009
+    buf = (C.c_float * 18)(); n = C.c_uint32(0)
+    ok = lambda: L.bfMarchingCubesExtract(C.byref(hd), C.byref(hp), C.byref(p), buf, C.byref(n))
+    assert L.bfMarchingCubesExtract(None, C.byref(hp), C.byref(p), buf, C.byref(n)) == 1                      # cudaErrorInvalidValue
+    p.m_sdfBlockSize = 16
+    assert ok() == 1
+    p.m_sdfBlockSize = 8; p.m_hashBucketSize = 10
+    assert ok() == 1
+    p.m_hashBucketSize = 4; p.m_hashNumBuckets = 2003
+    assert ok() == 1
+    p.m_hashNumBuckets = 1009; hp.m_virtualVoxelSize = 0.0
+    assert ok() == 1
+
+
 def test_sift_pod_layouts():
     assert C.sizeof(capi.BFImagePairMatch) == 24                      # three device pointers, SIFTImageManager.h:38-42
     assert C.sizeof(capi.BFSiftMatchJob) == 64 and capi.BFSiftMatchJob.out.offset == 32 and capi.BFSiftMatchJob.keyPointOffset.offset == 56
