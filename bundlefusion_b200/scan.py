@@ -32,11 +32,9 @@ def reconstruct(sens_path: str, ply_path: str | None = None, device="cuda:0", ma
     """runs the sequence; returns {"frames", "valid", "keyframes", "trajectory" [n, 4, 4], "mesh_path", "triangles", "status" (per frame)}"""
     r = SensorDataReader(sens_path)
     hd = r.header
-    if (hd.colorWidth, hd.colorHeight) != (hd.depthWidth, hd.depthHeight):
-        raise ValueError(f"{sens_path}: colour {hd.colorWidth}x{hd.colorHeight} and depth {hd.depthWidth}x{hd.depthHeight} differ; resample the colour stream to the depth size first "
-                         "(the reference's CUDAImageManager does that on arrival)")
     n = len(r) if max_frames is None else min(len(r), max_frames)
     P = default_params(hd.depthWidth, hd.depthHeight)
+    P.colorWidth, P.colorHeight = hd.colorWidth, hd.colorHeight          # the ingest resamples colour to the integration size, as CUDAImageManager::process does
     for k in range(16):
         P.depthIntrinsics[k] = hd.depthIntrinsic[k]; P.colorIntrinsics[k] = hd.colorIntrinsic[k]
     P.maxNumFrames = max(int(P.submapSize) * 2, n + int(P.submapSize))
