@@ -644,7 +644,7 @@ def mesh_leg(L, loop, P, dev, active_blocks):
         import torch
         from bundlefusion_b200.marching_cubes import _bind, marching_cubes_params
         _bind(L)
-        hp = P.hash
+        hp = L.bfFrameLoopGetHashParams(loop._h).contents           # the loop's own copy (table size, voxel size)
         cap = 6_000_000                                               # 72 B each
         mp = marching_cubes_params(int(hp.m_hashNumBuckets), float(hp.m_virtualVoxelSize), cap)
         tri = torch.empty(cap * 18, dtype=torch.float32, device=dev)
