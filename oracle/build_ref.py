@@ -421,12 +421,15 @@ def build_sens_host():
 
 
 def build_trajectory_host():
-    """The reference's TrajectoryManager (FL/TrajectoryManager.{h,cpp}) and the Lie part of FL/PoseHelper.h compiled by g++ -> libref_trajectory_host.so
-    (runs on the CPU), against the minimal mLib types of oracle/ref_traj_stubs/mlib_min.h (mLib is an un-vendored submodule and does not compile
-    under g++).  Patch on the scratch copy of PoseHelper.h: the evaluation / file helpers in front of the pose maps (they need mLib's eigen
-    solver and quaternions) are cut; the Lie pose maps are untouched.  Built -DNDEBUG like the reference's Release configuration (its asserts on list
-    invariants fire on operation orders the application does not produce)."""
+    """The reference's TrajectoryManager (FL/TrajectoryManager.{h,cpp}) and the Lie part of FL/PoseHelper.h compiled by g++ against mLib's OWN math types
+    (prepare_mlib_scratch) -> libref_trajectory_host.so (runs on the CPU).  oracle/ref_traj_stubs holds what is not mLib: stdafx.h (mLibCore.h, the POD float4x4 of the
+    CUDA side, cudaMemcpy as memcpy), an empty CUDAImageManager.h and the two GlobalAppState settings the constructor reads.  (Until the g++ patches for mLib were
+    found this was built against hand-written minimal vector / matrix types; the golden file that build produced is reproduced byte for byte by this one.)  Patch on the
+    scratch copy of PoseHelper.h: the evaluation / file helpers in front of the pose maps are cut; the Lie pose maps are untouched.  Built -DNDEBUG like the reference's
+    Release configuration (its asserts on list invariants fire on operation orders the application does not produce).  TrajectoryManager.cpp waits for a key press
+    (getchar) after one of its error messages: drive the library with stdin closed."""
     root = os.path.join(TMP, "trajhost")
+    cmd, srcs = prepare_mlib_scratch(os.path.join(TMP, "trajhost_mlib"))
     os.makedirs(root)
     S = os.path.join(REF, "Source")
     for f in ("TrajectoryManager.h", "TrajectoryManager.cpp", "PoseHelper.h", "GlobalDefines.h"):
@@ -435,9 +438,8 @@ def build_trajectory_host():
         (r"\tstatic unsigned int countNumValidTransforms.*?(#ifndef USE_LIE_SPACE)", r"\1", 1),
     ])
     stubs = os.path.join(HERE, "ref_traj_stubs")
-    cmd = ["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-DNDEBUG", "-shared", "-fPIC", "-I", stubs, "-I", root,
-           os.path.join(HERE, "ref_trajectory_host.cpp"), os.path.join(root, "TrajectoryManager.cpp"), "-o", os.path.join(OUT, "libref_trajectory_host.so"), "-lm"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    r = subprocess.run(cmd + ["-DNDEBUG", "-I", stubs, "-I", root, os.path.join(HERE, "ref_trajectory_host.cpp"), os.path.join(root, "TrajectoryManager.cpp")] + srcs +
+                       ["-o", os.path.join(OUT, "libref_trajectory_host.so"), "-lm"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-6000:])
         raise RuntimeError("building libref_trajectory_host.so failed")

@@ -1,3 +1,2 @@
 // TEST INFRASTRUCTURE ONLY: empty stand-in (TrajectoryManager.h includes it, uses nothing from it)
 #pragma once
-#include "mlib_min.h"

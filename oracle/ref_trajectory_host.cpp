@@ -1,5 +1,5 @@
 // ref_trajectory_host.cpp -- TEST INFRASTRUCTURE ONLY.  C entry points around the REFERENCE's own TrajectoryManager (FL/TrajectoryManager.{h,cpp}) and
-// the Lie part of FL/PoseHelper.h, compiled by g++ from the scratch copy against the minimal mLib types of oracle/ref_traj_stubs/mlib_min.h
+// the Lie part of FL/PoseHelper.h, compiled by g++ from the scratch copy against mLib's own math types (oracle/ref_traj_stubs/stdafx.h)
 // (oracle/build_ref.py -> oracle/_ref/libref_trajectory_host.so).  Runs on the CPU.  This file contains no reference code.
 #include "stdafx.h"
 #include "TrajectoryManager.h"
