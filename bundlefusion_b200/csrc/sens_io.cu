@@ -175,7 +175,66 @@ void idct_block(const short d[64], uint8_t* out, size_t stride) {
         o[2] = clamp_u8((L.x2 + L.t1) >> 17); o[5] = clamp_u8((L.x2 - L.t1) >> 17); o[3] = clamp_u8((L.x3 + L.t0) >> 17); o[4] = clamp_u8((L.x3 - L.t0) >> 17);
     }
 }
-struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; int bw = 0, bh = 0; size_t stride = 0; std::vector<uint8_t> plane; };
+struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; int bw = 0, bh = 0; size_t stride = 0; std::vector<uint8_t> plane; std::vector<short> coeff; };     // coeff: progressive only, [bh][bw][64]
+
+// One block of a progressive scan (T.81 G.1.2; the reference's decoder: stb_image v2.08 stbi__jpeg_decode_block_prog_dc / _prog_ac).  Coefficients accumulate in
+// `data` (natural order, not yet de-quantised) over the scans; eobRun is the scan's count of further blocks that are all end-of-band.
+int prog_block(BitReader& br, const Huff* hdc, const Huff* hac, Comp* c, short* data, int ss, int se, int ah, int al, int& eobRun) {
+    if (ss == 0) {                                                                     // DC: first scan carries the value (shifted), later ones one more bit each
+        if (se != 0) return BF_SENS_ERR_FORMAT;
+        if (ah == 0) {
+            const int t = huff_decode(br, *hdc);
+            if (t < 0 || t > 15) return BF_SENS_ERR_FORMAT;
+            c->pred += extend(br.bits(t), t);
+            data[0] = (short)(c->pred << al);
+        } else if (br.bit()) data[0] += (short)(1 << al);
+        return BF_SENS_OK;
+    }
+    if (ah == 0) {                                                                     // AC, first pass over the band [ss, se]
+        if (eobRun) { --eobRun; return BF_SENS_OK; }
+        int k = ss;
+        do {
+            const int rs = huff_decode(br, *hac);
+            if (rs < 0) return BF_SENS_ERR_FORMAT;
+            const int sz = rs & 15, r = rs >> 4;
+            if (sz == 0) {
+                if (r < 15) { eobRun = 1 << r; if (r) eobRun += br.bits(r); --eobRun; break; }
+                k += 16;
+            } else {
+                k += r;
+                if (k > 63) return BF_SENS_ERR_FORMAT;
+                data[kZigzag[k++]] = (short)(extend(br.bits(sz), sz) << al);
+            }
+        } while (k <= se);
+        return BF_SENS_OK;
+    }
+    const short bit = (short)(1 << al);                                                // AC refinement: one more bit for known coefficients, new ones of magnitude 1
+    auto refine = [&](short* q) { if (br.bit() && (*q & bit) == 0) { if (*q > 0) *q += bit; else *q -= bit; } };
+    if (eobRun) {
+        --eobRun;
+        for (int k = ss; k <= se; ++k) { short* q = &data[kZigzag[k]]; if (*q != 0) refine(q); }
+        return BF_SENS_OK;
+    }
+    int k = ss;
+    do {
+        const int rs = huff_decode(br, *hac);
+        if (rs < 0) return BF_SENS_ERR_FORMAT;
+        int sz = rs & 15, r = rs >> 4;
+        if (sz == 0) {
+            if (r < 15) { eobRun = (1 << r) - 1; if (r) eobRun += br.bits(r); r = 64; }      // the rest of this block: only refinements
+        } else {
+            if (sz != 1) return BF_SENS_ERR_FORMAT;
+            sz = br.bit() ? bit : -bit;
+        }
+        while (k <= se) {                                                              // skip r zero-history coefficients, refining the non-zero ones passed
+            short* q = &data[kZigzag[k++]];
+            if (*q != 0) refine(q);
+            else { if (r == 0) { *q = (short)sz; break; } --r; }
+        }
+    } while (k <= se);
+    return BF_SENS_OK;
+}
+
 
 int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t* H) {
     if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return BF_SENS_ERR_FORMAT;
@@ -183,7 +242,7 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
     Huff hdc[4], hac[4];
     std::vector<Comp> comps;
     int width = 0, height = 0, hmax = 1, vmax = 1, restart = 0;
-    bool haveFrame = false, decoded = false;
+    bool haveFrame = false, decoded = false, progressive = false;
     size_t at = 2;
     while (at + 4 <= n) {
         if (d[at] != 0xFF) { ++at; continue; }
@@ -218,7 +277,8 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
                 memcpy(h.vals, s + i, total); i += total;
                 huff_build(h);
             }
-        } else if (m == 0xC0 || m == 0xC1) {                                          // SOF0 / SOF1: sequential DCT, Huffman
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {                             // SOF0 / SOF1: sequential DCT; SOF2: progressive DCT; Huffman
+            progressive = m == 0xC2;
             if (sl < 6 || s[0] != 8) return BF_SENS_ERR_UNSUPPORTED;
             height = (s[1] << 8) | s[2]; width = (s[3] << 8) | s[4];
             const int nf = s[5];
@@ -234,7 +294,8 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
             haveFrame = true;
             *W = (uint32_t)width; *H = (uint32_t)height;
             if (!rgb) return BF_SENS_OK;
-        } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) return BF_SENS_ERR_UNSUPPORTED;    // progressive, lossless, arithmetic
+            if (progressive) for (Comp& c : comps) c.coeff.assign((size_t)c.bw * c.bh * 64, 0);
+        } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) return BF_SENS_ERR_UNSUPPORTED;    // lossless, hierarchical, arithmetic
         else if (m == 0xDD) { if (sl < 2) return BF_SENS_ERR_FORMAT; restart = (s[0] << 8) | s[1]; }
         else if (m == 0xDA) {                                                         // SOS + entropy-coded segment
             if (!haveFrame || sl < 1) return BF_SENS_ERR_FORMAT;
@@ -246,10 +307,17 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
                 for (Comp& q : comps) if (q.id == s[1 + 2 * k]) c = &q;
                 if (!c) return BF_SENS_ERR_FORMAT;
                 c->td = s[2 + 2 * k] >> 4; c->ta = s[2 + 2 * k] & 15; c->pred = 0;
-                if (c->td > 3 || c->ta > 3 || !hdc[c->td].set || !hac[c->ta].set || !qset[c->tq]) return BF_SENS_ERR_FORMAT;
+                if (c->td > 3 || c->ta > 3 || !qset[c->tq]) return BF_SENS_ERR_FORMAT;
+                if (!progressive && (!hdc[c->td].set || !hac[c->ta].set)) return BF_SENS_ERR_FORMAT;
                 sc.push_back(c);
             }
-            if (s[1 + 2 * ns] != 0 || s[2 + 2 * ns] != 63) return BF_SENS_ERR_UNSUPPORTED;
+            const int ss = s[1 + 2 * ns], se = s[2 + 2 * ns], ah = s[3 + 2 * ns] >> 4, al = s[3 + 2 * ns] & 15;
+            if (!progressive && (ss != 0 || se != 63)) return BF_SENS_ERR_UNSUPPORTED;
+            if (progressive) {
+                if (ss > 63 || se > 63 || ss > se || ah > 13 || al > 13 || (ss != 0 && ns != 1)) return BF_SENS_ERR_FORMAT;
+                for (Comp* c : sc) if (ss == 0 ? (ah == 0 && !hdc[c->td].set) : !hac[c->ta].set) return BF_SENS_ERR_FORMAT;
+            }
+            int eobRun = 0;
             BitReader br; br.p = d + at + len; br.end = d + n;
             // an interleaved scan walks MCUs of h x v blocks per component; a single-component scan walks that component's own blocks (T.81 A.2.2 / A.2.3)
             const bool inter = ns > 1;
@@ -264,12 +332,20 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
                         if (br.p + 1 < br.end) br.p += 2;
                         nextRst = (nextRst + 1) & 7;
                         for (Comp* c : sc) c->pred = 0;
+                        eobRun = 0;
                         untilRestart = restart;
                     }
                     for (Comp* c : sc) {
                         const int nbx = inter ? c->h : 1, nby = inter ? c->v : 1;
                         for (int by = 0; by < nby; ++by)
                             for (int bx = 0; bx < nbx; ++bx) {
+                                if (progressive) {
+                                    const int gx = (inter ? mx * c->h : mx) + bx, gy = (inter ? my * c->v : my) + by;
+                                    if (gx >= c->bw || gy >= c->bh) return BF_SENS_ERR_FORMAT;
+                                    const int rc = prog_block(br, &hdc[c->td], &hac[c->ta], c, c->coeff.data() + ((size_t)gy * c->bw + gx) * 64, ss, se, ah, al, eobRun);
+                                    if (rc) return rc;
+                                    continue;
+                                }
                                 short blk[64]; for (int k = 0; k < 64; ++k) blk[k] = 0;
                                 const int t = huff_decode(br, hdc[c->td]);
                                 if (t < 0 || t > 11) return BF_SENS_ERR_FORMAT;
@@ -298,6 +374,16 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
         at += len;
     }
     if (!haveFrame || !decoded) return BF_SENS_ERR_FORMAT;
+    if (progressive)                                                                   // all scans are in: de-quantise and transform the blocks under the image
+        for (Comp& c : comps) {
+            const int nbx = ((width * c.h + hmax - 1) / hmax + 7) / 8, nby = ((height * c.v + vmax - 1) / vmax + 7) / 8;
+            for (int gy = 0; gy < nby; ++gy)
+                for (int gx = 0; gx < nbx; ++gx) {
+                    short* blk = c.coeff.data() + ((size_t)gy * c.bw + gx) * 64;
+                    for (int k = 0; k < 64; ++k) blk[kZigzag[k]] = (short)(blk[kZigzag[k]] * (int)qt[c.tq][k]);
+                    idct_block(blk, c.plane.data() + (size_t)gy * 8 * c.stride + (size_t)gx * 8, c.stride);
+                }
+        }
     // ---- up-sample and convert, row by row, with the reference decoder's arithmetic (stb_image v2.08: load_jpeg_image and its resample_row_* / YCbCr kernels):
     // vertically 3/4 of the nearer chroma row + 1/4 of the farther one, horizontally the same triangle on those sums; fixed-point JFIF conversion ----
     std::vector<std::vector<uint8_t>> line(comps.size());
@@ -364,7 +450,7 @@ struct BFSensWriter { FILE* f = nullptr; BFSensHeader h; long numFramesPos = 0; 
 BF_API const char* bfSensErrorString(int code) {
     switch (code) {
         case BF_SENS_OK: return "ok"; case BF_SENS_ERR_IO: return "i/o error"; case BF_SENS_ERR_FORMAT: return "malformed data";
-        case BF_SENS_ERR_UNSUPPORTED: return "unsupported variant (progressive JPEG, OCCI depth, 16-bit / interlaced PNG, ...)";
+        case BF_SENS_ERR_UNSUPPORTED: return "unsupported variant (lossless / arithmetic-coded JPEG, OCCI depth, 16-bit / interlaced PNG, ...)";
         case BF_SENS_ERR_RANGE: return "frame index out of range"; case BF_SENS_ERR_ARGUMENT: return "invalid argument";
     }
     return "unknown";

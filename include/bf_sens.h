@@ -7,8 +7,8 @@
  *   RGBDFrame::decompressDepthAlloc / decompressColorAlloc                                ext-depthcamera/sensorData.h:540-600, 640-668
  *   SensorDataReader::processDepth (ushort -> metres, 0 -> -inf; RGB -> RGBX)             FL/SensorDataReader.cpp:100-117
  * mLib decodes through a vendored stb_image v2.08 (JPEG / PNG / zlib).  Here: zlib from the system library, PNG (8-bit grey / RGB / RGBA, non-interlaced) and
- * baseline JPEG (sequential DCT, Huffman, up to 2x2 chroma subsampling, restart markers) decoded by this library's own code; progressive JPEG and OCCI
- * depth are reported as unsupported.  JPEG decoding is not normative in its last bit (IDCT, chroma up-sampling, colour conversion) and SIFT sees that bit:
+ * baseline and progressive JPEG (Huffman; up to 2x2 chroma subsampling, restart markers) decoded by this library's own code; arithmetic-coded / lossless JPEG
+ * (which the reference's decoder refuses too) and OCCI depth are reported as unsupported.  JPEG decoding is not normative in its last bit (IDCT, chroma up-sampling, colour conversion) and SIFT sees that bit:
  * the decoder restates the reference decoder's fixed-point pipeline and is bit-identical to it (tests/test_sens_reference_stb.py: golden outputs of the
  * reference's stb_image compiled from /root/reference; libjpeg's output is compared under a tolerance of 3 levels besides).  The container: files written by the
  * reference's ml::SensorData are read field for field, the writer's raw-depth file equals the reference's byte for byte (tests/test_sens_reference_sensordata.py).

@@ -164,9 +164,12 @@ def test_decoders_on_odd_sizes_grey_restart_markers_and_errors():
     bio = io.BytesIO(); Image.fromarray(img).save(bio, "JPEG", quality=90, subsampling=2, restart_marker_blocks=3)        # DRI + RSTn
     if b"\xff\xdd" in bio.getvalue():
         assert np.abs(sens.decode_jpeg(bio.getvalue()).astype(int) - pil_decode(bio.getvalue()).astype(int))[:-2, :-2].max() <= 3
-    bio = io.BytesIO(); Image.fromarray(img).save(bio, "JPEG", quality=90, progressive=True)
+    bio = io.BytesIO(); Image.fromarray(img).save(bio, "JPEG", quality=90, progressive=True)                              # SOF2: spectral selection + successive approximation
+    assert b"\xff\xc2" in bio.getvalue()
+    assert np.abs(sens.decode_jpeg(bio.getvalue()).astype(int) - pil_decode(bio.getvalue()).astype(int))[:-2, :-2].max() <= 3
+    arith = bio.getvalue().replace(b"\xff\xc2", b"\xff\xc9", 1)                                                         # SOF9 (arithmetic coding): refused, as by the reference's decoder
     with pytest.raises(RuntimeError, match="unsupported"):
-        sens.decode_jpeg(bio.getvalue())
+        sens.decode_jpeg(arith)
     for mode in ("RGB", "RGBA", "L", "LA"):
         bio = io.BytesIO(); Image.fromarray(img).convert(mode).save(bio, "PNG")
         assert np.array_equal(sens.decode_png(bio.getvalue()), np.asarray(Image.open(io.BytesIO(bio.getvalue())).convert("RGB")))

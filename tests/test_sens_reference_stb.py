@@ -4,7 +4,8 @@ ext-depthcamera/sensorData/.  oracle/build_ref.py (build_sens_host) compiles tho
 scripts/make_golden_sens_stb.py ran it on the streams below and stored streams + outputs in tests/golden/sens_reference_stb.npz.
 
 JPEG decoding is not normative in its last bit (IDCT, chroma up-sampling, colour conversion), and the frame loop's SIFT sees that bit: csrc/sens_io.cu restates the
-reference decoder's fixed-point pipeline, and the bar here is bit-exact on every stream (odd sizes, every sub-sampling up to 2x2, restart intervals, grey)."""
+reference decoder's fixed-point pipeline, and the bar here is bit-exact on every stream (odd sizes, every sub-sampling up to 2x2, restart intervals, grey, baseline
+and progressive)."""
 import ctypes as C
 import io
 import os
@@ -42,6 +43,10 @@ def make_streams():
         for kw in VARIANTS if h * w <= 64 * 64 else VARIANTS[:4]:
             bio = io.BytesIO(); Image.fromarray(img).save(bio, "JPEG", **kw); jpegs.append(bio.getvalue())
         bio = io.BytesIO(); Image.fromarray(img[..., 0]).save(bio, "JPEG", quality=80); jpegs.append(bio.getvalue())          # one component
+        if h * w <= 64 * 64 or (h, w) == (120, 160):                                                                     # progressive (SOF2): DC / AC first and refinement scans, end-of-band runs
+            for kw in (dict(quality=88, subsampling=2, progressive=True), dict(quality=40, subsampling=0, progressive=True)):
+                bio = io.BytesIO(); Image.fromarray(img).save(bio, "JPEG", **kw); jpegs.append(bio.getvalue())
+            bio = io.BytesIO(); Image.fromarray(img[..., 1]).save(bio, "JPEG", quality=70, progressive=True); jpegs.append(bio.getvalue())
         if (h, w) in ((37, 53), (2, 3), (48, 64)):
             for mode in ("RGB", "RGBA", "L", "LA"):
                 bio = io.BytesIO(); Image.fromarray(img).convert(mode).save(bio, "PNG"); pngs.append(bio.getvalue())
@@ -96,7 +101,7 @@ def assemble_sens(path, w, h, color_blobs, depth_blobs, cc, dc):
 def test_jpeg_and_png_decoders_bit_exact_with_the_references_stb_golden():
     g = np.load(GOLDEN)
     n = int(g["num_jpeg"])
-    assert n >= 50
+    assert n >= 80 and sum(1 for i in range(n) if b"\xff\xc2" in g[f"jpeg_{i}"].tobytes()) >= 20
     for i in range(n):
         got = sens.decode_jpeg(g[f"jpeg_{i}"].tobytes())
         assert got.shape == g[f"jpeg_rgb_{i}"].shape and np.array_equal(got, g[f"jpeg_rgb_{i}"]), i
@@ -137,7 +142,8 @@ def test_live_against_the_references_stb(tmp_path):
         h, w = int(rng.integers(1, 90)), int(rng.integers(1, 90))
         img = picture(rng, h, w)
         bio = io.BytesIO()
-        Image.fromarray(img).save(bio, "JPEG", quality=int(rng.integers(5, 101)), subsampling=int(rng.integers(0, 3)), restart_marker_blocks=int(rng.integers(0, 4)))
+        Image.fromarray(img).save(bio, "JPEG", quality=int(rng.integers(5, 101)), subsampling=int(rng.integers(0, 3)), restart_marker_blocks=int(rng.integers(0, 4)),
+                                  progressive=bool(rng.integers(0, 2)))
         assert np.array_equal(sens.decode_jpeg(bio.getvalue()), R.decode(bio.getvalue())), (h, w)
     K = np.eye(4, dtype=np.float32)
     p = str(tmp_path / "w.sens")
