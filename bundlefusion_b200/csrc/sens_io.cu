@@ -53,40 +53,70 @@ int decode_png(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t* 
     size_t at = 8;
     uint32_t w = 0, h = 0; int depth = 0, type = -1, interlace = 0;
     std::vector<uint8_t> idat;
+    uint8_t palette[256 * 3]; unsigned paletteLen = 0;
     while (at + 12 <= n) {
         const uint32_t len = be32(d + at); const uint8_t* tag = d + at + 4; const uint8_t* body = d + at + 8;
         if (at + 12 + (size_t)len > n) return BF_SENS_ERR_FORMAT;
         if (!memcmp(tag, "IHDR", 4)) { if (len < 13) return BF_SENS_ERR_FORMAT; w = be32(body); h = be32(body + 4); depth = body[8]; type = body[9]; interlace = body[12]; }
+        else if (!memcmp(tag, "PLTE", 4)) { if (len > 768 || len % 3) return BF_SENS_ERR_FORMAT; memcpy(palette, body, len); paletteLen = len / 3; }
         else if (!memcmp(tag, "IDAT", 4)) idat.insert(idat.end(), body, body + len);
         else if (!memcmp(tag, "IEND", 4)) break;
         at += 12 + (size_t)len;
     }
     if (w == 0 || h == 0) return BF_SENS_ERR_FORMAT;
-    if (depth != 8 || interlace != 0 || !(type == 0 || type == 2 || type == 4 || type == 6)) return BF_SENS_ERR_UNSUPPORTED;
+    // what the reference's decoder (stb_image v2.08) reads: 8 bits per channel for every colour type, 1 / 2 / 4 bits for grey and palette images, Adam7 interlacing; not 16 bits
+    const bool small = depth == 1 || depth == 2 || depth == 4;
+    if (!(type == 0 || type == 2 || type == 3 || type == 4 || type == 6) || interlace > 1) return BF_SENS_ERR_UNSUPPORTED;
+    if (!(depth == 8 || (small && (type == 0 || type == 3)))) return BF_SENS_ERR_UNSUPPORTED;
+    if (type == 3 && paletteLen == 0) return BF_SENS_ERR_FORMAT;
     *W = w; *H = h;
     if (!rgb) return BF_SENS_OK;
-    const int ch = type == 0 ? 1 : (type == 4 ? 2 : (type == 2 ? 3 : 4));
-    const size_t stride = (size_t)w * ch;
+    const int ch = (type == 0 || type == 3) ? 1 : (type == 4 ? 2 : (type == 2 ? 3 : 4));
+    const int bitsPerPixel = ch * depth, fbpp = bitsPerPixel >= 8 ? bitsPerPixel / 8 : 1;       // the filters work on bytes; below 8 bits a "pixel" is the previous byte
+    // Adam7: seven reduced images, each filtered and stored like an image of its own (PNG 1.2, section 8.2); not interlaced: one pass over everything
+    static const int px0[7] = { 0, 4, 0, 2, 0, 1, 0 }, py0[7] = { 0, 0, 4, 0, 2, 0, 1 }, pdx[7] = { 8, 8, 4, 4, 2, 2, 1 }, pdy[7] = { 8, 8, 8, 4, 4, 2, 2 };
+    size_t need = 0;
+    for (int p = 0; p < (interlace ? 7 : 1); ++p) {
+        const uint32_t pw = interlace ? (w + pdx[p] - 1 - px0[p]) / pdx[p] : w, ph = interlace ? (h + pdy[p] - 1 - py0[p]) / pdy[p] : h;
+        if (pw && ph) need += (((size_t)pw * bitsPerPixel + 7) / 8 + 1) * ph;
+    }
     std::vector<uint8_t> raw;
-    const int rc = inflate_all(idat.data(), idat.size(), raw, (stride + 1) * h);
+    const int rc = inflate_all(idat.data(), idat.size(), raw, need);
     if (rc) return rc;
-    if (raw.size() < (stride + 1) * h) return BF_SENS_ERR_FORMAT;
-    std::vector<uint8_t> prev(stride, 0), cur(stride);
-    for (uint32_t y = 0; y < h; ++y) {
-        const uint8_t* s = raw.data() + (stride + 1) * y;
-        const int f = s[0]; ++s;
-        for (size_t i = 0; i < stride; ++i) {
-            const int a = i >= (size_t)ch ? cur[i - ch] : 0, b = prev[i], c = i >= (size_t)ch ? prev[i - ch] : 0;
-            int v = s[i];
-            switch (f) { case 0: break; case 1: v += a; break; case 2: v += b; break; case 3: v += (a + b) >> 1; break; case 4: v += paeth(a, b, c); break; default: return BF_SENS_ERR_FORMAT; }
-            cur[i] = (uint8_t)v;
+    if (raw.size() < need) return BF_SENS_ERR_FORMAT;
+    const int greyScale = depth == 1 ? 255 : (depth == 2 ? 85 : (depth == 4 ? 17 : 1));
+    const uint8_t* s = raw.data();
+    for (int p = 0; p < (interlace ? 7 : 1); ++p) {
+        const uint32_t pw = interlace ? (w + pdx[p] - 1 - px0[p]) / pdx[p] : w, ph = interlace ? (h + pdy[p] - 1 - py0[p]) / pdy[p] : h;
+        if (!pw || !ph) continue;
+        const size_t stride = ((size_t)pw * bitsPerPixel + 7) / 8;
+        std::vector<uint8_t> prev(stride, 0), cur(stride);
+        for (uint32_t y = 0; y < ph; ++y) {
+            const int f = s[0]; ++s;
+            for (size_t i = 0; i < stride; ++i) {
+                const int a = i >= (size_t)fbpp ? cur[i - fbpp] : 0, bb = prev[i], c = i >= (size_t)fbpp ? prev[i - fbpp] : 0;
+                int v = s[i];
+                switch (f) { case 0: break; case 1: v += a; break; case 2: v += bb; break; case 3: v += (a + bb) >> 1; break; case 4: v += paeth(a, bb, c); break; default: return BF_SENS_ERR_FORMAT; }
+                cur[i] = (uint8_t)v;
+            }
+            s += stride;
+            const uint32_t oy = interlace ? (uint32_t)py0[p] + y * (uint32_t)pdy[p] : y;
+            for (uint32_t x = 0; x < pw; ++x) {
+                const uint32_t ox = interlace ? (uint32_t)px0[p] + x * (uint32_t)pdx[p] : x;
+                uint8_t* o = rgb + ((size_t)oy * w + ox) * 3;
+                if (ch == 1) {
+                    unsigned v = depth == 8 ? cur[x] : (cur[((size_t)x * depth) >> 3] >> (8 - depth - (int)(((size_t)x * depth) & 7))) & ((1u << depth) - 1u);      // samples are packed from the high bit down
+                    if (type == 3) {
+                        if (v >= paletteLen) return BF_SENS_ERR_FORMAT;
+                        o[0] = palette[3 * v]; o[1] = palette[3 * v + 1]; o[2] = palette[3 * v + 2];
+                    } else o[0] = o[1] = o[2] = (uint8_t)(v * greyScale);
+                } else {
+                    const uint8_t* px = &cur[(size_t)x * ch];
+                    if (ch == 2) { o[0] = o[1] = o[2] = px[0]; } else { o[0] = px[0]; o[1] = px[1]; o[2] = px[2]; }
+                }
+            }
+            prev.swap(cur);
         }
-        uint8_t* o = rgb + (size_t)3 * w * y;
-        for (uint32_t x = 0; x < w; ++x) {
-            const uint8_t* px = &cur[(size_t)x * ch];
-            if (ch <= 2) { o[3 * x] = o[3 * x + 1] = o[3 * x + 2] = px[0]; } else { o[3 * x] = px[0]; o[3 * x + 1] = px[1]; o[3 * x + 2] = px[2]; }
-        }
-        prev.swap(cur);
     }
     return BF_SENS_OK;
 }
@@ -450,7 +480,7 @@ struct BFSensWriter { FILE* f = nullptr; BFSensHeader h; long numFramesPos = 0; 
 BF_API const char* bfSensErrorString(int code) {
     switch (code) {
         case BF_SENS_OK: return "ok"; case BF_SENS_ERR_IO: return "i/o error"; case BF_SENS_ERR_FORMAT: return "malformed data";
-        case BF_SENS_ERR_UNSUPPORTED: return "unsupported variant (lossless / arithmetic-coded JPEG, OCCI depth, 16-bit / interlaced PNG, ...)";
+        case BF_SENS_ERR_UNSUPPORTED: return "unsupported variant (lossless / arithmetic-coded JPEG, OCCI depth, 16-bit PNG, ...)";
         case BF_SENS_ERR_RANGE: return "frame index out of range"; case BF_SENS_ERR_ARGUMENT: return "invalid argument";
     }
     return "unknown";

@@ -6,7 +6,8 @@
  *   ml::SensorData::loadFromFile / saveToFile, RGBDFrame::loadFromFile / saveToFile      ext-depthcamera/sensorData.h:676-700, 1040-1048, 1187-1227   (on-disk layout, version 4)
  *   RGBDFrame::decompressDepthAlloc / decompressColorAlloc                                ext-depthcamera/sensorData.h:540-600, 640-668
  *   SensorDataReader::processDepth (ushort -> metres, 0 -> -inf; RGB -> RGBX)             FL/SensorDataReader.cpp:100-117
- * mLib decodes through a vendored stb_image v2.08 (JPEG / PNG / zlib).  Here: zlib from the system library, PNG (8-bit grey / RGB / RGBA, non-interlaced) and
+ * mLib decodes through a vendored stb_image v2.08 (JPEG / PNG / zlib).  Here: zlib from the system library, PNG (what the reference's decoder reads: 8 bits per channel for every colour type, 1 / 2 / 4 bits for grey and palette images,
+ * Adam7 interlacing; not 16 bits) and
  * baseline and progressive JPEG (Huffman; up to 2x2 chroma subsampling, restart markers) decoded by this library's own code; arithmetic-coded / lossless JPEG
  * (which the reference's decoder refuses too) and OCCI depth are reported as unsupported.  JPEG decoding is not normative in its last bit (IDCT, chroma up-sampling, colour conversion) and SIFT sees that bit:
  * the decoder restates the reference decoder's fixed-point pipeline and is bit-identical to it (tests/test_sens_reference_stb.py: golden outputs of the

@@ -170,9 +170,19 @@ def test_decoders_on_odd_sizes_grey_restart_markers_and_errors():
     arith = bio.getvalue().replace(b"\xff\xc2", b"\xff\xc9", 1)                                                         # SOF9 (arithmetic coding): refused, as by the reference's decoder
     with pytest.raises(RuntimeError, match="unsupported"):
         sens.decode_jpeg(arith)
-    for mode in ("RGB", "RGBA", "L", "LA"):
+    for mode in ("RGB", "RGBA", "L", "LA", "P", "1"):                                             # "1": one bit per pixel, rows filtered (libpng picks Up / Paeth)
         bio = io.BytesIO(); Image.fromarray(img).convert(mode).save(bio, "PNG")
         assert np.array_equal(sens.decode_png(bio.getvalue()), np.asarray(Image.open(io.BytesIO(bio.getvalue())).convert("RGB")))
+    for colors in (2, 4, 16):                                                                     # palette images of 1, 2 and 4 bits
+        bio = io.BytesIO(); Image.fromarray(img).convert("P", palette=Image.ADAPTIVE, colors=colors).save(bio, "PNG", bits={2: 1, 4: 2, 16: 4}[colors])
+        assert np.array_equal(sens.decode_png(bio.getvalue()), np.asarray(Image.open(io.BytesIO(bio.getvalue())).convert("RGB")))
+    from tests.test_sens_reference_stb import handmade_png
+    for il in (True, False):                                                                      # Adam7 (PIL reads it, cannot write it)
+        d = handmade_png(img, 2, 8, None, il)
+        assert np.array_equal(sens.decode_png(d), img) and np.array_equal(np.asarray(Image.open(io.BytesIO(d)).convert("RGB")), img)
+    bio = io.BytesIO(); Image.fromarray(img[..., 0].astype(np.uint16) * 257).save(bio, "PNG")                               # 16 bits per channel: refused, as by the reference's decoder
+    with pytest.raises(RuntimeError, match="unsupported"):
+        sens.decode_png(bio.getvalue())
     with pytest.raises(RuntimeError):
         sens.decode_png(b"not a png at all, not even close to one........")
     with pytest.raises(RuntimeError):

@@ -33,6 +33,35 @@ def picture(rng, h, w):
     return np.clip(img + rng.integers(-6, 7, img.shape), 0, 255).astype(np.uint8)
 
 
+def handmade_png(arr, ctype, depth, palette=None, interlace=True):
+    """a PNG assembled by hand, filter type 0 on every row, optionally Adam7-interlaced (PIL writes neither interlaced files nor 2-bit grey); arr: [h, w] samples
+    (colour type 0 / 3) or [h, w, c] bytes"""
+    import zlib
+
+    def chunk(t, b):
+        return struct.pack(">I", len(b)) + t + b + struct.pack(">I", zlib.crc32(t + b) & 0xffffffff)
+    h, w = arr.shape[:2]
+    raw = b""
+    for x0, y0, dx, dy in (((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)) if interlace else ((0, 0, 1, 1),)):
+        sub = arr[y0::dy, x0::dx]
+        if sub.size == 0:
+            continue
+        for row in sub:
+            if row.ndim == 1 and depth < 8:
+                bits = np.zeros(((len(row) * depth + 7) // 8) * 8, np.uint8)
+                for i, v in enumerate(row):
+                    for k in range(depth):
+                        bits[i * depth + k] = (int(v) >> (depth - 1 - k)) & 1
+                data = np.packbits(bits).tobytes()
+            else:
+                data = np.ascontiguousarray(row, np.uint8).tobytes()
+            raw += b"\x00" + data
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1 if interlace else 0))
+    if palette is not None:
+        out += chunk(b"PLTE", np.ascontiguousarray(palette, np.uint8).tobytes())
+    return out + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+
+
 def make_streams():
     """the streams of the golden file (encoded by libjpeg / libpng through PIL; the bytes are stored, so another libjpeg version does not change the test)"""
     from PIL import Image
@@ -48,8 +77,16 @@ def make_streams():
                 bio = io.BytesIO(); Image.fromarray(img).save(bio, "JPEG", **kw); jpegs.append(bio.getvalue())
             bio = io.BytesIO(); Image.fromarray(img[..., 1]).save(bio, "JPEG", quality=70, progressive=True); jpegs.append(bio.getvalue())
         if (h, w) in ((37, 53), (2, 3), (48, 64)):
-            for mode in ("RGB", "RGBA", "L", "LA"):
+            for mode in ("RGB", "RGBA", "L", "LA", "P"):
                 bio = io.BytesIO(); Image.fromarray(img).convert(mode).save(bio, "PNG"); pngs.append(bio.getvalue())
+            # Adam7 and the 1 / 2 / 4-bit layouts, rows unfiltered: with Up / Average / Paeth rows stb_image v2.08 reads the "prior row" of a sub-byte image from the
+            # wrong place (it unfilters in place at the right end of the row buffer and looks for the previous row at the left end) -- the reference's pixels are
+            # undefined there, and tests/test_sens_io.py holds this decoder to the PNG specification (PIL) for those files
+            pal = rng.integers(0, 256, (16, 3)).astype(np.uint8)
+            for il in (True, False):
+                pngs += [handmade_png(img[..., 0] >> 6, 0, 2, None, il), handmade_png(img[..., 1] >> 4, 3, 4, pal, il), handmade_png(img[..., 2] >> 7, 3, 1, pal[:2], il),
+                         handmade_png(img[..., 0] >> 4, 0, 4, None, il)]
+            pngs += [handmade_png(img, 2, 8), handmade_png(np.dstack([img, img[..., :1]]), 6, 8), handmade_png(img[..., 0], 0, 8), handmade_png(np.dstack([img[..., 0], img[..., 1]]), 4, 8)]
     depth = (1000.0 + 600.0 * np.sin(np.arange(120)[:, None] / 17.0) * np.cos(np.arange(160)[None, :] / 23.0)).astype(np.uint16)
     depth[rng.random(depth.shape) < 0.07] = 0
     return jpegs, pngs, depth
