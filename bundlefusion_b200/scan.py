@@ -37,8 +37,8 @@ def reconstruct(sens_path: str, ply_path: str | None = None, device="cuda:0", ma
     P.colorWidth, P.colorHeight = hd.colorWidth, hd.colorHeight          # the ingest resamples colour to the integration size, as CUDAImageManager::process does
     for k in range(16):
         P.depthIntrinsics[k] = hd.depthIntrinsic[k]; P.colorIntrinsics[k] = hd.colorIntrinsic[k]
-    P.maxNumFrames = max(int(P.submapSize) * 2, n + int(P.submapSize))
-    P.maxNumImages = max(4, (int(P.maxNumFrames) + int(P.submapSize) - 1) // int(P.submapSize) + 1)
+    P.maxNumFrames = max(32, n + int(P.submapSize))                                  # frame store / trajectories: the sequence plus one chunk of slack
+    P.maxNumImages = max(8, (int(P.maxNumFrames) + int(P.submapSize) - 1) // int(P.submapSize) + 1)      # one keyframe per chunk
     if hash_buckets is not None:
         P.hash.m_hashNumBuckets = hash_buckets
     if sdf_blocks is not None:
