@@ -70,6 +70,33 @@ def reconstruct(sens_path: str, ply_path: str | None = None, device="cuda:0", ma
     return out
 
 
+def ate(estimated, recorded) -> dict:
+    """Absolute trajectory error of camera-to-world poses [n, 4, 4] against the poses recorded with the sequence (the `.sens` frames carry them, e.g. ScanNet's): the
+    camera centres of the frames valid in both are aligned by the least-squares rigid transform (Horn / Kabsch, float64, no scale), then RMSE / mean / max of the residual
+    distances in metres.  Frames whose pose is not finite on either side (lost tracking: -inf) are left out."""
+    E, R = np.asarray(estimated, np.float64), np.asarray(recorded, np.float64)
+    n = min(len(E), len(R))
+    ok = np.array([np.isfinite(E[i]).all() and np.isfinite(R[i]).all() for i in range(n)], bool)
+    if ok.sum() < 3:
+        return {"frames": int(ok.sum()), "rmse": float("nan"), "mean": float("nan"), "max": float("nan")}
+    a, b = E[:n][ok][:, :3, 3], R[:n][ok][:, :3, 3]
+    ca, cb = a.mean(0), b.mean(0)
+    U, _, Vt = np.linalg.svd((a - ca).T @ (b - cb))
+    D = np.diag([1.0, 1.0, np.sign(np.linalg.det(Vt.T @ U.T))])
+    Rot = Vt.T @ D @ U.T
+    d = np.linalg.norm((Rot @ (a - ca).T).T + cb - b, axis=1)
+    return {"frames": int(ok.sum()), "rmse": float(np.sqrt((d * d).mean())), "mean": float(d.mean()), "max": float(d.max())}
+
+
+def recorded_poses(sens_path: str, max_frames: int | None = None) -> np.ndarray:
+    """the camera-to-world poses stored with the frames ([n, 4, 4]; all -inf where the recorder had none)"""
+    r = SensorDataReader(sens_path)
+    n = len(r) if max_frames is None else min(len(r), max_frames)
+    out = np.stack([r.frame_pose(i) for i in range(n)]) if n else np.zeros((0, 4, 4), np.float32)
+    r.close()
+    return out
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("sens"); ap.add_argument("ply")
@@ -80,7 +107,11 @@ def main(argv=None) -> int:
     o = reconstruct(a.sens, a.ply, a.device, a.frames, a.hash_buckets, a.sdf_blocks)
     if a.trajectory:
         np.savetxt(a.trajectory, o["trajectory"].reshape(-1, 16))
-    print(json.dumps({k: o[k] for k in ("frames", "valid", "keyframes", "triangles", "mesh_path")}))
+    summary = {k: o[k] for k in ("frames", "valid", "keyframes", "triangles", "mesh_path")}
+    gt = recorded_poses(a.sens, a.frames)
+    if np.isfinite(gt).all(axis=(1, 2)).sum() >= 3:
+        summary["ate"] = ate(o["trajectory"], gt[:len(o["trajectory"])])
+    print(json.dumps(summary))
     return 0
 
 

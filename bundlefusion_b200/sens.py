@@ -88,6 +88,12 @@ class SensorDataReader:
         _check(self.L, self.L.bfSensReadFrame(self._h, i, dp, cp, pose.ctypes.data, ts.ctypes.data), f"bfSensReadFrame({i})")
         return depth, color, pose, ts
 
+    def frame_pose(self, i: int) -> np.ndarray:
+        """the recorded camera-to-world pose of frame i (no pixel decoding)"""
+        pose = np.zeros((4, 4), np.float32)
+        _check(self.L, self.L.bfSensReadFrame(self._h, i, None, None, pose.ctypes.data, None), f"bfSensReadFrame({i})")
+        return pose
+
     def frame_raw(self, i: int):
         hd = self.header
         depth = np.zeros((hd.depthHeight, hd.depthWidth), np.uint16); color = np.zeros((hd.colorHeight, hd.colorWidth, 3), np.uint8)

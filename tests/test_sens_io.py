@@ -197,3 +197,27 @@ def test_open_rejects_other_versions(tmp_path):
         sens.SensorDataReader(p)
     with pytest.raises(RuntimeError):
         sens.SensorDataReader(str(tmp_path / "missing.sens"))
+
+
+def test_ate_of_a_trajectory_against_the_recorded_poses(tmp_path):
+    """scan.ate: rigid alignment then residuals; scan.recorded_poses: the poses of a file without decoding its images"""
+    from bundlefusion_b200 import scan
+    fs = frames(6)
+    K = np.eye(4, dtype=np.float32)
+    path = str(tmp_path / "p.sens")
+    w = sens.SensorDataWriter(path, W, H, K)
+    for i, (d, c, T) in enumerate(fs):
+        w.append(d, c, T if i != 2 else np.full((4, 4), -np.inf, np.float32))
+    w.finish()
+    gt = scan.recorded_poses(path)
+    assert gt.shape == (6, 4, 4) and np.isneginf(gt[2]).all() and np.array_equal(gt[0], fs[0][2])
+    # an estimate in another world frame (the loop starts at the identity), with 5 mm of noise on two frames
+    rng = np.random.default_rng(0)
+    G = np.eye(4); G[:3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]; G[:3, :3] *= np.sign(np.linalg.det(G[:3, :3])); G[:3, 3] = (0.3, -1.0, 2.0)
+    est = np.stack([(G @ T.astype(np.float64)) for _, _, T in fs])
+    e = scan.ate(est, gt)
+    assert e["frames"] == 5 and e["rmse"] < 1e-6
+    est[1, :3, 3] += (0.005, 0, 0); est[4, :3, 3] -= (0, 0.005, 0)
+    e = scan.ate(est, gt)
+    assert 0.001 < e["rmse"] < 0.005 and e["max"] < 0.0051 and e["mean"] <= e["rmse"]
+    assert np.isnan(scan.ate(est[:2], gt[:2])["rmse"])                    # fewer than three common frames: nothing to align
