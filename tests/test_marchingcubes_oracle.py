@@ -99,19 +99,21 @@ def test_emulated_kernel_matches_oracle_bit_for_bit(emu):
     want, found = orc.marchingcubes_extract(sc, p)
     got = run_emulated(emu, sc, p)
     assert len(got) == len(want) == found > 10000 and np.array_equal(canon(got), canon(want))
-    # a block's triangles are contiguous: every run of triangles inside one block's bounding box is one piece (spot check: the first block's)
+    sc, cam, frames = golden_scene(small=True)                                      # the variants on a smaller model
+    want, found = orc.marchingcubes_extract(sc, golden_params(sc.hp))
+    assert found > 1000
     box = scene_box(sc)
     pb = golden_params(sc.hp, box)
     assert np.array_equal(canon(run_emulated(emu, sc, pb)), canon(orc.marchingcubes_extract(sc, pb)[0]))
     # a full buffer: the count is the capacity, every triangle written is one of the full soup's
-    pc = golden_params(sc.hp, cap=1000)
+    pc = golden_params(sc.hp, cap=500)
     capped = run_emulated(emu, sc, pc)
     full = {r.tobytes() for r in canon(want)}
-    assert len(capped) == 1000 and all(r.tobytes() in full for r in canon(capped))
+    assert len(capped) == 500 and all(r.tobytes() in full for r in canon(capped))
 
 
 def test_emulated_reference_named_stubs_and_host_class(emu, tmp_path):
-    sc, cam, frames = golden_scene()
+    sc, cam, frames = golden_scene(small=True)
     p = golden_params(sc.hp, scene_box(sc))
     want, _ = orc.marchingcubes_extract(sc, p)
     # the reference's call sequence: constants, reset, extract with the parameters in "device" memory (MarchingCubesData::updateParams)

@@ -18,7 +18,8 @@ SW, SH = 80, 60              # frames the scene is fused from
 BUCKETS = 499                # a small table: the reference's kernel runs one 512-thread CTA per hash slot (the emulation runs them one after the other)
 
 
-def golden_scene():
+def golden_scene(small=False):
+    """small: a sixth of the blocks (the emulated product kernel spends most of its time in 512-thread barriers per block)"""
     cam = camera_params(SW, SH)
     hp = default_hash_params(num_buckets=BUCKETS, num_sdf_blocks=1500)
     sc = orc.OracleSceneRepHashSDF(hp)
@@ -26,6 +27,8 @@ def golden_scene():
     for i in range(2):
         d, c, T = synth.make_frame(40 + 2 * i, SW, SH)
         keep = np.zeros_like(d, bool); keep[20:40, 25:55] = True                # the middle of the frame: a few hundred blocks
+        if small:
+            keep[:, :] = False; keep[26:34, 34:46] = True
         frames.append((np.where(keep, d, -np.inf).astype(np.float32), c, T))
     for d, c, T in frames:
         sc.integrate(T, d, c, cam)
