@@ -96,6 +96,7 @@ def main():
     build_siftmgr()
     build_sift_emulated()
     build_mgr_emulated()
+    build_fuse_emulated()
     build_trajectory_host()
     build_raycast_emulated()
     build_sens_host()
@@ -284,6 +285,39 @@ def build_mgr_emulated():
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-8000:])
         raise RuntimeError("building libref_mgr_emulated.so failed")
+
+
+def build_fuse_emulated():
+    """The reference's chunk -> keyframe fusion, host code of its manager class (FL/SiftGPU/SIFTImageManager.cpp: fuseToGlobal / computeTracks / findTrack), compiled with the
+    class and its kernels (SIFTImageManager.cu) by g++ against the CUDA emulation -> libref_fuse_emulated.so (wrapper: oracle/ref_fuse_wrap.cpp).  Pins row N2's oracle
+    (oracle/fuse_oracle.c) without a GPU.  The two application-state headers the .cpp includes (and uses only in comments) are empty files in the scratch tree."""
+    root = os.path.join(TMP, "fuseemu")
+    src = os.path.join(root, "Source")
+    S = os.path.join(REF, "Source")
+    sg = os.path.join(src, "SiftGPU")
+    os.makedirs(sg)
+    for f in os.listdir(os.path.join(S, "SiftGPU")):
+        if f.endswith(".h") or f in ("SIFTImageManager.cu", "SIFTImageManager.cpp"):
+            shutil.copy(os.path.join(S, "SiftGPU", f), sg)
+    for f in ("GlobalDefines.h", "CUDACacheUtil.h", "mLibCuda.h"):
+        shutil.copy(os.path.join(S, f), src)
+    shutil.copy(os.path.join(S, "mLibCuda.h"), os.path.join(src, "mlibCuda.h"))
+    for f in ("GlobalBundlingState.h", "GlobalAppState.h"):
+        open(os.path.join(src, f), "w").write("#pragma once\n")
+    patch(os.path.join(sg, "cuda_SimpleMatrixUtil.h"),
+          [(r"\ninline __device__ __host__ matNxM<4, 1>::operator float4\(\)", "\ntemplate<> inline __device__ __host__ matNxM<4, 1>::operator float4()", 1)])
+    launch = (r"([A-Za-z_]\w*(?:<[^<>()]*>)?)\s*<<\s*<\s*([^;]*?)\s*>>\s*>\s*\(", r"EMU_KERNEL(\1, \2)(", None)
+    patch(os.path.join(sg, "SIFTImageManager.cu"), [launch])
+    # the last member function of the file (fuseLocalKeyDepths, a debugging aid over mLib's DepthImage32) is cut; nothing on the path calls it
+    patch(os.path.join(sg, "SIFTImageManager.cpp"), [(r"void SIFTImageManager::fuseLocalKeyDepths\(.*\Z", "", 1)])
+    emu_dir = os.path.join(HERE, "ref_emu")
+    cmd = ["g++", "-std=c++17", "-O2", "-w", "-fpermissive", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-D__CUDACC__", "-D__NVCC__",
+           "-I", emu_dir, "-I", os.path.join(os.path.dirname(HERE), "tests", "cuda_emu"), "-I", src, "-I", sg, "-I", os.path.join(REF, "Include", "cutil", "inc"),
+           os.path.join(HERE, "ref_fuse_wrap.cpp"), "-o", os.path.join(OUT, "libref_fuse_emulated.so"), "-lm"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-8000:])
+        raise RuntimeError("building libref_fuse_emulated.so failed")
 
 
 def build_raycast_emulated():

@@ -5,9 +5,10 @@
  * (host code in the reference: it copies keys, descriptors, correspondences and poses to the CPU, recurses there and uploads the result).
  *
  * TEST INFRASTRUCTURE ONLY: the oracle the CUDA path (bundlefusion_b200/csrc/sift_fuse.cu) is checked against; only tests/,
- * __graft_entry__.smoke() and bench.py's cpu_baseline leg may use it.  Parity pin: the reference has no test or golden vector for this
- * function; the restatement follows the source line by line (recursion order included, it decides which key represents a track and
- * which of a key's correspondences supplies its position).
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg may use it.  PARITY STATUS: pinned against the reference's OWN code -- fuseToGlobal / computeTracks /
+ * findTrack are host code of its manager class; oracle/build_ref.py (build_fuse_emulated) compiles SIFTImageManager.cpp + .cu against the CUDA emulation, and on the solved
+ * chunks of tests/test_fuse_reference_emulated.py (golden: tests/golden/fuse_reference_emulated.npz; live where oracle/_ref is built) the fused keyframe's keys and
+ * descriptors agree bit for bit: which key represents a track, which correspondences contribute to its position, the order of the fused keys.
  *
  * Arithmetic: IEEE binary32, individually rounded operations (the reference code here is MSVC host code), float4x4 * float3 evaluated as
  * ((m0 x + m1 y) + m2 z) + m3 (cuda_SimpleMatrixUtil.h:937-944).  Compile with -ffp-contract=off.
