@@ -35,3 +35,16 @@ extern "C" int ref_fuse_to_global(unsigned numImages, const unsigned* numKeys, u
     memcpy(outDescs, global.getImageGPU(0).d_keyPointDescs, sizeof(SIFTKeyPointDesc) * n);
     return (int)n;
 }
+
+// SIFTImageManager::filterFrames (SIFTImageManager.cpp:551-575): numFiltered [numFrames] (the current frame's filtered match counts per earlier frame), validImages
+// [>= max(numFrames, curFrame + 1)] in / out; returns the last matched frame or (unsigned)-1
+extern "C" unsigned ref_filter_frames(unsigned curFrame, unsigned startFrame, unsigned numFrames, const int* numFiltered, int* validImages, unsigned numValid) {
+    SIFTImageManager m(numValid + 2, 16);
+    std::vector<int> v(validImages, validImages + numValid);
+    v.resize(numValid + 2, 0);
+    m.setValidImagesDEBUG(v);
+    memcpy(m.d_currNumFilteredMatchesPerImagePair, numFiltered, sizeof(int) * numFrames);
+    const unsigned last = m.filterFrames(curFrame, startFrame, numFrames);
+    for (unsigned i = 0; i < numValid; ++i) validImages[i] = m.m_validImages[i];
+    return last;
+}

@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bundlefusion_b200 import synth                                                            # noqa: E402
-from tests.test_fuse_reference_emulated import CASES, GOLDEN, reference_fuse                   # noqa: E402
+from tests.test_fuse_reference_emulated import CASES, GOLDEN, reference_filter_frames, reference_fuse                   # noqa: E402
 
 
 def main():
@@ -21,6 +21,7 @@ def main():
         k, d = reference_fuse(synth.make_fuse_problem(**kw))
         out[f"keys_{c}"], out[f"descs_{c}"] = k, d
         print(kw, "->", len(k), "fused keys")
+    out["ff_last"], out["ff_valid"] = reference_filter_frames()
     np.savez_compressed(GOLDEN, **out)
     print("wrote", GOLDEN, os.path.getsize(GOLDEN), "bytes")
 

@@ -54,3 +54,38 @@ def test_live_against_the_references_manager_class():
         pb = synth.make_fuse_problem(seed=seed, n_images=int(4 + seed % 7), n_points=80 + 5 * (seed % 5), invalid_frac=0.1)
         (k, d), (rk, rd) = oracle_fuse(pb), reference_fuse(pb)
         assert len(k) == len(rk) > 5 and np.array_equal(k.view(np.uint32), rk.view(np.uint32)) and np.array_equal(d, rd)
+
+
+def filter_frames_cases():
+    rng = np.random.default_rng(4)
+    out = []
+    for _ in range(40):
+        n = int(rng.integers(1, 12)); cur = int(rng.integers(0, n + 1)); start = int(rng.integers(0, n))
+        nf = (rng.integers(0, 4, n) * rng.integers(0, 2, n)).astype(np.int32); valid = rng.integers(0, 2, n + 2).astype(np.int32)
+        out.append((cur, start, n, nf, valid))
+    return out
+
+
+def test_filter_frames_oracle_equals_the_references_member_function():
+    """SIFTImageManager::filterFrames (FL/SiftGPU/SIFTImageManager.cpp:551-575), host code of the same class: last matched frame and the validity it writes"""
+    g = np.load(GOLDEN)
+    for k, (cur, start, n, nf, valid) in enumerate(filter_frames_cases()):
+        last, v = orc.sift_filter_frames(cur, start, n, nf, valid.copy())
+        assert (last & 0xFFFFFFFF) == int(g["ff_last"][k]) and np.array_equal(v, g["ff_valid"][k][:len(v)]), k
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libref_fuse_emulated.so not built (needs /root/reference: python oracle/build_ref.py)")
+def test_filter_frames_live():
+    last, valid = reference_filter_frames()
+    g = np.load(GOLDEN)
+    assert np.array_equal(last, g["ff_last"]) and np.array_equal(valid, g["ff_valid"])
+
+
+def reference_filter_frames():
+    R = C.CDLL(REF_SO)
+    R.ref_filter_frames.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint]; R.ref_filter_frames.restype = C.c_uint
+    lasts, valids = [], []
+    for cur, start, n, nf, valid in filter_frames_cases():
+        v = np.zeros(16, np.int32); v[:len(valid)] = valid
+        lasts.append(R.ref_filter_frames(cur, start, n, nf.ctypes.data, v.ctypes.data, len(valid))); valids.append(v)
+    return np.array(lasts, np.uint32), np.stack(valids)
