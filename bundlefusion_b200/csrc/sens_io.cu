@@ -64,6 +64,7 @@ int decode_png(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t* 
         at += 12 + (size_t)len;
     }
     if (w == 0 || h == 0) return BF_SENS_ERR_FORMAT;
+    if (w > (1u << 24) || h > (1u << 24) || (1u << 30) / w / 4 < h) return BF_SENS_ERR_FORMAT;          // "too large" in the reference's decoder: a corrupt header must not drive an allocation
     // what the reference's decoder (stb_image v2.08) reads: 8 bits per channel for every colour type, 1 / 2 / 4 bits for grey and palette images, Adam7 interlacing; not 16 bits
     const bool small = depth == 1 || depth == 2 || depth == 4;
     if (!(type == 0 || type == 2 || type == 3 || type == 4 || type == 6) || interlace > 1) return BF_SENS_ERR_UNSUPPORTED;
@@ -313,6 +314,7 @@ int decode_jpeg(const uint8_t* d, size_t n, uint8_t* rgb, uint32_t* W, uint32_t*
             height = (s[1] << 8) | s[2]; width = (s[3] << 8) | s[4];
             const int nf = s[5];
             if (width == 0 || height == 0 || !(nf == 1 || nf == 3) || sl < (size_t)(6 + 3 * nf)) return BF_SENS_ERR_UNSUPPORTED;
+            if ((1 << 30) / width / nf < height) return BF_SENS_ERR_FORMAT;                 // "too large" in the reference's decoder
             comps.resize(nf);
             for (int c = 0; c < nf; ++c) {
                 comps[c].id = s[6 + 3 * c]; comps[c].h = s[7 + 3 * c] >> 4; comps[c].v = s[7 + 3 * c] & 15; comps[c].tq = s[8 + 3 * c];

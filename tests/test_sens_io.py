@@ -221,3 +221,32 @@ def test_ate_of_a_trajectory_against_the_recorded_poses(tmp_path):
     e = scan.ate(est, gt)
     assert 0.001 < e["rmse"] < 0.005 and e["max"] < 0.0051 and e["mean"] <= e["rmse"]
     assert np.isnan(scan.ate(est[:2], gt[:2])["rmse"])                    # fewer than three common frames: nothing to align
+
+
+def test_decoders_reject_or_decode_mutated_streams_without_crashing():
+    """recordings come from outside: a corrupt payload must give an error code (or some picture), not a fault or an absurd allocation"""
+    from tests.test_sens_reference_stb import make_streams
+    jpegs, pngs, _ = make_streams()
+    rng = np.random.default_rng(0)
+    rejected = 0
+    for it in range(1200):
+        pool = jpegs if it % 2 else pngs
+        b = bytearray(pool[int(rng.integers(0, len(pool)))])
+        mode = it % 4
+        if mode == 0:
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        elif mode == 1:
+            b = b[: int(rng.integers(1, len(b)))]
+        elif mode == 2:
+            i = int(rng.integers(0, len(b))); b[i:i] = bytes(rng.integers(0, 256, int(rng.integers(1, 40))).astype(np.uint8))
+        else:
+            i = int(rng.integers(2, len(b))); del b[i:i + int(rng.integers(1, 30))]
+        try:
+            (sens.decode_jpeg if it % 2 else sens.decode_png)(bytes(b))
+        except (RuntimeError, MemoryError):
+            rejected += 1
+    assert rejected > 300
+    huge = bytearray(pngs[0]); huge[16:24] = (0x7FFFFFFF).to_bytes(4, "big") * 2          # IHDR claims 2^31 x 2^31 pixels
+    with pytest.raises(RuntimeError):
+        sens.decode_png(bytes(huge))
