@@ -489,11 +489,11 @@ BF_API const char* bfSensErrorString(int code) {
 }
 BF_API int bfSensDecodeJpeg(const uint8_t* data, size_t bytes, uint8_t* rgb, uint32_t* width, uint32_t* height) {
     if (!data || !width || !height) return BF_SENS_ERR_ARGUMENT;
-    return decode_jpeg(data, bytes, rgb, width, height);
+    try { return decode_jpeg(data, bytes, rgb, width, height); } catch (const std::exception&) { return BF_SENS_ERR_FORMAT; }
 }
 BF_API int bfSensDecodePng(const uint8_t* data, size_t bytes, uint8_t* rgb, uint32_t* width, uint32_t* height) {
     if (!data || !width || !height) return BF_SENS_ERR_ARGUMENT;
-    return decode_png(data, bytes, rgb, width, height);
+    try { return decode_png(data, bytes, rgb, width, height); } catch (const std::exception&) { return BF_SENS_ERR_FORMAT; }
 }
 
 BF_API int bfSensOpen(const char* path, BFSensReader** out, BFSensHeader* header) {
@@ -503,6 +503,9 @@ BF_API int bfSensOpen(const char* path, BFSensReader** out, BFSensHeader* header
     BFSensReader* r = new BFSensReader(); r->f = f;
     BFSensHeader& h = r->h; memset(&h, 0, sizeof(h));
     int rc = BF_SENS_ERR_FORMAT;
+    uint64_t fileSize = 0;
+    if (fseeko(f, 0, SEEK_END) == 0) { fileSize = (uint64_t)ftello(f); fseeko(f, 0, SEEK_SET); }
+    try {
     do {
         uint64_t strLen = 0;
         if (!rd(f, &h.version) || h.version != 4 || !rd(f, &strLen) || strLen > (1u << 20)) break;                 // sensorData.h:1194-1199
@@ -512,18 +515,21 @@ BF_API int bfSensOpen(const char* path, BFSensReader** out, BFSensHeader* header
         if (!rd(f, h.colorIntrinsic, 16) || !rd(f, h.colorExtrinsic, 16) || !rd(f, h.depthIntrinsic, 16) || !rd(f, h.depthExtrinsic, 16)) break;
         if (!rd(f, &h.colorCompression) || !rd(f, &h.depthCompression) || !rd(f, &h.colorWidth) || !rd(f, &h.colorHeight) || !rd(f, &h.depthWidth) || !rd(f, &h.depthHeight) ||
             !rd(f, &h.depthShift) || !rd(f, &h.numFrames)) break;
-        if (h.numFrames > (1ull << 32)) break;
+        if (h.colorWidth > (1u << 15) || h.colorHeight > (1u << 15) || h.depthWidth > (1u << 15) || h.depthHeight > (1u << 15)) break;      // image sizes no sensor has
+        if (h.numFrames > fileSize / 96) break;                                                                   // a frame record is at least 96 bytes: a corrupt count must not drive an allocation
         r->frames.resize((size_t)h.numFrames);
         bool ok = true;
         for (FrameRec& fr : r->frames) {                                                                          // RGBDFrame::loadFromFile, :686-700
             if (!rd(f, fr.pose, 16) || !rd(f, &fr.tsColor) || !rd(f, &fr.tsDepth) || !rd(f, &fr.colorBytes) || !rd(f, &fr.depthBytes)) { ok = false; break; }
             fr.at = (uint64_t)ftello(f);
+            if (fr.colorBytes > fileSize || fr.depthBytes > fileSize || fr.at + fr.colorBytes + fr.depthBytes > fileSize) { ok = false; break; }      // payloads lie inside the file
             if (fseeko(f, (off_t)(fr.colorBytes + fr.depthBytes), SEEK_CUR) != 0) { ok = false; break; }
         }
         if (!ok) break;
         if (!rd(f, &h.numIMUFrames)) h.numIMUFrames = 0;                                                          // older writers stop after the frames
         rc = BF_SENS_OK;
     } while (0);
+    } catch (const std::exception&) { rc = BF_SENS_ERR_FORMAT; }                                                     // e.g. bad_alloc on a size a corrupt file claims
     if (rc) { fclose(f); delete r; return rc; }
     if (header) *header = h;
     *out = r;
@@ -563,15 +569,22 @@ static int read_payload(BFSensReader* r, uint64_t index, uint16_t* depth, uint8_
     }
     return BF_SENS_OK;
 }
-BF_API int bfSensReadFrameRaw(BFSensReader* r, uint64_t index, uint16_t* depth, uint8_t* colorRGB) { return r ? read_payload(r, index, depth, colorRGB) : BF_SENS_ERR_ARGUMENT; }
+BF_API int bfSensReadFrameRaw(BFSensReader* r, uint64_t index, uint16_t* depth, uint8_t* colorRGB) {
+    if (!r) return BF_SENS_ERR_ARGUMENT;
+    try { return read_payload(r, index, depth, colorRGB); } catch (const std::exception&) { return BF_SENS_ERR_FORMAT; }
+}
 
 BF_API int bfSensReadFrame(BFSensReader* r, uint64_t index, float* depthMetres, uint8_t* colorRGBX, float* cameraToWorld, uint64_t* timeStamps) {
     if (!r) return BF_SENS_ERR_ARGUMENT;
     if (index >= r->frames.size()) return BF_SENS_ERR_RANGE;
     const BFSensHeader& h = r->h;
     const size_t nd = (size_t)h.depthWidth * h.depthHeight, nc = (size_t)h.colorWidth * h.colorHeight;
-    std::vector<uint16_t> d(depthMetres ? nd : 0); std::vector<uint8_t> c(colorRGBX ? nc * 3 : 0);
-    const int rc = read_payload(r, index, depthMetres ? d.data() : nullptr, colorRGBX ? c.data() : nullptr);
+    std::vector<uint16_t> d; std::vector<uint8_t> c;
+    int rc;
+    try {
+        d.resize(depthMetres ? nd : 0); c.resize(colorRGBX ? nc * 3 : 0);
+        rc = read_payload(r, index, depthMetres ? d.data() : nullptr, colorRGBX ? c.data() : nullptr);
+    } catch (const std::exception&) { rc = BF_SENS_ERR_FORMAT; }
     if (rc) return rc;
     if (depthMetres)                                                       // SensorDataReader::processDepth, FL/SensorDataReader.cpp:104-107
         for (size_t i = 0; i < nd; ++i) depthMetres[i] = d[i] == 0 ? -INFINITY : (float)d[i] / h.depthShift;

@@ -115,3 +115,39 @@ def test_live_against_the_references_sensor_data_class(tmp_path):
         du, cu = r.frame_raw(i)
         assert np.array_equal(cu, rrgb[i]) and np.array_equal(du, rdepth[i]) and np.array_equal(du, depth[i])
     r.close()
+
+
+def test_reader_survives_corrupt_files(tmp_path):
+    """sizes a corrupt file claims (frame count, payload bytes, image dimensions) must end in an error code, not an allocation failure that takes the process down"""
+    g = np.load(GOLDEN)
+    rng = np.random.default_rng(1)
+    p = str(tmp_path / "f.sens")
+    rejected = 0
+    for it in range(600):
+        b = bytearray(g[f"file_depth{it % 2}"].tobytes())
+        mode = it % 4
+        if mode == 0:
+            for _ in range(int(rng.integers(1, 5))):
+                b[int(rng.integers(0, 600))] = int(rng.integers(0, 256))                    # header and first frame record
+        elif mode == 1:
+            b = b[: int(rng.integers(1, len(b)))]
+        elif mode == 2:
+            for _ in range(int(rng.integers(1, 5))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        else:
+            i = int(rng.integers(2, len(b))); del b[i:i + int(rng.integers(1, 30))]
+        open(p, "wb").write(bytes(b))
+        try:
+            r = sens.SensorDataReader(p)
+            for i in range(min(len(r), 4)):
+                r.frame(i); r.frame_raw(i)
+            r.close()
+        except (RuntimeError, MemoryError, ValueError):
+            rejected += 1
+    assert rejected > 100
+    b = bytearray(g["file_depth0"].tobytes())
+    at = 4 + 8 + len(NAME) + 4 * 64 + 8 + 16 + 4                                            # numFrames: a count the file cannot hold
+    b[at:at + 8] = (1 << 40).to_bytes(8, "little")
+    open(p, "wb").write(bytes(b))
+    with pytest.raises(RuntimeError):
+        sens.SensorDataReader(p)
